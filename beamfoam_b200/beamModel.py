@@ -1,0 +1,370 @@
+"""Host-side mirror of the reference's ``beamModel`` /
+``coupledTotalLagNewtonRaphsonBeam`` interface for the Newton-iteration path.
+
+The class keeps the reference's names and call order
+(``beamModel::New`` → ``evolve()`` per time step → ``solutionW()`` ...;
+applications/solvers/beamFoam/beamFoam.C:57-94) but owns no numerics: every
+per-cell / per-face operation happens behind the C ABI of include/beamgpu.h in
+``libbeamgpu.so`` (CUDA, sm_100a).  The host part is what stays on the host in the
+reference as well: dictionary-level set-up (constant/beamProperties, 0/W, 0/Theta,
+system/fvSchemes), the BC time series, and the time loop.
+
+OpenFOAM itself is not available in this environment, so the case description is
+a plain-Python ``BeamCase`` instead of dictionaries on disk; INTEGRATION.md shows
+the OpenFOAM-side subclass that feeds the same C ABI from real dictionaries.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import BeamGpuError
+from .fvPatchFields import _PatchField, fixedValue
+
+
+def axisAngleRotation(axis: Sequence[float], angleDeg: float) -> np.ndarray:
+    """``coordinateRotations::axisAngle::rotation(axis, angle, degrees=true)`` as used by
+    setInitialPositionBeam (applications/utilities/setInitialPositionBeam/setInitialPositionBeam.C:197-212):
+    Rodrigues rotation about the normalised axis."""
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    th = math.radians(angleDeg)
+    S = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + math.sin(th) * S + (1 - math.cos(th)) * (S @ S)
+
+
+@dataclass
+class BeamCase:
+    """Everything the reference reads from a case directory for this path.
+
+    Per-beam quantities are arrays of length nBeams (a scalar is broadcast), so a
+    65,536-beam bundle costs a handful of numpy arrays, not 65,536 objects.
+    """
+    # constant/beamProperties: beams ( beam_k { crossSectionModel ...; length; nSegments; E; G; rho } )
+    nSegments: Union[int, Sequence[int]]
+    length: Union[float, Sequence[float]]
+    A: Union[float, Sequence[float]]      # crossSection.A()
+    Iyy: Union[float, Sequence[float]]    # beamModel::Iyy = crossSection.Ixx()  (beamModel.H:449-461)
+    Izz: Union[float, Sequence[float]]    # beamModel::Izz = crossSection.Iyy()  (beamModel.H:463-475)
+    J: Union[float, Sequence[float]]      # crossSection.IT()
+    E: Union[float, Sequence[float]]
+    G: Union[float, Sequence[float]]
+    rho: Union[float, Sequence[float]] = 0.0
+    nBeams: int = 1
+    # boundary conditions: one patch-field object per end (applies to every beam) or a list per beam
+    W_left: Union[_PatchField, Sequence[_PatchField]] = field(default_factory=lambda: fixedValue(variable="W"))
+    W_right: Union[_PatchField, Sequence[_PatchField]] = field(default_factory=lambda: fixedValue(variable="W"))
+    Theta_left: Union[_PatchField, Sequence[_PatchField]] = field(default_factory=lambda: fixedValue(variable="Theta"))
+    Theta_right: Union[_PatchField, Sequence[_PatchField]] = field(default_factory=lambda: fixedValue(variable="Theta"))
+    # system/fvSchemes d2dt2Schemes
+    d2dt2Scheme: str = "steadyState"
+    newmarkBeta: float = 0.25
+    newmarkGamma: float = 0.5
+    # <model>Coeffs
+    nCorrectors: int = 1000
+    residualTol: float = -1.0
+    convergenceTol: Optional[float] = None
+    solutionTol: float = 1e-10
+    absoluteTol: float = 1e-30
+    divergenceTol: float = 1e6
+    scalingInertiaTensor: float = 1.0
+    # constant/g, 0/q, 0/m
+    g: Sequence[float] = (0.0, 0.0, 0.0)
+    q: Optional[Sequence[float]] = None   # uniform (3,) or per-cell (nCells,3)
+    m: Optional[Sequence[float]] = None
+    # setInitialPositionBeam -rotateAngle '(axis angle)': 3x3 T (all beams) or (nBeams,3,3); None = I
+    initialRotation: Optional[np.ndarray] = None
+    # system/controlDict
+    deltaT: float = 1.0
+    endTime: float = 1.0
+    name: str = "case"
+
+    def per_beam(self, x, dtype=np.float64) -> np.ndarray:
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dtype), (self.nBeams,)))
+
+    def rtol(self) -> float:
+        # Evolve.C:67-79: residualTol, else convergenceTol, else 1e-8
+        if self.residualTol >= 0:
+            return self.residualTol
+        return self.convergenceTol if self.convergenceTol is not None else 1e-8
+
+
+def shard_range(nBeams: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous beam range of ``rank``: beam b lives on rank floor(b*world/nBeams)
+    (SURVEY §8e)."""
+    lo = -(-rank * nBeams // world)
+    hi = -(-(rank + 1) * nBeams // world)
+    return lo, min(hi, nBeams)
+
+
+class coupledTotalLagNewtonRaphsonBeam:
+    """Drop-in host object for the reference class of the same name.
+
+    ``library`` selects the implementation of include/beamgpu.h; the default is the
+    CUDA product library and nothing else is ever chosen automatically.
+    ``beamRange=(lo, hi)`` makes this object own only that shard of the bundle;
+    ``reducer(np.ndarray[3]) -> None`` then sums the three squared norms over all
+    shards in place (NCCL all-reduce in bench.py, gloo in the CPU tests).
+    """
+
+    typeName = "coupledTotalLagNewtonRaphsonBeam"
+
+    def __init__(self, case: BeamCase, library: Optional[C.CDLL] = None, device: int = 0,
+                 beamRange: Optional[tuple[int, int]] = None,
+                 reducer: Optional[Callable[[np.ndarray], None]] = None,
+                 storeIncrements: bool = True):
+        self.case = case
+        self.lib = library if library is not None else L.load_library()
+        lo, hi = beamRange if beamRange is not None else (0, case.nBeams)
+        if not (0 <= lo < hi <= case.nBeams):
+            raise ValueError(f"empty or invalid beam range {(lo, hi)} for {case.nBeams} beams")
+        self.beamRange = (lo, hi)
+        B = self._B = hi - lo
+        sl = slice(lo, hi)
+
+        scheme = {"steadyState": L.BF_SCHEME_STEADY, "Newmark": L.BF_SCHEME_NEWMARK,
+                  "Euler": L.BF_SCHEME_EULER}.get(case.d2dt2Scheme)
+        if scheme is None:  # CTL.C:708-720
+            raise ValueError("Please specify the d2dt2Schemes: steadyState, Euler, Newmark")
+
+        nSeg = case.per_beam(case.nSegments, np.int32)[sl].copy()
+        length = case.per_beam(case.length)[sl].copy()
+        A, Iyy, Izz, J = (case.per_beam(x)[sl] for x in (case.A, case.Iyy, case.Izz, case.J))
+        E, G, rho = (case.per_beam(x)[sl] for x in (case.E, case.G, case.rho))
+        if scheme != L.BF_SCHEME_STEADY and np.any(rho == 0.0):  # Evolve.C:323-335
+            raise ValueError(f"The time integration scheme provided is {case.d2dt2Scheme} "
+                             "but density 'rho' is not specified!!")
+        # CTL.C:538-585 (CQ_, CM_), :621-667 (ARho_, CIRho_), Evolve.C:201-209 (self-weight)
+        CQ = np.ascontiguousarray(np.stack([E * A, G * A, G * A], axis=1))
+        CM = np.ascontiguousarray(np.stack([G * J, E * Iyy, E * Izz], axis=1))
+        ARho = np.ascontiguousarray(A * rho)
+        kCI = case.scalingInertiaTensor
+        CIRho = np.ascontiguousarray(np.stack([kCI * (rho * J), kCI * (rho * Iyy), kCI * (rho * Izz)], axis=1))
+        g = np.asarray(case.g, dtype=np.float64).reshape(3)
+        weight = np.ascontiguousarray((rho * A)[:, None] * g[None, :])
+        refL = None
+        if case.initialRotation is not None:
+            T = np.asarray(case.initialRotation, dtype=np.float64)
+            T = np.broadcast_to(T, (case.nBeams, 3, 3))[sl] if T.ndim == 2 else T[sl]
+            refL = np.ascontiguousarray(T.reshape(B, 9))
+
+        self._bcs = {}
+        wType = np.zeros(2 * B, np.int32)
+        thType = np.zeros(2 * B, np.int32)
+        springK = np.zeros(2 * B)
+        springDir = np.zeros((2 * B, 3))
+        for end, (wspec, tspec) in enumerate(((case.W_left, case.Theta_left), (case.W_right, case.Theta_right))):
+            for var, spec, types in (("W", wspec, wType), ("Theta", tspec, thType)):
+                objs = spec if isinstance(spec, (list, tuple)) else None
+                if objs is not None:
+                    if len(objs) != case.nBeams:
+                        raise ValueError("per-beam patch-field list must have nBeams entries")
+                    objs = list(objs[lo:hi])
+                    types[end * B:(end + 1) * B] = [o.code for o in objs]
+                else:
+                    types[end * B:(end + 1) * B] = spec.code
+                self._bcs[(end, var)] = (spec, objs)
+                if var == "W":
+                    for b in range(B):
+                        o = objs[b] if objs is not None else spec
+                        if o.code == L.BF_W_SPRING:
+                            springK[end * B + b] = o.springStiffness
+                            springDir[end * B + b] = o.springDirection
+                    if objs is None and spec.code != L.BF_W_SPRING:
+                        pass
+
+        self._keep = (nSeg, length, CQ, CM, ARho, CIRho, weight, refL, wType, thType, springK, springDir)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None  # noqa: E731
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+        lay = L.bf_layout(B, ip(nSeg), dp(length), None)
+        props = L.bf_beam_props(dp(CQ), dp(CM), dp(ARho), dp(CIRho), dp(weight), dp(refL))
+        bc = L.bf_bc(ip(wType), ip(thType), dp(springK), dp(springDir))
+        opt = L.bf_options(scheme, case.newmarkBeta, case.newmarkGamma, device, int(storeIncrements))
+        ctx = C.c_void_p()
+        rc = self.lib.bf_create(C.byref(lay), C.byref(props), C.byref(bc), C.byref(opt), C.byref(ctx))
+        if rc != L.BF_OK:
+            raise BeamGpuError(rc, self.lib.bf_last_error(None).decode())
+        self._ctx = ctx
+        self.nSeg = nSeg
+        self.cellStart = np.concatenate([[0], np.cumsum(nSeg)]).astype(np.int64)
+        self.nCells = int(self.lib.bf_num_cells(ctx))
+        self.nInternalFaces = int(self.lib.bf_num_internal_faces(ctx))
+
+        # patch values read from 0/W, 0/Theta ("value uniform ...") for fixedValue patches
+        for var in ("W", "Theta"):
+            left = self._bc_values(0, var, 0.0, only_fixed=True)
+            right = self._bc_values(1, var, 0.0, only_fixed=True)
+            if np.any(left) or np.any(right):
+                self.set_field(var, None, left, right)
+        if case.q is not None or case.m is not None:
+            self._set_loads(case.q, case.m, lo, hi)
+
+        self.tol = L.bf_tolerances(case.nCorrectors, case.rtol(), case.solutionTol, case.absoluteTol,
+                                   case.divergenceTol)
+        self._reducer_cb = None
+        if reducer is not None:
+            def _cb(ptr, n, _user, _r=reducer):
+                try:
+                    arr = np.ctypeslib.as_array(ptr, shape=(n,))
+                    _r(arr)
+                    return 0
+                except Exception:  # never let an exception cross the C boundary
+                    return 1
+            self._reducer_cb = L.bf_reduce_fn(_cb)
+            self._check(self.lib.bf_set_reducer(ctx, self._reducer_cb, None))
+
+        self.time = 0.0
+        self.timeIndex = 0
+        self._iOuterCorr = 0
+        self.totalIter_ = 0
+        self.lastStep: Optional[L.bf_step_out] = None
+
+    # ------------------------------------------------------------------ utils
+    def _check(self, rc: int):
+        if rc != L.BF_OK:
+            raise BeamGpuError(rc, self.lib.bf_last_error(self._ctx).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.bf_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _bc_values(self, end: int, var: str, t: float, only_fixed: bool = False) -> np.ndarray:
+        spec, objs = self._bcs[(end, var)]
+        lo, hi = self.beamRange
+        B = self._B
+        fixed_code = L.BF_W_FIXED if var == "W" else L.BF_TH_FIXED
+        if objs is None:
+            if only_fixed and spec.code != fixed_code:
+                return np.zeros((B, 3))
+            v = spec.values(t, self.case.nBeams)[lo:hi]
+            return np.ascontiguousarray(v)
+        out = np.zeros((B, 3))
+        for b, o in enumerate(objs):
+            if only_fixed and o.code != fixed_code:
+                continue
+            out[b] = o.valueAt(t)
+        return out
+
+    def _set_loads(self, q, m, lo, hi):
+        def expand(x):
+            if x is None:
+                return None
+            x = np.asarray(x, dtype=np.float64)
+            if x.ndim == 1:
+                return np.ascontiguousarray(np.broadcast_to(x, (self.nCells, 3)))
+            allStart = np.concatenate([[0], np.cumsum(self.case.per_beam(self.case.nSegments, np.int64))])
+            return np.ascontiguousarray(x[allStart[lo]:allStart[hi]])
+        qa, ma = expand(q), expand(m)
+        self._check(self.lib.bf_set_distributed_loads(
+            self._ctx, qa.ctypes.data if qa is not None else None, ma.ctypes.data if ma is not None else None))
+
+    # ------------------------------------------------- field mirroring (host)
+    def _ncomp(self, name):
+        return L.FIELD_NCOMP.get(name, 3)
+
+    def get_field(self, name: str, internal: bool = True, boundary: bool = True):
+        """(internal, left, right) numpy arrays in the reference's ordering."""
+        nc = self._ncomp(name)
+        n_int = self.nInternalFaces if name in L.SURFACE_FIELDS else self.nCells
+        has_b = boundary and (name in L.SURFACE_FIELDS or name in L.VOL_FIELDS_WITH_BOUNDARY)
+        I = np.empty((n_int, nc)) if internal else None
+        Lf = np.empty((self._B, nc)) if has_b else None
+        R = np.empty((self._B, nc)) if has_b else None
+        self._check(self.lib.bf_get_field(
+            self._ctx, L.FIELDS[name], I.ctypes.data if I is not None else None,
+            Lf.ctypes.data if Lf is not None else None, R.ctypes.data if R is not None else None))
+        return I, Lf, R
+
+    def set_field(self, name: str, internal=None, left=None, right=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (internal, left, right)]
+        self._check(self.lib.bf_set_field(self._ctx, L.FIELDS[name],
+                                          *[a.ctypes.data if a is not None else None for a in arrs]))
+
+    # reference accessors (beamModel.H:637-712)
+    def solutionW(self):
+        return self.get_field("W")
+
+    def solutionDW(self):
+        return self.get_field("DW")
+
+    def solutionTheta(self):
+        return self.get_field("Theta")
+
+    def solutionLambda(self):
+        return self.get_field("Lambdaf")
+
+    def solutionRMC(self):
+        return self.get_field("Lambda")
+
+    def iOuterCorr(self) -> int:
+        return self._iOuterCorr
+
+    def tip(self, end: int = 1):
+        """Patch values (W_b, Theta_b) of every beam at one end — the parity observable."""
+        _, wl, wr = self.get_field("W", internal=False)
+        _, tl, tr = self.get_field("Theta", internal=False)
+        return (wr, tr) if end == 1 else (wl, tl)
+
+    # ------------------------------------------------------------- hot path
+    def updateCoeffs(self, t: float):
+        """W_/Theta_.boundaryFieldRef().updateCoeffs() (Evolve.C:156-157): evaluate every
+        BC series at time t and hand the values to the device."""
+        for end in (0, 1):
+            for var in ("W", "Theta"):
+                spec, objs = self._bcs[(end, var)]
+                vals = self._bc_values(end, var, t)
+                kinds = {spec.kind} if objs is None else {o.kind for o in objs}
+                for kind in kinds:
+                    v = vals
+                    if objs is not None and len(kinds) > 1:
+                        v = np.where(np.array([o.kind == kind for o in objs])[:, None], vals, 0.0)
+                    v = np.ascontiguousarray(v)
+                    self._check(self.lib.bf_set_bc_values(self._ctx, end, kind, v.ctypes.data))
+
+    def evolve(self) -> float:
+        """``scalar evolve()`` (Evolve.C:55-670).  Returns the initial residual norm; a
+        diverged / non-converged step raises (FatalError in the reference)."""
+        self.updateCoeffs(self.time)
+        self._check(self.lib.bf_begin_step(self._ctx, float(self.case.deltaT)))
+        out = L.bf_step_out()
+        rc = self.lib.bf_evolve(self._ctx, C.byref(self.tol), C.byref(out))
+        self.lastStep = out
+        self._iOuterCorr = out.nIter
+        self.totalIter_ += out.nIter
+        self._check(rc)
+        return out.initialResidualNorm
+
+    def newton_iteration(self) -> np.ndarray:
+        s = (C.c_double * 3)()
+        self._check(self.lib.bf_newton_iteration(self._ctx, s))
+        return np.array(s[:])
+
+    def loop(self) -> bool:
+        """``runTime.loop()``: advance time first, False past endTime."""
+        if self.time > self.case.endTime - 0.5 * self.case.deltaT:
+            return False
+        self.timeIndex += 1
+        self.time = self.timeIndex * self.case.deltaT
+        return True
+
+    def run(self, nSteps: Optional[int] = None, callback=None):
+        """beamFoam.C:73-89 time loop.  Returns per-step iteration counts."""
+        iters = []
+        while (nSteps is None or len(iters) < nSteps) and self.loop():
+            self.evolve()
+            iters.append(self._iOuterCorr)
+            if callback is not None:
+                callback(self)
+        return iters

@@ -1,0 +1,263 @@
+/* beamgpu.h — C-ABI boundary of the B200-native beamFoam Newton-iteration path.
+ *
+ * This header is the drop-in boundary between an OpenFOAM host (the beamModel
+ * subclass `coupledTotalLagNewtonRaphsonBeamGPU`) and the
+ * sm_100a CUDA implementation of ONE hot path of solids4foam/beamFoam:
+ * the per-Newton-iteration update of `coupledTotalLagNewtonRaphsonBeam`.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout,
+ * CTL = src/wireBunchingModels/beamModels/coupledTotalLagNewtonRaphsonBeam):
+ *   scalar evolve()                       CTL/coupledTotalLagNewtonRaphsonBeamEvolve.C:55-670
+ *   void   updateEqnCoefficients()        CTL/...Evolve.C:673-753
+ *   void   assembleMatrixCoefficients()   CTL/...Matrix.C:55-475
+ *   void   assembleBoundaryConditions()   CTL/...BoundaryConditions.C:64-1190
+ *   BlockEigenSolverOF::solve()           src/wireBunchingModels/numerics/BlockEigenSolvers/
+ *                                         BlockEigenSolverOF/BlockEigenSolverOF.C:200-412
+ *   void   updateSolutionVariables()      CTL/...Evolve.C:757-923
+ *   bool   checkConvergence()             CTL/...Evolve.C:926-1026
+ *   fvPatchField evaluate()/updateCoeffs  src/wireBunchingModels/beamModels/fvPatchFields/<name>
+ *
+ * The same header is implemented twice:
+ *   beamfoam_b200/libbeamgpu.so   — the product: hand-written FP64 CUDA, sm_100a
+ *   oracle/_build/libbeamoracle.so — TEST INFRASTRUCTURE ONLY: a literal CPU
+ *                                    restatement of the reference arithmetic
+ *
+ * Conventions
+ *   - POD only: plain pointers and sizes; no C++ / torch types cross the ABI.
+ *   - All floating point is IEEE FP64; indices are 32-bit (OpenFOAM `label`)
+ *     except global counts, which are int64_t.
+ *   - Every function returns an int status (BF_OK == 0).  Nothing aborts or
+ *     throws across the boundary; bf_last_error() gives the message.  The
+ *     reference's FatalError cases (divergence, max iterations: Evolve.C:1003-1022)
+ *     map to BF_DIVERGED / BF_MAXITER.
+ *   - Host arrays use the reference's own field representation and the
+ *     createBeamMesh ordering (applications/utilities/createBeamMesh/createBeamMesh.C:199-408):
+ *       cells    : beam-major contiguous, cellStart[k] = sum(nSeg[<k])
+ *       internal faces : beam-major contiguous, nSeg[k]-1 per beam,
+ *                        owner = i-1+cellStart[k], neighbour = i+cellStart[k]
+ *       boundary : patch left_k (1 face, faceCell = first cell of beam k),
+ *                  patch right_k (1 face, faceCell = last cell of beam k)
+ *       vector   : 3 contiguous doubles (x y z)
+ *       tensor   : 9 contiguous doubles (xx xy xz yx yy yz zx zy zz)
+ *   - One context per host thread; one CUDA device per context.  Calls are
+ *     synchronous at return.
+ */
+#ifndef BEAMGPU_H
+#define BEAMGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes -------------------------------------------------------- */
+#define BF_OK               0
+#define BF_ERR_INVALID      1   /* bad argument / inconsistent sizes             */
+#define BF_ERR_CUDA         2   /* CUDA runtime error (message in bf_last_error) */
+#define BF_ERR_NOMEM        3
+#define BF_DIVERGED         4   /* Evolve.C:1003-1012 "Diverged - Residual grew excessively" */
+#define BF_MAXITER          5   /* Evolve.C:1015-1022 "Failed - Maximum iterations reached"  */
+#define BF_ERR_UNSUPPORTED  6   /* e.g. coupled patches: BoundaryConditions.C:79-83 notImplemented */
+#define BF_ERR_COMM         7   /* NCCL / reducer failure */
+
+/* ---- enumerations -------------------------------------------------------- */
+/* d2dt2Schemes default (CTL/coupledTotalLagNewtonRaphsonBeam.C:668-683,708-765) */
+#define BF_SCHEME_STEADY    0
+#define BF_SCHEME_NEWMARK   1
+#define BF_SCHEME_EULER     2
+
+/* W boundary-condition classes (all derive from fixedValueFvPatchVectorField) */
+#define BF_W_FIXED          0   /* fixedValue, fixedDisplacement                      */
+#define BF_W_FORCE          1   /* forceBeamDisplacementNR                            */
+#define BF_W_FOLLOWER       2   /* followerForceBeamDisplacementNR (material-frame F) */
+#define BF_W_SPRING         3   /* linearSpringForceBeamDisplacementNR                */
+
+/* Theta boundary-condition classes */
+#define BF_TH_FIXED         0   /* fixedValue, fixedRotation */
+#define BF_TH_MOMENT        1   /* momentBeamRotationNR      */
+
+/* patch ends */
+#define BF_END_LEFT         0
+#define BF_END_RIGHT        1
+
+/* per-step boundary values set by bf_set_bc_values (what the reference's
+ * updateCoeffs() evaluates from its time series at the NEW time) */
+#define BF_BCV_W            0   /* prescribed W_b      (fixedValue / displacementSeries)   */
+#define BF_BCV_THETA        1   /* prescribed Theta_b  (fixedValue / thetaSeries)          */
+#define BF_BCV_FORCE        2   /* force(): forceSeries; followerForceSeries (material
+                                   frame); offsetForceSeries for the spring BC             */
+#define BF_BCV_MOMENT       3   /* moment(): momentSeries                                  */
+
+/* field identifiers for bf_set_field / bf_get_field */
+#define BF_FIELD_W          0   /* volVectorField  W        + boundary */
+#define BF_FIELD_THETA      1   /* volVectorField  Theta    + boundary */
+#define BF_FIELD_LAMBDA     2   /* volTensorField  Lambda   + boundary */
+#define BF_FIELD_DW         3   /* volVectorField  DW       + boundary (last increment) */
+#define BF_FIELD_DTHETA     4   /* volVectorField  DTheta   + boundary */
+#define BF_FIELD_U          5   /* volVectorField  U        (internal only) */
+#define BF_FIELD_ACCL       6   /* volVectorField  Accl     (internal only) */
+#define BF_FIELD_OMEGA      7   /* volVectorField  Omega    (internal only) */
+#define BF_FIELD_DOTOMEGA   8   /* volVectorField  dotOmega (internal only) */
+#define BF_FIELD_LAMBDAF    9   /* surfaceTensorField Lambdaf */
+#define BF_FIELD_GAMMA      10  /* surfaceVectorField Gamma   */
+#define BF_FIELD_K          11  /* surfaceVectorField K       */
+#define BF_FIELD_Q          12  /* surfaceVectorField Q       */
+#define BF_FIELD_M          13  /* surfaceVectorField M       */
+#define BF_FIELD_COUNT      14
+
+typedef struct bf_ctx bf_ctx;
+
+/* ---- construction -------------------------------------------------------- */
+
+/* Mesh of createBeamMesh: nBeams straight prism chains along global x
+ * (createBeamMesh.C:100-135,199-408).  dZ = length/nSeg; internal
+ * deltaCoeffs = 1/dZ, boundary deltaCoeffs = 2/dZ, weights = 0.5. */
+typedef struct bf_layout {
+    int64_t        nBeams;
+    const int32_t* nSeg;        /* [nBeams] cells per beam ("nSegments")            */
+    const double*  length;      /* [nBeams] beam length                              */
+    const double*  cellLength;  /* [sum(nSeg)] L() per cell, or NULL => dZ of its beam
+                                   (CTL.C:1060-1108: HermiteSpline::segLengths())    */
+} bf_layout;
+
+/* Per-beam constants the reference builds in its constructor
+ * (CTL.C:538-667,781-845; beamModel.H:449-584). */
+typedef struct bf_beam_props {
+    const double* CQ;          /* [nBeams*3] diag(EA, GA, GA)                        */
+    const double* CM;          /* [nBeams*3] diag(GJ, E*Iyy, E*Izz)                  */
+    const double* ARho;        /* [nBeams]   rho*A            (NULL => 0)            */
+    const double* CIRho;       /* [nBeams*3] kCI*rho*(J, Iyy, Izz) (NULL => 0)       */
+    const double* weight;      /* [nBeams*3] rho*A*g  (Evolve.C:201-209) (NULL => 0) */
+    const double* refLambdaf;  /* [nBeams*9] rigid initial rotation T written by
+                                  setInitialPositionBeam (refLambdaf = T, dR0Ds = T.x,
+                                  sign-flipped on the left patch: CTL.C:987-994);
+                                  NULL => identity                                   */
+} bf_beam_props;
+
+/* Boundary-condition classes per beam end; index = end*nBeams + beam. */
+typedef struct bf_bc {
+    const int32_t* wType;            /* [2*nBeams] BF_W_*                            */
+    const int32_t* thetaType;        /* [2*nBeams] BF_TH_*                           */
+    const double*  springStiffness;  /* [2*nBeams]   (NULL if no BF_W_SPRING)        */
+    const double*  springDirection;  /* [2*nBeams*3] normalised by the library as in
+                                        linearSpringForce...C:116-119                */
+} bf_bc;
+
+typedef struct bf_options {
+    int32_t scheme;          /* BF_SCHEME_*                                          */
+    double  newmarkBeta;     /* default 0.25  (CTL.C:755)                            */
+    double  newmarkGamma;    /* default 0.5   (CTL.C:756)                            */
+    int32_t device;          /* CUDA device ordinal (ignored by the oracle)          */
+    int32_t storeIncrements; /* !=0: keep the DW/DTheta cell fields in memory so that
+                                bf_get_field(BF_FIELD_DW/DTHETA) returns them        */
+    int32_t reserved[6];     /* must be zero */
+} bf_options;
+
+/* Keys of <model>Coeffs in constant/beamProperties (Evolve.C:61-102). */
+typedef struct bf_tolerances {
+    int32_t nCorrectors;     /* default 1000 */
+    double  residualTol;     /* rtol; default 1e-8 (falls back to convergenceTol)    */
+    double  solutionTol;     /* stol; default 1e-10 */
+    double  absoluteTol;     /* atol; default 1e-30 */
+    double  divergenceTol;   /* divtol; default 1e6 */
+} bf_tolerances;
+
+/* Result of one evolve(): iOuterCorr() after the loop and the norms of the
+ * last checkConvergence call (Evolve.C:104-107,644-669). */
+typedef struct bf_step_out {
+    int32_t nIter;               /* number of linear solves performed this step      */
+    int32_t status;              /* BF_OK, BF_DIVERGED or BF_MAXITER                 */
+    double  initialResidualNorm; /* what evolve() returns                            */
+    double  currentResidualNorm;
+    double  deltaXNorm;
+    double  xNorm;
+} bf_step_out;
+
+/* Sum-reduction of `n` doubles over all ranks that hold a shard of the bundle
+ * (in place).  Return 0 on success.  An OpenFOAM host passes a wrapper of
+ * Pstream `reduce(..., sumOp<scalar>())`; a torch host passes an all_reduce. */
+typedef int (*bf_reduce_fn)(double* values, int32_t n, void* user);
+
+/* Replaces: coupledTotalLagNewtonRaphsonBeam constructor state set-up
+ * (CTL.C:74-1182) for the quantities the hot path touches.  Fresh-run initial
+ * values: W=Theta=0, Lambda=Lambdaf=I, Gamma=K=Q=M=0,
+ * U=Accl=Omega=dotOmega=0, prevIter = current. */
+int bf_create(const bf_layout* layout, const bf_beam_props* props,
+              const bf_bc* bc, const bf_options* options, bf_ctx** out);
+int bf_destroy(bf_ctx* ctx);
+
+const char* bf_last_error(const bf_ctx* ctx);   /* ctx may be NULL: last create error */
+const char* bf_version(void);
+/* "cuda-sm100a" for libbeamgpu, "cpu-oracle" for the oracle */
+const char* bf_backend(void);
+
+int64_t bf_num_cells(const bf_ctx* ctx);
+int64_t bf_num_internal_faces(const bf_ctx* ctx);
+int64_t bf_num_beams(const bf_ctx* ctx);
+
+/* ---- state mirroring (host <-> authoritative solver state) ------------------
+ * Replaces the field members of CTL.H:108-177 being read/written by the host.
+ * Vol fields:     internal [nCells*nc], left/right = patch values [nBeams*nc].
+ * Surface fields: internal [nInternalFaces*nc], left/right [nBeams*nc].
+ * Any pointer may be NULL (that part is skipped).  Setting W or Theta also
+ * refreshes their prevIter copy (storePrevIter, CTL.C:1110-1111). */
+int bf_set_field(bf_ctx* ctx, int32_t field, const double* internal,
+                 const double* left, const double* right);
+int bf_get_field(bf_ctx* ctx, int32_t field, double* internal,
+                 double* left, double* right);
+
+/* Distributed loads q, m (volVectorFields "q","m"; Evolve.C:193-198,274-279).
+ * [nCells*3] each; NULL => zero. */
+int bf_set_distributed_loads(bf_ctx* ctx, const double* q, const double* m);
+
+/* Per-step boundary values == what W_/Theta_.boundaryFieldRef().updateCoeffs()
+ * (Evolve.C:156-157) evaluates from the BC time series at the new time.
+ * values: [nBeams*3] for patch `end`; entries of beams whose BC class does not
+ * use `kind` are ignored. */
+int bf_set_bc_values(bf_ctx* ctx, int32_t end, int32_t kind, const double* values);
+
+/* ---- the hot path ---------------------------------------------------------- */
+
+/* Start of a time/load step (beamFoam.C:73-79): sets deltaT and resets
+ * iOuterCorr.  With Newmark the predictor of Evolve.C:167-186 is applied inside
+ * the first bf_newton_iteration of the step. */
+int bf_begin_step(bf_ctx* ctx, double deltaT);
+
+/* One pass of the do{}-body of evolve() (Evolve.C:119-632): coefficients,
+ * assembly, BC closure, loads+inertia, block-tridiagonal solve, state update,
+ * BC evaluate.  sumsq[0] = sum(source^2) (= currentResidualNorm^2, x0 = 0),
+ * sumsq[1] = sum(solVec^2), sumsq[2] = sum|W|^2 + sum|Theta|^2, LOCAL to this
+ * context (EigenOF.C:279-281 "use sum instead of gSum"); no reducer applied. */
+int bf_newton_iteration(bf_ctx* ctx, double sumsq[3]);
+
+/* The whole Newton loop of evolve() with checkConvergence (Evolve.C:926-1026)
+ * evaluated on the (reduced) norms.  Always fills `out`. */
+int bf_evolve(bf_ctx* ctx, const bf_tolerances* tol, bf_step_out* out);
+
+/* Multi-GPU: beams are sharded across contexts; the only exchange is the sum of
+ * the three squared norms per Newton iteration. */
+int bf_set_reducer(bf_ctx* ctx, bf_reduce_fn fn, void* user);
+/* Built-in reducer: ncclAllReduce(sum, 3 x double) on the context's stream.
+ * uniqueId = the 128 bytes of ncclUniqueId created on rank 0 and broadcast by the
+ * host (MPI_Bcast in an OpenFOAM host).  libnccl is dlopen()ed on first use. */
+int bf_nccl_unique_id(void* uniqueId128);
+int bf_comm_init_nccl(bf_ctx* ctx, const void* uniqueId128, int32_t nRanks, int32_t rank);
+
+/* ---- instrumentation --------------------------------------------------------
+ * Kernel launches issued by this context since creation (bench gpu_launches),
+ * and device time in ms of the Newton-iteration kernels since the last reset,
+ * measured with CUDA events on the context's stream. */
+int64_t bf_launch_count(const bf_ctx* ctx);
+int bf_kernel_time_ms(bf_ctx* ctx, int32_t reset, double* fwd_ms, double* bwd_ms,
+                      int64_t* iterations);
+int bf_set_timing(bf_ctx* ctx, int32_t enabled);
+
+/* Pinned host memory for the mirror buffers (cudaHostAlloc; malloc in the oracle). */
+int bf_host_alloc(void** ptr, int64_t bytes);
+int bf_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEAMGPU_H */

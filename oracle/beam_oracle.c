@@ -1,0 +1,1091 @@
+/* beam_oracle.c — CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A literal, field-by-field CPU restatement (plain C99) of the per-Newton-iteration
+ * path of solids4foam/beamFoam's `coupledTotalLagNewtonRaphsonBeam`.  It exists to
+ * CHECK the CUDA implementation (tests/, __graft_entry__.smoke(), bench.py's
+ * cpu_baseline / --impl reference legs).  The product (beamfoam_b200/) never links,
+ * imports or calls anything in this directory.
+ *
+ * It deliberately keeps the reference's own structure — array-of-structs tensors,
+ * every coefficient field materialised (CQW, CQTheta, ... explicitMQ), d/l/u/source
+ * assembled as separate 6x6 blocks, one global linear solve — so that it is an
+ * independent statement of the arithmetic, not a CPU twin of the fused GPU kernels.
+ *
+ * PARITY PINNING: the reference (OpenFOAM + Eigen) cannot be built in this
+ * environment and ships no golden vectors at 1e-10.  This oracle is pinned against
+ * the only solver-generated numbers the reference ships — the 4-significant-figure
+ * tip deflections of tutorials/largeDeflectionCantilever/README.md:116-122 — plus
+ * the analytic roll-up of tutorials/cantilever/README.md:31, the digitised
+ * Simo & Vu-Quoc curve of tutorials/cantileverFollowerForce and the README
+ * iteration-count statements (tests/test_oracle_anchors.py).  Beyond 4 s.f. parity
+ * with the real binary is UNPINNED; see DESIGN.md.
+ *
+ * Citations: paths relative to the reference checkout;
+ *   Evolve.C = src/wireBunchingModels/beamModels/coupledTotalLagNewtonRaphsonBeam/
+ *              coupledTotalLagNewtonRaphsonBeamEvolve.C
+ *   Matrix.C = .../coupledTotalLagNewtonRaphsonBeamMatrix.C
+ *   BC.C     = .../coupledTotalLagNewtonRaphsonBeamBoundaryConditions.C
+ *   CTL.C    = .../coupledTotalLagNewtonRaphsonBeam.C
+ *   PF/      = src/wireBunchingModels/beamModels/fvPatchFields/
+ *   EigenOF.C= src/wireBunchingModels/numerics/BlockEigenSolvers/BlockEigenSolverOF/BlockEigenSolverOF.C
+ */
+#include "../include/beamgpu.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SMALL 1e-15 /* OpenFOAM double-precision SMALL */
+#define GREAT 1e15
+
+/* ------------------------------------------------------------------------- */
+/* small tensor algebra in OpenFOAM conventions (row-major xx xy xz yx ...)   */
+/* ------------------------------------------------------------------------- */
+static void t_zero(double* A) { memset(A, 0, 9 * sizeof(double)); }
+static void t_eye(double* A) { t_zero(A); A[0] = A[4] = A[8] = 1.0; }
+static void t_copy(const double* A, double* O) { memcpy(O, A, 9 * sizeof(double)); }
+static void t_T(const double* A, double* O)
+{
+    double t[9] = {A[0], A[3], A[6], A[1], A[4], A[7], A[2], A[5], A[8]};
+    memcpy(O, t, sizeof t);
+}
+static void t_mul_t(const double* A, const double* B, double* O) /* A & B */
+{
+    double t[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    memcpy(O, t, sizeof t);
+}
+static void t_mul_v(const double* A, const double* v, double* o) /* A & v */
+{
+    double t[3];
+    for (int i = 0; i < 3; i++) t[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+    memcpy(o, t, sizeof t);
+}
+static void t_diag(const double* dg, double* O) { t_zero(O); O[0] = dg[0]; O[4] = dg[1]; O[8] = dg[2]; }
+static void t_axpy(double a, const double* X, double* Y) { for (int i = 0; i < 9; i++) Y[i] += a * X[i]; }
+static void t_scale(double a, double* X) { for (int i = 0; i < 9; i++) X[i] *= a; }
+static void t_sub(const double* A, const double* B, double* O) { for (int i = 0; i < 9; i++) O[i] = A[i] - B[i]; }
+static void t_add(const double* A, const double* B, double* O) { for (int i = 0; i < 9; i++) O[i] = A[i] + B[i]; }
+/* spinTensor(v): src/wireBunchingModels/numerics/spinTensor/spinTensor.C:154-168 */
+static void spin(const double* v, double* O)
+{
+    t_zero(O);
+    O[1] = -v[2]; O[2] = v[1];
+    O[3] = v[2];  O[5] = -v[0];
+    O[6] = -v[1]; O[7] = v[0];
+}
+static void cross(const double* a, const double* b, double* o)
+{
+    double t[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    memcpy(o, t, sizeof t);
+}
+static double vmag(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+/* OpenFOAM inv(tensor): adjugate / determinant */
+static void t_inv(const double* A, double* O)
+{
+    const double xx = A[0], xy = A[1], xz = A[2], yx = A[3], yy = A[4], yz = A[5], zx = A[6], zy = A[7], zz = A[8];
+    const double det = xx * yy * zz + xy * yz * zx + xz * yx * zy - xx * yz * zy - xy * yx * zz - xz * yy * zx;
+    double t[9] = {
+        yy * zz - zy * yz, xz * zy - xy * zz, xy * yz - xz * yy,
+        zx * yz - yx * zz, xx * zz - xz * zx, yx * xz - xx * yz,
+        yx * zy - yy * zx, xy * zx - xx * zy, xx * yy - yx * xy};
+    for (int i = 0; i < 9; i++) O[i] = t[i] / det;
+}
+/* rotationMatrix(theta): src/wireBunchingModels/numerics/pseudoVector/pseudoVector.C:250-264
+ * R = I + (sin(phi)/phi) S + ((1-cos(phi))/phi^2) S&S, phi = mag(theta) + SMALL (no series branch) */
+static void rotationMatrix(const double* th, double* R)
+{
+    const double phi = vmag(th) + SMALL;
+    double S[9], SS[9];
+    spin(th, S);
+    t_mul_t(S, S, SS);
+    t_eye(R);
+    t_axpy(sin(phi) / phi, S, R);
+    t_axpy((1.0 - cos(phi)) / (phi * phi), SS, R);
+}
+
+/* ------------------------------------------------------------------------- */
+struct bf_ctx {
+    char err[512];
+    int64_t B, N, F, NF; /* beams, cells, internal faces, all faces = F + 2B */
+    int32_t* nSeg;
+    int64_t *cellStart, *faceStart;
+    int32_t *own, *nei; /* [F] mesh().owner()/neighbour() */
+    int32_t* pcell;     /* [2B] patch faceCells: p = end*B + beam */
+    double* dc;         /* [NF] mesh().deltaCoeffs(): internal then boundary */
+    double* wf;         /* [F]  mesh().weights() */
+    double* L;          /* [N]  L() */
+    int32_t* cellBeam;  /* [N]  whichBeam */
+    int32_t* faceBeam;  /* [NF] */
+    /* per-beam constants */
+    double *CQ, *CM, *ARho, *CIRho, *weight;
+    /* surface fields [NF*nc]: internal faces then left patches then right patches */
+    double *Lambdaf, *refLambdaf, *dR0Ds, *Gamma, *K, *Q, *M;
+    double *CQW, *CQTheta, *CQDTheta, *CMTheta, *CMTheta2, *CMQW, *CMQTheta;
+    double *explicitQ, *explicitM, *explicitMQ;
+    /* vol fields: internal [N*nc], boundary [2B*nc] */
+    double *W, *Wb, *WbPrev, *Theta, *Thetab, *ThetabPrev;
+    double *Lambda, *Lambdab, *DW, *DWb, *DTheta, *DThetab;
+    double *U, *Accl, *Omega, *dotOmega;
+    double *q, *m;
+    /* boundary-condition objects */
+    int32_t *wType, *thType;
+    double *springK, *springDir;
+    double *wPresc, *thPresc;     /* prescribed values (series at new time) */
+    double *force;                /* force() == curForce_ */
+    double *followerForce;        /* followerForce_ (material frame) */
+    double *offsetForce;          /* offsetForce_ */
+    double *moment;               /* moment_ */
+    /* block system of the last iteration (kept for tests) */
+    double *d, *l, *u, *source, *solVec;
+    /* options / time state */
+    int scheme;
+    double betaN, gammaN, deltaT;
+    int iOuterCorr;
+    bf_reduce_fn reducer;
+    void* reducerUser;
+    int64_t launches;
+};
+
+static char g_create_err[512];
+
+#define ALLOC(ptr, n)                                                    \
+    do {                                                                 \
+        (ptr) = calloc((size_t)((n) > 0 ? (n) : 1), sizeof(*(ptr)));      \
+        if (!(ptr)) { snprintf(g_create_err, sizeof g_create_err, "out of memory"); goto fail; } \
+    } while (0)
+
+const char* bf_version(void) { return "beamgpu-oracle 0.1"; }
+const char* bf_backend(void) { return "cpu-oracle"; }
+const char* bf_last_error(const bf_ctx* c) { return c ? c->err : g_create_err; }
+int64_t bf_num_cells(const bf_ctx* c) { return c->N; }
+int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
+int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
+int64_t bf_launch_count(const bf_ctx* c) { (void)c; return 0; }
+int bf_kernel_time_ms(bf_ctx* c, int32_t r, double* a, double* b, int64_t* it)
+{
+    (void)c; (void)r;
+    if (a) *a = 0;
+    if (b) *b = 0;
+    if (it) *it = 0;
+    return BF_OK;
+}
+int bf_set_timing(bf_ctx* c, int32_t e) { (void)c; (void)e; return BF_OK; }
+int bf_host_alloc(void** p, int64_t bytes) { *p = malloc((size_t)bytes); return *p ? BF_OK : BF_ERR_NOMEM; }
+int bf_host_free(void* p) { free(p); return BF_OK; }
+int bf_nccl_unique_id(void* id) { (void)id; return BF_ERR_UNSUPPORTED; }
+int bf_comm_init_nccl(bf_ctx* c, const void* id, int32_t n, int32_t r)
+{
+    (void)id; (void)n; (void)r;
+    snprintf(c->err, sizeof c->err, "the CPU oracle has no NCCL reducer; use bf_set_reducer");
+    return BF_ERR_UNSUPPORTED;
+}
+int bf_set_reducer(bf_ctx* c, bf_reduce_fn fn, void* user) { c->reducer = fn; c->reducerUser = user; return BF_OK; }
+
+int bf_destroy(bf_ctx* c)
+{
+    if (!c) return BF_OK;
+    void* ptrs[] = {c->nSeg, c->cellStart, c->faceStart, c->own, c->nei, c->pcell, c->dc, c->wf, c->L, c->cellBeam,
+                    c->faceBeam, c->CQ, c->CM, c->ARho, c->CIRho, c->weight, c->Lambdaf, c->refLambdaf, c->dR0Ds,
+                    c->Gamma, c->K, c->Q, c->M, c->CQW, c->CQTheta, c->CQDTheta, c->CMTheta, c->CMTheta2, c->CMQW,
+                    c->CMQTheta, c->explicitQ, c->explicitM, c->explicitMQ, c->W, c->Wb, c->WbPrev, c->Theta,
+                    c->Thetab, c->ThetabPrev, c->Lambda, c->Lambdab, c->DW, c->DWb, c->DTheta, c->DThetab, c->U,
+                    c->Accl, c->Omega, c->dotOmega, c->q, c->m, c->wType, c->thType, c->springK, c->springDir,
+                    c->wPresc, c->thPresc, c->force, c->followerForce, c->offsetForce, c->moment, c->d, c->l, c->u,
+                    c->source, c->solVec};
+    for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) free(ptrs[i]);
+    free(c);
+    return BF_OK;
+}
+
+/* Constructor state: CTL.C:74-1182 (fields), createBeamMesh.C:199-408 (addressing). */
+int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf_bc* bc, const bf_options* opt, bf_ctx** out)
+{
+    bf_ctx* c = NULL;
+    if (!lay || !pr || !bc || !opt || !out || lay->nBeams <= 0 || !lay->nSeg || !lay->length || !pr->CQ || !pr->CM ||
+        !bc->wType || !bc->thetaType) {
+        snprintf(g_create_err, sizeof g_create_err, "bf_create: null/invalid argument");
+        return BF_ERR_INVALID;
+    }
+    if (opt->scheme != BF_SCHEME_STEADY && opt->scheme != BF_SCHEME_NEWMARK) {
+        snprintf(g_create_err, sizeof g_create_err, "bf_create: d2dt2 scheme %d not supported (steadyState, Newmark)",
+                 opt->scheme);
+        return BF_ERR_UNSUPPORTED;
+    }
+    c = calloc(1, sizeof *c);
+    if (!c) return BF_ERR_NOMEM;
+    const int64_t B = lay->nBeams;
+    c->B = B;
+    ALLOC(c->nSeg, B); ALLOC(c->cellStart, B + 1); ALLOC(c->faceStart, B + 1);
+    for (int64_t b = 0; b < B; b++) {
+        if (lay->nSeg[b] < 1 || !(lay->length[b] > 0)) {
+            snprintf(g_create_err, sizeof g_create_err, "bf_create: beam %lld has nSeg<1 or length<=0", (long long)b);
+            goto fail_invalid;
+        }
+        c->nSeg[b] = lay->nSeg[b];
+        c->cellStart[b + 1] = c->cellStart[b] + lay->nSeg[b];
+        c->faceStart[b + 1] = c->faceStart[b] + lay->nSeg[b] - 1;
+    }
+    const int64_t N = c->N = c->cellStart[B], F = c->F = c->faceStart[B], NF = c->NF = F + 2 * B;
+    ALLOC(c->own, F); ALLOC(c->nei, F); ALLOC(c->pcell, 2 * B); ALLOC(c->dc, NF); ALLOC(c->wf, F); ALLOC(c->L, N);
+    ALLOC(c->cellBeam, N); ALLOC(c->faceBeam, NF);
+    ALLOC(c->CQ, 3 * B); ALLOC(c->CM, 3 * B); ALLOC(c->ARho, B); ALLOC(c->CIRho, 3 * B); ALLOC(c->weight, 3 * B);
+    for (int64_t b = 0; b < B; b++) {
+        const int n = c->nSeg[b];
+        const double dZ = lay->length[b] / n; /* createBeamMesh.C:245 */
+        for (int i = 0; i < n; i++) {
+            const int64_t cell = c->cellStart[b] + i;
+            c->cellBeam[cell] = (int32_t)b;
+            c->L[cell] = lay->cellLength ? lay->cellLength[cell] : dZ;
+        }
+        for (int i = 1; i < n; i++) { /* createBeamMesh.C:357-370,398-408 */
+            const int64_t f = c->faceStart[b] + i - 1;
+            c->own[f] = (int32_t)(c->cellStart[b] + i - 1);
+            c->nei[f] = (int32_t)(c->cellStart[b] + i);
+            c->dc[f] = 1.0 / dZ;
+            c->wf[f] = 0.5;
+            c->faceBeam[f] = (int32_t)b;
+        }
+        c->pcell[b] = (int32_t)c->cellStart[b];             /* left_k  */
+        c->pcell[B + b] = (int32_t)(c->cellStart[b] + n - 1); /* right_k */
+        c->dc[F + b] = c->dc[F + B + b] = 2.0 / dZ;
+        c->faceBeam[F + b] = c->faceBeam[F + B + b] = (int32_t)b;
+        for (int k = 0; k < 3; k++) {
+            c->CQ[3 * b + k] = pr->CQ[3 * b + k];
+            c->CM[3 * b + k] = pr->CM[3 * b + k];
+            c->CIRho[3 * b + k] = pr->CIRho ? pr->CIRho[3 * b + k] : 0.0;
+            c->weight[3 * b + k] = pr->weight ? pr->weight[3 * b + k] : 0.0;
+        }
+        c->ARho[b] = pr->ARho ? pr->ARho[b] : 0.0;
+    }
+    ALLOC(c->Lambdaf, 9 * NF); ALLOC(c->refLambdaf, 9 * NF); ALLOC(c->dR0Ds, 3 * NF); ALLOC(c->Gamma, 3 * NF);
+    ALLOC(c->K, 3 * NF); ALLOC(c->Q, 3 * NF); ALLOC(c->M, 3 * NF);
+    ALLOC(c->CQW, 9 * NF); ALLOC(c->CQTheta, 9 * NF); ALLOC(c->CQDTheta, 9 * NF); ALLOC(c->CMTheta, 9 * NF);
+    ALLOC(c->CMTheta2, 9 * NF); ALLOC(c->CMQW, 9 * NF); ALLOC(c->CMQTheta, 9 * NF);
+    ALLOC(c->explicitQ, 3 * NF); ALLOC(c->explicitM, 3 * NF); ALLOC(c->explicitMQ, 3 * NF);
+    ALLOC(c->W, 3 * N); ALLOC(c->Wb, 6 * B); ALLOC(c->WbPrev, 6 * B);
+    ALLOC(c->Theta, 3 * N); ALLOC(c->Thetab, 6 * B); ALLOC(c->ThetabPrev, 6 * B);
+    ALLOC(c->Lambda, 9 * N); ALLOC(c->Lambdab, 18 * B);
+    ALLOC(c->DW, 3 * N); ALLOC(c->DWb, 6 * B); ALLOC(c->DTheta, 3 * N); ALLOC(c->DThetab, 6 * B);
+    ALLOC(c->U, 3 * N); ALLOC(c->Accl, 3 * N); ALLOC(c->Omega, 3 * N); ALLOC(c->dotOmega, 3 * N);
+    ALLOC(c->q, 3 * N); ALLOC(c->m, 3 * N);
+    ALLOC(c->wType, 2 * B); ALLOC(c->thType, 2 * B); ALLOC(c->springK, 2 * B); ALLOC(c->springDir, 6 * B);
+    ALLOC(c->wPresc, 6 * B); ALLOC(c->thPresc, 6 * B); ALLOC(c->force, 6 * B); ALLOC(c->followerForce, 6 * B);
+    ALLOC(c->offsetForce, 6 * B); ALLOC(c->moment, 6 * B);
+    ALLOC(c->d, 36 * N); ALLOC(c->l, 36 * F); ALLOC(c->u, 36 * F); ALLOC(c->source, 6 * N); ALLOC(c->solVec, 6 * N);
+
+    /* Lambda = Lambdaf = I (CTL.C:289-314); refLambdaf = T; dR0Ds = refTangent with the
+       start patches sign-flipped (CTL.C:987-994; CTL.C:906-907 for T = I). */
+    for (int64_t f = 0; f < NF; f++) {
+        const int64_t b = c->faceBeam[f];
+        t_eye(c->Lambdaf + 9 * f);
+        if (pr->refLambdaf) t_copy(pr->refLambdaf + 9 * b, c->refLambdaf + 9 * f);
+        else t_eye(c->refLambdaf + 9 * f);
+        const double ex[3] = {1, 0, 0};
+        t_mul_v(c->refLambdaf + 9 * f, ex, c->dR0Ds + 3 * f);
+        if (f >= F && f < F + B)
+            for (int k = 0; k < 3; k++) c->dR0Ds[3 * f + k] *= -1;
+    }
+    for (int64_t i = 0; i < N; i++) t_eye(c->Lambda + 9 * i);
+    for (int64_t p = 0; p < 2 * B; p++) {
+        t_eye(c->Lambdab + 9 * p);
+        c->wType[p] = bc->wType[p];
+        c->thType[p] = bc->thetaType[p];
+        if (c->wType[p] < BF_W_FIXED || c->wType[p] > BF_W_SPRING || c->thType[p] < BF_TH_FIXED ||
+            c->thType[p] > BF_TH_MOMENT) {
+            snprintf(g_create_err, sizeof g_create_err, "bf_create: unknown boundary-condition class at patch %lld",
+                     (long long)p);
+            goto fail_invalid;
+        }
+        if (c->wType[p] == BF_W_SPRING) {
+            if (!bc->springStiffness || !bc->springDirection) {
+                snprintf(g_create_err, sizeof g_create_err, "bf_create: spring BC without linearSpringCoeffs");
+                goto fail_invalid;
+            }
+            c->springK[p] = bc->springStiffness[p];
+            double dir[3] = {bc->springDirection[3 * p], bc->springDirection[3 * p + 1], bc->springDirection[3 * p + 2]};
+            const double mg = vmag(dir); /* PF/linearSpringForce...C:116-119 */
+            if (mg > SMALL)
+                for (int k = 0; k < 3; k++) dir[k] /= mg;
+            memcpy(c->springDir + 3 * p, dir, sizeof dir);
+        }
+    }
+    c->scheme = opt->scheme;
+    c->betaN = opt->newmarkBeta > 0 ? opt->newmarkBeta : 0.25;
+    c->gammaN = opt->newmarkGamma > 0 ? opt->newmarkGamma : 0.5;
+    c->deltaT = 1.0;
+    *out = c;
+    return BF_OK;
+fail_invalid:
+    bf_destroy(c);
+    return BF_ERR_INVALID;
+fail:
+    bf_destroy(c);
+    return BF_ERR_NOMEM;
+}
+
+/* ------------------------------------------------------------------------- */
+/* field mirroring                                                            */
+/* ------------------------------------------------------------------------- */
+static int field_ptrs(bf_ctx* c, int field, double** in, double** bnd, int* nc, int* surface)
+{
+    *bnd = NULL; *surface = 0;
+    switch (field) {
+    case BF_FIELD_W: *in = c->W; *bnd = c->Wb; *nc = 3; break;
+    case BF_FIELD_THETA: *in = c->Theta; *bnd = c->Thetab; *nc = 3; break;
+    case BF_FIELD_LAMBDA: *in = c->Lambda; *bnd = c->Lambdab; *nc = 9; break;
+    case BF_FIELD_DW: *in = c->DW; *bnd = c->DWb; *nc = 3; break;
+    case BF_FIELD_DTHETA: *in = c->DTheta; *bnd = c->DThetab; *nc = 3; break;
+    case BF_FIELD_U: *in = c->U; *nc = 3; break;
+    case BF_FIELD_ACCL: *in = c->Accl; *nc = 3; break;
+    case BF_FIELD_OMEGA: *in = c->Omega; *nc = 3; break;
+    case BF_FIELD_DOTOMEGA: *in = c->dotOmega; *nc = 3; break;
+    case BF_FIELD_LAMBDAF: *in = c->Lambdaf; *nc = 9; *surface = 1; break;
+    case BF_FIELD_GAMMA: *in = c->Gamma; *nc = 3; *surface = 1; break;
+    case BF_FIELD_K: *in = c->K; *nc = 3; *surface = 1; break;
+    case BF_FIELD_Q: *in = c->Q; *nc = 3; *surface = 1; break;
+    case BF_FIELD_M: *in = c->M; *nc = 3; *surface = 1; break;
+    default: snprintf(c->err, sizeof c->err, "unknown field id %d", field); return BF_ERR_INVALID;
+    }
+    return BF_OK;
+}
+
+int bf_set_field(bf_ctx* c, int32_t field, const double* internal, const double* left, const double* right)
+{
+    double *in, *bnd; int nc, surf;
+    int rc = field_ptrs(c, field, &in, &bnd, &nc, &surf);
+    if (rc) return rc;
+    const int64_t B = c->B;
+    if (surf) {
+        if (internal) memcpy(in, internal, sizeof(double) * nc * c->F);
+        if (left) memcpy(in + nc * c->F, left, sizeof(double) * nc * B);
+        if (right) memcpy(in + nc * (c->F + B), right, sizeof(double) * nc * B);
+    } else {
+        if (internal) memcpy(in, internal, sizeof(double) * nc * c->N);
+        if (bnd && left) memcpy(bnd, left, sizeof(double) * nc * B);
+        if (bnd && right) memcpy(bnd + nc * B, right, sizeof(double) * nc * B);
+    }
+    if (field == BF_FIELD_W) { /* storePrevIter (CTL.C:1110); a plain fixedValue keeps its value */
+        memcpy(c->WbPrev, c->Wb, sizeof(double) * 6 * B);
+        memcpy(c->wPresc, c->Wb, sizeof(double) * 6 * B);
+    }
+    if (field == BF_FIELD_THETA) {
+        memcpy(c->ThetabPrev, c->Thetab, sizeof(double) * 6 * B);
+        memcpy(c->thPresc, c->Thetab, sizeof(double) * 6 * B);
+    }
+    return BF_OK;
+}
+
+int bf_get_field(bf_ctx* c, int32_t field, double* internal, double* left, double* right)
+{
+    double *in, *bnd; int nc, surf;
+    int rc = field_ptrs(c, field, &in, &bnd, &nc, &surf);
+    if (rc) return rc;
+    const int64_t B = c->B;
+    if (surf) {
+        if (internal) memcpy(internal, in, sizeof(double) * nc * c->F);
+        if (left) memcpy(left, in + nc * c->F, sizeof(double) * nc * B);
+        if (right) memcpy(right, in + nc * (c->F + B), sizeof(double) * nc * B);
+    } else {
+        if (internal) memcpy(internal, in, sizeof(double) * nc * c->N);
+        if (left || right) {
+            if (!bnd) { snprintf(c->err, sizeof c->err, "field %d has no mirrored boundary values", field); return BF_ERR_INVALID; }
+            if (left) memcpy(left, bnd, sizeof(double) * nc * B);
+            if (right) memcpy(right, bnd + nc * B, sizeof(double) * nc * B);
+        }
+    }
+    return BF_OK;
+}
+
+int bf_set_distributed_loads(bf_ctx* c, const double* q, const double* m)
+{
+    if (q) memcpy(c->q, q, sizeof(double) * 3 * c->N); else memset(c->q, 0, sizeof(double) * 3 * c->N);
+    if (m) memcpy(c->m, m, sizeof(double) * 3 * c->N); else memset(c->m, 0, sizeof(double) * 3 * c->N);
+    return BF_OK;
+}
+
+/* What the patch fields' updateCoeffs() read from their series at the new time:
+ * PF/fixedDisplacement...C:160-198, PF/fixedRotation...C:160-213,
+ * PF/forceBeamDisplacementNR...C:186-209, PF/followerForce...C:183-190,
+ * PF/linearSpringForce...C:204-217, PF/momentBeamRotationNR...C:168-181. */
+int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const double* v)
+{
+    if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !v) { snprintf(c->err, sizeof c->err, "bf_set_bc_values: bad argument"); return BF_ERR_INVALID; }
+    const int64_t B = c->B;
+    for (int64_t b = 0; b < B; b++) {
+        const int64_t p = end * B + b;
+        const double* x = v + 3 * b;
+        switch (kind) {
+        case BF_BCV_W: if (c->wType[p] == BF_W_FIXED) memcpy(c->wPresc + 3 * p, x, 24); break;
+        case BF_BCV_THETA: if (c->thType[p] == BF_TH_FIXED) memcpy(c->thPresc + 3 * p, x, 24); break;
+        case BF_BCV_FORCE:
+            if (c->wType[p] == BF_W_FORCE) memcpy(c->force + 3 * p, x, 24);
+            else if (c->wType[p] == BF_W_FOLLOWER) memcpy(c->followerForce + 3 * p, x, 24);
+            else if (c->wType[p] == BF_W_SPRING) memcpy(c->offsetForce + 3 * p, x, 24);
+            break;
+        case BF_BCV_MOMENT: if (c->thType[p] == BF_TH_MOMENT) memcpy(c->moment + 3 * p, x, 24); break;
+        default: snprintf(c->err, sizeof c->err, "bf_set_bc_values: unknown kind %d", kind); return BF_ERR_INVALID;
+        }
+    }
+    return BF_OK;
+}
+
+int bf_begin_step(bf_ctx* c, double deltaT)
+{
+    if (!(deltaT > 0)) { snprintf(c->err, sizeof c->err, "bf_begin_step: deltaT must be > 0"); return BF_ERR_INVALID; }
+    c->deltaT = deltaT;
+    c->iOuterCorr = 0;
+    return BF_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* fvc:: helpers on the 1-D chain mesh (orthogonal snGrad, linear interpolate) */
+/* ------------------------------------------------------------------------- */
+/* snGrad of a vol vector field at face f (internal: (nei-own)*dc; boundary: (b-c)*dc) */
+static void snGrad(const bf_ctx* c, const double* vI, const double* vB, int64_t f, double* o)
+{
+    if (f < c->F) {
+        const double *a = vI + 3 * c->own[f], *b = vI + 3 * c->nei[f];
+        for (int k = 0; k < 3; k++) o[k] = c->dc[f] * (b[k] - a[k]);
+    } else {
+        const int64_t p = f - c->F;
+        const double *a = vI + 3 * c->pcell[p], *b = vB + 3 * p;
+        for (int k = 0; k < 3; k++) o[k] = c->dc[f] * (b[k] - a[k]);
+    }
+}
+/* linear interpolate of a vol vector field at face f (boundary: patch value) */
+static void interpolate(const bf_ctx* c, const double* vI, const double* vB, int64_t f, double* o)
+{
+    if (f < c->F) {
+        const double w = c->wf[f];
+        const double *a = vI + 3 * c->own[f], *b = vI + 3 * c->nei[f];
+        for (int k = 0; k < 3; k++) o[k] = w * a[k] + (1 - w) * b[k];
+    } else {
+        memcpy(o, vB + 3 * (f - c->F), 24);
+    }
+}
+
+/* Evolve.C:673-753 */
+static void updateEqnCoefficients(bf_ctx* c)
+{
+    for (int64_t f = 0; f < c->NF; f++) {
+        const int64_t b = c->faceBeam[f];
+        double dRdS[3], g[3];
+        snGrad(c, c->W, c->Wb, f, g);
+        for (int k = 0; k < 3; k++) dRdS[k] = c->dR0Ds[3 * f + k] + g[k]; /* :675 */
+        double Lam[9], LamT[9], CQ[9], CM[9], tmp[9], tv[3], S[9], SQ[9];
+        t_mul_t(c->Lambdaf + 9 * f, c->refLambdaf + 9 * f, Lam); /* :678 */
+        t_T(Lam, LamT);
+        t_diag(c->CQ + 3 * b, CQ);
+        t_diag(c->CM + 3 * b, CM);
+        double* CQW = c->CQW + 9 * f;
+        t_mul_t(CQ, LamT, tmp); t_mul_t(Lam, tmp, CQW);                       /* :680 */
+        t_mul_v(CQ, c->Gamma + 3 * f, tv); t_mul_v(Lam, tv, c->explicitQ + 3 * f); /* :682 */
+        t_mul_v(CM, c->K + 3 * f, tv); t_mul_v(Lam, tv, c->explicitM + 3 * f);     /* :684 */
+        spin(dRdS, S);
+        spin(c->Q + 3 * f, SQ);
+        t_mul_t(CQW, S, tmp); t_sub(tmp, SQ, c->CQTheta + 9 * f);              /* :686-693 */
+        t_zero(c->CQDTheta + 9 * f);                                           /* :697, CDQDK_ == 0 (CTL.C:586-603) */
+        t_mul_t(CM, LamT, tmp); t_mul_t(Lam, tmp, c->CMTheta + 9 * f);         /* :699 */
+        spin(c->M + 3 * f, tmp);
+        for (int k = 0; k < 9; k++) c->CMTheta2[9 * f + k] = -tmp[k];          /* :703 */
+        double SC[9];
+        t_mul_t(S, CQW, SC);
+        t_sub(SC, SQ, tmp);
+        for (int k = 0; k < 9; k++) c->CMQW[9 * f + k] = 0.5 * tmp[k] / c->dc[f]; /* :706-715 */
+        double SCS[9], SSQ[9];
+        t_mul_t(SC, S, SCS);
+        t_mul_t(S, SQ, SSQ);
+        t_sub(SCS, SSQ, tmp);
+        for (int k = 0; k < 9; k++) c->CMQTheta[9 * f + k] = 0.5 * tmp[k] / c->dc[f]; /* :718-735 */
+        t_mul_v(S, c->explicitQ + 3 * f, tv);
+        for (int k = 0; k < 3; k++) c->explicitMQ[3 * f + k] = 0.5 * tv[k] / c->dc[f]; /* :737-741 */
+        if (f >= c->F) { /* :744-752 non-coupled boundary patches */
+            t_scale(2.0, c->CMQW + 9 * f);
+            t_scale(2.0, c->CMQTheta + 9 * f);
+            for (int k = 0; k < 3; k++) c->explicitMQ[3 * f + k] *= 2;
+        }
+    }
+}
+
+#define BLK(M, i, r, cc) (M)[36 * (i) + 6 * (r) + (cc)]
+static void add_block(double* M, int64_t i, int r0, int c0, double a, const double* T)
+{
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) BLK(M, i, r0 + r, c0 + k) += a * T[3 * r + k];
+}
+
+/* Matrix.C:55-475 (internal faces) */
+static void assembleMatrixCoefficients(bf_ctx* c)
+{
+    double *d = c->d, *l = c->l, *u = c->u, *src = c->source;
+    for (int64_t f = 0; f < c->F; f++) {
+        const int64_t o = c->own[f], n = c->nei[f];
+        const double a = c->dc[f]; /* 1/deltaf */
+        const double w = c->wf[f];
+        const double *CQW = c->CQW + 9 * f, *CQDT = c->CQDTheta + 9 * f, *CQT = c->CQTheta + 9 * f;
+        const double *CMT = c->CMTheta + 9 * f, *CMT2 = c->CMTheta2 + 9 * f, *CMQW = c->CMQW + 9 * f;
+        const double *CMQT = c->CMQTheta + 9 * f;
+        const double *eQ = c->explicitQ + 3 * f, *eM = c->explicitM + 3 * f, *eMQ = c->explicitMQ + 3 * f;
+        /* W part (Laplacian) :84-130 */
+        add_block(u, f, 0, 0, a, CQW); add_block(d, o, 0, 0, -a, CQW);
+        add_block(l, f, 0, 0, a, CQW); add_block(d, n, 0, 0, -a, CQW);
+        /* Theta part: Laplacian :134-180 */
+        add_block(u, f, 0, 3, a, CQDT); add_block(d, o, 0, 3, -a, CQDT);
+        add_block(l, f, 0, 3, a, CQDT); add_block(d, n, 0, 3, -a, CQDT);
+        /* Theta part :184-238 */
+        add_block(u, f, 0, 3, (1 - w), CQT); add_block(d, o, 0, 3, w, CQT);
+        add_block(l, f, 0, 3, -w, CQT);      add_block(d, n, 0, 3, -(1 - w), CQT);
+        for (int k = 0; k < 3; k++) { src[6 * o + k] -= eQ[k]; src[6 * n + k] -= -eQ[k]; }
+        /* Theta equation, Laplacian :245-291 */
+        add_block(u, f, 3, 3, a, CMT); add_block(d, o, 3, 3, -a, CMT);
+        add_block(l, f, 3, 3, a, CMT); add_block(d, n, 3, 3, -a, CMT);
+        /* Theta part :296-352 */
+        add_block(u, f, 3, 3, (1 - w), CMT2); add_block(d, o, 3, 3, w, CMT2);
+        add_block(l, f, 3, 3, -w, CMT2);      add_block(d, n, 3, 3, -(1 - w), CMT2);
+        for (int k = 0; k < 3; k++) { src[6 * o + 3 + k] -= eM[k]; src[6 * n + 3 + k] -= -eM[k]; }
+        /* (dr x Q) term, W part :359-405 */
+        add_block(u, f, 3, 0, a, CMQW);  add_block(d, o, 3, 0, -a, CMQW);
+        add_block(l, f, 3, 0, -a, CMQW); add_block(d, n, 3, 0, a, CMQW);
+        /* Theta part :408-456 */
+        add_block(u, f, 3, 3, (1 - w), CMQT); add_block(d, o, 3, 3, w, CMQT);
+        add_block(l, f, 3, 3, w, CMQT);       add_block(d, n, 3, 3, (1 - w), CMQT);
+        /* explicit part :459-470 (same sign on both cells) */
+        for (int k = 0; k < 3; k++) { src[6 * o + 3 + k] -= eMQ[k]; src[6 * n + 3 + k] -= eMQ[k]; }
+    }
+}
+
+/* BC.C:64-1190.  All W classes but BF_W_FIXED are forceBeamDisplacementNR (or derived);
+ * every Theta class isA<fixedValueFvPatchVectorField>. */
+static void assembleBoundaryConditions(bf_ctx* c)
+{
+    double *d = c->d, *src = c->source;
+    const int64_t B = c->B, F = c->F;
+    for (int64_t p = 0; p < 2 * B; p++) { /* patch order left_0.., right_0.. */
+        const int64_t f = F + p, fc = c->pcell[p];
+        const double *pCQW = c->CQW + 9 * f, *pCQTheta = c->CQTheta + 9 * f, *pCQDTheta = c->CQDTheta + 9 * f;
+        const double *pCMTheta = c->CMTheta + 9 * f, *pCMTheta2 = c->CMTheta2 + 9 * f, *pCMQW = c->CMQW + 9 * f;
+        const double *pCMQTheta = c->CMQTheta + 9 * f;
+        const double *pExplicitQ = c->explicitQ + 3 * f, *pExplicitM = c->explicitM + 3 * f;
+        const double *pExplicitMQ = c->explicitMQ + 3 * f;
+        const double* pLambdaf = c->Lambdaf + 9 * f;
+        const double pDelta = 1.0 / c->dc[f];
+        const int isForce = c->wType[p] != BF_W_FIXED;
+        const int isFollower = c->wType[p] == BF_W_FOLLOWER;
+        const int isMoment = c->thType[p] == BF_TH_MOMENT;
+        const double* force = c->force + 3 * p;
+        double dRdS[3], g[3], tv[3], tv2[3], T1[9], T2[9];
+        snGrad(c, c->W, c->Wb, f, g);
+        for (int k = 0; k < 3; k++) dRdS[k] = c->dR0Ds[3 * f + k] + g[k]; /* :72 */
+
+        /* ---- W equation ---- */
+        if (isForce) { /* :102-155 */
+            for (int k = 0; k < 3; k++) { src[6 * fc + k] -= force[k]; src[6 * fc + k] += pExplicitQ[k]; }
+            if (isFollower) { /* :128-154 */
+                spin(force, T1);
+                add_block(d, fc, 0, 3, -1.0, T1);
+            }
+        } else { /* fixedValue :339-521 */
+            double* pWCorr = c->DWb + 3 * p;
+            for (int k = 0; k < 3; k++) pWCorr[k] = c->Wb[3 * p + k] - c->WbPrev[3 * p + k]; /* :361 */
+            add_block(d, fc, 0, 0, -1.0 / pDelta, pCQW); /* :368-381 */
+            for (int k = 0; k < 3; k++) tv[k] = pWCorr[k] + SMALL; /* :386-393 "Not sure why" */
+            t_mul_v(pCQW, tv, tv2);
+            for (int k = 0; k < 3; k++) src[6 * fc + k] -= tv2[k] / pDelta;
+            if (isMoment) { /* :400-458 */
+                double invCM[9];
+                t_copy(pCMTheta, T1); t_scale(1.0 / pDelta, T1); t_add(T1, pCMTheta2, T1);
+                t_inv(T1, invCM);
+                t_copy(pCMTheta, T1); t_scale(1.0 / pDelta, T1);
+                t_mul_t(invCM, T1, T2); t_mul_t(pCQTheta, T2, T1); /* CqCt */
+                add_block(d, fc, 0, 3, 1.0, T1);
+                for (int k = 0; k < 3; k++) tv[k] = c->moment[3 * p + k] - pExplicitM[k];
+                t_mul_v(invCM, tv, tv2); t_mul_v(pCQTheta, tv2, tv);
+                for (int k = 0; k < 3; k++) src[6 * fc + k] -= tv[k];
+            } else { /* fixedValue Theta :459-520 */
+                double* pThetaCorr = c->DThetab + 3 * p;
+                for (int k = 0; k < 3; k++) tv[k] = c->Thetab[3 * p + k] - c->ThetabPrev[3 * p + k];
+                t_mul_v(pLambdaf, tv, pThetaCorr); /* :482 */
+                t_mul_v(pCQTheta, pThetaCorr, tv);
+                t_mul_v(pCQDTheta, pThetaCorr, tv2);
+                for (int k = 0; k < 3; k++) src[6 * fc + k] -= tv[k] + tv2[k] / pDelta;
+                add_block(d, fc, 0, 0, -1.0 / pDelta, pCQDTheta);
+            }
+        }
+        for (int k = 0; k < 3; k++) src[6 * fc + k] -= pExplicitQ[k]; /* :524-529 */
+
+        /* ---- Theta equation ---- */
+        if (isMoment) { /* :534-583 */
+            for (int k = 0; k < 3; k++) src[6 * fc + 3 + k] -= c->moment[3 * p + k] - pExplicitM[k];
+        } else { /* :584-677 */
+            double* pThetaCorr = c->DThetab + 3 * p;
+            for (int k = 0; k < 3; k++) tv[k] = c->Thetab[3 * p + k] - c->ThetabPrev[3 * p + k];
+            t_mul_v(pLambdaf, tv, pThetaCorr); /* :606 */
+            add_block(d, fc, 3, 3, -1.0 / pDelta, pCMTheta);
+            t_mul_v(pCMTheta, pThetaCorr, tv);
+            t_mul_v(pCMTheta2, pThetaCorr, tv2);
+            for (int k = 0; k < 3; k++) { src[6 * fc + 3 + k] -= tv[k] / pDelta; src[6 * fc + 3 + k] -= tv2[k]; }
+        }
+        for (int k = 0; k < 3; k++) src[6 * fc + 3 + k] -= pExplicitM[k]; /* :680-685 */
+
+        /* ---- dr x Q term ---- */
+        if (isForce) { /* :694-878 */
+            double invCQW[9], S[9];
+            t_inv(pCQW, invCQW);
+            spin(dRdS, S);
+            for (int k = 0; k < 3; k++) tv[k] = force[k] - pExplicitQ[k];
+            t_mul_v(S, tv, tv2);
+            for (int k = 0; k < 3; k++) src[6 * fc + 3 + k] -= tv2[k] * pDelta; /* :714-730 */
+            if (isMoment) { /* :732-791 */
+                double invCM[9], A[3], Bm[9], iCC[9], t3[3];
+                t_copy(pCMTheta, T1); t_scale(1.0 / pDelta, T1); t_add(T1, pCMTheta2, T1);
+                t_inv(T1, invCM);
+                for (int k = 0; k < 3; k++) tv[k] = c->moment[3 * p + k] - pExplicitM[k];
+                t_mul_v(invCM, tv, A);
+                t_copy(pCMTheta, T1); t_scale(1.0 / pDelta, T1);
+                t_mul_t(invCM, T1, Bm);
+                t_mul_t(invCQW, pCQTheta, iCC);
+                /* src = (CMQTheta & A) - (CMQW & ((invCQW & CQTheta) & A)) */
+                t_mul_v(pCMQTheta, A, tv);
+                t_mul_v(iCC, A, t3); t_mul_v(pCMQW, t3, tv2);
+                for (int k = 0; k < 3; k++) src[6 * fc + 3 + k] -= tv[k] - tv2[k];
+                /* diag = (CMQTheta & B) - (CMQW & ((invCQW & CQTheta) & B)) */
+                t_mul_t(pCMQTheta, Bm, T1);
+                t_mul_t(iCC, Bm, T2); t_mul_t(pCMQW, T2, T2);
+                t_sub(T1, T2, T1);
+                add_block(d, fc, 3, 3, 1.0, T1);
+            }
+            if (isFollower) { /* :793-835 */
+                double SF[9];
+                spin(force, SF);
+                t_mul_t(S, SF, T1);
+                add_block(d, fc, 3, 3, -pDelta, T1);
+            } else { /* :836-877 "else if isA<fixedValue>(Theta)" — true for EVERY Theta class */
+                double* pThetaCorr = c->DThetab + 3 * p;
+                double iCC[9], dwds1[3];
+                for (int k = 0; k < 3; k++) tv[k] = c->Thetab[3 * p + k] - c->ThetabPrev[3 * p + k];
+                t_mul_v(pLambdaf, tv, pThetaCorr); /* :859 (zeroes DTheta_b for a moment patch) */
+                t_mul_t(invCQW, pCQTheta, iCC);
+                t_mul_v(iCC, pThetaCorr, dwds1);
+                for (int k = 0; k < 3; k++) dwds1[k] = -dwds1[k];
+                t_mul_v(pCMQW, dwds1, tv);
+                t_mul_v(pCMQTheta, pThetaCorr, tv2);
+                for (int k = 0; k < 3; k++) src[6 * fc + 3 + k] -= tv[k] + tv2[k];
+            }
+        } else { /* fixedValue W :1034-1175 */
+            double* pWCorr = c->DWb + 3 * p;
+            for (int k = 0; k < 3; k++) pWCorr[k] = c->Wb[3 * p + k] - c->WbPrev[3 * p + k]; /* :1054 */
+            add_block(d, fc, 3, 0, -1.0 / pDelta, pCMQW); /* :1057-1070 */
+            for (int k = 0; k < 3; k++) tv[k] = pWCorr[k] + SMALL;
+            t_mul_v(pCMQW, tv, tv2);
+            for (int k = 0; k < 3; k++) src[6 * fc + 3 + k] -= tv2[k] / pDelta; /* :1073-1087 */
+            if (isMoment) { /* :1089-1138 */
+                double invCM[9], A[3], Bm[9];
+                t_copy(pCMTheta, T1); t_scale(1.0 / pDelta, T1); t_add(T1, pCMTheta2, T1);
+                t_inv(T1, invCM);
+                for (int k = 0; k < 3; k++) tv[k] = c->moment[3 * p + k] - pExplicitM[k];
+                t_mul_v(invCM, tv, A);
+                t_copy(pCMTheta, T1); t_scale(1.0 / pDelta, T1);
+                t_mul_t(invCM, T1, Bm);
+                t_mul_t(pCMQTheta, Bm, T1);
+                add_block(d, fc, 3, 3, 1.0, T1);
+                t_mul_v(pCMQTheta, A, tv);
+                for (int k = 0; k < 3; k++) src[6 * fc + 3 + k] -= tv[k];
+            } else { /* :1139-1174 */
+                double* pThetaCorr = c->DThetab + 3 * p;
+                for (int k = 0; k < 3; k++) tv[k] = c->Thetab[3 * p + k] - c->ThetabPrev[3 * p + k];
+                t_mul_v(pLambdaf, tv, pThetaCorr); /* :1160 */
+                t_mul_v(pCMQTheta, pThetaCorr, tv);
+                for (int k = 0; k < 3; k++) src[6 * fc + 3 + k] -= tv[k];
+            }
+        }
+        for (int k = 0; k < 3; k++) src[6 * fc + 3 + k] -= pExplicitMQ[k]; /* :1178-1187 */
+    }
+}
+
+/* Loads and inertia: Evolve.C:192-209, 274-279, 320-536 (steadyState, Newmark). */
+static void addLoadsAndInertia(bf_ctx* c)
+{
+    double *d = c->d, *src = c->source;
+    const double dt = c->deltaT, beta = c->betaN, gamma = c->gammaN;
+    for (int64_t i = 0; i < c->N; i++) {
+        const int64_t b = c->cellBeam[i];
+        const double L = c->L[i];
+        for (int k = 0; k < 3; k++) {
+            src[6 * i + k] -= c->q[3 * i + k] * L;           /* :193-198 */
+            src[6 * i + k] -= c->weight[3 * b + k] * L;      /* :201-209 rho*L*A*g */
+            src[6 * i + 3 + k] -= c->m[3 * i + k] * L;       /* :274-279 */
+        }
+        if (c->scheme == BF_SCHEME_NEWMARK) {
+            const double ARho = c->ARho[b];
+            double CI[9], Lam[9], LamT[9], tv[3], tv2[3], a1[3], a2[3], T1[9], T2[9], T3[9];
+            t_diag(c->CIRho + 3 * b, CI);
+            t_copy(c->Lambda + 9 * i, Lam);
+            t_T(Lam, LamT);
+            const double *Om = c->Omega + 3 * i, *dOm = c->dotOmega + 3 * i;
+            /* QRho = ARho*L*Accl :372 ; MRho = L*(Lam&(CI&dOm) + Lam&(Om^(CI&Om))) :375-382 */
+            t_mul_v(CI, dOm, tv); t_mul_v(Lam, tv, a1);
+            t_mul_v(CI, Om, tv); cross(Om, tv, tv2); t_mul_v(Lam, tv2, a2);
+            for (int k = 0; k < 3; k++) {
+                src[6 * i + k] += ARho * L * c->Accl[3 * i + k];     /* :411-413 */
+                src[6 * i + 3 + k] += L * (a1[k] + a2[k]);           /* :416-418 */
+            }
+            /* QRhoCoeff = -L*ARho/(dt^2*beta) :462-463 */
+            const double QRhoCoeff = -L * ARho / (dt * dt * beta);
+            for (int k = 0; k < 3; k++) BLK(d, i, k, k) += QRhoCoeff;
+            /* MRhoCoeff :467-488 */
+            double sv[3];
+            for (int k = 0; k < 3; k++) sv[k] = a2[k] + a1[k];
+            spin(sv, T1);                                            /* spinTensor(Lam&(Om^CI Om) + Lam&(CI dOm)) */
+            t_mul_v(CI, Om, tv); t_mul_v(Lam, tv, tv2); spin(tv2, T2); /* spinTensor(Lam & (CI & Om)) */
+            spin(Om, T3);
+            double CILT[9], SCILT[9], LSCILT[9];
+            t_mul_t(CI, LamT, CILT); t_mul_t(T3, CILT, SCILT); t_mul_t(Lam, SCILT, LSCILT);
+            t_sub(T2, LSCILT, T2);
+            t_scale(gamma / (beta * dt), T2);
+            double LCILT[9];
+            t_mul_t(Lam, CILT, LCILT);
+            t_scale(1.0 / (beta * dt * dt), LCILT);
+            double MRhoCoeff[9];
+            t_add(T1, T2, MRhoCoeff);
+            t_sub(MRhoCoeff, LCILT, MRhoCoeff);
+            add_block(d, i, 3, 3, L, MRhoCoeff); /* :524-534 */
+        }
+    }
+}
+
+/* Stand-in for Eigen::SparseLU<COLAMD> (EigenOF.C:285-297): a backward-stable direct
+ * solve of the same matrix — banded LU with partial pivoting (half-bandwidth 11),
+ * one independent chain per beam.  Matrix layout as EigenOF.C:60-175: row block
+ * own[f] gets u[f] at column nei[f]; row block nei[f] gets l[f] at column own[f]. */
+static int solveBanded(bf_ctx* c)
+{
+    enum { KL = 11, KU = 11, LD = 2 * KL + KU + 1 };
+    int rc = BF_OK;
+    int nmax = 0;
+    for (int64_t b = 0; b < c->B; b++) if (c->nSeg[b] > nmax) nmax = c->nSeg[b];
+    const int64_t nmax6 = 6 * (int64_t)nmax;
+    double* ab = malloc(sizeof(double) * LD * nmax6);
+    double* x = malloc(sizeof(double) * nmax6);
+    if (!ab || !x) { free(ab); free(x); return BF_ERR_NOMEM; }
+#define AB(i, j) ab[(KL + KU + (i) - (j)) + (int64_t)(j) * LD]
+    for (int64_t b = 0; b < c->B; b++) {
+        const int n = c->nSeg[b], n6 = 6 * n;
+        memset(ab, 0, sizeof(double) * LD * n6);
+        for (int i = 0; i < n; i++) {
+            const int64_t cell = c->cellStart[b] + i;
+            for (int r = 0; r < 6; r++) {
+                for (int k = 0; k < 6; k++) AB(6 * i + r, 6 * i + k) = BLK(c->d, cell, r, k);
+                x[6 * i + r] = c->source[6 * cell + r];
+            }
+            if (i + 1 < n) {
+                const int64_t f = c->faceStart[b] + i;
+                for (int r = 0; r < 6; r++)
+                    for (int k = 0; k < 6; k++) {
+                        AB(6 * i + r, 6 * (i + 1) + k) = BLK(c->u, f, r, k);
+                        AB(6 * (i + 1) + r, 6 * i + k) = BLK(c->l, f, r, k);
+                    }
+            }
+        }
+        for (int j = 0; j < n6; j++) { /* dgbtf2-style elimination + forward substitution */
+            const int imax = j + KL < n6 - 1 ? j + KL : n6 - 1;
+            int piv = j;
+            double pv = fabs(AB(j, j));
+            for (int i = j + 1; i <= imax; i++)
+                if (fabs(AB(i, j)) > pv) { pv = fabs(AB(i, j)); piv = i; }
+            if (pv == 0.0) {
+                snprintf(c->err, sizeof c->err, "singular block-tridiagonal system in beam %lld (column %d)", (long long)b, j);
+                rc = BF_ERR_INVALID;
+                goto done;
+            }
+            const int jmax = j + KU + KL < n6 - 1 ? j + KU + KL : n6 - 1;
+            if (piv != j) {
+                for (int k = j; k <= jmax; k++) { double t = AB(j, k); AB(j, k) = AB(piv, k); AB(piv, k) = t; }
+                double t = x[j]; x[j] = x[piv]; x[piv] = t;
+            }
+            const double inv = 1.0 / AB(j, j);
+            for (int i = j + 1; i <= imax; i++) {
+                const double m = AB(i, j) * inv;
+                if (m != 0.0) {
+                    for (int k = j + 1; k <= jmax; k++) AB(i, k) -= m * AB(j, k);
+                    x[i] -= m * x[j];
+                }
+            }
+        }
+        for (int j = n6 - 1; j >= 0; j--) { /* back substitution */
+            const int jmax = j + KU + KL < n6 - 1 ? j + KU + KL : n6 - 1;
+            double s = x[j];
+            for (int k = j + 1; k <= jmax; k++) s -= AB(j, k) * x[k];
+            x[j] = s / AB(j, j);
+        }
+        memcpy(c->solVec + 6 * c->cellStart[b], x, sizeof(double) * n6);
+    }
+#undef AB
+done:
+    free(ab); free(x);
+    return rc;
+}
+
+/* PF/momentBeamRotationNR/momentBeamRotationNRFvPatchVectorField.C:183-222 */
+static void evaluateMomentBC(bf_ctx* c, int64_t p)
+{
+    const int64_t f = c->F + p, fc = c->pcell[p];
+    const double delta = 1.0 / c->dc[f];
+    double A[9], invA[9], T1[9], tv[3], a[3], b[3], newDTheta[3], LT[9];
+    t_copy(c->CMTheta + 9 * f, A); t_scale(1.0 / delta, A);
+    t_copy(A, T1);
+    t_add(T1, c->CMTheta2 + 9 * f, T1);
+    t_inv(T1, invA);
+    for (int k = 0; k < 3; k++) tv[k] = c->moment[3 * p + k] - c->explicitM[3 * f + k];
+    t_mul_v(invA, tv, a);
+    t_mul_t(invA, A, T1);
+    t_mul_v(T1, c->DTheta + 3 * fc, b);
+    for (int k = 0; k < 3; k++) newDTheta[k] = a[k] + b[k];
+    t_T(c->Lambdab + 9 * p, LT);
+    t_mul_v(LT, newDTheta, tv);
+    for (int k = 0; k < 3; k++) { c->Thetab[3 * p + k] += tv[k]; c->DThetab[3 * p + k] = newDTheta[k]; }
+}
+
+/* PF/forceBeamDisplacementNR/...C:218-262 (also followerForce, which inherits evaluate)
+ * and PF/linearSpringForceBeamDisplacementNR/...C:219-300 */
+static void evaluateForceBC(bf_ctx* c, int64_t p)
+{
+    const int64_t f = c->F + p, fc = c->pcell[p];
+    const double delta = 1.0 / c->dc[f];
+    double* force = c->force + 3 * p;
+    const double *CQW = c->CQW + 9 * f, *CQTheta = c->CQTheta + 9 * f, *CQDTheta = c->CQDTheta + 9 * f;
+    const double *DThetab = c->DThetab + 3 * p, *DThetac = c->DTheta + 3 * fc, *DWc = c->DW + 3 * fc;
+    double A[9], invA[9], tv[3], t1[3], t2[3], t3[3], newDW[3];
+    t_copy(CQW, A); t_scale(1.0 / delta, A);
+    if (c->wType[p] == BF_W_SPRING) {
+        const double* s = c->springDir + 3 * p;
+        const double k_ = c->springK[p];
+        /* spring force from the boundary W of the previous Newton iterate :226-245 */
+        const double mag = k_ * (c->Wb[3 * p] * s[0] + c->Wb[3 * p + 1] * s[1] + c->Wb[3 * p + 2] * s[2]);
+        for (int k = 0; k < 3; k++) force[k] = -mag * s[k] + c->offsetForce[3 * p + k];
+        double Am[9];
+        t_copy(A, Am);
+        for (int r = 0; r < 3; r++)
+            for (int k = 0; k < 3; k++) Am[3 * r + k] += k_ * (s[r] * s[k]); /* Ks_ :123 */
+        t_inv(Am, invA);
+        for (int k = 0; k < 3; k++) tv[k] = force[k] - c->explicitQ[3 * f + k];
+        t_mul_v(invA, tv, t1);
+        t_mul_v(CQTheta, DThetab, tv); t_mul_v(invA, tv, t2);
+        t_mul_v(A, DWc, tv); t_mul_v(invA, tv, t3);
+        for (int k = 0; k < 3; k++) newDW[k] = t1[k] - t2[k] + t3[k];
+    } else {
+        t_inv(A, invA);
+        for (int k = 0; k < 3; k++) tv[k] = force[k] - c->explicitQ[3 * f + k];
+        t_mul_v(invA, tv, t1);
+        t_mul_v(CQTheta, DThetab, tv); t_mul_v(invA, tv, t2);
+        for (int k = 0; k < 3; k++) tv[k] = DThetab[k] - DThetac[k];
+        t_mul_v(CQDTheta, tv, t3); t_mul_v(invA, t3, t3);
+        for (int k = 0; k < 3; k++) newDW[k] = t1[k] - t2[k] - t3[k] / delta + DWc[k];
+    }
+    for (int k = 0; k < 3; k++) { c->DWb[3 * p + k] = newDW[k]; c->Wb[3 * p + k] += newDW[k]; }
+}
+
+/* Evolve.C:757-923 */
+static void updateSolutionVariables(bf_ctx* c)
+{
+    const int64_t N = c->N, NF = c->NF, B = c->B;
+    const double dt = c->deltaT, beta = c->betaN, gamma = c->gammaN;
+    double LT[9], tv[3];
+    for (int64_t i = 0; i < N; i++) { /* :759-760 (Lambda before its update) */
+        t_T(c->Lambda + 9 * i, LT);
+        t_mul_v(LT, c->DTheta + 3 * i, tv);
+        for (int k = 0; k < 3; k++) c->Theta[3 * i + k] += tv[k];
+    }
+    for (int64_t p = 0; p < 2 * B; p++) /* Theta_.correctBoundaryConditions() :764 */
+        if (c->thType[p] == BF_TH_MOMENT) evaluateMomentBC(c, p);
+    memcpy(c->ThetabPrev, c->Thetab, sizeof(double) * 6 * B); /* storePrevIter :765 */
+    for (int64_t i = 0; i < 3 * N; i++) c->W[i] += c->DW[i]; /* :769 */
+    for (int64_t p = 0; p < 2 * B; p++) /* W_.correctBoundaryConditions() :771 */
+        if (c->wType[p] != BF_W_FIXED) evaluateForceBC(c, p);
+    memcpy(c->WbPrev, c->Wb, sizeof(double) * 6 * B); /* :772 */
+    if (c->scheme == BF_SCHEME_NEWMARK) { /* :782-789 */
+        for (int64_t i = 0; i < 3 * N; i++) {
+            c->U[i] += (1 / dt) * (gamma / beta) * c->DW[i];
+            c->Accl[i] += (1 / (dt * dt * beta)) * c->DW[i];
+        }
+    }
+    /* faces :804-836 */
+    for (int64_t f = 0; f < NF; f++) {
+        double th[3], sg[3], S[9], DT[9], DTT[9], RT[9], LfT[9], T1[9], v1[3], v2[3], R[9];
+        interpolate(c, c->DTheta, c->DThetab, f, th);
+        const double phi = vmag(th) + SMALL; /* :806 */
+        spin(th, S);
+        const double sphi = sin(phi) / phi;
+        t_zero(DT);
+        DT[0] = DT[4] = DT[8] = sphi;
+        const double c2 = (1.0 - sphi) / (phi * phi), c3 = (1.0 - cos(phi)) / (phi * phi);
+        for (int r = 0; r < 3; r++)
+            for (int k = 0; k < 3; k++) DT[3 * r + k] += c2 * (th[r] * th[k]);
+        t_axpy(c3, S, DT); /* :812-822 */
+        snGrad(c, c->DTheta, c->DThetab, f, sg);
+        t_T(DT, DTT);
+        t_mul_v(DTT, sg, v1);
+        t_T(c->refLambdaf + 9 * f, RT);
+        t_T(c->Lambdaf + 9 * f, LfT);
+        t_mul_t(RT, LfT, T1);
+        t_mul_v(T1, v1, v2);
+        for (int k = 0; k < 3; k++) c->K[3 * f + k] += v2[k]; /* :825-830 (old Lambdaf) */
+        rotationMatrix(th, R);
+        t_mul_t(R, c->Lambdaf + 9 * f, c->Lambdaf + 9 * f); /* :833-836 */
+    }
+    /* cell-centre rotation :839-841 (internal + boundary values of the vol field) */
+    for (int64_t i = 0; i < N; i++) {
+        double R[9];
+        rotationMatrix(c->DTheta + 3 * i, R);
+        t_mul_t(R, c->Lambda + 9 * i, c->Lambda + 9 * i);
+    }
+    for (int64_t p = 0; p < 2 * B; p++) {
+        double R[9];
+        rotationMatrix(c->DThetab + 3 * p, R);
+        t_mul_t(R, c->Lambdab + 9 * p, c->Lambdab + 9 * p);
+    }
+    if (c->scheme == BF_SCHEME_NEWMARK) { /* :849-863 (new Lambda) */
+        for (int64_t i = 0; i < N; i++) {
+            t_T(c->Lambda + 9 * i, LT);
+            t_mul_v(LT, c->DTheta + 3 * i, tv);
+            for (int k = 0; k < 3; k++) {
+                c->Omega[3 * i + k] += (gamma / (beta * dt)) * tv[k];
+                c->dotOmega[3 * i + k] += (1 / (beta * dt * dt)) * tv[k];
+            }
+        }
+    }
+    for (int64_t f = 0; f < NF; f++) {
+        double g[3], dRdS[3], v1[3], RT[9], LfT[9], sgW[3], sgT[3], th[3], a[3], b[3];
+        snGrad(c, c->W, c->Wb, f, g);
+        for (int k = 0; k < 3; k++) dRdS[k] = c->dR0Ds[3 * f + k] + g[k]; /* :884 */
+        t_T(c->Lambdaf + 9 * f, LfT);
+        t_mul_v(LfT, dRdS, v1);
+        for (int k = 0; k < 3; k++) v1[k] -= c->dR0Ds[3 * f + k];
+        t_T(c->refLambdaf + 9 * f, RT);
+        t_mul_v(RT, v1, c->Gamma + 3 * f); /* :886 */
+        snGrad(c, c->DW, c->DWb, f, sgW);
+        snGrad(c, c->DTheta, c->DThetab, f, sgT);
+        interpolate(c, c->DTheta, c->DThetab, f, th);
+        t_mul_v(c->CQW + 9 * f, sgW, a);
+        t_mul_v(c->CQTheta + 9 * f, th, b);
+        for (int k = 0; k < 3; k++) c->Q[3 * f + k] = c->explicitQ[3 * f + k] + (a[k] + b[k]); /* :896-903 */
+        t_mul_v(c->CMTheta + 9 * f, sgT, a);
+        t_mul_v(c->CMTheta2 + 9 * f, th, b);
+        for (int k = 0; k < 3; k++) c->M[3 * f + k] = c->explicitM[3 * f + k] + (a[k] + b[k]); /* :906-913 */
+    }
+}
+
+/* One pass of the do{} body of evolve(): Evolve.C:119-632 */
+int bf_newton_iteration(bf_ctx* c, double sumsq[3])
+{
+    const int64_t N = c->N, F = c->F, B = c->B;
+    memset(c->d, 0, sizeof(double) * 36 * N);
+    memset(c->u, 0, sizeof(double) * 36 * F);
+    memset(c->l, 0, sizeof(double) * 36 * F);
+    memset(c->source, 0, sizeof(double) * 6 * N);
+    memset(c->solVec, 0, sizeof(double) * 6 * N);
+
+    /* W_/Theta_.boundaryFieldRef().updateCoeffs() :156-157 */
+    for (int64_t p = 0; p < 2 * B; p++) {
+        if (c->wType[p] == BF_W_FIXED) memcpy(c->Wb + 3 * p, c->wPresc + 3 * p, 24);
+        if (c->thType[p] == BF_TH_FIXED) memcpy(c->Thetab + 3 * p, c->thPresc + 3 * p, 24);
+        if (c->wType[p] == BF_W_FOLLOWER) /* PF/followerForce...C:183-265: force = Lambdaf_b . F_material */
+            t_mul_v(c->Lambdaf + 9 * (F + p), c->followerForce + 3 * p, c->force + 3 * p);
+    }
+    updateEqnCoefficients(c); /* :163 */
+    if (c->scheme == BF_SCHEME_NEWMARK && c->iOuterCorr == 0) { /* :167-186 (old == current at step start) */
+        const double dt = c->deltaT, beta = c->betaN, gamma = c->gammaN;
+        for (int64_t i = 0; i < 3 * N; i++) {
+            const double Uo = c->U[i], Ao = c->Accl[i], Oo = c->Omega[i], dOo = c->dotOmega[i];
+            c->Accl[i] = -(1 / (dt * beta)) * Uo - (0.5 / beta - 1) * Ao;
+            c->U[i] = Uo + dt * ((1 - gamma) * Ao + gamma * c->Accl[i]);
+            c->dotOmega[i] = -(1 / (dt * beta)) * Oo - (0.5 / beta - 1) * dOo;
+            c->Omega[i] = Oo + dt * ((1 - gamma) * dOo + gamma * c->dotOmega[i]);
+        }
+    }
+    assembleMatrixCoefficients(c); /* :190 */
+    assembleBoundaryConditions(c); /* Matrix.C:474 */
+    addLoadsAndInertia(c);         /* :192-536 */
+
+    double res = 0; /* EigenOF.C:253-282 with x0 = 0: ||b||^2 */
+    for (int64_t i = 0; i < 6 * N; i++) res += c->source[i] * c->source[i];
+    int rc = solveBanded(c); /* :588 */
+    if (rc) return rc;
+    for (int64_t i = 0; i < N; i++) /* :596-608 */
+        for (int k = 0; k < 3; k++) {
+            c->DW[3 * i + k] = c->solVec[6 * i + k];
+            c->DTheta[3 * i + k] = c->solVec[6 * i + 3 + k];
+        }
+    updateSolutionVariables(c); /* :615 */
+    double dx = 0, xn = 0;
+    for (int64_t i = 0; i < 6 * N; i++) dx += c->solVec[i] * c->solVec[i]; /* :618 */
+    for (int64_t i = 0; i < 3 * N; i++) xn += c->W[i] * c->W[i];
+    for (int64_t i = 0; i < 3 * N; i++) xn += c->Theta[i] * c->Theta[i]; /* :621-626 */
+    sumsq[0] = res; sumsq[1] = dx; sumsq[2] = xn;
+    c->iOuterCorr++;
+    return BF_OK;
+}
+
+/* Evolve.C:55-670 with checkConvergence :926-1026 */
+int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
+{
+    if (!tol || !out) { snprintf(c->err, sizeof c->err, "bf_evolve: null argument"); return BF_ERR_INVALID; }
+    double initialResidualNorm = 1, currentResidualNorm = GREAT, deltaXNorm = GREAT, XNorm = GREAT;
+    memset(out, 0, sizeof *out);
+    c->iOuterCorr = 0;
+    int status = BF_OK;
+    for (;;) {
+        double s[3];
+        const int iteration = c->iOuterCorr; /* value passed as iOuterCorr()++ */
+        int rc = bf_newton_iteration(c, s);
+        if (rc) { out->status = rc; return rc; }
+        if (c->reducer && c->reducer(s, 3, c->reducerUser)) {
+            snprintf(c->err, sizeof c->err, "norm reducer failed");
+            out->status = BF_ERR_COMM;
+            return BF_ERR_COMM;
+        }
+        currentResidualNorm = sqrt(s[0]);
+        deltaXNorm = sqrt(s[1]);
+        XNorm = sqrt(s[2]);
+        if (iteration == 0) initialResidualNorm = currentResidualNorm;
+        if (currentResidualNorm <= tol->absoluteTol) break;                       /* 1 */
+        if (currentResidualNorm <= tol->residualTol * initialResidualNorm) break; /* 2 */
+        if (deltaXNorm <= tol->solutionTol * XNorm) break;                        /* 3 */
+        if (currentResidualNorm >= tol->divergenceTol * initialResidualNorm && iteration > 1) {
+            snprintf(c->err, sizeof c->err, "Iteration %d: Diverged - Residual grew excessively.", iteration);
+            status = BF_DIVERGED;
+            break;
+        }
+        if (iteration >= tol->nCorrectors) {
+            snprintf(c->err, sizeof c->err, "Iteration %d: Failed - Maximum iterations reached.", iteration);
+            status = BF_MAXITER;
+            break;
+        }
+    }
+    out->nIter = c->iOuterCorr;
+    out->status = status;
+    out->initialResidualNorm = initialResidualNorm;
+    out->currentResidualNorm = currentResidualNorm;
+    out->deltaXNorm = deltaXNorm;
+    out->xNorm = XNorm;
+    return status;
+}
+
+/* ---- test-only accessors (not part of beamgpu.h) -------------------------- */
+/* Block system of the last iteration, reference layout: d [N*36], l/u [F*36], source/x [N*6]. */
+int oracle_get_system(bf_ctx* c, double* d, double* l, double* u, double* source, double* x)
+{
+    if (d) memcpy(d, c->d, sizeof(double) * 36 * c->N);
+    if (l) memcpy(l, c->l, sizeof(double) * 36 * c->F);
+    if (u) memcpy(u, c->u, sizeof(double) * 36 * c->F);
+    if (source) memcpy(source, c->source, sizeof(double) * 6 * c->N);
+    if (x) memcpy(x, c->solVec, sizeof(double) * 6 * c->N);
+    return BF_OK;
+}
+/* helper functions exposed for unit tests against closed forms */
+void oracle_rotationMatrix(const double* th, double* R) { rotationMatrix(th, R); }
+void oracle_spinTensor(const double* v, double* S) { spin(v, S); }
+void oracle_inv(const double* A, double* O) { t_inv(A, O); }
