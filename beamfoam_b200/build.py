@@ -1,0 +1,53 @@
+"""Builds beamfoam_b200/libbeamgpu.so in-tree with nvcc for sm_100a.
+
+    python -m beamfoam_b200.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU; the built .so travels to the GPU box with the
+repo snapshot (it is git-ignored, not gpurun-ignored).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SOURCES = [os.path.join(HERE, "csrc", "beamgpu.cu")]
+HEADERS = [os.path.join(HERE, "csrc", "beam_kernels.cuh"), os.path.join(HERE, "csrc", "beam_math.cuh"),
+           os.path.join(ROOT, "include", "beamgpu.h")]
+OUTPUT = os.path.join(HERE, "libbeamgpu.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v",
+]
+
+
+def up_to_date() -> bool:
+    if not os.path.exists(OUTPUT):
+        return False
+    t = os.path.getmtime(OUTPUT)
+    return all(os.path.getmtime(f) <= t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return OUTPUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUTPUT] + SOURCES + ["-ldl"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = res.stdout + res.stderr
+    with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if res.returncode != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building libbeamgpu.so")
+    if verbose:
+        print(log)
+    return OUTPUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv)
+    print(OUTPUT)

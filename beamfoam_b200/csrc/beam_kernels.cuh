@@ -1,0 +1,636 @@
+// beam_kernels.cuh — the fused Newton-iteration kernels (FP64, sm_100a).
+//
+// One Newton iteration of coupledTotalLagNewtonRaphsonBeam::evolve() is TWO kernels:
+//
+//   beam_forward  : per beam, left -> right.  For every cell it recomputes the face
+//                   coefficients (updateEqnCoefficients, Evolve.C:673-753), assembles the
+//                   6x6 blocks d, l, u and the source (Matrix.C:55-475, BC.C:64-1190, loads and
+//                   inertia Evolve.C:192-536) IN REGISTERS and immediately performs the
+//                   block-Thomas forward elimination.  d/l/u/source never exist in HBM;
+//                   only uPrime (36) and bPrime (6) per cell are written to scratch.
+//   beam_backward : per beam, right -> left.  Back-substitution, BC evaluate()
+//                   (PF/*: momentBeamRotationNR, forceBeamDisplacementNR, followerForce,
+//                   linearSpring), updateSolutionVariables (Evolve.C:757-923) and the partial
+//                   sums of the three convergence norms (Evolve.C:588,618-626).
+//
+// Mapping: ONE THREAD PER BEAM, 32 beams per warp.  All arrays are "beam-interleaved
+// structure of arrays": element (cell i, component c, beam b) lives at
+// ((i*nc + c)*Bpad + b), so the 32 lanes of a warp read 32 consecutive doubles (256 B,
+// fully coalesced) for every scalar they touch, and the serial block recurrence of each
+// beam runs entirely in one thread's registers with no cross-lane traffic.
+#pragma once
+#include "beam_math.cuh"
+#include <stdint.h>
+
+#define BFK_W_FIXED 0
+#define BFK_W_FORCE 1
+#define BFK_W_FOLLOWER 2
+#define BFK_W_SPRING 3
+#define BFK_TH_FIXED 0
+#define BFK_TH_MOMENT 1
+
+struct BeamParams {
+    int B;        // beams in this context
+    int Bpad;     // padded beam count (leading dimension)
+    int nmax;     // max cells per beam
+    int newmark;  // 0 steadyState, 1 Newmark
+    int first;    // 1 on the first Newton iteration of a time step (Newmark predictor)
+    int storeInc; // keep DW/DTheta cell fields
+    double dt, beta, gamma;
+    // per beam [Bpad]
+    const int* nSeg;
+    const double* dZ;
+    const double* CQ;     // [3][Bpad]
+    const double* CM;     // [3][Bpad]
+    const double* ARho;   // [Bpad]
+    const double* CI;     // [3][Bpad]
+    const double* weight; // [3][Bpad]
+    const double* refL;   // [9][Bpad]
+    const int* wType;     // [2][Bpad]
+    const int* thType;    // [2][Bpad]
+    // cells [nmax][nc][Bpad]
+    double *W, *Th, *Lam, *U, *Ac, *Om, *dOm, *DW, *DTh;
+    const double *q, *m, *Lc; // optional (may be null)
+    // faces [nmax+1][nc][Bpad]: face j of beam b; j=0 left patch, j=nSeg[b] right patch
+    double *Lf, *Gam, *K, *Q, *M;
+    // ends [2][nc][Bpad]
+    double *Wb, *Thb, *Lamb, *DWb, *DThb, *force;
+    const double *wPresc, *thPresc, *follower, *offset, *moment, *springK, *springDir;
+    // block-Thomas scratch
+    double* uP; // [nmax][36][Bpad]
+    double* bP; // [nmax][6][Bpad]
+    // per-block partial sums: [3][gridDim.x]
+    double* partial;
+};
+
+DEV V3 ld3(const double* __restrict__ p, size_t i, size_t s) { return v3(p[i], p[i + s], p[i + 2 * s]); }
+DEV void st3(double* __restrict__ p, size_t i, size_t s, V3 v) { p[i] = v.x; p[i + s] = v.y; p[i + 2 * s] = v.z; }
+DEV M3 ld9(const double* __restrict__ p, size_t i, size_t s)
+{
+    M3 r;
+#pragma unroll
+    for (int k = 0; k < 9; k++) r.a[k] = p[i + k * s];
+    return r;
+}
+DEV void st9(double* __restrict__ p, size_t i, size_t s, const M3& A)
+{
+#pragma unroll
+    for (int k = 0; k < 9; k++) p[i + k * s] = A.a[k];
+}
+
+// Coefficients of one face (updateEqnCoefficients, Evolve.C:673-753), from the PRE-solve state.
+struct FaceCoef {
+    M3 CQW, CQTheta, CMTheta, CMQW, CMQTheta; // CQDTheta == 0 (CTL.C:586-603), CMTheta2 = -spin(M)
+    V3 eQ, eM, eMQ, Mold, t;
+};
+
+// dc = deltaCoeffs of the face; boundary faces get the x2 of Evolve.C:744-752.
+DEV FaceCoef faceCoefficients(const M3& Lf, const M3& refL, V3 CQ, V3 CM, V3 Gam, V3 K, V3 Q, V3 M, V3 t,
+                              double dc, bool boundary)
+{
+    FaceCoef f;
+    const M3 Lm = mul(Lf, refL);               // :678
+    f.CQW = conjDiag(Lm, CQ);                  // :680
+    f.eQ = mul(Lm, cmul(CQ, Gam));             // :682
+    f.eM = mul(Lm, cmul(CM, K));               // :684
+    const M3 SQ = spin(Q);
+    f.CQTheta = mulSpinR(f.CQW, t) - SQ;       // :686-693
+    f.CMTheta = conjDiag(Lm, CM);              // :699
+    f.Mold = M;                                // CMTheta2 = -spin(M) :703
+    const M3 SC = mulSpinL(t, f.CQW);
+    const double h = boundary ? 1.0 / dc : 0.5 / dc; // 0.5*(..)/deltaCoeffs, x2 on patches
+    f.CMQW = h * (SC - SQ);                    // :706-715
+    f.CMQTheta = h * (mulSpinR(SC, t) - mulSpinL(t, SQ)); // :718-735
+    f.eMQ = h * cross(t, f.eQ);                // :737-741
+    f.t = t;
+    return f;
+}
+
+DEV void addBlk(double (&D)[6][6], int r0, int c0, double s, const M3& T)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) D[r0 + r][c0 + c] += s * T.a[3 * r + c];
+}
+DEV void subV(double (&b)[6], int r0, V3 v) { b[r0] -= v.x; b[r0 + 1] -= v.y; b[r0 + 2] -= v.z; }
+DEV void addV(double (&b)[6], int r0, V3 v) { b[r0] += v.x; b[r0 + 1] += v.y; b[r0 + 2] += v.z; }
+
+// End-patch values a thread needs for one end of its beam.
+struct EndBC {
+    int wType, thType;
+    V3 Wb, Thb;        // stored patch values (== prevIter at iteration start)
+    V3 wPresc, thPresc;
+    V3 force;          // force() as seen by the assembly of this iteration
+    V3 moment;
+};
+
+DEV EndBC loadEnd(const BeamParams& p, int end, int b, const M3& Lfb)
+{
+    const size_t s = p.Bpad;
+    EndBC e;
+    e.wType = p.wType[end * s + b];
+    e.thType = p.thType[end * s + b];
+    const size_t i3 = (size_t)end * 3 * s + b;
+    e.Wb = ld3(p.Wb, i3, s);
+    e.Thb = ld3(p.Thb, i3, s);
+    e.wPresc = ld3(p.wPresc, i3, s);
+    e.thPresc = ld3(p.thPresc, i3, s);
+    e.moment = ld3(p.moment, i3, s);
+    if (e.wType == BFK_W_FOLLOWER) // followerForce...C:183-265: force = Lambdaf_b . F_material, every iteration
+        e.force = mul(Lfb, ld3(p.follower, i3, s));
+    else
+        e.force = ld3(p.force, i3, s);
+    return e;
+}
+
+// assembleBoundaryConditions for ONE end patch (BC.C:64-1190) into the diagonal block D and
+// the source b of its face cell.  pDelta = 1/deltaCoeffs_b.
+DEV void bcClosure(double (&D)[6][6], double (&b)[6], const FaceCoef& f, const EndBC& e, const M3& Lfb,
+                   double pDelta)
+{
+    const double ipd = 1.0 / pDelta;
+    const bool isForce = e.wType != BFK_W_FIXED;
+    const bool isFollower = e.wType == BFK_W_FOLLOWER;
+    const bool isMoment = e.thType == BFK_TH_MOMENT;
+    const M3 CMTheta2 = -1.0 * spin(f.Mold);
+    // Lambdaf_b & (pTheta - pThetaPrev).  Only a fixed-Theta patch changes its value in
+    // updateCoeffs(); for a moment patch pTheta == pThetaPrev (storePrevIter, Evolve.C:764-765).
+    const V3 pThetaCorr = isMoment ? v3(0, 0, 0) : mul(Lfb, e.thPresc - e.Thb);
+    const V3 pWCorr = e.wPresc - e.Wb;                 // pW - pWPrev
+    M3 invCM, Bm;
+    V3 A = v3(0, 0, 0);
+    if (isMoment) {
+        invCM = inv(ipd * f.CMTheta + CMTheta2);
+        A = mul(invCM, e.moment - f.eM);
+        Bm = mul(invCM, ipd * f.CMTheta);
+    }
+    // ---- W equation
+    if (isForce) { // :102-155
+        subV(b, 0, e.force);
+        addV(b, 0, f.eQ);
+        if (isFollower) addBlk(D, 0, 3, -1.0, spin(e.force)); // :128-154
+    } else { // :339-521
+        addBlk(D, 0, 0, -ipd, f.CQW);
+        const V3 wc = v3(pWCorr.x + BF_SMALL, pWCorr.y + BF_SMALL, pWCorr.z + BF_SMALL); // :386-393
+        subV(b, 0, ipd * mul(f.CQW, wc));
+        if (isMoment) { // :400-458
+            addBlk(D, 0, 3, 1.0, mul(f.CQTheta, Bm));
+            subV(b, 0, mul(f.CQTheta, A));
+        } else { // :459-520 (CQDTheta == 0)
+            subV(b, 0, mul(f.CQTheta, pThetaCorr));
+        }
+    }
+    subV(b, 0, f.eQ); // :524-529
+    // ---- Theta equation
+    if (isMoment) { // :534-583
+        subV(b, 3, e.moment - f.eM);
+    } else { // :584-677
+        addBlk(D, 3, 3, -ipd, f.CMTheta);
+        subV(b, 3, ipd * mul(f.CMTheta, pThetaCorr));
+        subV(b, 3, mul(CMTheta2, pThetaCorr));
+    }
+    subV(b, 3, f.eM); // :680-685
+    // ---- dr x Q term
+    if (isForce) { // :694-878
+        subV(b, 3, pDelta * cross(f.t, e.force - f.eQ)); // :714-730
+        M3 iCC;
+        if (isMoment || !isFollower) iCC = mul(inv(f.CQW), f.CQTheta);
+        if (isMoment) { // :732-791
+            subV(b, 3, mul(f.CMQTheta, A) - mul(f.CMQW, mul(iCC, A)));
+            addBlk(D, 3, 3, 1.0, mul(f.CMQTheta, Bm) - mul(f.CMQW, mul(iCC, Bm)));
+        }
+        if (isFollower) { // :793-835
+            addBlk(D, 3, 3, -pDelta, mulSpinL(f.t, spin(e.force)));
+        } else { // :836-877 — runs for every Theta class (all derive from fixedValue)
+            const V3 dwds1 = -mul(iCC, pThetaCorr);
+            subV(b, 3, mul(f.CMQW, dwds1) + mul(f.CMQTheta, pThetaCorr));
+        }
+    } else { // :1034-1175
+        addBlk(D, 3, 0, -ipd, f.CMQW);
+        const V3 wc = v3(pWCorr.x + BF_SMALL, pWCorr.y + BF_SMALL, pWCorr.z + BF_SMALL);
+        subV(b, 3, ipd * mul(f.CMQW, wc));
+        if (isMoment) { // :1089-1138
+            addBlk(D, 3, 3, 1.0, mul(f.CMQTheta, Bm));
+            subV(b, 3, mul(f.CMQTheta, A));
+        } else { // :1139-1174
+            subV(b, 3, mul(f.CMQTheta, pThetaCorr));
+        }
+    }
+    subV(b, 3, f.eMQ); // :1178-1187
+}
+
+// Block reduction of up to 3 values; thread 0 writes partial[k*gridDim.x + blockIdx.x].
+template <int NV>
+DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slot0)
+{
+    __shared__ double sm[NV][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+        if (lane == 0) sm[k][wid] = v[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double x = lane < nw ? sm[k][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            if (lane == 0) partial[(size_t)(slot0 + k) * gridDim.x + blockIdx.x] = x;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// forward: coefficients + assembly + block-Thomas elimination
+// ---------------------------------------------------------------------------
+template <bool NEWMARK>
+__global__ void __launch_bounds__(128) beam_forward(const BeamParams p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t s = p.Bpad;
+    double res = 0.0;
+    if (b < p.B) {
+        const int n = p.nSeg[b];
+        const double dZ = p.dZ[b];
+        const double dcI = 1.0 / dZ, dcB = 2.0 / dZ; // mesh().deltaCoeffs()
+        const double pDelta = 1.0 / dcB;
+        const V3 CQ = ld3(p.CQ, b, s), CM = ld3(p.CM, b, s), wgt = ld3(p.weight, b, s);
+        const M3 refL = ld9(p.refL, b, s);
+        const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]); // refLambdaf & (1 0 0)
+        double ARho = 0.0;
+        V3 CI = v3(0, 0, 0);
+        if (NEWMARK) { ARho = p.ARho[b]; CI = ld3(p.CI, b, s); }
+        const double dt = p.dt, beta = p.beta, gamma = p.gamma;
+
+        double Dc[6][6], sc[6], lb[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            sc[r] = 0.0; lb[r] = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) Dc[r][c] = 0.0;
+        }
+        V3 Wi = ld3(p.W, b, s);
+        { // left patch: face 0, outward normal -x  => dR0Ds = -dR0 (CTL.C:987-994)
+            const M3 Lfb = ld9(p.Lf, b, s);
+            const EndBC e = loadEnd(p, 0, b, Lfb);
+            const V3 Wb = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb; // after updateCoeffs()
+            const V3 t = dcB * (Wb - Wi) - dR0;
+            const FaceCoef f = faceCoefficients(Lfb, refL, CQ, CM, ld3(p.Gam, b, s), ld3(p.K, b, s),
+                                                ld3(p.Q, b, s), ld3(p.M, b, s), t, dcB, true);
+            bcClosure(Dc, sc, f, e, Lfb, pDelta);
+        }
+        for (int i = 0; i < n; i++) {
+            double D[6][6], R[6][7];
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) D[r][c] = Dc[r][c];
+#pragma unroll
+                for (int c = 0; c < 6; c++) R[r][c] = 0.0;
+            }
+            double src[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) src[r] = sc[r];
+            const size_t j = (size_t)(i + 1);
+            const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
+            const bool last = (i == n - 1);
+            M3 Pm, Qt, Rm, S1, S23p, S23m; // face tensors for the carry (internal faces only)
+            V3 Wn = Wi, eQ, eM, eMQ;
+            if (!last) {
+                Wn = ld3(p.W, j * 3 * s + b, s);
+                const V3 t = dR0 + dcI * (Wn - Wi);
+                const FaceCoef f = faceCoefficients(ld9(p.Lf, f9, s), refL, CQ, CM, ld3(p.Gam, f3, s),
+                                                    ld3(p.K, f3, s), ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcI, false);
+                // Matrix.C:84-470 with w = 0.5, a = 1/deltaf
+                Pm = dcI * f.CQW;
+                Qt = 0.5 * f.CQTheta;
+                Rm = dcI * f.CMQW;
+                S1 = dcI * f.CMTheta;
+                const M3 S2 = -0.5 * spin(f.Mold); // 0.5*CMTheta2
+                const M3 S3 = 0.5 * f.CMQTheta;
+                S23p = S3 + S2;
+                S23m = S3 - S2;
+                eQ = f.eQ; eM = f.eM; eMQ = f.eMQ;
+                // own part of d and u
+                addBlk(D, 0, 0, -1.0, Pm);
+                addBlk(D, 0, 3, 1.0, Qt);
+                addBlk(D, 3, 0, -1.0, Rm);
+                addBlk(D, 3, 3, -1.0, S1);
+                addBlk(D, 3, 3, 1.0, S23p);
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        R[r][c] = Pm.a[3 * r + c];
+                        R[r][3 + c] = Qt.a[3 * r + c];
+                        R[3 + r][c] = Rm.a[3 * r + c];
+                        R[3 + r][3 + c] = S1.a[3 * r + c] + S23p.a[3 * r + c];
+                    }
+                subV(src, 0, eQ);
+                subV(src, 3, eM + eMQ);
+            } else { // right patch: face n
+                const M3 Lfb = ld9(p.Lf, f9, s);
+                const EndBC e = loadEnd(p, 1, b, Lfb);
+                const V3 Wb = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb;
+                const V3 t = dR0 + dcB * (Wb - Wi);
+                const FaceCoef f = faceCoefficients(Lfb, refL, CQ, CM, ld3(p.Gam, f3, s), ld3(p.K, f3, s),
+                                                    ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcB, true);
+                bcClosure(D, src, f, e, Lfb, pDelta);
+            }
+            // loads: Evolve.C:193-209,274-279
+            const size_t c3 = (size_t)i * 3 * s + b;
+            const double Lcell = p.Lc ? p.Lc[(size_t)i * s + b] : dZ;
+            if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, s));
+            subV(src, 0, Lcell * wgt);
+            if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, s));
+            if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
+                const M3 Lm = ld9(p.Lam, (size_t)i * 9 * s + b, s);
+                V3 Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
+                if (p.first) {
+                    const V3 Uo = ld3(p.U, c3, s);
+                    const double k1 = 1.0 / (dt * beta), k2 = 0.5 / beta - 1.0;
+                    const V3 Ao = Ac, Oo = Om, dOo = dOm;
+                    Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
+                    dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
+                    Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
+                }
+                const V3 CIOm = cmul(CI, Om);
+                const V3 a1 = mul(Lm, cmul(CI, dOm));      // Lambda & (CIRho & dotOmega)
+                const V3 a2 = mul(Lm, cross(Om, CIOm));     // Lambda & (Omega ^ (CIRho & Omega))
+                addV(src, 0, (ARho * Lcell) * Ac);
+                addV(src, 3, Lcell * (a1 + a2));
+                const double QRhoCoeff = -Lcell * ARho / (dt * dt * beta);
+                D[0][0] += QRhoCoeff; D[1][1] += QRhoCoeff; D[2][2] += QRhoCoeff;
+                // MRhoCoeff :467-488
+                const M3 LCL = conjDiag(Lm, CI);            // Lambda & (CIRho & Lambda.T())
+                const M3 T2 = spin(mul(Lm, CIOm)) - mul(Lm, mulSpinL(Om, diagMulT(CI, Lm)));
+                const M3 MR = spin(a2 + a1) + (gamma / (beta * dt)) * T2 - (1.0 / (beta * dt * dt)) * LCL;
+                addBlk(D, 3, 3, Lcell, MR);
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) res += src[r] * src[r];
+#pragma unroll
+            for (int r = 0; r < 6; r++) R[r][6] = src[r] - lb[r];
+            solve6<7>(D, R); // R = D'^{-1} [u | b']
+            const size_t u0 = (size_t)i * 36 * s + b, b0 = (size_t)i * 6 * s + b;
+            if (!last) {
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int c = 0; c < 6; c++) p.uP[u0 + (size_t)(6 * r + c) * s] = R[r][c];
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) p.bP[b0 + (size_t)r * s] = R[r][6];
+            if (!last) {
+                // carry for cell i+1: nei part of d minus l&uPrime; l&bPrime; nei part of source
+                // l = [[P, -Qt], [-R, S1 + S23m]] ; d_nei = [[-P, -Qt], [R, -S1 + S23m]]
+                double l[6][6];
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        l[r][c] = Pm.a[3 * r + c];
+                        l[r][3 + c] = -Qt.a[3 * r + c];
+                        l[3 + r][c] = -Rm.a[3 * r + c];
+                        l[3 + r][3 + c] = S1.a[3 * r + c] + S23m.a[3 * r + c];
+                    }
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+#pragma unroll
+                    for (int c = 0; c < 7; c++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 6; k++) acc += l[r][k] * R[k][c];
+                        if (c < 6) Dc[r][c] = -acc; else lb[r] = acc;
+                    }
+                }
+                addBlk(Dc, 0, 0, -1.0, Pm);
+                addBlk(Dc, 0, 3, -1.0, Qt);
+                addBlk(Dc, 3, 0, 1.0, Rm);
+                addBlk(Dc, 3, 3, -1.0, S1);
+                addBlk(Dc, 3, 3, 1.0, S23m);
+                sc[0] = eQ.x; sc[1] = eQ.y; sc[2] = eQ.z;
+                sc[3] = eM.x - eMQ.x; sc[4] = eM.y - eMQ.y; sc[5] = eM.z - eMQ.z;
+                Wi = Wn;
+            }
+        }
+    }
+    double v[1] = {res};
+    blockReduceStore<1>(v, p.partial, 0);
+}
+
+// ---------------------------------------------------------------------------
+// backward: back-substitution + BC evaluate + updateSolutionVariables + norms
+// ---------------------------------------------------------------------------
+struct FaceState {
+    M3 Lf;
+    V3 Gam, K, Q, M;
+};
+
+// Update of one face (Evolve.C:804-836, 881-913).  (A) = owner / face cell, (B) = neighbour /
+// patch value.  f holds the PRE-solve coefficients; tnew = dR0Ds + snGrad(W_new).
+DEV FaceState updateFace(const FaceCoef& f, const M3& LfOld, const M3& refL, V3 Kold, V3 dR0s, V3 tnew,
+                         V3 DWa, V3 DWb, V3 DTa, V3 DTb, double dc, bool boundary)
+{
+    FaceState o;
+    const V3 DThf = boundary ? DTb : v3(0.5 * DTa.x + 0.5 * DTb.x, 0.5 * DTa.y + 0.5 * DTb.y, 0.5 * DTa.z + 0.5 * DTb.z);
+    const V3 sgT = dc * (DTb - DTa), sgW = dc * (DWb - DWa);
+    // K += (refLambdaf.T() & Lambdaf.T()) & (DT.T() & snGrad(DTheta))   :825-830 (old Lambdaf)
+    o.K = Kold + mulT(refL, mulT(LfOld, tangentT(DThf, sgT)));
+    o.Lf = mul(rotationMatrix(DThf), LfOld); // :833-836
+    // Gamma = refLambdaf.T() & ((Lambdaf.T() & dRdS) - dR0Ds)           :881-887 (new W, new Lambdaf)
+    o.Gam = mulT(refL, mulT(o.Lf, tnew) - dR0s);
+    // Q = explicitQ + CQW & snGrad(DW) + CQTheta & interpolate(DTheta)  :896-903
+    o.Q = f.eQ + (mul(f.CQW, sgW) + mul(f.CQTheta, DThf));
+    // M = explicitM + CMTheta & snGrad(DTheta) + CMTheta2 & interpolate(DTheta) :906-913
+    o.M = f.eM + (mul(f.CMTheta, sgT) - cross(f.Mold, DThf));
+    return o;
+}
+
+// correctBoundaryConditions() for ONE end patch followed by the update of its boundary face.
+// Theta BC first, then W BC (Evolve.C:764 then :771), so the W evaluate sees the new DTheta_b.
+//   momentBeamRotationNR::evaluate        PF/momentBeamRotationNR/...C:183-222
+//   forceBeamDisplacementNR::evaluate     PF/forceBeamDisplacementNR/...C:218-262 (also followerForce)
+//   linearSpringForce...::evaluate        PF/linearSpringForceBeamDisplacementNR/...C:219-300
+//   fixedValue / fixedRotation / fixedDisplacement: value from updateCoeffs(); DW_b, DTheta_b are the
+//   pWCorr / pThetaCorr written by assembleBoundaryConditions (BC.C:359-361, 478-482).
+// dR0s is dR0Ds of this patch (sign-flipped on the left patch).
+DEV FaceState patchUpdate(const BeamParams& p, int end, int b, const M3& LfOld, const M3& refL, V3 CQ, V3 CM,
+                          V3 Gam, V3 Kold, V3 Q, V3 M, V3 dR0s, V3 WoldC, V3 WnewC, V3 DWc, V3 DTc, double dcB,
+                          double delta)
+{
+    const size_t s = p.Bpad;
+    const size_t i3 = (size_t)end * 3 * s + b, i9 = (size_t)end * 9 * s + b;
+    const EndBC e = loadEnd(p, end, b, LfOld);
+    const V3 WbOld = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb;
+    const V3 t = dR0s + dcB * (WbOld - WoldC);
+    const FaceCoef f = faceCoefficients(LfOld, refL, CQ, CM, Gam, Kold, Q, M, t, dcB, true);
+    const double ipd = 1.0 / delta;
+    const M3 LambOld = ld9(p.Lamb, i9, s);
+    V3 DTb, ThbNew;
+    if (e.thType == BFK_TH_MOMENT) {
+        const M3 A = ipd * f.CMTheta;
+        const M3 invA = inv(A - spin(f.Mold)); // CMTheta/delta + CMTheta2
+        DTb = mul(invA, e.moment - f.eM) + mul(mul(invA, A), DTc);
+        ThbNew = e.Thb + mulT(LambOld, DTb);
+    } else {
+        DTb = mul(LfOld, e.thPresc - e.Thb);
+        ThbNew = e.thPresc;
+    }
+    V3 DWb, WbNew;
+    if (e.wType == BFK_W_FIXED) {
+        DWb = e.wPresc - e.Wb;
+        WbNew = e.wPresc;
+    } else {
+        M3 A = ipd * f.CQW;
+        V3 force = e.force;
+        if (e.wType == BFK_W_SPRING) {
+            const V3 sd = ld3(p.springDir, i3, s);
+            const double k_ = p.springK[(size_t)end * s + b];
+            const double fm = k_ * dot(e.Wb, sd); // from the boundary W of the previous iterate
+            force = ld3(p.offset, i3, s) - fm * sd;
+            st3(p.force, i3, s, force);
+            M3 Am = A;
+            Am.a[0] += k_ * (sd.x * sd.x); Am.a[1] += k_ * (sd.x * sd.y); Am.a[2] += k_ * (sd.x * sd.z);
+            Am.a[3] += k_ * (sd.y * sd.x); Am.a[4] += k_ * (sd.y * sd.y); Am.a[5] += k_ * (sd.y * sd.z);
+            Am.a[6] += k_ * (sd.z * sd.x); Am.a[7] += k_ * (sd.z * sd.y); Am.a[8] += k_ * (sd.z * sd.z);
+            const M3 invA = inv(Am);
+            DWb = mul(invA, force - f.eQ) - mul(invA, mul(f.CQTheta, DTb)) + mul(invA, mul(A, DWc));
+        } else {
+            const M3 invA = inv(A);
+            DWb = mul(invA, force - f.eQ) - mul(invA, mul(f.CQTheta, DTb)) + DWc; // CQDTheta == 0
+        }
+        WbNew = e.Wb + DWb;
+    }
+    st3(p.Wb, i3, s, WbNew);
+    st3(p.Thb, i3, s, ThbNew);
+    st3(p.DWb, i3, s, DWb);
+    st3(p.DThb, i3, s, DTb);
+    st9(p.Lamb, i9, s, mul(rotationMatrix(DTb), LambOld)); // Lambda_ = DLambda & Lambda_ on the patch
+    const V3 tnew = dR0s + dcB * (WbNew - WnewC);
+    return updateFace(f, LfOld, refL, Kold, dR0s, tnew, DWc, DWb, DTc, DTb, dcB, true);
+}
+
+template <bool NEWMARK>
+__global__ void __launch_bounds__(128) beam_backward(const BeamParams p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t s = p.Bpad;
+    double dx2 = 0.0, x2 = 0.0;
+    if (b < p.B) {
+        const int n = p.nSeg[b];
+        const double dZ = p.dZ[b];
+        const double dcI = 1.0 / dZ, dcB = 2.0 / dZ;
+        const double delta = 1.0 / dcB;
+        const V3 CQ = ld3(p.CQ, b, s), CM = ld3(p.CM, b, s);
+        const M3 refL = ld9(p.refL, b, s);
+        const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
+        const double dt = p.dt, beta = p.beta, gamma = p.gamma;
+
+        V3 xWn = v3(0, 0, 0), xTn = v3(0, 0, 0); // x_{i+1}
+        V3 WoldN = v3(0, 0, 0), WnewN = v3(0, 0, 0);
+        for (int i = n - 1; i >= 0; i--) {
+            // ---- back substitution: x_i = bPrime_i - uPrime_i & x_{i+1}
+            const size_t u0 = (size_t)i * 36 * s + b, b0 = (size_t)i * 6 * s + b;
+            double x[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) x[r] = p.bP[b0 + (size_t)r * s];
+            if (i < n - 1) {
+                const double xn[6] = {xWn.x, xWn.y, xWn.z, xTn.x, xTn.y, xTn.z};
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; c++) acc += p.uP[u0 + (size_t)(6 * r + c) * s] * xn[c];
+                    x[r] -= acc;
+                }
+            }
+            const V3 DW = v3(x[0], x[1], x[2]), DT = v3(x[3], x[4], x[5]);
+#pragma unroll
+            for (int r = 0; r < 6; r++) dx2 += x[r] * x[r];
+            // ---- cell i: Evolve.C:759-802, 839-863
+            const size_t c3 = (size_t)i * 3 * s + b, c9 = (size_t)i * 9 * s + b;
+            const V3 Wold = ld3(p.W, c3, s);
+            const M3 LmOld = ld9(p.Lam, c9, s);
+            const V3 Thn = ld3(p.Th, c3, s) + mulT(LmOld, DT); // :759 (Lambda before its update)
+            const V3 Wnew = Wold + DW;                          // :769
+            const M3 LmNew = mul(rotationMatrix(DT), LmOld);    // :839-841
+            st3(p.Th, c3, s, Thn);
+            st3(p.W, c3, s, Wnew);
+            st9(p.Lam, c9, s, LmNew);
+            x2 += dot(Wnew, Wnew) + dot(Thn, Thn);
+            if (p.storeInc) { st3(p.DW, c3, s, DW); st3(p.DTh, c3, s, DT); }
+            if (NEWMARK) {
+                V3 U = ld3(p.U, c3, s), Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
+                if (p.first) { // predictor :167-186
+                    const double k1 = 1.0 / (dt * beta), k2 = 0.5 / beta - 1.0;
+                    const V3 Uo = U, Ao = Ac, Oo = Om, dOo = dOm;
+                    Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
+                    U = Uo + dt * ((1.0 - gamma) * Ao + gamma * Ac);
+                    dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
+                    Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
+                }
+                U = U + ((1.0 / dt) * (gamma / beta)) * DW;           // :785
+                Ac = Ac + (1.0 / (dt * dt * beta)) * DW;              // :788
+                const V3 w = mulT(LmNew, DT);                          // new Lambda :853-862
+                Om = Om + (gamma / (beta * dt)) * w;
+                dOm = dOm + (1.0 / (beta * dt * dt)) * w;
+                st3(p.U, c3, s, U); st3(p.Ac, c3, s, Ac); st3(p.Om, c3, s, Om); st3(p.dOm, c3, s, dOm);
+            }
+            // ---- face j = i+1
+            {
+                const size_t j = (size_t)(i + 1);
+                const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
+                const M3 LfOld = ld9(p.Lf, f9, s);
+                const V3 Kold = ld3(p.K, f3, s);
+                FaceState o;
+                if (i == n - 1) { // right patch
+                    o = patchUpdate(p, 1, b, LfOld, refL, CQ, CM, ld3(p.Gam, f3, s), Kold, ld3(p.Q, f3, s),
+                                    ld3(p.M, f3, s), dR0, Wold, Wnew, DW, DT, dcB, delta);
+                } else {
+                    const V3 t = dR0 + dcI * (WoldN - Wold);
+                    const FaceCoef f = faceCoefficients(LfOld, refL, CQ, CM, ld3(p.Gam, f3, s), Kold, ld3(p.Q, f3, s),
+                                                        ld3(p.M, f3, s), t, dcI, false);
+                    const V3 tnew = dR0 + dcI * (WnewN - Wnew);
+                    o = updateFace(f, LfOld, refL, Kold, dR0, tnew, DW, xWn, DT, xTn, dcI, false);
+                }
+                st9(p.Lf, f9, s, o.Lf);
+                st3(p.Gam, f3, s, o.Gam); st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
+            }
+            if (i == 0) { // left patch: face 0
+                const M3 LfOld = ld9(p.Lf, b, s);
+                const V3 Kold = ld3(p.K, b, s);
+                const FaceState o = patchUpdate(p, 0, b, LfOld, refL, CQ, CM, ld3(p.Gam, b, s), Kold, ld3(p.Q, b, s),
+                                                ld3(p.M, b, s), -dR0, Wold, Wnew, DW, DT, dcB, delta);
+                st9(p.Lf, b, s, o.Lf);
+                st3(p.Gam, b, s, o.Gam); st3(p.K, b, s, o.K); st3(p.Q, b, s, o.Q); st3(p.M, b, s, o.M);
+            }
+            xWn = DW; xTn = DT; WoldN = Wold; WnewN = Wnew;
+        }
+    }
+    double v[2] = {dx2, x2};
+    blockReduceStore<2>(v, p.partial, 1);
+}
+
+// Deterministic final reduction of the per-block partial sums (fixed order).
+__global__ void beam_reduce_partials(const double* __restrict__ partial, int nBlocks, double* __restrict__ out)
+{
+    __shared__ double sm[3][256];
+    for (int k = 0; k < 3; k++) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < nBlocks; i += blockDim.x) acc += partial[(size_t)k * nBlocks + i];
+        sm[k][threadIdx.x] = acc;
+    }
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+            for (int k = 0; k < 3; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) out[threadIdx.x] = sm[threadIdx.x][0];
+}

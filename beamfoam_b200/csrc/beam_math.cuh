@@ -1,0 +1,265 @@
+// beam_math.cuh — register-resident 3x3 / 6x6 FP64 helpers for the beam kernels.
+//
+// Device counterparts of the reference's numerics helpers:
+//   spinTensor(v), axialVector      src/wireBunchingModels/numerics/spinTensor/spinTensor.C:154-168,290-299
+//   rotationMatrix(theta)           src/wireBunchingModels/numerics/pseudoVector/pseudoVector.C:250-264
+//   inv(tensor)                     OpenFOAM Tensor::inv (adjugate / determinant)
+// Everything is fully unrolled with compile-time indices so that the small
+// matrices live in registers.  Tensors are row-major (xx xy xz yx yy yz zx zy zz).
+#pragma once
+#include <math.h>
+
+#define BF_SMALL 1e-15  // OpenFOAM SMALL (double)
+
+#define DEV __device__ __forceinline__
+
+struct V3 {
+    double x, y, z;
+};
+struct M3 {
+    double a[9];
+};
+
+DEV V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+DEV V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+DEV V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+DEV V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+DEV V3 operator*(double s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+DEV double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+DEV V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+DEV double mag(V3 a) { return sqrt(dot(a, a)); }
+
+DEV M3 m3zero()
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.a[i] = 0.0;
+    return r;
+}
+DEV M3 m3eye()
+{
+    M3 r = m3zero();
+    r.a[0] = r.a[4] = r.a[8] = 1.0;
+    return r;
+}
+DEV M3 operator+(const M3& A, const M3& B)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.a[i] = A.a[i] + B.a[i];
+    return r;
+}
+DEV M3 operator-(const M3& A, const M3& B)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.a[i] = A.a[i] - B.a[i];
+    return r;
+}
+DEV M3 operator*(double s, const M3& A)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.a[i] = s * A.a[i];
+    return r;
+}
+DEV M3 transpose(const M3& A)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) r.a[3 * i + j] = A.a[3 * j + i];
+    return r;
+}
+// A & B
+DEV M3 mul(const M3& A, const M3& B)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            r.a[3 * i + j] = A.a[3 * i] * B.a[j] + A.a[3 * i + 1] * B.a[3 + j] + A.a[3 * i + 2] * B.a[6 + j];
+    return r;
+}
+// A & v
+DEV V3 mul(const M3& A, V3 v)
+{
+    return v3(A.a[0] * v.x + A.a[1] * v.y + A.a[2] * v.z, A.a[3] * v.x + A.a[4] * v.y + A.a[5] * v.z,
+              A.a[6] * v.x + A.a[7] * v.y + A.a[8] * v.z);
+}
+// A.T() & v
+DEV V3 mulT(const M3& A, V3 v)
+{
+    return v3(A.a[0] * v.x + A.a[3] * v.y + A.a[6] * v.z, A.a[1] * v.x + A.a[4] * v.y + A.a[7] * v.z,
+              A.a[2] * v.x + A.a[5] * v.y + A.a[8] * v.z);
+}
+// spinTensor(v): S(v) w = v x w
+DEV M3 spin(V3 v)
+{
+    M3 r;
+    r.a[0] = 0.0;  r.a[1] = -v.z; r.a[2] = v.y;
+    r.a[3] = v.z;  r.a[4] = 0.0;  r.a[5] = -v.x;
+    r.a[6] = -v.y; r.a[7] = v.x;  r.a[8] = 0.0;
+    return r;
+}
+// A & spinTensor(t): row r of the result is (row r of A) x t
+DEV M3 mulSpinR(const M3& A, V3 t)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double ax = A.a[3 * i], ay = A.a[3 * i + 1], az = A.a[3 * i + 2];
+        r.a[3 * i] = ay * t.z - az * t.y;
+        r.a[3 * i + 1] = az * t.x - ax * t.z;
+        r.a[3 * i + 2] = ax * t.y - ay * t.x;
+    }
+    return r;
+}
+// spinTensor(t) & A: column c of the result is t x (column c of A)
+DEV M3 mulSpinL(V3 t, const M3& A)
+{
+    M3 r;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double ax = A.a[c], ay = A.a[3 + c], az = A.a[6 + c];
+        r.a[c] = t.y * az - t.z * ay;
+        r.a[3 + c] = t.z * ax - t.x * az;
+        r.a[6 + c] = t.x * ay - t.y * ax;
+    }
+    return r;
+}
+// Lam & (diag(c) & Lam.T())
+DEV M3 conjDiag(const M3& Lm, V3 c)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            r.a[3 * i + j] = Lm.a[3 * i] * (c.x * Lm.a[3 * j]) + Lm.a[3 * i + 1] * (c.y * Lm.a[3 * j + 1]) +
+                             Lm.a[3 * i + 2] * (c.z * Lm.a[3 * j + 2]);
+    return r;
+}
+// diag(c) & Lam.T()
+DEV M3 diagMulT(V3 c, const M3& Lm)
+{
+    M3 r;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        r.a[j] = c.x * Lm.a[3 * j];
+        r.a[3 + j] = c.y * Lm.a[3 * j + 1];
+        r.a[6 + j] = c.z * Lm.a[3 * j + 2];
+    }
+    return r;
+}
+DEV V3 cmul(V3 c, V3 v) { return v3(c.x * v.x, c.y * v.y, c.z * v.z); }
+
+// OpenFOAM inv(tensor): adjugate / determinant
+DEV M3 inv(const M3& A)
+{
+    const double xx = A.a[0], xy = A.a[1], xz = A.a[2], yx = A.a[3], yy = A.a[4], yz = A.a[5], zx = A.a[6],
+                 zy = A.a[7], zz = A.a[8];
+    const double det = xx * yy * zz + xy * yz * zx + xz * yx * zy - xx * yz * zy - xy * yx * zz - xz * yy * zx;
+    const double id = 1.0 / det;
+    M3 r;
+    r.a[0] = (yy * zz - zy * yz) * id; r.a[1] = (xz * zy - xy * zz) * id; r.a[2] = (xy * yz - xz * yy) * id;
+    r.a[3] = (zx * yz - yx * zz) * id; r.a[4] = (xx * zz - xz * zx) * id; r.a[5] = (yx * xz - xx * yz) * id;
+    r.a[6] = (yx * zy - yy * zx) * id; r.a[7] = (xy * zx - xx * zy) * id; r.a[8] = (xx * yy - yx * xy) * id;
+    return r;
+}
+
+// Rodrigues, exactly the reference's plain formula (phi = |theta| + SMALL, no series branch):
+// R = I + (sin phi / phi) S + ((1 - cos phi)/phi^2) S&S      pseudoVector.C:250-264
+DEV M3 rotationMatrix(V3 th)
+{
+    const double phi = mag(th) + BF_SMALL;
+    double s, c;
+    sincos(phi, &s, &c);
+    const double c1 = s / phi, c2 = (1.0 - c) / (phi * phi);
+    M3 R;
+    // S&S = th th^T - |th|^2 I
+    const double xx = th.x * th.x, yy = th.y * th.y, zz = th.z * th.z;
+    R.a[0] = 1.0 + c2 * (-(yy + zz));
+    R.a[4] = 1.0 + c2 * (-(xx + zz));
+    R.a[8] = 1.0 + c2 * (-(xx + yy));
+    const double xy = c2 * (th.x * th.y), xz = c2 * (th.x * th.z), yz = c2 * (th.y * th.z);
+    R.a[1] = xy - c1 * th.z; R.a[3] = xy + c1 * th.z;
+    R.a[2] = xz + c1 * th.y; R.a[6] = xz - c1 * th.y;
+    R.a[5] = yz - c1 * th.x; R.a[7] = yz + c1 * th.x;
+    return R;
+}
+
+// Tangent operator DT^T applied to g (Evolve.C:806-829):
+// DT = (sin/phi) I + ((1 - sin/phi)/phi^2) th th^T + ((1-cos)/phi^2) S(th);  returns DT.T() & g
+DEV V3 tangentT(V3 th, V3 g)
+{
+    const double phi = mag(th) + BF_SMALL;
+    double s, c;
+    sincos(phi, &s, &c);
+    const double sp = s / phi;
+    const double c2 = (1.0 - sp) / (phi * phi), c3 = (1.0 - c) / (phi * phi);
+    // DT^T g = sp g + c2 th (th.g) - c3 (th x g)
+    const double tg = dot(th, g);
+    const V3 x = cross(th, g);
+    return v3(sp * g.x + c2 * th.x * tg - c3 * x.x, sp * g.y + c2 * th.y * tg - c3 * x.y,
+              sp * g.z + c2 * th.z * tg - c3 * x.z);
+}
+
+// ---------------------------------------------------------------------------
+// Dense 6x6 solve with partial pivoting inside the block, NR right-hand sides,
+// everything in registers: the pivot row is brought up by predicated swaps so no
+// array is ever indexed dynamically.  On return B holds A^{-1} B.
+// ---------------------------------------------------------------------------
+template <int NR>
+DEV void solve6(double (&A)[6][6], double (&B)[6][NR])
+{
+    double piv[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        int p = k;
+        double mx = fabs(A[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < 6; r++) {
+            const double v = fabs(A[r][k]);
+            if (v > mx) { mx = v; p = r; }
+        }
+#pragma unroll
+        for (int r = k + 1; r < 6; r++) {
+            const bool sw = (p == r);
+#pragma unroll
+            for (int c = k; c < 6; c++) {
+                const double t0 = A[k][c], t1 = A[r][c];
+                A[k][c] = sw ? t1 : t0;
+                A[r][c] = sw ? t0 : t1;
+            }
+#pragma unroll
+            for (int c = 0; c < NR; c++) {
+                const double t0 = B[k][c], t1 = B[r][c];
+                B[k][c] = sw ? t1 : t0;
+                B[r][c] = sw ? t0 : t1;
+            }
+        }
+        const double ip = 1.0 / A[k][k];
+        piv[k] = ip;
+#pragma unroll
+        for (int r = k + 1; r < 6; r++) {
+            const double m = A[r][k] * ip;
+#pragma unroll
+            for (int c = k + 1; c < 6; c++) A[r][c] -= m * A[k][c];
+#pragma unroll
+            for (int c = 0; c < NR; c++) B[r][c] -= m * B[k][c];
+        }
+    }
+#pragma unroll
+    for (int k = 5; k >= 0; k--) {
+#pragma unroll
+        for (int c = 0; c < NR; c++) {
+            double s = B[k][c];
+#pragma unroll
+            for (int j = k + 1; j < 6; j++) s -= A[k][j] * B[j][c];
+            B[k][c] = s * piv[k];
+        }
+    }
+}

@@ -1,0 +1,714 @@
+// beamgpu.cu — C-ABI (include/beamgpu.h) over the fused CUDA kernels.  sm_100a only.
+//
+// Host side of libbeamgpu.so: owns the device-resident state in the beam-interleaved SoA
+// layout, transposes to/from the reference's array-of-structs ordering at the boundary
+// (bf_set_field / bf_get_field), and drives the Newton loop of evolve()
+// (coupledTotalLagNewtonRaphsonBeamEvolve.C:55-670) with checkConvergence (:926-1026) on the
+// host, exactly where the reference evaluates it.  There is no CPU compute path here.
+#include "../../include/beamgpu.h"
+#include "beam_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#define BF_GREAT 1e15
+#define THREADS 128
+
+static char g_create_err[512] = "";
+
+struct Id128 { // ncclUniqueId: 128 opaque bytes, passed by value to ncclCommInitRank
+    char internal[128];
+};
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct bf_ctx {
+    char err[512];
+    int device;
+    cudaStream_t stream;
+    int64_t B, N, F;
+    int Bpad, nmax, grid;
+    std::vector<int32_t> nSeg, hostWType; // hostWType: [2][B]
+    std::vector<int64_t> cellStart, faceStart;
+    bool uniformN;
+    // device pools
+    void* pools[8];
+    int nPools;
+    int32_t *d_nSeg, *d_wType, *d_thType;
+    int64_t *d_cellStart, *d_faceStart;
+    double *d_dZ, *d_CQ, *d_CM, *d_ARho, *d_CI, *d_weight, *d_refL;
+    double *d_W, *d_Th, *d_Lam, *d_U, *d_Ac, *d_Om, *d_dOm, *d_DW, *d_DTh, *d_q, *d_m, *d_Lc;
+    double *d_Lf, *d_Gam, *d_K, *d_Q, *d_M;
+    double *d_Wb, *d_Thb, *d_Lamb, *d_DWb, *d_DThb, *d_force, *d_wPresc, *d_thPresc, *d_follower, *d_offset,
+        *d_moment, *d_springK, *d_springDir;
+    double *d_uP, *d_bP, *d_partial, *d_sums;
+    double* d_stage; // staging buffer in host (AoS) ordering
+    size_t stageDoubles;
+    double* h_sums;  // pinned
+    // options / time state
+    int scheme, storeInc;
+    double betaN, gammaN, deltaT;
+    int iOuterCorr;
+    bool hasQ, hasM;
+    bf_reduce_fn reducer;
+    void* reducerUser;
+    // NCCL
+    NcclApi nccl;
+    void* comm;
+    // instrumentation
+    int64_t launches;
+    int timing;
+    cudaEvent_t ev[3];
+    double fwdMs, bwdMs;
+    int64_t timedIters;
+};
+
+static int fail(bf_ctx* c, int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_OK(c, call)                                                                        \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(c, BF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+extern "C" const char* bf_version(void) { return "beamgpu 0.1 (sm_100a)"; }
+extern "C" const char* bf_backend(void) { return "cuda-sm100a"; }
+extern "C" const char* bf_last_error(const bf_ctx* c) { return c ? c->err : g_create_err; }
+extern "C" int64_t bf_num_cells(const bf_ctx* c) { return c->N; }
+extern "C" int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
+extern "C" int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
+extern "C" int64_t bf_launch_count(const bf_ctx* c) { return c->launches; }
+
+extern "C" int bf_host_alloc(void** p, int64_t bytes)
+{
+    return cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? BF_OK : BF_ERR_NOMEM;
+}
+extern "C" int bf_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BF_OK : BF_ERR_CUDA; }
+
+// ---------------------------------------------------------------------------
+// layout transposition: reference ordering (AoS, beam-major) <-> [i][c][b]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int findBeam(const int64_t* __restrict__ start, int B, int64_t g)
+{
+    int lo = 0, hi = B; // start[lo] <= g < start[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (start[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// cells: host index g = cellStart[b] + i ;  dev index ((i*nc + c)*Bpad + b)
+// faces: host index g = faceStart[b] + (j-1), j = 1..n-1 ; dev face index j
+template <bool TO_DEVICE>
+__global__ void transposeInternal(double* __restrict__ dev, double* __restrict__ host, const int64_t* __restrict__ start,
+                                  int B, int Bpad, int nc, int64_t count, int faceOffset, int uniformN)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= count) return;
+    int b;
+    int64_t i;
+    if (uniformN > 0) { b = (int)(g / uniformN); i = g % uniformN; }
+    else { b = findBeam(start, B, g); i = g - start[b]; }
+    i += faceOffset;
+    for (int c = 0; c < nc; c++) {
+        const size_t d = ((size_t)i * nc + c) * Bpad + b;
+        if (TO_DEVICE) dev[d] = host[g * nc + c]; else host[g * nc + c] = dev[d];
+    }
+}
+// patch values: host [b*nc + c] ; dev ((row*nc + c)*Bpad + b) with row = end (end arrays) or
+// the face index of the patch (face arrays: 0 or nSeg[b])
+template <bool TO_DEVICE>
+__global__ void transposePatch(double* __restrict__ dev, double* __restrict__ host, const int32_t* __restrict__ nSeg,
+                               int B, int Bpad, int nc, int end, int faceArray)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const size_t row = faceArray ? (end ? (size_t)nSeg[b] : 0) : (size_t)end;
+    for (int c = 0; c < nc; c++) {
+        const size_t d = (row * nc + c) * Bpad + b;
+        if (TO_DEVICE) dev[d] = host[(size_t)b * nc + c]; else host[(size_t)b * nc + c] = dev[d];
+    }
+}
+__global__ void fillIdentity(double* __restrict__ T, int64_t rows, int Bpad)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= rows * Bpad) return;
+    const int64_t r = k / Bpad, b = k % Bpad;
+    T[(r * 9 + 0) * Bpad + b] = 1.0;
+    T[(r * 9 + 4) * Bpad + b] = 1.0;
+    T[(r * 9 + 8) * Bpad + b] = 1.0;
+}
+
+template <typename T>
+static T* carve(char*& cur, size_t count)
+{
+    T* p = (T*)cur;
+    cur += ((count * sizeof(T) + 255) / 256) * 256;
+    return p;
+}
+
+extern "C" int bf_destroy(bf_ctx* c)
+{
+    if (!c) return BF_OK;
+    cudaSetDevice(c->device);
+    if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+    for (int i = 0; i < c->nPools; i++) cudaFree(c->pools[i]);
+    if (c->h_sums) cudaFreeHost(c->h_sums);
+    for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return BF_OK;
+}
+
+static int devAlloc(bf_ctx* c, void** p, size_t bytes)
+{
+    CUDA_OK(c, cudaMalloc(p, bytes));
+    CUDA_OK(c, cudaMemsetAsync(*p, 0, bytes, c->stream));
+    c->pools[c->nPools++] = *p;
+    return BF_OK;
+}
+
+// Replaces the constructor state set-up of CTL.C:74-1182 for what the hot path touches.
+extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf_bc* bc, const bf_options* opt,
+                         bf_ctx** out)
+{
+    if (!lay || !pr || !bc || !opt || !out || lay->nBeams <= 0 || !lay->nSeg || !lay->length || !pr->CQ || !pr->CM ||
+        !bc->wType || !bc->thetaType)
+        return fail(nullptr, BF_ERR_INVALID, "bf_create: null/invalid argument");
+    if (opt->scheme != BF_SCHEME_STEADY && opt->scheme != BF_SCHEME_NEWMARK)
+        return fail(nullptr, BF_ERR_UNSUPPORTED, "bf_create: d2dt2 scheme %d not supported (steadyState, Newmark)",
+                    opt->scheme);
+    if (lay->nBeams > (int64_t)1 << 30) return fail(nullptr, BF_ERR_INVALID, "bf_create: too many beams");
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+        return fail(nullptr, BF_ERR_CUDA, "bf_create: no CUDA device visible (libbeamgpu has no CPU fallback)");
+    if (opt->device < 0 || opt->device >= nDev)
+        return fail(nullptr, BF_ERR_INVALID, "bf_create: device %d out of range (%d visible)", opt->device, nDev);
+
+    bf_ctx* c = new bf_ctx();
+    memset(c->err, 0, sizeof c->err);
+    c->device = opt->device;
+    c->stream = nullptr; c->nPools = 0; c->h_sums = nullptr; c->comm = nullptr;
+    c->ev[0] = c->ev[1] = c->ev[2] = nullptr;
+    c->reducer = nullptr; c->reducerUser = nullptr;
+    c->launches = 0; c->timing = 0; c->fwdMs = c->bwdMs = 0; c->timedIters = 0;
+    c->hasQ = c->hasM = false;
+    c->d_q = c->d_m = c->d_Lc = c->d_DW = c->d_DTh = nullptr;
+#define CREATE_FAIL(code, ...) do { int rc_ = fail(nullptr, code, __VA_ARGS__); bf_destroy(c); return rc_; } while (0)
+#define CREATE_CUDA(call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) CREATE_FAIL(BF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+    CREATE_CUDA(cudaSetDevice(c->device));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
+
+    const int64_t B = c->B = lay->nBeams;
+    c->nSeg.assign(lay->nSeg, lay->nSeg + B);
+    c->cellStart.assign(B + 1, 0);
+    c->faceStart.assign(B + 1, 0);
+    int nmax = 0;
+    bool uniform = true;
+    for (int64_t b = 0; b < B; b++) {
+        if (lay->nSeg[b] < 1 || !(lay->length[b] > 0)) CREATE_FAIL(BF_ERR_INVALID, "bf_create: beam %lld has nSeg<1 or length<=0", (long long)b);
+        c->cellStart[b + 1] = c->cellStart[b] + lay->nSeg[b];
+        c->faceStart[b + 1] = c->faceStart[b] + lay->nSeg[b] - 1;
+        if (lay->nSeg[b] > nmax) nmax = lay->nSeg[b];
+        if (lay->nSeg[b] != lay->nSeg[0]) uniform = false;
+    }
+    c->uniformN = uniform;
+    c->N = c->cellStart[B];
+    c->F = c->faceStart[B];
+    c->nmax = nmax;
+    const int Bpad = c->Bpad = (int)((B + 31) / 32 * 32);
+    c->grid = (int)((B + THREADS - 1) / THREADS);
+    c->scheme = opt->scheme;
+    c->storeInc = opt->storeIncrements ? 1 : 0;
+    c->betaN = opt->newmarkBeta > 0 ? opt->newmarkBeta : 0.25;
+    c->gammaN = opt->newmarkGamma > 0 ? opt->newmarkGamma : 0.5;
+    c->deltaT = 1.0;
+    c->iOuterCorr = 0;
+    const bool newmark = c->scheme == BF_SCHEME_NEWMARK;
+    const size_t bp = (size_t)Bpad, nc_ = (size_t)nmax, nf_ = (size_t)nmax + 1;
+
+    // ---- per-beam + end arrays (one pool)
+    {
+        const size_t bytes = 256 * 40 + sizeof(double) * bp * (1 + 3 + 3 + 1 + 3 + 3 + 9 + 2 * (3 + 3 + 9 + 3 + 3 + 3 + 3 + 3 + 3 + 3 + 3 + 1 + 3)) +
+                             sizeof(int32_t) * bp * 5 + sizeof(int64_t) * 2 * (size_t)(B + 1);
+        char* cur;
+        if (devAlloc(c, (void**)&cur, bytes)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        c->d_dZ = carve<double>(cur, bp); c->d_CQ = carve<double>(cur, 3 * bp); c->d_CM = carve<double>(cur, 3 * bp);
+        c->d_ARho = carve<double>(cur, bp); c->d_CI = carve<double>(cur, 3 * bp); c->d_weight = carve<double>(cur, 3 * bp);
+        c->d_refL = carve<double>(cur, 9 * bp);
+        c->d_Wb = carve<double>(cur, 6 * bp); c->d_Thb = carve<double>(cur, 6 * bp); c->d_Lamb = carve<double>(cur, 18 * bp);
+        c->d_DWb = carve<double>(cur, 6 * bp); c->d_DThb = carve<double>(cur, 6 * bp); c->d_force = carve<double>(cur, 6 * bp);
+        c->d_wPresc = carve<double>(cur, 6 * bp); c->d_thPresc = carve<double>(cur, 6 * bp);
+        c->d_follower = carve<double>(cur, 6 * bp); c->d_offset = carve<double>(cur, 6 * bp);
+        c->d_moment = carve<double>(cur, 6 * bp); c->d_springK = carve<double>(cur, 2 * bp);
+        c->d_springDir = carve<double>(cur, 6 * bp);
+        c->d_nSeg = carve<int32_t>(cur, bp); c->d_wType = carve<int32_t>(cur, 2 * bp); c->d_thType = carve<int32_t>(cur, 2 * bp);
+        c->d_cellStart = carve<int64_t>(cur, (size_t)B + 1); c->d_faceStart = carve<int64_t>(cur, (size_t)B + 1);
+    }
+    // ---- cell / face state
+    {
+        const size_t cellD = nc_ * bp * (3 + 3 + 9 + (newmark ? 12 : 0) + (c->storeInc ? 6 : 0));
+        const size_t faceD = nf_ * bp * (9 + 3 + 3 + 3 + 3);
+        char* cur;
+        if (devAlloc(c, (void**)&cur, sizeof(double) * (cellD + faceD) + 256 * 16)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        c->d_W = carve<double>(cur, 3 * nc_ * bp); c->d_Th = carve<double>(cur, 3 * nc_ * bp); c->d_Lam = carve<double>(cur, 9 * nc_ * bp);
+        if (newmark) {
+            c->d_U = carve<double>(cur, 3 * nc_ * bp); c->d_Ac = carve<double>(cur, 3 * nc_ * bp);
+            c->d_Om = carve<double>(cur, 3 * nc_ * bp); c->d_dOm = carve<double>(cur, 3 * nc_ * bp);
+        } else {
+            c->d_U = c->d_Ac = c->d_Om = c->d_dOm = nullptr;
+        }
+        if (c->storeInc) { c->d_DW = carve<double>(cur, 3 * nc_ * bp); c->d_DTh = carve<double>(cur, 3 * nc_ * bp); }
+        c->d_Lf = carve<double>(cur, 9 * nf_ * bp); c->d_Gam = carve<double>(cur, 3 * nf_ * bp); c->d_K = carve<double>(cur, 3 * nf_ * bp);
+        c->d_Q = carve<double>(cur, 3 * nf_ * bp); c->d_M = carve<double>(cur, 3 * nf_ * bp);
+    }
+    // ---- block-Thomas scratch + partial sums
+    {
+        char* cur;
+        if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->grid + 8) + 256 * 4)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
+        c->d_partial = carve<double>(cur, 3 * (size_t)c->grid); c->d_sums = carve<double>(cur, 8);
+    }
+    // ---- staging buffer (largest field in host ordering: a tensor vol field)
+    c->stageDoubles = (size_t)c->N * 9;
+    if (devAlloc(c, (void**)&c->d_stage, sizeof(double) * c->stageDoubles)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+    CREATE_CUDA(cudaHostAlloc((void**)&c->h_sums, 8 * sizeof(double), cudaHostAllocDefault));
+
+    // ---- upload constants
+    {
+        std::vector<double> h(bp * 9);
+        std::vector<int32_t> hi(bp * 2);
+        auto up = [&](double* dst, size_t n) { return cudaMemcpyAsync(dst, h.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream); };
+        std::fill(h.begin(), h.end(), 1.0);
+        for (int64_t b = 0; b < B; b++) h[b] = lay->length[b] / lay->nSeg[b]; // createBeamMesh.C:245
+        CREATE_CUDA(up(c->d_dZ, bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        auto fill3 = [&](const double* src, double dflt) {
+            std::fill(h.begin(), h.end(), dflt);
+            if (src) for (int64_t b = 0; b < B; b++) for (int k = 0; k < 3; k++) h[k * bp + b] = src[3 * b + k];
+        };
+        fill3(pr->CQ, 1.0); CREATE_CUDA(up(c->d_CQ, 3 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        fill3(pr->CM, 1.0); CREATE_CUDA(up(c->d_CM, 3 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        fill3(pr->CIRho, 0.0); CREATE_CUDA(up(c->d_CI, 3 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        fill3(pr->weight, 0.0); CREATE_CUDA(up(c->d_weight, 3 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        std::fill(h.begin(), h.end(), 0.0);
+        if (pr->ARho) for (int64_t b = 0; b < B; b++) h[b] = pr->ARho[b];
+        CREATE_CUDA(up(c->d_ARho, bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        std::fill(h.begin(), h.end(), 0.0);
+        for (size_t b = 0; b < bp; b++) { h[0 * bp + b] = 1.0; h[4 * bp + b] = 1.0; h[8 * bp + b] = 1.0; }
+        if (pr->refLambdaf) for (int64_t b = 0; b < B; b++) for (int k = 0; k < 9; k++) h[k * bp + b] = pr->refLambdaf[9 * b + k];
+        CREATE_CUDA(up(c->d_refL, 9 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        // boundary-condition classes and spring data
+        std::vector<double> sk(2 * bp, 0.0), sd(6 * bp, 0.0);
+        c->hostWType.assign(2 * (size_t)B, 0);
+        for (int end = 0; end < 2; end++)
+            for (int64_t b = 0; b < B; b++) {
+                const int64_t pI = end * B + b;
+                const int wt = bc->wType[pI], tt = bc->thetaType[pI];
+                if (wt < BF_W_FIXED || wt > BF_W_SPRING || tt < BF_TH_FIXED || tt > BF_TH_MOMENT)
+                    CREATE_FAIL(BF_ERR_INVALID, "bf_create: unknown boundary-condition class at patch %lld", (long long)pI);
+                hi[end * bp + b] = wt;
+                c->hostWType[(size_t)end * B + b] = wt;
+                if (wt == BF_W_SPRING) {
+                    if (!bc->springStiffness || !bc->springDirection)
+                        CREATE_FAIL(BF_ERR_INVALID, "bf_create: spring BC without linearSpringCoeffs");
+                    double d[3] = {bc->springDirection[3 * pI], bc->springDirection[3 * pI + 1], bc->springDirection[3 * pI + 2]};
+                    const double mg = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                    if (mg > BF_SMALL) for (int k = 0; k < 3; k++) d[k] /= mg; // linearSpringForce...C:116-119
+                    sk[end * bp + b] = bc->springStiffness[pI];
+                    for (int k = 0; k < 3; k++) sd[((size_t)end * 3 + k) * bp + b] = d[k];
+                }
+            }
+        CREATE_CUDA(cudaMemcpyAsync(c->d_wType, hi.data(), 2 * bp * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        for (int end = 0; end < 2; end++) for (int64_t b = 0; b < B; b++) hi[end * bp + b] = bc->thetaType[end * B + b];
+        CREATE_CUDA(cudaMemcpyAsync(c->d_thType, hi.data(), 2 * bp * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CREATE_CUDA(cudaMemcpyAsync(c->d_springK, sk.data(), 2 * bp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CREATE_CUDA(cudaMemcpyAsync(c->d_springDir, sd.data(), 6 * bp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        std::vector<int32_t> ns(bp, 1);
+        for (int64_t b = 0; b < B; b++) ns[b] = lay->nSeg[b];
+        CREATE_CUDA(cudaMemcpyAsync(c->d_nSeg, ns.data(), bp * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CREATE_CUDA(cudaMemcpyAsync(c->d_cellStart, c->cellStart.data(), (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        CREATE_CUDA(cudaMemcpyAsync(c->d_faceStart, c->faceStart.data(), (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        CREATE_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    // Lambda = Lambdaf = I (CTL.C:289-314), also the patch values of the vol field Lambda
+    {
+        int64_t rows = (int64_t)nmax;
+        fillIdentity<<<(unsigned)((rows * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lam, rows, Bpad);
+        rows = (int64_t)nmax + 1;
+        fillIdentity<<<(unsigned)((rows * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lf, rows, Bpad);
+        fillIdentity<<<(unsigned)((2 * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lamb, 2, Bpad);
+        c->launches += 3;
+        CREATE_CUDA(cudaGetLastError());
+    }
+    if (lay->cellLength) { // L() per cell (HermiteSpline::segLengths), otherwise dZ
+        char* cur;
+        if (devAlloc(c, (void**)&cur, sizeof(double) * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        c->d_Lc = (double*)cur;
+        CREATE_CUDA(cudaMemcpyAsync(c->d_stage, lay->cellLength, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
+        transposeInternal<true><<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(
+            c->d_Lc, c->d_stage, c->d_cellStart, (int)B, Bpad, 1, c->N, 0, uniform ? nmax : 0);
+        c->launches++;
+    }
+    CREATE_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return BF_OK;
+}
+
+// ---------------------------------------------------------------------------
+static int fieldInfo(bf_ctx* c, int field, double** dev, double** endArr, int* nc, int* surface)
+{
+    *endArr = nullptr; *surface = 0; *nc = 3;
+    switch (field) {
+    case BF_FIELD_W: *dev = c->d_W; *endArr = c->d_Wb; break;
+    case BF_FIELD_THETA: *dev = c->d_Th; *endArr = c->d_Thb; break;
+    case BF_FIELD_LAMBDA: *dev = c->d_Lam; *endArr = c->d_Lamb; *nc = 9; break;
+    case BF_FIELD_DW: *dev = c->d_DW; *endArr = c->d_DWb; break;
+    case BF_FIELD_DTHETA: *dev = c->d_DTh; *endArr = c->d_DThb; break;
+    case BF_FIELD_U: *dev = c->d_U; break;
+    case BF_FIELD_ACCL: *dev = c->d_Ac; break;
+    case BF_FIELD_OMEGA: *dev = c->d_Om; break;
+    case BF_FIELD_DOTOMEGA: *dev = c->d_dOm; break;
+    case BF_FIELD_LAMBDAF: *dev = c->d_Lf; *nc = 9; *surface = 1; break;
+    case BF_FIELD_GAMMA: *dev = c->d_Gam; *surface = 1; break;
+    case BF_FIELD_K: *dev = c->d_K; *surface = 1; break;
+    case BF_FIELD_Q: *dev = c->d_Q; *surface = 1; break;
+    case BF_FIELD_M: *dev = c->d_M; *surface = 1; break;
+    default: return fail(c, BF_ERR_INVALID, "unknown field id %d", field);
+    }
+    return BF_OK;
+}
+
+static int xferInternal(bf_ctx* c, double* dev, double* host, int nc, int surface, bool toDevice)
+{
+    const int64_t count = surface ? c->F : c->N;
+    if (count == 0) return BF_OK;
+    const int64_t* start = surface ? c->d_faceStart : c->d_cellStart;
+    const int uni = c->uniformN ? (surface ? c->nmax - 1 : c->nmax) : 0;
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (toDevice) {
+        CUDA_OK(c, cudaMemcpyAsync(c->d_stage, host, sizeof(double) * count * nc, cudaMemcpyHostToDevice, c->stream));
+        transposeInternal<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stage, start, (int)c->B, c->Bpad, nc, count, surface, uni);
+    } else {
+        transposeInternal<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stage, start, (int)c->B, c->Bpad, nc, count, surface, uni);
+        CUDA_OK(c, cudaMemcpyAsync(host, c->d_stage, sizeof(double) * count * nc, cudaMemcpyDeviceToHost, c->stream));
+    }
+    c->launches++;
+    CUDA_OK(c, cudaGetLastError());
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+static int xferPatch(bf_ctx* c, double* dev, double* host, int nc, int end, int faceArray, bool toDevice)
+{
+    const unsigned grid = (unsigned)((c->B + 255) / 256);
+    const size_t bytes = sizeof(double) * c->B * nc;
+    if (toDevice) {
+        CUDA_OK(c, cudaMemcpyAsync(c->d_stage, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        transposePatch<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stage, c->d_nSeg, (int)c->B, c->Bpad, nc, end, faceArray);
+    } else {
+        transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stage, c->d_nSeg, (int)c->B, c->Bpad, nc, end, faceArray);
+        CUDA_OK(c, cudaMemcpyAsync(host, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    c->launches++;
+    CUDA_OK(c, cudaGetLastError());
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+extern "C" int bf_set_field(bf_ctx* c, int32_t field, const double* internal, const double* left, const double* right)
+{
+    CUDA_OK(c, cudaSetDevice(c->device));
+    double *dev, *endArr; int nc, surf;
+    int rc = fieldInfo(c, field, &dev, &endArr, &nc, &surf);
+    if (rc) return rc;
+    if (internal) {
+        if (!dev) return fail(c, BF_ERR_INVALID, "field %d is not allocated in this context", field);
+        if ((rc = xferInternal(c, dev, (double*)internal, nc, surf, true))) return rc;
+    }
+    const double* sides[2] = {left, right};
+    for (int end = 0; end < 2; end++) {
+        if (!sides[end]) continue;
+        if (surf) { if ((rc = xferPatch(c, dev, (double*)sides[end], nc, end, 1, true))) return rc; }
+        else if (endArr) {
+            if ((rc = xferPatch(c, endArr, (double*)sides[end], nc, end, 0, true))) return rc;
+            // a plain fixedValue keeps the value it was given; prevIter == value (CTL.C:1110-1111)
+            if (field == BF_FIELD_W && (rc = xferPatch(c, c->d_wPresc, (double*)sides[end], nc, end, 0, true))) return rc;
+            if (field == BF_FIELD_THETA && (rc = xferPatch(c, c->d_thPresc, (double*)sides[end], nc, end, 0, true))) return rc;
+        }
+    }
+    return BF_OK;
+}
+
+extern "C" int bf_get_field(bf_ctx* c, int32_t field, double* internal, double* left, double* right)
+{
+    CUDA_OK(c, cudaSetDevice(c->device));
+    double *dev, *endArr; int nc, surf;
+    int rc = fieldInfo(c, field, &dev, &endArr, &nc, &surf);
+    if (rc) return rc;
+    if (internal) {
+        if (!dev) return fail(c, BF_ERR_INVALID, "field %d is not kept in this context (scheme / storeIncrements)", field);
+        if ((rc = xferInternal(c, dev, internal, nc, surf, false))) return rc;
+    }
+    double* sides[2] = {left, right};
+    for (int end = 0; end < 2; end++) {
+        if (!sides[end]) continue;
+        if (surf) { if ((rc = xferPatch(c, dev, sides[end], nc, end, 1, false))) return rc; }
+        else if (endArr) { if ((rc = xferPatch(c, endArr, sides[end], nc, end, 0, false))) return rc; }
+        else return fail(c, BF_ERR_INVALID, "field %d has no mirrored boundary values", field);
+    }
+    return BF_OK;
+}
+
+extern "C" int bf_set_distributed_loads(bf_ctx* c, const double* q, const double* m)
+{
+    CUDA_OK(c, cudaSetDevice(c->device));
+    const double* src[2] = {q, m};
+    double** dst[2] = {&c->d_q, &c->d_m};
+    bool* has[2] = {&c->hasQ, &c->hasM};
+    for (int k = 0; k < 2; k++) {
+        if (!src[k]) { *has[k] = false; continue; }
+        if (!*dst[k]) {
+            int rc = devAlloc(c, (void**)dst[k], sizeof(double) * 3 * (size_t)c->nmax * c->Bpad);
+            if (rc) return rc;
+        }
+        int rc = xferInternal(c, *dst[k], (double*)src[k], 3, 0, true);
+        if (rc) return rc;
+        *has[k] = true;
+    }
+    return BF_OK;
+}
+
+extern "C" int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const double* v)
+{
+    if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !v) return fail(c, BF_ERR_INVALID, "bf_set_bc_values: bad argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    // entries of beams whose BC class does not use `kind` are never read by the kernels
+    switch (kind) {
+    case BF_BCV_W: return xferPatch(c, c->d_wPresc, (double*)v, 3, end, 0, true);
+    case BF_BCV_THETA: return xferPatch(c, c->d_thPresc, (double*)v, 3, end, 0, true);
+    case BF_BCV_MOMENT: return xferPatch(c, c->d_moment, (double*)v, 3, end, 0, true);
+    case BF_BCV_FORCE: {
+        // forceSeries -> force(), followerForceSeries -> followerForce_, offsetForceSeries -> offsetForce_.
+        // force() of a spring patch is its own state (set in evaluate) and must not be overwritten.
+        int rc = xferPatch(c, c->d_follower, (double*)v, 3, end, 0, true);
+        if (!rc) rc = xferPatch(c, c->d_offset, (double*)v, 3, end, 0, true);
+        if (rc) return rc;
+        const int32_t* wt = c->hostWType.data() + (size_t)end * c->B;
+        bool anySpring = false;
+        for (int64_t b = 0; b < c->B; b++) if (wt[b] == BF_W_SPRING) { anySpring = true; break; }
+        if (!anySpring) return xferPatch(c, c->d_force, (double*)v, 3, end, 0, true);
+        std::vector<double> cur((size_t)c->B * 3), in(v, v + (size_t)c->B * 3);
+        if ((rc = xferPatch(c, c->d_force, cur.data(), 3, end, 0, false))) return rc;
+        for (int64_t b = 0; b < c->B; b++)
+            if (wt[b] == BF_W_SPRING) for (int k = 0; k < 3; k++) in[3 * b + k] = cur[3 * b + k];
+        return xferPatch(c, c->d_force, in.data(), 3, end, 0, true);
+    }
+    default: return fail(c, BF_ERR_INVALID, "bf_set_bc_values: unknown kind %d", kind);
+    }
+}
+
+extern "C" int bf_begin_step(bf_ctx* c, double deltaT)
+{
+    if (!(deltaT > 0)) return fail(c, BF_ERR_INVALID, "bf_begin_step: deltaT must be > 0");
+    c->deltaT = deltaT;
+    c->iOuterCorr = 0;
+    return BF_OK;
+}
+
+extern "C" int bf_set_timing(bf_ctx* c, int32_t enabled) { c->timing = enabled; return BF_OK; }
+extern "C" int bf_kernel_time_ms(bf_ctx* c, int32_t reset, double* fwd, double* bwd, int64_t* it)
+{
+    if (fwd) *fwd = c->fwdMs;
+    if (bwd) *bwd = c->bwdMs;
+    if (it) *it = c->timedIters;
+    if (reset) { c->fwdMs = c->bwdMs = 0; c->timedIters = 0; }
+    return BF_OK;
+}
+
+static BeamParams makeParams(bf_ctx* c)
+{
+    BeamParams p;
+    p.B = (int)c->B; p.Bpad = c->Bpad; p.nmax = c->nmax;
+    p.newmark = c->scheme == BF_SCHEME_NEWMARK; p.first = c->iOuterCorr == 0; p.storeInc = c->storeInc;
+    p.dt = c->deltaT; p.beta = c->betaN; p.gamma = c->gammaN;
+    p.nSeg = c->d_nSeg; p.dZ = c->d_dZ; p.CQ = c->d_CQ; p.CM = c->d_CM; p.ARho = c->d_ARho; p.CI = c->d_CI;
+    p.weight = c->d_weight; p.refL = c->d_refL; p.wType = c->d_wType; p.thType = c->d_thType;
+    p.W = c->d_W; p.Th = c->d_Th; p.Lam = c->d_Lam; p.U = c->d_U; p.Ac = c->d_Ac; p.Om = c->d_Om; p.dOm = c->d_dOm;
+    p.DW = c->d_DW; p.DTh = c->d_DTh;
+    p.q = c->hasQ ? c->d_q : nullptr; p.m = c->hasM ? c->d_m : nullptr; p.Lc = c->d_Lc;
+    p.Lf = c->d_Lf; p.Gam = c->d_Gam; p.K = c->d_K; p.Q = c->d_Q; p.M = c->d_M;
+    p.Wb = c->d_Wb; p.Thb = c->d_Thb; p.Lamb = c->d_Lamb; p.DWb = c->d_DWb; p.DThb = c->d_DThb; p.force = c->d_force;
+    p.wPresc = c->d_wPresc; p.thPresc = c->d_thPresc; p.follower = c->d_follower; p.offset = c->d_offset;
+    p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir;
+    p.uP = c->d_uP; p.bP = c->d_bP; p.partial = c->d_partial;
+    return p;
+}
+
+// Launches one Newton iteration; the three LOCAL sums of squares end up in d_sums.
+static int launchIteration(bf_ctx* c)
+{
+    const BeamParams p = makeParams(c);
+    if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[0], c->stream));
+    if (p.newmark) beam_forward<true><<<c->grid, THREADS, 0, c->stream>>>(p);
+    else beam_forward<false><<<c->grid, THREADS, 0, c->stream>>>(p);
+    if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
+    if (p.newmark) beam_backward<true><<<c->grid, THREADS, 0, c->stream>>>(p);
+    else beam_backward<false><<<c->grid, THREADS, 0, c->stream>>>(p);
+    if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[2], c->stream));
+    beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->grid, c->d_sums);
+    c->launches += 3;
+    CUDA_OK(c, cudaGetLastError());
+    c->iOuterCorr++;
+    return BF_OK;
+}
+
+static int fetchSums(bf_ctx* c, double sumsq[3])
+{
+    CUDA_OK(c, cudaMemcpyAsync(c->h_sums, c->d_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 3; k++) sumsq[k] = c->h_sums[k];
+    if (c->timing) {
+        float a = 0, b = 0;
+        CUDA_OK(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+        CUDA_OK(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+        c->fwdMs += a; c->bwdMs += b; c->timedIters++;
+    }
+    return BF_OK;
+}
+
+extern "C" int bf_newton_iteration(bf_ctx* c, double sumsq[3])
+{
+    CUDA_OK(c, cudaSetDevice(c->device));
+    int rc = launchIteration(c);
+    if (rc) return rc;
+    return fetchSums(c, sumsq);
+}
+
+enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+// evolve(): Evolve.C:55-670, checkConvergence :926-1026
+extern "C" int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
+{
+    if (!tol || !out) return fail(c, BF_ERR_INVALID, "bf_evolve: null argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    double initialResidualNorm = 1, currentResidualNorm = BF_GREAT, deltaXNorm = BF_GREAT, XNorm = BF_GREAT;
+    memset(out, 0, sizeof *out);
+    c->iOuterCorr = 0;
+    int status = BF_OK;
+    for (;;) {
+        const int iteration = c->iOuterCorr; // the value passed as iOuterCorr()++
+        double s[3];
+        int rc = launchIteration(c);
+        if (rc) { out->status = rc; return rc; }
+        if (c->comm) { // global norms: one all-reduce of three doubles per Newton iteration
+            int nr = c->nccl.AllReduce(c->d_sums, c->d_sums, 3, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+            if (nr) { out->status = BF_ERR_COMM; return fail(c, BF_ERR_COMM, "ncclAllReduce failed: %s", c->nccl.GetErrorString(nr)); }
+        }
+        if ((rc = fetchSums(c, s))) { out->status = rc; return rc; }
+        if (c->reducer && c->reducer(s, 3, c->reducerUser)) { out->status = BF_ERR_COMM; return fail(c, BF_ERR_COMM, "norm reducer failed"); }
+        if (!(s[0] == s[0]) || !(s[1] == s[1])) { // NaN: a singular block — the reference would abort inside SparseLU
+            out->status = BF_DIVERGED;
+            out->nIter = c->iOuterCorr;
+            return fail(c, BF_DIVERGED, "Iteration %d: non-finite residual/solution norm", iteration);
+        }
+        currentResidualNorm = sqrt(s[0]);
+        deltaXNorm = sqrt(s[1]);
+        XNorm = sqrt(s[2]);
+        if (iteration == 0) initialResidualNorm = currentResidualNorm;
+        if (currentResidualNorm <= tol->absoluteTol) break;
+        if (currentResidualNorm <= tol->residualTol * initialResidualNorm) break;
+        if (deltaXNorm <= tol->solutionTol * XNorm) break;
+        if (currentResidualNorm >= tol->divergenceTol * initialResidualNorm && iteration > 1) {
+            fail(c, BF_DIVERGED, "Iteration %d: Diverged - Residual grew excessively.", iteration);
+            status = BF_DIVERGED;
+            break;
+        }
+        if (iteration >= tol->nCorrectors) {
+            fail(c, BF_MAXITER, "Iteration %d: Failed - Maximum iterations reached.", iteration);
+            status = BF_MAXITER;
+            break;
+        }
+    }
+    out->nIter = c->iOuterCorr;
+    out->status = status;
+    out->initialResidualNorm = initialResidualNorm;
+    out->currentResidualNorm = currentResidualNorm;
+    out->deltaXNorm = deltaXNorm;
+    out->xNorm = XNorm;
+    return status;
+}
+
+extern "C" int bf_set_reducer(bf_ctx* c, bf_reduce_fn fn, void* user)
+{
+    c->reducer = fn;
+    c->reducerUser = user;
+    return BF_OK;
+}
+
+// ---- NCCL (dlopen()ed so that single-GPU use has no NCCL dependency) ----------
+static int loadNccl(NcclApi* api, char* err)
+{
+    if (api->handle) return BF_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        api->handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api->handle) break;
+    }
+    if (!api->handle) { snprintf(err, 512, "cannot dlopen libnccl.so.2: %s", dlerror()); return BF_ERR_COMM; }
+    api->GetUniqueId = (int (*)(void*))dlsym(api->handle, "ncclGetUniqueId");
+    api->CommInitRank = (int (*)(void**, int, Id128, int))dlsym(api->handle, "ncclCommInitRank");
+    api->AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api->handle, "ncclAllReduce");
+    api->CommDestroy = (int (*)(void*))dlsym(api->handle, "ncclCommDestroy");
+    api->GetErrorString = (const char* (*)(int))dlsym(api->handle, "ncclGetErrorString");
+    if (!api->GetUniqueId || !api->CommInitRank || !api->AllReduce || !api->CommDestroy || !api->GetErrorString) {
+        snprintf(err, 512, "libnccl is missing a required symbol");
+        return BF_ERR_COMM;
+    }
+    return BF_OK;
+}
+
+extern "C" int bf_nccl_unique_id(void* id128)
+{
+    static NcclApi api;
+    if (!id128) return BF_ERR_INVALID;
+    if (loadNccl(&api, g_create_err)) return BF_ERR_COMM;
+    return api.GetUniqueId(id128) == 0 ? BF_OK : BF_ERR_COMM;
+}
+
+extern "C" int bf_comm_init_nccl(bf_ctx* c, const void* id128, int32_t nRanks, int32_t rank)
+{
+    if (!id128 || nRanks < 1 || rank < 0 || rank >= nRanks) return fail(c, BF_ERR_INVALID, "bf_comm_init_nccl: bad argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    if (loadNccl(&c->nccl, c->err)) return BF_ERR_COMM;
+    Id128 id;
+    memcpy(&id, id128, sizeof id);
+    int nr = c->nccl.CommInitRank(&c->comm, nRanks, id, rank);
+    if (nr) { c->comm = nullptr; return fail(c, BF_ERR_COMM, "ncclCommInitRank failed: %s", c->nccl.GetErrorString(nr)); }
+    return BF_OK;
+}
