@@ -88,6 +88,8 @@ EXPORTS = {
     "bf_launch_count": (C.c_int64, [C.c_void_p]),
     "bf_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp, C.POINTER(C.c_int64)]),
     "bf_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
+    "bf_region_mark": (C.c_int, [C.c_void_p, C.c_int32]),
+    "bf_region_elapsed_ms": (C.c_int, [C.c_void_p, _dp]),
     "bf_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "bf_host_free": (C.c_int, [C.c_void_p]),
 }

@@ -1,14 +1,15 @@
 // beam_kernels.cuh — the fused Newton-iteration kernels (FP64, sm_100a).
 //
-// One Newton iteration of coupledTotalLagNewtonRaphsonBeam::evolve() is TWO kernels:
+// One Newton iteration of coupledTotalLagNewtonRaphsonBeam::evolve() is ONE kernel
+// (beam_newton) made of two sweeps that every thread runs back to back:
 //
-//   beam_forward  : per beam, left -> right.  For every cell it recomputes the face
+//   forwardSweep  : per beam, left -> right.  For every cell it recomputes the face
 //                   coefficients (updateEqnCoefficients, Evolve.C:673-753), assembles the
 //                   6x6 blocks d, l, u and the source (Matrix.C:55-475, BC.C:64-1190, loads and
 //                   inertia Evolve.C:192-536) IN REGISTERS and immediately performs the
 //                   block-Thomas forward elimination.  d/l/u/source never exist in HBM;
 //                   only uPrime (36) and bPrime (6) per cell are written to scratch.
-//   beam_backward : per beam, right -> left.  Back-substitution, BC evaluate()
+//   backwardSweep : per beam, right -> left.  Back-substitution, BC evaluate()
 //                   (PF/*: momentBeamRotationNR, forceBeamDisplacementNR, followerForce,
 //                   linearSpring), updateSolutionVariables (Evolve.C:757-923) and the partial
 //                   sums of the three convergence norms (Evolve.C:588,618-626).
@@ -249,12 +250,11 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 // forward: coefficients + assembly + block-Thomas elimination
 // ---------------------------------------------------------------------------
 template <bool NEWMARK>
-__global__ void __launch_bounds__(128) beam_forward(const BeamParams p)
+DEV double forwardSweep(const BeamParams& p, const int b)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t s = p.Bpad;
     double res = 0.0;
-    if (b < p.B) {
+    {
         const int n = p.nSeg[b];
         const double dZ = p.dZ[b];
         const double dcI = 1.0 / dZ, dcB = 2.0 / dZ; // mesh().deltaCoeffs()
@@ -420,8 +420,7 @@ __global__ void __launch_bounds__(128) beam_forward(const BeamParams p)
             }
         }
     }
-    double v[1] = {res};
-    blockReduceStore<1>(v, p.partial, 0);
+    return res;
 }
 
 // ---------------------------------------------------------------------------
@@ -517,12 +516,10 @@ DEV FaceState patchUpdate(const BeamParams& p, int end, int b, const M3& LfOld, 
 }
 
 template <bool NEWMARK>
-__global__ void __launch_bounds__(128) beam_backward(const BeamParams p)
+DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t s = p.Bpad;
-    double dx2 = 0.0, x2 = 0.0;
-    if (b < p.B) {
+    {
         const int n = p.nSeg[b];
         const double dZ = p.dZ[b];
         const double dcI = 1.0 / dZ, dcB = 2.0 / dZ;
@@ -613,7 +610,39 @@ __global__ void __launch_bounds__(128) beam_backward(const BeamParams p)
             xWn = DW; xTn = DT; WoldN = Wold; WnewN = Wnew;
         }
     }
-    double v[2] = {dx2, x2};
+}
+
+// ---------------------------------------------------------------------------
+// Kernels.  beam_newton is the product path: ONE launch per Newton iteration, each thread
+// runs the forward sweep and then the backward sweep of its own beam (no inter-thread
+// dependency exists, so no grid-wide synchronisation is needed between the two).
+// beam_forward / beam_backward are the same sweeps as two launches, kept for profiling.
+// ---------------------------------------------------------------------------
+template <bool NEWMARK>
+__global__ void __launch_bounds__(128) beam_newton(const BeamParams p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[3] = {0.0, 0.0, 0.0};
+    if (b < p.B) {
+        v[0] = forwardSweep<NEWMARK>(p, b);
+        backwardSweep<NEWMARK>(p, b, v[1], v[2]);
+    }
+    blockReduceStore<3>(v, p.partial, 0);
+}
+template <bool NEWMARK>
+__global__ void __launch_bounds__(128) beam_forward(const BeamParams p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = {0.0};
+    if (b < p.B) v[0] = forwardSweep<NEWMARK>(p, b);
+    blockReduceStore<1>(v, p.partial, 0);
+}
+template <bool NEWMARK>
+__global__ void __launch_bounds__(128) beam_backward(const BeamParams p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[2] = {0.0, 0.0};
+    if (b < p.B) backwardSweep<NEWMARK>(p, b, v[0], v[1]);
     blockReduceStore<2>(v, p.partial, 1);
 }
 

@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — beam-cell Newton updates/s on the synthetic multi-beam bundle.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3]): 65,536 beams x 200 cells PER GPU of the
+`3DdynamicCantileverMultiBeamDensity` tutorial scaled up — Newmark (beta .25, gamma .5),
+dt = 1e-3, square 0.2 x 0.2 section, rho cycling 500/1000/2000, clamped left end, constant
+tip force (2000 2000 0) with a deterministic +-10 % per-beam jitter, tolerances of the
+tutorial (nCorrectors 200, solutionTol 1e-10 => rtol 1e-8).  A "step" is one time step =
+one evolve() = one Newton loop (3-4 iterations) over every cell of the bundle.
+
+metric  = beam-cell Newton updates per second = cells x Newton iterations / time.
+value   = state resident in HBM; the K timed steps are bracketed by a barrier +
+          synchronize and timed with CUDA events on the library's stream (max over ranks).
+e2e     = the same K steps through the host-facing call sequence with HOST buffers inside
+          the timed region: BC values host->device every step, W and Theta mirrored
+          device->host into pinned buffers every step.
+roofline= the fused Newton-iteration kernel: 760 B (Newmark) algorithmic bytes per
+          beam-cell update / measured kernel time, against the measured HBM
+          copy bandwidth of MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "beam-cell Newton updates/s"
+UNIT = "updates/s"
+BYTES_PER_UPDATE_NEWMARK = 760.0  # 95 doubles
+HBM_FALLBACK_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--beams", type=int, default=65536, help="beams per GPU (weak scaling)")
+    ap.add_argument("--cells", type=int, default=200)
+    ap.add_argument("--strong", action="store_true", help="keep the total at --beams (strong scaling)")
+    ap.add_argument("--no-jitter", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-beams-per-thread", type=int, default=256)
+    return ap.parse_args()
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9 or f[0] != str(self.gpu):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_case(args, world):
+    from beamfoam_b200 import cases
+    total = args.beams if args.strong else args.beams * world
+    return cases.multiBeamDensity(total, args.cells, jitter=not args.no_jitter), total
+
+
+def config_dict(args, world, total):
+    return {
+        "workload": f"3DdynamicCantileverMultiBeamDensity scaled: {total} beams x {args.cells} cells total "
+                    f"({total // world} beams per GPU), Newmark beta .25 gamma .5 dt 1e-3, "
+                    f"rho 500/1000/2000, tip force (2000 2000 0)" + ("" if args.no_jitter else " x (1+0.1u_b)"),
+        "beams_total": total, "beams_per_gpu": total // world, "cells_per_beam": args.cells,
+        "cells_total": total * args.cells, "tolerances": "nCorrectors 200, rtol 1e-8, stol 1e-10",
+        "l2_policy": "inputs larger than L2: >=9.9 GB of state + 4.4 GB scratch per GPU vs 126 MB L2",
+        "parallelism": f"beams sharded over {world} GPU(s); one 3-double all-reduce per Newton iteration",
+    }
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_oracle_rate(args, steps, warmup, threads=None):
+    """Times the CPU oracle (a port of the reference arithmetic; the reference binary cannot be
+    built here) on a bounded sample of the same workload: `threads` independent shards of
+    `cpu_beams_per_thread` beams x cells, one oracle context per host thread (ctypes releases
+    the GIL).  Returns (updates/s, description, threads)."""
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from build_oracle import build as build_oracle
+    from beamfoam_b200 import cases, coupledTotalLagNewtonRaphsonBeam, load_library
+    lib = load_library(build_oracle())
+    threads = threads or os.cpu_count() or 1
+    bpt = args.cpu_beams_per_thread
+    case = cases.multiBeamDensity(threads * bpt, args.cells, jitter=not args.no_jitter)
+    models = [coupledTotalLagNewtonRaphsonBeam(case, library=lib, beamRange=(t * bpt, (t + 1) * bpt),
+                                               storeIncrements=False) for t in range(threads)]
+
+    def work(m, n):
+        it = 0
+        for _ in range(n):
+            m.loop()
+            m.evolve()
+            it += m.iOuterCorr()
+        return it
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda m: work(m, warmup), models))
+        t0 = time.perf_counter()
+        iters = list(ex.map(lambda m: work(m, steps), models))
+        dt = time.perf_counter() - t0
+    updates = sum(iters) * bpt * args.cells
+    for m in models:
+        m.close()
+    desc = (f"{threads} threads x {bpt} beams x {args.cells} cells, {steps} time steps "
+            f"({sum(iters) // threads} Newton iterations per shard), oracle port, banded LU per beam")
+    return updates / dt, desc, threads, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    _, total = make_case_sizes(args, world)
+    rate, desc, threads, ms = cpu_oracle_rate(args, args.steps, args.warmup)
+    line = {
+        "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, world, total), "impl": "reference",
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = CPU oracle port of the reference arithmetic (OpenFOAM+Eigen cannot be built here)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def make_case_sizes(args, world):
+    total = args.beams if args.strong else args.beams * world
+    return None, total
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from beamfoam_b200 import _lib as L
+    from beamfoam_b200 import coupledTotalLagNewtonRaphsonBeam, load_library, shard_range
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    lib = load_library()
+    case, total = make_case(args, world)
+    lo, hi = shard_range(total, rank, world)
+    model = coupledTotalLagNewtonRaphsonBeam(case, library=lib, device=local, beamRange=(lo, hi),
+                                             storeIncrements=False)
+    ctx = model._ctx
+    if world > 1:  # built-in reducer: ncclAllReduce of the 3 squared norms on the library's stream
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            rc = lib.bf_nccl_unique_id(buf)
+            if rc:
+                raise SystemExit("bf_nccl_unique_id failed")
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        raw = (C.c_char * 128).from_buffer_copy(uid.cpu().numpy().tobytes())
+        model._check(lib.bf_comm_init_nccl(ctx, raw, world, rank))
+
+    nCellsLocal = model.nCells
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def step_resident():
+        model.loop()
+        model._check(lib.bf_begin_step(ctx, float(case.deltaT)))
+        out = L.bf_step_out()
+        rc = lib.bf_evolve(ctx, C.byref(model.tol), C.byref(out))
+        model._check(rc)
+        return out.nIter
+
+    # ---- warm-up (BC values uploaded once: they are constant in this workload)
+    model.updateCoeffs(case.deltaT)
+    for _ in range(args.warmup):
+        step_resident()
+
+    # ---- timed region 1: state resident in HBM
+    sampler = ClockSampler(local)
+    lib.bf_set_timing(ctx, 1)
+    lib.bf_kernel_time_ms(ctx, 1, None, None, None)
+    launches0 = lib.bf_launch_count(ctx)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    lib.bf_region_mark(ctx, 0)
+    iters = 0
+    for _ in range(args.steps):
+        iters += step_resident()
+    lib.bf_region_mark(ctx, 1)
+    ms = C.c_double()
+    model._check(lib.bf_region_elapsed_ms(ctx, C.byref(ms)))
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    launches = lib.bf_launch_count(ctx) - launches0
+    fwd, bwd, nit = C.c_double(), C.c_double(), C.c_int64()
+    lib.bf_kernel_time_ms(ctx, 1, C.byref(fwd), C.byref(bwd), C.byref(nit))
+    lib.bf_set_timing(ctx, 0)
+    region_ms = max_over_ranks(ms.value)
+    updates_total = sum_over_ranks(float(nCellsLocal) * iters)
+    value = updates_total / (region_ms * 1e-3)
+
+    # ---- roofline of the fused Newton-iteration kernel (this rank)
+    kern_ms = (fwd.value + bwd.value) / max(nit.value, 1)
+    peak, peak_src = hbm_peak()
+    achieved = BYTES_PER_UPDATE_NEWMARK * nCellsLocal / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("beam_newton_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "beam_newton<true>", "kernel_ms": kern_ms,
+                "bytes_per_update": BYTES_PER_UPDATE_NEWMARK, "updates_per_launch": nCellsLocal,
+                "peak_source": peak_src, "kernel_share_of_step": (fwd.value + bwd.value) / ms.value}
+
+    # ---- timed region 2: end to end with host buffers
+    e2e = None
+    if not args.no_e2e:
+        Wh = torch.empty((nCellsLocal, 3), dtype=torch.float64, pin_memory=True)
+        Th = torch.empty((nCellsLocal, 3), dtype=torch.float64, pin_memory=True)
+        B = model._B
+        h2d = 4 * 2 * B * 3 * 8  # W, Theta, force, moment values for both ends (bf_set_bc_values)
+        d2h = 2 * nCellsLocal * 3 * 8
+        wf, tf = L.FIELDS["W"], L.FIELDS["Theta"]
+
+        def step_e2e():
+            model.loop()
+            model.updateCoeffs(model.time)  # host -> device
+            model._check(lib.bf_begin_step(ctx, float(case.deltaT)))
+            out = L.bf_step_out()
+            model._check(lib.bf_evolve(ctx, C.byref(model.tol), C.byref(out)))
+            model._check(lib.bf_get_field(ctx, wf, Wh.data_ptr(), None, None))  # device -> host
+            model._check(lib.bf_get_field(ctx, tf, Th.data_ptr(), None, None))
+            return out.nIter
+
+        step_e2e()
+        barrier()
+        lib.bf_region_mark(ctx, 0)
+        t0 = time.perf_counter()
+        it2 = 0
+        for _ in range(args.steps):
+            it2 += step_e2e()
+        lib.bf_region_mark(ctx, 1)
+        ms2 = C.c_double()
+        model._check(lib.bf_region_elapsed_ms(ctx, C.byref(ms2)))
+        barrier()
+        wall2 = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max_over_ranks(max(ms2.value, wall2))
+        e2e_updates = sum_over_ranks(float(nCellsLocal) * it2)
+        e2e = {"value": e2e_updates / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+               "mirrored": "W, Theta internal fields -> pinned host; BC values -> device, every step",
+               "checksum": float(Wh[-1, 0]) + float(Th[-1, 1])}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, desc, threads, _ = cpu_oracle_rate(args, steps=8, warmup=1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": region_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args, world, total), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "newton_iterations_per_step": iters / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+            "impl": "ours",
+        }
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -247,11 +247,17 @@ int bf_comm_init_nccl(bf_ctx* ctx, const void* uniqueId128, int32_t nRanks, int3
 /* ---- instrumentation --------------------------------------------------------
  * Kernel launches issued by this context since creation (bench gpu_launches),
  * and device time in ms of the Newton-iteration kernels since the last reset,
- * measured with CUDA events on the context's stream. */
+ * measured with CUDA events on the context's stream.  The product path is ONE fused kernel per
+ * iteration: fwd_ms then holds its time and bwd_ms is 0; with BEAMGPU_SPLIT_KERNELS=1 in the
+ * environment the two sweeps are launched separately (profiling aid) and both are filled. */
 int64_t bf_launch_count(const bf_ctx* ctx);
 int bf_kernel_time_ms(bf_ctx* ctx, int32_t reset, double* fwd_ms, double* bwd_ms,
                       int64_t* iterations);
 int bf_set_timing(bf_ctx* ctx, int32_t enabled);
+/* Device-side stopwatch for a caller-chosen region: a pair of CUDA events recorded on the
+ * context's stream (which = 0 start, 1 stop); elapsed waits for the stop event. */
+int bf_region_mark(bf_ctx* ctx, int32_t which);
+int bf_region_elapsed_ms(bf_ctx* ctx, double* ms);
 
 /* Pinned host memory for the mirror buffers (cudaHostAlloc; malloc in the oracle). */
 int bf_host_alloc(void** ptr, int64_t bytes);

@@ -1,5 +1,4 @@
 import os
-import subprocess
 import sys
 
 import pytest
@@ -8,18 +7,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libbeamoracle.so")
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from build_oracle import ORACLE_SO, build as build_oracle  # noqa: E402
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-
-
-def build_oracle():
-    src = os.path.join(ROOT, "oracle", "beam_oracle.c")
-    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
-    return ORACLE_SO
 
 
 @pytest.fixture(scope="session")
