@@ -249,175 +249,319 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 // ---------------------------------------------------------------------------
 // forward: coefficients + assembly + block-Thomas elimination
 // ---------------------------------------------------------------------------
+// Per-thread shared-memory slots (doubles).  Element k of thread t lives at sm[k*BEAM_THREADS + t]:
+// consecutive threads hit consecutive banks, so every access is conflict-free.  The stash is a
+// register extension: an FP64 warp instruction occupies the pipe for 2 cycles, an LDS.64 costs
+// the same, so parking the face tensors here is cheaper than any local-memory spill.
+#define BEAM_THREADS 128
+enum {
+    S_REFL = 0,  // refLambdaf (9)
+    S_CQ = 9,    // diag CQ (3)
+    S_CM = 12,   // diag CM (3)
+    S_CI = 15,   // diag CIRho (3)
+    S_WGT = 18,  // rho A g (3)
+    S_P = 21,    // a*CQW            (9)   face i+1
+    S_QT = 30,   // 0.5*CQTheta      (9)
+    S_RM = 39,   // a*CMQW           (9)
+    S_S1 = 48,   // a*CMTheta        (9)
+    S_S3 = 57,   // 0.5*CMQTheta     (9)
+    S_MF = 66,   // M of face i+1    (3)   0.5*CMTheta2 = -0.5*spin(M)
+    S_SC = 69,   // nei part of the source of cell i+1 (6)
+    S_TOTAL = 75
+};
+#define SMEM_BYTES (S_TOTAL * BEAM_THREADS * sizeof(double))
+
+DEV double smLd(const double* sm, int k) { return ((const volatile double*)sm)[k * BEAM_THREADS]; }
+DEV void smSt(double* sm, int k, double v) { sm[k * BEAM_THREADS] = v; }
+DEV V3 smLd3(const double* sm, int k) { return v3(smLd(sm, k), smLd(sm, k + 1), smLd(sm, k + 2)); }
+DEV M3 smLd9(const double* sm, int k)
+{
+    M3 r;
+#pragma unroll
+    for (int j = 0; j < 9; j++) r.a[j] = smLd(sm, k + j);
+    return r;
+}
+DEV void smSt9(double* sm, int k, const M3& A)
+{
+#pragma unroll
+    for (int j = 0; j < 9; j++) smSt(sm, k + j, A.a[j]);
+}
+
+// Boundary closure is executed for 2 of the n cells of a beam; keeping it out of line keeps its
+// temporaries out of the register allocation of the steady-state loop.
+__device__ __noinline__ void patchClosure(const BeamParams& p, int end, int b, V3 Wc, double* D36, double* src6)
+{
+    const size_t s = p.Bpad;
+    const double dZ = p.dZ[b];
+    const double dcB = 2.0 / dZ, pDelta = 1.0 / dcB;
+    const M3 refL = ld9(p.refL, b, s);
+    const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
+    const size_t j = end ? (size_t)p.nSeg[b] : 0;
+    const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
+    const M3 Lfb = ld9(p.Lf, f9, s);
+    const EndBC e = loadEnd(p, end, b, Lfb);
+    const V3 Wb = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb; // after updateCoeffs()
+    // left patch: outward normal -x => dR0Ds = -dR0 (CTL.C:987-994)
+    const V3 t = end ? dR0 + dcB * (Wb - Wc) : dcB * (Wb - Wc) - dR0;
+    const FaceCoef f = faceCoefficients(Lfb, refL, ld3(p.CQ, b, s), ld3(p.CM, b, s), ld3(p.Gam, f3, s),
+                                        ld3(p.K, f3, s), ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcB, true);
+    double D[6][6], src[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        src[r] = src6[r];
+#pragma unroll
+        for (int c = 0; c < 6; c++) D[r][c] = D36[6 * r + c];
+    }
+    bcClosure(D, src, f, e, Lfb, pDelta);
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        src6[r] = src[r];
+#pragma unroll
+        for (int c = 0; c < 6; c++) D36[6 * r + c] = D[r][c];
+    }
+}
+
 template <bool NEWMARK>
-DEV double forwardSweep(const BeamParams& p, const int b)
+DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ sm)
 {
     const size_t s = p.Bpad;
     double res = 0.0;
+    const int n = p.nSeg[b];
+    const double dZ = p.dZ[b];
+    const double dcI = 1.0 / dZ; // mesh().deltaCoeffs() of internal faces
     {
-        const int n = p.nSeg[b];
-        const double dZ = p.dZ[b];
-        const double dcI = 1.0 / dZ, dcB = 2.0 / dZ; // mesh().deltaCoeffs()
-        const double pDelta = 1.0 / dcB;
-        const V3 CQ = ld3(p.CQ, b, s), CM = ld3(p.CM, b, s), wgt = ld3(p.weight, b, s);
         const M3 refL = ld9(p.refL, b, s);
-        const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]); // refLambdaf & (1 0 0)
-        double ARho = 0.0;
-        V3 CI = v3(0, 0, 0);
-        if (NEWMARK) { ARho = p.ARho[b]; CI = ld3(p.CI, b, s); }
-        const double dt = p.dt, beta = p.beta, gamma = p.gamma;
+        smSt9(sm, S_REFL, refL);
+        const V3 CQ = ld3(p.CQ, b, s), CM = ld3(p.CM, b, s), CI = ld3(p.CI, b, s), wg = ld3(p.weight, b, s);
+        smSt(sm, S_CQ, CQ.x); smSt(sm, S_CQ + 1, CQ.y); smSt(sm, S_CQ + 2, CQ.z);
+        smSt(sm, S_CM, CM.x); smSt(sm, S_CM + 1, CM.y); smSt(sm, S_CM + 2, CM.z);
+        smSt(sm, S_CI, CI.x); smSt(sm, S_CI + 1, CI.y); smSt(sm, S_CI + 2, CI.z);
+        smSt(sm, S_WGT, wg.x); smSt(sm, S_WGT + 1, wg.y); smSt(sm, S_WGT + 2, wg.z);
+    }
+    const double ARho = NEWMARK ? p.ARho[b] : 0.0;
+    const double dt = p.dt, beta = p.beta, gamma = p.gamma;
 
-        double Dc[6][6], sc[6], lb[6];
+    // loop-carried: Dc = (nei part of d_i) - l_{i-1} & uPrime_{i-1};  lb = l_{i-1} & bPrime_{i-1};
+    // sc = nei part of source_i;  Wi = W of cell i
+    double Dc[6][6], sc[6], lb[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        sc[r] = 0.0; lb[r] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) Dc[r][c] = 0.0;
+    }
+    V3 Wi = ld3(p.W, b, s);
+    {
+        double D36[36], s6[6];
+#pragma unroll
+        for (int k = 0; k < 36; k++) D36[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s6[k] = 0.0;
+        patchClosure(p, 0, b, Wi, D36, s6);
 #pragma unroll
         for (int r = 0; r < 6; r++) {
-            sc[r] = 0.0; lb[r] = 0.0;
+            sc[r] = s6[r];
 #pragma unroll
-            for (int c = 0; c < 6; c++) Dc[r][c] = 0.0;
+            for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
         }
-        V3 Wi = ld3(p.W, b, s);
-        { // left patch: face 0, outward normal -x  => dR0Ds = -dR0 (CTL.C:987-994)
-            const M3 Lfb = ld9(p.Lf, b, s);
-            const EndBC e = loadEnd(p, 0, b, Lfb);
-            const V3 Wb = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb; // after updateCoeffs()
-            const V3 t = dcB * (Wb - Wi) - dR0;
-            const FaceCoef f = faceCoefficients(Lfb, refL, CQ, CM, ld3(p.Gam, b, s), ld3(p.K, b, s),
-                                                ld3(p.Q, b, s), ld3(p.M, b, s), t, dcB, true);
-            bcClosure(Dc, sc, f, e, Lfb, pDelta);
-        }
-        for (int i = 0; i < n; i++) {
-            double D[6][6], R[6][7];
+    }
+    for (int i = 0; i < n; i++) {
+        const bool last = (i == n - 1);
+        const size_t j = (size_t)(i + 1);
+        const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
+        double src[6];
 #pragma unroll
-            for (int r = 0; r < 6; r++) {
-#pragma unroll
-                for (int c = 0; c < 6; c++) D[r][c] = Dc[r][c];
-#pragma unroll
-                for (int c = 0; c < 6; c++) R[r][c] = 0.0;
+        for (int r = 0; r < 6; r++) src[r] = sc[r];
+        V3 Wn = Wi;
+        // ---- phase A: coefficients of face i+1, own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
+        if (!last) {
+            Wn = ld3(p.W, j * 3 * s + b, s);
+            const M3 Lm = mul(ld9(p.Lf, f9, s), smLd9(sm, S_REFL));                       // Evolve.C:678
+            const V3 t = v3(smLd(sm, S_REFL) + dcI * (Wn.x - Wi.x), smLd(sm, S_REFL + 3) + dcI * (Wn.y - Wi.y),
+                            smLd(sm, S_REFL + 6) + dcI * (Wn.z - Wi.z));                  // dR0Ds + snGrad(W)
+            const double h = 0.5 / dcI;
+            V3 eQ;
+            M3 SC;
+            const M3 SQ = spin(ld3(p.Q, f3, s));
+            {
+                const V3 CQ = smLd3(sm, S_CQ);
+                const M3 CQW = conjDiag(Lm, CQ);                                          // :680
+                eQ = mul(Lm, cmul(CQ, ld3(p.Gam, f3, s)));                                // :682
+                SC = mulSpinL(t, CQW);
+                const M3 Pm = dcI * CQW;
+                const M3 Qt = 0.5 * (mulSpinR(CQW, t) - SQ);                              // 0.5*CQTheta :686-693
+                smSt9(sm, S_P, Pm);
+                smSt9(sm, S_QT, Qt);
+                addBlk(Dc, 0, 0, -1.0, Pm);
+                addBlk(Dc, 0, 3, 1.0, Qt);
             }
-            double src[6];
-#pragma unroll
-            for (int r = 0; r < 6; r++) src[r] = sc[r];
-            const size_t j = (size_t)(i + 1);
-            const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
-            const bool last = (i == n - 1);
-            M3 Pm, Qt, Rm, S1, S23p, S23m; // face tensors for the carry (internal faces only)
-            V3 Wn = Wi, eQ, eM, eMQ;
-            if (!last) {
-                Wn = ld3(p.W, j * 3 * s + b, s);
-                const V3 t = dR0 + dcI * (Wn - Wi);
-                const FaceCoef f = faceCoefficients(ld9(p.Lf, f9, s), refL, CQ, CM, ld3(p.Gam, f3, s),
-                                                    ld3(p.K, f3, s), ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcI, false);
-                // Matrix.C:84-470 with w = 0.5, a = 1/deltaf
-                Pm = dcI * f.CQW;
-                Qt = 0.5 * f.CQTheta;
-                Rm = dcI * f.CMQW;
-                S1 = dcI * f.CMTheta;
-                const M3 S2 = -0.5 * spin(f.Mold); // 0.5*CMTheta2
-                const M3 S3 = 0.5 * f.CMQTheta;
-                S23p = S3 + S2;
-                S23m = S3 - S2;
-                eQ = f.eQ; eM = f.eM; eMQ = f.eMQ;
-                // own part of d and u
-                addBlk(D, 0, 0, -1.0, Pm);
-                addBlk(D, 0, 3, 1.0, Qt);
-                addBlk(D, 3, 0, -1.0, Rm);
-                addBlk(D, 3, 3, -1.0, S1);
-                addBlk(D, 3, 3, 1.0, S23p);
-#pragma unroll
-                for (int r = 0; r < 3; r++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        R[r][c] = Pm.a[3 * r + c];
-                        R[r][3 + c] = Qt.a[3 * r + c];
-                        R[3 + r][c] = Rm.a[3 * r + c];
-                        R[3 + r][3 + c] = S1.a[3 * r + c] + S23p.a[3 * r + c];
-                    }
+            {
+                const M3 Rm = (dcI * h) * (SC - SQ);                                      // a*CMQW :706-715
+                smSt9(sm, S_RM, Rm);
+                addBlk(Dc, 3, 0, -1.0, Rm);
+            }
+            const V3 eMQ = h * cross(t, eQ);                                              // :737-741
+            {
+                const V3 CM = smLd3(sm, S_CM);
+                const M3 S1 = dcI * conjDiag(Lm, CM);                                     // a*CMTheta :699
+                const V3 eM = mul(Lm, cmul(CM, ld3(p.K, f3, s)));                         // :684
+                const M3 S3 = (0.5 * h) * (mulSpinR(SC, t) - mulSpinL(t, SQ));            // 0.5*CMQTheta :718-735
+                const V3 Mf = ld3(p.M, f3, s);
+                const M3 S2 = -0.5 * spin(Mf);                                            // 0.5*CMTheta2 :703
+                smSt9(sm, S_S1, S1);
+                smSt9(sm, S_S3, S3);
+                smSt(sm, S_MF, Mf.x); smSt(sm, S_MF + 1, Mf.y); smSt(sm, S_MF + 2, Mf.z);
+                addBlk(Dc, 3, 3, -1.0, S1);
+                addBlk(Dc, 3, 3, 1.0, S3 + S2);
                 subV(src, 0, eQ);
                 subV(src, 3, eM + eMQ);
-            } else { // right patch: face n
-                const M3 Lfb = ld9(p.Lf, f9, s);
-                const EndBC e = loadEnd(p, 1, b, Lfb);
-                const V3 Wb = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb;
-                const V3 t = dR0 + dcB * (Wb - Wi);
-                const FaceCoef f = faceCoefficients(Lfb, refL, CQ, CM, ld3(p.Gam, f3, s), ld3(p.K, f3, s),
-                                                    ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcB, true);
-                bcClosure(D, src, f, e, Lfb, pDelta);
+                smSt(sm, S_SC, eQ.x); smSt(sm, S_SC + 1, eQ.y); smSt(sm, S_SC + 2, eQ.z);
+                smSt(sm, S_SC + 3, eM.x - eMQ.x); smSt(sm, S_SC + 4, eM.y - eMQ.y); smSt(sm, S_SC + 5, eM.z - eMQ.z);
             }
-            // loads: Evolve.C:193-209,274-279
-            const size_t c3 = (size_t)i * 3 * s + b;
-            const double Lcell = p.Lc ? p.Lc[(size_t)i * s + b] : dZ;
-            if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, s));
-            subV(src, 0, Lcell * wgt);
-            if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, s));
-            if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
-                const M3 Lm = ld9(p.Lam, (size_t)i * 9 * s + b, s);
-                V3 Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
-                if (p.first) {
-                    const V3 Uo = ld3(p.U, c3, s);
-                    const double k1 = 1.0 / (dt * beta), k2 = 0.5 / beta - 1.0;
-                    const V3 Ao = Ac, Oo = Om, dOo = dOm;
-                    Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
-                    dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
-                    Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
+        } else { // right patch
+            double D36[36], s6[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                s6[r] = src[r];
+#pragma unroll
+                for (int c = 0; c < 6; c++) D36[6 * r + c] = Dc[r][c];
+            }
+            patchClosure(p, 1, b, Wi, D36, s6);
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                src[r] = s6[r];
+#pragma unroll
+                for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
+            }
+        }
+        // ---- loads: Evolve.C:193-209,274-279
+        const size_t c3 = (size_t)i * 3 * s + b;
+        const double Lcell = p.Lc ? p.Lc[(size_t)i * s + b] : dZ;
+        if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, s));
+        subV(src, 0, Lcell * smLd3(sm, S_WGT));
+        if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, s));
+        if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
+            const M3 Lm = ld9(p.Lam, (size_t)i * 9 * s + b, s);
+            V3 Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
+            if (p.first) {
+                const V3 Uo = ld3(p.U, c3, s);
+                const double k1 = 1.0 / (dt * beta), k2 = 0.5 / beta - 1.0;
+                const V3 Ao = Ac, Oo = Om, dOo = dOm;
+                Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
+                dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
+                Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
+            }
+            const V3 CI = smLd3(sm, S_CI);
+            const V3 CIOm = cmul(CI, Om);
+            const V3 a1 = mul(Lm, cmul(CI, dOm));  // Lambda & (CIRho & dotOmega)
+            const V3 a2 = mul(Lm, cross(Om, CIOm)); // Lambda & (Omega ^ (CIRho & Omega))
+            addV(src, 0, (ARho * Lcell) * Ac);
+            addV(src, 3, Lcell * (a1 + a2));
+            const double QRhoCoeff = -Lcell * ARho / (dt * dt * beta);
+            Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
+            // MRhoCoeff :467-488
+            const M3 T2 = spin(mul(Lm, CIOm)) - mul(Lm, mulSpinL(Om, diagMulT(CI, Lm)));
+            const M3 MR = spin(a2 + a1) + (gamma / (beta * dt)) * T2 - (1.0 / (beta * dt * dt)) * conjDiag(Lm, CI);
+            addBlk(Dc, 3, 3, Lcell, MR);
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
+        // ---- phase B: block elimination operators of D'_i = [[A, B], [C, E]] (now held in Dc)
+        M3 Ai, AiB, Si, Cm;
+        {
+            M3 A, Bm, E;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    A.a[3 * r + c] = Dc[r][c];
+                    Bm.a[3 * r + c] = Dc[r][3 + c];
+                    Cm.a[3 * r + c] = Dc[3 + r][c];
+                    E.a[3 * r + c] = Dc[3 + r][3 + c];
                 }
-                const V3 CIOm = cmul(CI, Om);
-                const V3 a1 = mul(Lm, cmul(CI, dOm));      // Lambda & (CIRho & dotOmega)
-                const V3 a2 = mul(Lm, cross(Om, CIOm));     // Lambda & (Omega ^ (CIRho & Omega))
-                addV(src, 0, (ARho * Lcell) * Ac);
-                addV(src, 3, Lcell * (a1 + a2));
-                const double QRhoCoeff = -Lcell * ARho / (dt * dt * beta);
-                D[0][0] += QRhoCoeff; D[1][1] += QRhoCoeff; D[2][2] += QRhoCoeff;
-                // MRhoCoeff :467-488
-                const M3 LCL = conjDiag(Lm, CI);            // Lambda & (CIRho & Lambda.T())
-                const M3 T2 = spin(mul(Lm, CIOm)) - mul(Lm, mulSpinL(Om, diagMulT(CI, Lm)));
-                const M3 MR = spin(a2 + a1) + (gamma / (beta * dt)) * T2 - (1.0 / (beta * dt * dt)) * LCL;
-                addBlk(D, 3, 3, Lcell, MR);
+            Ai = inv(A);
+            AiB = mul(Ai, Bm);
+            Si = inv(E - mul(Cm, AiB));
+        }
+        // ---- phase C: X = D'^{-1} [u | source - lb], column by column; u comes back from the stash
+        double X1[3][7], X2[3][7];
+        const M3 S2 = -0.5 * spin(smLd3(sm, S_MF)); // only meaningful when !last
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+            if (c < 6 && last) continue;
+            V3 r1, r2;
+            if (c < 3) { // u[:, c] = (P[:, c] ; Rm[:, c])
+                r1 = v3(smLd(sm, S_P + c), smLd(sm, S_P + 3 + c), smLd(sm, S_P + 6 + c));
+                r2 = v3(smLd(sm, S_RM + c), smLd(sm, S_RM + 3 + c), smLd(sm, S_RM + 6 + c));
+            } else if (c < 6) { // u[:, c] = (Qt[:, k] ; (S1 + S3 + S2)[:, k])
+                const int k = c - 3;
+                r1 = v3(smLd(sm, S_QT + k), smLd(sm, S_QT + 3 + k), smLd(sm, S_QT + 6 + k));
+                r2 = v3(smLd(sm, S_S1 + k) + smLd(sm, S_S3 + k) + S2.a[k],
+                        smLd(sm, S_S1 + 3 + k) + smLd(sm, S_S3 + 3 + k) + S2.a[3 + k],
+                        smLd(sm, S_S1 + 6 + k) + smLd(sm, S_S3 + 6 + k) + S2.a[6 + k]);
+            } else { // source_i - l_{i-1} & bPrime_{i-1}
+                r1 = v3(src[0] - lb[0], src[1] - lb[1], src[2] - lb[2]);
+                r2 = v3(src[3] - lb[3], src[4] - lb[4], src[5] - lb[5]);
             }
+            const V3 y1 = mul(Ai, r1);
+            const V3 x2 = mul(Si, r2 - mul(Cm, y1));
+            const V3 x1 = y1 - mul(AiB, x2);
+            X1[0][c] = x1.x; X1[1][c] = x1.y; X1[2][c] = x1.z;
+            X2[0][c] = x2.x; X2[1][c] = x2.y; X2[2][c] = x2.z;
+        }
+        // ---- store uPrime (36) and bPrime (6)
+        const size_t u0 = (size_t)i * 36 * s + b, b0 = (size_t)i * 6 * s + b;
+        if (!last) {
 #pragma unroll
-            for (int r = 0; r < 6; r++) res += src[r] * src[r];
+            for (int r = 0; r < 3; r++)
 #pragma unroll
-            for (int r = 0; r < 6; r++) R[r][6] = src[r] - lb[r];
-            solve6<7>(D, R); // R = D'^{-1} [u | b']
-            const size_t u0 = (size_t)i * 36 * s + b, b0 = (size_t)i * 6 * s + b;
-            if (!last) {
+                for (int c = 0; c < 6; c++) {
+                    p.uP[u0 + (size_t)(6 * r + c) * s] = X1[r][c];
+                    p.uP[u0 + (size_t)(6 * (r + 3) + c) * s] = X2[r][c];
+                }
+        }
 #pragma unroll
-                for (int r = 0; r < 6; r++)
+        for (int r = 0; r < 3; r++) {
+            p.bP[b0 + (size_t)r * s] = X1[r][6];
+            p.bP[b0 + (size_t)(r + 3) * s] = X2[r][6];
+        }
+        if (!last) {
+            // ---- carry for cell i+1:  l = [[P, -Qt], [-Rm, S1 + S23m]],  d_nei = [[-P, -Qt], [Rm, -S1 + S23m]]
+            //      (S23m = S3 - S2)   Dc = d_nei - l & uPrime ;  lb = l & bPrime
+            {
+                const M3 Pm = smLd9(sm, S_P), Qt = smLd9(sm, S_QT);
 #pragma unroll
-                    for (int c = 0; c < 6; c++) p.uP[u0 + (size_t)(6 * r + c) * s] = R[r][c];
-            }
-#pragma unroll
-            for (int r = 0; r < 6; r++) p.bP[b0 + (size_t)r * s] = R[r][6];
-            if (!last) {
-                // carry for cell i+1: nei part of d minus l&uPrime; l&bPrime; nei part of source
-                // l = [[P, -Qt], [-R, S1 + S23m]] ; d_nei = [[-P, -Qt], [R, -S1 + S23m]]
-                double l[6][6];
-#pragma unroll
-                for (int r = 0; r < 3; r++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        l[r][c] = Pm.a[3 * r + c];
-                        l[r][3 + c] = -Qt.a[3 * r + c];
-                        l[3 + r][c] = -Rm.a[3 * r + c];
-                        l[3 + r][3 + c] = S1.a[3 * r + c] + S23m.a[3 * r + c];
-                    }
-#pragma unroll
-                for (int r = 0; r < 6; r++) {
+                for (int r = 0; r < 3; r++) {
 #pragma unroll
                     for (int c = 0; c < 7; c++) {
                         double acc = 0.0;
 #pragma unroll
-                        for (int k = 0; k < 6; k++) acc += l[r][k] * R[k][c];
-                        if (c < 6) Dc[r][c] = -acc; else lb[r] = acc;
+                        for (int k = 0; k < 3; k++) acc += Pm.a[3 * r + k] * X1[k][c] - Qt.a[3 * r + k] * X2[k][c];
+                        if (c < 3) Dc[r][c] = -Pm.a[3 * r + c] - acc;
+                        else if (c < 6) Dc[r][c] = -Qt.a[3 * r + c - 3] - acc;
+                        else lb[r] = acc;
                     }
                 }
-                addBlk(Dc, 0, 0, -1.0, Pm);
-                addBlk(Dc, 0, 3, -1.0, Qt);
-                addBlk(Dc, 3, 0, 1.0, Rm);
-                addBlk(Dc, 3, 3, -1.0, S1);
-                addBlk(Dc, 3, 3, 1.0, S23m);
-                sc[0] = eQ.x; sc[1] = eQ.y; sc[2] = eQ.z;
-                sc[3] = eM.x - eMQ.x; sc[4] = eM.y - eMQ.y; sc[5] = eM.z - eMQ.z;
-                Wi = Wn;
             }
+            {
+                const M3 Rm = smLd9(sm, S_RM), S1 = smLd9(sm, S_S1), Sm = smLd9(sm, S_S3) - S2;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+#pragma unroll
+                    for (int c = 0; c < 7; c++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 3; k++)
+                            acc += (S1.a[3 * r + k] + Sm.a[3 * r + k]) * X2[k][c] - Rm.a[3 * r + k] * X1[k][c];
+                        if (c < 3) Dc[3 + r][c] = Rm.a[3 * r + c] - acc;
+                        else if (c < 6) Dc[3 + r][c] = (Sm.a[3 * r + c - 3] - S1.a[3 * r + c - 3]) - acc;
+                        else lb[3 + r] = acc;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) sc[r] = smLd(sm, S_SC + r);
+            Wi = Wn;
         }
     }
     return res;
@@ -619,26 +763,28 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
 // beam_forward / beam_backward are the same sweeps as two launches, kept for profiling.
 // ---------------------------------------------------------------------------
 template <bool NEWMARK>
-__global__ void __launch_bounds__(128) beam_newton(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS) beam_newton(const BeamParams p)
 {
+    extern __shared__ double beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[3] = {0.0, 0.0, 0.0};
     if (b < p.B) {
-        v[0] = forwardSweep<NEWMARK>(p, b);
+        v[0] = forwardSweep<NEWMARK>(p, b, beam_smem + threadIdx.x);
         backwardSweep<NEWMARK>(p, b, v[1], v[2]);
     }
     blockReduceStore<3>(v, p.partial, 0);
 }
 template <bool NEWMARK>
-__global__ void __launch_bounds__(128) beam_forward(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS) beam_forward(const BeamParams p)
 {
+    extern __shared__ double beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[1] = {0.0};
-    if (b < p.B) v[0] = forwardSweep<NEWMARK>(p, b);
+    if (b < p.B) v[0] = forwardSweep<NEWMARK>(p, b, beam_smem + threadIdx.x);
     blockReduceStore<1>(v, p.partial, 0);
 }
 template <bool NEWMARK>
-__global__ void __launch_bounds__(128) beam_backward(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS) beam_backward(const BeamParams p)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};

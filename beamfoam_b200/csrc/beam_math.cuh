@@ -263,3 +263,38 @@ DEV void solve6(double (&A)[6][6], double (&B)[6][NR])
         }
     }
 }
+
+// ---------------------------------------------------------------------------
+// 6x6 solve by 2x2 block elimination over 3x3 blocks, D = [[A, B], [C, E]]:
+//   X2 = S^{-1} (R2 - C A^{-1} R1),  X1 = A^{-1} R1 - A^{-1} B X2,  S = E - C A^{-1} B,
+// with the 3x3 inverses by adjugate/determinant (the formula OpenFOAM's inv(tensor) uses).
+// No row exchanges, hence no select instructions and no dynamic register indexing.  The
+// ordering is "pivoted by physics": A is the translational block (-2 CQW/dZ minus the mass
+// term, always definite) and S the condensed rotational block.  On return R = D^{-1} R.
+// ---------------------------------------------------------------------------
+template <int NR>
+DEV void solve6blk(const double (&D)[6][6], double (&R)[6][NR])
+{
+    M3 A, Bm, Cm, E;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            A.a[3 * r + c] = D[r][c];
+            Bm.a[3 * r + c] = D[r][3 + c];
+            Cm.a[3 * r + c] = D[3 + r][c];
+            E.a[3 * r + c] = D[3 + r][3 + c];
+        }
+    const M3 Ai = inv(A);
+    const M3 AiB = mul(Ai, Bm);
+    const M3 Si = inv(E - mul(Cm, AiB));
+#pragma unroll
+    for (int c = 0; c < NR; c++) {
+        const V3 y1 = mul(Ai, v3(R[0][c], R[1][c], R[2][c]));
+        const V3 z2 = v3(R[3][c], R[4][c], R[5][c]) - mul(Cm, y1);
+        const V3 x2 = mul(Si, z2);
+        const V3 x1 = y1 - mul(AiB, x2);
+        R[0][c] = x1.x; R[1][c] = x1.y; R[2][c] = x1.z;
+        R[3][c] = x2.x; R[4][c] = x2.y; R[5][c] = x2.z;
+    }
+}

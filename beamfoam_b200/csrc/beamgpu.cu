@@ -19,7 +19,7 @@
 #include <vector>
 
 #define BF_GREAT 1e15
-#define THREADS 128
+#define THREADS BEAM_THREADS
 
 static char g_create_err[512] = "";
 
@@ -225,6 +225,11 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         if (e_ != cudaSuccess) CREATE_FAIL(BF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
     CREATE_CUDA(cudaSetDevice(c->device));
+    // the sweeps park their face tensors in dynamic shared memory (> 48 KB needs the opt-in)
+    CREATE_CUDA(cudaFuncSetAttribute(beam_newton<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_newton<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
@@ -598,15 +603,15 @@ static int launchIteration(bf_ctx* c)
     const BeamParams p = makeParams(c);
     if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[0], c->stream));
     if (c->splitKernels) { // profiling aid: the same two sweeps as two launches
-        if (p.newmark) beam_forward<true><<<c->grid, THREADS, 0, c->stream>>>(p);
-        else beam_forward<false><<<c->grid, THREADS, 0, c->stream>>>(p);
+        if (p.newmark) beam_forward<true><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);
+        else beam_forward<false><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
         if (p.newmark) beam_backward<true><<<c->grid, THREADS, 0, c->stream>>>(p);
         else beam_backward<false><<<c->grid, THREADS, 0, c->stream>>>(p);
         c->launches += 2;
     } else {
-        if (p.newmark) beam_newton<true><<<c->grid, THREADS, 0, c->stream>>>(p);
-        else beam_newton<false><<<c->grid, THREADS, 0, c->stream>>>(p);
+        if (p.newmark) beam_newton<true><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);
+        else beam_newton<false><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
         c->launches += 1;
     }
