@@ -79,6 +79,22 @@ DEV void st9(double* __restrict__ p, size_t i, size_t s, const M3& A)
     for (int k = 0; k < 9; k++) p[i + k * s] = A.a[k];
 }
 
+// L2 prefetch of the rows the NEXT loop iteration will read.  The serial recurrence of a beam
+// leaves only ~2 resident warps per scheduler (register-bound), so the DRAM latency of the loads
+// at the top of an iteration is exposed; pulling the lines into L2 one cell ahead turns it into an
+// L2 hit.  Every lane prefetches its own element: the LSU coalesces a warp into two 128 B lines.
+#ifndef BEAM_NO_PREFETCH
+DEV void pfL2(const double* __restrict__ p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+DEV void pfL2(const double* __restrict__) {}
+#endif
+template <int NR>
+DEV void pfRows(const double* __restrict__ p, size_t i0, size_t s)
+{
+#pragma unroll
+    for (int k = 0; k < NR; k++) pfL2(p + i0 + (size_t)k * s);
+}
+
 // Coefficients of one face (updateEqnCoefficients, Evolve.C:673-753), from the PRE-solve state.
 struct FaceCoef {
     M3 CQW, CQTheta, CMTheta, CMQW, CMQTheta; // CQDTheta == 0 (CTL.C:586-603), CMTheta2 = -spin(M)
@@ -373,6 +389,18 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ s
 #pragma unroll
         for (int r = 0; r < 6; r++) src[r] = sc[r];
         V3 Wn = Wi;
+        if (!last) { // prefetch what iteration i+1 reads: face i+2, W_{i+2}, cell i+1
+            const size_t jn = j + 1;
+            pfRows<9>(p.Lf, jn * 9 * s + b, s);
+            pfRows<3>(p.Gam, jn * 3 * s + b, s); pfRows<3>(p.K, jn * 3 * s + b, s);
+            pfRows<3>(p.Q, jn * 3 * s + b, s); pfRows<3>(p.M, jn * 3 * s + b, s);
+            if (i + 2 < n) pfRows<3>(p.W, jn * 3 * s + b, s);
+            if (NEWMARK) {
+                pfRows<9>(p.Lam, j * 9 * s + b, s);
+                pfRows<3>(p.Ac, j * 3 * s + b, s); pfRows<3>(p.Om, j * 3 * s + b, s); pfRows<3>(p.dOm, j * 3 * s + b, s);
+                if (p.first) pfRows<3>(p.U, j * 3 * s + b, s);
+            }
+        }
         // ---- phase A: coefficients of face i+1, own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
         if (!last) {
             Wn = ld3(p.W, j * 3 * s + b, s);
@@ -678,6 +706,20 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
         for (int i = n - 1; i >= 0; i--) {
             // ---- back substitution: x_i = bPrime_i - uPrime_i & x_{i+1}
             const size_t u0 = (size_t)i * 36 * s + b, b0 = (size_t)i * 6 * s + b;
+            if (i > 0) { // prefetch what iteration i-1 reads: scratch and cell i-1, face i
+                const size_t cm = (size_t)(i - 1), fj = (size_t)i;
+                pfRows<36>(p.uP, cm * 36 * s + b, s);
+                pfRows<6>(p.bP, cm * 6 * s + b, s);
+                pfRows<3>(p.W, cm * 3 * s + b, s); pfRows<3>(p.Th, cm * 3 * s + b, s);
+                pfRows<9>(p.Lam, cm * 9 * s + b, s);
+                if (NEWMARK) {
+                    pfRows<3>(p.U, cm * 3 * s + b, s); pfRows<3>(p.Ac, cm * 3 * s + b, s);
+                    pfRows<3>(p.Om, cm * 3 * s + b, s); pfRows<3>(p.dOm, cm * 3 * s + b, s);
+                }
+                pfRows<9>(p.Lf, fj * 9 * s + b, s);
+                pfRows<3>(p.Gam, fj * 3 * s + b, s); pfRows<3>(p.K, fj * 3 * s + b, s);
+                pfRows<3>(p.Q, fj * 3 * s + b, s); pfRows<3>(p.M, fj * 3 * s + b, s);
+            }
             double x[6];
 #pragma unroll
             for (int r = 0; r < 6; r++) x[r] = p.bP[b0 + (size_t)r * s];
