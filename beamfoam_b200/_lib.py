@@ -77,6 +77,8 @@ EXPORTS = {
     "bf_num_beams": (C.c_int64, [C.c_void_p]),
     "bf_set_field": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bf_get_field": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bf_mirror_begin": (C.c_int, [C.c_void_p, C.c_int32, _ip, C.POINTER(C.c_void_p)]),
+    "bf_mirror_wait": (C.c_int, [C.c_void_p]),
     "bf_set_distributed_loads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bf_set_bc_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "bf_begin_step": (C.c_int, [C.c_void_p, C.c_double]),

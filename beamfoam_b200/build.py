@@ -35,7 +35,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUTPUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUTPUT] + SOURCES + ["-ldl"]
+    extra = os.environ.get("BEAMGPU_NVCC_EXTRA", "").split()  # e.g. -DBEAM_THREADS=64 -DBEAM_MIN_BLOCKS=5
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", OUTPUT] + SOURCES + ["-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as f:

@@ -269,7 +269,12 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 // consecutive threads hit consecutive banks, so every access is conflict-free.  The stash is a
 // register extension: an FP64 warp instruction occupies the pipe for 2 cycles, an LDS.64 costs
 // the same, so parking the face tensors here is cheaper than any local-memory spill.
+#ifndef BEAM_THREADS
 #define BEAM_THREADS 128
+#endif
+#ifndef BEAM_MIN_BLOCKS
+#define BEAM_MIN_BLOCKS 2
+#endif
 enum {
     S_REFL = 0,  // refLambdaf (9)
     S_CQ = 9,    // diag CQ (3)
@@ -805,7 +810,7 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
 // beam_forward / beam_backward are the same sweeps as two launches, kept for profiling.
 // ---------------------------------------------------------------------------
 template <bool NEWMARK>
-__global__ void __launch_bounds__(BEAM_THREADS) beam_newton(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton(const BeamParams p)
 {
     extern __shared__ double beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -817,7 +822,7 @@ __global__ void __launch_bounds__(BEAM_THREADS) beam_newton(const BeamParams p)
     blockReduceStore<3>(v, p.partial, 0);
 }
 template <bool NEWMARK>
-__global__ void __launch_bounds__(BEAM_THREADS) beam_forward(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(const BeamParams p)
 {
     extern __shared__ double beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -826,7 +831,7 @@ __global__ void __launch_bounds__(BEAM_THREADS) beam_forward(const BeamParams p)
     blockReduceStore<1>(v, p.partial, 0);
 }
 template <bool NEWMARK>
-__global__ void __launch_bounds__(BEAM_THREADS) beam_backward(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_backward(const BeamParams p)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
@@ -835,7 +840,8 @@ __global__ void __launch_bounds__(BEAM_THREADS) beam_backward(const BeamParams p
 }
 
 // Deterministic final reduction of the per-block partial sums (fixed order).
-__global__ void beam_reduce_partials(const double* __restrict__ partial, int nBlocks, double* __restrict__ out)
+__global__ void beam_reduce_partials(const double* __restrict__ partial, int nBlocks, double* __restrict__ out,
+                                     double* __restrict__ outHost)
 {
     __shared__ double sm[3][256];
     for (int k = 0; k < 3; k++) {
@@ -849,5 +855,12 @@ __global__ void beam_reduce_partials(const double* __restrict__ partial, int nBl
             for (int k = 0; k < 3; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x < 3) out[threadIdx.x] = sm[threadIdx.x][0];
+    if (threadIdx.x < 3) {
+        out[threadIdx.x] = sm[threadIdx.x][0];
+        if (outHost) outHost[threadIdx.x] = sm[threadIdx.x][0]; // mapped pinned host memory
+    }
+}
+__global__ void beam_publish_sums(const double* __restrict__ in, double* __restrict__ outHost)
+{
+    if (threadIdx.x < 3) outHost[threadIdx.x] = in[threadIdx.x];
 }

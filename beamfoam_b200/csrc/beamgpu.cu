@@ -44,7 +44,7 @@ struct bf_ctx {
     std::vector<int64_t> cellStart, faceStart;
     bool uniformN;
     // device pools
-    void* pools[8];
+    void* pools[12];
     int nPools;
     int32_t *d_nSeg, *d_wType, *d_thType;
     int64_t *d_cellStart, *d_faceStart;
@@ -55,8 +55,11 @@ struct bf_ctx {
         *d_moment, *d_springK, *d_springDir;
     double *d_uP, *d_bP, *d_partial, *d_sums;
     double* d_stage; // staging buffer in host (AoS) ordering
+    double* d_stagePatch; // separate small staging for patch values (never shared with a pending mirror)
     size_t stageDoubles;
-    double* h_sums;  // pinned
+    double* h_sums;  // pinned + mapped: the kernels write the norms straight into host memory, so the
+                     // per-iteration read never queues behind a bulk D2H copy on the copy engine
+    double* d_hsums; // device alias of h_sums
     // options / time state
     int scheme, storeInc;
     double betaN, gammaN, deltaT;
@@ -71,6 +74,10 @@ struct bf_ctx {
     int64_t launches;
     int timing, splitKernels;
     cudaEvent_t evRegion[2];
+    // asynchronous mirroring (bf_mirror_begin / bf_mirror_wait)
+    cudaStream_t copyStream;
+    cudaEvent_t evStaged, evCopied;
+    bool copyPending;
     cudaEvent_t ev[3];
     double fwdMs, bwdMs;
     int64_t timedIters;
@@ -120,21 +127,56 @@ __device__ __forceinline__ int findBeam(const int64_t* __restrict__ start, int B
 }
 
 // cells: host index g = cellStart[b] + i ;  dev index ((i*nc + c)*Bpad + b)
-// faces: host index g = faceStart[b] + (j-1), j = 1..n-1 ; dev face index j
+// faces: host index g = faceStart[b] + (j-1), j = 1..n-1 ; dev face index j = i + faceOffset
+// Tiled through shared memory so that BOTH sides are coalesced: a block moves a tile of
+// 32 beams x 32 cells x nc components; device accesses run along beams (threadIdx.x = beam),
+// host-order accesses run along the contiguous (cell, component) run of one beam.
 template <bool TO_DEVICE>
 __global__ void transposeInternal(double* __restrict__ dev, double* __restrict__ host, const int64_t* __restrict__ start,
-                                  int B, int Bpad, int nc, int64_t count, int faceOffset, int uniformN)
+                                  int B, int Bpad, int nc, int faceOffset)
 {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= count) return;
-    int b;
-    int64_t i;
-    if (uniformN > 0) { b = (int)(g / uniformN); i = g % uniformN; }
-    else { b = findBeam(start, B, g); i = g - start[b]; }
-    i += faceOffset;
-    for (int c = 0; c < nc; c++) {
-        const size_t d = ((size_t)i * nc + c) * Bpad + b;
-        if (TO_DEVICE) dev[d] = host[g * nc + c]; else host[g * nc + c] = dev[d];
+    extern __shared__ double tile[]; // [32 cells][nc][33]
+    const int b0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y; // 32 x 8
+    const int run = 32 * nc;                      // doubles of one beam inside the tile (host order)
+    if (!TO_DEVICE) {
+        const int b = b0 + tx;
+        const int nb = b < B ? (int)(start[b + 1] - start[b]) : 0;
+        for (int k = ty; k < run; k += 8) { // k = il*nc + c
+            const int il = k / nc, c = k - il * nc;
+            const int i = i0 + il;
+            if (i < nb) tile[(size_t)k * 33 + tx] = dev[((size_t)(i + faceOffset) * nc + c) * Bpad + b];
+        }
+        __syncthreads();
+        for (int bl = ty; bl < 32; bl += 8) {
+            const int bb = b0 + bl;
+            if (bb >= B) continue;
+            const int64_t s0 = start[bb];
+            const int nbb = (int)(start[bb + 1] - s0);
+            for (int k = tx; k < run; k += 32) {
+                const int il = k / nc;
+                if (i0 + il < nbb) host[(s0 + i0) * nc + k] = tile[(size_t)k * 33 + bl];
+            }
+        }
+    } else {
+        for (int bl = ty; bl < 32; bl += 8) {
+            const int bb = b0 + bl;
+            if (bb >= B) continue;
+            const int64_t s0 = start[bb];
+            const int nbb = (int)(start[bb + 1] - s0);
+            for (int k = tx; k < run; k += 32) {
+                const int il = k / nc;
+                if (i0 + il < nbb) tile[(size_t)k * 33 + bl] = host[(s0 + i0) * nc + k];
+            }
+        }
+        __syncthreads();
+        const int b = b0 + tx;
+        const int nb = b < B ? (int)(start[b + 1] - start[b]) : 0;
+        for (int k = ty; k < run; k += 8) {
+            const int il = k / nc, c = k - il * nc;
+            const int i = i0 + il;
+            if (i < nb) dev[((size_t)(i + faceOffset) * nc + c) * Bpad + b] = tile[(size_t)k * 33 + tx];
+        }
     }
 }
 // patch values: host [b*nc + c] ; dev ((row*nc + c)*Bpad + b) with row = end (end arrays) or
@@ -161,12 +203,27 @@ __global__ void fillIdentity(double* __restrict__ T, int64_t rows, int Bpad)
     T[(r * 9 + 8) * Bpad + b] = 1.0;
 }
 
+struct bf_ctx;
+template <bool TO_DEVICE>
+static void launchTranspose(bf_ctx* c, double* dev, double* hostOrder, int nc, int surface);
+
 template <typename T>
 static T* carve(char*& cur, size_t count)
 {
     T* p = (T*)cur;
     cur += ((count * sizeof(T) + 255) / 256) * 256;
     return p;
+}
+
+template <bool TO_DEVICE>
+static void launchTranspose(bf_ctx* c, double* dev, double* hostOrder, int nc, int surface)
+{
+    const int rows = surface ? c->nmax - 1 : c->nmax; // internal faces per beam = cells - 1
+    if (rows <= 0) return;
+    const dim3 grid((unsigned)((c->B + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    const size_t smem = sizeof(double) * 32 * nc * 33;
+    transposeInternal<TO_DEVICE><<<grid, block, smem, c->stream>>>(
+        dev, hostOrder, surface ? c->d_faceStart : c->d_cellStart, (int)c->B, c->Bpad, nc, surface);
 }
 
 extern "C" int bf_destroy(bf_ctx* c)
@@ -178,6 +235,9 @@ extern "C" int bf_destroy(bf_ctx* c)
     if (c->h_sums) cudaFreeHost(c->h_sums);
     for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->evRegion[i]) cudaEventDestroy(c->evRegion[i]);
+    if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
+    if (c->evStaged) cudaEventDestroy(c->evStaged);
+    if (c->evCopied) cudaEventDestroy(c->evCopied);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return BF_OK;
@@ -215,7 +275,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->ev[0] = c->ev[1] = c->ev[2] = nullptr;
     c->reducer = nullptr; c->reducerUser = nullptr;
     c->launches = 0; c->timing = 0; c->splitKernels = getenv("BEAMGPU_SPLIT_KERNELS") ? 1 : 0;
-    c->evRegion[0] = c->evRegion[1] = nullptr; c->fwdMs = c->bwdMs = 0; c->timedIters = 0;
+    c->evRegion[0] = c->evRegion[1] = nullptr;
+    c->copyStream = nullptr; c->evStaged = c->evCopied = nullptr; c->copyPending = false; c->fwdMs = c->bwdMs = 0; c->timedIters = 0;
     c->hasQ = c->hasM = false;
     c->d_q = c->d_m = c->d_Lc = c->d_DW = c->d_DTh = nullptr;
 #define CREATE_FAIL(code, ...) do { int rc_ = fail(nullptr, code, __VA_ARGS__); bf_destroy(c); return rc_; } while (0)
@@ -226,6 +287,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     } while (0)
     CREATE_CUDA(cudaSetDevice(c->device));
     // the sweeps park their face tensors in dynamic shared memory (> 48 KB needs the opt-in)
+    CREATE_CUDA(cudaFuncSetAttribute(transposeInternal<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 33 * 8));
+    CREATE_CUDA(cudaFuncSetAttribute(transposeInternal<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 33 * 8));
     CREATE_CUDA(cudaFuncSetAttribute(beam_newton<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_newton<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -233,6 +296,9 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->evStaged, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->evCopied, cudaEventDisableTiming));
 
     const int64_t B = c->B = lay->nBeams;
     c->nSeg.assign(lay->nSeg, lay->nSeg + B);
@@ -307,7 +373,9 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     // ---- staging buffer (largest field in host ordering: a tensor vol field)
     c->stageDoubles = (size_t)c->N * 9;
     if (devAlloc(c, (void**)&c->d_stage, sizeof(double) * c->stageDoubles)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
-    CREATE_CUDA(cudaHostAlloc((void**)&c->h_sums, 8 * sizeof(double), cudaHostAllocDefault));
+    if (devAlloc(c, (void**)&c->d_stagePatch, sizeof(double) * (size_t)B * 9)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+    CREATE_CUDA(cudaHostAlloc((void**)&c->h_sums, 8 * sizeof(double), cudaHostAllocMapped));
+    CREATE_CUDA(cudaHostGetDevicePointer((void**)&c->d_hsums, c->h_sums, 0));
 
     // ---- upload constants
     {
@@ -381,8 +449,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         if (devAlloc(c, (void**)&cur, sizeof(double) * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_Lc = (double*)cur;
         CREATE_CUDA(cudaMemcpyAsync(c->d_stage, lay->cellLength, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
-        transposeInternal<true><<<(unsigned)((c->N + 255) / 256), 256, 0, c->stream>>>(
-            c->d_Lc, c->d_stage, c->d_cellStart, (int)B, Bpad, 1, c->N, 0, uniform ? nmax : 0);
+        launchTranspose<true>(c, c->d_Lc, c->d_stage, 1, 0);
         c->launches++;
     }
     CREATE_CUDA(cudaStreamSynchronize(c->stream));
@@ -414,18 +481,21 @@ static int fieldInfo(bf_ctx* c, int field, double** dev, double** endArr, int* n
     return BF_OK;
 }
 
+static int drainMirror(bf_ctx* c)
+{
+    if (c->copyPending) { CUDA_OK(c, cudaStreamSynchronize(c->copyStream)); c->copyPending = false; }
+    return BF_OK;
+}
 static int xferInternal(bf_ctx* c, double* dev, double* host, int nc, int surface, bool toDevice)
 {
+    if (int rc = drainMirror(c)) return rc;
     const int64_t count = surface ? c->F : c->N;
     if (count == 0) return BF_OK;
-    const int64_t* start = surface ? c->d_faceStart : c->d_cellStart;
-    const int uni = c->uniformN ? (surface ? c->nmax - 1 : c->nmax) : 0;
-    const unsigned grid = (unsigned)((count + 255) / 256);
     if (toDevice) {
         CUDA_OK(c, cudaMemcpyAsync(c->d_stage, host, sizeof(double) * count * nc, cudaMemcpyHostToDevice, c->stream));
-        transposeInternal<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stage, start, (int)c->B, c->Bpad, nc, count, surface, uni);
+        launchTranspose<true>(c, dev, c->d_stage, nc, surface);
     } else {
-        transposeInternal<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stage, start, (int)c->B, c->Bpad, nc, count, surface, uni);
+        launchTranspose<false>(c, dev, c->d_stage, nc, surface);
         CUDA_OK(c, cudaMemcpyAsync(host, c->d_stage, sizeof(double) * count * nc, cudaMemcpyDeviceToHost, c->stream));
     }
     c->launches++;
@@ -438,11 +508,11 @@ static int xferPatch(bf_ctx* c, double* dev, double* host, int nc, int end, int 
     const unsigned grid = (unsigned)((c->B + 255) / 256);
     const size_t bytes = sizeof(double) * c->B * nc;
     if (toDevice) {
-        CUDA_OK(c, cudaMemcpyAsync(c->d_stage, host, bytes, cudaMemcpyHostToDevice, c->stream));
-        transposePatch<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stage, c->d_nSeg, (int)c->B, c->Bpad, nc, end, faceArray);
+        CUDA_OK(c, cudaMemcpyAsync(c->d_stagePatch, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        transposePatch<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, nc, end, faceArray);
     } else {
-        transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stage, c->d_nSeg, (int)c->B, c->Bpad, nc, end, faceArray);
-        CUDA_OK(c, cudaMemcpyAsync(host, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+        transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, nc, end, faceArray);
+        CUDA_OK(c, cudaMemcpyAsync(host, c->d_stagePatch, bytes, cudaMemcpyDeviceToHost, c->stream));
     }
     c->launches++;
     CUDA_OK(c, cudaGetLastError());
@@ -491,6 +561,53 @@ extern "C" int bf_get_field(bf_ctx* c, int32_t field, double* internal, double* 
         else if (endArr) { if ((rc = xferPatch(c, endArr, sides[end], nc, end, 0, false))) return rc; }
         else return fail(c, BF_ERR_INVALID, "field %d has no mirrored boundary values", field);
     }
+    return BF_OK;
+}
+
+// Asynchronous mirror of internal fields into (pinned) host buffers: the fields are transposed
+// to the reference ordering into disjoint regions of the staging buffer on the compute stream,
+// then copied device->host on a second stream, so the copy of step k overlaps the Newton loop of
+// step k+1.  bf_mirror_wait() (or the next bf_mirror_begin) waits for the copies.
+extern "C" int bf_mirror_begin(bf_ctx* c, int32_t nFields, const int32_t* fields, double* const* hostInternal)
+{
+    if (nFields < 1 || !fields || !hostInternal) return fail(c, BF_ERR_INVALID, "bf_mirror_begin: bad argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    if (c->copyPending) { // the staging regions are about to be overwritten
+        CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->evCopied, 0));
+    }
+    size_t off = 0;
+    struct Job { double* host; size_t off, count; } jobs[16];
+    if (nFields > 16) return fail(c, BF_ERR_INVALID, "bf_mirror_begin: at most 16 fields");
+    for (int k = 0; k < nFields; k++) {
+        double *dev, *endArr; int nc, surf;
+        int rc = fieldInfo(c, fields[k], &dev, &endArr, &nc, &surf);
+        if (rc) return rc;
+        if (!dev) return fail(c, BF_ERR_INVALID, "field %d is not kept in this context", fields[k]);
+        const int64_t count = surf ? c->F : c->N;
+        if (off + (size_t)count * nc > c->stageDoubles) return fail(c, BF_ERR_INVALID, "bf_mirror_begin: fields exceed the staging buffer (9 doubles per cell)");
+        if (count > 0) {
+            launchTranspose<false>(c, dev, c->d_stage + off, nc, surf);
+            c->launches++;
+        }
+        jobs[k] = {hostInternal[k], off, (size_t)count * nc};
+        off += (size_t)count * nc;
+    }
+    CUDA_OK(c, cudaGetLastError());
+    CUDA_OK(c, cudaEventRecord(c->evStaged, c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->copyStream, c->evStaged, 0));
+    for (int k = 0; k < nFields; k++)
+        if (jobs[k].count)
+            CUDA_OK(c, cudaMemcpyAsync(jobs[k].host, c->d_stage + jobs[k].off, sizeof(double) * jobs[k].count,
+                                       cudaMemcpyDeviceToHost, c->copyStream));
+    CUDA_OK(c, cudaEventRecord(c->evCopied, c->copyStream));
+    c->copyPending = true;
+    return BF_OK;
+}
+extern "C" int bf_mirror_wait(bf_ctx* c)
+{
+    CUDA_OK(c, cudaSetDevice(c->device));
+    CUDA_OK(c, cudaStreamSynchronize(c->copyStream));
+    c->copyPending = false;
     return BF_OK;
 }
 
@@ -616,7 +733,7 @@ static int launchIteration(bf_ctx* c)
         c->launches += 1;
     }
     if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[2], c->stream));
-    beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->grid, c->d_sums);
+    beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->grid, c->d_sums, c->comm ? nullptr : c->d_hsums);
     c->launches += 1;
     CUDA_OK(c, cudaGetLastError());
     c->iOuterCorr++;
@@ -625,7 +742,10 @@ static int launchIteration(bf_ctx* c)
 
 static int fetchSums(bf_ctx* c, double sumsq[3])
 {
-    CUDA_OK(c, cudaMemcpyAsync(c->h_sums, c->d_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (c->comm) { // the all-reduced sums live in device memory: publish them to the mapped host words
+        beam_publish_sums<<<1, 32, 0, c->stream>>>(c->d_sums, c->d_hsums);
+        c->launches++;
+    }
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 3; k++) sumsq[k] = c->h_sums[k];
     if (c->timing) {

@@ -207,6 +207,16 @@ int bf_set_field(bf_ctx* ctx, int32_t field, const double* internal,
 int bf_get_field(bf_ctx* ctx, int32_t field, double* internal,
                  double* left, double* right);
 
+/* Asynchronous mirror of the INTERNAL parts of nFields fields (reference ordering) into host
+ * buffers, which should be pinned (bf_host_alloc): returns once the copies are queued; they
+ * overlap whatever the context does next (the Newton loop of the following step).
+ * bf_mirror_wait blocks until the host buffers are complete.  At most 9 doubles per cell in
+ * total per call (e.g. W + Theta + one more vector field).  Synchronous transfers of INTERNAL
+ * fields (bf_set_field / bf_get_field) drain a pending mirror first; patch-value transfers
+ * (bf_set_bc_values, boundary-only bf_get_field) do not. */
+int bf_mirror_begin(bf_ctx* ctx, int32_t nFields, const int32_t* fields, double* const* hostInternal);
+int bf_mirror_wait(bf_ctx* ctx);
+
 /* Distributed loads q, m (volVectorFields "q","m"; Evolve.C:193-198,274-279).
  * [nCells*3] each; NULL => zero. */
 int bf_set_distributed_loads(bf_ctx* ctx, const double* q, const double* m);

@@ -402,6 +402,17 @@ int bf_get_field(bf_ctx* c, int32_t field, double* internal, double* left, doubl
     return BF_OK;
 }
 
+int bf_mirror_begin(bf_ctx* c, int32_t nFields, const int32_t* fields, double* const* hostInternal)
+{
+    if (nFields < 1 || !fields || !hostInternal) { snprintf(c->err, sizeof c->err, "bf_mirror_begin: bad argument"); return BF_ERR_INVALID; }
+    for (int k = 0; k < nFields; k++) {
+        int rc = bf_get_field(c, fields[k], hostInternal[k], NULL, NULL);
+        if (rc) return rc;
+    }
+    return BF_OK;
+}
+int bf_mirror_wait(bf_ctx* c) { (void)c; return BF_OK; }
+
 int bf_set_distributed_loads(bf_ctx* c, const double* q, const double* m)
 {
     if (q) memcpy(c->q, q, sizeof(double) * 3 * c->N); else memset(c->q, 0, sizeof(double) * 3 * c->N);
