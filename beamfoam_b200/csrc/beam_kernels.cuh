@@ -83,7 +83,9 @@ DEV void st9(double* __restrict__ p, size_t i, size_t s, const M3& A)
 // leaves only ~2 resident warps per scheduler (register-bound), so the DRAM latency of the loads
 // at the top of an iteration is exposed; pulling the lines into L2 one cell ahead turns it into an
 // L2 hit.  Every lane prefetches its own element: the LSU coalesces a warp into two 128 B lines.
-#ifndef BEAM_NO_PREFETCH
+#if defined(BEAM_PREFETCH_L1)
+DEV void pfL2(const double* __restrict__ p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#elif !defined(BEAM_NO_PREFETCH)
 DEV void pfL2(const double* __restrict__ p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #else
 DEV void pfL2(const double* __restrict__) {}
@@ -342,6 +344,226 @@ __device__ __noinline__ void patchClosure(const BeamParams& p, int end, int b, V
     }
 }
 
+// One cell of the forward sweep.  LAST = the cell whose right face is the right patch: it has no
+// u block, closes the patch instead of an internal face and produces no carry.  Splitting the two
+// cases at compile time keeps the patch code out of the steady-state loop's register allocation.
+template <bool NEWMARK, bool LAST>
+DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, const int i, const int n,
+                     const double dZ, const double dcI, const double ARho, double (&Dc)[6][6], double (&sc)[6],
+                     double (&lb)[6], V3& Wi, double& res)
+{
+    const size_t s = p.Bpad;
+    const double dt = p.dt, beta = p.beta, gamma = p.gamma;
+    const size_t j = (size_t)(i + 1);
+    const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
+    double src[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) src[r] = sc[r];
+    V3 Wn = Wi;
+    if (!LAST) { // prefetch what iteration i+1 reads: face i+2, W_{i+2}, cell i+1
+        const size_t jn = j + 1;
+        pfRows<9>(p.Lf, jn * 9 * s + b, s);
+        pfRows<3>(p.Gam, jn * 3 * s + b, s); pfRows<3>(p.K, jn * 3 * s + b, s);
+        pfRows<3>(p.Q, jn * 3 * s + b, s); pfRows<3>(p.M, jn * 3 * s + b, s);
+        if (i + 2 < n) pfRows<3>(p.W, jn * 3 * s + b, s);
+        if (NEWMARK) {
+            pfRows<9>(p.Lam, j * 9 * s + b, s);
+            pfRows<3>(p.Ac, j * 3 * s + b, s); pfRows<3>(p.Om, j * 3 * s + b, s); pfRows<3>(p.dOm, j * 3 * s + b, s);
+            if (p.first) pfRows<3>(p.U, j * 3 * s + b, s);
+        }
+    }
+    // ---- phase A: coefficients of face i+1, own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
+    if (!LAST) {
+        Wn = ld3(p.W, j * 3 * s + b, s);
+        const M3 Lm = mul(ld9(p.Lf, f9, s), smLd9(sm, S_REFL));                       // Evolve.C:678
+        const V3 t = v3(smLd(sm, S_REFL) + dcI * (Wn.x - Wi.x), smLd(sm, S_REFL + 3) + dcI * (Wn.y - Wi.y),
+                        smLd(sm, S_REFL + 6) + dcI * (Wn.z - Wi.z));                  // dR0Ds + snGrad(W)
+        const double h = 0.5 / dcI;
+        V3 eQ;
+        M3 SC;
+        const M3 SQ = spin(ld3(p.Q, f3, s));
+        {
+            const V3 CQ = smLd3(sm, S_CQ);
+            const M3 CQW = conjDiag(Lm, CQ);                                          // :680
+            eQ = mul(Lm, cmul(CQ, ld3(p.Gam, f3, s)));                                // :682
+            SC = mulSpinL(t, CQW);
+            const M3 Pm = dcI * CQW;
+            const M3 Qt = 0.5 * (mulSpinR(CQW, t) - SQ);                              // 0.5*CQTheta :686-693
+            smSt9(sm, S_P, Pm);
+            smSt9(sm, S_QT, Qt);
+            addBlk(Dc, 0, 0, -1.0, Pm);
+            addBlk(Dc, 0, 3, 1.0, Qt);
+        }
+        {
+            const M3 Rm = (dcI * h) * (SC - SQ);                                      // a*CMQW :706-715
+            smSt9(sm, S_RM, Rm);
+            addBlk(Dc, 3, 0, -1.0, Rm);
+        }
+        const V3 eMQ = h * cross(t, eQ);                                              // :737-741
+        {
+            const V3 CM = smLd3(sm, S_CM);
+            const M3 S1 = dcI * conjDiag(Lm, CM);                                     // a*CMTheta :699
+            const V3 eM = mul(Lm, cmul(CM, ld3(p.K, f3, s)));                         // :684
+            const M3 S3 = (0.5 * h) * (mulSpinR(SC, t) - mulSpinL(t, SQ));            // 0.5*CMQTheta :718-735
+            const V3 Mf = ld3(p.M, f3, s);
+            const M3 S2 = -0.5 * spin(Mf);                                            // 0.5*CMTheta2 :703
+            smSt9(sm, S_S1, S1);
+            smSt9(sm, S_S3, S3);
+            smSt(sm, S_MF, Mf.x); smSt(sm, S_MF + 1, Mf.y); smSt(sm, S_MF + 2, Mf.z);
+            addBlk(Dc, 3, 3, -1.0, S1);
+            addBlk(Dc, 3, 3, 1.0, S3 + S2);
+            subV(src, 0, eQ);
+            subV(src, 3, eM + eMQ);
+            smSt(sm, S_SC, eQ.x); smSt(sm, S_SC + 1, eQ.y); smSt(sm, S_SC + 2, eQ.z);
+            smSt(sm, S_SC + 3, eM.x - eMQ.x); smSt(sm, S_SC + 4, eM.y - eMQ.y); smSt(sm, S_SC + 5, eM.z - eMQ.z);
+        }
+    } else { // right patch
+        double D36[36], s6[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            s6[r] = src[r];
+#pragma unroll
+            for (int c = 0; c < 6; c++) D36[6 * r + c] = Dc[r][c];
+        }
+        patchClosure(p, 1, b, Wi, D36, s6);
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            src[r] = s6[r];
+#pragma unroll
+            for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
+        }
+    }
+    // ---- loads: Evolve.C:193-209,274-279
+    const size_t c3 = (size_t)i * 3 * s + b;
+    const double Lcell = p.Lc ? p.Lc[(size_t)i * s + b] : dZ;
+    if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, s));
+    subV(src, 0, Lcell * smLd3(sm, S_WGT));
+    if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, s));
+    if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
+        const M3 Lm = ld9(p.Lam, (size_t)i * 9 * s + b, s);
+        V3 Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
+        if (p.first) {
+            const V3 Uo = ld3(p.U, c3, s);
+            const double k1 = 1.0 / (dt * beta), k2 = 0.5 / beta - 1.0;
+            const V3 Ao = Ac, Oo = Om, dOo = dOm;
+            Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
+            dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
+            Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
+        }
+        const V3 CI = smLd3(sm, S_CI);
+        const V3 CIOm = cmul(CI, Om);
+        const V3 a1 = mul(Lm, cmul(CI, dOm));  // Lambda & (CIRho & dotOmega)
+        const V3 a2 = mul(Lm, cross(Om, CIOm)); // Lambda & (Omega ^ (CIRho & Omega))
+        addV(src, 0, (ARho * Lcell) * Ac);
+        addV(src, 3, Lcell * (a1 + a2));
+        const double QRhoCoeff = -Lcell * ARho / (dt * dt * beta);
+        Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
+        // MRhoCoeff :467-488
+        const M3 T2 = spin(mul(Lm, CIOm)) - mul(Lm, mulSpinL(Om, diagMulT(CI, Lm)));
+        const M3 MR = spin(a2 + a1) + (gamma / (beta * dt)) * T2 - (1.0 / (beta * dt * dt)) * conjDiag(Lm, CI);
+        addBlk(Dc, 3, 3, Lcell, MR);
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
+    // ---- phase B: block elimination operators of D'_i = [[A, B], [C, E]] (now held in Dc)
+    M3 Ai, AiB, Si, Cm;
+    {
+        M3 A, Bm, E;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                A.a[3 * r + c] = Dc[r][c];
+                Bm.a[3 * r + c] = Dc[r][3 + c];
+                Cm.a[3 * r + c] = Dc[3 + r][c];
+                E.a[3 * r + c] = Dc[3 + r][3 + c];
+            }
+        Ai = inv(A);
+        AiB = mul(Ai, Bm);
+        Si = inv(E - mul(Cm, AiB));
+    }
+    // ---- phase C: X = D'^{-1} [u | source - lb], column by column; u comes back from the stash
+    double X1[3][7], X2[3][7];
+    const M3 S2 = -0.5 * spin(smLd3(sm, S_MF)); // only meaningful when !last
+#pragma unroll
+    for (int c = 0; c < 7; c++) {
+        if (c < 6 && LAST) continue;
+        V3 r1, r2;
+        if (c < 3) { // u[:, c] = (P[:, c] ; Rm[:, c])
+            r1 = v3(smLd(sm, S_P + c), smLd(sm, S_P + 3 + c), smLd(sm, S_P + 6 + c));
+            r2 = v3(smLd(sm, S_RM + c), smLd(sm, S_RM + 3 + c), smLd(sm, S_RM + 6 + c));
+        } else if (c < 6) { // u[:, c] = (Qt[:, k] ; (S1 + S3 + S2)[:, k])
+            const int k = c - 3;
+            r1 = v3(smLd(sm, S_QT + k), smLd(sm, S_QT + 3 + k), smLd(sm, S_QT + 6 + k));
+            r2 = v3(smLd(sm, S_S1 + k) + smLd(sm, S_S3 + k) + S2.a[k],
+                    smLd(sm, S_S1 + 3 + k) + smLd(sm, S_S3 + 3 + k) + S2.a[3 + k],
+                    smLd(sm, S_S1 + 6 + k) + smLd(sm, S_S3 + 6 + k) + S2.a[6 + k]);
+        } else { // source_i - l_{i-1} & bPrime_{i-1}
+            r1 = v3(src[0] - lb[0], src[1] - lb[1], src[2] - lb[2]);
+            r2 = v3(src[3] - lb[3], src[4] - lb[4], src[5] - lb[5]);
+        }
+        const V3 y1 = mul(Ai, r1);
+        const V3 x2 = mul(Si, r2 - mul(Cm, y1));
+        const V3 x1 = y1 - mul(AiB, x2);
+        X1[0][c] = x1.x; X1[1][c] = x1.y; X1[2][c] = x1.z;
+        X2[0][c] = x2.x; X2[1][c] = x2.y; X2[2][c] = x2.z;
+    }
+    // ---- store uPrime (36) and bPrime (6)
+    const size_t u0 = (size_t)i * 36 * s + b, b0 = (size_t)i * 6 * s + b;
+    if (!LAST) {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                p.uP[u0 + (size_t)(6 * r + c) * s] = X1[r][c];
+                p.uP[u0 + (size_t)(6 * (r + 3) + c) * s] = X2[r][c];
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        p.bP[b0 + (size_t)r * s] = X1[r][6];
+        p.bP[b0 + (size_t)(r + 3) * s] = X2[r][6];
+    }
+    if (!LAST) {
+        // ---- carry for cell i+1:  l = [[P, -Qt], [-Rm, S1 + S23m]],  d_nei = [[-P, -Qt], [Rm, -S1 + S23m]]
+        //      (S23m = S3 - S2)   Dc = d_nei - l & uPrime ;  lb = l & bPrime
+        {
+            const M3 Pm = smLd9(sm, S_P), Qt = smLd9(sm, S_QT);
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int c = 0; c < 7; c++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) acc += Pm.a[3 * r + k] * X1[k][c] - Qt.a[3 * r + k] * X2[k][c];
+                    if (c < 3) Dc[r][c] = -Pm.a[3 * r + c] - acc;
+                    else if (c < 6) Dc[r][c] = -Qt.a[3 * r + c - 3] - acc;
+                    else lb[r] = acc;
+                }
+            }
+        }
+        {
+            const M3 Rm = smLd9(sm, S_RM), S1 = smLd9(sm, S_S1), Sm = smLd9(sm, S_S3) - S2;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int c = 0; c < 7; c++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                        acc += (S1.a[3 * r + k] + Sm.a[3 * r + k]) * X2[k][c] - Rm.a[3 * r + k] * X1[k][c];
+                    if (c < 3) Dc[3 + r][c] = Rm.a[3 * r + c] - acc;
+                    else if (c < 6) Dc[3 + r][c] = (Sm.a[3 * r + c - 3] - S1.a[3 * r + c - 3]) - acc;
+                    else lb[3 + r] = acc;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) sc[r] = smLd(sm, S_SC + r);
+        Wi = Wn;
+    }
+}
+
 template <bool NEWMARK>
 DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ sm)
 {
@@ -360,7 +582,6 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ s
         smSt(sm, S_WGT, wg.x); smSt(sm, S_WGT + 1, wg.y); smSt(sm, S_WGT + 2, wg.z);
     }
     const double ARho = NEWMARK ? p.ARho[b] : 0.0;
-    const double dt = p.dt, beta = p.beta, gamma = p.gamma;
 
     // loop-carried: Dc = (nei part of d_i) - l_{i-1} & uPrime_{i-1};  lb = l_{i-1} & bPrime_{i-1};
     // sc = nei part of source_i;  Wi = W of cell i
@@ -386,217 +607,8 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ s
             for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
         }
     }
-    for (int i = 0; i < n; i++) {
-        const bool last = (i == n - 1);
-        const size_t j = (size_t)(i + 1);
-        const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
-        double src[6];
-#pragma unroll
-        for (int r = 0; r < 6; r++) src[r] = sc[r];
-        V3 Wn = Wi;
-        if (!last) { // prefetch what iteration i+1 reads: face i+2, W_{i+2}, cell i+1
-            const size_t jn = j + 1;
-            pfRows<9>(p.Lf, jn * 9 * s + b, s);
-            pfRows<3>(p.Gam, jn * 3 * s + b, s); pfRows<3>(p.K, jn * 3 * s + b, s);
-            pfRows<3>(p.Q, jn * 3 * s + b, s); pfRows<3>(p.M, jn * 3 * s + b, s);
-            if (i + 2 < n) pfRows<3>(p.W, jn * 3 * s + b, s);
-            if (NEWMARK) {
-                pfRows<9>(p.Lam, j * 9 * s + b, s);
-                pfRows<3>(p.Ac, j * 3 * s + b, s); pfRows<3>(p.Om, j * 3 * s + b, s); pfRows<3>(p.dOm, j * 3 * s + b, s);
-                if (p.first) pfRows<3>(p.U, j * 3 * s + b, s);
-            }
-        }
-        // ---- phase A: coefficients of face i+1, own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
-        if (!last) {
-            Wn = ld3(p.W, j * 3 * s + b, s);
-            const M3 Lm = mul(ld9(p.Lf, f9, s), smLd9(sm, S_REFL));                       // Evolve.C:678
-            const V3 t = v3(smLd(sm, S_REFL) + dcI * (Wn.x - Wi.x), smLd(sm, S_REFL + 3) + dcI * (Wn.y - Wi.y),
-                            smLd(sm, S_REFL + 6) + dcI * (Wn.z - Wi.z));                  // dR0Ds + snGrad(W)
-            const double h = 0.5 / dcI;
-            V3 eQ;
-            M3 SC;
-            const M3 SQ = spin(ld3(p.Q, f3, s));
-            {
-                const V3 CQ = smLd3(sm, S_CQ);
-                const M3 CQW = conjDiag(Lm, CQ);                                          // :680
-                eQ = mul(Lm, cmul(CQ, ld3(p.Gam, f3, s)));                                // :682
-                SC = mulSpinL(t, CQW);
-                const M3 Pm = dcI * CQW;
-                const M3 Qt = 0.5 * (mulSpinR(CQW, t) - SQ);                              // 0.5*CQTheta :686-693
-                smSt9(sm, S_P, Pm);
-                smSt9(sm, S_QT, Qt);
-                addBlk(Dc, 0, 0, -1.0, Pm);
-                addBlk(Dc, 0, 3, 1.0, Qt);
-            }
-            {
-                const M3 Rm = (dcI * h) * (SC - SQ);                                      // a*CMQW :706-715
-                smSt9(sm, S_RM, Rm);
-                addBlk(Dc, 3, 0, -1.0, Rm);
-            }
-            const V3 eMQ = h * cross(t, eQ);                                              // :737-741
-            {
-                const V3 CM = smLd3(sm, S_CM);
-                const M3 S1 = dcI * conjDiag(Lm, CM);                                     // a*CMTheta :699
-                const V3 eM = mul(Lm, cmul(CM, ld3(p.K, f3, s)));                         // :684
-                const M3 S3 = (0.5 * h) * (mulSpinR(SC, t) - mulSpinL(t, SQ));            // 0.5*CMQTheta :718-735
-                const V3 Mf = ld3(p.M, f3, s);
-                const M3 S2 = -0.5 * spin(Mf);                                            // 0.5*CMTheta2 :703
-                smSt9(sm, S_S1, S1);
-                smSt9(sm, S_S3, S3);
-                smSt(sm, S_MF, Mf.x); smSt(sm, S_MF + 1, Mf.y); smSt(sm, S_MF + 2, Mf.z);
-                addBlk(Dc, 3, 3, -1.0, S1);
-                addBlk(Dc, 3, 3, 1.0, S3 + S2);
-                subV(src, 0, eQ);
-                subV(src, 3, eM + eMQ);
-                smSt(sm, S_SC, eQ.x); smSt(sm, S_SC + 1, eQ.y); smSt(sm, S_SC + 2, eQ.z);
-                smSt(sm, S_SC + 3, eM.x - eMQ.x); smSt(sm, S_SC + 4, eM.y - eMQ.y); smSt(sm, S_SC + 5, eM.z - eMQ.z);
-            }
-        } else { // right patch
-            double D36[36], s6[6];
-#pragma unroll
-            for (int r = 0; r < 6; r++) {
-                s6[r] = src[r];
-#pragma unroll
-                for (int c = 0; c < 6; c++) D36[6 * r + c] = Dc[r][c];
-            }
-            patchClosure(p, 1, b, Wi, D36, s6);
-#pragma unroll
-            for (int r = 0; r < 6; r++) {
-                src[r] = s6[r];
-#pragma unroll
-                for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
-            }
-        }
-        // ---- loads: Evolve.C:193-209,274-279
-        const size_t c3 = (size_t)i * 3 * s + b;
-        const double Lcell = p.Lc ? p.Lc[(size_t)i * s + b] : dZ;
-        if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, s));
-        subV(src, 0, Lcell * smLd3(sm, S_WGT));
-        if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, s));
-        if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
-            const M3 Lm = ld9(p.Lam, (size_t)i * 9 * s + b, s);
-            V3 Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
-            if (p.first) {
-                const V3 Uo = ld3(p.U, c3, s);
-                const double k1 = 1.0 / (dt * beta), k2 = 0.5 / beta - 1.0;
-                const V3 Ao = Ac, Oo = Om, dOo = dOm;
-                Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
-                dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
-                Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
-            }
-            const V3 CI = smLd3(sm, S_CI);
-            const V3 CIOm = cmul(CI, Om);
-            const V3 a1 = mul(Lm, cmul(CI, dOm));  // Lambda & (CIRho & dotOmega)
-            const V3 a2 = mul(Lm, cross(Om, CIOm)); // Lambda & (Omega ^ (CIRho & Omega))
-            addV(src, 0, (ARho * Lcell) * Ac);
-            addV(src, 3, Lcell * (a1 + a2));
-            const double QRhoCoeff = -Lcell * ARho / (dt * dt * beta);
-            Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
-            // MRhoCoeff :467-488
-            const M3 T2 = spin(mul(Lm, CIOm)) - mul(Lm, mulSpinL(Om, diagMulT(CI, Lm)));
-            const M3 MR = spin(a2 + a1) + (gamma / (beta * dt)) * T2 - (1.0 / (beta * dt * dt)) * conjDiag(Lm, CI);
-            addBlk(Dc, 3, 3, Lcell, MR);
-        }
-#pragma unroll
-        for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
-        // ---- phase B: block elimination operators of D'_i = [[A, B], [C, E]] (now held in Dc)
-        M3 Ai, AiB, Si, Cm;
-        {
-            M3 A, Bm, E;
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    A.a[3 * r + c] = Dc[r][c];
-                    Bm.a[3 * r + c] = Dc[r][3 + c];
-                    Cm.a[3 * r + c] = Dc[3 + r][c];
-                    E.a[3 * r + c] = Dc[3 + r][3 + c];
-                }
-            Ai = inv(A);
-            AiB = mul(Ai, Bm);
-            Si = inv(E - mul(Cm, AiB));
-        }
-        // ---- phase C: X = D'^{-1} [u | source - lb], column by column; u comes back from the stash
-        double X1[3][7], X2[3][7];
-        const M3 S2 = -0.5 * spin(smLd3(sm, S_MF)); // only meaningful when !last
-#pragma unroll
-        for (int c = 0; c < 7; c++) {
-            if (c < 6 && last) continue;
-            V3 r1, r2;
-            if (c < 3) { // u[:, c] = (P[:, c] ; Rm[:, c])
-                r1 = v3(smLd(sm, S_P + c), smLd(sm, S_P + 3 + c), smLd(sm, S_P + 6 + c));
-                r2 = v3(smLd(sm, S_RM + c), smLd(sm, S_RM + 3 + c), smLd(sm, S_RM + 6 + c));
-            } else if (c < 6) { // u[:, c] = (Qt[:, k] ; (S1 + S3 + S2)[:, k])
-                const int k = c - 3;
-                r1 = v3(smLd(sm, S_QT + k), smLd(sm, S_QT + 3 + k), smLd(sm, S_QT + 6 + k));
-                r2 = v3(smLd(sm, S_S1 + k) + smLd(sm, S_S3 + k) + S2.a[k],
-                        smLd(sm, S_S1 + 3 + k) + smLd(sm, S_S3 + 3 + k) + S2.a[3 + k],
-                        smLd(sm, S_S1 + 6 + k) + smLd(sm, S_S3 + 6 + k) + S2.a[6 + k]);
-            } else { // source_i - l_{i-1} & bPrime_{i-1}
-                r1 = v3(src[0] - lb[0], src[1] - lb[1], src[2] - lb[2]);
-                r2 = v3(src[3] - lb[3], src[4] - lb[4], src[5] - lb[5]);
-            }
-            const V3 y1 = mul(Ai, r1);
-            const V3 x2 = mul(Si, r2 - mul(Cm, y1));
-            const V3 x1 = y1 - mul(AiB, x2);
-            X1[0][c] = x1.x; X1[1][c] = x1.y; X1[2][c] = x1.z;
-            X2[0][c] = x2.x; X2[1][c] = x2.y; X2[2][c] = x2.z;
-        }
-        // ---- store uPrime (36) and bPrime (6)
-        const size_t u0 = (size_t)i * 36 * s + b, b0 = (size_t)i * 6 * s + b;
-        if (!last) {
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 6; c++) {
-                    p.uP[u0 + (size_t)(6 * r + c) * s] = X1[r][c];
-                    p.uP[u0 + (size_t)(6 * (r + 3) + c) * s] = X2[r][c];
-                }
-        }
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            p.bP[b0 + (size_t)r * s] = X1[r][6];
-            p.bP[b0 + (size_t)(r + 3) * s] = X2[r][6];
-        }
-        if (!last) {
-            // ---- carry for cell i+1:  l = [[P, -Qt], [-Rm, S1 + S23m]],  d_nei = [[-P, -Qt], [Rm, -S1 + S23m]]
-            //      (S23m = S3 - S2)   Dc = d_nei - l & uPrime ;  lb = l & bPrime
-            {
-                const M3 Pm = smLd9(sm, S_P), Qt = smLd9(sm, S_QT);
-#pragma unroll
-                for (int r = 0; r < 3; r++) {
-#pragma unroll
-                    for (int c = 0; c < 7; c++) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 3; k++) acc += Pm.a[3 * r + k] * X1[k][c] - Qt.a[3 * r + k] * X2[k][c];
-                        if (c < 3) Dc[r][c] = -Pm.a[3 * r + c] - acc;
-                        else if (c < 6) Dc[r][c] = -Qt.a[3 * r + c - 3] - acc;
-                        else lb[r] = acc;
-                    }
-                }
-            }
-            {
-                const M3 Rm = smLd9(sm, S_RM), S1 = smLd9(sm, S_S1), Sm = smLd9(sm, S_S3) - S2;
-#pragma unroll
-                for (int r = 0; r < 3; r++) {
-#pragma unroll
-                    for (int c = 0; c < 7; c++) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 3; k++)
-                            acc += (S1.a[3 * r + k] + Sm.a[3 * r + k]) * X2[k][c] - Rm.a[3 * r + k] * X1[k][c];
-                        if (c < 3) Dc[3 + r][c] = Rm.a[3 * r + c] - acc;
-                        else if (c < 6) Dc[3 + r][c] = (Sm.a[3 * r + c - 3] - S1.a[3 * r + c - 3]) - acc;
-                        else lb[3 + r] = acc;
-                    }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 6; r++) sc[r] = smLd(sm, S_SC + r);
-            Wi = Wn;
-        }
-    }
+    for (int i = 0; i < n - 1; i++) forwardCell<NEWMARK, false>(p, b, sm, i, n, dZ, dcI, ARho, Dc, sc, lb, Wi, res);
+    forwardCell<NEWMARK, true>(p, b, sm, n - 1, n, dZ, dcI, ARho, Dc, sc, lb, Wi, res);
     return res;
 }
 
