@@ -14,11 +14,15 @@
 //                   linearSpring), updateSolutionVariables (Evolve.C:757-923) and the partial
 //                   sums of the three convergence norms (Evolve.C:588,618-626).
 //
-// Mapping: ONE THREAD PER BEAM, 32 beams per warp.  All arrays are "beam-interleaved
-// structure of arrays": element (cell i, component c, beam b) lives at
-// ((i*nc + c)*Bpad + b), so the 32 lanes of a warp read 32 consecutive doubles (256 B,
-// fully coalesced) for every scalar they touch, and the serial block recurrence of each
-// beam runs entirely in one thread's registers with no cross-lane traffic.
+// Mapping: ONE THREAD PER BEAM, 32 beams per warp.  Cell, face and scratch arrays are
+// "warp-tiled structure of arrays": the 32 beams of warp tile T = b/32 own one contiguous
+// slab per array, element (cell i, component c, lane l = b%32) at
+// (((T*R + i)*nc + c)*32 + l), R = rows per beam (nmax cells / nmax+1 faces).  The 32 lanes
+// of a warp read 32 consecutive doubles (256 B, fully coalesced) for every scalar, a warp
+// walks each array as ONE contiguous stream (a handful of 2 MB pages live per warp instead
+// of one page per component row, which thrashed the TLB), and the serial block recurrence
+// of each beam runs entirely in one thread's registers with no cross-lane traffic.
+// Per-beam constants and end-patch arrays stay [c][Bpad].
 #pragma once
 #include "beam_math.cuh"
 #include <stdint.h>
@@ -49,17 +53,17 @@ struct BeamParams {
     const double* refL;   // [9][Bpad]
     const int* wType;     // [2][Bpad]
     const int* thType;    // [2][Bpad]
-    // cells [nmax][nc][Bpad]
+    // cells [tile][nmax][nc][32]
     double *W, *Th, *Lam, *U, *Ac, *Om, *dOm, *DW, *DTh;
     const double *q, *m, *Lc; // optional (may be null)
-    // faces [nmax+1][nc][Bpad]: face j of beam b; j=0 left patch, j=nSeg[b] right patch
+    // faces [tile][nmax+1][nc][32]: face j of beam b; j=0 left patch, j=nSeg[b] right patch
     double *Lf, *Gam, *K, *Q, *M;
     // ends [2][nc][Bpad]
     double *Wb, *Thb, *Lamb, *DWb, *DThb, *force;
     const double *wPresc, *thPresc, *follower, *offset, *moment, *springK, *springDir;
     // block-Thomas scratch
-    double* uP; // [nmax][36][Bpad]
-    double* bP; // [nmax][6][Bpad]
+    double* uP; // [tile][nmax][36][32]
+    double* bP; // [tile][nmax][6][32]
     // per-block partial sums: [3][gridDim.x]
     double* partial;
 };
@@ -78,6 +82,11 @@ DEV void st9(double* __restrict__ p, size_t i, size_t s, const M3& A)
 #pragma unroll
     for (int k = 0; k < 9; k++) p[i + k * s] = A.a[k];
 }
+
+// Warp-tiled addressing: TS = doubles between two components of one cell (the tile width);
+// tileRow(T, R, r, nc, lane) = first component of row r (cell or face) of the lane's beam.
+#define TS ((size_t)32)
+DEV size_t tileRow(size_t T, int R, int r, int nc, int lane) { return ((T * (size_t)R + (size_t)r) * nc) * TS + lane; }
 
 // L2 prefetch of the rows the NEXT loop iteration will read.  The serial recurrence of a beam
 // leaves only ~2 resident warps per scheduler (register-bound), so the DRAM latency of the loads
@@ -319,15 +328,15 @@ __device__ __noinline__ void patchClosure(const BeamParams& p, int end, int b, V
     const double dcB = 2.0 / dZ, pDelta = 1.0 / dcB;
     const M3 refL = ld9(p.refL, b, s);
     const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
-    const size_t j = end ? (size_t)p.nSeg[b] : 0;
-    const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
-    const M3 Lfb = ld9(p.Lf, f9, s);
+    const int j = end ? p.nSeg[b] : 0;
+    const size_t f3 = tileRow(b >> 5, p.nmax + 1, j, 3, b & 31), f9 = tileRow(b >> 5, p.nmax + 1, j, 9, b & 31);
+    const M3 Lfb = ld9(p.Lf, f9, TS);
     const EndBC e = loadEnd(p, end, b, Lfb);
     const V3 Wb = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb; // after updateCoeffs()
     // left patch: outward normal -x => dR0Ds = -dR0 (CTL.C:987-994)
     const V3 t = end ? dR0 + dcB * (Wb - Wc) : dcB * (Wb - Wc) - dR0;
-    const FaceCoef f = faceCoefficients(Lfb, refL, ld3(p.CQ, b, s), ld3(p.CM, b, s), ld3(p.Gam, f3, s),
-                                        ld3(p.K, f3, s), ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcB, true);
+    const FaceCoef f = faceCoefficients(Lfb, refL, ld3(p.CQ, b, s), ld3(p.CM, b, s), ld3(p.Gam, f3, TS),
+                                        ld3(p.K, f3, TS), ld3(p.Q, f3, TS), ld3(p.M, f3, TS), t, dcB, true);
     double D[6][6], src[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
@@ -352,29 +361,31 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
                      const double dZ, const double dcI, const double ARho, double (&Dc)[6][6], double (&sc)[6],
                      double (&lb)[6], V3& Wi, double& res)
 {
-    const size_t s = p.Bpad;
+    const size_t s = TS;
+    const size_t T = (size_t)(b >> 5);
+    const int lane = b & 31, Rc = p.nmax, Rf = p.nmax + 1;
     const double dt = p.dt, beta = p.beta, gamma = p.gamma;
-    const size_t j = (size_t)(i + 1);
-    const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
+    const int j = i + 1;
+    const size_t f3 = tileRow(T, Rf, j, 3, lane), f9 = tileRow(T, Rf, j, 9, lane);
     double src[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) src[r] = sc[r];
     V3 Wn = Wi;
     if (!LAST) { // prefetch what iteration i+1 reads: face i+2, W_{i+2}, cell i+1
-        const size_t jn = j + 1;
-        pfRows<9>(p.Lf, jn * 9 * s + b, s);
-        pfRows<3>(p.Gam, jn * 3 * s + b, s); pfRows<3>(p.K, jn * 3 * s + b, s);
-        pfRows<3>(p.Q, jn * 3 * s + b, s); pfRows<3>(p.M, jn * 3 * s + b, s);
-        if (i + 2 < n) pfRows<3>(p.W, jn * 3 * s + b, s);
+        const size_t g3 = tileRow(T, Rf, j + 1, 3, lane), n3 = tileRow(T, Rc, j, 3, lane);
+        pfRows<9>(p.Lf, tileRow(T, Rf, j + 1, 9, lane), s);
+        pfRows<3>(p.Gam, g3, s); pfRows<3>(p.K, g3, s);
+        pfRows<3>(p.Q, g3, s); pfRows<3>(p.M, g3, s);
+        if (i + 2 < n) pfRows<3>(p.W, tileRow(T, Rc, j + 1, 3, lane), s);
         if (NEWMARK) {
-            pfRows<9>(p.Lam, j * 9 * s + b, s);
-            pfRows<3>(p.Ac, j * 3 * s + b, s); pfRows<3>(p.Om, j * 3 * s + b, s); pfRows<3>(p.dOm, j * 3 * s + b, s);
-            if (p.first) pfRows<3>(p.U, j * 3 * s + b, s);
+            pfRows<9>(p.Lam, tileRow(T, Rc, j, 9, lane), s);
+            pfRows<3>(p.Ac, n3, s); pfRows<3>(p.Om, n3, s); pfRows<3>(p.dOm, n3, s);
+            if (p.first) pfRows<3>(p.U, n3, s);
         }
     }
     // ---- phase A: coefficients of face i+1, own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
     if (!LAST) {
-        Wn = ld3(p.W, j * 3 * s + b, s);
+        Wn = ld3(p.W, tileRow(T, Rc, j, 3, lane), s);
         const M3 Lm = mul(ld9(p.Lf, f9, s), smLd9(sm, S_REFL));                       // Evolve.C:678
         const V3 t = v3(smLd(sm, S_REFL) + dcI * (Wn.x - Wi.x), smLd(sm, S_REFL + 3) + dcI * (Wn.y - Wi.y),
                         smLd(sm, S_REFL + 6) + dcI * (Wn.z - Wi.z));                  // dR0Ds + snGrad(W)
@@ -434,13 +445,13 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
         }
     }
     // ---- loads: Evolve.C:193-209,274-279
-    const size_t c3 = (size_t)i * 3 * s + b;
-    const double Lcell = p.Lc ? p.Lc[(size_t)i * s + b] : dZ;
+    const size_t c3 = tileRow(T, Rc, i, 3, lane);
+    const double Lcell = p.Lc ? p.Lc[tileRow(T, Rc, i, 1, lane)] : dZ;
     if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, s));
     subV(src, 0, Lcell * smLd3(sm, S_WGT));
     if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, s));
     if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
-        const M3 Lm = ld9(p.Lam, (size_t)i * 9 * s + b, s);
+        const M3 Lm = ld9(p.Lam, tileRow(T, Rc, i, 9, lane), s);
         V3 Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
         if (p.first) {
             const V3 Uo = ld3(p.U, c3, s);
@@ -509,7 +520,7 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
         X2[0][c] = x2.x; X2[1][c] = x2.y; X2[2][c] = x2.z;
     }
     // ---- store uPrime (36) and bPrime (6)
-    const size_t u0 = (size_t)i * 36 * s + b, b0 = (size_t)i * 6 * s + b;
+    const size_t u0 = tileRow(T, Rc, i, 36, lane), b0 = tileRow(T, Rc, i, 6, lane);
     if (!LAST) {
 #pragma unroll
         for (int r = 0; r < 3; r++)
@@ -592,7 +603,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ s
 #pragma unroll
         for (int c = 0; c < 6; c++) Dc[r][c] = 0.0;
     }
-    V3 Wi = ld3(p.W, b, s);
+    V3 Wi = ld3(p.W, tileRow(b >> 5, p.nmax, 0, 3, b & 31), TS);
     {
         double D36[36], s6[6];
 #pragma unroll
@@ -707,14 +718,16 @@ DEV FaceState patchUpdate(const BeamParams& p, int end, int b, const M3& LfOld, 
 template <bool NEWMARK>
 DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2)
 {
-    const size_t s = p.Bpad;
+    const size_t s = TS;
+    const size_t T = (size_t)(b >> 5);
+    const int lane = b & 31, Rc = p.nmax, Rf = p.nmax + 1;
     {
         const int n = p.nSeg[b];
         const double dZ = p.dZ[b];
         const double dcI = 1.0 / dZ, dcB = 2.0 / dZ;
         const double delta = 1.0 / dcB;
-        const V3 CQ = ld3(p.CQ, b, s), CM = ld3(p.CM, b, s);
-        const M3 refL = ld9(p.refL, b, s);
+        const V3 CQ = ld3(p.CQ, b, p.Bpad), CM = ld3(p.CM, b, p.Bpad);
+        const M3 refL = ld9(p.refL, b, p.Bpad);
         const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
         const double dt = p.dt, beta = p.beta, gamma = p.gamma;
 
@@ -722,20 +735,20 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
         V3 WoldN = v3(0, 0, 0), WnewN = v3(0, 0, 0);
         for (int i = n - 1; i >= 0; i--) {
             // ---- back substitution: x_i = bPrime_i - uPrime_i & x_{i+1}
-            const size_t u0 = (size_t)i * 36 * s + b, b0 = (size_t)i * 6 * s + b;
+            const size_t u0 = tileRow(T, Rc, i, 36, lane), b0 = tileRow(T, Rc, i, 6, lane);
             if (i > 0) { // prefetch what iteration i-1 reads: scratch and cell i-1, face i
-                const size_t cm = (size_t)(i - 1), fj = (size_t)i;
-                pfRows<36>(p.uP, cm * 36 * s + b, s);
-                pfRows<6>(p.bP, cm * 6 * s + b, s);
-                pfRows<3>(p.W, cm * 3 * s + b, s); pfRows<3>(p.Th, cm * 3 * s + b, s);
-                pfRows<9>(p.Lam, cm * 9 * s + b, s);
+                const size_t m3 = tileRow(T, Rc, i - 1, 3, lane), g3 = tileRow(T, Rf, i, 3, lane);
+                pfRows<36>(p.uP, tileRow(T, Rc, i - 1, 36, lane), s);
+                pfRows<6>(p.bP, tileRow(T, Rc, i - 1, 6, lane), s);
+                pfRows<3>(p.W, m3, s); pfRows<3>(p.Th, m3, s);
+                pfRows<9>(p.Lam, tileRow(T, Rc, i - 1, 9, lane), s);
                 if (NEWMARK) {
-                    pfRows<3>(p.U, cm * 3 * s + b, s); pfRows<3>(p.Ac, cm * 3 * s + b, s);
-                    pfRows<3>(p.Om, cm * 3 * s + b, s); pfRows<3>(p.dOm, cm * 3 * s + b, s);
+                    pfRows<3>(p.U, m3, s); pfRows<3>(p.Ac, m3, s);
+                    pfRows<3>(p.Om, m3, s); pfRows<3>(p.dOm, m3, s);
                 }
-                pfRows<9>(p.Lf, fj * 9 * s + b, s);
-                pfRows<3>(p.Gam, fj * 3 * s + b, s); pfRows<3>(p.K, fj * 3 * s + b, s);
-                pfRows<3>(p.Q, fj * 3 * s + b, s); pfRows<3>(p.M, fj * 3 * s + b, s);
+                pfRows<9>(p.Lf, tileRow(T, Rf, i, 9, lane), s);
+                pfRows<3>(p.Gam, g3, s); pfRows<3>(p.K, g3, s);
+                pfRows<3>(p.Q, g3, s); pfRows<3>(p.M, g3, s);
             }
             double x[6];
 #pragma unroll
@@ -754,7 +767,7 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
 #pragma unroll
             for (int r = 0; r < 6; r++) dx2 += x[r] * x[r];
             // ---- cell i: Evolve.C:759-802, 839-863
-            const size_t c3 = (size_t)i * 3 * s + b, c9 = (size_t)i * 9 * s + b;
+            const size_t c3 = tileRow(T, Rc, i, 3, lane), c9 = tileRow(T, Rc, i, 9, lane);
             const V3 Wold = ld3(p.W, c3, s);
             const M3 LmOld = ld9(p.Lam, c9, s);
             const V3 Thn = ld3(p.Th, c3, s) + mulT(LmOld, DT); // :759 (Lambda before its update)
@@ -784,8 +797,7 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
             }
             // ---- face j = i+1
             {
-                const size_t j = (size_t)(i + 1);
-                const size_t f3 = j * 3 * s + b, f9 = j * 9 * s + b;
+                const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f9 = tileRow(T, Rf, i + 1, 9, lane);
                 const M3 LfOld = ld9(p.Lf, f9, s);
                 const V3 Kold = ld3(p.K, f3, s);
                 FaceState o;
@@ -803,12 +815,13 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 st3(p.Gam, f3, s, o.Gam); st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
             }
             if (i == 0) { // left patch: face 0
-                const M3 LfOld = ld9(p.Lf, b, s);
-                const V3 Kold = ld3(p.K, b, s);
-                const FaceState o = patchUpdate(p, 0, b, LfOld, refL, CQ, CM, ld3(p.Gam, b, s), Kold, ld3(p.Q, b, s),
-                                                ld3(p.M, b, s), -dR0, Wold, Wnew, DW, DT, dcB, delta);
-                st9(p.Lf, b, s, o.Lf);
-                st3(p.Gam, b, s, o.Gam); st3(p.K, b, s, o.K); st3(p.Q, b, s, o.Q); st3(p.M, b, s, o.M);
+                const size_t f3 = tileRow(T, Rf, 0, 3, lane), f9 = tileRow(T, Rf, 0, 9, lane);
+                const M3 LfOld = ld9(p.Lf, f9, s);
+                const V3 Kold = ld3(p.K, f3, s);
+                const FaceState o = patchUpdate(p, 0, b, LfOld, refL, CQ, CM, ld3(p.Gam, f3, s), Kold, ld3(p.Q, f3, s),
+                                                ld3(p.M, f3, s), -dR0, Wold, Wnew, DW, DT, dcB, delta);
+                st9(p.Lf, f9, s, o.Lf);
+                st3(p.Gam, f3, s, o.Gam); st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
             }
             xWn = DW; xTn = DT; WoldN = Wold; WnewN = Wnew;
         }

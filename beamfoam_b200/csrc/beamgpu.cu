@@ -114,7 +114,7 @@ extern "C" int bf_host_alloc(void** p, int64_t bytes)
 extern "C" int bf_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BF_OK : BF_ERR_CUDA; }
 
 // ---------------------------------------------------------------------------
-// layout transposition: reference ordering (AoS, beam-major) <-> [i][c][b]
+// layout transposition: reference ordering (AoS, beam-major) <-> warp-tiled [b/32][row][c][b%32]
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int findBeam(const int64_t* __restrict__ start, int B, int64_t g)
 {
@@ -126,14 +126,14 @@ __device__ __forceinline__ int findBeam(const int64_t* __restrict__ start, int B
     return lo;
 }
 
-// cells: host index g = cellStart[b] + i ;  dev index ((i*nc + c)*Bpad + b)
+// cells: host index g = cellStart[b] + i ;  dev index (((b/32)*R + i)*nc + c)*32 + b%32, R rows per beam
 // faces: host index g = faceStart[b] + (j-1), j = 1..n-1 ; dev face index j = i + faceOffset
 // Tiled through shared memory so that BOTH sides are coalesced: a block moves a tile of
 // 32 beams x 32 cells x nc components; device accesses run along beams (threadIdx.x = beam),
 // host-order accesses run along the contiguous (cell, component) run of one beam.
 template <bool TO_DEVICE>
 __global__ void transposeInternal(double* __restrict__ dev, double* __restrict__ host, const int64_t* __restrict__ start,
-                                  int B, int Bpad, int nc, int faceOffset)
+                                  int B, int R, int nc, int faceOffset)
 {
     extern __shared__ double tile[]; // [32 cells][nc][33]
     const int b0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
@@ -145,7 +145,7 @@ __global__ void transposeInternal(double* __restrict__ dev, double* __restrict__
         for (int k = ty; k < run; k += 8) { // k = il*nc + c
             const int il = k / nc, c = k - il * nc;
             const int i = i0 + il;
-            if (i < nb) tile[(size_t)k * 33 + tx] = dev[((size_t)(i + faceOffset) * nc + c) * Bpad + b];
+            if (i < nb) tile[(size_t)k * 33 + tx] = dev[(((size_t)blockIdx.x * R + (i + faceOffset)) * nc + c) * 32 + tx];
         }
         __syncthreads();
         for (int bl = ty; bl < 32; bl += 8) {
@@ -175,21 +175,21 @@ __global__ void transposeInternal(double* __restrict__ dev, double* __restrict__
         for (int k = ty; k < run; k += 8) {
             const int il = k / nc, c = k - il * nc;
             const int i = i0 + il;
-            if (i < nb) dev[((size_t)(i + faceOffset) * nc + c) * Bpad + b] = tile[(size_t)k * 33 + tx];
+            if (i < nb) dev[(((size_t)blockIdx.x * R + (i + faceOffset)) * nc + c) * 32 + tx] = tile[(size_t)k * 33 + tx];
         }
     }
 }
-// patch values: host [b*nc + c] ; dev ((row*nc + c)*Bpad + b) with row = end (end arrays) or
-// the face index of the patch (face arrays: 0 or nSeg[b])
+// patch values: host [b*nc + c] ; dev end arrays ((end*nc + c)*Bpad + b), or for face arrays the
+// warp-tiled element of the patch face (face 0 or nSeg[b]; R = nmax+1 rows per beam)
 template <bool TO_DEVICE>
 __global__ void transposePatch(double* __restrict__ dev, double* __restrict__ host, const int32_t* __restrict__ nSeg,
-                               int B, int Bpad, int nc, int end, int faceArray)
+                               int B, int Bpad, int R, int nc, int end, int faceArray)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const size_t row = faceArray ? (end ? (size_t)nSeg[b] : 0) : (size_t)end;
     for (int c = 0; c < nc; c++) {
-        const size_t d = (row * nc + c) * Bpad + b;
+        const size_t d = faceArray ? ((((size_t)(b >> 5) * R + (end ? nSeg[b] : 0)) * nc + c) * 32 + (b & 31))
+                                   : (((size_t)end * nc + c) * Bpad + b);
         if (TO_DEVICE) dev[d] = host[(size_t)b * nc + c]; else host[(size_t)b * nc + c] = dev[d];
     }
 }
@@ -223,7 +223,7 @@ static void launchTranspose(bf_ctx* c, double* dev, double* hostOrder, int nc, i
     const dim3 grid((unsigned)((c->B + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
     const size_t smem = sizeof(double) * 32 * nc * 33;
     transposeInternal<TO_DEVICE><<<grid, block, smem, c->stream>>>(
-        dev, hostOrder, surface ? c->d_faceStart : c->d_cellStart, (int)c->B, c->Bpad, nc, surface);
+        dev, hostOrder, surface ? c->d_faceStart : c->d_cellStart, (int)c->B, surface ? c->nmax + 1 : c->nmax, nc, surface);
 }
 
 extern "C" int bf_destroy(bf_ctx* c)
@@ -436,10 +436,11 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     }
     // Lambda = Lambdaf = I (CTL.C:289-314), also the patch values of the vol field Lambda
     {
-        int64_t rows = (int64_t)nmax;
-        fillIdentity<<<(unsigned)((rows * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lam, rows, Bpad);
-        rows = (int64_t)nmax + 1;
-        fillIdentity<<<(unsigned)((rows * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lf, rows, Bpad);
+        // tiled arrays: (Bpad/32)*R rows of 32 lanes
+        int64_t rows = (int64_t)nmax * (Bpad / 32);
+        fillIdentity<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_Lam, rows, 32);
+        rows = ((int64_t)nmax + 1) * (Bpad / 32);
+        fillIdentity<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_Lf, rows, 32);
         fillIdentity<<<(unsigned)((2 * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lamb, 2, Bpad);
         c->launches += 3;
         CREATE_CUDA(cudaGetLastError());
@@ -509,9 +510,9 @@ static int xferPatch(bf_ctx* c, double* dev, double* host, int nc, int end, int 
     const size_t bytes = sizeof(double) * c->B * nc;
     if (toDevice) {
         CUDA_OK(c, cudaMemcpyAsync(c->d_stagePatch, host, bytes, cudaMemcpyHostToDevice, c->stream));
-        transposePatch<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, nc, end, faceArray);
+        transposePatch<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, c->nmax + 1, nc, end, faceArray);
     } else {
-        transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, nc, end, faceArray);
+        transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, c->nmax + 1, nc, end, faceArray);
         CUDA_OK(c, cudaMemcpyAsync(host, c->d_stagePatch, bytes, cudaMemcpyDeviceToHost, c->stream));
     }
     c->launches++;
