@@ -53,11 +53,13 @@ struct BeamParams {
     const double* refL;   // [9][Bpad]
     const int* wType;     // [2][Bpad]
     const int* thType;    // [2][Bpad]
-    // cells [tile][nmax][nc][32]
+    // cells [tile][nmax][nc][32]; Lam = unit quaternion (4) of the cell rotation Lambda
     double *W, *Th, *Lam, *U, *Ac, *Om, *dOm, *DW, *DTh;
     const double *q, *m, *Lc; // optional (may be null)
     // faces [tile][nmax+1][nc][32]: face j of beam b; j=0 left patch, j=nSeg[b] right patch
-    double *Lf, *Gam, *K, *Q, *M;
+    // Lf = unit quaternion (4) of Lambdaf.  Gamma is not stored: it is a pure function of the stored
+    // W and Lambdaf (Evolve.C:881-887) and is recomputed where explicitQ needs it.
+    double *Lf, *K, *Q, *M;
     // ends [2][nc][Bpad]
     double *Wb, *Thb, *Lamb, *DWb, *DThb, *force;
     const double *wPresc, *thPresc, *follower, *offset, *moment, *springK, *springDir;
@@ -82,6 +84,10 @@ DEV void st9(double* __restrict__ p, size_t i, size_t s, const M3& A)
 #pragma unroll
     for (int k = 0; k < 9; k++) p[i + k * s] = A.a[k];
 }
+DEV Q4 ldq(const double* __restrict__ p, size_t i, size_t s) { return q4(p[i], p[i + s], p[i + 2 * s], p[i + 3 * s]); }
+DEV void stq(double* __restrict__ p, size_t i, size_t s, Q4 q) { p[i] = q.w; p[i + s] = q.x; p[i + 2 * s] = q.y; p[i + 3 * s] = q.z; }
+// Gamma = refLambdaf.T() & ((Lambdaf.T() & dRdS) - dR0Ds)   Evolve.C:881-887, from the STORED W, Lambdaf
+DEV V3 gammaOf(const M3& Lf, const M3& refL, V3 t, V3 dR0s) { return mulT(refL, mulT(Lf, t) - dR0s); }
 
 // Warp-tiled addressing: TS = doubles between two components of one cell (the tile width);
 // tileRow(T, R, r, nc, lane) = first component of row r (cell or face) of the lane's beam.
@@ -329,13 +335,15 @@ __device__ __noinline__ void patchClosure(const BeamParams& p, int end, int b, V
     const M3 refL = ld9(p.refL, b, s);
     const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
     const int j = end ? p.nSeg[b] : 0;
-    const size_t f3 = tileRow(b >> 5, p.nmax + 1, j, 3, b & 31), f9 = tileRow(b >> 5, p.nmax + 1, j, 9, b & 31);
-    const M3 Lfb = ld9(p.Lf, f9, TS);
+    const size_t f3 = tileRow(b >> 5, p.nmax + 1, j, 3, b & 31), f4 = tileRow(b >> 5, p.nmax + 1, j, 4, b & 31);
+    const M3 Lfb = quatToMat(ldq(p.Lf, f4, TS));
     const EndBC e = loadEnd(p, end, b, Lfb);
     const V3 Wb = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb; // after updateCoeffs()
     // left patch: outward normal -x => dR0Ds = -dR0 (CTL.C:987-994)
-    const V3 t = end ? dR0 + dcB * (Wb - Wc) : dcB * (Wb - Wc) - dR0;
-    const FaceCoef f = faceCoefficients(Lfb, refL, ld3(p.CQ, b, s), ld3(p.CM, b, s), ld3(p.Gam, f3, TS),
+    const V3 dR0s = end ? dR0 : -dR0;
+    const V3 t = dR0s + dcB * (Wb - Wc);
+    const V3 Gam = gammaOf(Lfb, refL, dR0s + dcB * (e.Wb - Wc), dR0s); // Gamma of the previous update: stored patch W
+    const FaceCoef f = faceCoefficients(Lfb, refL, ld3(p.CQ, b, s), ld3(p.CM, b, s), Gam,
                                         ld3(p.K, f3, TS), ld3(p.Q, f3, TS), ld3(p.M, f3, TS), t, dcB, true);
     double D[6][6], src[6];
 #pragma unroll
@@ -366,19 +374,19 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
     const int lane = b & 31, Rc = p.nmax, Rf = p.nmax + 1;
     const double dt = p.dt, beta = p.beta, gamma = p.gamma;
     const int j = i + 1;
-    const size_t f3 = tileRow(T, Rf, j, 3, lane), f9 = tileRow(T, Rf, j, 9, lane);
+    const size_t f3 = tileRow(T, Rf, j, 3, lane), f4 = tileRow(T, Rf, j, 4, lane);
     double src[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) src[r] = sc[r];
     V3 Wn = Wi;
     if (!LAST) { // prefetch what iteration i+1 reads: face i+2, W_{i+2}, cell i+1
         const size_t g3 = tileRow(T, Rf, j + 1, 3, lane), n3 = tileRow(T, Rc, j, 3, lane);
-        pfRows<9>(p.Lf, tileRow(T, Rf, j + 1, 9, lane), s);
-        pfRows<3>(p.Gam, g3, s); pfRows<3>(p.K, g3, s);
+        pfRows<4>(p.Lf, tileRow(T, Rf, j + 1, 4, lane), s);
+        pfRows<3>(p.K, g3, s);
         pfRows<3>(p.Q, g3, s); pfRows<3>(p.M, g3, s);
         if (i + 2 < n) pfRows<3>(p.W, tileRow(T, Rc, j + 1, 3, lane), s);
         if (NEWMARK) {
-            pfRows<9>(p.Lam, tileRow(T, Rc, j, 9, lane), s);
+            pfRows<4>(p.Lam, tileRow(T, Rc, j, 4, lane), s);
             pfRows<3>(p.Ac, n3, s); pfRows<3>(p.Om, n3, s); pfRows<3>(p.dOm, n3, s);
             if (p.first) pfRows<3>(p.U, n3, s);
         }
@@ -386,9 +394,16 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
     // ---- phase A: coefficients of face i+1, own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
     if (!LAST) {
         Wn = ld3(p.W, tileRow(T, Rc, j, 3, lane), s);
-        const M3 Lm = mul(ld9(p.Lf, f9, s), smLd9(sm, S_REFL));                       // Evolve.C:678
-        const V3 t = v3(smLd(sm, S_REFL) + dcI * (Wn.x - Wi.x), smLd(sm, S_REFL + 3) + dcI * (Wn.y - Wi.y),
-                        smLd(sm, S_REFL + 6) + dcI * (Wn.z - Wi.z));                  // dR0Ds + snGrad(W)
+        const V3 dR0 = v3(smLd(sm, S_REFL), smLd(sm, S_REFL + 3), smLd(sm, S_REFL + 6));
+        const V3 t = v3(dR0.x + dcI * (Wn.x - Wi.x), dR0.y + dcI * (Wn.y - Wi.y),
+                        dR0.z + dcI * (Wn.z - Wi.z));                                 // dR0Ds + snGrad(W)
+        V3 Gam;
+        M3 Lm;
+        {
+            const M3 Lf = quatToMat(ldq(p.Lf, f4, s)), refL = smLd9(sm, S_REFL);
+            Gam = gammaOf(Lf, refL, t, dR0);
+            Lm = mul(Lf, refL);                                                       // Evolve.C:678
+        }
         const double h = 0.5 / dcI;
         V3 eQ;
         M3 SC;
@@ -396,7 +411,7 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
         {
             const V3 CQ = smLd3(sm, S_CQ);
             const M3 CQW = conjDiag(Lm, CQ);                                          // :680
-            eQ = mul(Lm, cmul(CQ, ld3(p.Gam, f3, s)));                                // :682
+            eQ = mul(Lm, cmul(CQ, Gam));                                              // :682
             SC = mulSpinL(t, CQW);
             const M3 Pm = dcI * CQW;
             const M3 Qt = 0.5 * (mulSpinR(CQW, t) - SQ);                              // 0.5*CQTheta :686-693
@@ -451,7 +466,7 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
     subV(src, 0, Lcell * smLd3(sm, S_WGT));
     if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, s));
     if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
-        const M3 Lm = ld9(p.Lam, tileRow(T, Rc, i, 9, lane), s);
+        const M3 Lm = quatToMat(ldq(p.Lam, tileRow(T, Rc, i, 4, lane), s));
         V3 Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
         if (p.first) {
             const V3 Uo = ld3(p.U, c3, s);
@@ -627,23 +642,23 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ s
 // backward: back-substitution + BC evaluate + updateSolutionVariables + norms
 // ---------------------------------------------------------------------------
 struct FaceState {
-    M3 Lf;
-    V3 Gam, K, Q, M;
+    Q4 Lf;
+    V3 K, Q, M;
 };
 
 // Update of one face (Evolve.C:804-836, 881-913).  (A) = owner / face cell, (B) = neighbour /
 // patch value.  f holds the PRE-solve coefficients; tnew = dR0Ds + snGrad(W_new).
-DEV FaceState updateFace(const FaceCoef& f, const M3& LfOld, const M3& refL, V3 Kold, V3 dR0s, V3 tnew,
+DEV FaceState updateFace(const FaceCoef& f, Q4 qOld, const M3& LfOld, const M3& refL, V3 Kold,
                          V3 DWa, V3 DWb, V3 DTa, V3 DTb, double dc, bool boundary)
 {
     FaceState o;
     const V3 DThf = boundary ? DTb : v3(0.5 * DTa.x + 0.5 * DTb.x, 0.5 * DTa.y + 0.5 * DTb.y, 0.5 * DTa.z + 0.5 * DTb.z);
     const V3 sgT = dc * (DTb - DTa), sgW = dc * (DWb - DWa);
+    const HalfAngle h = halfAngle(DThf);
     // K += (refLambdaf.T() & Lambdaf.T()) & (DT.T() & snGrad(DTheta))   :825-830 (old Lambdaf)
-    o.K = Kold + mulT(refL, mulT(LfOld, tangentT(DThf, sgT)));
-    o.Lf = mul(rotationMatrix(DThf), LfOld); // :833-836
-    // Gamma = refLambdaf.T() & ((Lambdaf.T() & dRdS) - dR0Ds)           :881-887 (new W, new Lambdaf)
-    o.Gam = mulT(refL, mulT(o.Lf, tnew) - dR0s);
+    o.K = Kold + mulT(refL, mulT(LfOld, tangentT(DThf, sgT, h)));
+    o.Lf = quatNormalize(quatMul(quatFromRotVec(DThf, h), qOld)); // Lambdaf = R(DThetaf) & Lambdaf :833-836
+    // Gamma (:881-887) is a function of the new W and Lambdaf: recomputed by its consumers, not stored
     // Q = explicitQ + CQW & snGrad(DW) + CQTheta & interpolate(DTheta)  :896-903
     o.Q = f.eQ + (mul(f.CQW, sgW) + mul(f.CQTheta, DThf));
     // M = explicitM + CMTheta & snGrad(DTheta) + CMTheta2 & interpolate(DTheta) :906-913
@@ -659,15 +674,16 @@ DEV FaceState updateFace(const FaceCoef& f, const M3& LfOld, const M3& refL, V3 
 //   fixedValue / fixedRotation / fixedDisplacement: value from updateCoeffs(); DW_b, DTheta_b are the
 //   pWCorr / pThetaCorr written by assembleBoundaryConditions (BC.C:359-361, 478-482).
 // dR0s is dR0Ds of this patch (sign-flipped on the left patch).
-DEV FaceState patchUpdate(const BeamParams& p, int end, int b, const M3& LfOld, const M3& refL, V3 CQ, V3 CM,
-                          V3 Gam, V3 Kold, V3 Q, V3 M, V3 dR0s, V3 WoldC, V3 WnewC, V3 DWc, V3 DTc, double dcB,
-                          double delta)
+DEV FaceState patchUpdate(const BeamParams& p, int end, int b, Q4 qOld, const M3& refL, V3 CQ, V3 CM,
+                          V3 Kold, V3 Q, V3 M, V3 dR0s, V3 WoldC, V3 DWc, V3 DTc, double dcB, double delta)
 {
     const size_t s = p.Bpad;
     const size_t i3 = (size_t)end * 3 * s + b, i9 = (size_t)end * 9 * s + b;
+    const M3 LfOld = quatToMat(qOld);
     const EndBC e = loadEnd(p, end, b, LfOld);
     const V3 WbOld = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb;
     const V3 t = dR0s + dcB * (WbOld - WoldC);
+    const V3 Gam = gammaOf(LfOld, refL, dR0s + dcB * (e.Wb - WoldC), dR0s);
     const FaceCoef f = faceCoefficients(LfOld, refL, CQ, CM, Gam, Kold, Q, M, t, dcB, true);
     const double ipd = 1.0 / delta;
     const M3 LambOld = ld9(p.Lamb, i9, s);
@@ -711,8 +727,7 @@ DEV FaceState patchUpdate(const BeamParams& p, int end, int b, const M3& LfOld, 
     st3(p.DWb, i3, s, DWb);
     st3(p.DThb, i3, s, DTb);
     st9(p.Lamb, i9, s, mul(rotationMatrix(DTb), LambOld)); // Lambda_ = DLambda & Lambda_ on the patch
-    const V3 tnew = dR0s + dcB * (WbNew - WnewC);
-    return updateFace(f, LfOld, refL, Kold, dR0s, tnew, DWc, DWb, DTc, DTb, dcB, true);
+    return updateFace(f, qOld, LfOld, refL, Kold, DWc, DWb, DTc, DTb, dcB, true);
 }
 
 template <bool NEWMARK>
@@ -732,7 +747,7 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
         const double dt = p.dt, beta = p.beta, gamma = p.gamma;
 
         V3 xWn = v3(0, 0, 0), xTn = v3(0, 0, 0); // x_{i+1}
-        V3 WoldN = v3(0, 0, 0), WnewN = v3(0, 0, 0);
+        V3 WoldN = v3(0, 0, 0);
         for (int i = n - 1; i >= 0; i--) {
             // ---- back substitution: x_i = bPrime_i - uPrime_i & x_{i+1}
             const size_t u0 = tileRow(T, Rc, i, 36, lane), b0 = tileRow(T, Rc, i, 6, lane);
@@ -741,13 +756,13 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 pfRows<36>(p.uP, tileRow(T, Rc, i - 1, 36, lane), s);
                 pfRows<6>(p.bP, tileRow(T, Rc, i - 1, 6, lane), s);
                 pfRows<3>(p.W, m3, s); pfRows<3>(p.Th, m3, s);
-                pfRows<9>(p.Lam, tileRow(T, Rc, i - 1, 9, lane), s);
+                pfRows<4>(p.Lam, tileRow(T, Rc, i - 1, 4, lane), s);
                 if (NEWMARK) {
                     pfRows<3>(p.U, m3, s); pfRows<3>(p.Ac, m3, s);
                     pfRows<3>(p.Om, m3, s); pfRows<3>(p.dOm, m3, s);
                 }
-                pfRows<9>(p.Lf, tileRow(T, Rf, i, 9, lane), s);
-                pfRows<3>(p.Gam, g3, s); pfRows<3>(p.K, g3, s);
+                pfRows<4>(p.Lf, tileRow(T, Rf, i, 4, lane), s);
+                pfRows<3>(p.K, g3, s);
                 pfRows<3>(p.Q, g3, s); pfRows<3>(p.M, g3, s);
             }
             double x[6];
@@ -767,15 +782,17 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
 #pragma unroll
             for (int r = 0; r < 6; r++) dx2 += x[r] * x[r];
             // ---- cell i: Evolve.C:759-802, 839-863
-            const size_t c3 = tileRow(T, Rc, i, 3, lane), c9 = tileRow(T, Rc, i, 9, lane);
+            const size_t c3 = tileRow(T, Rc, i, 3, lane), c4 = tileRow(T, Rc, i, 4, lane);
             const V3 Wold = ld3(p.W, c3, s);
-            const M3 LmOld = ld9(p.Lam, c9, s);
-            const V3 Thn = ld3(p.Th, c3, s) + mulT(LmOld, DT); // :759 (Lambda before its update)
+            const Q4 qOld = ldq(p.Lam, c4, s);
+            // Lambda.T() & DTheta.  R(DTheta) leaves its own axis unchanged, so this vector is the same for
+            // the Lambda before the update (:759) and after it (:853-862): (R Lambda).T() & DT = Lambda.T() & DT
+            const V3 LtDT = mulT(quatToMat(qOld), DT);
+            const V3 Thn = ld3(p.Th, c3, s) + LtDT;             // :759
             const V3 Wnew = Wold + DW;                          // :769
-            const M3 LmNew = mul(rotationMatrix(DT), LmOld);    // :839-841
             st3(p.Th, c3, s, Thn);
             st3(p.W, c3, s, Wnew);
-            st9(p.Lam, c9, s, LmNew);
+            stq(p.Lam, c4, s, quatNormalize(quatMul(quatFromRotVec(DT, halfAngle(DT)), qOld))); // :839-841
             x2 += dot(Wnew, Wnew) + dot(Thn, Thn);
             if (p.storeInc) { st3(p.DW, c3, s, DW); st3(p.DTh, c3, s, DT); }
             if (NEWMARK) {
@@ -790,40 +807,39 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 }
                 U = U + ((1.0 / dt) * (gamma / beta)) * DW;           // :785
                 Ac = Ac + (1.0 / (dt * dt * beta)) * DW;              // :788
-                const V3 w = mulT(LmNew, DT);                          // new Lambda :853-862
-                Om = Om + (gamma / (beta * dt)) * w;
-                dOm = dOm + (1.0 / (beta * dt * dt)) * w;
+                Om = Om + (gamma / (beta * dt)) * LtDT;                // :853-862
+                dOm = dOm + (1.0 / (beta * dt * dt)) * LtDT;
                 st3(p.U, c3, s, U); st3(p.Ac, c3, s, Ac); st3(p.Om, c3, s, Om); st3(p.dOm, c3, s, dOm);
             }
             // ---- face j = i+1
             {
-                const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f9 = tileRow(T, Rf, i + 1, 9, lane);
-                const M3 LfOld = ld9(p.Lf, f9, s);
+                const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f4 = tileRow(T, Rf, i + 1, 4, lane);
+                const Q4 qfOld = ldq(p.Lf, f4, s);
                 const V3 Kold = ld3(p.K, f3, s);
                 FaceState o;
                 if (i == n - 1) { // right patch
-                    o = patchUpdate(p, 1, b, LfOld, refL, CQ, CM, ld3(p.Gam, f3, s), Kold, ld3(p.Q, f3, s),
-                                    ld3(p.M, f3, s), dR0, Wold, Wnew, DW, DT, dcB, delta);
+                    o = patchUpdate(p, 1, b, qfOld, refL, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s), dR0, Wold, DW,
+                                    DT, dcB, delta);
                 } else {
+                    const M3 LfOld = quatToMat(qfOld);
                     const V3 t = dR0 + dcI * (WoldN - Wold);
-                    const FaceCoef f = faceCoefficients(LfOld, refL, CQ, CM, ld3(p.Gam, f3, s), Kold, ld3(p.Q, f3, s),
-                                                        ld3(p.M, f3, s), t, dcI, false);
-                    const V3 tnew = dR0 + dcI * (WnewN - Wnew);
-                    o = updateFace(f, LfOld, refL, Kold, dR0, tnew, DW, xWn, DT, xTn, dcI, false);
+                    const FaceCoef f = faceCoefficients(LfOld, refL, CQ, CM, gammaOf(LfOld, refL, t, dR0), Kold,
+                                                        ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcI, false);
+                    o = updateFace(f, qfOld, LfOld, refL, Kold, DW, xWn, DT, xTn, dcI, false);
                 }
-                st9(p.Lf, f9, s, o.Lf);
-                st3(p.Gam, f3, s, o.Gam); st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
+                stq(p.Lf, f4, s, o.Lf);
+                st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
             }
             if (i == 0) { // left patch: face 0
-                const size_t f3 = tileRow(T, Rf, 0, 3, lane), f9 = tileRow(T, Rf, 0, 9, lane);
-                const M3 LfOld = ld9(p.Lf, f9, s);
+                const size_t f3 = tileRow(T, Rf, 0, 3, lane), f4 = tileRow(T, Rf, 0, 4, lane);
+                const Q4 qfOld = ldq(p.Lf, f4, s);
                 const V3 Kold = ld3(p.K, f3, s);
-                const FaceState o = patchUpdate(p, 0, b, LfOld, refL, CQ, CM, ld3(p.Gam, f3, s), Kold, ld3(p.Q, f3, s),
-                                                ld3(p.M, f3, s), -dR0, Wold, Wnew, DW, DT, dcB, delta);
-                st9(p.Lf, f9, s, o.Lf);
-                st3(p.Gam, f3, s, o.Gam); st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
+                const FaceState o = patchUpdate(p, 0, b, qfOld, refL, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s),
+                                                -dR0, Wold, DW, DT, dcB, delta);
+                stq(p.Lf, f4, s, o.Lf);
+                st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
             }
-            xWn = DW; xTn = DT; WoldN = Wold; WnewN = Wnew;
+            xWn = DW; xTn = DT; WoldN = Wold;
         }
     }
 }

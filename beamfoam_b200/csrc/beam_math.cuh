@@ -208,6 +208,94 @@ DEV V3 tangentT(V3 th, V3 g)
 }
 
 // ---------------------------------------------------------------------------
+// Unit quaternions: the device representation of Lambda (cells) and Lambdaf (faces).
+// The reference keeps the 9 entries of each rotation tensor and multiplies increments in
+// (Lambda = R(DTheta) & Lambda, Evolve.C:833-841); a rotation has 3 degrees of freedom, so the
+// device keeps (w, x, y, z) -- 4 doubles instead of 9 per tensor per read and per write -- and
+// rebuilds the tensor in registers.  R(q1 q0) = R(q1) R(q0) exactly; the stored state differs from
+// the reference's running matrix product by rounding only (both drift by O(eps) per update; the
+// quaternion is renormalised each time, the matrix product is not).
+// ---------------------------------------------------------------------------
+struct Q4 {
+    double w, x, y, z;
+};
+DEV Q4 q4(double w, double x, double y, double z) { Q4 q; q.w = w; q.x = x; q.y = y; q.z = z; return q; }
+DEV M3 quatToMat(Q4 q)
+{
+    const double x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
+    const double xx = q.x * x2, yy = q.y * y2, zz = q.z * z2;
+    const double xy = q.x * y2, xz = q.x * z2, yz = q.y * z2;
+    const double wx = q.w * x2, wy = q.w * y2, wz = q.w * z2;
+    M3 R;
+    R.a[0] = 1.0 - (yy + zz); R.a[1] = xy - wz;         R.a[2] = xz + wy;
+    R.a[3] = xy + wz;         R.a[4] = 1.0 - (xx + zz); R.a[5] = yz - wx;
+    R.a[6] = xz - wy;         R.a[7] = yz + wx;         R.a[8] = 1.0 - (xx + yy);
+    return R;
+}
+// R(quatMul(a, b)) = R(a) & R(b)
+DEV Q4 quatMul(Q4 a, Q4 b)
+{
+    return q4(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+              a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w);
+}
+DEV Q4 quatNormalize(Q4 q)
+{
+    const double n = 1.0 / sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    return q4(q.w * n, q.x * n, q.y * n, q.z * n);
+}
+// Half-angle form of the reference's Rodrigues formula (pseudoVector.C:250-264, phi = |theta| + SMALL):
+// with s = sin(phi/2), c = cos(phi/2):  sin(phi)/phi = 2 s c / phi,  (1 - cos phi)/phi^2 = 2 (s/phi)^2,
+// so q = (c, (s/phi) theta) gives R(q) = I + (sin phi/phi) S + ((1 - cos phi)/phi^2) S&S.
+struct HalfAngle {
+    double phi, s, c;
+};
+DEV HalfAngle halfAngle(V3 th)
+{
+    HalfAngle h;
+    h.phi = mag(th) + BF_SMALL;
+    sincos(0.5 * h.phi, &h.s, &h.c);
+    return h;
+}
+DEV Q4 quatFromRotVec(V3 th, const HalfAngle& h)
+{
+    const double k = h.s / h.phi;
+    return q4(h.c, k * th.x, k * th.y, k * th.z);
+}
+// Tangent operator DT^T applied to g with the trigonometry taken from the half angle.
+DEV V3 tangentT(V3 th, V3 g, const HalfAngle& h)
+{
+    const double ip = 1.0 / h.phi;
+    const double sp = 2.0 * h.s * h.c * ip;           // sin(phi)/phi
+    const double c3 = 2.0 * (h.s * ip) * (h.s * ip);  // (1 - cos phi)/phi^2
+    const double c2 = (1.0 - sp) * (ip * ip);
+    const double tg = dot(th, g);
+    const V3 x = cross(th, g);
+    return v3(sp * g.x + c2 * th.x * tg - c3 * x.x, sp * g.y + c2 * th.y * tg - c3 * x.y,
+              sp * g.z + c2 * th.z * tg - c3 * x.z);
+}
+// Rotation tensor -> unit quaternion (Shepperd's branch on the largest diagonal combination);
+// used only when the host sets Lambda / Lambdaf.
+DEV Q4 matToQuat(const M3& R)
+{
+    const double tr = R.a[0] + R.a[4] + R.a[8];
+    Q4 q;
+    if (tr > 0.0) {
+        const double s = sqrt(tr + 1.0) * 2.0;
+        q = q4(0.25 * s, (R.a[7] - R.a[5]) / s, (R.a[2] - R.a[6]) / s, (R.a[3] - R.a[1]) / s);
+    } else if (R.a[0] > R.a[4] && R.a[0] > R.a[8]) {
+        const double s = sqrt(1.0 + R.a[0] - R.a[4] - R.a[8]) * 2.0;
+        q = q4((R.a[7] - R.a[5]) / s, 0.25 * s, (R.a[1] + R.a[3]) / s, (R.a[2] + R.a[6]) / s);
+    } else if (R.a[4] > R.a[8]) {
+        const double s = sqrt(1.0 + R.a[4] - R.a[0] - R.a[8]) * 2.0;
+        q = q4((R.a[2] - R.a[6]) / s, (R.a[1] + R.a[3]) / s, 0.25 * s, (R.a[5] + R.a[7]) / s);
+    } else {
+        const double s = sqrt(1.0 + R.a[8] - R.a[0] - R.a[4]) * 2.0;
+        q = q4((R.a[3] - R.a[1]) / s, (R.a[2] + R.a[6]) / s, (R.a[5] + R.a[7]) / s, 0.25 * s);
+    }
+    return quatNormalize(q);
+}
+
+// ---------------------------------------------------------------------------
 // Dense 6x6 solve with partial pivoting inside the block, NR right-hand sides,
 // everything in registers: the pivot row is brought up by predicated swaps so no
 // array is ever indexed dynamically.  On return B holds A^{-1} B.

@@ -44,18 +44,20 @@ struct bf_ctx {
     std::vector<int64_t> cellStart, faceStart;
     bool uniformN;
     // device pools
-    void* pools[12];
+    void* pools[16];
     int nPools;
     int32_t *d_nSeg, *d_wType, *d_thType;
     int64_t *d_cellStart, *d_faceStart;
     double *d_dZ, *d_CQ, *d_CM, *d_ARho, *d_CI, *d_weight, *d_refL;
     double *d_W, *d_Th, *d_Lam, *d_U, *d_Ac, *d_Om, *d_dOm, *d_DW, *d_DTh, *d_q, *d_m, *d_Lc;
-    double *d_Lf, *d_Gam, *d_K, *d_Q, *d_M;
+    double *d_Lf, *d_K, *d_Q, *d_M; // d_Lf, d_Lam: unit quaternions (4 components); Gamma is derived, not stored
     double *d_Wb, *d_Thb, *d_Lamb, *d_DWb, *d_DThb, *d_force, *d_wPresc, *d_thPresc, *d_follower, *d_offset,
         *d_moment, *d_springK, *d_springDir;
     double *d_uP, *d_bP, *d_partial, *d_sums;
     double* d_stage; // staging buffer in host (AoS) ordering
     double* d_stagePatch; // separate small staging for patch values (never shared with a pending mirror)
+    double* d_stageQ;     // host-ordered quaternions (4 per cell/face) between the transposition and the tensor conversion
+    double* d_stagePatchQ;
     size_t stageDoubles;
     double* h_sums;  // pinned + mapped: the kernels write the norms straight into host memory, so the
                      // per-iteration read never queues behind a bulk D2H copy on the copy engine
@@ -193,14 +195,68 @@ __global__ void transposePatch(double* __restrict__ dev, double* __restrict__ ho
         if (TO_DEVICE) dev[d] = host[(size_t)b * nc + c]; else host[(size_t)b * nc + c] = dev[d];
     }
 }
-__global__ void fillIdentity(double* __restrict__ T, int64_t rows, int Bpad)
+// rows x nc x width array of identity rotations: tensors (nc = 9: xx = yy = zz = 1) or quaternions (nc = 4: w = 1)
+__global__ void fillIdentity(double* __restrict__ T, int64_t rows, int width, int nc)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= rows * Bpad) return;
-    const int64_t r = k / Bpad, b = k % Bpad;
-    T[(r * 9 + 0) * Bpad + b] = 1.0;
-    T[(r * 9 + 4) * Bpad + b] = 1.0;
-    T[(r * 9 + 8) * Bpad + b] = 1.0;
+    if (k >= rows * width) return;
+    const int64_t r = k / width, b = k % width;
+    T[(r * nc + 0) * width + b] = 1.0;
+    if (nc == 9) {
+        T[(r * 9 + 4) * width + b] = 1.0;
+        T[(r * 9 + 8) * width + b] = 1.0;
+    }
+}
+
+// host-ordered rotation tensors (9) <-> unit quaternions (4): the device keeps Lambda / Lambdaf as quaternions
+template <bool TO_QUAT>
+__global__ void convertRotation(double* __restrict__ tens, double* __restrict__ quat, int64_t count)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= count) return;
+    if (TO_QUAT) {
+        M3 R;
+        for (int k = 0; k < 9; k++) R.a[k] = tens[g * 9 + k];
+        const Q4 q = matToQuat(R);
+        quat[g * 4] = q.w; quat[g * 4 + 1] = q.x; quat[g * 4 + 2] = q.y; quat[g * 4 + 3] = q.z;
+    } else {
+        const M3 R = quatToMat(q4(quat[g * 4], quat[g * 4 + 1], quat[g * 4 + 2], quat[g * 4 + 3]));
+        for (int k = 0; k < 9; k++) tens[g * 9 + k] = R.a[k];
+    }
+}
+// Gamma = refLambdaf.T() & ((Lambdaf.T() & (dR0Ds + snGrad(W))) - dR0Ds)  (Evolve.C:881-887), evaluated from the
+// stored W / Lambdaf when the host asks for the field.  One thread per beam; internal faces into host order,
+// patch faces into left[b*3..], right[b*3..].
+__global__ void gammaField(const BeamParams p, const int64_t* __restrict__ faceStart, double* __restrict__ internal,
+                           double* __restrict__ left, double* __restrict__ right)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const size_t T = (size_t)(b >> 5);
+    const int lane = b & 31, n = p.nSeg[b], Rc = p.nmax, Rf = p.nmax + 1;
+    const double dZ = p.dZ[b], dcI = 1.0 / dZ, dcB = 2.0 / dZ;
+    const M3 refL = ld9(p.refL, b, p.Bpad);
+    const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
+    V3 Wprev = ld3(p.W, tileRow(T, Rc, 0, 3, lane), TS);
+    if (left) {
+        const V3 g = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, 0, 4, lane), TS)), refL,
+                             dcB * (ld3(p.Wb, b, p.Bpad) - Wprev) - dR0, -dR0);
+        left[3 * (size_t)b] = g.x; left[3 * (size_t)b + 1] = g.y; left[3 * (size_t)b + 2] = g.z;
+    }
+    for (int j = 1; j < n; j++) {
+        const V3 Wn = ld3(p.W, tileRow(T, Rc, j, 3, lane), TS);
+        if (internal) {
+            const V3 g = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, j, 4, lane), TS)), refL, dR0 + dcI * (Wn - Wprev), dR0);
+            double* o = internal + 3 * (faceStart[b] + j - 1);
+            o[0] = g.x; o[1] = g.y; o[2] = g.z;
+        }
+        Wprev = Wn;
+    }
+    if (right) {
+        const V3 g = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, n, 4, lane), TS)), refL,
+                             dR0 + dcB * (ld3(p.Wb, (size_t)3 * p.Bpad + b, p.Bpad) - Wprev), dR0);
+        right[3 * (size_t)b] = g.x; right[3 * (size_t)b + 1] = g.y; right[3 * (size_t)b + 2] = g.z;
+    }
 }
 
 struct bf_ctx;
@@ -348,11 +404,11 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     }
     // ---- cell / face state
     {
-        const size_t cellD = nc_ * bp * (3 + 3 + 9 + (newmark ? 12 : 0) + (c->storeInc ? 6 : 0));
-        const size_t faceD = nf_ * bp * (9 + 3 + 3 + 3 + 3);
+        const size_t cellD = nc_ * bp * (3 + 3 + 4 + (newmark ? 12 : 0) + (c->storeInc ? 6 : 0));
+        const size_t faceD = nf_ * bp * (4 + 3 + 3 + 3);
         char* cur;
         if (devAlloc(c, (void**)&cur, sizeof(double) * (cellD + faceD) + 256 * 16)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
-        c->d_W = carve<double>(cur, 3 * nc_ * bp); c->d_Th = carve<double>(cur, 3 * nc_ * bp); c->d_Lam = carve<double>(cur, 9 * nc_ * bp);
+        c->d_W = carve<double>(cur, 3 * nc_ * bp); c->d_Th = carve<double>(cur, 3 * nc_ * bp); c->d_Lam = carve<double>(cur, 4 * nc_ * bp);
         if (newmark) {
             c->d_U = carve<double>(cur, 3 * nc_ * bp); c->d_Ac = carve<double>(cur, 3 * nc_ * bp);
             c->d_Om = carve<double>(cur, 3 * nc_ * bp); c->d_dOm = carve<double>(cur, 3 * nc_ * bp);
@@ -360,7 +416,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
             c->d_U = c->d_Ac = c->d_Om = c->d_dOm = nullptr;
         }
         if (c->storeInc) { c->d_DW = carve<double>(cur, 3 * nc_ * bp); c->d_DTh = carve<double>(cur, 3 * nc_ * bp); }
-        c->d_Lf = carve<double>(cur, 9 * nf_ * bp); c->d_Gam = carve<double>(cur, 3 * nf_ * bp); c->d_K = carve<double>(cur, 3 * nf_ * bp);
+        c->d_Lf = carve<double>(cur, 4 * nf_ * bp); c->d_K = carve<double>(cur, 3 * nf_ * bp);
         c->d_Q = carve<double>(cur, 3 * nf_ * bp); c->d_M = carve<double>(cur, 3 * nf_ * bp);
     }
     // ---- block-Thomas scratch + partial sums
@@ -374,6 +430,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->stageDoubles = (size_t)c->N * 9;
     if (devAlloc(c, (void**)&c->d_stage, sizeof(double) * c->stageDoubles)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
     if (devAlloc(c, (void**)&c->d_stagePatch, sizeof(double) * (size_t)B * 9)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+    if (devAlloc(c, (void**)&c->d_stageQ, sizeof(double) * (size_t)c->N * 4)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+    if (devAlloc(c, (void**)&c->d_stagePatchQ, sizeof(double) * (size_t)B * 4)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
     CREATE_CUDA(cudaHostAlloc((void**)&c->h_sums, 8 * sizeof(double), cudaHostAllocMapped));
     CREATE_CUDA(cudaHostGetDevicePointer((void**)&c->d_hsums, c->h_sums, 0));
 
@@ -438,10 +496,10 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     {
         // tiled arrays: (Bpad/32)*R rows of 32 lanes
         int64_t rows = (int64_t)nmax * (Bpad / 32);
-        fillIdentity<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_Lam, rows, 32);
+        fillIdentity<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_Lam, rows, 32, 4);
         rows = ((int64_t)nmax + 1) * (Bpad / 32);
-        fillIdentity<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_Lf, rows, 32);
-        fillIdentity<<<(unsigned)((2 * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lamb, 2, Bpad);
+        fillIdentity<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_Lf, rows, 32, 4);
+        fillIdentity<<<(unsigned)((2 * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lamb, 2, Bpad, 9);
         c->launches += 3;
         CREATE_CUDA(cudaGetLastError());
     }
@@ -459,21 +517,22 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
 }
 
 // ---------------------------------------------------------------------------
-static int fieldInfo(bf_ctx* c, int field, double** dev, double** endArr, int* nc, int* surface)
+enum { FK_PLAIN = 0, FK_ROTATION = 1, FK_GAMMA = 2 }; // how a field is represented on the device
+static int fieldInfo(bf_ctx* c, int field, double** dev, double** endArr, int* nc, int* surface, int* kind)
 {
-    *endArr = nullptr; *surface = 0; *nc = 3;
+    *endArr = nullptr; *surface = 0; *nc = 3; *kind = FK_PLAIN; *dev = nullptr;
     switch (field) {
     case BF_FIELD_W: *dev = c->d_W; *endArr = c->d_Wb; break;
     case BF_FIELD_THETA: *dev = c->d_Th; *endArr = c->d_Thb; break;
-    case BF_FIELD_LAMBDA: *dev = c->d_Lam; *endArr = c->d_Lamb; *nc = 9; break;
+    case BF_FIELD_LAMBDA: *dev = c->d_Lam; *endArr = c->d_Lamb; *nc = 9; *kind = FK_ROTATION; break;
     case BF_FIELD_DW: *dev = c->d_DW; *endArr = c->d_DWb; break;
     case BF_FIELD_DTHETA: *dev = c->d_DTh; *endArr = c->d_DThb; break;
     case BF_FIELD_U: *dev = c->d_U; break;
     case BF_FIELD_ACCL: *dev = c->d_Ac; break;
     case BF_FIELD_OMEGA: *dev = c->d_Om; break;
     case BF_FIELD_DOTOMEGA: *dev = c->d_dOm; break;
-    case BF_FIELD_LAMBDAF: *dev = c->d_Lf; *nc = 9; *surface = 1; break;
-    case BF_FIELD_GAMMA: *dev = c->d_Gam; *surface = 1; break;
+    case BF_FIELD_LAMBDAF: *dev = c->d_Lf; *nc = 9; *surface = 1; *kind = FK_ROTATION; break;
+    case BF_FIELD_GAMMA: *dev = c->d_Lf; *surface = 1; *kind = FK_GAMMA; break;
     case BF_FIELD_K: *dev = c->d_K; *surface = 1; break;
     case BF_FIELD_Q: *dev = c->d_Q; *surface = 1; break;
     case BF_FIELD_M: *dev = c->d_M; *surface = 1; break;
@@ -487,32 +546,74 @@ static int drainMirror(bf_ctx* c)
     if (c->copyPending) { CUDA_OK(c, cudaStreamSynchronize(c->copyStream)); c->copyPending = false; }
     return BF_OK;
 }
-static int xferInternal(bf_ctx* c, double* dev, double* host, int nc, int surface, bool toDevice)
+static BeamParams makeParams(bf_ctx* c);
+// Device state -> host-ordered (createBeamMesh) array `dst` in device memory, on the compute stream.
+static void stageInternal(bf_ctx* c, double* dev, int nc, int surface, int kind, double* dst)
+{
+    const int64_t count = surface ? c->F : c->N;
+    if (count == 0) return;
+    if (kind == FK_PLAIN) {
+        launchTranspose<false>(c, dev, dst, nc, surface);
+        c->launches++;
+    } else if (kind == FK_ROTATION) {
+        launchTranspose<false>(c, dev, c->d_stageQ, 4, surface);
+        convertRotation<false><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(dst, c->d_stageQ, count);
+        c->launches += 2;
+    } else {
+        gammaField<<<(unsigned)((c->B + 127) / 128), 128, 0, c->stream>>>(makeParams(c), c->d_faceStart, dst, nullptr, nullptr);
+        c->launches++;
+    }
+}
+static int xferInternal(bf_ctx* c, double* dev, double* host, int nc, int surface, int kind, bool toDevice)
 {
     if (int rc = drainMirror(c)) return rc;
     const int64_t count = surface ? c->F : c->N;
     if (count == 0) return BF_OK;
     if (toDevice) {
+        if (kind == FK_GAMMA) return BF_OK; // derived from W and Lambdaf on the device (Evolve.C:881-887): nothing to store
         CUDA_OK(c, cudaMemcpyAsync(c->d_stage, host, sizeof(double) * count * nc, cudaMemcpyHostToDevice, c->stream));
-        launchTranspose<true>(c, dev, c->d_stage, nc, surface);
+        if (kind == FK_ROTATION) {
+            convertRotation<true><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(c->d_stage, c->d_stageQ, count);
+            launchTranspose<true>(c, dev, c->d_stageQ, 4, surface);
+            c->launches += 2;
+        } else {
+            launchTranspose<true>(c, dev, c->d_stage, nc, surface);
+            c->launches++;
+        }
     } else {
-        launchTranspose<false>(c, dev, c->d_stage, nc, surface);
+        stageInternal(c, dev, nc, surface, kind, c->d_stage);
         CUDA_OK(c, cudaMemcpyAsync(host, c->d_stage, sizeof(double) * count * nc, cudaMemcpyDeviceToHost, c->stream));
     }
-    c->launches++;
     CUDA_OK(c, cudaGetLastError());
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return BF_OK;
 }
-static int xferPatch(bf_ctx* c, double* dev, double* host, int nc, int end, int faceArray, bool toDevice)
+// faceArray: the patch faces of a surface field (kind as for the internal part); otherwise an end array [2][nc][Bpad]
+static int xferPatch(bf_ctx* c, double* dev, double* host, int nc, int end, int faceArray, bool toDevice, int kind = FK_PLAIN)
 {
     const unsigned grid = (unsigned)((c->B + 255) / 256);
     const size_t bytes = sizeof(double) * c->B * nc;
-    if (toDevice) {
+    const int R = c->nmax + 1;
+    if (kind == FK_GAMMA) {
+        if (toDevice) return BF_OK;
+        gammaField<<<(unsigned)((c->B + 127) / 128), 128, 0, c->stream>>>(makeParams(c), c->d_faceStart, nullptr,
+                                                                          end ? nullptr : c->d_stagePatch, end ? c->d_stagePatch : nullptr);
+        CUDA_OK(c, cudaMemcpyAsync(host, c->d_stagePatch, bytes, cudaMemcpyDeviceToHost, c->stream));
+    } else if (toDevice) {
         CUDA_OK(c, cudaMemcpyAsync(c->d_stagePatch, host, bytes, cudaMemcpyHostToDevice, c->stream));
-        transposePatch<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, c->nmax + 1, nc, end, faceArray);
+        if (kind == FK_ROTATION) {
+            convertRotation<true><<<grid, 256, 0, c->stream>>>(c->d_stagePatch, c->d_stagePatchQ, c->B);
+            transposePatch<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatchQ, c->d_nSeg, (int)c->B, c->Bpad, R, 4, end, faceArray);
+            c->launches++;
+        } else
+            transposePatch<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, R, nc, end, faceArray);
     } else {
-        transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, c->nmax + 1, nc, end, faceArray);
+        if (kind == FK_ROTATION) {
+            transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatchQ, c->d_nSeg, (int)c->B, c->Bpad, R, 4, end, faceArray);
+            convertRotation<false><<<grid, 256, 0, c->stream>>>(c->d_stagePatch, c->d_stagePatchQ, c->B);
+            c->launches++;
+        } else
+            transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, R, nc, end, faceArray);
         CUDA_OK(c, cudaMemcpyAsync(host, c->d_stagePatch, bytes, cudaMemcpyDeviceToHost, c->stream));
     }
     c->launches++;
@@ -524,17 +625,17 @@ static int xferPatch(bf_ctx* c, double* dev, double* host, int nc, int end, int 
 extern "C" int bf_set_field(bf_ctx* c, int32_t field, const double* internal, const double* left, const double* right)
 {
     CUDA_OK(c, cudaSetDevice(c->device));
-    double *dev, *endArr; int nc, surf;
-    int rc = fieldInfo(c, field, &dev, &endArr, &nc, &surf);
+    double *dev, *endArr; int nc, surf, kind;
+    int rc = fieldInfo(c, field, &dev, &endArr, &nc, &surf, &kind);
     if (rc) return rc;
     if (internal) {
         if (!dev) return fail(c, BF_ERR_INVALID, "field %d is not allocated in this context", field);
-        if ((rc = xferInternal(c, dev, (double*)internal, nc, surf, true))) return rc;
+        if ((rc = xferInternal(c, dev, (double*)internal, nc, surf, kind, true))) return rc;
     }
     const double* sides[2] = {left, right};
     for (int end = 0; end < 2; end++) {
         if (!sides[end]) continue;
-        if (surf) { if ((rc = xferPatch(c, dev, (double*)sides[end], nc, end, 1, true))) return rc; }
+        if (surf) { if ((rc = xferPatch(c, dev, (double*)sides[end], nc, end, 1, true, kind))) return rc; }
         else if (endArr) {
             if ((rc = xferPatch(c, endArr, (double*)sides[end], nc, end, 0, true))) return rc;
             // a plain fixedValue keeps the value it was given; prevIter == value (CTL.C:1110-1111)
@@ -548,17 +649,17 @@ extern "C" int bf_set_field(bf_ctx* c, int32_t field, const double* internal, co
 extern "C" int bf_get_field(bf_ctx* c, int32_t field, double* internal, double* left, double* right)
 {
     CUDA_OK(c, cudaSetDevice(c->device));
-    double *dev, *endArr; int nc, surf;
-    int rc = fieldInfo(c, field, &dev, &endArr, &nc, &surf);
+    double *dev, *endArr; int nc, surf, kind;
+    int rc = fieldInfo(c, field, &dev, &endArr, &nc, &surf, &kind);
     if (rc) return rc;
     if (internal) {
         if (!dev) return fail(c, BF_ERR_INVALID, "field %d is not kept in this context (scheme / storeIncrements)", field);
-        if ((rc = xferInternal(c, dev, internal, nc, surf, false))) return rc;
+        if ((rc = xferInternal(c, dev, internal, nc, surf, kind, false))) return rc;
     }
     double* sides[2] = {left, right};
     for (int end = 0; end < 2; end++) {
         if (!sides[end]) continue;
-        if (surf) { if ((rc = xferPatch(c, dev, sides[end], nc, end, 1, false))) return rc; }
+        if (surf) { if ((rc = xferPatch(c, dev, sides[end], nc, end, 1, false, kind))) return rc; }
         else if (endArr) { if ((rc = xferPatch(c, endArr, sides[end], nc, end, 0, false))) return rc; }
         else return fail(c, BF_ERR_INVALID, "field %d has no mirrored boundary values", field);
     }
@@ -580,16 +681,13 @@ extern "C" int bf_mirror_begin(bf_ctx* c, int32_t nFields, const int32_t* fields
     struct Job { double* host; size_t off, count; } jobs[16];
     if (nFields > 16) return fail(c, BF_ERR_INVALID, "bf_mirror_begin: at most 16 fields");
     for (int k = 0; k < nFields; k++) {
-        double *dev, *endArr; int nc, surf;
-        int rc = fieldInfo(c, fields[k], &dev, &endArr, &nc, &surf);
+        double *dev, *endArr; int nc, surf, kind;
+        int rc = fieldInfo(c, fields[k], &dev, &endArr, &nc, &surf, &kind);
         if (rc) return rc;
         if (!dev) return fail(c, BF_ERR_INVALID, "field %d is not kept in this context", fields[k]);
         const int64_t count = surf ? c->F : c->N;
         if (off + (size_t)count * nc > c->stageDoubles) return fail(c, BF_ERR_INVALID, "bf_mirror_begin: fields exceed the staging buffer (9 doubles per cell)");
-        if (count > 0) {
-            launchTranspose<false>(c, dev, c->d_stage + off, nc, surf);
-            c->launches++;
-        }
+        stageInternal(c, dev, nc, surf, kind, c->d_stage + off);
         jobs[k] = {hostInternal[k], off, (size_t)count * nc};
         off += (size_t)count * nc;
     }
@@ -624,7 +722,7 @@ extern "C" int bf_set_distributed_loads(bf_ctx* c, const double* q, const double
             int rc = devAlloc(c, (void**)dst[k], sizeof(double) * 3 * (size_t)c->nmax * c->Bpad);
             if (rc) return rc;
         }
-        int rc = xferInternal(c, *dst[k], (double*)src[k], 3, 0, true);
+        int rc = xferInternal(c, *dst[k], (double*)src[k], 3, 0, FK_PLAIN, true);
         if (rc) return rc;
         *has[k] = true;
     }
@@ -699,6 +797,7 @@ extern "C" int bf_kernel_time_ms(bf_ctx* c, int32_t reset, double* fwd, double* 
 static BeamParams makeParams(bf_ctx* c)
 {
     BeamParams p;
+    memset(&p, 0, sizeof p);
     p.B = (int)c->B; p.Bpad = c->Bpad; p.nmax = c->nmax;
     p.newmark = c->scheme == BF_SCHEME_NEWMARK; p.first = c->iOuterCorr == 0; p.storeInc = c->storeInc;
     p.dt = c->deltaT; p.beta = c->betaN; p.gamma = c->gammaN;
@@ -707,7 +806,7 @@ static BeamParams makeParams(bf_ctx* c)
     p.W = c->d_W; p.Th = c->d_Th; p.Lam = c->d_Lam; p.U = c->d_U; p.Ac = c->d_Ac; p.Om = c->d_Om; p.dOm = c->d_dOm;
     p.DW = c->d_DW; p.DTh = c->d_DTh;
     p.q = c->hasQ ? c->d_q : nullptr; p.m = c->hasM ? c->d_m : nullptr; p.Lc = c->d_Lc;
-    p.Lf = c->d_Lf; p.Gam = c->d_Gam; p.K = c->d_K; p.Q = c->d_Q; p.M = c->d_M;
+    p.Lf = c->d_Lf; p.K = c->d_K; p.Q = c->d_Q; p.M = c->d_M;
     p.Wb = c->d_Wb; p.Thb = c->d_Thb; p.Lamb = c->d_Lamb; p.DWb = c->d_DWb; p.DThb = c->d_DThb; p.force = c->d_force;
     p.wPresc = c->d_wPresc; p.thPresc = c->d_thPresc; p.follower = c->d_follower; p.offset = c->d_offset;
     p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir;
