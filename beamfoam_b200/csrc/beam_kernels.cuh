@@ -57,7 +57,8 @@ struct BeamParams {
     double *W, *Th, *Lam, *U, *Ac, *Om, *dOm, *DW, *DTh;
     const double *q, *m, *Lc; // optional (may be null)
     // faces [tile][nmax+1][nc][32]: face j of beam b; j=0 left patch, j=nSeg[b] right patch
-    // Lf = unit quaternion (4) of Lambdaf.  Gamma is not stored: it is a pure function of the stored
+    // Lf = unit quaternion (4) of the product Lambdaf & refLambdaf (the only form the interior of a beam
+    // needs, Evolve.C:678,825-830,881-887).  Gamma is not stored: it is a pure function of the stored
     // W and Lambdaf (Evolve.C:881-887) and is recomputed where explicitQ needs it.
     double *Lf, *K, *Q, *M;
     // ends [2][nc][Bpad]
@@ -86,8 +87,9 @@ DEV void st9(double* __restrict__ p, size_t i, size_t s, const M3& A)
 }
 DEV Q4 ldq(const double* __restrict__ p, size_t i, size_t s) { return q4(p[i], p[i + s], p[i + 2 * s], p[i + 3 * s]); }
 DEV void stq(double* __restrict__ p, size_t i, size_t s, Q4 q) { p[i] = q.w; p[i + s] = q.x; p[i + 2 * s] = q.y; p[i + 3 * s] = q.z; }
-// Gamma = refLambdaf.T() & ((Lambdaf.T() & dRdS) - dR0Ds)   Evolve.C:881-887, from the STORED W, Lambdaf
-DEV V3 gammaOf(const M3& Lf, const M3& refL, V3 t, V3 dR0s) { return mulT(refL, mulT(Lf, t) - dR0s); }
+// Gamma = refLambdaf.T() & ((Lambdaf.T() & dRdS) - dR0Ds)   Evolve.C:881-887, from the STORED W and
+// Lm = Lambdaf & refLambdaf:  Gamma = Lm.T() & dRdS - e0,  e0 = refLambdaf.T() & dR0Ds
+DEV V3 gammaOf(const M3& Lm, V3 e0, V3 t) { return mulT(Lm, t) - e0; }
 
 // Warp-tiled addressing: TS = doubles between two components of one cell (the tile width);
 // tileRow(T, R, r, nc, lane) = first component of row r (cell or face) of the lane's beam.
@@ -119,11 +121,11 @@ struct FaceCoef {
 };
 
 // dc = deltaCoeffs of the face; boundary faces get the x2 of Evolve.C:744-752.
-DEV FaceCoef faceCoefficients(const M3& Lf, const M3& refL, V3 CQ, V3 CM, V3 Gam, V3 K, V3 Q, V3 M, V3 t,
+// Lm = Lambdaf & refLambdaf (:678): the device stores this product (as a quaternion), not Lambdaf.
+DEV FaceCoef faceCoefficients(const M3& Lm, V3 CQ, V3 CM, V3 Gam, V3 K, V3 Q, V3 M, V3 t,
                               double dc, bool boundary)
 {
     FaceCoef f;
-    const M3 Lm = mul(Lf, refL);               // :678
     f.CQW = conjDiag(Lm, CQ);                  // :680
     f.eQ = mul(Lm, cmul(CQ, Gam));             // :682
     f.eM = mul(Lm, cmul(CM, K));               // :684
@@ -146,6 +148,15 @@ DEV void addBlk(double (&D)[6][6], int r0, int c0, double s, const M3& T)
     for (int r = 0; r < 3; r++)
 #pragma unroll
         for (int c = 0; c < 3; c++) D[r0 + r][c0 + c] += s * T.a[3 * r + c];
+}
+DEV void addBlkS(double (&D)[6][6], int r0, int c0, double s, const Sym3& T) { addBlk(D, r0, c0, s, full(T)); }
+// D[r0.., c0..] += s * T.T()
+DEV void addBlkT(double (&D)[6][6], int r0, int c0, double s, const M3& T)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) D[r0 + r][c0 + c] += s * T.a[3 * c + r];
 }
 DEV void subV(double (&b)[6], int r0, V3 v) { b[r0] -= v.x; b[r0 + 1] -= v.y; b[r0 + 2] -= v.z; }
 DEV void addV(double (&b)[6], int r0, V3 v) { b[r0] += v.x; b[r0 + 1] += v.y; b[r0 + 2] += v.z; }
@@ -282,10 +293,17 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 // ---------------------------------------------------------------------------
 // forward: coefficients + assembly + block-Thomas elimination
 // ---------------------------------------------------------------------------
-// Per-thread shared-memory slots (doubles).  Element k of thread t lives at sm[k*BEAM_THREADS + t]:
-// consecutive threads hit consecutive banks, so every access is conflict-free.  The stash is a
-// register extension: an FP64 warp instruction occupies the pipe for 2 cycles, an LDS.64 costs
-// the same, so parking the face tensors here is cheaper than any local-memory spill.
+// Every warp owns a private slab of shared memory, [row][32 lanes] doubles (row r of lane l at
+// sm[r*32 + l]: consecutive lanes hit consecutive banks, every access is conflict-free):
+//   * per-beam constants (18 rows),
+//   * the "stash": the face tensors of face i+1 that are needed again after the elimination of
+//     cell i (u columns, l block, neighbour part of d_{i+1}); a register extension -- an FP64 warp
+//     instruction occupies the pipe for 2 cycles, an LDS.64 costs the same,
+//   * the prefetch buffer: the state rows the NEXT cell will read, brought in by the TMA engine
+//     (cp.async.bulk, one copy per array, completion on the warp's mbarrier) while the current
+//     cell is being eliminated.  The warp-tiled layout makes every array's rows of one cell one
+//     contiguous run (nc x 256 B), so a cell needs 9 bulk copies and no register ever waits on
+//     a global load in the steady state.
 #ifndef BEAM_THREADS
 #define BEAM_THREADS 128
 #endif
@@ -293,25 +311,37 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 #define BEAM_MIN_BLOCKS 2
 #endif
 enum {
-    S_REFL = 0,  // refLambdaf (9)
-    S_CQ = 9,    // diag CQ (3)
-    S_CM = 12,   // diag CM (3)
-    S_CI = 15,   // diag CIRho (3)
-    S_WGT = 18,  // rho A g (3)
-    S_P = 21,    // a*CQW            (9)   face i+1
-    S_QT = 30,   // 0.5*CQTheta      (9)
-    S_RM = 39,   // a*CMQW           (9)
-    S_S1 = 48,   // a*CMTheta        (9)
-    S_S3 = 57,   // 0.5*CMQTheta     (9)
-    S_MF = 66,   // M of face i+1    (3)   0.5*CMTheta2 = -0.5*spin(M)
-    S_SC = 69,   // nei part of the source of cell i+1 (6)
-    S_TOTAL = 75
+    R_DR0 = 0,   // dR0Ds = refLambdaf & e_x (3)
+    R_E0 = 3,    // refLambdaf.T() & dR0Ds (3)  (= e_x for an orthonormal refLambdaf)
+    R_CQ = 6,    // diag CQ (3)
+    R_CM = 9,    // diag CM (3)
+    R_CI = 12,   // diag CIRho (3)
+    R_WGT = 15,  // rho A g (3)
+    R_P = 18,    // a*CQW, symmetric: xx xy xz yy yz zz (6)   face i+1
+    R_QT = 24,   // 0.5*CQTheta (9);  a*CMQW = -(0.5*CQTheta).T()
+    R_S1 = 33,   // a*CMTheta, symmetric (6)
+    R_S3 = 39,   // 0.5*CMQTheta (9)
+    R_MF = 48,   // M of face i+1 (3): 0.5*CMTheta2 = -0.5*spin(M)
+    R_SC = 51,   // neighbour part of the source of cell i+1 (6)
+    R_BUF = 57,  // prefetch buffer
+    B_W = 0,     //   W of cell i+1 (3)
+    B_LF = 3,    //   Lambdaf & refLambdaf of face i+1, quaternion (4)
+    B_K = 7, B_Q = 10, B_M = 13, //   K, Q, M of face i+1
+    B_LAM = 16,  //   Lambda of cell i, quaternion (4)          (Newmark only from here)
+    B_AC = 20, B_OM = 23, B_DOM = 26, //   Accl, Omega, dotOmega of cell i
+    B_U = 29,    //   U of cell i (first iteration of a time step only)
+    B_ROWS = 32,
+    R_TOTAL = R_BUF + B_ROWS
 };
-#define SMEM_BYTES (S_TOTAL * BEAM_THREADS * sizeof(double))
+#define WARP_SMEM_DOUBLES (R_TOTAL * 32)
+#define SMEM_HEADER_BYTES 128 // one mbarrier (8 B) per warp
+#define SMEM_BYTES (SMEM_HEADER_BYTES + (BEAM_THREADS / 32) * WARP_SMEM_DOUBLES * sizeof(double))
 
-DEV double smLd(const double* sm, int k) { return ((const volatile double*)sm)[k * BEAM_THREADS]; }
-DEV void smSt(double* sm, int k, double v) { sm[k * BEAM_THREADS] = v; }
+DEV double smLd(const double* sm, int k) { return ((const volatile double*)sm)[k * 32]; }
+DEV void smSt(double* sm, int k, double v) { sm[k * 32] = v; }
 DEV V3 smLd3(const double* sm, int k) { return v3(smLd(sm, k), smLd(sm, k + 1), smLd(sm, k + 2)); }
+DEV void smSt3(double* sm, int k, V3 v) { smSt(sm, k, v.x); smSt(sm, k + 1, v.y); smSt(sm, k + 2, v.z); }
+DEV Q4 smLdq(const double* sm, int k) { return q4(smLd(sm, k), smLd(sm, k + 1), smLd(sm, k + 2), smLd(sm, k + 3)); }
 DEV M3 smLd9(const double* sm, int k)
 {
     M3 r;
@@ -323,6 +353,73 @@ DEV void smSt9(double* sm, int k, const M3& A)
 {
 #pragma unroll
     for (int j = 0; j < 9; j++) smSt(sm, k + j, A.a[j]);
+}
+DEV Sym3 smLdS(const double* sm, int k)
+{
+    Sym3 r;
+    r.xx = smLd(sm, k); r.xy = smLd(sm, k + 1); r.xz = smLd(sm, k + 2);
+    r.yy = smLd(sm, k + 3); r.yz = smLd(sm, k + 4); r.zz = smLd(sm, k + 5);
+    return r;
+}
+DEV void smStS(double* sm, int k, const Sym3& A)
+{
+    smSt(sm, k, A.xx); smSt(sm, k + 1, A.xy); smSt(sm, k + 2, A.xz);
+    smSt(sm, k + 3, A.yy); smSt(sm, k + 4, A.yz); smSt(sm, k + 5, A.zz);
+}
+
+// ---- mbarrier + bulk async copy (TMA engine, linear mode: no tensor map needed) ----
+DEV uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEV void mbarInit(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DEV void mbarExpectTx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+DEV void mbarWait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "BEAM_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra BEAM_MBAR_DONE;\n"
+        "bra BEAM_MBAR_WAIT;\n"
+        "BEAM_MBAR_DONE:\n"
+        "}" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+DEV void bulkLoad(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+
+// Prefetch of cell i for the whole warp: one elected lane arms the warp's mbarrier with the byte count and
+// issues one bulk copy per array (every address is warp-uniform).  Face arrays are read at face i+1, W at
+// cell i+1, the Newmark cell arrays at cell i.
+template <bool NEWMARK>
+DEV void fwdPrefetch(const BeamParams& p, size_t T, double* warpSm, uint64_t* bar, int lane, int i)
+{
+    if (lane != 0) return;
+    const int Rc = p.nmax, Rf = p.nmax + 1;
+    const bool hasW = i + 1 < p.nmax; // no cell i+1 in the slab for the last row
+    const bool first = NEWMARK && p.first;
+    mbarExpectTx(bar, ((hasW ? 3 : 0) + 4 + 9 + (NEWMARK ? 4 + 9 : 0) + (first ? 3 : 0)) * 256u);
+    double* buf = warpSm + (size_t)R_BUF * 32;
+    if (hasW) bulkLoad(buf + B_W * 32, p.W + tileRow(T, Rc, i + 1, 3, 0), 3 * 256, bar);
+    bulkLoad(buf + B_LF * 32, p.Lf + tileRow(T, Rf, i + 1, 4, 0), 4 * 256, bar);
+    bulkLoad(buf + B_K * 32, p.K + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
+    bulkLoad(buf + B_Q * 32, p.Q + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
+    bulkLoad(buf + B_M * 32, p.M + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
+    if (NEWMARK) {
+        bulkLoad(buf + B_LAM * 32, p.Lam + tileRow(T, Rc, i, 4, 0), 4 * 256, bar);
+        bulkLoad(buf + B_AC * 32, p.Ac + tileRow(T, Rc, i, 3, 0), 3 * 256, bar);
+        bulkLoad(buf + B_OM * 32, p.Om + tileRow(T, Rc, i, 3, 0), 3 * 256, bar);
+        bulkLoad(buf + B_DOM * 32, p.dOm + tileRow(T, Rc, i, 3, 0), 3 * 256, bar);
+        if (first) bulkLoad(buf + B_U * 32, p.U + tileRow(T, Rc, i, 3, 0), 3 * 256, bar);
+    }
 }
 
 // Boundary closure is executed for 2 of the n cells of a beam; keeping it out of line keeps its
@@ -336,14 +433,15 @@ __device__ __noinline__ void patchClosure(const BeamParams& p, int end, int b, V
     const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
     const int j = end ? p.nSeg[b] : 0;
     const size_t f3 = tileRow(b >> 5, p.nmax + 1, j, 3, b & 31), f4 = tileRow(b >> 5, p.nmax + 1, j, 4, b & 31);
-    const M3 Lfb = quatToMat(ldq(p.Lf, f4, TS));
+    const M3 Lmb = quatToMat(ldq(p.Lf, f4, TS));  // Lambdaf_b & refLambdaf
+    const M3 Lfb = mulBT(Lmb, refL);              // Lambdaf_b
     const EndBC e = loadEnd(p, end, b, Lfb);
     const V3 Wb = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb; // after updateCoeffs()
     // left patch: outward normal -x => dR0Ds = -dR0 (CTL.C:987-994)
     const V3 dR0s = end ? dR0 : -dR0;
     const V3 t = dR0s + dcB * (Wb - Wc);
-    const V3 Gam = gammaOf(Lfb, refL, dR0s + dcB * (e.Wb - Wc), dR0s); // Gamma of the previous update: stored patch W
-    const FaceCoef f = faceCoefficients(Lfb, refL, ld3(p.CQ, b, s), ld3(p.CM, b, s), Gam,
+    const V3 Gam = gammaOf(Lmb, mulT(refL, dR0s), dR0s + dcB * (e.Wb - Wc)); // Gamma of the previous update: stored patch W
+    const FaceCoef f = faceCoefficients(Lmb, ld3(p.CQ, b, s), ld3(p.CM, b, s), Gam,
                                         ld3(p.K, f3, TS), ld3(p.Q, f3, TS), ld3(p.M, f3, TS), t, dcB, true);
     double D[6][6], src[6];
 #pragma unroll
@@ -361,87 +459,59 @@ __device__ __noinline__ void patchClosure(const BeamParams& p, int end, int b, V
     }
 }
 
-// One cell of the forward sweep.  LAST = the cell whose right face is the right patch: it has no
-// u block, closes the patch instead of an internal face and produces no carry.  Splitting the two
-// cases at compile time keeps the patch code out of the steady-state loop's register allocation.
+// Assembly of cell i (first half of a forward step).  Reads the prefetch buffer (face i+1,
+// W_{i+1}, Newmark state of cell i), adds the own part of d_i and the loads/inertia to the
+// carry Dc, forms source_i, and parks the face tensors in the stash.  LAST = the cell whose right
+// face is the right patch: it closes the patch instead of an internal face.
 template <bool NEWMARK, bool LAST>
-DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, const int i, const int n,
-                     const double dZ, const double dcI, const double ARho, double (&Dc)[6][6], double (&sc)[6],
-                     double (&lb)[6], V3& Wi, double& res)
+DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, const int i, const double dZ,
+                     const double dcI, const double ARho, double (&Dc)[6][6], double (&src)[6], V3& Wi, double& res)
 {
-    const size_t s = TS;
-    const size_t T = (size_t)(b >> 5);
-    const int lane = b & 31, Rc = p.nmax, Rf = p.nmax + 1;
     const double dt = p.dt, beta = p.beta, gamma = p.gamma;
-    const int j = i + 1;
-    const size_t f3 = tileRow(T, Rf, j, 3, lane), f4 = tileRow(T, Rf, j, 4, lane);
-    double src[6];
 #pragma unroll
-    for (int r = 0; r < 6; r++) src[r] = sc[r];
-    V3 Wn = Wi;
-    if (!LAST) { // prefetch what iteration i+1 reads: face i+2, W_{i+2}, cell i+1
-        const size_t g3 = tileRow(T, Rf, j + 1, 3, lane), n3 = tileRow(T, Rc, j, 3, lane);
-        pfRows<4>(p.Lf, tileRow(T, Rf, j + 1, 4, lane), s);
-        pfRows<3>(p.K, g3, s);
-        pfRows<3>(p.Q, g3, s); pfRows<3>(p.M, g3, s);
-        if (i + 2 < n) pfRows<3>(p.W, tileRow(T, Rc, j + 1, 3, lane), s);
-        if (NEWMARK) {
-            pfRows<4>(p.Lam, tileRow(T, Rc, j, 4, lane), s);
-            pfRows<3>(p.Ac, n3, s); pfRows<3>(p.Om, n3, s); pfRows<3>(p.dOm, n3, s);
-            if (p.first) pfRows<3>(p.U, n3, s);
-        }
-    }
-    // ---- phase A: coefficients of face i+1, own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
+    for (int r = 0; r < 6; r++) src[r] = smLd(sm, R_SC + r);
     if (!LAST) {
-        Wn = ld3(p.W, tileRow(T, Rc, j, 3, lane), s);
-        const V3 dR0 = v3(smLd(sm, S_REFL), smLd(sm, S_REFL + 3), smLd(sm, S_REFL + 6));
-        const V3 t = v3(dR0.x + dcI * (Wn.x - Wi.x), dR0.y + dcI * (Wn.y - Wi.y),
-                        dR0.z + dcI * (Wn.z - Wi.z));                                 // dR0Ds + snGrad(W)
-        V3 Gam;
-        M3 Lm;
-        {
-            const M3 Lf = quatToMat(ldq(p.Lf, f4, s)), refL = smLd9(sm, S_REFL);
-            Gam = gammaOf(Lf, refL, t, dR0);
-            Lm = mul(Lf, refL);                                                       // Evolve.C:678
-        }
+        // ---- coefficients of face i+1 (Evolve.C:673-753) and own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
+        const V3 Wn = smLd3(sm, R_BUF + B_W);
+        const V3 dR0 = smLd3(sm, R_DR0);
+        const V3 t = v3(dR0.x + dcI * (Wn.x - Wi.x), dR0.y + dcI * (Wn.y - Wi.y), dR0.z + dcI * (Wn.z - Wi.z)); // dR0Ds + snGrad(W)
+        Wi = Wn;
+        const M3 Lm = quatToMat(smLdq(sm, R_BUF + B_LF));                             // Lambdaf & refLambdaf :678
         const double h = 0.5 / dcI;
+        const M3 SQ = spin(smLd3(sm, R_BUF + B_Q));
         V3 eQ;
-        M3 SC;
-        const M3 SQ = spin(ld3(p.Q, f3, s));
+        M3 SC; // spinTensor(t) & CQW = -(CQW & spinTensor(t)).T() for the symmetric CQW
         {
-            const V3 CQ = smLd3(sm, S_CQ);
-            const M3 CQW = conjDiag(Lm, CQ);                                          // :680
-            eQ = mul(Lm, cmul(CQ, Gam));                                              // :682
-            SC = mulSpinL(t, CQW);
-            const M3 Pm = dcI * CQW;
-            const M3 Qt = 0.5 * (mulSpinR(CQW, t) - SQ);                              // 0.5*CQTheta :686-693
-            smSt9(sm, S_P, Pm);
-            smSt9(sm, S_QT, Qt);
-            addBlk(Dc, 0, 0, -1.0, Pm);
+            const V3 CQ = smLd3(sm, R_CQ);
+            const Sym3 CQW = conjDiagSym(Lm, CQ);                                       // :680
+            eQ = mul(Lm, cmul(CQ, gammaOf(Lm, smLd3(sm, R_E0), t)));                  // :682 with Gamma of :881-887
+            const M3 G = mulSpinR(CQW, t);
+            const M3 Qt = 0.5 * (G - SQ);                                             // 0.5*CQTheta :686-693
+            const Sym3 Pm = dcI * CQW;
+            smStS(sm, R_P, Pm);
+            smSt9(sm, R_QT, Qt);
+            addBlkS(Dc, 0, 0, -1.0, Pm);
             addBlk(Dc, 0, 3, 1.0, Qt);
-        }
-        {
-            const M3 Rm = (dcI * h) * (SC - SQ);                                      // a*CMQW :706-715
-            smSt9(sm, S_RM, Rm);
-            addBlk(Dc, 3, 0, -1.0, Rm);
+            addBlkT(Dc, 3, 0, 1.0, Qt);                                               // -a*CMQW = +(0.5*CQTheta).T() :706-715
+            SC = -1.0 * transpose(G);
         }
         const V3 eMQ = h * cross(t, eQ);                                              // :737-741
         {
-            const V3 CM = smLd3(sm, S_CM);
-            const M3 S1 = dcI * conjDiag(Lm, CM);                                     // a*CMTheta :699
-            const V3 eM = mul(Lm, cmul(CM, ld3(p.K, f3, s)));                         // :684
+            const V3 CM = smLd3(sm, R_CM);
+            const Sym3 S1 = dcI * conjDiagSym(Lm, CM);                                  // a*CMTheta :699
+            const V3 eM = mul(Lm, cmul(CM, smLd3(sm, R_BUF + B_K)));                  // :684
             const M3 S3 = (0.5 * h) * (mulSpinR(SC, t) - mulSpinL(t, SQ));            // 0.5*CMQTheta :718-735
-            const V3 Mf = ld3(p.M, f3, s);
+            const V3 Mf = smLd3(sm, R_BUF + B_M);
             const M3 S2 = -0.5 * spin(Mf);                                            // 0.5*CMTheta2 :703
-            smSt9(sm, S_S1, S1);
-            smSt9(sm, S_S3, S3);
-            smSt(sm, S_MF, Mf.x); smSt(sm, S_MF + 1, Mf.y); smSt(sm, S_MF + 2, Mf.z);
-            addBlk(Dc, 3, 3, -1.0, S1);
+            smStS(sm, R_S1, S1);
+            smSt9(sm, R_S3, S3);
+            smSt3(sm, R_MF, Mf);
+            addBlkS(Dc, 3, 3, -1.0, S1);
             addBlk(Dc, 3, 3, 1.0, S3 + S2);
             subV(src, 0, eQ);
             subV(src, 3, eM + eMQ);
-            smSt(sm, S_SC, eQ.x); smSt(sm, S_SC + 1, eQ.y); smSt(sm, S_SC + 2, eQ.z);
-            smSt(sm, S_SC + 3, eM.x - eMQ.x); smSt(sm, S_SC + 4, eM.y - eMQ.y); smSt(sm, S_SC + 5, eM.z - eMQ.z);
+            smSt3(sm, R_SC, eQ);
+            smSt3(sm, R_SC + 3, eM - eMQ);
         }
     } else { // right patch
         double D36[36], s6[6];
@@ -460,23 +530,23 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
         }
     }
     // ---- loads: Evolve.C:193-209,274-279
-    const size_t c3 = tileRow(T, Rc, i, 3, lane);
-    const double Lcell = p.Lc ? p.Lc[tileRow(T, Rc, i, 1, lane)] : dZ;
-    if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, s));
-    subV(src, 0, Lcell * smLd3(sm, S_WGT));
-    if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, s));
+    const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31);
+    const double Lcell = p.Lc ? p.Lc[tileRow((size_t)(b >> 5), p.nmax, i, 1, b & 31)] : dZ;
+    if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, TS));
+    subV(src, 0, Lcell * smLd3(sm, R_WGT));
+    if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, TS));
     if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
-        const M3 Lm = quatToMat(ldq(p.Lam, tileRow(T, Rc, i, 4, lane), s));
-        V3 Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
+        const M3 Lm = quatToMat(smLdq(sm, R_BUF + B_LAM));
+        V3 Ac = smLd3(sm, R_BUF + B_AC), Om = smLd3(sm, R_BUF + B_OM), dOm = smLd3(sm, R_BUF + B_DOM);
         if (p.first) {
-            const V3 Uo = ld3(p.U, c3, s);
+            const V3 Uo = smLd3(sm, R_BUF + B_U);
             const double k1 = 1.0 / (dt * beta), k2 = 0.5 / beta - 1.0;
             const V3 Ao = Ac, Oo = Om, dOo = dOm;
             Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
             dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
             Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
         }
-        const V3 CI = smLd3(sm, S_CI);
+        const V3 CI = smLd3(sm, R_CI);
         const V3 CIOm = cmul(CI, Om);
         const V3 a1 = mul(Lm, cmul(CI, dOm));  // Lambda & (CIRho & dotOmega)
         const V3 a2 = mul(Lm, cross(Om, CIOm)); // Lambda & (Omega ^ (CIRho & Omega))
@@ -491,7 +561,17 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
     }
 #pragma unroll
     for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
-    // ---- phase B: block elimination operators of D'_i = [[A, B], [C, E]] (now held in Dc)
+}
+
+// Elimination step of cell i (second half): D'_i = Dc is factored by 2x2 block elimination over
+// 3x3 blocks, X = D'^{-1} [u_i | source_i - l_{i-1} bPrime_{i-1}] is formed column by column,
+// stored (uPrime, bPrime), and folded straight into the carry of cell i+1:
+//   l = [[P, -Qt], [Qt.T(), S1 + Sm]],   d_nei = [[-P, -Qt], [-Qt.T(), Sm - S1]],   Sm = S3 + 0.5 spin(M)
+//   Dc <- d_nei - l & uPrime ;  lb <- l & bPrime
+template <bool LAST>
+DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm, const int i, double (&Dc)[6][6],
+                      const double (&src)[6], double (&lb)[6])
+{
     M3 Ai, AiB, Si, Cm;
     {
         M3 A, Bm, E;
@@ -508,22 +588,24 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
         AiB = mul(Ai, Bm);
         Si = inv(E - mul(Cm, AiB));
     }
-    // ---- phase C: X = D'^{-1} [u | source - lb], column by column; u comes back from the stash
+    // ---- X = D'^{-1} [u | source - lb], column by column; u comes back from the stash
     double X1[3][7], X2[3][7];
-    const M3 S2 = -0.5 * spin(smLd3(sm, S_MF)); // only meaningful when !last
 #pragma unroll
     for (int c = 0; c < 7; c++) {
         if (c < 6 && LAST) continue;
         V3 r1, r2;
-        if (c < 3) { // u[:, c] = (P[:, c] ; Rm[:, c])
-            r1 = v3(smLd(sm, S_P + c), smLd(sm, S_P + 3 + c), smLd(sm, S_P + 6 + c));
-            r2 = v3(smLd(sm, S_RM + c), smLd(sm, S_RM + 3 + c), smLd(sm, S_RM + 6 + c));
-        } else if (c < 6) { // u[:, c] = (Qt[:, k] ; (S1 + S3 + S2)[:, k])
+        if (c < 3) { // u[:, c] = (P[:, c] ; -Qt[c, :])
+            const int pi[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+            r1 = v3(smLd(sm, R_P + pi[c][0]), smLd(sm, R_P + pi[c][1]), smLd(sm, R_P + pi[c][2]));
+            r2 = -smLd3(sm, R_QT + 3 * c);
+        } else if (c < 6) { // u[:, c] = (Qt[:, k] ; (S1 + S3 + S2)[:, k]),  S2 = -0.5 spin(M)
             const int k = c - 3;
-            r1 = v3(smLd(sm, S_QT + k), smLd(sm, S_QT + 3 + k), smLd(sm, S_QT + 6 + k));
-            r2 = v3(smLd(sm, S_S1 + k) + smLd(sm, S_S3 + k) + S2.a[k],
-                    smLd(sm, S_S1 + 3 + k) + smLd(sm, S_S3 + 3 + k) + S2.a[3 + k],
-                    smLd(sm, S_S1 + 6 + k) + smLd(sm, S_S3 + 6 + k) + S2.a[6 + k]);
+            const int pi[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+            const V3 Mf = smLd3(sm, R_MF);
+            const V3 s2k = k == 0 ? v3(0.0, -0.5 * Mf.z, 0.5 * Mf.y) : k == 1 ? v3(0.5 * Mf.z, 0.0, -0.5 * Mf.x) : v3(-0.5 * Mf.y, 0.5 * Mf.x, 0.0);
+            r1 = v3(smLd(sm, R_QT + k), smLd(sm, R_QT + 3 + k), smLd(sm, R_QT + 6 + k));
+            r2 = v3(smLd(sm, R_S1 + pi[k][0]) + smLd(sm, R_S3 + k) + s2k.x, smLd(sm, R_S1 + pi[k][1]) + smLd(sm, R_S3 + 3 + k) + s2k.y,
+                    smLd(sm, R_S1 + pi[k][2]) + smLd(sm, R_S3 + 6 + k) + s2k.z);
         } else { // source_i - l_{i-1} & bPrime_{i-1}
             r1 = v3(src[0] - lb[0], src[1] - lb[1], src[2] - lb[2]);
             r2 = v3(src[3] - lb[3], src[4] - lb[4], src[5] - lb[5]);
@@ -535,26 +617,25 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
         X2[0][c] = x2.x; X2[1][c] = x2.y; X2[2][c] = x2.z;
     }
     // ---- store uPrime (36) and bPrime (6)
-    const size_t u0 = tileRow(T, Rc, i, 36, lane), b0 = tileRow(T, Rc, i, 6, lane);
+    const size_t u0 = tileRow((size_t)(b >> 5), p.nmax, i, 36, b & 31), b0 = tileRow((size_t)(b >> 5), p.nmax, i, 6, b & 31);
     if (!LAST) {
 #pragma unroll
         for (int r = 0; r < 3; r++)
 #pragma unroll
             for (int c = 0; c < 6; c++) {
-                p.uP[u0 + (size_t)(6 * r + c) * s] = X1[r][c];
-                p.uP[u0 + (size_t)(6 * (r + 3) + c) * s] = X2[r][c];
+                p.uP[u0 + (size_t)(6 * r + c) * TS] = X1[r][c];
+                p.uP[u0 + (size_t)(6 * (r + 3) + c) * TS] = X2[r][c];
             }
     }
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        p.bP[b0 + (size_t)r * s] = X1[r][6];
-        p.bP[b0 + (size_t)(r + 3) * s] = X2[r][6];
+        p.bP[b0 + (size_t)r * TS] = X1[r][6];
+        p.bP[b0 + (size_t)(r + 3) * TS] = X2[r][6];
     }
     if (!LAST) {
-        // ---- carry for cell i+1:  l = [[P, -Qt], [-Rm, S1 + S23m]],  d_nei = [[-P, -Qt], [Rm, -S1 + S23m]]
-        //      (S23m = S3 - S2)   Dc = d_nei - l & uPrime ;  lb = l & bPrime
+        // ---- carry for cell i+1, one row of l at a time
         {
-            const M3 Pm = smLd9(sm, S_P), Qt = smLd9(sm, S_QT);
+            const M3 Pm = full(smLdS(sm, R_P)), Qt = smLd9(sm, R_QT);
 #pragma unroll
             for (int r = 0; r < 3; r++) {
 #pragma unroll
@@ -569,7 +650,11 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
             }
         }
         {
-            const M3 Rm = smLd9(sm, S_RM), S1 = smLd9(sm, S_S1), Sm = smLd9(sm, S_S3) - S2;
+            const M3 Qt = smLd9(sm, R_QT), S1 = full(smLdS(sm, R_S1));
+            const V3 Mf = smLd3(sm, R_MF);
+            M3 Sm = smLd9(sm, R_S3); // S3 - S2 = S3 + 0.5 spin(M)
+            Sm.a[1] -= 0.5 * Mf.z; Sm.a[2] += 0.5 * Mf.y; Sm.a[3] += 0.5 * Mf.z;
+            Sm.a[5] -= 0.5 * Mf.x; Sm.a[6] -= 0.5 * Mf.y; Sm.a[7] += 0.5 * Mf.x;
 #pragma unroll
             for (int r = 0; r < 3; r++) {
 #pragma unroll
@@ -577,49 +662,58 @@ DEV void forwardCell(const BeamParams& p, const int b, double* __restrict__ sm, 
                     double acc = 0.0;
 #pragma unroll
                     for (int k = 0; k < 3; k++)
-                        acc += (S1.a[3 * r + k] + Sm.a[3 * r + k]) * X2[k][c] - Rm.a[3 * r + k] * X1[k][c];
-                    if (c < 3) Dc[3 + r][c] = Rm.a[3 * r + c] - acc;
+                        acc += (S1.a[3 * r + k] + Sm.a[3 * r + k]) * X2[k][c] + Qt.a[3 * k + r] * X1[k][c];
+                    if (c < 3) Dc[3 + r][c] = -Qt.a[3 * c + r] - acc;
                     else if (c < 6) Dc[3 + r][c] = (Sm.a[3 * r + c - 3] - S1.a[3 * r + c - 3]) - acc;
                     else lb[3 + r] = acc;
                 }
             }
         }
-#pragma unroll
-        for (int r = 0; r < 6; r++) sc[r] = smLd(sm, S_SC + r);
-        Wi = Wn;
     }
 }
 
+// Forward sweep of the 32 beams of one warp.  sm = the warp's slab + lane; bar = the warp's mbarrier.
 template <bool NEWMARK>
-DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ sm)
+DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ warpSm, uint64_t* bar)
 {
     const size_t s = p.Bpad;
+    const int lane = threadIdx.x & 31;
+    const size_t T = (size_t)(b >> 5);
+    double* sm = warpSm + lane;
     double res = 0.0;
-    const int n = p.nSeg[b];
+    const bool live = b < p.B;
+    const int n = live ? p.nSeg[b] : 0;
+    const int nW = __reduce_max_sync(0xffffffffu, n); // cells of the longest beam of the warp
+    if (lane == 0) mbarInit(bar, 1);
+    __syncwarp();
+    if (nW > 0) fwdPrefetch<NEWMARK>(p, T, warpSm, bar, lane, 0);
+
     const double dZ = p.dZ[b];
     const double dcI = 1.0 / dZ; // mesh().deltaCoeffs() of internal faces
     {
         const M3 refL = ld9(p.refL, b, s);
-        smSt9(sm, S_REFL, refL);
-        const V3 CQ = ld3(p.CQ, b, s), CM = ld3(p.CM, b, s), CI = ld3(p.CI, b, s), wg = ld3(p.weight, b, s);
-        smSt(sm, S_CQ, CQ.x); smSt(sm, S_CQ + 1, CQ.y); smSt(sm, S_CQ + 2, CQ.z);
-        smSt(sm, S_CM, CM.x); smSt(sm, S_CM + 1, CM.y); smSt(sm, S_CM + 2, CM.z);
-        smSt(sm, S_CI, CI.x); smSt(sm, S_CI + 1, CI.y); smSt(sm, S_CI + 2, CI.z);
-        smSt(sm, S_WGT, wg.x); smSt(sm, S_WGT + 1, wg.y); smSt(sm, S_WGT + 2, wg.z);
+        const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
+        smSt3(sm, R_DR0, dR0);
+        smSt3(sm, R_E0, mulT(refL, dR0));
+        smSt3(sm, R_CQ, ld3(p.CQ, b, s));
+        smSt3(sm, R_CM, ld3(p.CM, b, s));
+        smSt3(sm, R_CI, ld3(p.CI, b, s));
+        smSt3(sm, R_WGT, ld3(p.weight, b, s));
     }
     const double ARho = NEWMARK ? p.ARho[b] : 0.0;
 
-    // loop-carried: Dc = (nei part of d_i) - l_{i-1} & uPrime_{i-1};  lb = l_{i-1} & bPrime_{i-1};
-    // sc = nei part of source_i;  Wi = W of cell i
-    double Dc[6][6], sc[6], lb[6];
+    // loop-carried in registers: Dc = (nei part of d_i) - l_{i-1} & uPrime_{i-1};  lb = l_{i-1} & bPrime_{i-1};
+    // Wi = W of cell i.  The nei part of source_i travels through the stash (R_SC).
+    double Dc[6][6], lb[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
-        sc[r] = 0.0; lb[r] = 0.0;
+        lb[r] = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; c++) Dc[r][c] = 0.0;
     }
-    V3 Wi = ld3(p.W, tileRow(b >> 5, p.nmax, 0, 3, b & 31), TS);
-    {
+    V3 Wi = v3(0, 0, 0);
+    if (live) {
+        Wi = ld3(p.W, tileRow(T, p.nmax, 0, 3, lane), TS);
         double D36[36], s6[6];
 #pragma unroll
         for (int k = 0; k < 36; k++) D36[k] = 0.0;
@@ -628,13 +722,21 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ s
         patchClosure(p, 0, b, Wi, D36, s6);
 #pragma unroll
         for (int r = 0; r < 6; r++) {
-            sc[r] = s6[r];
+            smSt(sm, R_SC + r, s6[r]);
 #pragma unroll
             for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
         }
     }
-    for (int i = 0; i < n - 1; i++) forwardCell<NEWMARK, false>(p, b, sm, i, n, dZ, dcI, ARho, Dc, sc, lb, Wi, res);
-    forwardCell<NEWMARK, true>(p, b, sm, n - 1, n, dZ, dcI, ARho, Dc, sc, lb, Wi, res);
+    for (int i = 0; i < nW; i++) {
+        double src[6];
+        mbarWait(bar, (uint32_t)(i & 1));
+        if (i < n - 1) fwdAssemble<NEWMARK, false>(p, b, sm, i, dZ, dcI, ARho, Dc, src, Wi, res);
+        else if (i == n - 1) fwdAssemble<NEWMARK, true>(p, b, sm, i, dZ, dcI, ARho, Dc, src, Wi, res);
+        __syncwarp(); // every lane has consumed the buffer: refill it while this cell is eliminated
+        if (i + 1 < nW) fwdPrefetch<NEWMARK>(p, T, warpSm, bar, lane, i + 1);
+        if (i < n - 1) fwdEliminate<false>(p, b, sm, i, Dc, src, lb);
+        else if (i == n - 1) fwdEliminate<true>(p, b, sm, i, Dc, src, lb);
+    }
     return res;
 }
 
@@ -648,7 +750,7 @@ struct FaceState {
 
 // Update of one face (Evolve.C:804-836, 881-913).  (A) = owner / face cell, (B) = neighbour /
 // patch value.  f holds the PRE-solve coefficients; tnew = dR0Ds + snGrad(W_new).
-DEV FaceState updateFace(const FaceCoef& f, Q4 qOld, const M3& LfOld, const M3& refL, V3 Kold,
+DEV FaceState updateFace(const FaceCoef& f, Q4 qOld, const M3& LmOld, V3 Kold,
                          V3 DWa, V3 DWb, V3 DTa, V3 DTb, double dc, bool boundary)
 {
     FaceState o;
@@ -656,8 +758,9 @@ DEV FaceState updateFace(const FaceCoef& f, Q4 qOld, const M3& LfOld, const M3& 
     const V3 sgT = dc * (DTb - DTa), sgW = dc * (DWb - DWa);
     const HalfAngle h = halfAngle(DThf);
     // K += (refLambdaf.T() & Lambdaf.T()) & (DT.T() & snGrad(DTheta))   :825-830 (old Lambdaf)
-    o.K = Kold + mulT(refL, mulT(LfOld, tangentT(DThf, sgT, h)));
-    o.Lf = quatNormalize(quatMul(quatFromRotVec(DThf, h), qOld)); // Lambdaf = R(DThetaf) & Lambdaf :833-836
+    o.K = Kold + mulT(LmOld, tangentT(DThf, sgT, h));
+    // Lambdaf = R(DThetaf) & Lambdaf :833-836; the same left factor updates the stored Lambdaf & refLambdaf
+    o.Lf = quatNormalize(quatMul(quatFromRotVec(DThf, h), qOld));
     // Gamma (:881-887) is a function of the new W and Lambdaf: recomputed by its consumers, not stored
     // Q = explicitQ + CQW & snGrad(DW) + CQTheta & interpolate(DTheta)  :896-903
     o.Q = f.eQ + (mul(f.CQW, sgW) + mul(f.CQTheta, DThf));
@@ -674,17 +777,20 @@ DEV FaceState updateFace(const FaceCoef& f, Q4 qOld, const M3& LfOld, const M3& 
 //   fixedValue / fixedRotation / fixedDisplacement: value from updateCoeffs(); DW_b, DTheta_b are the
 //   pWCorr / pThetaCorr written by assembleBoundaryConditions (BC.C:359-361, 478-482).
 // dR0s is dR0Ds of this patch (sign-flipped on the left patch).
-DEV FaceState patchUpdate(const BeamParams& p, int end, int b, Q4 qOld, const M3& refL, V3 CQ, V3 CM,
-                          V3 Kold, V3 Q, V3 M, V3 dR0s, V3 WoldC, V3 DWc, V3 DTc, double dcB, double delta)
+__device__ __noinline__ FaceState patchUpdate(const BeamParams& p, int end, int b, Q4 qOld, V3 CQ, V3 CM,
+                          V3 Kold, V3 Q, V3 M, V3 WoldC, V3 DWc, V3 DTc, double dcB, double delta)
 {
     const size_t s = p.Bpad;
+    const M3 refL = ld9(p.refL, b, s);
+    const V3 dR0s = end ? v3(refL.a[0], refL.a[3], refL.a[6]) : v3(-refL.a[0], -refL.a[3], -refL.a[6]);
     const size_t i3 = (size_t)end * 3 * s + b, i9 = (size_t)end * 9 * s + b;
-    const M3 LfOld = quatToMat(qOld);
+    const M3 LmOld = quatToMat(qOld);       // Lambdaf_b & refLambdaf
+    const M3 LfOld = mulBT(LmOld, refL);    // Lambdaf_b
     const EndBC e = loadEnd(p, end, b, LfOld);
     const V3 WbOld = e.wType == BFK_W_FIXED ? e.wPresc : e.Wb;
     const V3 t = dR0s + dcB * (WbOld - WoldC);
-    const V3 Gam = gammaOf(LfOld, refL, dR0s + dcB * (e.Wb - WoldC), dR0s);
-    const FaceCoef f = faceCoefficients(LfOld, refL, CQ, CM, Gam, Kold, Q, M, t, dcB, true);
+    const V3 Gam = gammaOf(LmOld, mulT(refL, dR0s), dR0s + dcB * (e.Wb - WoldC));
+    const FaceCoef f = faceCoefficients(LmOld, CQ, CM, Gam, Kold, Q, M, t, dcB, true);
     const double ipd = 1.0 / delta;
     const M3 LambOld = ld9(p.Lamb, i9, s);
     V3 DTb, ThbNew;
@@ -727,7 +833,7 @@ DEV FaceState patchUpdate(const BeamParams& p, int end, int b, Q4 qOld, const M3
     st3(p.DWb, i3, s, DWb);
     st3(p.DThb, i3, s, DTb);
     st9(p.Lamb, i9, s, mul(rotationMatrix(DTb), LambOld)); // Lambda_ = DLambda & Lambda_ on the patch
-    return updateFace(f, qOld, LfOld, refL, Kold, DWc, DWb, DTc, DTb, dcB, true);
+    return updateFace(f, qOld, LmOld, Kold, DWc, DWb, DTc, DTb, dcB, true);
 }
 
 template <bool NEWMARK>
@@ -742,8 +848,12 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
         const double dcI = 1.0 / dZ, dcB = 2.0 / dZ;
         const double delta = 1.0 / dcB;
         const V3 CQ = ld3(p.CQ, b, p.Bpad), CM = ld3(p.CM, b, p.Bpad);
-        const M3 refL = ld9(p.refL, b, p.Bpad);
-        const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
+        V3 dR0, e0;
+        {
+            const M3 refL = ld9(p.refL, b, p.Bpad);
+            dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
+            e0 = mulT(refL, dR0);
+        }
         const double dt = p.dt, beta = p.beta, gamma = p.gamma;
 
         V3 xWn = v3(0, 0, 0), xTn = v3(0, 0, 0); // x_{i+1}
@@ -818,14 +928,13 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 const V3 Kold = ld3(p.K, f3, s);
                 FaceState o;
                 if (i == n - 1) { // right patch
-                    o = patchUpdate(p, 1, b, qfOld, refL, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s), dR0, Wold, DW,
-                                    DT, dcB, delta);
+                    o = patchUpdate(p, 1, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s), Wold, DW, DT, dcB, delta);
                 } else {
-                    const M3 LfOld = quatToMat(qfOld);
+                    const M3 LmOld = quatToMat(qfOld);
                     const V3 t = dR0 + dcI * (WoldN - Wold);
-                    const FaceCoef f = faceCoefficients(LfOld, refL, CQ, CM, gammaOf(LfOld, refL, t, dR0), Kold,
+                    const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, t), Kold,
                                                         ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcI, false);
-                    o = updateFace(f, qfOld, LfOld, refL, Kold, DW, xWn, DT, xTn, dcI, false);
+                    o = updateFace(f, qfOld, LmOld, Kold, DW, xWn, DT, xTn, dcI, false);
                 }
                 stq(p.Lf, f4, s, o.Lf);
                 st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
@@ -834,8 +943,8 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 const size_t f3 = tileRow(T, Rf, 0, 3, lane), f4 = tileRow(T, Rf, 0, 4, lane);
                 const Q4 qfOld = ldq(p.Lf, f4, s);
                 const V3 Kold = ld3(p.K, f3, s);
-                const FaceState o = patchUpdate(p, 0, b, qfOld, refL, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s),
-                                                -dR0, Wold, DW, DT, dcB, delta);
+                const FaceState o = patchUpdate(p, 0, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s),
+                                                Wold, DW, DT, dcB, delta);
                 stq(p.Lf, f4, s, o.Lf);
                 st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
             }
@@ -853,22 +962,23 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
 template <bool NEWMARK>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton(const BeamParams p)
 {
-    extern __shared__ double beam_smem[];
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(128) unsigned char beam_smem[];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5;
     double v[3] = {0.0, 0.0, 0.0};
-    if (b < p.B) {
-        v[0] = forwardSweep<NEWMARK>(p, b, beam_smem + threadIdx.x);
-        backwardSweep<NEWMARK>(p, b, v[1], v[2]);
-    }
+    // whole warps run the forward sweep (the prefetch is a warp-collective); padding lanes idle inside
+    v[0] = forwardSweep<NEWMARK>(p, b, (double*)(beam_smem + SMEM_HEADER_BYTES) + (size_t)w * WARP_SMEM_DOUBLES,
+                                 (uint64_t*)beam_smem + w);
+    if (b < p.B) backwardSweep<NEWMARK>(p, b, v[1], v[2]);
     blockReduceStore<3>(v, p.partial, 0);
 }
 template <bool NEWMARK>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(const BeamParams p)
 {
-    extern __shared__ double beam_smem[];
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(128) unsigned char beam_smem[];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5;
     double v[1] = {0.0};
-    if (b < p.B) v[0] = forwardSweep<NEWMARK>(p, b, beam_smem + threadIdx.x);
+    v[0] = forwardSweep<NEWMARK>(p, b, (double*)(beam_smem + SMEM_HEADER_BYTES) + (size_t)w * WARP_SMEM_DOUBLES,
+                                 (uint64_t*)beam_smem + w);
     blockReduceStore<1>(v, p.partial, 0);
 }
 template <bool NEWMARK>

@@ -156,6 +156,59 @@ DEV M3 diagMulT(V3 c, const M3& Lm)
 }
 DEV V3 cmul(V3 c, V3 v) { return v3(c.x * v.x, c.y * v.y, c.z * v.z); }
 
+// A & B.T()
+DEV M3 mulBT(const M3& A, const M3& B)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            r.a[3 * i + j] = A.a[3 * i] * B.a[3 * j] + A.a[3 * i + 1] * B.a[3 * j + 1] + A.a[3 * i + 2] * B.a[3 * j + 2];
+    return r;
+}
+
+// Symmetric 3x3 tensor (CQW = Lam C Lam^T and CMTheta are symmetric by construction): 6 entries.
+struct Sym3 {
+    double xx, xy, xz, yy, yz, zz;
+};
+DEV Sym3 operator*(double s, const Sym3& A)
+{
+    Sym3 r;
+    r.xx = s * A.xx; r.xy = s * A.xy; r.xz = s * A.xz; r.yy = s * A.yy; r.yz = s * A.yz; r.zz = s * A.zz;
+    return r;
+}
+// Lam & (diag(c) & Lam.T()), upper triangle with the operation order of conjDiag
+DEV Sym3 conjDiagSym(const M3& Lm, V3 c)
+{
+    const double a0 = c.x * Lm.a[0], a1 = c.y * Lm.a[1], a2 = c.z * Lm.a[2];
+    const double b0 = c.x * Lm.a[3], b1 = c.y * Lm.a[4], b2 = c.z * Lm.a[5];
+    const double c0 = c.x * Lm.a[6], c1 = c.y * Lm.a[7], c2 = c.z * Lm.a[8];
+    Sym3 r;
+    r.xx = Lm.a[0] * a0 + Lm.a[1] * a1 + Lm.a[2] * a2;
+    r.xy = Lm.a[0] * b0 + Lm.a[1] * b1 + Lm.a[2] * b2;
+    r.xz = Lm.a[0] * c0 + Lm.a[1] * c1 + Lm.a[2] * c2;
+    r.yy = Lm.a[3] * b0 + Lm.a[4] * b1 + Lm.a[5] * b2;
+    r.yz = Lm.a[3] * c0 + Lm.a[4] * c1 + Lm.a[5] * c2;
+    r.zz = Lm.a[6] * c0 + Lm.a[7] * c1 + Lm.a[8] * c2;
+    return r;
+}
+DEV M3 full(const Sym3& A)
+{
+    M3 r;
+    r.a[0] = A.xx; r.a[1] = A.xy; r.a[2] = A.xz;
+    r.a[3] = A.xy; r.a[4] = A.yy; r.a[5] = A.yz;
+    r.a[6] = A.xz; r.a[7] = A.yz; r.a[8] = A.zz;
+    return r;
+}
+DEV V3 symMul(const Sym3& A, V3 v)
+{
+    return v3(A.xx * v.x + A.xy * v.y + A.xz * v.z, A.xy * v.x + A.yy * v.y + A.yz * v.z,
+              A.xz * v.x + A.yz * v.y + A.zz * v.z);
+}
+// A & spinTensor(t) for symmetric A
+DEV M3 mulSpinR(const Sym3& A, V3 t) { return mulSpinR(full(A), t); }
+
 // OpenFOAM inv(tensor): adjugate / determinant
 DEV M3 inv(const M3& A)
 {

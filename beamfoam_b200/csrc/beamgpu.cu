@@ -208,19 +208,42 @@ __global__ void fillIdentity(double* __restrict__ T, int64_t rows, int width, in
     }
 }
 
-// host-ordered rotation tensors (9) <-> unit quaternions (4): the device keeps Lambda / Lambdaf as quaternions
+// Lambdaf = I at start (CTL.C:289-314): the stored product Lambdaf & refLambdaf starts as refLambdaf.
+// One thread per (tile row, lane) of the warp-tiled face array [tile][R][4][32].
+__global__ void fillRefRotation(double* __restrict__ Lf, int64_t rowsTotal, int R, const double* __restrict__ refL, int Bpad)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= rowsTotal * 32) return;
+    const int64_t row = k / 32;
+    const int lane = (int)(k % 32);
+    const int b = (int)(row / R) * 32 + lane;
+    const Q4 q = matToQuat(ld9(refL, b, Bpad));
+    double* o = Lf + row * 4 * 32 + lane;
+    o[0] = q.w; o[32] = q.x; o[64] = q.y; o[96] = q.z;
+}
+
+// host-ordered rotation tensors (9) <-> unit quaternions (4): the device keeps Lambda as a quaternion and, for the
+// face field, the quaternion of Lambdaf & refLambdaf (refL != nullptr; start = faceStart to find the beam of an
+// internal face, nullptr for patch values, where element g belongs to beam g).
 template <bool TO_QUAT>
-__global__ void convertRotation(double* __restrict__ tens, double* __restrict__ quat, int64_t count)
+__global__ void convertRotation(double* __restrict__ tens, double* __restrict__ quat, int64_t count,
+                                const double* __restrict__ refL, const int64_t* __restrict__ start, int B, int Bpad)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= count) return;
+    M3 ref = m3eye();
+    if (refL) {
+        const int b = start ? findBeam(start, B, g) : (int)g;
+        ref = ld9(refL, b, Bpad);
+    }
     if (TO_QUAT) {
         M3 R;
         for (int k = 0; k < 9; k++) R.a[k] = tens[g * 9 + k];
-        const Q4 q = matToQuat(R);
+        const Q4 q = matToQuat(refL ? mul(R, ref) : R);
         quat[g * 4] = q.w; quat[g * 4 + 1] = q.x; quat[g * 4 + 2] = q.y; quat[g * 4 + 3] = q.z;
     } else {
-        const M3 R = quatToMat(q4(quat[g * 4], quat[g * 4 + 1], quat[g * 4 + 2], quat[g * 4 + 3]));
+        M3 R = quatToMat(q4(quat[g * 4], quat[g * 4 + 1], quat[g * 4 + 2], quat[g * 4 + 3]));
+        if (refL) R = mulBT(R, ref);
         for (int k = 0; k < 9; k++) tens[g * 9 + k] = R.a[k];
     }
 }
@@ -237,24 +260,25 @@ __global__ void gammaField(const BeamParams p, const int64_t* __restrict__ faceS
     const double dZ = p.dZ[b], dcI = 1.0 / dZ, dcB = 2.0 / dZ;
     const M3 refL = ld9(p.refL, b, p.Bpad);
     const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
+    const V3 e0 = mulT(refL, dR0);
     V3 Wprev = ld3(p.W, tileRow(T, Rc, 0, 3, lane), TS);
     if (left) {
-        const V3 g = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, 0, 4, lane), TS)), refL,
-                             dcB * (ld3(p.Wb, b, p.Bpad) - Wprev) - dR0, -dR0);
+        const V3 g = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, 0, 4, lane), TS)), -e0,
+                             dcB * (ld3(p.Wb, b, p.Bpad) - Wprev) - dR0);
         left[3 * (size_t)b] = g.x; left[3 * (size_t)b + 1] = g.y; left[3 * (size_t)b + 2] = g.z;
     }
     for (int j = 1; j < n; j++) {
         const V3 Wn = ld3(p.W, tileRow(T, Rc, j, 3, lane), TS);
         if (internal) {
-            const V3 g = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, j, 4, lane), TS)), refL, dR0 + dcI * (Wn - Wprev), dR0);
+            const V3 g = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, j, 4, lane), TS)), e0, dR0 + dcI * (Wn - Wprev));
             double* o = internal + 3 * (faceStart[b] + j - 1);
             o[0] = g.x; o[1] = g.y; o[2] = g.z;
         }
         Wprev = Wn;
     }
     if (right) {
-        const V3 g = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, n, 4, lane), TS)), refL,
-                             dR0 + dcB * (ld3(p.Wb, (size_t)3 * p.Bpad + b, p.Bpad) - Wprev), dR0);
+        const V3 g = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, n, 4, lane), TS)), e0,
+                             dR0 + dcB * (ld3(p.Wb, (size_t)3 * p.Bpad + b, p.Bpad) - Wprev));
         right[3 * (size_t)b] = g.x; right[3 * (size_t)b + 1] = g.y; right[3 * (size_t)b + 2] = g.z;
     }
 }
@@ -498,7 +522,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         int64_t rows = (int64_t)nmax * (Bpad / 32);
         fillIdentity<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_Lam, rows, 32, 4);
         rows = ((int64_t)nmax + 1) * (Bpad / 32);
-        fillIdentity<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_Lf, rows, 32, 4);
+        fillRefRotation<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_Lf, rows, nmax + 1, c->d_refL, Bpad);
         fillIdentity<<<(unsigned)((2 * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lamb, 2, Bpad, 9);
         c->launches += 3;
         CREATE_CUDA(cudaGetLastError());
@@ -557,7 +581,8 @@ static void stageInternal(bf_ctx* c, double* dev, int nc, int surface, int kind,
         c->launches++;
     } else if (kind == FK_ROTATION) {
         launchTranspose<false>(c, dev, c->d_stageQ, 4, surface);
-        convertRotation<false><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(dst, c->d_stageQ, count);
+        convertRotation<false><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(
+            dst, c->d_stageQ, count, surface ? c->d_refL : nullptr, c->d_faceStart, (int)c->B, c->Bpad);
         c->launches += 2;
     } else {
         gammaField<<<(unsigned)((c->B + 127) / 128), 128, 0, c->stream>>>(makeParams(c), c->d_faceStart, dst, nullptr, nullptr);
@@ -573,7 +598,8 @@ static int xferInternal(bf_ctx* c, double* dev, double* host, int nc, int surfac
         if (kind == FK_GAMMA) return BF_OK; // derived from W and Lambdaf on the device (Evolve.C:881-887): nothing to store
         CUDA_OK(c, cudaMemcpyAsync(c->d_stage, host, sizeof(double) * count * nc, cudaMemcpyHostToDevice, c->stream));
         if (kind == FK_ROTATION) {
-            convertRotation<true><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(c->d_stage, c->d_stageQ, count);
+            convertRotation<true><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(
+                c->d_stage, c->d_stageQ, count, surface ? c->d_refL : nullptr, c->d_faceStart, (int)c->B, c->Bpad);
             launchTranspose<true>(c, dev, c->d_stageQ, 4, surface);
             c->launches += 2;
         } else {
@@ -602,7 +628,7 @@ static int xferPatch(bf_ctx* c, double* dev, double* host, int nc, int end, int 
     } else if (toDevice) {
         CUDA_OK(c, cudaMemcpyAsync(c->d_stagePatch, host, bytes, cudaMemcpyHostToDevice, c->stream));
         if (kind == FK_ROTATION) {
-            convertRotation<true><<<grid, 256, 0, c->stream>>>(c->d_stagePatch, c->d_stagePatchQ, c->B);
+            convertRotation<true><<<grid, 256, 0, c->stream>>>(c->d_stagePatch, c->d_stagePatchQ, c->B, c->d_refL, nullptr, (int)c->B, c->Bpad);
             transposePatch<true><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatchQ, c->d_nSeg, (int)c->B, c->Bpad, R, 4, end, faceArray);
             c->launches++;
         } else
@@ -610,7 +636,7 @@ static int xferPatch(bf_ctx* c, double* dev, double* host, int nc, int end, int 
     } else {
         if (kind == FK_ROTATION) {
             transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatchQ, c->d_nSeg, (int)c->B, c->Bpad, R, 4, end, faceArray);
-            convertRotation<false><<<grid, 256, 0, c->stream>>>(c->d_stagePatch, c->d_stagePatchQ, c->B);
+            convertRotation<false><<<grid, 256, 0, c->stream>>>(c->d_stagePatch, c->d_stagePatchQ, c->B, c->d_refL, nullptr, (int)c->B, c->Bpad);
             c->launches++;
         } else
             transposePatch<false><<<grid, 256, 0, c->stream>>>(dev, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, R, nc, end, faceArray);
