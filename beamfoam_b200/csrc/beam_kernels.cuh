@@ -42,6 +42,8 @@ struct BeamParams {
     int first;    // 1 on the first Newton iteration of a time step (Newmark predictor)
     int storeInc; // keep DW/DTheta cell fields
     double dt, beta, gamma;
+    // Newmark scalars, divided once on the host: 1/(beta dt), 0.5/beta - 1, gamma/(beta dt), 1/(beta dt^2), (1/dt)(gamma/beta)
+    double nk1, nk2, nVel, nAcc, nU;
     // per beam [Bpad]
     const int* nSeg;
     const double* dZ;
@@ -157,6 +159,15 @@ DEV void addBlkT(double (&D)[6][6], int r0, int c0, double s, const M3& T)
     for (int r = 0; r < 3; r++)
 #pragma unroll
         for (int c = 0; c < 3; c++) D[r0 + r][c0 + c] += s * T.a[3 * c + r];
+}
+// D[r0.., c0..] = carry block from the stash + s * T  (rows k0.. of the warp slab hold the carry, 6x6 row-major)
+DEV void carryBlkFrom(double (&D)[6][6], const double* sm, int k0, int r0, int c0, double s, const M3& T)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            D[r0 + r][c0 + c] = ((const volatile double*)sm)[(k0 + 6 * (r0 + r) + c0 + c) * 32] + s * T.a[3 * r + c];
 }
 DEV void subV(double (&b)[6], int r0, V3 v) { b[r0] -= v.x; b[r0 + 1] -= v.y; b[r0 + 2] -= v.z; }
 DEV void addV(double (&b)[6], int r0, V3 v) { b[r0] += v.x; b[r0 + 1] += v.y; b[r0 + 2] += v.z; }
@@ -295,15 +306,18 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 // ---------------------------------------------------------------------------
 // Every warp owns a private slab of shared memory, [row][32 lanes] doubles (row r of lane l at
 // sm[r*32 + l]: consecutive lanes hit consecutive banks, every access is conflict-free):
-//   * per-beam constants (18 rows),
+//   * per-beam constants (12 rows; CIRho and the self-weight are used once per cell and come from L1),
 //   * the "stash": the face tensors of face i+1 that are needed again after the elimination of
 //     cell i (u columns, l block, neighbour part of d_{i+1}); a register extension -- an FP64 warp
 //     instruction occupies the pipe for 2 cycles, an LDS.64 costs the same,
-//   * the prefetch buffer: the state rows the NEXT cell will read, brought in by the TMA engine
-//     (cp.async.bulk, one copy per array, completion on the warp's mbarrier) while the current
-//     cell is being eliminated.  The warp-tiled layout makes every array's rows of one cell one
-//     contiguous run (nc x 256 B), so a cell needs 9 bulk copies and no register ever waits on
-//     a global load in the steady state.
+//   * the prefetch buffer: the face rows the NEXT cell will read first, brought in by the TMA
+//     engine (cp.async.bulk, one copy per array, completion on the warp's mbarrier) while the
+//     current cell is being eliminated.  The warp-tiled layout makes every array's rows of one
+//     cell one contiguous run (nc x 256 B).  The Newmark cell rows are consumed late in the
+//     assembly and are loaded directly (L2-prefetched one cell ahead),
+//   * the carry of the block-Thomas recurrence (36 doubles): written at the end of a cell, read
+//     back where the next cell first needs each block, so that the 72 registers it would occupy
+//     across the loop are free for the assembly.
 #ifndef BEAM_THREADS
 #define BEAM_THREADS 128
 #endif
@@ -315,8 +329,7 @@ enum {
     R_E0 = 3,    // refLambdaf.T() & dR0Ds (3)  (= e_x for an orthonormal refLambdaf)
     R_CQ = 6,    // diag CQ (3)
     R_CM = 9,    // diag CM (3)
-    R_CI = 12,   // diag CIRho (3)
-    R_WGT = 15,  // rho A g (3)
+    R_LB = 12,   // l_{i-1} & bPrime_{i-1} (6): the right-hand-side part of the carry
     R_P = 18,    // a*CQW, symmetric: xx xy xz yy yz zz (6)   face i+1
     R_QT = 24,   // 0.5*CQTheta (9);  a*CMQW = -(0.5*CQTheta).T()
     R_S1 = 33,   // a*CMTheta, symmetric (6)
@@ -327,16 +340,15 @@ enum {
     B_W = 0,     //   W of cell i+1 (3)
     B_LF = 3,    //   Lambdaf & refLambdaf of face i+1, quaternion (4)
     B_K = 7, B_Q = 10, B_M = 13, //   K, Q, M of face i+1
-    B_LAM = 16,  //   Lambda of cell i, quaternion (4)          (Newmark only from here)
-    B_AC = 20, B_OM = 23, B_DOM = 26, //   Accl, Omega, dotOmega of cell i
-    B_U = 29,    //   U of cell i (first iteration of a time step only)
-    B_ROWS = 32,
-    R_TOTAL = R_BUF + B_ROWS
+    B_ROWS = 16,
+    R_DC = R_BUF + B_ROWS, // the carry: (nei part of d_i) - l_{i-1} & uPrime_{i-1}, row-major 6x6 (36)
+    R_TOTAL = R_DC + 36
 };
 #define WARP_SMEM_DOUBLES (R_TOTAL * 32)
 #define SMEM_HEADER_BYTES 128 // one mbarrier (8 B) per warp
 #define SMEM_BYTES (SMEM_HEADER_BYTES + (BEAM_THREADS / 32) * WARP_SMEM_DOUBLES * sizeof(double))
 
+#define carryBlk(D, sm, r0, c0, s, T) carryBlkFrom(D, sm, R_DC, r0, c0, s, T)
 DEV double smLd(const double* sm, int k) { return ((const volatile double*)sm)[k * 32]; }
 DEV void smSt(double* sm, int k, double v) { sm[k * 32] = v; }
 DEV V3 smLd3(const double* sm, int k) { return v3(smLd(sm, k), smLd(sm, k + 1), smLd(sm, k + 2)); }
@@ -402,24 +414,24 @@ DEV void bulkLoad(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t
 template <bool NEWMARK>
 DEV void fwdPrefetch(const BeamParams& p, size_t T, double* warpSm, uint64_t* bar, int lane, int i)
 {
-    if (lane != 0) return;
     const int Rc = p.nmax, Rf = p.nmax + 1;
+    if (NEWMARK) { // cell i+... rows read by plain loads late in the assembly: pull them into L2
+        const size_t n3 = tileRow(T, Rc, i, 3, lane);
+        pfL2(p.Lam + tileRow(T, Rc, i, 4, 0) + 4 * lane); // 4 rows x 32 doubles: one double in four per lane
+        pfL2(p.Ac + n3); pfL2(p.Ac + n3 + 2 * TS);
+        pfL2(p.Om + n3); pfL2(p.Om + n3 + 2 * TS);
+        pfL2(p.dOm + n3); pfL2(p.dOm + n3 + 2 * TS);
+        if (p.first) { pfL2(p.U + n3); pfL2(p.U + n3 + 2 * TS); }
+    }
+    if (lane != 0) return;
     const bool hasW = i + 1 < p.nmax; // no cell i+1 in the slab for the last row
-    const bool first = NEWMARK && p.first;
-    mbarExpectTx(bar, ((hasW ? 3 : 0) + 4 + 9 + (NEWMARK ? 4 + 9 : 0) + (first ? 3 : 0)) * 256u);
+    mbarExpectTx(bar, ((hasW ? 3 : 0) + 4 + 9) * 256u);
     double* buf = warpSm + (size_t)R_BUF * 32;
     if (hasW) bulkLoad(buf + B_W * 32, p.W + tileRow(T, Rc, i + 1, 3, 0), 3 * 256, bar);
     bulkLoad(buf + B_LF * 32, p.Lf + tileRow(T, Rf, i + 1, 4, 0), 4 * 256, bar);
     bulkLoad(buf + B_K * 32, p.K + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
     bulkLoad(buf + B_Q * 32, p.Q + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
     bulkLoad(buf + B_M * 32, p.M + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
-    if (NEWMARK) {
-        bulkLoad(buf + B_LAM * 32, p.Lam + tileRow(T, Rc, i, 4, 0), 4 * 256, bar);
-        bulkLoad(buf + B_AC * 32, p.Ac + tileRow(T, Rc, i, 3, 0), 3 * 256, bar);
-        bulkLoad(buf + B_OM * 32, p.Om + tileRow(T, Rc, i, 3, 0), 3 * 256, bar);
-        bulkLoad(buf + B_DOM * 32, p.dOm + tileRow(T, Rc, i, 3, 0), 3 * 256, bar);
-        if (first) bulkLoad(buf + B_U * 32, p.U + tileRow(T, Rc, i, 3, 0), 3 * 256, bar);
-    }
 }
 
 // Boundary closure is executed for 2 of the n cells of a beam; keeping it out of line keeps its
@@ -459,26 +471,46 @@ __device__ __noinline__ void patchClosure(const BeamParams& p, int end, int b, V
     }
 }
 
+// What a cell reads from the prefetch buffer: copied to registers first, so that the buffer can be
+// refilled for the next cell before any of the heavy work starts.
+struct FaceIn {
+    V3 Wn;     // W of cell i+1
+    Q4 qf;     // Lambdaf & refLambdaf of face i+1
+    V3 K, Q, M;
+};
+DEV FaceIn loadFaceIn(const double* sm)
+{
+    FaceIn f;
+    f.Wn = smLd3(sm, R_BUF + B_W);
+    f.qf = smLdq(sm, R_BUF + B_LF);
+    f.K = smLd3(sm, R_BUF + B_K);
+    f.Q = smLd3(sm, R_BUF + B_Q);
+    f.M = smLd3(sm, R_BUF + B_M);
+    return f;
+}
+
 // Assembly of cell i (first half of a forward step).  Reads the prefetch buffer (face i+1,
 // W_{i+1}, Newmark state of cell i), adds the own part of d_i and the loads/inertia to the
 // carry Dc, forms source_i, and parks the face tensors in the stash.  LAST = the cell whose right
 // face is the right patch: it closes the patch instead of an internal face.
 template <bool NEWMARK, bool LAST>
 DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, const int i, const double dZ,
-                     const double dcI, const double ARho, double (&Dc)[6][6], double (&src)[6], V3& Wi, double& res)
+                     const double dcI, const double h, const double ARho, const FaceIn& in, double (&Dc)[6][6],
+                     double (&src)[6], V3& Wi, double& res)
 {
-    const double dt = p.dt, beta = p.beta, gamma = p.gamma;
+    // Dc is an OUTPUT: each 3x3 block of the carry is fetched from the stash (R_DC) where its first
+    // contribution is added
+    const double dt = p.dt, gamma = p.gamma;
 #pragma unroll
     for (int r = 0; r < 6; r++) src[r] = smLd(sm, R_SC + r);
     if (!LAST) {
         // ---- coefficients of face i+1 (Evolve.C:673-753) and own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
-        const V3 Wn = smLd3(sm, R_BUF + B_W);
+        const V3 Wn = in.Wn;
         const V3 dR0 = smLd3(sm, R_DR0);
         const V3 t = v3(dR0.x + dcI * (Wn.x - Wi.x), dR0.y + dcI * (Wn.y - Wi.y), dR0.z + dcI * (Wn.z - Wi.z)); // dR0Ds + snGrad(W)
         Wi = Wn;
-        const M3 Lm = quatToMat(smLdq(sm, R_BUF + B_LF));                             // Lambdaf & refLambdaf :678
-        const double h = 0.5 / dcI;
-        const M3 SQ = spin(smLd3(sm, R_BUF + B_Q));
+        const M3 Lm = quatToMat(in.qf);                                               // Lambdaf & refLambdaf :678
+        const M3 SQ = spin(in.Q);
         V3 eQ;
         M3 SC; // spinTensor(t) & CQW = -(CQW & spinTensor(t)).T() for the symmetric CQW
         {
@@ -490,23 +522,23 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
             const Sym3 Pm = dcI * CQW;
             smStS(sm, R_P, Pm);
             smSt9(sm, R_QT, Qt);
-            addBlkS(Dc, 0, 0, -1.0, Pm);
-            addBlk(Dc, 0, 3, 1.0, Qt);
-            addBlkT(Dc, 3, 0, 1.0, Qt);                                               // -a*CMQW = +(0.5*CQTheta).T() :706-715
+            carryBlk(Dc, sm, 0, 0, -1.0, full(Pm));
+            carryBlk(Dc, sm, 0, 3, 1.0, Qt);
+            carryBlk(Dc, sm, 3, 0, 1.0, transpose(Qt));                               // -a*CMQW = +(0.5*CQTheta).T() :706-715
             SC = -1.0 * transpose(G);
         }
         const V3 eMQ = h * cross(t, eQ);                                              // :737-741
         {
             const V3 CM = smLd3(sm, R_CM);
             const Sym3 S1 = dcI * conjDiagSym(Lm, CM);                                  // a*CMTheta :699
-            const V3 eM = mul(Lm, cmul(CM, smLd3(sm, R_BUF + B_K)));                  // :684
+            const V3 eM = mul(Lm, cmul(CM, in.K));                                    // :684
             const M3 S3 = (0.5 * h) * (mulSpinR(SC, t) - mulSpinL(t, SQ));            // 0.5*CMQTheta :718-735
-            const V3 Mf = smLd3(sm, R_BUF + B_M);
+            const V3 Mf = in.M;
             const M3 S2 = -0.5 * spin(Mf);                                            // 0.5*CMTheta2 :703
             smStS(sm, R_S1, S1);
             smSt9(sm, R_S3, S3);
             smSt3(sm, R_MF, Mf);
-            addBlkS(Dc, 3, 3, -1.0, S1);
+            carryBlk(Dc, sm, 3, 3, -1.0, full(S1));
             addBlk(Dc, 3, 3, 1.0, S3 + S2);
             subV(src, 0, eQ);
             subV(src, 3, eM + eMQ);
@@ -519,7 +551,7 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
         for (int r = 0; r < 6; r++) {
             s6[r] = src[r];
 #pragma unroll
-            for (int c = 0; c < 6; c++) D36[6 * r + c] = Dc[r][c];
+            for (int c = 0; c < 6; c++) D36[6 * r + c] = smLd(sm, R_DC + 6 * r + c);
         }
         patchClosure(p, 1, b, Wi, D36, s6);
 #pragma unroll
@@ -533,30 +565,30 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
     const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31);
     const double Lcell = p.Lc ? p.Lc[tileRow((size_t)(b >> 5), p.nmax, i, 1, b & 31)] : dZ;
     if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, TS));
-    subV(src, 0, Lcell * smLd3(sm, R_WGT));
+    subV(src, 0, Lcell * ld3(p.weight, b, p.Bpad));
     if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, TS));
     if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
-        const M3 Lm = quatToMat(smLdq(sm, R_BUF + B_LAM));
-        V3 Ac = smLd3(sm, R_BUF + B_AC), Om = smLd3(sm, R_BUF + B_OM), dOm = smLd3(sm, R_BUF + B_DOM);
+        const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
+        V3 Ac = ld3(p.Ac, c3, TS), Om = ld3(p.Om, c3, TS), dOm = ld3(p.dOm, c3, TS);
         if (p.first) {
-            const V3 Uo = smLd3(sm, R_BUF + B_U);
-            const double k1 = 1.0 / (dt * beta), k2 = 0.5 / beta - 1.0;
+            const V3 Uo = ld3(p.U, c3, TS);
+            const double k1 = p.nk1, k2 = p.nk2;
             const V3 Ao = Ac, Oo = Om, dOo = dOm;
             Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
             dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
             Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
         }
-        const V3 CI = smLd3(sm, R_CI);
+        const V3 CI = ld3(p.CI, b, p.Bpad);
         const V3 CIOm = cmul(CI, Om);
         const V3 a1 = mul(Lm, cmul(CI, dOm));  // Lambda & (CIRho & dotOmega)
         const V3 a2 = mul(Lm, cross(Om, CIOm)); // Lambda & (Omega ^ (CIRho & Omega))
         addV(src, 0, (ARho * Lcell) * Ac);
         addV(src, 3, Lcell * (a1 + a2));
-        const double QRhoCoeff = -Lcell * ARho / (dt * dt * beta);
+        const double QRhoCoeff = -(Lcell * ARho) * p.nAcc;
         Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
         // MRhoCoeff :467-488
         const M3 T2 = spin(mul(Lm, CIOm)) - mul(Lm, mulSpinL(Om, diagMulT(CI, Lm)));
-        const M3 MR = spin(a2 + a1) + (gamma / (beta * dt)) * T2 - (1.0 / (beta * dt * dt)) * conjDiag(Lm, CI);
+        const M3 MR = spin(a2 + a1) + p.nVel * T2 - p.nAcc * conjDiag(Lm, CI);
         addBlk(Dc, 3, 3, Lcell, MR);
     }
 #pragma unroll
@@ -569,8 +601,8 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
 //   l = [[P, -Qt], [Qt.T(), S1 + Sm]],   d_nei = [[-P, -Qt], [-Qt.T(), Sm - S1]],   Sm = S3 + 0.5 spin(M)
 //   Dc <- d_nei - l & uPrime ;  lb <- l & bPrime
 template <bool LAST>
-DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm, const int i, double (&Dc)[6][6],
-                      const double (&src)[6], double (&lb)[6])
+DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm, const int i, const double (&Dc)[6][6],
+                      const double (&src)[6])
 {
     M3 Ai, AiB, Si, Cm;
     {
@@ -607,8 +639,8 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
             r2 = v3(smLd(sm, R_S1 + pi[k][0]) + smLd(sm, R_S3 + k) + s2k.x, smLd(sm, R_S1 + pi[k][1]) + smLd(sm, R_S3 + 3 + k) + s2k.y,
                     smLd(sm, R_S1 + pi[k][2]) + smLd(sm, R_S3 + 6 + k) + s2k.z);
         } else { // source_i - l_{i-1} & bPrime_{i-1}
-            r1 = v3(src[0] - lb[0], src[1] - lb[1], src[2] - lb[2]);
-            r2 = v3(src[3] - lb[3], src[4] - lb[4], src[5] - lb[5]);
+            r1 = v3(src[0] - smLd(sm, R_LB), src[1] - smLd(sm, R_LB + 1), src[2] - smLd(sm, R_LB + 2));
+            r2 = v3(src[3] - smLd(sm, R_LB + 3), src[4] - smLd(sm, R_LB + 4), src[5] - smLd(sm, R_LB + 5));
         }
         const V3 y1 = mul(Ai, r1);
         const V3 x2 = mul(Si, r2 - mul(Cm, y1));
@@ -640,12 +672,13 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
             for (int r = 0; r < 3; r++) {
 #pragma unroll
                 for (int c = 0; c < 7; c++) {
-                    double acc = 0.0;
+                    double acc = Pm.a[3 * r] * X1[0][c];
+                    acc = fma(Pm.a[3 * r + 1], X1[1][c], acc); acc = fma(Pm.a[3 * r + 2], X1[2][c], acc);
 #pragma unroll
-                    for (int k = 0; k < 3; k++) acc += Pm.a[3 * r + k] * X1[k][c] - Qt.a[3 * r + k] * X2[k][c];
-                    if (c < 3) Dc[r][c] = -Pm.a[3 * r + c] - acc;
-                    else if (c < 6) Dc[r][c] = -Qt.a[3 * r + c - 3] - acc;
-                    else lb[r] = acc;
+                    for (int k = 0; k < 3; k++) acc = fma(-Qt.a[3 * r + k], X2[k][c], acc);
+                    if (c < 3) smSt(sm, R_DC + 6 * r + c, -Pm.a[3 * r + c] - acc);
+                    else if (c < 6) smSt(sm, R_DC + 6 * r + c, -Qt.a[3 * r + c - 3] - acc);
+                    else smSt(sm, R_LB + r, acc);
                 }
             }
         }
@@ -655,21 +688,36 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
             M3 Sm = smLd9(sm, R_S3); // S3 - S2 = S3 + 0.5 spin(M)
             Sm.a[1] -= 0.5 * Mf.z; Sm.a[2] += 0.5 * Mf.y; Sm.a[3] += 0.5 * Mf.z;
             Sm.a[5] -= 0.5 * Mf.x; Sm.a[6] -= 0.5 * Mf.y; Sm.a[7] += 0.5 * Mf.x;
+            const M3 Sl = S1 + Sm;
 #pragma unroll
             for (int r = 0; r < 3; r++) {
 #pragma unroll
                 for (int c = 0; c < 7; c++) {
-                    double acc = 0.0;
+                    double acc = Sl.a[3 * r] * X2[0][c];
+                    acc = fma(Sl.a[3 * r + 1], X2[1][c], acc); acc = fma(Sl.a[3 * r + 2], X2[2][c], acc);
 #pragma unroll
-                    for (int k = 0; k < 3; k++)
-                        acc += (S1.a[3 * r + k] + Sm.a[3 * r + k]) * X2[k][c] + Qt.a[3 * k + r] * X1[k][c];
-                    if (c < 3) Dc[3 + r][c] = -Qt.a[3 * c + r] - acc;
-                    else if (c < 6) Dc[3 + r][c] = (Sm.a[3 * r + c - 3] - S1.a[3 * r + c - 3]) - acc;
-                    else lb[3 + r] = acc;
+                    for (int k = 0; k < 3; k++) acc = fma(Qt.a[3 * k + r], X1[k][c], acc);
+                    if (c < 3) smSt(sm, R_DC + 6 * (3 + r) + c, -Qt.a[3 * c + r] - acc);
+                    else if (c < 6) smSt(sm, R_DC + 6 * (3 + r) + c, (Sm.a[3 * r + c - 3] - S1.a[3 * r + c - 3]) - acc);
+                    else smSt(sm, R_LB + 3 + r, acc);
                 }
             }
         }
     }
+}
+
+// The last cell of a beam (right patch instead of an internal face): once per beam, kept out of line so that
+// its patch code and stack arrays stay out of the register allocation of the steady-state loop.
+template <bool NEWMARK>
+__device__ __noinline__ double fwdLastCell(const BeamParams& p, const int b, double* __restrict__ sm, const int i,
+                                           const double dZ, const double ARho, V3 Wi)
+{
+    double Dc[6][6], src[6], res = 0.0;
+    FaceIn none;
+    none.Wn = none.K = none.Q = none.M = v3(0, 0, 0); none.qf = q4(1, 0, 0, 0);
+    fwdAssemble<NEWMARK, true>(p, b, sm, i, dZ, 1.0 / dZ, 0.5 * dZ, ARho, none, Dc, src, Wi, res);
+    fwdEliminate<true>(p, b, sm, i, Dc, src);
+    return res;
 }
 
 // Forward sweep of the 32 beams of one warp.  sm = the warp's slab + lane; bar = the warp's mbarrier.
@@ -690,6 +738,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
 
     const double dZ = p.dZ[b];
     const double dcI = 1.0 / dZ; // mesh().deltaCoeffs() of internal faces
+    const double h = 0.5 / dcI;  // 0.5/deltaCoeffs of :706-741
     {
         const M3 refL = ld9(p.refL, b, s);
         const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
@@ -697,20 +746,13 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
         smSt3(sm, R_E0, mulT(refL, dR0));
         smSt3(sm, R_CQ, ld3(p.CQ, b, s));
         smSt3(sm, R_CM, ld3(p.CM, b, s));
-        smSt3(sm, R_CI, ld3(p.CI, b, s));
-        smSt3(sm, R_WGT, ld3(p.weight, b, s));
+#pragma unroll
+        for (int r = 0; r < 6; r++) smSt(sm, R_LB + r, 0.0);
     }
     const double ARho = NEWMARK ? p.ARho[b] : 0.0;
 
-    // loop-carried in registers: Dc = (nei part of d_i) - l_{i-1} & uPrime_{i-1};  lb = l_{i-1} & bPrime_{i-1};
-    // Wi = W of cell i.  The nei part of source_i travels through the stash (R_SC).
-    double Dc[6][6], lb[6];
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-        lb[r] = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; c++) Dc[r][c] = 0.0;
-    }
+    // loop-carried in registers: lb = l_{i-1} & bPrime_{i-1};  Wi = W of cell i.  The carry
+    // (nei part of d_i) - l_{i-1} & uPrime_{i-1} and the nei part of source_i travel through the stash.
     V3 Wi = v3(0, 0, 0);
     if (live) {
         Wi = ld3(p.W, tileRow(T, p.nmax, 0, 3, lane), TS);
@@ -724,18 +766,20 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
         for (int r = 0; r < 6; r++) {
             smSt(sm, R_SC + r, s6[r]);
 #pragma unroll
-            for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
+            for (int c = 0; c < 6; c++) smSt(sm, R_DC + 6 * r + c, D36[6 * r + c]);
         }
     }
     for (int i = 0; i < nW; i++) {
-        double src[6];
         mbarWait(bar, (uint32_t)(i & 1));
-        if (i < n - 1) fwdAssemble<NEWMARK, false>(p, b, sm, i, dZ, dcI, ARho, Dc, src, Wi, res);
-        else if (i == n - 1) fwdAssemble<NEWMARK, true>(p, b, sm, i, dZ, dcI, ARho, Dc, src, Wi, res);
-        __syncwarp(); // every lane has consumed the buffer: refill it while this cell is eliminated
+        const FaceIn in = loadFaceIn(sm);
+        __syncwarp(); // every lane holds its buffer rows in registers: refill the buffer for the next cell now
         if (i + 1 < nW) fwdPrefetch<NEWMARK>(p, T, warpSm, bar, lane, i + 1);
-        if (i < n - 1) fwdEliminate<false>(p, b, sm, i, Dc, src, lb);
-        else if (i == n - 1) fwdEliminate<true>(p, b, sm, i, Dc, src, lb);
+        if (i < n - 1) { // a cell with an internal face on its right
+            double src[6], Dc[6][6];
+            fwdAssemble<NEWMARK, false>(p, b, sm, i, dZ, dcI, h, ARho, in, Dc, src, Wi, res);
+            fwdEliminate<false>(p, b, sm, i, Dc, src);
+        } else if (i == n - 1)
+            res += fwdLastCell<NEWMARK>(p, b, sm, i, dZ, ARho, Wi);
     }
     return res;
 }
@@ -908,17 +952,17 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
             if (NEWMARK) {
                 V3 U = ld3(p.U, c3, s), Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
                 if (p.first) { // predictor :167-186
-                    const double k1 = 1.0 / (dt * beta), k2 = 0.5 / beta - 1.0;
+                    const double k1 = p.nk1, k2 = p.nk2;
                     const V3 Uo = U, Ao = Ac, Oo = Om, dOo = dOm;
                     Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
                     U = Uo + dt * ((1.0 - gamma) * Ao + gamma * Ac);
                     dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
                     Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
                 }
-                U = U + ((1.0 / dt) * (gamma / beta)) * DW;           // :785
-                Ac = Ac + (1.0 / (dt * dt * beta)) * DW;              // :788
-                Om = Om + (gamma / (beta * dt)) * LtDT;                // :853-862
-                dOm = dOm + (1.0 / (beta * dt * dt)) * LtDT;
+                U = U + p.nU * DW;                                    // :785
+                Ac = Ac + p.nAcc * DW;                                // :788
+                Om = Om + p.nVel * LtDT;                              // :853-862
+                dOm = dOm + p.nAcc * LtDT;
                 st3(p.U, c3, s, U); st3(p.Ac, c3, s, Ac); st3(p.Om, c3, s, Om); st3(p.dOm, c3, s, dOm);
             }
             // ---- face j = i+1

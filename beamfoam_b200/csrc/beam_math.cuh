@@ -209,13 +209,26 @@ DEV V3 symMul(const Sym3& A, V3 v)
 // A & spinTensor(t) for symmetric A
 DEV M3 mulSpinR(const Sym3& A, V3 t) { return mulSpinR(full(A), t); }
 
+// 1/x to <= 1 ulp without the IEEE-division slow path: MUFU.RCP64H seed + two Newton steps.  The compiler's
+// own division guards denormal / huge operands with a CALL to a slow-path subroutine; a call site inside
+// the sweep loops pins registers and forces spills around it.  The operands here (determinants of the
+// diagonal blocks, |theta| + SMALL) are ordinary normal numbers; 0 -> inf, NaN -> NaN still propagate.
+DEV double rcpFast(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 // OpenFOAM inv(tensor): adjugate / determinant
 DEV M3 inv(const M3& A)
 {
     const double xx = A.a[0], xy = A.a[1], xz = A.a[2], yx = A.a[3], yy = A.a[4], yz = A.a[5], zx = A.a[6],
                  zy = A.a[7], zz = A.a[8];
     const double det = xx * yy * zz + xy * yz * zx + xz * yx * zy - xx * yz * zy - xy * yx * zz - xz * yy * zx;
-    const double id = 1.0 / det;
+    const double id = rcpFast(det);
     M3 r;
     r.a[0] = (yy * zz - zy * yz) * id; r.a[1] = (xz * zy - xy * zz) * id; r.a[2] = (xy * yz - xz * yy) * id;
     r.a[3] = (zx * yz - yx * zz) * id; r.a[4] = (xx * zz - xz * zx) * id; r.a[5] = (yx * xz - xx * yz) * id;

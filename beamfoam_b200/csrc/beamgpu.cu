@@ -827,6 +827,8 @@ static BeamParams makeParams(bf_ctx* c)
     p.B = (int)c->B; p.Bpad = c->Bpad; p.nmax = c->nmax;
     p.newmark = c->scheme == BF_SCHEME_NEWMARK; p.first = c->iOuterCorr == 0; p.storeInc = c->storeInc;
     p.dt = c->deltaT; p.beta = c->betaN; p.gamma = c->gammaN;
+    p.nk1 = 1.0 / (p.dt * p.beta); p.nk2 = 0.5 / p.beta - 1.0; p.nVel = p.gamma / (p.beta * p.dt);
+    p.nAcc = 1.0 / (p.beta * p.dt * p.dt); p.nU = (1.0 / p.dt) * (p.gamma / p.beta);
     p.nSeg = c->d_nSeg; p.dZ = c->d_dZ; p.CQ = c->d_CQ; p.CM = c->d_CM; p.ARho = c->d_ARho; p.CI = c->d_CI;
     p.weight = c->d_weight; p.refL = c->d_refL; p.wType = c->d_wType; p.thType = c->d_thType;
     p.W = c->d_W; p.Th = c->d_Th; p.Lam = c->d_Lam; p.U = c->d_U; p.Ac = c->d_Ac; p.Om = c->d_Om; p.dOm = c->d_dOm;
