@@ -69,8 +69,14 @@ struct BeamParams {
     // block-Thomas scratch
     double* uP; // [tile][nmax][36][32]
     double* bP; // [tile][nmax][6][32]
-    // per-block partial sums: [3][gridDim.x]
+    // per-tile partial sums: [3][nTiles], tile = 128 consecutive beams (one block's worth)
     double* partial;
+    // pipelined launch (beam_newton_pipelined): tickets and per-tile "forward done" flags
+    int nTiles;
+    int epoch;   // value a flag takes when the forward sweep of this launch has finished the tile
+    int* ctl;    // [0] next forward ticket, [1] next backward ticket, [2 + smid] blocks seen on an SM; zeroed per launch
+    int* fDone;  // [nTiles]
+    unsigned long long* trace; // optional [nTiles][4]: forward start/end, backward start/end (globaltimer ns), else null
 };
 
 DEV V3 ld3(const double* __restrict__ p, size_t i, size_t s) { return v3(p[i], p[i + s], p[i + 2 * s]); }
@@ -276,11 +282,12 @@ DEV void bcClosure(double (&D)[6][6], double (&b)[6], const FaceCoef& f, const E
     subV(b, 3, f.eMQ); // :1178-1187
 }
 
-// Block reduction of up to 3 values; thread 0 writes partial[k*gridDim.x + blockIdx.x].
+// Block reduction of up to 3 values; thread 0 writes partial[(slot0 + k)*nTiles + tile].
 template <int NV>
-DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slot0)
+DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slot0, int nTiles, int tile)
 {
     __shared__ double sm[NV][32];
+    __syncthreads(); // the staging words may still be read by the previous reduction of a persistent block
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; k++) {
@@ -296,7 +303,7 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
             double x = lane < nw ? sm[k][lane] : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-            if (lane == 0) partial[(size_t)(slot0 + k) * gridDim.x + blockIdx.x] = x;
+            if (lane == 0) partial[(size_t)(slot0 + k) * nTiles + tile] = x;
         }
     }
 }
@@ -721,8 +728,9 @@ __device__ __noinline__ double fwdLastCell(const BeamParams& p, const int b, dou
 }
 
 // Forward sweep of the 32 beams of one warp.  sm = the warp's slab + lane; bar = the warp's mbarrier.
+// phase = number of buffer fills this warp's mbarrier has completed so far (its parity selects the wait).
 template <bool NEWMARK>
-DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ warpSm, uint64_t* bar)
+DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ warpSm, uint64_t* bar, uint32_t& phase)
 {
     const size_t s = p.Bpad;
     const int lane = threadIdx.x & 31;
@@ -732,8 +740,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
     const bool live = b < p.B;
     const int n = live ? p.nSeg[b] : 0;
     const int nW = __reduce_max_sync(0xffffffffu, n); // cells of the longest beam of the warp
-    if (lane == 0) mbarInit(bar, 1);
-    __syncwarp();
+    __syncwarp(); // (persistent blocks) every lane has left the previous tile's buffer
     if (nW > 0) fwdPrefetch<NEWMARK>(p, T, warpSm, bar, lane, 0);
 
     const double dZ = p.dZ[b];
@@ -770,7 +777,8 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
         }
     }
     for (int i = 0; i < nW; i++) {
-        mbarWait(bar, (uint32_t)(i & 1));
+        mbarWait(bar, phase & 1u);
+        phase++;
         const FaceIn in = loadFaceIn(sm);
         __syncwarp(); // every lane holds its buffer rows in registers: refill the buffer for the next cell now
         if (i + 1 < nW) fwdPrefetch<NEWMARK>(p, T, warpSm, bar, lane, i + 1);
@@ -921,14 +929,14 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
             }
             double x[6];
 #pragma unroll
-            for (int r = 0; r < 6; r++) x[r] = p.bP[b0 + (size_t)r * s];
+            for (int r = 0; r < 6; r++) x[r] = __ldcg(p.bP + b0 + (size_t)r * s); // written by another SM in this launch: L2
             if (i < n - 1) {
                 const double xn[6] = {xWn.x, xWn.y, xWn.z, xTn.x, xTn.y, xTn.z};
 #pragma unroll
                 for (int r = 0; r < 6; r++) {
                     double acc = 0.0;
 #pragma unroll
-                    for (int c = 0; c < 6; c++) acc += p.uP[u0 + (size_t)(6 * r + c) * s] * xn[c];
+                    for (int c = 0; c < 6; c++) acc += __ldcg(p.uP + u0 + (size_t)(6 * r + c) * s) * xn[c];
                     x[r] -= acc;
                 }
             }
@@ -998,32 +1006,117 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
 }
 
 // ---------------------------------------------------------------------------
-// Kernels.  beam_newton is the product path: ONE launch per Newton iteration, each thread
-// runs the forward sweep and then the backward sweep of its own beam (no inter-thread
-// dependency exists, so no grid-wide synchronisation is needed between the two).
-// beam_forward / beam_backward are the same sweeps as two launches, kept for profiling.
+// Kernels.
+//   beam_newton_pipelined : the product path, ONE launch per Newton iteration.  The forward sweep is
+//       FP64-pipe bound and leaves HBM idle, the backward sweep is HBM bound and leaves the FP64 pipe
+//       idle, and a sweep is a 200-step serial recurrence, so the two only overlap if different tiles
+//       (128 beams) are in different phases on the same SM at the same time.  Persistent blocks, two per
+//       SM: the first block to arrive on an SM takes forward tickets, the second takes backward tickets
+//       (and waits on the per-tile "forward done" flag); when the forward tickets run out the forward
+//       blocks drain backward tickets too.  Every wait is on a forward sweep that is already running,
+//       and forward sweeps never wait, so the scheme cannot deadlock.
+//   beam_newton           : each thread runs forward then backward on its own beam (all tiles in phase).
+//   beam_forward / beam_backward : the two sweeps as two launches, for profiling.
 // ---------------------------------------------------------------------------
+DEV uint32_t warpBarrierSetup(unsigned char* smem)
+{
+    if ((threadIdx.x & 31) == 0) mbarInit((uint64_t*)smem + (threadIdx.x >> 5), 1);
+    __syncwarp();
+    return 0;
+}
+#define WARP_SLAB(smem, w) ((double*)((smem) + SMEM_HEADER_BYTES) + (size_t)(w) * WARP_SMEM_DOUBLES)
+
+template <bool NEWMARK>
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton_pipelined(const BeamParams p)
+{
+    extern __shared__ __align__(128) unsigned char beam_smem[];
+    __shared__ int sTicket[2]; // tile, kind (1 forward, 2 backward)
+    const int w = threadIdx.x >> 5;
+    uint32_t phase = warpBarrierSetup(beam_smem);
+    int role = 0;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        sTicket[0] = atomicAdd(&p.ctl[2 + smid], 1) & 1; // first block on this SM: forward role, second: backward role
+    }
+    __syncthreads();
+    role = sTicket[0];
+    bool forwardLeft = role == 0;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tile = -1, kind = 0;
+            if (forwardLeft) {
+                tile = atomicAdd(&p.ctl[0], 1);
+                if (tile < p.nTiles) kind = 1;
+            }
+            if (!kind) {
+                tile = atomicAdd(&p.ctl[1], 1);
+                if (tile < p.nTiles) {
+                    kind = 2;
+                    // acquire: the forward sweep of this launch has finished the tile (its scratch is visible)
+                    int seen;
+                    for (;;) {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.fDone + tile) : "memory");
+                        if (seen == p.epoch) break;
+                        __nanosleep(200);
+                    }
+                }
+            }
+            sTicket[0] = tile; sTicket[1] = kind;
+        }
+        __syncthreads();
+        const int tile = sTicket[0], kind = sTicket[1];
+        if (!kind) break;
+        const int b = tile * BEAM_THREADS + threadIdx.x;
+        if (p.trace && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[4 * tile + (kind == 1 ? 0 : 2)] = t;
+        }
+        if (kind == 1) {
+            double v[1];
+            v[0] = forwardSweep<NEWMARK>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
+            blockReduceStore<1>(v, p.partial, 0, p.nTiles, tile);
+            __threadfence(); // scratch + partial sums of every thread are visible device-wide ...
+            __syncthreads();
+            if (threadIdx.x == 0) // ... before the flag is
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.fDone + tile), "r"(p.epoch) : "memory");
+        } else {
+            forwardLeft = false;
+            __threadfence();
+            double v[2] = {0.0, 0.0};
+            if (b < p.B) backwardSweep<NEWMARK>(p, b, v[0], v[1]);
+            blockReduceStore<2>(v, p.partial, 1, p.nTiles, tile);
+        }
+        if (p.trace && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[4 * tile + (kind == 1 ? 1 : 3)] = t;
+        }
+    }
+}
 template <bool NEWMARK>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton(const BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5;
+    uint32_t phase = warpBarrierSetup(beam_smem);
     double v[3] = {0.0, 0.0, 0.0};
     // whole warps run the forward sweep (the prefetch is a warp-collective); padding lanes idle inside
-    v[0] = forwardSweep<NEWMARK>(p, b, (double*)(beam_smem + SMEM_HEADER_BYTES) + (size_t)w * WARP_SMEM_DOUBLES,
-                                 (uint64_t*)beam_smem + w);
+    v[0] = forwardSweep<NEWMARK>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
     if (b < p.B) backwardSweep<NEWMARK>(p, b, v[1], v[2]);
-    blockReduceStore<3>(v, p.partial, 0);
+    blockReduceStore<3>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
 template <bool NEWMARK>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(const BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5;
+    uint32_t phase = warpBarrierSetup(beam_smem);
     double v[1] = {0.0};
-    v[0] = forwardSweep<NEWMARK>(p, b, (double*)(beam_smem + SMEM_HEADER_BYTES) + (size_t)w * WARP_SMEM_DOUBLES,
-                                 (uint64_t*)beam_smem + w);
-    blockReduceStore<1>(v, p.partial, 0);
+    v[0] = forwardSweep<NEWMARK>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
+    blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
 template <bool NEWMARK>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_backward(const BeamParams p)
@@ -1031,7 +1124,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_backward(c
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
     if (b < p.B) backwardSweep<NEWMARK>(p, b, v[0], v[1]);
-    blockReduceStore<2>(v, p.partial, 1);
+    blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
 }
 
 // Deterministic final reduction of the per-block partial sums (fixed order).

@@ -19,6 +19,7 @@
 #include <vector>
 
 #define BF_GREAT 1e15
+#define CTL_INTS (2 + 1024) // forward ticket, backward ticket, blocks seen per SM (smid < 1024)
 #define THREADS BEAM_THREADS
 
 static char g_create_err[512] = "";
@@ -54,6 +55,9 @@ struct bf_ctx {
     double *d_Wb, *d_Thb, *d_Lamb, *d_DWb, *d_DThb, *d_force, *d_wPresc, *d_thPresc, *d_follower, *d_offset,
         *d_moment, *d_springK, *d_springDir;
     double *d_uP, *d_bP, *d_partial, *d_sums;
+    int *d_ctl, *d_fDone; // pipelined launch: tickets / per-SM role counters, per-tile forward-done flags
+    int epoch, pipeGrid, pipelined;
+    unsigned long long* d_trace; // BEAMGPU_TRACE=1: per-tile sweep time stamps of the last pipelined launch
     double* d_stage; // staging buffer in host (AoS) ordering
     double* d_stagePatch; // separate small staging for patch values (never shared with a pending mirror)
     double* d_stageQ;     // host-ordered quaternions (4 per cell/face) between the transposition and the tensor conversion
@@ -369,6 +373,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     // the sweeps park their face tensors in dynamic shared memory (> 48 KB needs the opt-in)
     CREATE_CUDA(cudaFuncSetAttribute(transposeInternal<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 33 * 8));
     CREATE_CUDA(cudaFuncSetAttribute(transposeInternal<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 33 * 8));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_newton_pipelined<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_newton_pipelined<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_newton<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_newton<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -446,9 +452,25 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     // ---- block-Thomas scratch + partial sums
     {
         char* cur;
-        if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->grid + 8) + 256 * 4)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->grid + 8) + sizeof(int) * (CTL_INTS + (size_t)c->grid) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
         c->d_partial = carve<double>(cur, 3 * (size_t)c->grid); c->d_sums = carve<double>(cur, 8);
+        c->d_ctl = carve<int>(cur, CTL_INTS); c->d_fDone = carve<int>(cur, (size_t)c->grid);
+        c->epoch = 0;
+        // persistent pipelined launch: as many blocks as are co-resident (2 per SM with these kernels), never more
+        // than the 2 tickets (forward + backward) per tile
+        int perSm = 0, nSm = 0;
+        CREATE_CUDA(cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, c->device));
+        CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, beam_newton_pipelined<true>, THREADS, SMEM_BYTES));
+        if (perSm < 1) perSm = 1;
+        if (perSm > 2) perSm = 2;
+        c->pipeGrid = perSm * nSm < 2 * c->grid ? perSm * nSm : 2 * c->grid;
+        // Off by default: measured on B200 at 65,536 x 200 the tile-level forward/backward overlap gains 12 % in the
+        // steady state but a launch is only 3.5 tiles per SM deep, so the ramp (backward blocks idle until the first
+        // forward tile is done) and the tail cost more than that (4.99 ms vs 4.35 ms).
+        c->pipelined = getenv("BEAMGPU_PIPELINE") ? 1 : 0;
+        c->d_trace = nullptr;
+        if (getenv("BEAMGPU_TRACE") && devAlloc(c, (void**)&c->d_trace, sizeof(unsigned long long) * 4 * (size_t)c->grid)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
     }
     // ---- staging buffer (largest field in host ordering: a tensor vol field)
     c->stageDoubles = (size_t)c->N * 9;
@@ -811,6 +833,15 @@ extern "C" int bf_region_elapsed_ms(bf_ctx* c, double* ms)
     *ms = t;
     return BF_OK;
 }
+// Debug aid (not in beamgpu.h): copies the [nTiles][4] time stamps of the last pipelined launch (BEAMGPU_TRACE=1).
+extern "C" int bf_debug_trace(bf_ctx* c, unsigned long long* out, int64_t maxTiles)
+{
+    if (!c->d_trace) return BF_ERR_INVALID;
+    const int64_t n = maxTiles < c->grid ? maxTiles : c->grid;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    CUDA_OK(c, cudaMemcpy(out, c->d_trace, sizeof(unsigned long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    return (int)n;
+}
 extern "C" int bf_kernel_time_ms(bf_ctx* c, int32_t reset, double* fwd, double* bwd, int64_t* it)
 {
     if (fwd) *fwd = c->fwdMs;
@@ -839,6 +870,7 @@ static BeamParams makeParams(bf_ctx* c)
     p.wPresc = c->d_wPresc; p.thPresc = c->d_thPresc; p.follower = c->d_follower; p.offset = c->d_offset;
     p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir;
     p.uP = c->d_uP; p.bP = c->d_bP; p.partial = c->d_partial;
+    p.nTiles = c->grid; p.epoch = c->epoch; p.ctl = c->d_ctl; p.fDone = c->d_fDone; p.trace = c->d_trace;
     return p;
 }
 
@@ -854,6 +886,18 @@ static int launchIteration(bf_ctx* c)
         if (p.newmark) beam_backward<true><<<c->grid, THREADS, 0, c->stream>>>(p);
         else beam_backward<false><<<c->grid, THREADS, 0, c->stream>>>(p);
         c->launches += 2;
+    } else if (c->pipelined) { // product path: persistent blocks, forward and backward sweeps of different tiles overlap
+        if (++c->epoch == 0x7fffffff) { // flags compare equal to the epoch: start over before it wraps
+            CUDA_OK(c, cudaMemsetAsync(c->d_fDone, 0, sizeof(int) * (size_t)c->grid, c->stream));
+            c->epoch = 1;
+        }
+        BeamParams q = p;
+        q.epoch = c->epoch;
+        CUDA_OK(c, cudaMemsetAsync(c->d_ctl, 0, sizeof(int) * CTL_INTS, c->stream));
+        if (q.newmark) beam_newton_pipelined<true><<<c->pipeGrid, THREADS, SMEM_BYTES, c->stream>>>(q);
+        else beam_newton_pipelined<false><<<c->pipeGrid, THREADS, SMEM_BYTES, c->stream>>>(q);
+        if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
+        c->launches += 1;
     } else {
         if (p.newmark) beam_newton<true><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);
         else beam_newton<false><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);

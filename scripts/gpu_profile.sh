@@ -10,4 +10,3 @@ $CMD > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:beam_newton -s 6 -c 2 -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 tail -3 gpurun_out/ncu_full.log
-ls -la gpurun_out
