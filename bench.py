@@ -130,7 +130,7 @@ def config_dict(args, world, total):
                     f"rho 500/1000/2000, tip force (2000 2000 0)" + ("" if args.no_jitter else " x (1+0.1u_b)"),
         "beams_total": total, "beams_per_gpu": total // world, "cells_per_beam": args.cells,
         "cells_total": total * args.cells, "tolerances": "nCorrectors 200, rtol 1e-8, stol 1e-10",
-        "l2_policy": "inputs larger than L2: >=9.9 GB of state + 4.4 GB scratch per GPU vs 126 MB L2",
+        "l2_policy": f"inputs larger than L2: {total // world * args.cells * 280 / 1e9:.1f} GB of state + {total // world * args.cells * 336 / 1e9:.1f} GB of scratch per GPU vs 126 MB L2",
         "parallelism": f"beams sharded over {world} GPU(s); one 3-double all-reduce per Newton iteration",
     }
 
