@@ -44,6 +44,12 @@ struct BeamParams {
     double dt, beta, gamma;
     // Newmark scalars, divided once on the host: 1/(beta dt), 0.5/beta - 1, gamma/(beta dt), 1/(beta dt^2), (1/dt)(gamma/beta)
     double nk1, nk2, nVel, nAcc, nU;
+    // The arrays U and Om hold the Newmark step constants  U* = U - gamma dt Accl,  Omega* = Omega - gamma dt dotOmega
+    // (= U_old + dt (1 - gamma) Accl_old, the explicit part of the Newmark velocity): every correction adds
+    // gamma/(beta dt) DW to U and 1/(beta dt^2) DW to Accl (Evolve.C:782-789, 849-863), so U - gamma dt Accl does not
+    // change inside a time step and neither U nor Omega has to be read or written by the corrections.
+    // gdt = gamma * dt of this step; gdtPrev = gamma * dt of the step the stored constants belong to.
+    double gdt, gdtPrev;
     // per beam [Bpad]
     const int* nSeg;
     const double* dZ;
@@ -55,7 +61,7 @@ struct BeamParams {
     const double* refL;   // [9][Bpad]
     const int* wType;     // [2][Bpad]
     const int* thType;    // [2][Bpad]
-    // cells [tile][nmax][nc][32]; Lam = unit quaternion (4) of the cell rotation Lambda
+    // cells [tile][nmax][nc][32]; Lam = unit quaternion (4) of the cell rotation Lambda; U, Om = U*, Omega* (above)
     double *W, *Th, *Lam, *U, *Ac, *Om, *dOm, *DW, *DTh;
     const double *q, *m, *Lc; // optional (may be null)
     // faces [tile][nmax+1][nc][32]: face j of beam b; j=0 left patch, j=nSeg[b] right patch
@@ -576,15 +582,17 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
     if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, TS));
     if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
         const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
-        V3 Ac = ld3(p.Ac, c3, TS), Om = ld3(p.Om, c3, TS), dOm = ld3(p.dOm, c3, TS);
+        V3 Ac = ld3(p.Ac, c3, TS), dOm = ld3(p.dOm, c3, TS), Om;
+        const V3 OmS = ld3(p.Om, c3, TS); // Omega*
         if (p.first) {
-            const V3 Uo = ld3(p.U, c3, TS);
+            const V3 Ao = Ac, dOo = dOm;
+            const V3 Uo = ld3(p.U, c3, TS) + p.gdtPrev * Ao, Oo = OmS + p.gdtPrev * dOo; // end of the previous step
             const double k1 = p.nk1, k2 = p.nk2;
-            const V3 Ao = Ac, Oo = Om, dOo = dOm;
             Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
             dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
             Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
-        }
+        } else
+            Om = OmS + p.gdt * dOm;
         const V3 CI = ld3(p.CI, b, p.Bpad);
         const V3 CIOm = cmul(CI, Om);
         const V3 a1 = mul(Lm, cmul(CI, dOm));  // Lambda & (CIRho & dotOmega)
@@ -920,8 +928,8 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 pfRows<3>(p.W, m3, s); pfRows<3>(p.Th, m3, s);
                 pfRows<4>(p.Lam, tileRow(T, Rc, i - 1, 4, lane), s);
                 if (NEWMARK) {
-                    pfRows<3>(p.U, m3, s); pfRows<3>(p.Ac, m3, s);
-                    pfRows<3>(p.Om, m3, s); pfRows<3>(p.dOm, m3, s);
+                    pfRows<3>(p.Ac, m3, s); pfRows<3>(p.dOm, m3, s);
+                    if (p.first) { pfRows<3>(p.U, m3, s); pfRows<3>(p.Om, m3, s); }
                 }
                 pfRows<4>(p.Lf, tileRow(T, Rf, i, 4, lane), s);
                 pfRows<3>(p.K, g3, s);
@@ -958,20 +966,19 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
             x2 += dot(Wnew, Wnew) + dot(Thn, Thn);
             if (p.storeInc) { st3(p.DW, c3, s, DW); st3(p.DTh, c3, s, DT); }
             if (NEWMARK) {
-                V3 U = ld3(p.U, c3, s), Ac = ld3(p.Ac, c3, s), Om = ld3(p.Om, c3, s), dOm = ld3(p.dOm, c3, s);
-                if (p.first) { // predictor :167-186
+                V3 Ac = ld3(p.Ac, c3, s), dOm = ld3(p.dOm, c3, s);
+                if (p.first) { // predictor :167-186, and the step constants U*, Omega* (see BeamParams)
                     const double k1 = p.nk1, k2 = p.nk2;
-                    const V3 Uo = U, Ao = Ac, Oo = Om, dOo = dOm;
+                    const V3 Ao = Ac, dOo = dOm;
+                    const V3 Uo = ld3(p.U, c3, s) + p.gdtPrev * Ao, Oo = ld3(p.Om, c3, s) + p.gdtPrev * dOo;
                     Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
-                    U = Uo + dt * ((1.0 - gamma) * Ao + gamma * Ac);
                     dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
-                    Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
+                    st3(p.U, c3, s, Uo + (dt * (1.0 - gamma)) * Ao);   // U = U* + gamma dt Accl from here on
+                    st3(p.Om, c3, s, Oo + (dt * (1.0 - gamma)) * dOo);
                 }
-                U = U + p.nU * DW;                                    // :785
-                Ac = Ac + p.nAcc * DW;                                // :788
-                Om = Om + p.nVel * LtDT;                              // :853-862
-                dOm = dOm + p.nAcc * LtDT;
-                st3(p.U, c3, s, U); st3(p.Ac, c3, s, Ac); st3(p.Om, c3, s, Om); st3(p.dOm, c3, s, dOm);
+                Ac = Ac + p.nAcc * DW;                                // :788 (and :785 through U*)
+                dOm = dOm + p.nAcc * LtDT;                            // :853-862
+                st3(p.Ac, c3, s, Ac); st3(p.dOm, c3, s, dOm);
             }
             // ---- face j = i+1
             {

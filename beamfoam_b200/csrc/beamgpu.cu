@@ -69,6 +69,7 @@ struct bf_ctx {
     // options / time state
     int scheme, storeInc;
     double betaN, gammaN, deltaT;
+    double dtStar; // the time step the stored Newmark constants U*, Omega* belong to (beam_kernels.cuh, BeamParams)
     int iOuterCorr;
     bool hasQ, hasM;
     bf_reduce_fn reducer;
@@ -410,6 +411,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->betaN = opt->newmarkBeta > 0 ? opt->newmarkBeta : 0.25;
     c->gammaN = opt->newmarkGamma > 0 ? opt->newmarkGamma : 0.5;
     c->deltaT = 1.0;
+    c->dtStar = 1.0;
     c->iOuterCorr = 0;
     const bool newmark = c->scheme == BF_SCHEME_NEWMARK;
     const size_t bp = (size_t)Bpad, nc_ = (size_t)nmax, nf_ = (size_t)nmax + 1;
@@ -563,7 +565,29 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
 }
 
 // ---------------------------------------------------------------------------
-enum { FK_PLAIN = 0, FK_ROTATION = 1, FK_GAMMA = 2 }; // how a field is represented on the device
+// How a field is represented on the device.  FK_STAR: a Newmark velocity stored as its step constant
+// (U* = U - gamma dt Accl), FK_RATE: the rate such a constant refers to (setting it must keep the velocity).
+enum { FK_PLAIN = 0, FK_ROTATION = 1, FK_GAMMA = 2, FK_STAR = 3, FK_RATE = 4 };
+static double* starPartner(bf_ctx* c, double* dev)
+{
+    if (dev == c->d_U) return c->d_Ac;
+    if (dev == c->d_Om) return c->d_dOm;
+    if (dev == c->d_Ac) return c->d_U;
+    if (dev == c->d_dOm) return c->d_Om;
+    return nullptr;
+}
+// out = a + g * x over a whole tiled cell array (3 components)
+__global__ void axpyCells(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ x, double g, size_t n)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = a[k] + g * x[k];
+}
+// star += g * (rateOld - rateNew); rateOld = rateNew   (the velocity star + g * rate is unchanged)
+__global__ void rebaseStar(double* __restrict__ star, double* __restrict__ rate, const double* __restrict__ rateNew, double g, size_t n)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { star[k] += g * (rate[k] - rateNew[k]); rate[k] = rateNew[k]; }
+}
 static int fieldInfo(bf_ctx* c, int field, double** dev, double** endArr, int* nc, int* surface, int* kind)
 {
     *endArr = nullptr; *surface = 0; *nc = 3; *kind = FK_PLAIN; *dev = nullptr;
@@ -573,10 +597,10 @@ static int fieldInfo(bf_ctx* c, int field, double** dev, double** endArr, int* n
     case BF_FIELD_LAMBDA: *dev = c->d_Lam; *endArr = c->d_Lamb; *nc = 9; *kind = FK_ROTATION; break;
     case BF_FIELD_DW: *dev = c->d_DW; *endArr = c->d_DWb; break;
     case BF_FIELD_DTHETA: *dev = c->d_DTh; *endArr = c->d_DThb; break;
-    case BF_FIELD_U: *dev = c->d_U; break;
-    case BF_FIELD_ACCL: *dev = c->d_Ac; break;
-    case BF_FIELD_OMEGA: *dev = c->d_Om; break;
-    case BF_FIELD_DOTOMEGA: *dev = c->d_dOm; break;
+    case BF_FIELD_U: *dev = c->d_U; *kind = FK_STAR; break;
+    case BF_FIELD_ACCL: *dev = c->d_Ac; *kind = FK_RATE; break;
+    case BF_FIELD_OMEGA: *dev = c->d_Om; *kind = FK_STAR; break;
+    case BF_FIELD_DOTOMEGA: *dev = c->d_dOm; *kind = FK_RATE; break;
     case BF_FIELD_LAMBDAF: *dev = c->d_Lf; *nc = 9; *surface = 1; *kind = FK_ROTATION; break;
     case BF_FIELD_GAMMA: *dev = c->d_Lf; *surface = 1; *kind = FK_GAMMA; break;
     case BF_FIELD_K: *dev = c->d_K; *surface = 1; break;
@@ -598,9 +622,14 @@ static void stageInternal(bf_ctx* c, double* dev, int nc, int surface, int kind,
 {
     const int64_t count = surface ? c->F : c->N;
     if (count == 0) return;
-    if (kind == FK_PLAIN) {
+    if (kind == FK_PLAIN || kind == FK_RATE) {
         launchTranspose<false>(c, dev, dst, nc, surface);
         c->launches++;
+    } else if (kind == FK_STAR) { // velocity = constant + gamma dt * rate, formed in the (idle) block-Thomas scratch
+        const size_t n = (size_t)3 * c->nmax * c->Bpad;
+        axpyCells<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_uP, dev, starPartner(c, dev), c->gammaN * c->dtStar, n);
+        launchTranspose<false>(c, c->d_uP, dst, nc, surface);
+        c->launches += 2;
     } else if (kind == FK_ROTATION) {
         launchTranspose<false>(c, dev, c->d_stageQ, 4, surface);
         convertRotation<false><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(
@@ -623,6 +652,13 @@ static int xferInternal(bf_ctx* c, double* dev, double* host, int nc, int surfac
             convertRotation<true><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(
                 c->d_stage, c->d_stageQ, count, surface ? c->d_refL : nullptr, c->d_faceStart, (int)c->B, c->Bpad);
             launchTranspose<true>(c, dev, c->d_stageQ, 4, surface);
+            c->launches += 2;
+        } else if (kind == FK_STAR || kind == FK_RATE) {
+            const size_t n = (size_t)3 * c->nmax * c->Bpad;
+            const double g = c->gammaN * c->dtStar;
+            launchTranspose<true>(c, c->d_uP, c->d_stage, nc, surface); // padding rows of the scratch are never read back
+            if (kind == FK_STAR) axpyCells<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(dev, c->d_uP, starPartner(c, dev), -g, n);
+            else rebaseStar<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(starPartner(c, dev), dev, c->d_uP, g, n);
             c->launches += 2;
         } else {
             launchTranspose<true>(c, dev, c->d_stage, nc, surface);
@@ -860,6 +896,7 @@ static BeamParams makeParams(bf_ctx* c)
     p.dt = c->deltaT; p.beta = c->betaN; p.gamma = c->gammaN;
     p.nk1 = 1.0 / (p.dt * p.beta); p.nk2 = 0.5 / p.beta - 1.0; p.nVel = p.gamma / (p.beta * p.dt);
     p.nAcc = 1.0 / (p.beta * p.dt * p.dt); p.nU = (1.0 / p.dt) * (p.gamma / p.beta);
+    p.gdt = p.gamma * p.dt; p.gdtPrev = p.gamma * c->dtStar;
     p.nSeg = c->d_nSeg; p.dZ = c->d_dZ; p.CQ = c->d_CQ; p.CM = c->d_CM; p.ARho = c->d_ARho; p.CI = c->d_CI;
     p.weight = c->d_weight; p.refL = c->d_refL; p.wType = c->d_wType; p.thType = c->d_thType;
     p.W = c->d_W; p.Th = c->d_Th; p.Lam = c->d_Lam; p.U = c->d_U; p.Ac = c->d_Ac; p.Om = c->d_Om; p.dOm = c->d_dOm;
@@ -908,6 +945,7 @@ static int launchIteration(bf_ctx* c)
     beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->grid, c->d_sums, c->comm ? nullptr : c->d_hsums);
     c->launches += 1;
     CUDA_OK(c, cudaGetLastError());
+    if (p.first) c->dtStar = c->deltaT; // the backward sweep of a first iteration re-bases U*, Omega* on this step
     c->iOuterCorr++;
     return BF_OK;
 }
