@@ -342,12 +342,12 @@ enum {
     R_E0 = 3,    // refLambdaf.T() & dR0Ds (3)  (= e_x for an orthonormal refLambdaf)
     R_CQ = 6,    // diag CQ (3)
     R_CM = 9,    // diag CM (3)
-    R_LB = 12,   // l_{i-1} & bPrime_{i-1} (6): the right-hand-side part of the carry
+    R_LB = 12,   // -(l_{i-1} & bPrime_{i-1}) (6): the right-hand-side part of the carry
     R_P = 18,    // a*CQW, symmetric: xx xy xz yy yz zz (6)   face i+1
     R_QT = 24,   // 0.5*CQTheta (9);  a*CMQW = -(0.5*CQTheta).T()
     R_S1 = 33,   // a*CMTheta, symmetric (6)
     R_S3 = 39,   // 0.5*CMQTheta (9)
-    R_MF = 48,   // M of face i+1 (3): 0.5*CMTheta2 = -0.5*spin(M)
+    R_MF = 48,   // 0.5 M of face i+1 (3): 0.5*CMTheta2 = -spin(0.5 M)
     R_SC = 51,   // neighbour part of the source of cell i+1 (6)
     R_BUF = 57,  // prefetch buffer
     B_W = 0,     //   W of cell i+1 (3)
@@ -517,42 +517,56 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
 #pragma unroll
     for (int r = 0; r < 6; r++) src[r] = smLd(sm, R_SC + r);
     if (!LAST) {
-        // ---- coefficients of face i+1 (Evolve.C:673-753) and own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf)
+        // ---- coefficients of face i+1 (Evolve.C:673-753) and own part of d_i (Matrix.C:84-470, w = 0.5, a = 1/deltaf).
+        // The scalings of the reference (a = deltaCoeffs, 0.5/deltaCoeffs, the 0.5 interpolation weights) are folded
+        // into the vectors: with h = 0.5/deltaCoeffs, th = h t, hQ = 0.5 Q, hM = 0.5 M and P = a CQW,
+        //   0.5 CQTheta = P S(th) - S(hQ)            a CMQW = -(0.5 CQTheta).T()        explicitMQ = th x explicitQ
+        //   0.5 CMQTheta = -(Gh.T() S(th) + S(th) S(hQ)),  Gh = P S(th),  S(a) S(b) = b a.T() - (a.b) I
         const V3 Wn = in.Wn;
         const V3 dR0 = smLd3(sm, R_DR0);
         const V3 t = v3(dR0.x + dcI * (Wn.x - Wi.x), dR0.y + dcI * (Wn.y - Wi.y), dR0.z + dcI * (Wn.z - Wi.z)); // dR0Ds + snGrad(W)
         Wi = Wn;
+        const V3 th = h * t;
         const M3 Lm = quatToMat(in.qf);                                               // Lambdaf & refLambdaf :678
-        const M3 SQ = spin(in.Q);
+        const V3 hQ = 0.5 * in.Q;
         V3 eQ;
-        M3 SC; // spinTensor(t) & CQW = -(CQW & spinTensor(t)).T() for the symmetric CQW
+        M3 Gh;
         {
             const V3 CQ = smLd3(sm, R_CQ);
-            const Sym3 CQW = conjDiagSym(Lm, CQ);                                       // :680
-            eQ = mul(Lm, cmul(CQ, gammaOf(Lm, smLd3(sm, R_E0), t)));                  // :682 with Gamma of :881-887
-            const M3 G = mulSpinR(CQW, t);
-            const M3 Qt = 0.5 * (G - SQ);                                             // 0.5*CQTheta :686-693
-            const Sym3 Pm = dcI * CQW;
+            const Sym3 Pm = conjDiagSym(Lm, dcI * CQ);                                // a*CQW :680
+            eQ = mul(Lm, cmul(CQ, mulTSub(Lm, t, smLd3(sm, R_E0))));                  // :682 with Gamma of :881-887
+            Gh = mulSpinR(Pm, th);
+            M3 Qt = Gh;                                                               // 0.5*CQTheta :686-693
+            Qt.a[1] += hQ.z; Qt.a[2] -= hQ.y; Qt.a[3] -= hQ.z; Qt.a[5] += hQ.x; Qt.a[6] += hQ.y; Qt.a[7] -= hQ.x;
             smStS(sm, R_P, Pm);
             smSt9(sm, R_QT, Qt);
             carryBlk(Dc, sm, 0, 0, -1.0, full(Pm));
             carryBlk(Dc, sm, 0, 3, 1.0, Qt);
-            carryBlk(Dc, sm, 3, 0, 1.0, transpose(Qt));                               // -a*CMQW = +(0.5*CQTheta).T() :706-715
-            SC = -1.0 * transpose(G);
+            carryBlk(Dc, sm, 3, 0, 1.0, transpose(Qt));                               // -a*CMQW :706-715
         }
-        const V3 eMQ = h * cross(t, eQ);                                              // :737-741
+        const V3 eMQ = cross(th, eQ);                                                 // :737-741
         {
             const V3 CM = smLd3(sm, R_CM);
-            const Sym3 S1 = dcI * conjDiagSym(Lm, CM);                                  // a*CMTheta :699
+            const Sym3 S1 = conjDiagSym(Lm, dcI * CM);                                // a*CMTheta :699
             const V3 eM = mul(Lm, cmul(CM, in.K));                                    // :684
-            const M3 S3 = (0.5 * h) * (mulSpinR(SC, t) - mulSpinL(t, SQ));            // 0.5*CMQTheta :718-735
-            const V3 Mf = in.M;
-            const M3 S2 = -0.5 * spin(Mf);                                            // 0.5*CMTheta2 :703
+            M3 S3;                                                                    // 0.5*CMQTheta :718-735
+            {
+                const double d = dot(th, hQ);
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const V3 y = cross(th, v3(Gh.a[r], Gh.a[3 + r], Gh.a[6 + r])); // -(column r of Gh) x th
+                    const double q = r == 0 ? hQ.x : r == 1 ? hQ.y : hQ.z;
+                    S3.a[3 * r] = fma(-q, th.x, y.x); S3.a[3 * r + 1] = fma(-q, th.y, y.y); S3.a[3 * r + 2] = fma(-q, th.z, y.z);
+                    S3.a[4 * r] += d;
+                }
+            }
+            const V3 hM = 0.5 * in.M;                                                 // 0.5*CMTheta2 = -S(hM) :703
             smStS(sm, R_S1, S1);
             smSt9(sm, R_S3, S3);
-            smSt3(sm, R_MF, Mf);
-            carryBlk(Dc, sm, 3, 3, -1.0, full(S1));
-            addBlk(Dc, 3, 3, 1.0, S3 + S2);
+            smSt3(sm, R_MF, hM);
+            M3 Eo = S3 - full(S1);                                                    // -a*CMTheta + 0.5*CMQTheta + 0.5*CMTheta2
+            Eo.a[1] += hM.z; Eo.a[2] -= hM.y; Eo.a[3] -= hM.z; Eo.a[5] += hM.x; Eo.a[6] += hM.y; Eo.a[7] -= hM.x;
+            carryBlk(Dc, sm, 3, 3, 1.0, Eo);
             subV(src, 0, eQ);
             subV(src, 3, eM + eMQ);
             smSt3(sm, R_SC, eQ);
@@ -593,18 +607,29 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
             Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
         } else
             Om = OmS + p.gdt * dOm;
+        // QRho = ARho L Accl, MRho = L Lambda (CI dotOmega + Omega x CI Omega) :369-419;  QRhoCoeff, MRhoCoeff :459-535:
+        //   MRhoCoeff/L = S(a) + g1 (S(Lambda CI Omega) - Lambda S(Omega) CI Lambda.T()) - g2 Lambda CI Lambda.T()
+        //               = S(a + g1 Lambda CI Omega) + Lambda (-(g1 S(Omega) + g2 I) CI Lambda.T()),  g1 = gamma/(beta dt), g2 = 1/(beta dt^2)
         const V3 CI = ld3(p.CI, b, p.Bpad);
-        const V3 CIOm = cmul(CI, Om);
-        const V3 a1 = mul(Lm, cmul(CI, dOm));  // Lambda & (CIRho & dotOmega)
-        const V3 a2 = mul(Lm, cross(Om, CIOm)); // Lambda & (Omega ^ (CIRho & Omega))
-        addV(src, 0, (ARho * Lcell) * Ac);
-        addV(src, 3, Lcell * (a1 + a2));
-        const double QRhoCoeff = -(Lcell * ARho) * p.nAcc;
+        const V3 CIOm = cmul(CI, Om), CIdO = cmul(CI, dOm);
+        const V3 w = v3(fma(-Om.z, CIOm.y, fma(Om.y, CIOm.z, CIdO.x)), fma(-Om.x, CIOm.z, fma(Om.z, CIOm.x, CIdO.y)),
+                        fma(-Om.y, CIOm.x, fma(Om.x, CIOm.y, CIdO.z)));
+        const V3 a = mul(Lm, w);
+        const double mL = ARho * Lcell;
+        src[0] = fma(mL, Ac.x, src[0]); src[1] = fma(mL, Ac.y, src[1]); src[2] = fma(mL, Ac.z, src[2]);
+        src[3] = fma(Lcell, a.x, src[3]); src[4] = fma(Lcell, a.y, src[4]); src[5] = fma(Lcell, a.z, src[5]);
+        const double QRhoCoeff = -mL * p.nAcc;
         Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
-        // MRhoCoeff :467-488
-        const M3 T2 = spin(mul(Lm, CIOm)) - mul(Lm, mulSpinL(Om, diagMulT(CI, Lm)));
-        const M3 MR = spin(a2 + a1) + p.nVel * T2 - p.nAcc * conjDiag(Lm, CI);
-        addBlk(Dc, 3, 3, Lcell, MR);
+        const M3 Bt = diagMulT(CI, Lm);             // CI Lambda.T()
+        const M3 SB = mulSpinL(Om, Bt);             // S(Omega) CI Lambda.T()
+        M3 N;
+#pragma unroll
+        for (int k = 0; k < 9; k++) N.a[k] = fma(-p.nVel, SB.a[k], -p.nAcc * Bt.a[k]);
+        const M3 LN = mul(Lm, N);
+        const V3 sv = a + p.nVel * mul(Lm, CIOm);
+        Dc[3][3] = fma(Lcell, LN.a[0], Dc[3][3]); Dc[3][4] = fma(Lcell, LN.a[1] - sv.z, Dc[3][4]); Dc[3][5] = fma(Lcell, LN.a[2] + sv.y, Dc[3][5]);
+        Dc[4][3] = fma(Lcell, LN.a[3] + sv.z, Dc[4][3]); Dc[4][4] = fma(Lcell, LN.a[4], Dc[4][4]); Dc[4][5] = fma(Lcell, LN.a[5] - sv.x, Dc[4][5]);
+        Dc[5][3] = fma(Lcell, LN.a[6] - sv.y, Dc[5][3]); Dc[5][4] = fma(Lcell, LN.a[7] + sv.x, Dc[5][4]); Dc[5][5] = fma(Lcell, LN.a[8], Dc[5][5]);
     }
 #pragma unroll
     for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
@@ -633,33 +658,32 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
             }
         Ai = inv(A);
         AiB = mul(Ai, Bm);
-        Si = inv(E - mul(Cm, AiB));
+        Si = inv(subMulM(E, Cm, AiB));
     }
-    // ---- X = D'^{-1} [u | source - lb], column by column; u comes back from the stash
+    // ---- X = D'^{-1} [u | source - lb], column by column; u comes back from the stash.  R_LB holds -lb.
     double X1[3][7], X2[3][7];
+    const int pi[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}}; // symmetric storage: xx xy xz yy yz zz
 #pragma unroll
     for (int c = 0; c < 7; c++) {
         if (c < 6 && LAST) continue;
         V3 r1, r2;
         if (c < 3) { // u[:, c] = (P[:, c] ; -Qt[c, :])
-            const int pi[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
             r1 = v3(smLd(sm, R_P + pi[c][0]), smLd(sm, R_P + pi[c][1]), smLd(sm, R_P + pi[c][2]));
             r2 = -smLd3(sm, R_QT + 3 * c);
-        } else if (c < 6) { // u[:, c] = (Qt[:, k] ; (S1 + S3 + S2)[:, k]),  S2 = -0.5 spin(M)
+        } else if (c < 6) { // u[:, c] = (Qt[:, k] ; (S1 + S3 + S2)[:, k]),  S2 = -spin(hM)
             const int k = c - 3;
-            const int pi[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-            const V3 Mf = smLd3(sm, R_MF);
-            const V3 s2k = k == 0 ? v3(0.0, -0.5 * Mf.z, 0.5 * Mf.y) : k == 1 ? v3(0.5 * Mf.z, 0.0, -0.5 * Mf.x) : v3(-0.5 * Mf.y, 0.5 * Mf.x, 0.0);
+            const V3 hM = smLd3(sm, R_MF);
+            const V3 s2k = k == 0 ? v3(0.0, -hM.z, hM.y) : k == 1 ? v3(hM.z, 0.0, -hM.x) : v3(-hM.y, hM.x, 0.0);
             r1 = v3(smLd(sm, R_QT + k), smLd(sm, R_QT + 3 + k), smLd(sm, R_QT + 6 + k));
             r2 = v3(smLd(sm, R_S1 + pi[k][0]) + smLd(sm, R_S3 + k) + s2k.x, smLd(sm, R_S1 + pi[k][1]) + smLd(sm, R_S3 + 3 + k) + s2k.y,
                     smLd(sm, R_S1 + pi[k][2]) + smLd(sm, R_S3 + 6 + k) + s2k.z);
         } else { // source_i - l_{i-1} & bPrime_{i-1}
-            r1 = v3(src[0] - smLd(sm, R_LB), src[1] - smLd(sm, R_LB + 1), src[2] - smLd(sm, R_LB + 2));
-            r2 = v3(src[3] - smLd(sm, R_LB + 3), src[4] - smLd(sm, R_LB + 4), src[5] - smLd(sm, R_LB + 5));
+            r1 = v3(src[0] + smLd(sm, R_LB), src[1] + smLd(sm, R_LB + 1), src[2] + smLd(sm, R_LB + 2));
+            r2 = v3(src[3] + smLd(sm, R_LB + 3), src[4] + smLd(sm, R_LB + 4), src[5] + smLd(sm, R_LB + 5));
         }
         const V3 y1 = mul(Ai, r1);
-        const V3 x2 = mul(Si, r2 - mul(Cm, y1));
-        const V3 x1 = y1 - mul(AiB, x2);
+        const V3 x2 = mul(Si, subMul(r2, Cm, y1));
+        const V3 x1 = subMul(y1, AiB, x2);
         X1[0][c] = x1.x; X1[1][c] = x1.y; X1[2][c] = x1.z;
         X2[0][c] = x2.x; X2[1][c] = x2.y; X2[2][c] = x2.z;
     }
@@ -680,40 +704,41 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
         p.bP[b0 + (size_t)(r + 3) * TS] = X2[r][6];
     }
     if (!LAST) {
-        // ---- carry for cell i+1, one row of l at a time
+        // ---- carry for cell i+1, one row of l at a time, each entry one fused chain that starts from d_nei:
+        //      Dc[r][c] = d_nei[r][c] - sum_k l[r][k] X[k][c];   -lb[r] = 0 - sum_k l[r][k] X[k][6]
         {
             const M3 Pm = full(smLdS(sm, R_P)), Qt = smLd9(sm, R_QT);
 #pragma unroll
             for (int r = 0; r < 3; r++) {
 #pragma unroll
                 for (int c = 0; c < 7; c++) {
-                    double acc = Pm.a[3 * r] * X1[0][c];
-                    acc = fma(Pm.a[3 * r + 1], X1[1][c], acc); acc = fma(Pm.a[3 * r + 2], X1[2][c], acc);
+                    double acc = c < 3 ? -Pm.a[3 * r + c] : c < 6 ? -Qt.a[3 * r + c - 3] : 0.0;
 #pragma unroll
-                    for (int k = 0; k < 3; k++) acc = fma(-Qt.a[3 * r + k], X2[k][c], acc);
-                    if (c < 3) smSt(sm, R_DC + 6 * r + c, -Pm.a[3 * r + c] - acc);
-                    else if (c < 6) smSt(sm, R_DC + 6 * r + c, -Qt.a[3 * r + c - 3] - acc);
+                    for (int k = 0; k < 3; k++) acc = fma(-Pm.a[3 * r + k], X1[k][c], acc);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) acc = fma(Qt.a[3 * r + k], X2[k][c], acc);
+                    if (c < 6) smSt(sm, R_DC + 6 * r + c, acc);
                     else smSt(sm, R_LB + r, acc);
                 }
             }
         }
         {
             const M3 Qt = smLd9(sm, R_QT), S1 = full(smLdS(sm, R_S1));
-            const V3 Mf = smLd3(sm, R_MF);
-            M3 Sm = smLd9(sm, R_S3); // S3 - S2 = S3 + 0.5 spin(M)
-            Sm.a[1] -= 0.5 * Mf.z; Sm.a[2] += 0.5 * Mf.y; Sm.a[3] += 0.5 * Mf.z;
-            Sm.a[5] -= 0.5 * Mf.x; Sm.a[6] -= 0.5 * Mf.y; Sm.a[7] += 0.5 * Mf.x;
-            const M3 Sl = S1 + Sm;
+            const V3 hM = smLd3(sm, R_MF);
+            M3 Sm = smLd9(sm, R_S3); // S3 - S2 = S3 + spin(hM)
+            Sm.a[1] -= hM.z; Sm.a[2] += hM.y; Sm.a[3] += hM.z;
+            Sm.a[5] -= hM.x; Sm.a[6] -= hM.y; Sm.a[7] += hM.x;
+            const M3 Sl = S1 + Sm, Sd = Sm - S1;
 #pragma unroll
             for (int r = 0; r < 3; r++) {
 #pragma unroll
                 for (int c = 0; c < 7; c++) {
-                    double acc = Sl.a[3 * r] * X2[0][c];
-                    acc = fma(Sl.a[3 * r + 1], X2[1][c], acc); acc = fma(Sl.a[3 * r + 2], X2[2][c], acc);
+                    double acc = c < 3 ? -Qt.a[3 * c + r] : c < 6 ? Sd.a[3 * r + c - 3] : 0.0;
 #pragma unroll
-                    for (int k = 0; k < 3; k++) acc = fma(Qt.a[3 * k + r], X1[k][c], acc);
-                    if (c < 3) smSt(sm, R_DC + 6 * (3 + r) + c, -Qt.a[3 * c + r] - acc);
-                    else if (c < 6) smSt(sm, R_DC + 6 * (3 + r) + c, (Sm.a[3 * r + c - 3] - S1.a[3 * r + c - 3]) - acc);
+                    for (int k = 0; k < 3; k++) acc = fma(-Sl.a[3 * r + k], X2[k][c], acc);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) acc = fma(-Qt.a[3 * k + r], X1[k][c], acc);
+                    if (c < 6) smSt(sm, R_DC + 6 * (3 + r) + c, acc);
                     else smSt(sm, R_LB + 3 + r, acc);
                 }
             }

@@ -89,6 +89,31 @@ DEV V3 mul(const M3& A, V3 v)
     return v3(A.a[0] * v.x + A.a[1] * v.y + A.a[2] * v.z, A.a[3] * v.x + A.a[4] * v.y + A.a[5] * v.z,
               A.a[6] * v.x + A.a[7] * v.y + A.a[8] * v.z);
 }
+// c - A & v as three fused chains (no separate multiply / subtract)
+DEV V3 subMul(V3 c, const M3& A, V3 v)
+{
+    return v3(fma(-A.a[2], v.z, fma(-A.a[1], v.y, fma(-A.a[0], v.x, c.x))),
+              fma(-A.a[5], v.z, fma(-A.a[4], v.y, fma(-A.a[3], v.x, c.y))),
+              fma(-A.a[8], v.z, fma(-A.a[7], v.y, fma(-A.a[6], v.x, c.z))));
+}
+// A.T() & v - c as three fused chains
+DEV V3 mulTSub(const M3& A, V3 v, V3 c)
+{
+    return v3(fma(A.a[6], v.z, fma(A.a[3], v.y, fma(A.a[0], v.x, -c.x))),
+              fma(A.a[7], v.z, fma(A.a[4], v.y, fma(A.a[1], v.x, -c.y))),
+              fma(A.a[8], v.z, fma(A.a[5], v.y, fma(A.a[2], v.x, -c.z))));
+}
+// E - C & B as nine fused chains
+DEV M3 subMulM(const M3& E, const M3& C, const M3& B)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            r.a[3 * i + j] = fma(-C.a[3 * i + 2], B.a[6 + j], fma(-C.a[3 * i + 1], B.a[3 + j], fma(-C.a[3 * i], B.a[j], E.a[3 * i + j])));
+    return r;
+}
 // A.T() & v
 DEV V3 mulT(const M3& A, V3 v)
 {
