@@ -201,7 +201,18 @@ int64_t bf_num_beams(const bf_ctx* ctx);
  * Vol fields:     internal [nCells*nc], left/right = patch values [nBeams*nc].
  * Surface fields: internal [nInternalFaces*nc], left/right [nBeams*nc].
  * Any pointer may be NULL (that part is skipped).  Setting W or Theta also
- * refreshes their prevIter copy (storePrevIter, CTL.C:1110-1111). */
+ * refreshes their prevIter copy (storePrevIter, CTL.C:1110-1111).
+ *
+ * The host always sees the reference's representation; libbeamgpu keeps some fields
+ * in a compact form and converts at this boundary (libbeamoracle stores them as is):
+ *  - Lambda (internal) and Lambdaf are rotation tensors and are kept as unit
+ *    quaternions (Lambdaf as the product Lambdaf & refLambdaf): what is set must be a
+ *    proper rotation, what is read back equals it to rounding (1e-15), not bit for bit.
+ *  - Gamma is a pure function of W and Lambdaf (Evolve.C:881-887) and is evaluated on
+ *    request; setting it is accepted and ignored.
+ *  - U and Omega are kept as the Newmark step constants U - gamma*deltaT*Accl,
+ *    Omega - gamma*deltaT*dotOmega; setting Accl / dotOmega leaves U / Omega unchanged,
+ *    as in the reference. */
 int bf_set_field(bf_ctx* ctx, int32_t field, const double* internal,
                  const double* left, const double* right);
 int bf_get_field(bf_ctx* ctx, int32_t field, double* internal,
