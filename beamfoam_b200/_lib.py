@@ -80,6 +80,7 @@ EXPORTS = {
     "bf_mirror_begin": (C.c_int, [C.c_void_p, C.c_int32, _ip, C.POINTER(C.c_void_p)]),
     "bf_mirror_wait": (C.c_int, [C.c_void_p]),
     "bf_set_distributed_loads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bf_set_point_forces": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bf_set_bc_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "bf_begin_step": (C.c_int, [C.c_void_p, C.c_double]),
     "bf_newton_iteration": (C.c_int, [C.c_void_p, _dp]),

@@ -77,6 +77,9 @@ class BeamCase:
     g: Sequence[float] = (0.0, 0.0, 0.0)
     q: Optional[Sequence[float]] = None   # uniform (3,) or per-cell (nCells,3)
     m: Optional[Sequence[float]] = None
+    # constant/pointForces (beamModel.C:863-866): ((cellI zeta) force) with cellI the cell label in the bundle,
+    # zeta in [-1, 1] and force a 3-vector or an interpolationTable
+    pointForces: Optional[Sequence[tuple]] = None
     # setInitialPositionBeam -rotateAngle '(axis angle)': 3x3 T (all beams) or (nBeams,3,3); None = I
     initialRotation: Optional[np.ndarray] = None
     # system/controlDict
@@ -342,10 +345,31 @@ class coupledTotalLagNewtonRaphsonBeam:
                     v = np.ascontiguousarray(v)
                     self._check(self.lib.bf_set_bc_values(self._ctx, end, kind, v.ctypes.data))
 
+    def updatePointForces(self, t: float):
+        """pointForces()[pfI].second()(runTime().value()) (Evolve.C:219): evaluate the point-force series at
+        time t for the cells of this shard and hand them to the device."""
+        pfs = self.case.pointForces
+        if not pfs:
+            return
+        lo, hi = self.beamRange
+        allStart = np.concatenate([[0], np.cumsum(self.case.per_beam(self.case.nSegments, np.int64))])
+        c0, c1 = int(allStart[lo]), int(allStart[hi])
+        cells, zetas, forces = [], [], []
+        for cell, zeta, f in pfs:
+            if c0 <= cell < c1:
+                cells.append(cell - c0)
+                zetas.append(float(zeta))
+                forces.append(np.asarray(f.valueAt(t) if hasattr(f, "valueAt") else (f(t) if callable(f) else f), dtype=np.float64))
+        ca = np.ascontiguousarray(cells, dtype=np.int64)
+        za = np.ascontiguousarray(zetas, dtype=np.float64)
+        fa = np.ascontiguousarray(np.reshape(forces, (-1, 3)) if forces else np.zeros((0, 3)), dtype=np.float64)
+        self._check(self.lib.bf_set_point_forces(self._ctx, len(cells), ca.ctypes.data, za.ctypes.data, fa.ctypes.data))
+
     def evolve(self) -> float:
         """``scalar evolve()`` (Evolve.C:55-670).  Returns the initial residual norm; a
         diverged / non-converged step raises (FatalError in the reference)."""
         self.updateCoeffs(self.time)
+        self.updatePointForces(self.time)
         self._check(self.lib.bf_begin_step(self._ctx, float(self.case.deltaT)))
         out = L.bf_step_out()
         rc = self.lib.bf_evolve(self._ctx, C.byref(self.tol), C.byref(out))

@@ -33,12 +33,16 @@
 #define BFK_W_SPRING 3
 #define BFK_TH_FIXED 0
 #define BFK_TH_MOMENT 1
+// d2dt2Schemes (the kernels are instantiated per scheme)
+#define BFK_STEADY 0
+#define BFK_NEWMARK 1
+#define BFK_EULER 2
 
 struct BeamParams {
     int B;        // beams in this context
     int Bpad;     // padded beam count (leading dimension)
     int nmax;     // max cells per beam
-    int newmark;  // 0 steadyState, 1 Newmark
+    int newmark;  // d2dt2Scheme: BFK_STEADY / BFK_NEWMARK / BFK_EULER (the kernels are instantiated per scheme)
     int first;    // 1 on the first Newton iteration of a time step (Newmark predictor)
     int storeInc; // keep DW/DTheta cell fields
     double dt, beta, gamma;
@@ -64,6 +68,12 @@ struct BeamParams {
     // cells [tile][nmax][nc][32]; Lam = unit quaternion (4) of the cell rotation Lambda; U, Om = U*, Omega* (above)
     double *W, *Th, *Lam, *U, *Ac, *Om, *dOm, *DW, *DTh;
     const double *q, *m, *Lc; // optional (may be null)
+    // optional point forces (Evolve.C:211-271), 9 per cell: sum F, sum zeta F over zeta > 0, sum zeta F over zeta < 0
+    const double* pf;
+    double* pfSrc; // [cells][6] their contribution to the source, formed by beam_point_forces before each sweep
+    // Euler d2dt2Scheme only: old-time level of W, U, Omega (3 each) and Lambda (quaternion), written by the first
+    // iteration of a time step.  With Euler, U / Om hold the plain fields (no step constants) and dOm is not used.
+    double *Wold, *Uold, *Omold, *Lamold;
     // faces [tile][nmax+1][nc][32]: face j of beam b; j=0 left patch, j=nSeg[b] right patch
     // Lf = unit quaternion (4) of the product Lambdaf & refLambdaf (the only form the interior of a beam
     // needs, Evolve.C:678,825-830,881-887).  Gamma is not stored: it is a pure function of the stored
@@ -424,11 +434,11 @@ DEV void bulkLoad(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t
 // Prefetch of cell i for the whole warp: one elected lane arms the warp's mbarrier with the byte count and
 // issues one bulk copy per array (every address is warp-uniform).  Face arrays are read at face i+1, W at
 // cell i+1, the Newmark cell arrays at cell i.
-template <bool NEWMARK>
+template <int SCHEME>
 DEV void fwdPrefetch(const BeamParams& p, size_t T, double* warpSm, uint64_t* bar, int lane, int i)
 {
     const int Rc = p.nmax, Rf = p.nmax + 1;
-    if (NEWMARK) { // cell i+... rows read by plain loads late in the assembly: pull them into L2
+    if (SCHEME == BFK_NEWMARK) { // cell i+... rows read by plain loads late in the assembly: pull them into L2
         const size_t n3 = tileRow(T, Rc, i, 3, lane);
         pfL2(p.Lam + tileRow(T, Rc, i, 4, 0) + 4 * lane); // 4 rows x 32 doubles: one double in four per lane
         pfL2(p.Ac + n3); pfL2(p.Ac + n3 + 2 * TS);
@@ -502,11 +512,37 @@ DEV FaceIn loadFaceIn(const double* sm)
     return f;
 }
 
+// Point forces on cell i (Evolve.C:211-271): (sum F0 ; sum S(DR) F0) with DR = zeta * (dRdS of the face on that side
+// of the cell) * (0.5/deltaCoeffs on an internal face, 1/deltaCoeffs_b on an end patch); dRdS from the pre-solve W,
+// patch W after updateCoeffs().  Runs in its own small kernel (beam_point_forces) ahead of the sweeps, so that a case
+// without constant/pointForces carries none of this in the hot loop.
+DEV void pointForceSource(const BeamParams& p, const int b, const int i, double* out6)
+{
+    const size_t T = (size_t)(b >> 5), sb = p.Bpad;
+    const int lane = b & 31, n = p.nSeg[b];
+    const double dZ = p.dZ[b], dcI = 1.0 / dZ, dcB = 2.0 / dZ;
+    const V3 dR0 = v3(p.refL[b], p.refL[3 * sb + b], p.refL[6 * sb + b]);
+    const size_t f9 = tileRow(T, p.nmax, i, 9, lane);
+    const V3 F0 = ld3(p.pf, f9, TS), Zp = ld3(p.pf, f9 + 3 * TS, TS), Zn = ld3(p.pf, f9 + 6 * TS, TS);
+    const V3 Wc = ld3(p.W, tileRow(T, p.nmax, i, 3, lane), TS);
+    auto patchW = [&](int end) {
+        const size_t i3 = (size_t)end * 3 * sb + b;
+        return p.wType[end * sb + b] == BFK_W_FIXED ? ld3(p.wPresc, i3, sb) : ld3(p.Wb, i3, sb);
+    };
+    V3 uP, uN;
+    if (i < n - 1) uP = (0.5 * dZ) * (dR0 + dcI * (ld3(p.W, tileRow(T, p.nmax, i + 1, 3, lane), TS) - Wc));
+    else uP = (1.0 / dcB) * (dR0 + dcB * (patchW(1) - Wc));
+    if (i > 0) uN = (0.5 * dZ) * (dR0 + dcI * (Wc - ld3(p.W, tileRow(T, p.nmax, i - 1, 3, lane), TS)));
+    else uN = (1.0 / dcB) * (dcB * (patchW(0) - Wc) - dR0);
+    const V3 M0 = cross(uP, Zp) + cross(uN, Zn);
+    out6[0] = F0.x; out6[1] = F0.y; out6[2] = F0.z; out6[3] = M0.x; out6[4] = M0.y; out6[5] = M0.z;
+}
+
 // Assembly of cell i (first half of a forward step).  Reads the prefetch buffer (face i+1,
 // W_{i+1}, Newmark state of cell i), adds the own part of d_i and the loads/inertia to the
 // carry Dc, forms source_i, and parks the face tensors in the stash.  LAST = the cell whose right
 // face is the right patch: it closes the patch instead of an internal face.
-template <bool NEWMARK, bool LAST>
+template <int SCHEME, bool LAST>
 DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, const int i, const double dZ,
                      const double dcI, const double h, const double ARho, const FaceIn& in, double (&Dc)[6][6],
                      double (&src)[6], V3& Wi, double& res)
@@ -594,7 +630,12 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
     if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, TS));
     subV(src, 0, Lcell * ld3(p.weight, b, p.Bpad));
     if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, TS));
-    if (NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
+    if (p.pf) {
+        const size_t c6 = tileRow((size_t)(b >> 5), p.nmax, i, 6, b & 31);
+#pragma unroll
+        for (int r = 0; r < 6; r++) src[r] -= p.pfSrc[c6 + (size_t)r * TS];
+    }
+    if (SCHEME == BFK_NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
         const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
         V3 Ac = ld3(p.Ac, c3, TS), dOm = ld3(p.dOm, c3, TS), Om;
         const V3 OmS = ld3(p.Om, c3, TS); // Omega*
@@ -630,6 +671,31 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
         Dc[3][3] = fma(Lcell, LN.a[0], Dc[3][3]); Dc[3][4] = fma(Lcell, LN.a[1] - sv.z, Dc[3][4]); Dc[3][5] = fma(Lcell, LN.a[2] + sv.y, Dc[3][5]);
         Dc[4][3] = fma(Lcell, LN.a[3] + sv.z, Dc[4][3]); Dc[4][4] = fma(Lcell, LN.a[4], Dc[4][4]); Dc[4][5] = fma(Lcell, LN.a[5] - sv.x, Dc[4][5]);
         Dc[5][3] = fma(Lcell, LN.a[6] - sv.y, Dc[5][3]); Dc[5][4] = fma(Lcell, LN.a[7] + sv.x, Dc[5][4]); Dc[5][5] = fma(Lcell, LN.a[8], Dc[5][5]);
+    }
+    if (SCHEME == BFK_EULER) { // Evolve.C:385-400, 490-513 with fvc::ddt(X) = (X - X.oldTime())/deltaT
+        const double idt = 1.0 / dt;
+        const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
+        const V3 U = ld3(p.U, c3, TS), Om = ld3(p.Om, c3, TS);
+        // on the first iteration of a step the old-time level IS the current one (the backward sweep stores it)
+        const V3 Uold = p.first ? U : ld3(p.Uold, c3, TS), Omold = p.first ? Om : ld3(p.Omold, c3, TS);
+        const V3 CI = ld3(p.CI, b, p.Bpad);
+        const V3 CIOm = cmul(CI, Om);
+        const V3 gyro = cross(Om, CIOm);
+        const V3 a = mul(Lm, cmul(CI, idt * (Om - Omold)) + gyro);
+        const double mL = ARho * Lcell;
+        addV(src, 0, (mL * idt) * (U - Uold));
+        addV(src, 3, Lcell * a);
+        const double QRhoCoeff = -mL * idt * idt;
+        Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
+        // MRhoCoeff/L = -Lam CI Lam.T/dt^2 - S(Lam CI Om.old)/dt - S(Lam S(Om) CI Om) + Lam S(Om) CI Lam.T/dt
+        // (the +S(Lam CI Om)/dt and -S(Lam CI Om)/dt of :500,:509 cancel)
+        const M3 Bt = diagMulT(CI, Lm);
+        const M3 SB = mulSpinL(Om, Bt);
+        M3 N;
+#pragma unroll
+        for (int k = 0; k < 9; k++) N.a[k] = idt * SB.a[k] - (idt * idt) * Bt.a[k];
+        const M3 MR = mul(Lm, N) - spin(mul(Lm, idt * cmul(CI, Omold) + gyro));
+        addBlk(Dc, 3, 3, Lcell, MR);
     }
 #pragma unroll
     for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
@@ -748,21 +814,21 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
 
 // The last cell of a beam (right patch instead of an internal face): once per beam, kept out of line so that
 // its patch code and stack arrays stay out of the register allocation of the steady-state loop.
-template <bool NEWMARK>
+template <int SCHEME>
 __device__ __noinline__ double fwdLastCell(const BeamParams& p, const int b, double* __restrict__ sm, const int i,
                                            const double dZ, const double ARho, V3 Wi)
 {
     double Dc[6][6], src[6], res = 0.0;
     FaceIn none;
     none.Wn = none.K = none.Q = none.M = v3(0, 0, 0); none.qf = q4(1, 0, 0, 0);
-    fwdAssemble<NEWMARK, true>(p, b, sm, i, dZ, 1.0 / dZ, 0.5 * dZ, ARho, none, Dc, src, Wi, res);
+    fwdAssemble<SCHEME, true>(p, b, sm, i, dZ, 1.0 / dZ, 0.5 * dZ, ARho, none, Dc, src, Wi, res);
     fwdEliminate<true>(p, b, sm, i, Dc, src);
     return res;
 }
 
 // Forward sweep of the 32 beams of one warp.  sm = the warp's slab + lane; bar = the warp's mbarrier.
 // phase = number of buffer fills this warp's mbarrier has completed so far (its parity selects the wait).
-template <bool NEWMARK>
+template <int SCHEME>
 DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ warpSm, uint64_t* bar, uint32_t& phase)
 {
     const size_t s = p.Bpad;
@@ -774,7 +840,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
     const int n = live ? p.nSeg[b] : 0;
     const int nW = __reduce_max_sync(0xffffffffu, n); // cells of the longest beam of the warp
     __syncwarp(); // (persistent blocks) every lane has left the previous tile's buffer
-    if (nW > 0) fwdPrefetch<NEWMARK>(p, T, warpSm, bar, lane, 0);
+    if (nW > 0) fwdPrefetch<SCHEME>(p, T, warpSm, bar, lane, 0);
 
     const double dZ = p.dZ[b];
     const double dcI = 1.0 / dZ; // mesh().deltaCoeffs() of internal faces
@@ -789,7 +855,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
 #pragma unroll
         for (int r = 0; r < 6; r++) smSt(sm, R_LB + r, 0.0);
     }
-    const double ARho = NEWMARK ? p.ARho[b] : 0.0;
+    const double ARho = SCHEME != BFK_STEADY ? p.ARho[b] : 0.0;
 
     // loop-carried in registers: lb = l_{i-1} & bPrime_{i-1};  Wi = W of cell i.  The carry
     // (nei part of d_i) - l_{i-1} & uPrime_{i-1} and the nei part of source_i travel through the stash.
@@ -814,13 +880,13 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
         phase++;
         const FaceIn in = loadFaceIn(sm);
         __syncwarp(); // every lane holds its buffer rows in registers: refill the buffer for the next cell now
-        if (i + 1 < nW) fwdPrefetch<NEWMARK>(p, T, warpSm, bar, lane, i + 1);
+        if (i + 1 < nW) fwdPrefetch<SCHEME>(p, T, warpSm, bar, lane, i + 1);
         if (i < n - 1) { // a cell with an internal face on its right
             double src[6], Dc[6][6];
-            fwdAssemble<NEWMARK, false>(p, b, sm, i, dZ, dcI, h, ARho, in, Dc, src, Wi, res);
+            fwdAssemble<SCHEME, false>(p, b, sm, i, dZ, dcI, h, ARho, in, Dc, src, Wi, res);
             fwdEliminate<false>(p, b, sm, i, Dc, src);
         } else if (i == n - 1)
-            res += fwdLastCell<NEWMARK>(p, b, sm, i, dZ, ARho, Wi);
+            res += fwdLastCell<SCHEME>(p, b, sm, i, dZ, ARho, Wi);
     }
     return res;
 }
@@ -921,7 +987,7 @@ __device__ __noinline__ FaceState patchUpdate(const BeamParams& p, int end, int 
     return updateFace(f, qOld, LmOld, Kold, DWc, DWb, DTc, DTb, dcB, true);
 }
 
-template <bool NEWMARK>
+template <int SCHEME>
 DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2)
 {
     const size_t s = TS;
@@ -952,7 +1018,7 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 pfRows<6>(p.bP, tileRow(T, Rc, i - 1, 6, lane), s);
                 pfRows<3>(p.W, m3, s); pfRows<3>(p.Th, m3, s);
                 pfRows<4>(p.Lam, tileRow(T, Rc, i - 1, 4, lane), s);
-                if (NEWMARK) {
+                if (SCHEME == BFK_NEWMARK) {
                     pfRows<3>(p.Ac, m3, s); pfRows<3>(p.dOm, m3, s);
                     if (p.first) { pfRows<3>(p.U, m3, s); pfRows<3>(p.Om, m3, s); }
                 }
@@ -987,10 +1053,11 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
             const V3 Wnew = Wold + DW;                          // :769
             st3(p.Th, c3, s, Thn);
             st3(p.W, c3, s, Wnew);
-            stq(p.Lam, c4, s, quatNormalize(quatMul(quatFromRotVec(DT, halfAngle(DT)), qOld))); // :839-841
+            const Q4 qNew = quatNormalize(quatMul(quatFromRotVec(DT, halfAngle(DT)), qOld));
+            stq(p.Lam, c4, s, qNew); // :839-841
             x2 += dot(Wnew, Wnew) + dot(Thn, Thn);
             if (p.storeInc) { st3(p.DW, c3, s, DW); st3(p.DTh, c3, s, DT); }
-            if (NEWMARK) {
+            if (SCHEME == BFK_NEWMARK) {
                 V3 Ac = ld3(p.Ac, c3, s), dOm = ld3(p.dOm, c3, s);
                 if (p.first) { // predictor :167-186, and the step constants U*, Omega* (see BeamParams)
                     const double k1 = p.nk1, k2 = p.nk2;
@@ -1004,6 +1071,24 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 Ac = Ac + p.nAcc * DW;                                // :788 (and :785 through U*)
                 dOm = dOm + p.nAcc * LtDT;                            // :853-862
                 st3(p.Ac, c3, s, Ac); st3(p.dOm, c3, s, dOm);
+            }
+            if (SCHEME == BFK_EULER) { // :791-795, 864-869: U = ddt(W), Accl = ddt(U), Omega = axialVector(Lambda.T() & ddt(Lambda))
+                const double idt = 1.0 / dt;
+                V3 Wo, Uo;
+                Q4 qo;
+                if (p.first) { // the time index has just advanced: this iteration stores the old-time level
+                    Wo = Wold; Uo = ld3(p.U, c3, s); qo = qOld;
+                    st3(p.Wold, c3, s, Wo); st3(p.Uold, c3, s, Uo); stq(p.Lamold, c4, s, qo);
+                    st3(p.Omold, c3, s, ld3(p.Om, c3, s));
+                } else {
+                    Wo = ld3(p.Wold, c3, s); Uo = ld3(p.Uold, c3, s); qo = ldq(p.Lamold, c4, s);
+                }
+                const V3 U = idt * (Wnew - Wo);
+                st3(p.U, c3, s, U);
+                st3(p.Ac, c3, s, idt * (U - Uo));
+                const M3 Ln = quatToMat(qNew), Lo = quatToMat(qo);
+                const M3 Pm = mulTM(Ln, idt * (Ln - Lo)); // Lambda.T() & ddt(Lambda)
+                st3(p.Om, c3, s, v3(Pm.a[7], Pm.a[2], Pm.a[3])); // axialVector: (T.zy, T.xz, T.yx)
             }
             // ---- face j = i+1
             {
@@ -1058,7 +1143,7 @@ DEV uint32_t warpBarrierSetup(unsigned char* smem)
 }
 #define WARP_SLAB(smem, w) ((double*)((smem) + SMEM_HEADER_BYTES) + (size_t)(w) * WARP_SMEM_DOUBLES)
 
-template <bool NEWMARK>
+template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton_pipelined(const BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
@@ -1108,7 +1193,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton_pip
         }
         if (kind == 1) {
             double v[1];
-            v[0] = forwardSweep<NEWMARK>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
+            v[0] = forwardSweep<SCHEME>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
             blockReduceStore<1>(v, p.partial, 0, p.nTiles, tile);
             __threadfence(); // scratch + partial sums of every thread are visible device-wide ...
             __syncthreads();
@@ -1118,7 +1203,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton_pip
             forwardLeft = false;
             __threadfence();
             double v[2] = {0.0, 0.0};
-            if (b < p.B) backwardSweep<NEWMARK>(p, b, v[0], v[1]);
+            if (b < p.B) backwardSweep<SCHEME>(p, b, v[0], v[1]);
             blockReduceStore<2>(v, p.partial, 1, p.nTiles, tile);
         }
         if (p.trace && threadIdx.x == 0) {
@@ -1128,7 +1213,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton_pip
         }
     }
 }
-template <bool NEWMARK>
+template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton(const BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
@@ -1136,27 +1221,42 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton(con
     uint32_t phase = warpBarrierSetup(beam_smem);
     double v[3] = {0.0, 0.0, 0.0};
     // whole warps run the forward sweep (the prefetch is a warp-collective); padding lanes idle inside
-    v[0] = forwardSweep<NEWMARK>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
-    if (b < p.B) backwardSweep<NEWMARK>(p, b, v[1], v[2]);
+    v[0] = forwardSweep<SCHEME>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
+    if (b < p.B) backwardSweep<SCHEME>(p, b, v[1], v[2]);
     blockReduceStore<3>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
-template <bool NEWMARK>
+template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(const BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5;
     uint32_t phase = warpBarrierSetup(beam_smem);
     double v[1] = {0.0};
-    v[0] = forwardSweep<NEWMARK>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
+    v[0] = forwardSweep<SCHEME>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
     blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
-template <bool NEWMARK>
+template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_backward(const BeamParams p)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
-    if (b < p.B) backwardSweep<NEWMARK>(p, b, v[0], v[1]);
+    if (b < p.B) backwardSweep<SCHEME>(p, b, v[0], v[1]);
     blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
+}
+
+// Source contribution of the point forces for every cell of every beam (one thread per beam, its cells in turn).
+__global__ void beam_point_forces(const BeamParams p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int n = p.nSeg[b];
+    for (int i = 0; i < n; i++) {
+        double o[6];
+        pointForceSource(p, b, i, o);
+        const size_t c6 = tileRow((size_t)(b >> 5), p.nmax, i, 6, b & 31);
+#pragma unroll
+        for (int r = 0; r < 6; r++) p.pfSrc[c6 + (size_t)r * TS] = o[r];
+    }
 }
 
 // Deterministic final reduction of the per-block partial sums (fixed order).

@@ -181,6 +181,17 @@ DEV M3 diagMulT(V3 c, const M3& Lm)
 }
 DEV V3 cmul(V3 c, V3 v) { return v3(c.x * v.x, c.y * v.y, c.z * v.z); }
 
+// A.T() & B
+DEV M3 mulTM(const M3& A, const M3& B)
+{
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            r.a[3 * i + j] = A.a[i] * B.a[j] + A.a[3 + i] * B.a[3 + j] + A.a[6 + i] * B.a[6 + j];
+    return r;
+}
 // A & B.T()
 DEV M3 mulBT(const M3& A, const M3& B)
 {

@@ -45,12 +45,15 @@ struct bf_ctx {
     std::vector<int64_t> cellStart, faceStart;
     bool uniformN;
     // device pools
-    void* pools[16];
+    void* pools[20];
     int nPools;
     int32_t *d_nSeg, *d_wType, *d_thType;
     int64_t *d_cellStart, *d_faceStart;
     double *d_dZ, *d_CQ, *d_CM, *d_ARho, *d_CI, *d_weight, *d_refL;
     double *d_W, *d_Th, *d_Lam, *d_U, *d_Ac, *d_Om, *d_dOm, *d_DW, *d_DTh, *d_q, *d_m, *d_Lc;
+    double *d_Wold, *d_Uold, *d_Omold, *d_Lamold; // Euler d2dt2Scheme: old-time level
+    double *d_pf, *d_pfSrc;                       // point forces, 9 per cell, and their source terms, 6 per cell (on first use)
+    bool hasPf;
     double *d_Lf, *d_K, *d_Q, *d_M; // d_Lf, d_Lam: unit quaternions (4 components); Gamma is derived, not stored
     double *d_Wb, *d_Thb, *d_Lamb, *d_DWb, *d_DThb, *d_force, *d_wPresc, *d_thPresc, *d_follower, *d_offset,
         *d_moment, *d_springK, *d_springDir;
@@ -343,8 +346,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     if (!lay || !pr || !bc || !opt || !out || lay->nBeams <= 0 || !lay->nSeg || !lay->length || !pr->CQ || !pr->CM ||
         !bc->wType || !bc->thetaType)
         return fail(nullptr, BF_ERR_INVALID, "bf_create: null/invalid argument");
-    if (opt->scheme != BF_SCHEME_STEADY && opt->scheme != BF_SCHEME_NEWMARK)
-        return fail(nullptr, BF_ERR_UNSUPPORTED, "bf_create: d2dt2 scheme %d not supported (steadyState, Newmark)",
+    if (opt->scheme != BF_SCHEME_STEADY && opt->scheme != BF_SCHEME_NEWMARK && opt->scheme != BF_SCHEME_EULER)
+        return fail(nullptr, BF_ERR_UNSUPPORTED, "bf_create: unknown d2dt2 scheme %d (steadyState, Newmark, Euler)",
                     opt->scheme);
     if (lay->nBeams > (int64_t)1 << 30) return fail(nullptr, BF_ERR_INVALID, "bf_create: too many beams");
     int nDev = 0;
@@ -364,6 +367,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->copyStream = nullptr; c->evStaged = c->evCopied = nullptr; c->copyPending = false; c->fwdMs = c->bwdMs = 0; c->timedIters = 0;
     c->hasQ = c->hasM = false;
     c->d_q = c->d_m = c->d_Lc = c->d_DW = c->d_DTh = nullptr;
+    c->d_Wold = c->d_Uold = c->d_Omold = c->d_Lamold = c->d_pf = c->d_pfSrc = nullptr;
+    c->hasPf = false;
 #define CREATE_FAIL(code, ...) do { int rc_ = fail(nullptr, code, __VA_ARGS__); bf_destroy(c); return rc_; } while (0)
 #define CREATE_CUDA(call)                                                                          \
     do {                                                                                           \
@@ -374,12 +379,13 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     // the sweeps park their face tensors in dynamic shared memory (> 48 KB needs the opt-in)
     CREATE_CUDA(cudaFuncSetAttribute(transposeInternal<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 33 * 8));
     CREATE_CUDA(cudaFuncSetAttribute(transposeInternal<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 33 * 8));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_newton_pipelined<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_newton_pipelined<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_newton<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_newton<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+#define OPT_IN_SMEM(KERNEL)                                                                                               \
+    CREATE_CUDA(cudaFuncSetAttribute(KERNEL<BFK_STEADY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));  \
+    CREATE_CUDA(cudaFuncSetAttribute(KERNEL<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)); \
+    CREATE_CUDA(cudaFuncSetAttribute(KERNEL<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES))
+    OPT_IN_SMEM(beam_newton_pipelined);
+    OPT_IN_SMEM(beam_newton);
+    OPT_IN_SMEM(beam_forward);
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
@@ -413,7 +419,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->deltaT = 1.0;
     c->dtStar = 1.0;
     c->iOuterCorr = 0;
-    const bool newmark = c->scheme == BF_SCHEME_NEWMARK;
+    const bool newmark = c->scheme != BF_SCHEME_STEADY; // U, Accl, Omega, dotOmega exist for both transient schemes
+    const bool euler = c->scheme == BF_SCHEME_EULER;
     const size_t bp = (size_t)Bpad, nc_ = (size_t)nmax, nf_ = (size_t)nmax + 1;
 
     // ---- per-beam + end arrays (one pool)
@@ -436,16 +443,20 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     }
     // ---- cell / face state
     {
-        const size_t cellD = nc_ * bp * (3 + 3 + 4 + (newmark ? 12 : 0) + (c->storeInc ? 6 : 0));
+        const size_t cellD = nc_ * bp * (3 + 3 + 4 + (newmark ? 12 : 0) + (euler ? 13 : 0) + (c->storeInc ? 6 : 0));
         const size_t faceD = nf_ * bp * (4 + 3 + 3 + 3);
         char* cur;
-        if (devAlloc(c, (void**)&cur, sizeof(double) * (cellD + faceD) + 256 * 16)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        if (devAlloc(c, (void**)&cur, sizeof(double) * (cellD + faceD) + 256 * 24)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_W = carve<double>(cur, 3 * nc_ * bp); c->d_Th = carve<double>(cur, 3 * nc_ * bp); c->d_Lam = carve<double>(cur, 4 * nc_ * bp);
         if (newmark) {
             c->d_U = carve<double>(cur, 3 * nc_ * bp); c->d_Ac = carve<double>(cur, 3 * nc_ * bp);
             c->d_Om = carve<double>(cur, 3 * nc_ * bp); c->d_dOm = carve<double>(cur, 3 * nc_ * bp);
         } else {
             c->d_U = c->d_Ac = c->d_Om = c->d_dOm = nullptr;
+        }
+        if (euler) {
+            c->d_Wold = carve<double>(cur, 3 * nc_ * bp); c->d_Uold = carve<double>(cur, 3 * nc_ * bp);
+            c->d_Omold = carve<double>(cur, 3 * nc_ * bp); c->d_Lamold = carve<double>(cur, 4 * nc_ * bp);
         }
         if (c->storeInc) { c->d_DW = carve<double>(cur, 3 * nc_ * bp); c->d_DTh = carve<double>(cur, 3 * nc_ * bp); }
         c->d_Lf = carve<double>(cur, 4 * nf_ * bp); c->d_K = carve<double>(cur, 3 * nf_ * bp);
@@ -463,7 +474,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         // than the 2 tickets (forward + backward) per tile
         int perSm = 0, nSm = 0;
         CREATE_CUDA(cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, c->device));
-        CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, beam_newton_pipelined<true>, THREADS, SMEM_BYTES));
+        CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, beam_newton_pipelined<BFK_NEWMARK>, THREADS, SMEM_BYTES));
         if (perSm < 1) perSm = 1;
         if (perSm > 2) perSm = 2;
         c->pipeGrid = perSm * nSm < 2 * c->grid ? perSm * nSm : 2 * c->grid;
@@ -597,10 +608,11 @@ static int fieldInfo(bf_ctx* c, int field, double** dev, double** endArr, int* n
     case BF_FIELD_LAMBDA: *dev = c->d_Lam; *endArr = c->d_Lamb; *nc = 9; *kind = FK_ROTATION; break;
     case BF_FIELD_DW: *dev = c->d_DW; *endArr = c->d_DWb; break;
     case BF_FIELD_DTHETA: *dev = c->d_DTh; *endArr = c->d_DThb; break;
-    case BF_FIELD_U: *dev = c->d_U; *kind = FK_STAR; break;
-    case BF_FIELD_ACCL: *dev = c->d_Ac; *kind = FK_RATE; break;
-    case BF_FIELD_OMEGA: *dev = c->d_Om; *kind = FK_STAR; break;
-    case BF_FIELD_DOTOMEGA: *dev = c->d_dOm; *kind = FK_RATE; break;
+    // the step-constant representation belongs to the Newmark scheme; Euler keeps the plain fields
+    case BF_FIELD_U: *dev = c->d_U; *kind = c->scheme == BF_SCHEME_NEWMARK ? FK_STAR : FK_PLAIN; break;
+    case BF_FIELD_ACCL: *dev = c->d_Ac; *kind = c->scheme == BF_SCHEME_NEWMARK ? FK_RATE : FK_PLAIN; break;
+    case BF_FIELD_OMEGA: *dev = c->d_Om; *kind = c->scheme == BF_SCHEME_NEWMARK ? FK_STAR : FK_PLAIN; break;
+    case BF_FIELD_DOTOMEGA: *dev = c->d_dOm; *kind = c->scheme == BF_SCHEME_NEWMARK ? FK_RATE : FK_PLAIN; break;
     case BF_FIELD_LAMBDAF: *dev = c->d_Lf; *nc = 9; *surface = 1; *kind = FK_ROTATION; break;
     case BF_FIELD_GAMMA: *dev = c->d_Lf; *surface = 1; *kind = FK_GAMMA; break;
     case BF_FIELD_K: *dev = c->d_K; *surface = 1; break;
@@ -813,6 +825,34 @@ extern "C" int bf_set_distributed_loads(bf_ctx* c, const double* q, const double
     return BF_OK;
 }
 
+// constant/pointForces (Evolve.C:211-271), evaluated by the host at the current time.  The sweeps need, per cell,
+// sum F0 and sum zeta*F0 for each side of the cell (the lever arm is zeta times a per-side vector): 9 doubles.
+extern "C" int bf_set_point_forces(bf_ctx* c, int64_t n, const int64_t* cell, const double* zeta, const double* force)
+{
+    if (n < 0 || (n > 0 && (!cell || !zeta || !force))) return fail(c, BF_ERR_INVALID, "bf_set_point_forces: bad argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    if (n == 0) { c->hasPf = false; return BF_OK; }
+    std::vector<double> h((size_t)c->N * 9, 0.0);
+    for (int64_t k = 0; k < n; k++) {
+        if (cell[k] < 0 || cell[k] >= c->N) return fail(c, BF_ERR_INVALID, "bf_set_point_forces: cell %lld out of range", (long long)cell[k]);
+        double* o = h.data() + 9 * cell[k];
+        for (int j = 0; j < 3; j++) {
+            o[j] += force[3 * k + j];
+            if (zeta[k] > BF_SMALL) o[3 + j] += zeta[k] * force[3 * k + j];
+            else if (zeta[k] < -BF_SMALL) o[6 + j] += zeta[k] * force[3 * k + j];
+        }
+    }
+    if (!c->d_pf) {
+        int rc = devAlloc(c, (void**)&c->d_pf, sizeof(double) * 9 * (size_t)c->nmax * c->Bpad);
+        if (!rc) rc = devAlloc(c, (void**)&c->d_pfSrc, sizeof(double) * 6 * (size_t)c->nmax * c->Bpad);
+        if (rc) return rc;
+    }
+    int rc = xferInternal(c, c->d_pf, h.data(), 9, 0, FK_PLAIN, true);
+    if (rc) return rc;
+    c->hasPf = true;
+    return BF_OK;
+}
+
 extern "C" int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const double* v)
 {
     if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !v) return fail(c, BF_ERR_INVALID, "bf_set_bc_values: bad argument");
@@ -892,7 +932,7 @@ static BeamParams makeParams(bf_ctx* c)
     BeamParams p;
     memset(&p, 0, sizeof p);
     p.B = (int)c->B; p.Bpad = c->Bpad; p.nmax = c->nmax;
-    p.newmark = c->scheme == BF_SCHEME_NEWMARK; p.first = c->iOuterCorr == 0; p.storeInc = c->storeInc;
+    p.newmark = c->scheme; p.first = c->iOuterCorr == 0; p.storeInc = c->storeInc;
     p.dt = c->deltaT; p.beta = c->betaN; p.gamma = c->gammaN;
     p.nk1 = 1.0 / (p.dt * p.beta); p.nk2 = 0.5 / p.beta - 1.0; p.nVel = p.gamma / (p.beta * p.dt);
     p.nAcc = 1.0 / (p.beta * p.dt * p.dt); p.nU = (1.0 / p.dt) * (p.gamma / p.beta);
@@ -902,6 +942,8 @@ static BeamParams makeParams(bf_ctx* c)
     p.W = c->d_W; p.Th = c->d_Th; p.Lam = c->d_Lam; p.U = c->d_U; p.Ac = c->d_Ac; p.Om = c->d_Om; p.dOm = c->d_dOm;
     p.DW = c->d_DW; p.DTh = c->d_DTh;
     p.q = c->hasQ ? c->d_q : nullptr; p.m = c->hasM ? c->d_m : nullptr; p.Lc = c->d_Lc;
+    p.pf = c->hasPf ? c->d_pf : nullptr; p.pfSrc = c->d_pfSrc;
+    p.Wold = c->d_Wold; p.Uold = c->d_Uold; p.Omold = c->d_Omold; p.Lamold = c->d_Lamold;
     p.Lf = c->d_Lf; p.K = c->d_K; p.Q = c->d_Q; p.M = c->d_M;
     p.Wb = c->d_Wb; p.Thb = c->d_Thb; p.Lamb = c->d_Lamb; p.DWb = c->d_DWb; p.DThb = c->d_DThb; p.force = c->d_force;
     p.wPresc = c->d_wPresc; p.thPresc = c->d_thPresc; p.follower = c->d_follower; p.offset = c->d_offset;
@@ -911,17 +953,25 @@ static BeamParams makeParams(bf_ctx* c)
     return p;
 }
 
+#define LAUNCH_SCHEME(KERNEL, GRID, SMEM, P)                                                          \
+    do {                                                                                              \
+        if (c->scheme == BF_SCHEME_NEWMARK) KERNEL<BFK_NEWMARK><<<(GRID), THREADS, (SMEM), c->stream>>>(P); \
+        else if (c->scheme == BF_SCHEME_EULER) KERNEL<BFK_EULER><<<(GRID), THREADS, (SMEM), c->stream>>>(P); \
+        else KERNEL<BFK_STEADY><<<(GRID), THREADS, (SMEM), c->stream>>>(P);                           \
+    } while (0)
 // Launches one Newton iteration; the three LOCAL sums of squares end up in d_sums.
 static int launchIteration(bf_ctx* c)
 {
     const BeamParams p = makeParams(c);
+    if (p.pf) { // lever arms follow the current W: re-evaluated every iteration (Evolve.C:221)
+        beam_point_forces<<<(unsigned)((c->B + 127) / 128), 128, 0, c->stream>>>(p);
+        c->launches++;
+    }
     if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[0], c->stream));
     if (c->splitKernels) { // profiling aid: the same two sweeps as two launches
-        if (p.newmark) beam_forward<true><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);
-        else beam_forward<false><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);
+        LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
-        if (p.newmark) beam_backward<true><<<c->grid, THREADS, 0, c->stream>>>(p);
-        else beam_backward<false><<<c->grid, THREADS, 0, c->stream>>>(p);
+        LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
         c->launches += 2;
     } else if (c->pipelined) { // product path: persistent blocks, forward and backward sweeps of different tiles overlap
         if (++c->epoch == 0x7fffffff) { // flags compare equal to the epoch: start over before it wraps
@@ -931,13 +981,11 @@ static int launchIteration(bf_ctx* c)
         BeamParams q = p;
         q.epoch = c->epoch;
         CUDA_OK(c, cudaMemsetAsync(c->d_ctl, 0, sizeof(int) * CTL_INTS, c->stream));
-        if (q.newmark) beam_newton_pipelined<true><<<c->pipeGrid, THREADS, SMEM_BYTES, c->stream>>>(q);
-        else beam_newton_pipelined<false><<<c->pipeGrid, THREADS, SMEM_BYTES, c->stream>>>(q);
+        LAUNCH_SCHEME(beam_newton_pipelined, c->pipeGrid, SMEM_BYTES, q);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
         c->launches += 1;
     } else {
-        if (p.newmark) beam_newton<true><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);
-        else beam_newton<false><<<c->grid, THREADS, SMEM_BYTES, c->stream>>>(p);
+        LAUNCH_SCHEME(beam_newton, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
         c->launches += 1;
     }

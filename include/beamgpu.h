@@ -232,6 +232,13 @@ int bf_mirror_wait(bf_ctx* ctx);
  * [nCells*3] each; NULL => zero. */
 int bf_set_distributed_loads(bf_ctx* ctx, const double* q, const double* m);
 
+/* constant/pointForces (beamModel.C:863-866; Evolve.C:211-271): n point forces, each on cell
+ * cell[k] (index into the cells of this context) at relative coordinate zeta[k] in [-1, 1]
+ * with force[3k..] = the value of its time series at the current time.  Replaces the list
+ * set by a previous call; n = 0 removes all point forces. */
+int bf_set_point_forces(bf_ctx* ctx, int64_t n, const int64_t* cell, const double* zeta,
+                        const double* force);
+
 /* Per-step boundary values == what W_/Theta_.boundaryFieldRef().updateCoeffs()
  * (Evolve.C:156-157) evaluates from the BC time series at the new time.
  * values: [nBeams*3] for patch `end`; entries of beams whose BC class does not

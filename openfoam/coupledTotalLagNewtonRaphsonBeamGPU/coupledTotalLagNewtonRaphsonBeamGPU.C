@@ -280,6 +280,23 @@ scalar coupledTotalLagNewtonRaphsonBeamGPU::evolve()
     tol.divergenceTol = d.lookupOrDefault<scalar>("divergenceTol", 1e6);
 
     pushBoundaryValues();
+    if (pointForces().size())   // constant/pointForces, Evolve.C:211-219: the series at the new time
+    {
+        List<int64_t> cells(pointForces().size());
+        scalarField zeta(pointForces().size());
+        vectorField F0(pointForces().size());
+        forAll(pointForces(), pfI)
+        {
+            cells[pfI] = pointForces()[pfI].first().first();
+            zeta[pfI] = pointForces()[pfI].first().second();
+            F0[pfI] = pointForces()[pfI].second()(runTime().value());
+        }
+        check
+        (
+            bf_set_point_forces(ctx_, cells.size(), cells.cdata(), zeta.cdata(), reinterpret_cast<const double*>(F0.cdata())),
+            "bf_set_point_forces"
+        );
+    }
     check(bf_begin_step(ctx_, runTime().deltaTValue()), "bf_begin_step");
 
     bf_step_out out;

@@ -130,7 +130,13 @@ struct bf_ctx {
     double *W, *Wb, *WbPrev, *Theta, *Thetab, *ThetabPrev;
     double *Lambda, *Lambdab, *DW, *DWb, *DTheta, *DThetab;
     double *U, *Accl, *Omega, *dotOmega;
+    /* oldTime() fields read by the Euler d2dt2Scheme (CTL.C:767-779; stored when the time index is advanced) */
+    double *Wold, *Uold, *Omegaold, *Lambdaold;
     double *q, *m;
+    /* constant/pointForces (Evolve.C:211-271): cell, zeta, force at the current time */
+    int64_t nPointForces;
+    int64_t* pfCell;
+    double *pfZeta, *pfForce;
     /* boundary-condition objects */
     int32_t *wType, *thType;
     double *springK, *springDir;
@@ -197,7 +203,7 @@ int bf_destroy(bf_ctx* c)
                     c->Thetab, c->ThetabPrev, c->Lambda, c->Lambdab, c->DW, c->DWb, c->DTheta, c->DThetab, c->U,
                     c->Accl, c->Omega, c->dotOmega, c->q, c->m, c->wType, c->thType, c->springK, c->springDir,
                     c->wPresc, c->thPresc, c->force, c->followerForce, c->offsetForce, c->moment, c->d, c->l, c->u,
-                    c->source, c->solVec};
+                    c->source, c->solVec, c->Wold, c->Uold, c->Omegaold, c->Lambdaold, c->pfCell, c->pfZeta, c->pfForce};
     for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) free(ptrs[i]);
     free(c);
     return BF_OK;
@@ -212,8 +218,8 @@ int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf_bc* bc, co
         snprintf(g_create_err, sizeof g_create_err, "bf_create: null/invalid argument");
         return BF_ERR_INVALID;
     }
-    if (opt->scheme != BF_SCHEME_STEADY && opt->scheme != BF_SCHEME_NEWMARK) {
-        snprintf(g_create_err, sizeof g_create_err, "bf_create: d2dt2 scheme %d not supported (steadyState, Newmark)",
+    if (opt->scheme != BF_SCHEME_STEADY && opt->scheme != BF_SCHEME_NEWMARK && opt->scheme != BF_SCHEME_EULER) {
+        snprintf(g_create_err, sizeof g_create_err, "bf_create: unknown d2dt2 scheme %d (steadyState, Newmark, Euler)",
                  opt->scheme);
         return BF_ERR_UNSUPPORTED;
     }
@@ -274,6 +280,7 @@ int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf_bc* bc, co
     ALLOC(c->DW, 3 * N); ALLOC(c->DWb, 6 * B); ALLOC(c->DTheta, 3 * N); ALLOC(c->DThetab, 6 * B);
     ALLOC(c->U, 3 * N); ALLOC(c->Accl, 3 * N); ALLOC(c->Omega, 3 * N); ALLOC(c->dotOmega, 3 * N);
     ALLOC(c->q, 3 * N); ALLOC(c->m, 3 * N);
+    ALLOC(c->Wold, 3 * N); ALLOC(c->Uold, 3 * N); ALLOC(c->Omegaold, 3 * N); ALLOC(c->Lambdaold, 9 * N);
     ALLOC(c->wType, 2 * B); ALLOC(c->thType, 2 * B); ALLOC(c->springK, 2 * B); ALLOC(c->springDir, 6 * B);
     ALLOC(c->wPresc, 6 * B); ALLOC(c->thPresc, 6 * B); ALLOC(c->force, 6 * B); ALLOC(c->followerForce, 6 * B);
     ALLOC(c->offsetForce, 6 * B); ALLOC(c->moment, 6 * B);
@@ -451,6 +458,29 @@ int bf_begin_step(bf_ctx* c, double deltaT)
     if (!(deltaT > 0)) { snprintf(c->err, sizeof c->err, "bf_begin_step: deltaT must be > 0"); return BF_ERR_INVALID; }
     c->deltaT = deltaT;
     c->iOuterCorr = 0;
+    /* runTime++ stores the old-time level of every field that has one (CTL.C:767-779) */
+    memcpy(c->Wold, c->W, sizeof(double) * 3 * c->N);
+    memcpy(c->Uold, c->U, sizeof(double) * 3 * c->N);
+    memcpy(c->Omegaold, c->Omega, sizeof(double) * 3 * c->N);
+    memcpy(c->Lambdaold, c->Lambda, sizeof(double) * 9 * c->N);
+    return BF_OK;
+}
+
+/* constant/pointForces evaluated by the host at the current time (Evolve.C:211-219) */
+int bf_set_point_forces(bf_ctx* c, int64_t n, const int64_t* cell, const double* zeta, const double* force)
+{
+    if (n < 0 || (n > 0 && (!cell || !zeta || !force))) { snprintf(c->err, sizeof c->err, "bf_set_point_forces: bad argument"); return BF_ERR_INVALID; }
+    for (int64_t k = 0; k < n; k++)
+        if (cell[k] < 0 || cell[k] >= c->N) { snprintf(c->err, sizeof c->err, "bf_set_point_forces: cell %lld out of range", (long long)cell[k]); return BF_ERR_INVALID; }
+    free(c->pfCell); free(c->pfZeta); free(c->pfForce);
+    c->pfCell = NULL; c->pfZeta = c->pfForce = NULL;
+    c->nPointForces = n;
+    if (n == 0) return BF_OK;
+    c->pfCell = malloc(sizeof(int64_t) * n); c->pfZeta = malloc(sizeof(double) * n); c->pfForce = malloc(sizeof(double) * 3 * n);
+    if (!c->pfCell || !c->pfZeta || !c->pfForce) return BF_ERR_NOMEM;
+    memcpy(c->pfCell, cell, sizeof(int64_t) * n);
+    memcpy(c->pfZeta, zeta, sizeof(double) * n);
+    memcpy(c->pfForce, force, sizeof(double) * 3 * n);
     return BF_OK;
 }
 
@@ -720,10 +750,43 @@ static void assembleBoundaryConditions(bf_ctx* c)
 }
 
 /* Loads and inertia: Evolve.C:192-209, 274-279, 320-536 (steadyState, Newmark). */
+/* Evolve.C:211-271: point force F0 at relative coordinate zeta of a cell; the lever arm uses dRdS of the face on
+ * that side of the cell (internal face: 0.5*zeta*dRdS*deltaf; end cell: zeta*dRdS_b/dc_b). */
+static void addPointForces(bf_ctx* c)
+{
+    double* src = c->source;
+    for (int64_t k = 0; k < c->nPointForces; k++) {
+        const int64_t cell = c->pfCell[k];
+        const double zeta = c->pfZeta[k];
+        const double* F0 = c->pfForce + 3 * k;
+        for (int j = 0; j < 3; j++) src[6 * cell + j] -= F0[j];
+        double DR[3] = {0, 0, 0}, g[3];
+        const int64_t b = c->cellBeam[cell];
+        const int64_t il = cell - c->cellStart[b]; /* index inside the beam */
+        int64_t f = -1;
+        double scale = 0;
+        if (zeta > SMALL) {
+            if (il == c->nSeg[b] - 1) { f = c->F + c->B + b; scale = zeta / c->dc[f]; }        /* last cell: end patch */
+            else { f = c->faceStart[b] + il; scale = 0.5 * zeta / c->dc[f]; }                  /* own.find(cellI) */
+        } else if (zeta < -SMALL) {
+            if (il == 0) { f = c->F + b; scale = zeta / c->dc[f]; }                            /* first cell: start patch */
+            else { f = c->faceStart[b] + il - 1; scale = 0.5 * zeta / c->dc[f]; }              /* nei.find(cellI) */
+        }
+        if (f >= 0) {
+            snGrad(c, c->W, c->Wb, f, g);
+            for (int j = 0; j < 3; j++) DR[j] = scale * (c->dR0Ds[3 * f + j] + g[j]);
+        }
+        double M0[3];
+        cross(DR, F0, M0);
+        for (int j = 0; j < 3; j++) src[6 * cell + 3 + j] -= M0[j];
+    }
+}
+
 static void addLoadsAndInertia(bf_ctx* c)
 {
     double *d = c->d, *src = c->source;
     const double dt = c->deltaT, beta = c->betaN, gamma = c->gammaN;
+    addPointForces(c);
     for (int64_t i = 0; i < c->N; i++) {
         const int64_t b = c->cellBeam[i];
         const double L = c->L[i];
@@ -731,6 +794,36 @@ static void addLoadsAndInertia(bf_ctx* c)
             src[6 * i + k] -= c->q[3 * i + k] * L;           /* :193-198 */
             src[6 * i + k] -= c->weight[3 * b + k] * L;      /* :201-209 rho*L*A*g */
             src[6 * i + 3 + k] -= c->m[3 * i + k] * L;       /* :274-279 */
+        }
+        if (c->scheme == BF_SCHEME_EULER) { /* fvc::ddt with the Euler ddtScheme: (X - X.oldTime())/deltaT */
+            const double ARho = c->ARho[b];
+            double CI[9], Lam[9], LamT[9], tv[3], tv2[3], a1[3], a2[3], ddtOm[3];
+            t_diag(c->CIRho + 3 * b, CI);
+            t_copy(c->Lambda + 9 * i, Lam);
+            t_T(Lam, LamT);
+            const double *Om = c->Omega + 3 * i, *OmOld = c->Omegaold + 3 * i;
+            for (int k = 0; k < 3; k++) ddtOm[k] = (Om[k] - OmOld[k]) / dt;
+            /* QRho = ARho*L*ddt(U) :388 ; MRho = L*(Lam&(CI&ddt(Om)) + Lam&(Om^(CI&Om))) :391-398 */
+            t_mul_v(CI, ddtOm, tv); t_mul_v(Lam, tv, a1);
+            t_mul_v(CI, Om, tv); cross(Om, tv, tv2); t_mul_v(Lam, tv2, a2);
+            for (int k = 0; k < 3; k++) {
+                src[6 * i + k] += ARho * L * ((c->U[3 * i + k] - c->Uold[3 * i + k]) / dt);
+                src[6 * i + 3 + k] += L * (a1[k] + a2[k]);
+            }
+            const double QRhoCoeff = -L * ARho / (dt * dt); /* :493-494 */
+            for (int k = 0; k < 3; k++) BLK(d, i, k, k) += QRhoCoeff;
+            /* MRhoCoeff :498-512, term by term in the order written there */
+            double T[9], A[9], M[9], CILT[9], v[3], w[3];
+            t_zero(M);
+            t_mul_v(CI, Om, v); t_mul_v(Lam, v, w); spin(w, T); t_axpy(1.0 / dt, T, M);          /* + S(Lam CI Om)/dt */
+            t_mul_t(CI, LamT, CILT); t_mul_t(Lam, CILT, A); t_axpy(-1.0 / (dt * dt), A, M);      /* - Lam CI Lam.T/dt^2 */
+            t_mul_v(CI, OmOld, v); t_mul_v(Lam, v, w); spin(w, T); t_axpy(-1.0 / dt, T, M);      /* - S(Lam CI Om.old)/dt */
+            double SOm[9];
+            spin(Om, SOm);
+            t_mul_v(CI, Om, v); t_mul_v(SOm, v, w); t_mul_v(Lam, w, v); spin(v, T); t_axpy(-1.0, T, M); /* - S(Lam S(Om) CI Om) */
+            t_mul_v(CI, Om, v); t_mul_v(Lam, v, w); spin(w, T); t_axpy(-1.0 / dt, T, M);         /* - S(Lam CI Om)/dt */
+            t_mul_t(SOm, CILT, A); t_mul_t(Lam, A, T); t_axpy(1.0 / dt, T, M);                   /* + Lam S(Om) CI Lam.T/dt */
+            add_block(d, i, 3, 3, L, M);
         }
         if (c->scheme == BF_SCHEME_NEWMARK) {
             const double ARho = c->ARho[b];
@@ -924,6 +1017,11 @@ static void updateSolutionVariables(bf_ctx* c)
             c->U[i] += (1 / dt) * (gamma / beta) * c->DW[i];
             c->Accl[i] += (1 / (dt * dt * beta)) * c->DW[i];
         }
+    } else if (c->scheme == BF_SCHEME_EULER) { /* :791-795  U = ddt(W), Accl = ddt(U) */
+        for (int64_t i = 0; i < 3 * N; i++) {
+            c->U[i] = (c->W[i] - c->Wold[i]) / dt;
+            c->Accl[i] = (c->U[i] - c->Uold[i]) / dt;
+        }
     }
     /* faces :804-836 */
     for (int64_t f = 0; f < NF; f++) {
@@ -968,6 +1066,15 @@ static void updateSolutionVariables(bf_ctx* c)
                 c->Omega[3 * i + k] += (gamma / (beta * dt)) * tv[k];
                 c->dotOmega[3 * i + k] += (1 / (beta * dt * dt)) * tv[k];
             }
+        }
+    }
+    if (c->scheme == BF_SCHEME_EULER) { /* :864-869  Omega = axialVector(Lambda.T() & ddt(Lambda)); dotOmega untouched */
+        for (int64_t i = 0; i < N; i++) {
+            double ddtL[9], P[9];
+            for (int k = 0; k < 9; k++) ddtL[k] = (c->Lambda[9 * i + k] - c->Lambdaold[9 * i + k]) / dt;
+            t_T(c->Lambda + 9 * i, LT);
+            t_mul_t(LT, ddtL, P);
+            c->Omega[3 * i] = P[7]; c->Omega[3 * i + 1] = P[2]; c->Omega[3 * i + 2] = P[3]; /* (T.zy, T.xz, T.yx) */
         }
     }
     for (int64_t f = 0; f < NF; f++) {

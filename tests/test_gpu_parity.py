@@ -149,3 +149,42 @@ def test_bundle_4096_subset_matches_oracle(gpu_lib, oracle_lib):
     assert rel(gt[1000:1064], ot) <= TIP_RTOL
     g.close()
     o.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY 8a row a4, the two parts no tutorial exercises: constant/pointForces and the Euler d2dt2Scheme
+# ---------------------------------------------------------------------------------------------
+def test_point_forces_steady_and_newmark(gpu_lib, oracle_lib):
+    from beamfoam_b200.fvPatchFields import interpolationTable
+    # ragged 5-beam bundle, point forces on first / last / interior cells, both sides of a cell, a time series
+    base = cases.multiBeamDensity(5, 12)
+    nseg = np.array([12, 7, 9, 12, 5])
+    start = np.concatenate([[0], np.cumsum(nseg)])
+    ser = interpolationTable([(0, (0, 0, 0)), (0.01, (50.0, -20.0, 10.0)), (1, (50.0, -20.0, 10.0))])
+    pfs = [(int(start[0]), -1.0, (30.0, 0, 5.0)), (int(start[0]) + 5, 0.3, ser), (int(start[0]) + 5, -0.7, (0, 12.0, 0)),
+           (int(start[1]) + 6, 1.0, (0, -40.0, 0)), (int(start[2]) + 4, 0.0, (10.0, 10.0, 10.0)),
+           (int(start[4]), 0.5, ser), (int(start[4]) + 4, -0.25, (0, 0, -25.0))]
+    for scheme in ("Newmark", "steadyState"):
+        case = dataclasses.replace(base, nSegments=nseg, pointForces=pfs, d2dt2Scheme=scheme)
+        if scheme == "steadyState":  # the tutorial's 2000 N tip force needs load steps when there is no inertia
+            case = dataclasses.replace(case, W_right=type(case.W_right)(forceSeries=interpolationTable(
+                [(0, (0, 0, 0)), (0.02, (200.0, 200.0, 0)), (1, (200.0, 200.0, 0))])))
+        run_pair(case, gpu_lib, oracle_lib, nSteps=20, tip_rtol=1e-10)
+
+
+def test_euler_scheme(gpu_lib, oracle_lib):
+    case = dataclasses.replace(cases.multiBeamDensity(7, 16, jitter=True), d2dt2Scheme="Euler")
+    worst = run_pair(case, gpu_lib, oracle_lib, nSteps=60, tip_rtol=1e-9)
+    assert worst <= 1e-9
+    # a change of time step between steps (old-time levels are per step, not per dt)
+    g = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
+    o = coupledTotalLagNewtonRaphsonBeam(case, library=oracle_lib)
+    for m in (g, o):
+        m.run(nSteps=3)
+        m.case = dataclasses.replace(m.case, deltaT=2.5e-3)
+        m.run(nSteps=3)
+    for a, b in zip(g.tip(1), o.tip(1)):
+        assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))
+    for f in ("U", "Accl", "Omega"):
+        a, b = g.get_field(f)[0], o.get_field(f)[0]
+        assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-3), f
