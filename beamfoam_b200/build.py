@@ -14,7 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = [os.path.join(HERE, "csrc", "beamgpu.cu")]
-HEADERS = [os.path.join(HERE, "csrc", "beam_kernels.cuh"), os.path.join(HERE, "csrc", "beam_math.cuh"),
+HEADERS = [os.path.join(HERE, "csrc", "beam_kernels.cuh"), os.path.join(HERE, "csrc", "beam_long.cuh"),
+           os.path.join(HERE, "csrc", "beam_math.cuh"),
            os.path.join(ROOT, "include", "beamgpu.h")]
 OUTPUT = os.path.join(HERE, "libbeamgpu.so")
 

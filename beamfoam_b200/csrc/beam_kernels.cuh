@@ -538,6 +538,88 @@ DEV void pointForceSource(const BeamParams& p, const int b, const int i, double*
     out6[0] = F0.x; out6[1] = F0.y; out6[2] = F0.z; out6[3] = M0.x; out6[4] = M0.y; out6[5] = M0.z;
 }
 
+// Loads (Evolve.C:193-279) and inertia (Evolve.C:320-536, with the Newmark predictor :167-186 on the first iteration
+// of a time step) of cell i, added to its diagonal block and source.
+template <int SCHEME>
+DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const double dZ, const double ARho,
+                            double (&Dc)[6][6], double (&src)[6])
+{
+    const double dt = p.dt, gamma = p.gamma;
+    // ---- loads: Evolve.C:193-209,274-279
+    const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31);
+    const double Lcell = p.Lc ? p.Lc[tileRow((size_t)(b >> 5), p.nmax, i, 1, b & 31)] : dZ;
+    if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, TS));
+    subV(src, 0, Lcell * ld3(p.weight, b, p.Bpad));
+    if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, TS));
+    if (p.pf) {
+        const size_t c6 = tileRow((size_t)(b >> 5), p.nmax, i, 6, b & 31);
+#pragma unroll
+        for (int r = 0; r < 6; r++) src[r] -= p.pfSrc[c6 + (size_t)r * TS];
+    }
+    if (SCHEME == BFK_NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
+        const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
+        V3 Ac = ld3(p.Ac, c3, TS), dOm = ld3(p.dOm, c3, TS), Om;
+        const V3 OmS = ld3(p.Om, c3, TS); // Omega*
+        if (p.first) {
+            const V3 Ao = Ac, dOo = dOm;
+            const V3 Uo = ld3(p.U, c3, TS) + p.gdtPrev * Ao, Oo = OmS + p.gdtPrev * dOo; // end of the previous step
+            const double k1 = p.nk1, k2 = p.nk2;
+            Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
+            dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
+            Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
+        } else
+            Om = OmS + p.gdt * dOm;
+        // QRho = ARho L Accl, MRho = L Lambda (CI dotOmega + Omega x CI Omega) :369-419;  QRhoCoeff, MRhoCoeff :459-535:
+        //   MRhoCoeff/L = S(a) + g1 (S(Lambda CI Omega) - Lambda S(Omega) CI Lambda.T()) - g2 Lambda CI Lambda.T()
+        //               = S(a + g1 Lambda CI Omega) + Lambda (-(g1 S(Omega) + g2 I) CI Lambda.T()),  g1 = gamma/(beta dt), g2 = 1/(beta dt^2)
+        const V3 CI = ld3(p.CI, b, p.Bpad);
+        const V3 CIOm = cmul(CI, Om), CIdO = cmul(CI, dOm);
+        const V3 w = v3(fma(-Om.z, CIOm.y, fma(Om.y, CIOm.z, CIdO.x)), fma(-Om.x, CIOm.z, fma(Om.z, CIOm.x, CIdO.y)),
+                        fma(-Om.y, CIOm.x, fma(Om.x, CIOm.y, CIdO.z)));
+        const V3 a = mul(Lm, w);
+        const double mL = ARho * Lcell;
+        src[0] = fma(mL, Ac.x, src[0]); src[1] = fma(mL, Ac.y, src[1]); src[2] = fma(mL, Ac.z, src[2]);
+        src[3] = fma(Lcell, a.x, src[3]); src[4] = fma(Lcell, a.y, src[4]); src[5] = fma(Lcell, a.z, src[5]);
+        const double QRhoCoeff = -mL * p.nAcc;
+        Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
+        const M3 Bt = diagMulT(CI, Lm);             // CI Lambda.T()
+        const M3 SB = mulSpinL(Om, Bt);             // S(Omega) CI Lambda.T()
+        M3 N;
+#pragma unroll
+        for (int k = 0; k < 9; k++) N.a[k] = fma(-p.nVel, SB.a[k], -p.nAcc * Bt.a[k]);
+        const M3 LN = mul(Lm, N);
+        const V3 sv = a + p.nVel * mul(Lm, CIOm);
+        Dc[3][3] = fma(Lcell, LN.a[0], Dc[3][3]); Dc[3][4] = fma(Lcell, LN.a[1] - sv.z, Dc[3][4]); Dc[3][5] = fma(Lcell, LN.a[2] + sv.y, Dc[3][5]);
+        Dc[4][3] = fma(Lcell, LN.a[3] + sv.z, Dc[4][3]); Dc[4][4] = fma(Lcell, LN.a[4], Dc[4][4]); Dc[4][5] = fma(Lcell, LN.a[5] - sv.x, Dc[4][5]);
+        Dc[5][3] = fma(Lcell, LN.a[6] - sv.y, Dc[5][3]); Dc[5][4] = fma(Lcell, LN.a[7] + sv.x, Dc[5][4]); Dc[5][5] = fma(Lcell, LN.a[8], Dc[5][5]);
+    }
+    if (SCHEME == BFK_EULER) { // Evolve.C:385-400, 490-513 with fvc::ddt(X) = (X - X.oldTime())/deltaT
+        const double idt = 1.0 / dt;
+        const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
+        const V3 U = ld3(p.U, c3, TS), Om = ld3(p.Om, c3, TS);
+        // on the first iteration of a step the old-time level IS the current one (the backward sweep stores it)
+        const V3 Uold = p.first ? U : ld3(p.Uold, c3, TS), Omold = p.first ? Om : ld3(p.Omold, c3, TS);
+        const V3 CI = ld3(p.CI, b, p.Bpad);
+        const V3 CIOm = cmul(CI, Om);
+        const V3 gyro = cross(Om, CIOm);
+        const V3 a = mul(Lm, cmul(CI, idt * (Om - Omold)) + gyro);
+        const double mL = ARho * Lcell;
+        addV(src, 0, (mL * idt) * (U - Uold));
+        addV(src, 3, Lcell * a);
+        const double QRhoCoeff = -mL * idt * idt;
+        Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
+        // MRhoCoeff/L = -Lam CI Lam.T/dt^2 - S(Lam CI Om.old)/dt - S(Lam S(Om) CI Om) + Lam S(Om) CI Lam.T/dt
+        // (the +S(Lam CI Om)/dt and -S(Lam CI Om)/dt of :500,:509 cancel)
+        const M3 Bt = diagMulT(CI, Lm);
+        const M3 SB = mulSpinL(Om, Bt);
+        M3 N;
+#pragma unroll
+        for (int k = 0; k < 9; k++) N.a[k] = idt * SB.a[k] - (idt * idt) * Bt.a[k];
+        const M3 MR = mul(Lm, N) - spin(mul(Lm, idt * cmul(CI, Omold) + gyro));
+        addBlk(Dc, 3, 3, Lcell, MR);
+    }
+}
+
 // Assembly of cell i (first half of a forward step).  Reads the prefetch buffer (face i+1,
 // W_{i+1}, Newmark state of cell i), adds the own part of d_i and the loads/inertia to the
 // carry Dc, forms source_i, and parks the face tensors in the stash.  LAST = the cell whose right
@@ -549,7 +631,6 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
 {
     // Dc is an OUTPUT: each 3x3 block of the carry is fetched from the stash (R_DC) where its first
     // contribution is added
-    const double dt = p.dt, gamma = p.gamma;
 #pragma unroll
     for (int r = 0; r < 6; r++) src[r] = smLd(sm, R_SC + r);
     if (!LAST) {
@@ -624,79 +705,7 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
             for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
         }
     }
-    // ---- loads: Evolve.C:193-209,274-279
-    const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31);
-    const double Lcell = p.Lc ? p.Lc[tileRow((size_t)(b >> 5), p.nmax, i, 1, b & 31)] : dZ;
-    if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, TS));
-    subV(src, 0, Lcell * ld3(p.weight, b, p.Bpad));
-    if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, TS));
-    if (p.pf) {
-        const size_t c6 = tileRow((size_t)(b >> 5), p.nmax, i, 6, b & 31);
-#pragma unroll
-        for (int r = 0; r < 6; r++) src[r] -= p.pfSrc[c6 + (size_t)r * TS];
-    }
-    if (SCHEME == BFK_NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
-        const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
-        V3 Ac = ld3(p.Ac, c3, TS), dOm = ld3(p.dOm, c3, TS), Om;
-        const V3 OmS = ld3(p.Om, c3, TS); // Omega*
-        if (p.first) {
-            const V3 Ao = Ac, dOo = dOm;
-            const V3 Uo = ld3(p.U, c3, TS) + p.gdtPrev * Ao, Oo = OmS + p.gdtPrev * dOo; // end of the previous step
-            const double k1 = p.nk1, k2 = p.nk2;
-            Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
-            dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
-            Om = Oo + dt * ((1.0 - gamma) * dOo + gamma * dOm);
-        } else
-            Om = OmS + p.gdt * dOm;
-        // QRho = ARho L Accl, MRho = L Lambda (CI dotOmega + Omega x CI Omega) :369-419;  QRhoCoeff, MRhoCoeff :459-535:
-        //   MRhoCoeff/L = S(a) + g1 (S(Lambda CI Omega) - Lambda S(Omega) CI Lambda.T()) - g2 Lambda CI Lambda.T()
-        //               = S(a + g1 Lambda CI Omega) + Lambda (-(g1 S(Omega) + g2 I) CI Lambda.T()),  g1 = gamma/(beta dt), g2 = 1/(beta dt^2)
-        const V3 CI = ld3(p.CI, b, p.Bpad);
-        const V3 CIOm = cmul(CI, Om), CIdO = cmul(CI, dOm);
-        const V3 w = v3(fma(-Om.z, CIOm.y, fma(Om.y, CIOm.z, CIdO.x)), fma(-Om.x, CIOm.z, fma(Om.z, CIOm.x, CIdO.y)),
-                        fma(-Om.y, CIOm.x, fma(Om.x, CIOm.y, CIdO.z)));
-        const V3 a = mul(Lm, w);
-        const double mL = ARho * Lcell;
-        src[0] = fma(mL, Ac.x, src[0]); src[1] = fma(mL, Ac.y, src[1]); src[2] = fma(mL, Ac.z, src[2]);
-        src[3] = fma(Lcell, a.x, src[3]); src[4] = fma(Lcell, a.y, src[4]); src[5] = fma(Lcell, a.z, src[5]);
-        const double QRhoCoeff = -mL * p.nAcc;
-        Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
-        const M3 Bt = diagMulT(CI, Lm);             // CI Lambda.T()
-        const M3 SB = mulSpinL(Om, Bt);             // S(Omega) CI Lambda.T()
-        M3 N;
-#pragma unroll
-        for (int k = 0; k < 9; k++) N.a[k] = fma(-p.nVel, SB.a[k], -p.nAcc * Bt.a[k]);
-        const M3 LN = mul(Lm, N);
-        const V3 sv = a + p.nVel * mul(Lm, CIOm);
-        Dc[3][3] = fma(Lcell, LN.a[0], Dc[3][3]); Dc[3][4] = fma(Lcell, LN.a[1] - sv.z, Dc[3][4]); Dc[3][5] = fma(Lcell, LN.a[2] + sv.y, Dc[3][5]);
-        Dc[4][3] = fma(Lcell, LN.a[3] + sv.z, Dc[4][3]); Dc[4][4] = fma(Lcell, LN.a[4], Dc[4][4]); Dc[4][5] = fma(Lcell, LN.a[5] - sv.x, Dc[4][5]);
-        Dc[5][3] = fma(Lcell, LN.a[6] - sv.y, Dc[5][3]); Dc[5][4] = fma(Lcell, LN.a[7] + sv.x, Dc[5][4]); Dc[5][5] = fma(Lcell, LN.a[8], Dc[5][5]);
-    }
-    if (SCHEME == BFK_EULER) { // Evolve.C:385-400, 490-513 with fvc::ddt(X) = (X - X.oldTime())/deltaT
-        const double idt = 1.0 / dt;
-        const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
-        const V3 U = ld3(p.U, c3, TS), Om = ld3(p.Om, c3, TS);
-        // on the first iteration of a step the old-time level IS the current one (the backward sweep stores it)
-        const V3 Uold = p.first ? U : ld3(p.Uold, c3, TS), Omold = p.first ? Om : ld3(p.Omold, c3, TS);
-        const V3 CI = ld3(p.CI, b, p.Bpad);
-        const V3 CIOm = cmul(CI, Om);
-        const V3 gyro = cross(Om, CIOm);
-        const V3 a = mul(Lm, cmul(CI, idt * (Om - Omold)) + gyro);
-        const double mL = ARho * Lcell;
-        addV(src, 0, (mL * idt) * (U - Uold));
-        addV(src, 3, Lcell * a);
-        const double QRhoCoeff = -mL * idt * idt;
-        Dc[0][0] += QRhoCoeff; Dc[1][1] += QRhoCoeff; Dc[2][2] += QRhoCoeff;
-        // MRhoCoeff/L = -Lam CI Lam.T/dt^2 - S(Lam CI Om.old)/dt - S(Lam S(Om) CI Om) + Lam S(Om) CI Lam.T/dt
-        // (the +S(Lam CI Om)/dt and -S(Lam CI Om)/dt of :500,:509 cancel)
-        const M3 Bt = diagMulT(CI, Lm);
-        const M3 SB = mulSpinL(Om, Bt);
-        M3 N;
-#pragma unroll
-        for (int k = 0; k < 9; k++) N.a[k] = idt * SB.a[k] - (idt * idt) * Bt.a[k];
-        const M3 MR = mul(Lm, N) - spin(mul(Lm, idt * cmul(CI, Omold) + gyro));
-        addBlk(Dc, 3, 3, Lcell, MR);
-    }
+    addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, Dc, src);
 #pragma unroll
     for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
 }
@@ -987,6 +996,105 @@ __device__ __noinline__ FaceState patchUpdate(const BeamParams& p, int end, int 
     return updateFace(f, qOld, LmOld, Kold, DWc, DWb, DTc, DTb, dcB, true);
 }
 
+// updateSolutionVariables for ONE cell (Evolve.C:759-802, 839-869): Theta, W, Lambda and the time-scheme fields.
+// DW, DT = the solved increments of the cell; returns the pre-update W (the faces need it) and adds |W|^2 + |Theta|^2.
+template <int SCHEME>
+DEV void updateCell(const BeamParams& p, const size_t T, const int lane, const int i, const V3 DW, const V3 DT, V3& WoldOut,
+                    double& x2)
+{
+    const size_t s = TS;
+    const int Rc = p.nmax;
+    const double dt = p.dt, gamma = p.gamma;
+    // ---- cell i: Evolve.C:759-802, 839-863
+    const size_t c3 = tileRow(T, Rc, i, 3, lane), c4 = tileRow(T, Rc, i, 4, lane);
+    const V3 Wold = ld3(p.W, c3, s);
+    WoldOut = Wold;
+    const Q4 qOld = ldq(p.Lam, c4, s);
+    // Lambda.T() & DTheta.  R(DTheta) leaves its own axis unchanged, so this vector is the same for
+    // the Lambda before the update (:759) and after it (:853-862): (R Lambda).T() & DT = Lambda.T() & DT
+    const V3 LtDT = mulT(quatToMat(qOld), DT);
+    const V3 Thn = ld3(p.Th, c3, s) + LtDT;             // :759
+    const V3 Wnew = Wold + DW;                          // :769
+    st3(p.Th, c3, s, Thn);
+    st3(p.W, c3, s, Wnew);
+    const Q4 qNew = quatNormalize(quatMul(quatFromRotVec(DT, halfAngle(DT)), qOld));
+    stq(p.Lam, c4, s, qNew); // :839-841
+    x2 += dot(Wnew, Wnew) + dot(Thn, Thn);
+    if (p.storeInc) { st3(p.DW, c3, s, DW); st3(p.DTh, c3, s, DT); }
+    if (SCHEME == BFK_NEWMARK) {
+        V3 Ac = ld3(p.Ac, c3, s), dOm = ld3(p.dOm, c3, s);
+        if (p.first) { // predictor :167-186, and the step constants U*, Omega* (see BeamParams)
+            const double k1 = p.nk1, k2 = p.nk2;
+            const V3 Ao = Ac, dOo = dOm;
+            const V3 Uo = ld3(p.U, c3, s) + p.gdtPrev * Ao, Oo = ld3(p.Om, c3, s) + p.gdtPrev * dOo;
+            Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
+            dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
+            st3(p.U, c3, s, Uo + (dt * (1.0 - gamma)) * Ao);   // U = U* + gamma dt Accl from here on
+            st3(p.Om, c3, s, Oo + (dt * (1.0 - gamma)) * dOo);
+        }
+        Ac = Ac + p.nAcc * DW;                                // :788 (and :785 through U*)
+        dOm = dOm + p.nAcc * LtDT;                            // :853-862
+        st3(p.Ac, c3, s, Ac); st3(p.dOm, c3, s, dOm);
+    }
+    if (SCHEME == BFK_EULER) { // :791-795, 864-869: U = ddt(W), Accl = ddt(U), Omega = axialVector(Lambda.T() & ddt(Lambda))
+        const double idt = 1.0 / dt;
+        V3 Wo, Uo;
+        Q4 qo;
+        if (p.first) { // the time index has just advanced: this iteration stores the old-time level
+            Wo = Wold; Uo = ld3(p.U, c3, s); qo = qOld;
+            st3(p.Wold, c3, s, Wo); st3(p.Uold, c3, s, Uo); stq(p.Lamold, c4, s, qo);
+            st3(p.Omold, c3, s, ld3(p.Om, c3, s));
+        } else {
+            Wo = ld3(p.Wold, c3, s); Uo = ld3(p.Uold, c3, s); qo = ldq(p.Lamold, c4, s);
+        }
+        const V3 U = idt * (Wnew - Wo);
+        st3(p.U, c3, s, U);
+        st3(p.Ac, c3, s, idt * (U - Uo));
+        const M3 Ln = quatToMat(qNew), Lo = quatToMat(qo);
+        const M3 Pm = mulTM(Ln, idt * (Ln - Lo)); // Lambda.T() & ddt(Lambda)
+        st3(p.Om, c3, s, v3(Pm.a[7], Pm.a[2], Pm.a[3])); // axialVector: (T.zy, T.xz, T.yx)
+    }
+}
+
+// The faces a cell owns in the update: face i+1 (internal, or the right patch for the last cell) and, for cell 0, the
+// left patch (Evolve.C:804-836, 881-913 and the evaluate() of the patch fields, Theta before W).  (A) = this cell,
+// (N) = cell i+1: WoldN its pre-update W, xWn / xTn its increments.
+DEV void updateFacesOfCell(const BeamParams& p, const int b, const int i, const int n, const V3 CQ, const V3 CM, const V3 dR0,
+                           const V3 e0, const double dcI, const double dcB, const double delta, const V3 Wold, const V3 WoldN,
+                           const V3 DW, const V3 DT, const V3 xWn, const V3 xTn)
+{
+    const size_t s = TS;
+    const size_t T = (size_t)(b >> 5);
+    const int lane = b & 31, Rf = p.nmax + 1;
+    // ---- face j = i+1
+    {
+        const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f4 = tileRow(T, Rf, i + 1, 4, lane);
+        const Q4 qfOld = ldq(p.Lf, f4, s);
+        const V3 Kold = ld3(p.K, f3, s);
+        FaceState o;
+        if (i == n - 1) { // right patch
+            o = patchUpdate(p, 1, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s), Wold, DW, DT, dcB, delta);
+        } else {
+            const M3 LmOld = quatToMat(qfOld);
+            const V3 t = dR0 + dcI * (WoldN - Wold);
+            const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, t), Kold,
+                                                ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcI, false);
+            o = updateFace(f, qfOld, LmOld, Kold, DW, xWn, DT, xTn, dcI, false);
+        }
+        stq(p.Lf, f4, s, o.Lf);
+        st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
+    }
+    if (i == 0) { // left patch: face 0
+        const size_t f3 = tileRow(T, Rf, 0, 3, lane), f4 = tileRow(T, Rf, 0, 4, lane);
+        const Q4 qfOld = ldq(p.Lf, f4, s);
+        const V3 Kold = ld3(p.K, f3, s);
+        const FaceState o = patchUpdate(p, 0, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s),
+                                        Wold, DW, DT, dcB, delta);
+        stq(p.Lf, f4, s, o.Lf);
+        st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
+    }
+}
+
 template <int SCHEME>
 DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2)
 {
@@ -1042,81 +1150,9 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
             const V3 DW = v3(x[0], x[1], x[2]), DT = v3(x[3], x[4], x[5]);
 #pragma unroll
             for (int r = 0; r < 6; r++) dx2 += x[r] * x[r];
-            // ---- cell i: Evolve.C:759-802, 839-863
-            const size_t c3 = tileRow(T, Rc, i, 3, lane), c4 = tileRow(T, Rc, i, 4, lane);
-            const V3 Wold = ld3(p.W, c3, s);
-            const Q4 qOld = ldq(p.Lam, c4, s);
-            // Lambda.T() & DTheta.  R(DTheta) leaves its own axis unchanged, so this vector is the same for
-            // the Lambda before the update (:759) and after it (:853-862): (R Lambda).T() & DT = Lambda.T() & DT
-            const V3 LtDT = mulT(quatToMat(qOld), DT);
-            const V3 Thn = ld3(p.Th, c3, s) + LtDT;             // :759
-            const V3 Wnew = Wold + DW;                          // :769
-            st3(p.Th, c3, s, Thn);
-            st3(p.W, c3, s, Wnew);
-            const Q4 qNew = quatNormalize(quatMul(quatFromRotVec(DT, halfAngle(DT)), qOld));
-            stq(p.Lam, c4, s, qNew); // :839-841
-            x2 += dot(Wnew, Wnew) + dot(Thn, Thn);
-            if (p.storeInc) { st3(p.DW, c3, s, DW); st3(p.DTh, c3, s, DT); }
-            if (SCHEME == BFK_NEWMARK) {
-                V3 Ac = ld3(p.Ac, c3, s), dOm = ld3(p.dOm, c3, s);
-                if (p.first) { // predictor :167-186, and the step constants U*, Omega* (see BeamParams)
-                    const double k1 = p.nk1, k2 = p.nk2;
-                    const V3 Ao = Ac, dOo = dOm;
-                    const V3 Uo = ld3(p.U, c3, s) + p.gdtPrev * Ao, Oo = ld3(p.Om, c3, s) + p.gdtPrev * dOo;
-                    Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
-                    dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
-                    st3(p.U, c3, s, Uo + (dt * (1.0 - gamma)) * Ao);   // U = U* + gamma dt Accl from here on
-                    st3(p.Om, c3, s, Oo + (dt * (1.0 - gamma)) * dOo);
-                }
-                Ac = Ac + p.nAcc * DW;                                // :788 (and :785 through U*)
-                dOm = dOm + p.nAcc * LtDT;                            // :853-862
-                st3(p.Ac, c3, s, Ac); st3(p.dOm, c3, s, dOm);
-            }
-            if (SCHEME == BFK_EULER) { // :791-795, 864-869: U = ddt(W), Accl = ddt(U), Omega = axialVector(Lambda.T() & ddt(Lambda))
-                const double idt = 1.0 / dt;
-                V3 Wo, Uo;
-                Q4 qo;
-                if (p.first) { // the time index has just advanced: this iteration stores the old-time level
-                    Wo = Wold; Uo = ld3(p.U, c3, s); qo = qOld;
-                    st3(p.Wold, c3, s, Wo); st3(p.Uold, c3, s, Uo); stq(p.Lamold, c4, s, qo);
-                    st3(p.Omold, c3, s, ld3(p.Om, c3, s));
-                } else {
-                    Wo = ld3(p.Wold, c3, s); Uo = ld3(p.Uold, c3, s); qo = ldq(p.Lamold, c4, s);
-                }
-                const V3 U = idt * (Wnew - Wo);
-                st3(p.U, c3, s, U);
-                st3(p.Ac, c3, s, idt * (U - Uo));
-                const M3 Ln = quatToMat(qNew), Lo = quatToMat(qo);
-                const M3 Pm = mulTM(Ln, idt * (Ln - Lo)); // Lambda.T() & ddt(Lambda)
-                st3(p.Om, c3, s, v3(Pm.a[7], Pm.a[2], Pm.a[3])); // axialVector: (T.zy, T.xz, T.yx)
-            }
-            // ---- face j = i+1
-            {
-                const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f4 = tileRow(T, Rf, i + 1, 4, lane);
-                const Q4 qfOld = ldq(p.Lf, f4, s);
-                const V3 Kold = ld3(p.K, f3, s);
-                FaceState o;
-                if (i == n - 1) { // right patch
-                    o = patchUpdate(p, 1, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s), Wold, DW, DT, dcB, delta);
-                } else {
-                    const M3 LmOld = quatToMat(qfOld);
-                    const V3 t = dR0 + dcI * (WoldN - Wold);
-                    const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, t), Kold,
-                                                        ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcI, false);
-                    o = updateFace(f, qfOld, LmOld, Kold, DW, xWn, DT, xTn, dcI, false);
-                }
-                stq(p.Lf, f4, s, o.Lf);
-                st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
-            }
-            if (i == 0) { // left patch: face 0
-                const size_t f3 = tileRow(T, Rf, 0, 3, lane), f4 = tileRow(T, Rf, 0, 4, lane);
-                const Q4 qfOld = ldq(p.Lf, f4, s);
-                const V3 Kold = ld3(p.K, f3, s);
-                const FaceState o = patchUpdate(p, 0, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s),
-                                                Wold, DW, DT, dcB, delta);
-                stq(p.Lf, f4, s, o.Lf);
-                st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
-            }
+            V3 Wold;
+            updateCell<SCHEME>(p, T, lane, i, DW, DT, Wold, x2);
+            updateFacesOfCell(p, b, i, n, CQ, CM, dR0, e0, dcI, dcB, delta, Wold, WoldN, DW, DT, xWn, xTn);
             xWn = DW; xTn = DT; WoldN = Wold;
         }
     }

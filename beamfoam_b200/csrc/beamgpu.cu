@@ -7,6 +7,7 @@
 // host, exactly where the reference evaluates it.  There is no CPU compute path here.
 #include "../../include/beamgpu.h"
 #include "beam_kernels.cuh"
+#include "beam_long.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -61,6 +62,11 @@ struct bf_ctx {
     int *d_ctl, *d_fDone; // pipelined launch: tickets / per-SM role counters, per-tile forward-done flags
     int epoch, pipeGrid, pipelined;
     unsigned long long* d_trace; // BEAMGPU_TRACE=1: per-tile sweep time stamps of the last pipelined launch
+    // few long beams: one thread per cell, assembled block rows, block parallel cyclic reduction (beam_long.cuh)
+    int longMode, longBlocks;
+    int32_t* d_cellBeam;
+    double* d_longRows[8]; // L, D, U, R x 2 copies
+    double* d_longX;
     double* d_stage; // staging buffer in host (AoS) ordering
     double* d_stagePatch; // separate small staging for patch values (never shared with a pending mirror)
     double* d_stageQ;     // host-ordered quaternions (4 per cell/face) between the transposition and the tensor conversion
@@ -465,9 +471,9 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     // ---- block-Thomas scratch + partial sums
     {
         char* cur;
-        if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->grid + 8) + sizeof(int) * (CTL_INTS + (size_t)c->grid) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->grid + 3 * (size_t)((c->N + 127) / 128) + 8) + sizeof(int) * (CTL_INTS + (size_t)c->grid) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
-        c->d_partial = carve<double>(cur, 3 * (size_t)c->grid); c->d_sums = carve<double>(cur, 8);
+        c->d_partial = carve<double>(cur, 3 * (size_t)c->grid + 3 * (size_t)((c->N + 127) / 128)); c->d_sums = carve<double>(cur, 8);
         c->d_ctl = carve<int>(cur, CTL_INTS); c->d_fDone = carve<int>(cur, (size_t)c->grid);
         c->epoch = 0;
         // persistent pipelined launch: as many blocks as are co-resident (2 per SM with these kernels), never more
@@ -483,6 +489,13 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         // forward tile is done) and the tail cost more than that (4.99 ms vs 4.35 ms).
         c->pipelined = getenv("BEAMGPU_PIPELINE") ? 1 : 0;
         c->d_trace = nullptr;
+        // BEAMGPU_LONG_BEAMS = 1 / 0 forces the cell-parallel path on / off; by default it serves bundles that cannot
+        // occupy the GPU with one thread per beam but have enough cells per beam to do so with one thread per cell
+        const char* lm = getenv("BEAMGPU_LONG_BEAMS");
+        c->longMode = lm ? atoi(lm) != 0 : (nmax >= 512 && B <= 128);
+        c->longBlocks = (int)((c->N + 127) / 128);
+        c->d_cellBeam = nullptr; c->d_longX = nullptr;
+        for (int k = 0; k < 8; k++) c->d_longRows[k] = nullptr;
         if (getenv("BEAMGPU_TRACE") && devAlloc(c, (void**)&c->d_trace, sizeof(unsigned long long) * 4 * (size_t)c->grid)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
     }
     // ---- staging buffer (largest field in host ordering: a tensor vol field)
@@ -561,6 +574,18 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         fillIdentity<<<(unsigned)((2 * Bpad + 255) / 256), 256, 0, c->stream>>>(c->d_Lamb, 2, Bpad, 9);
         c->launches += 3;
         CREATE_CUDA(cudaGetLastError());
+    }
+    if (c->longMode) {
+        char* cur;
+        const size_t N = (size_t)c->N;
+        if (devAlloc(c, (void**)&cur, sizeof(double) * N * (2 * (36 * 3 + 6) + 6) + sizeof(int32_t) * N + 256 * 12)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        for (int k = 0; k < 8; k++) c->d_longRows[k] = carve<double>(cur, (k % 4 == 3 ? 6 : 36) * N);
+        c->d_longX = carve<double>(cur, 6 * N + 6); // one row of slack: the last cell reads "x of the next cell" unguarded
+        c->d_cellBeam = carve<int32_t>(cur, N);
+        std::vector<int32_t> cb(N);
+        for (int64_t b = 0; b < B; b++) for (int64_t g = c->cellStart[b]; g < c->cellStart[b + 1]; g++) cb[g] = (int32_t)b;
+        CREATE_CUDA(cudaMemcpyAsync(c->d_cellBeam, cb.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
+        CREATE_CUDA(cudaStreamSynchronize(c->stream));
     }
     if (lay->cellLength) { // L() per cell (HermiteSpline::segLengths), otherwise dZ
         char* cur;
@@ -968,7 +993,30 @@ static int launchIteration(bf_ctx* c)
         c->launches++;
     }
     if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[0], c->stream));
-    if (c->splitKernels) { // profiling aid: the same two sweeps as two launches
+    if (c->longMode) { // one thread per cell: assemble, block cyclic reduction, update
+        LongParams q;
+        q.N = c->N; q.cellBeam = c->d_cellBeam; q.cellStart = c->d_cellStart; q.X = c->d_longX;
+        for (int k = 0; k < 2; k++) { q.L[k] = c->d_longRows[4 * k]; q.D[k] = c->d_longRows[4 * k + 1]; q.U[k] = c->d_longRows[4 * k + 2]; q.R[k] = c->d_longRows[4 * k + 3]; }
+        q.src = 0; q.step = 0;
+        const int gb = c->longBlocks;
+        if (c->scheme == BF_SCHEME_NEWMARK) long_assemble<BFK_NEWMARK><<<gb, 128, 0, c->stream>>>(p, q);
+        else if (c->scheme == BF_SCHEME_EULER) long_assemble<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
+        else long_assemble<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
+        c->launches++;
+        for (int s = 1; s < c->nmax; s *= 2) {
+            q.step = s;
+            long_pcr_step<<<gb, 128, 0, c->stream>>>(p, q);
+            q.src = 1 - q.src;
+            c->launches++;
+        }
+        long_pcr_finish<<<gb, 128, 0, c->stream>>>(q);
+        if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
+        long_update_faces<<<gb, 128, 0, c->stream>>>(p, q);
+        if (c->scheme == BF_SCHEME_NEWMARK) long_update_cells<BFK_NEWMARK><<<gb, 128, 0, c->stream>>>(p, q);
+        else if (c->scheme == BF_SCHEME_EULER) long_update_cells<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
+        else long_update_cells<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
+        c->launches += 3;
+    } else if (c->splitKernels) { // profiling aid: the same two sweeps as two launches
         LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
         LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
@@ -990,7 +1038,8 @@ static int launchIteration(bf_ctx* c)
         c->launches += 1;
     }
     if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[2], c->stream));
-    beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->grid, c->d_sums, c->comm ? nullptr : c->d_hsums);
+    beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->longMode ? c->longBlocks : c->grid, c->d_sums,
+                                                   c->comm ? nullptr : c->d_hsums);
     c->launches += 1;
     CUDA_OK(c, cudaGetLastError());
     if (p.first) c->dtStar = c->deltaT; // the backward sweep of a first iteration re-bases U*, Omega* on this step
