@@ -5,9 +5,13 @@
 //   long_assemble      a1-a4 per cell: coefficients of its two faces, the blocks d_i, l_i (coupling to x_{i-1}),
 //                      u_i (coupling to x_{i+1}) and source_i, exactly the block system the reference hands to
 //                      BlockEigenSolverOF (EigenOF.C:60-175), in memory (this path is for small N);
+//   long_pcr_load      copies the rows into the reduction buffers (second pass: with the residual b - A x as right-hand side)
 //   long_pcr_step      a5 by block PARALLEL CYCLIC REDUCTION: in step s every row eliminates its couplings to rows
 //                      i-s and i+s, ceil(log2 n) steps; 6x6 solves with partial pivoting inside the block;
-//   long_pcr_finish    x_i = d_i^{-1} source_i;
+//   long_pcr_finish    x_i (+)= d_i^{-1} source_i.  Cyclic reduction does not pivot ACROSS blocks and on a 10^4-cell
+//                      beam (EA/EI ~ 10^3 per cell, cond ~ n^4) its solution carries ~1e-8 of noise, enough to cost the
+//                      Newton loop an extra iteration against the reference's pivoted LU; one step of iterative
+//                      refinement (a second reduction on the residual) brings it to the accuracy of a stable solve;
 //   long_update_faces  a6/a7 for the faces a cell owns (needs the neighbour's OLD W, so it runs before ...)
 //   long_update_cells  ... a6 for the cells, and the norms a8.
 // State, layout and every per-cell / per-face formula are shared with the fused path (the same device functions).
@@ -18,8 +22,11 @@ struct LongParams {
     int64_t N;                 // cells of this context
     const int32_t* cellBeam;   // [N] beam of a cell (host / createBeamMesh ordering)
     const int64_t* cellStart;  // [B+1]
-    // block rows, [N][36] / [N][6], two copies (cyclic reduction ping-pongs between them)
+    // block rows, [N][36] / [N][6]: the assembled system (kept for the residual) ...
+    double *L0, *D0, *U0, *R0;
+    // ... and two working copies (cyclic reduction ping-pongs between them)
     double *L[2], *D[2], *U[2], *R[2];
+    int refine;                // 0: first solve, 1: refinement pass (right-hand side = residual, x accumulates)
     double* X;                 // [N][6] the solution
     int step;                  // PCR stride of this launch
     int src;                   // which copy holds the input rows
@@ -126,13 +133,37 @@ __global__ void __launch_bounds__(128) long_assemble(const BeamParams p, const L
         const double ARho = SCHEME != BFK_STEADY ? p.ARho[b] : 0.0;
         addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, D, src);
         for (int r = 0; r < 6; r++) v[0] += src[r] * src[r];
-        double *oD = q.D[q.src] + 36 * g, *oL = q.L[q.src] + 36 * g, *oU = q.U[q.src] + 36 * g, *oR = q.R[q.src] + 6 * g;
+        double *oD = q.D0 + 36 * g, *oL = q.L0 + 36 * g, *oU = q.U0 + 36 * g, *oR = q.R0 + 6 * g;
         for (int r = 0; r < 6; r++) {
             oR[r] = src[r];
             for (int c = 0; c < 6; c++) { oD[6 * r + c] = D[r][c]; oL[6 * r + c] = Lb[r][c]; oU[6 * r + c] = Ub[r][c]; }
         }
     }
     blockReduceStore<1>(v, p.partial, 0, gridDim.x, blockIdx.x);
+}
+
+// Rows into working copy 0; right-hand side = source (first pass) or source - A x (refinement pass).
+__global__ void __launch_bounds__(128) long_pcr_load(const BeamParams p, const LongParams q)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= q.N) return;
+    for (int k = 0; k < 36; k++) { q.L[0][36 * g + k] = q.L0[36 * g + k]; q.D[0][36 * g + k] = q.D0[36 * g + k]; q.U[0][36 * g + k] = q.U0[36 * g + k]; }
+    double r[6];
+    for (int k = 0; k < 6; k++) r[k] = q.R0[6 * g + k];
+    if (q.refine) {
+        const int b = q.cellBeam[g];
+        const int i = (int)(g - q.cellStart[b]), n = p.nSeg[b];
+        for (int k = 0; k < 6; k++) {
+            double a = 0.0;
+            for (int c = 0; c < 6; c++) {
+                a += q.D0[36 * g + 6 * k + c] * q.X[6 * g + c];
+                if (i > 0) a += q.L0[36 * g + 6 * k + c] * q.X[6 * (g - 1) + c];
+                if (i < n - 1) a += q.U0[36 * g + 6 * k + c] * q.X[6 * (g + 1) + c];
+            }
+            r[k] -= a;
+        }
+    }
+    for (int k = 0; k < 6; k++) q.R[0][6 * g + k] = r[k];
 }
 
 // One step of block parallel cyclic reduction with stride q.step.  Row i:  L_i x_{i-s} + D_i x_i + U_i x_{i+s} = R_i.
@@ -185,7 +216,7 @@ __global__ void __launch_bounds__(128) long_pcr_finish(const LongParams q)
     for (int k = 0; k < 36; k++) A[k] = q.D[q.src][36 * g + k];
     for (int k = 0; k < 6; k++) x[k] = q.R[q.src][6 * g + k];
     luSolve6(A, x, 1);
-    for (int k = 0; k < 6; k++) q.X[6 * g + k] = x[k];
+    for (int k = 0; k < 6; k++) q.X[6 * g + k] = q.refine ? q.X[6 * g + k] + x[k] : x[k];
 }
 
 // Faces first (they read the neighbour cell's pre-update W) ...

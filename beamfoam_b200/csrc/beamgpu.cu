@@ -65,7 +65,7 @@ struct bf_ctx {
     // few long beams: one thread per cell, assembled block rows, block parallel cyclic reduction (beam_long.cuh)
     int longMode, longBlocks;
     int32_t* d_cellBeam;
-    double* d_longRows[8]; // L, D, U, R x 2 copies
+    double* d_longRows[12]; // L, D, U, R: the assembled rows and two working copies
     double* d_longX;
     double* d_stage; // staging buffer in host (AoS) ordering
     double* d_stagePatch; // separate small staging for patch values (never shared with a pending mirror)
@@ -495,7 +495,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         c->longMode = lm ? atoi(lm) != 0 : (nmax >= 512 && B <= 128);
         c->longBlocks = (int)((c->N + 127) / 128);
         c->d_cellBeam = nullptr; c->d_longX = nullptr;
-        for (int k = 0; k < 8; k++) c->d_longRows[k] = nullptr;
+        for (int k = 0; k < 12; k++) c->d_longRows[k] = nullptr;
         if (getenv("BEAMGPU_TRACE") && devAlloc(c, (void**)&c->d_trace, sizeof(unsigned long long) * 4 * (size_t)c->grid)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
     }
     // ---- staging buffer (largest field in host ordering: a tensor vol field)
@@ -578,8 +578,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     if (c->longMode) {
         char* cur;
         const size_t N = (size_t)c->N;
-        if (devAlloc(c, (void**)&cur, sizeof(double) * N * (2 * (36 * 3 + 6) + 6) + sizeof(int32_t) * N + 256 * 12)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
-        for (int k = 0; k < 8; k++) c->d_longRows[k] = carve<double>(cur, (k % 4 == 3 ? 6 : 36) * N);
+        if (devAlloc(c, (void**)&cur, sizeof(double) * N * (3 * (36 * 3 + 6) + 6) + sizeof(int32_t) * N + 256 * 16)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        for (int k = 0; k < 12; k++) c->d_longRows[k] = carve<double>(cur, (k % 4 == 3 ? 6 : 36) * N);
         c->d_longX = carve<double>(cur, 6 * N + 6); // one row of slack: the last cell reads "x of the next cell" unguarded
         c->d_cellBeam = carve<int32_t>(cur, N);
         std::vector<int32_t> cb(N);
@@ -997,25 +997,31 @@ static int launchIteration(bf_ctx* c)
         LongParams q;
         q.N = c->N; q.cellBeam = c->d_cellBeam; q.cellStart = c->d_cellStart; q.X = c->d_longX;
         for (int k = 0; k < 2; k++) { q.L[k] = c->d_longRows[4 * k]; q.D[k] = c->d_longRows[4 * k + 1]; q.U[k] = c->d_longRows[4 * k + 2]; q.R[k] = c->d_longRows[4 * k + 3]; }
-        q.src = 0; q.step = 0;
+        q.L0 = c->d_longRows[8]; q.D0 = c->d_longRows[9]; q.U0 = c->d_longRows[10]; q.R0 = c->d_longRows[11];
+        q.src = 0; q.step = 0; q.refine = 0;
         const int gb = c->longBlocks;
         if (c->scheme == BF_SCHEME_NEWMARK) long_assemble<BFK_NEWMARK><<<gb, 128, 0, c->stream>>>(p, q);
         else if (c->scheme == BF_SCHEME_EULER) long_assemble<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
         else long_assemble<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
         c->launches++;
-        for (int s = 1; s < c->nmax; s *= 2) {
-            q.step = s;
-            long_pcr_step<<<gb, 128, 0, c->stream>>>(p, q);
-            q.src = 1 - q.src;
-            c->launches++;
+        for (int pass = 0; pass < 2; pass++) { // solve, then one step of iterative refinement on the residual
+            q.refine = pass; q.src = 0;
+            long_pcr_load<<<gb, 128, 0, c->stream>>>(p, q);
+            for (int s = 1; s < c->nmax; s *= 2) {
+                q.step = s;
+                long_pcr_step<<<gb, 128, 0, c->stream>>>(p, q);
+                q.src = 1 - q.src;
+                c->launches++;
+            }
+            long_pcr_finish<<<gb, 128, 0, c->stream>>>(q);
+            c->launches += 2;
         }
-        long_pcr_finish<<<gb, 128, 0, c->stream>>>(q);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
         long_update_faces<<<gb, 128, 0, c->stream>>>(p, q);
         if (c->scheme == BF_SCHEME_NEWMARK) long_update_cells<BFK_NEWMARK><<<gb, 128, 0, c->stream>>>(p, q);
         else if (c->scheme == BF_SCHEME_EULER) long_update_cells<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
         else long_update_cells<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
-        c->launches += 3;
+        c->launches += 2;
     } else if (c->splitKernels) { // profiling aid: the same two sweeps as two launches
         LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));

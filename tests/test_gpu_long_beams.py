@@ -21,8 +21,10 @@ def long_path(monkeypatch):
 
 
 def test_config1_follower_beam_10000_cells(gpu_lib, oracle_lib):
-    """BASELINE configs[1]: cantileverFollowerForce with nSegments 10000 (the path is chosen automatically)."""
-    run_pair(cases.cantileverFollowerForce(nSegments=10000), gpu_lib, oracle_lib, nSteps=3, tip_rtol=1e-7, field_rtol=1e-5)
+    """BASELINE configs[1]: cantileverFollowerForce with nSegments 10000 (the path is chosen automatically).  20 load
+    steps: without the refinement pass of the cyclic reduction the Newton loop needs 5-6 iterations from step 3 on
+    where the reference-shaped pivoted LU of the oracle needs 4."""
+    run_pair(cases.cantileverFollowerForce(nSegments=10000), gpu_lib, oracle_lib, nSteps=20, tip_rtol=1e-7, field_rtol=1e-5)
 
 
 def test_cantilever_roll_up(gpu_lib, oracle_lib, long_path):
