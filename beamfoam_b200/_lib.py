@@ -82,6 +82,7 @@ EXPORTS = {
     "bf_set_distributed_loads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bf_set_point_forces": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bf_set_bc_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "bf_beam_energy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bf_begin_step": (C.c_int, [C.c_void_p, C.c_double]),
     "bf_newton_iteration": (C.c_int, [C.c_void_p, _dp]),
     "bf_evolve": (C.c_int, [C.c_void_p, C.POINTER(bf_tolerances), C.POINTER(bf_step_out)]),

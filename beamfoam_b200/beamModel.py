@@ -323,6 +323,13 @@ class coupledTotalLagNewtonRaphsonBeam:
     def iOuterCorr(self) -> int:
         return self._iOuterCorr
 
+    def beamEnergy(self) -> np.ndarray:
+        """functionObjects/beamEnergyData (beamEnergyData.C:84-215): [nBeams, 3] = internal (strain) energy,
+        linear kinetic energy, angular kinetic energy of every beam of this shard."""
+        out = np.zeros((self._B, 3))
+        self._check(self.lib.bf_beam_energy(self._ctx, out.ctypes.data))
+        return out
+
     def tip(self, end: int = 1):
         """Patch values (W_b, Theta_b) of every beam at one end — the parity observable."""
         _, wl, wr = self.get_field("W", internal=False)

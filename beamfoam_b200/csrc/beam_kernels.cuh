@@ -1295,6 +1295,51 @@ __global__ void beam_point_forces(const BeamParams p)
     }
 }
 
+// beamEnergyData (functionObjects/beamEnergyData/beamEnergyData.C:84-215): per beam the strain energy of the face
+// strains Gamma, K (0.5 L[own] on internal faces, 0.25 L[cell] on the end faces) and the linear / angular kinetic
+// energy of the cells, straight from the device state.  One thread per beam; out[3 b + k].
+template <int SCHEME>
+__global__ void beam_energy(const BeamParams p, double* __restrict__ out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const size_t T = (size_t)(b >> 5), sb = p.Bpad;
+    const int lane = b & 31, n = p.nSeg[b], Rc = p.nmax, Rf = p.nmax + 1;
+    const double dZ = p.dZ[b], dcI = 1.0 / dZ, dcB = 2.0 / dZ;
+    const V3 CQ = ld3(p.CQ, b, sb), CM = ld3(p.CM, b, sb);
+    const M3 refL = ld9(p.refL, b, sb);
+    const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]), e0 = mulT(refL, dR0);
+    auto strain = [&](int j, V3 t, V3 e) { // Gamma.CQ.Gamma + K.CM.K of face j
+        const V3 G = gammaOf(quatToMat(ldq(p.Lf, tileRow(T, Rf, j, 4, lane), TS)), e, t);
+        const V3 K = ld3(p.K, tileRow(T, Rf, j, 3, lane), TS);
+        return dot(G, cmul(CQ, G)) + dot(K, cmul(CM, K));
+    };
+    auto cellLen = [&](int i) { return p.Lc ? p.Lc[tileRow(T, Rc, i, 1, lane)] : dZ; };
+    double intE = 0.0, kinL = 0.0, kinA = 0.0;
+    V3 Wprev = ld3(p.W, tileRow(T, Rc, 0, 3, lane), TS);
+    intE += 0.25 * cellLen(0) * strain(0, dcB * (ld3(p.Wb, b, sb) - Wprev) - dR0, -e0);
+    for (int i = 0; i < n; i++) {
+        const double Li = cellLen(i);
+        if (i + 1 < n) {
+            const V3 Wn = ld3(p.W, tileRow(T, Rc, i + 1, 3, lane), TS);
+            intE += 0.5 * Li * strain(i + 1, dR0 + dcI * (Wn - Wprev), e0);
+            Wprev = Wn;
+        } else
+            intE += 0.25 * Li * strain(n, dR0 + dcB * (ld3(p.Wb, (size_t)3 * sb + b, sb) - Wprev), e0);
+        if (SCHEME != BFK_STEADY) {
+            const size_t c3 = tileRow(T, Rc, i, 3, lane);
+            V3 U = ld3(p.U, c3, TS), Om = ld3(p.Om, c3, TS);
+            if (SCHEME == BFK_NEWMARK) { // stored as step constants (BeamParams): U = U* + gamma dt Accl
+                U = U + p.gdtPrev * ld3(p.Ac, c3, TS);
+                Om = Om + p.gdtPrev * ld3(p.dOm, c3, TS);
+            }
+            kinL += 0.5 * Li * p.ARho[b] * dot(U, U);
+            kinA += 0.5 * Li * dot(Om, cmul(ld3(p.CI, b, sb), Om));
+        }
+    }
+    out[3 * (size_t)b] = intE; out[3 * (size_t)b + 1] = kinL; out[3 * (size_t)b + 2] = kinA;
+}
+
 // Deterministic final reduction of the per-block partial sums (fixed order).
 __global__ void beam_reduce_partials(const double* __restrict__ partial, int nBlocks, double* __restrict__ out,
                                      double* __restrict__ outHost)

@@ -934,6 +934,25 @@ extern "C" int bf_region_elapsed_ms(bf_ctx* c, double* ms)
     *ms = t;
     return BF_OK;
 }
+// functionObjects/beamEnergyData: per-beam energies from the device state (no field leaves the device)
+extern "C" int bf_beam_energy(bf_ctx* c, double* out)
+{
+    if (!out) return fail(c, BF_ERR_INVALID, "bf_beam_energy: null argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    if (int rc = drainMirror(c)) return rc;
+    if ((size_t)c->B * 3 > c->stageDoubles) return fail(c, BF_ERR_INVALID, "bf_beam_energy: staging buffer too small");
+    const BeamParams p = makeParams(c); // gdtPrev = gamma * (the step the Newmark constants belong to)
+    const unsigned grid = (unsigned)((c->B + 127) / 128);
+    if (c->scheme == BF_SCHEME_NEWMARK) beam_energy<BFK_NEWMARK><<<grid, 128, 0, c->stream>>>(p, c->d_stage);
+    else if (c->scheme == BF_SCHEME_EULER) beam_energy<BFK_EULER><<<grid, 128, 0, c->stream>>>(p, c->d_stage);
+    else beam_energy<BFK_STEADY><<<grid, 128, 0, c->stream>>>(p, c->d_stage);
+    c->launches++;
+    CUDA_OK(c, cudaGetLastError());
+    CUDA_OK(c, cudaMemcpyAsync(out, c->d_stage, sizeof(double) * 3 * (size_t)c->B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
 // Debug aid (not in beamgpu.h): copies the [nTiles][4] time stamps of the last pipelined launch (BEAMGPU_TRACE=1).
 extern "C" int bf_debug_trace(bf_ctx* c, unsigned long long* out, int64_t maxTiles)
 {

@@ -272,6 +272,12 @@ int bf_set_reducer(bf_ctx* ctx, bf_reduce_fn fn, void* user);
 int bf_nccl_unique_id(void* uniqueId128);
 int bf_comm_init_nccl(bf_ctx* ctx, const void* uniqueId128, int32_t nRanks, int32_t rank);
 
+/* ---- observables computed next to the state ----------------------------------
+ * Replaces functionObjects/beamEnergyData/beamEnergyData.C:84-215 (a reduction over every cell and face
+ * per write step; here it does not need the fields on the host).  out[3*b + 0] internal (strain) energy,
+ * + 1 linear kinetic energy, + 2 angular kinetic energy of beam b of this context. */
+int bf_beam_energy(bf_ctx* ctx, double* out);
+
 /* ---- instrumentation --------------------------------------------------------
  * Kernel launches issued by this context since creation (bench gpu_launches),
  * and device time in ms of the Newton-iteration kernels since the last reset,

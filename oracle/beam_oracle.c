@@ -1098,6 +1098,33 @@ static void updateSolutionVariables(bf_ctx* c)
     }
 }
 
+/* functionObjects/beamEnergyData/beamEnergyData.C:84-215: per beam, internal energy (strain energy of the face
+ * strains, 0.5*L[own] on internal faces, 0.25*L[cell] on the two end faces), linear and angular kinetic energy.
+ * out[3*b + (0 intE, 1 kinE_lin, 2 kinE_ang)]. */
+int bf_beam_energy(bf_ctx* c, double* out)
+{
+    if (!out) { snprintf(c->err, sizeof c->err, "bf_beam_energy: null argument"); return BF_ERR_INVALID; }
+    memset(out, 0, sizeof(double) * 3 * c->B);
+    for (int64_t f = 0; f < c->NF; f++) {
+        const int64_t b = c->faceBeam[f];
+        const int64_t cell = f < c->F ? c->own[f] : c->pcell[f - c->F];
+        const double w = f < c->F ? 0.5 : 0.25;
+        const double *G = c->Gamma + 3 * f, *K = c->K + 3 * f, *CQ = c->CQ + 3 * b, *CM = c->CM + 3 * b;
+        double e = 0;
+        for (int k = 0; k < 3; k++) e += G[k] * (CQ[k] * G[k]);
+        double e2 = 0;
+        for (int k = 0; k < 3; k++) e2 += K[k] * (CM[k] * K[k]);
+        out[3 * b] += w * c->L[cell] * (e + e2);
+    }
+    for (int64_t i = 0; i < c->N; i++) {
+        const int64_t b = c->cellBeam[i];
+        const double *U = c->U + 3 * i, *Om = c->Omega + 3 * i, *CI = c->CIRho + 3 * b;
+        out[3 * b + 1] += 0.5 * c->L[i] * c->ARho[b] * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);
+        out[3 * b + 2] += 0.5 * c->L[i] * (Om[0] * (CI[0] * Om[0]) + Om[1] * (CI[1] * Om[1]) + Om[2] * (CI[2] * Om[2]));
+    }
+    return BF_OK;
+}
+
 /* One pass of the do{} body of evolve(): Evolve.C:119-632 */
 int bf_newton_iteration(bf_ctx* c, double sumsq[3])
 {

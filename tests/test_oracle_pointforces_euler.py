@@ -96,3 +96,29 @@ def test_euler_scheme_tracks_newmark_at_small_time_steps(oracle_lib):
     W0 = b.get_field("W")[0].copy()
     b.run(nSteps=1)
     np.testing.assert_allclose(b.get_field("U")[0], (b.get_field("W")[0] - W0) / eu.deltaT, rtol=0, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+# bf_beam_energy (functionObjects/beamEnergyData/beamEnergyData.C:84-215)
+# ---------------------------------------------------------------------------------------------
+def test_beam_energy_static_equals_work_of_the_load(oracle_lib):
+    """Small tip load on a cantilever: strain energy = 1/2 F w (Clapeyron), no kinetic energy."""
+    F = -1e-3
+    c = dataclasses.replace(clean_cantilever(40), W_right=forceBeamDisplacementNR(force=(0, F, 0)))
+    m = coupledTotalLagNewtonRaphsonBeam(c, library=oracle_lib)
+    m.run()
+    e = m.beamEnergy()
+    assert e.shape == (1, 3) and e[0, 1] == 0.0 and e[0, 2] == 0.0
+    assert abs(e[0, 0] - 0.5 * F * m.tip(1)[0][0][1]) <= 2e-3 * e[0, 0]
+
+
+def test_beam_energy_newmark_balance(oracle_lib):
+    """Constant dead load from rest: internal + kinetic energy = work of the load, F . w_tip, which the
+    average-acceleration Newmark scheme preserves up to the nonlinearity."""
+    m = coupledTotalLagNewtonRaphsonBeam(cases.multiBeamDensity(3, 20), library=oracle_lib)
+    for _ in range(60):
+        m.run(nSteps=1)
+    e = m.beamEnergy()
+    work = (m.tip(1)[0] * np.array([2000.0, 2000.0, 0.0])).sum(axis=1)
+    assert np.all(e > 0)
+    np.testing.assert_allclose(e.sum(axis=1), work, rtol=2e-2)
