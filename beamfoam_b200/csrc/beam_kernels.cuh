@@ -95,8 +95,16 @@ struct BeamParams {
     unsigned long long* trace; // optional [nTiles][4]: forward start/end, backward start/end (globaltimer ns), else null
 };
 
+// Everything the sweeps write is next read a whole sweep later (3.7 GB of state + 4.4 GB of scratch against 126 MB of
+// L2), so the stores are marked streaming (evict-first): they must not push the rows that the L2 prefetch / the TMA
+// copies have staged for the next cells out of L2.
+#ifdef BEAM_NO_STREAM_HINTS
+DEV void stS(double* p, double v) { *p = v; }
+#else
+DEV void stS(double* p, double v) { __stcs(p, v); }
+#endif
 DEV V3 ld3(const double* __restrict__ p, size_t i, size_t s) { return v3(p[i], p[i + s], p[i + 2 * s]); }
-DEV void st3(double* __restrict__ p, size_t i, size_t s, V3 v) { p[i] = v.x; p[i + s] = v.y; p[i + 2 * s] = v.z; }
+DEV void st3(double* __restrict__ p, size_t i, size_t s, V3 v) { stS(p + i, v.x); stS(p + i + s, v.y); stS(p + i + 2 * s, v.z); }
 DEV M3 ld9(const double* __restrict__ p, size_t i, size_t s)
 {
     M3 r;
@@ -110,7 +118,7 @@ DEV void st9(double* __restrict__ p, size_t i, size_t s, const M3& A)
     for (int k = 0; k < 9; k++) p[i + k * s] = A.a[k];
 }
 DEV Q4 ldq(const double* __restrict__ p, size_t i, size_t s) { return q4(p[i], p[i + s], p[i + 2 * s], p[i + 3 * s]); }
-DEV void stq(double* __restrict__ p, size_t i, size_t s, Q4 q) { p[i] = q.w; p[i + s] = q.x; p[i + 2 * s] = q.y; p[i + 3 * s] = q.z; }
+DEV void stq(double* __restrict__ p, size_t i, size_t s, Q4 q) { stS(p + i, q.w); stS(p + i + s, q.x); stS(p + i + 2 * s, q.y); stS(p + i + 3 * s, q.z); }
 // Gamma = refLambdaf.T() & ((Lambdaf.T() & dRdS) - dR0Ds)   Evolve.C:881-887, from the STORED W and
 // Lm = Lambdaf & refLambdaf:  Gamma = Lm.T() & dRdS - e0,  e0 = refLambdaf.T() & dR0Ds
 DEV V3 gammaOf(const M3& Lm, V3 e0, V3 t) { return mulT(Lm, t) - e0; }
@@ -343,6 +351,9 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 //     across the loop are free for the assembly.
 #ifndef BEAM_THREADS
 #define BEAM_THREADS 128
+#endif
+#ifndef BEAM_PF_DIST
+#define BEAM_PF_DIST 1 // cells of look-ahead of the backward sweep's L2 prefetch
 #endif
 #ifndef BEAM_MIN_BLOCKS
 #define BEAM_MIN_BLOCKS 2
@@ -769,14 +780,14 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
         for (int r = 0; r < 3; r++)
 #pragma unroll
             for (int c = 0; c < 6; c++) {
-                p.uP[u0 + (size_t)(6 * r + c) * TS] = X1[r][c];
-                p.uP[u0 + (size_t)(6 * (r + 3) + c) * TS] = X2[r][c];
+                stS(p.uP + u0 + (size_t)(6 * r + c) * TS, X1[r][c]);
+                stS(p.uP + u0 + (size_t)(6 * (r + 3) + c) * TS, X2[r][c]);
             }
     }
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        p.bP[b0 + (size_t)r * TS] = X1[r][6];
-        p.bP[b0 + (size_t)(r + 3) * TS] = X2[r][6];
+        stS(p.bP + b0 + (size_t)r * TS, X1[r][6]);
+        stS(p.bP + b0 + (size_t)(r + 3) * TS, X2[r][6]);
     }
     if (!LAST) {
         // ---- carry for cell i+1, one row of l at a time, each entry one fused chain that starts from d_nei:
@@ -1120,17 +1131,18 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
         for (int i = n - 1; i >= 0; i--) {
             // ---- back substitution: x_i = bPrime_i - uPrime_i & x_{i+1}
             const size_t u0 = tileRow(T, Rc, i, 36, lane), b0 = tileRow(T, Rc, i, 6, lane);
-            if (i > 0) { // prefetch what iteration i-1 reads: scratch and cell i-1, face i
-                const size_t m3 = tileRow(T, Rc, i - 1, 3, lane), g3 = tileRow(T, Rf, i, 3, lane);
-                pfRows<36>(p.uP, tileRow(T, Rc, i - 1, 36, lane), s);
-                pfRows<6>(p.bP, tileRow(T, Rc, i - 1, 6, lane), s);
+            if (i >= BEAM_PF_DIST) { // prefetch what iteration i-D reads: scratch and cell i-D, face i-D+1
+                const int ic = i - BEAM_PF_DIST;
+                const size_t m3 = tileRow(T, Rc, ic, 3, lane), g3 = tileRow(T, Rf, ic + 1, 3, lane);
+                pfRows<36>(p.uP, tileRow(T, Rc, ic, 36, lane), s);
+                pfRows<6>(p.bP, tileRow(T, Rc, ic, 6, lane), s);
                 pfRows<3>(p.W, m3, s); pfRows<3>(p.Th, m3, s);
-                pfRows<4>(p.Lam, tileRow(T, Rc, i - 1, 4, lane), s);
+                pfRows<4>(p.Lam, tileRow(T, Rc, ic, 4, lane), s);
                 if (SCHEME == BFK_NEWMARK) {
                     pfRows<3>(p.Ac, m3, s); pfRows<3>(p.dOm, m3, s);
                     if (p.first) { pfRows<3>(p.U, m3, s); pfRows<3>(p.Om, m3, s); }
                 }
-                pfRows<4>(p.Lf, tileRow(T, Rf, i, 4, lane), s);
+                pfRows<4>(p.Lf, tileRow(T, Rf, ic + 1, 4, lane), s);
                 pfRows<3>(p.K, g3, s);
                 pfRows<3>(p.Q, g3, s); pfRows<3>(p.M, g3, s);
             }
