@@ -139,6 +139,11 @@ DEV void pfL2(const double* __restrict__ p) { asm volatile("prefetch.global.L2 [
 #else
 DEV void pfL2(const double* __restrict__) {}
 #endif
+#ifdef BEAM_NEWMARK_PF_L1
+DEV void pfNm(const double* __restrict__ p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+DEV void pfNm(const double* __restrict__ p) { pfL2(p); }
+#endif
 template <int NR>
 DEV void pfRows(const double* __restrict__ p, size_t i0, size_t s)
 {
@@ -360,7 +365,10 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 #endif
 enum {
     R_DR0 = 0,   // dR0Ds = refLambdaf & e_x (3)
-    R_E0 = 3,    // refLambdaf.T() & dR0Ds (3)  (= e_x for an orthonormal refLambdaf)
+    R_DZ = 3,    // dZ of the beam (1)
+    R_ARHO = 4,  // rho A (1)
+    R_N = 5,     // cells of the beam, as a double (1).  These three are read once per cell: kept here they cannot
+                 // be spilled to local memory, whose reloads go to L2 (L1 is all but carved out for shared memory)
     R_CQ = 6,    // diag CQ (3)
     R_CM = 9,    // diag CM (3)
     R_LB = 12,   // -(l_{i-1} & bPrime_{i-1}) (6): the right-hand-side part of the carry
@@ -449,13 +457,13 @@ template <int SCHEME>
 DEV void fwdPrefetch(const BeamParams& p, size_t T, double* warpSm, uint64_t* bar, int lane, int i)
 {
     const int Rc = p.nmax, Rf = p.nmax + 1;
-    if (SCHEME == BFK_NEWMARK) { // cell i+... rows read by plain loads late in the assembly: pull them into L2
+    if (SCHEME == BFK_NEWMARK) { // rows of cell i read by plain loads late in the assembly: pull them closer now
         const size_t n3 = tileRow(T, Rc, i, 3, lane);
-        pfL2(p.Lam + tileRow(T, Rc, i, 4, 0) + 4 * lane); // 4 rows x 32 doubles: one double in four per lane
-        pfL2(p.Ac + n3); pfL2(p.Ac + n3 + 2 * TS);
-        pfL2(p.Om + n3); pfL2(p.Om + n3 + 2 * TS);
-        pfL2(p.dOm + n3); pfL2(p.dOm + n3 + 2 * TS);
-        if (p.first) { pfL2(p.U + n3); pfL2(p.U + n3 + 2 * TS); }
+        pfNm(p.Lam + tileRow(T, Rc, i, 4, 0) + 4 * lane); // 4 rows x 32 doubles: one double in four per lane
+        pfNm(p.Ac + n3); pfNm(p.Ac + n3 + 2 * TS);
+        pfNm(p.Om + n3); pfNm(p.Om + n3 + 2 * TS);
+        pfNm(p.dOm + n3); pfNm(p.dOm + n3 + 2 * TS);
+        if (p.first) { pfNm(p.U + n3); pfNm(p.U + n3 + 2 * TS); }
     }
     if (lane != 0) return;
     const bool hasW = i + 1 < p.nmax; // no cell i+1 in the slab for the last row
@@ -662,7 +670,8 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
         {
             const V3 CQ = smLd3(sm, R_CQ);
             const Sym3 Pm = conjDiagSym(Lm, dcI * CQ);                                // a*CQW :680
-            eQ = mul(Lm, cmul(CQ, mulTSub(Lm, t, smLd3(sm, R_E0))));                  // :682 with Gamma of :881-887
+            // refLambdaf.T() & dR0Ds = e_x: bf_create orthonormalises refLambdaf and dR0Ds is its first column
+            eQ = mul(Lm, cmul(CQ, mulTSub(Lm, t, v3(1.0, 0.0, 0.0))));                // :682 with Gamma of :881-887
             Gh = mulSpinR(Pm, th);
             M3 Qt = Gh;                                                               // 0.5*CQTheta :686-693
             Qt.a[1] += hQ.z; Qt.a[2] -= hQ.y; Qt.a[3] -= hQ.z; Qt.a[5] += hQ.x; Qt.a[6] += hQ.y; Qt.a[7] -= hQ.x;
@@ -862,21 +871,18 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
     __syncwarp(); // (persistent blocks) every lane has left the previous tile's buffer
     if (nW > 0) fwdPrefetch<SCHEME>(p, T, warpSm, bar, lane, 0);
 
-    const double dZ = p.dZ[b];
-    const double dcI = 1.0 / dZ; // mesh().deltaCoeffs() of internal faces
-    const double h = 0.5 / dcI;  // 0.5/deltaCoeffs of :706-741
     {
         const M3 refL = ld9(p.refL, b, s);
         const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
         smSt3(sm, R_DR0, dR0);
-        smSt3(sm, R_E0, mulT(refL, dR0));
+        smSt(sm, R_DZ, p.dZ[b]);
+        smSt(sm, R_ARHO, SCHEME != BFK_STEADY ? p.ARho[b] : 0.0);
+        smSt(sm, R_N, (double)n);
         smSt3(sm, R_CQ, ld3(p.CQ, b, s));
         smSt3(sm, R_CM, ld3(p.CM, b, s));
 #pragma unroll
         for (int r = 0; r < 6; r++) smSt(sm, R_LB + r, 0.0);
     }
-    const double ARho = SCHEME != BFK_STEADY ? p.ARho[b] : 0.0;
-
     // loop-carried in registers: lb = l_{i-1} & bPrime_{i-1};  Wi = W of cell i.  The carry
     // (nei part of d_i) - l_{i-1} & uPrime_{i-1} and the nei part of source_i travel through the stash.
     V3 Wi = v3(0, 0, 0);
@@ -901,12 +907,14 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
         const FaceIn in = loadFaceIn(sm);
         __syncwarp(); // every lane holds its buffer rows in registers: refill the buffer for the next cell now
         if (i + 1 < nW) fwdPrefetch<SCHEME>(p, T, warpSm, bar, lane, i + 1);
-        if (i < n - 1) { // a cell with an internal face on its right
+        const int nb = (int)smLd(sm, R_N); // cells of this lane's beam
+        if (i < nb - 1) { // a cell with an internal face on its right
             double src[6], Dc[6][6];
-            fwdAssemble<SCHEME, false>(p, b, sm, i, dZ, dcI, h, ARho, in, Dc, src, Wi, res);
+            const double dz = smLd(sm, R_DZ);
+            fwdAssemble<SCHEME, false>(p, b, sm, i, dz, rcpFast(dz), 0.5 * dz, smLd(sm, R_ARHO), in, Dc, src, Wi, res);
             fwdEliminate<false>(p, b, sm, i, Dc, src);
-        } else if (i == n - 1)
-            res += fwdLastCell<SCHEME>(p, b, sm, i, dZ, ARho, Wi);
+        } else if (i == nb - 1)
+            res += fwdLastCell<SCHEME>(p, b, sm, i, smLd(sm, R_DZ), smLd(sm, R_ARHO), Wi);
     }
     return res;
 }

@@ -528,7 +528,24 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         CREATE_CUDA(up(c->d_ARho, bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
         std::fill(h.begin(), h.end(), 0.0);
         for (size_t b = 0; b < bp; b++) { h[0 * bp + b] = 1.0; h[4 * bp + b] = 1.0; h[8 * bp + b] = 1.0; }
-        if (pr->refLambdaf) for (int64_t b = 0; b < B; b++) for (int k = 0; k < 9; k++) h[k * bp + b] = pr->refLambdaf[9 * b + k];
+        if (pr->refLambdaf) for (int64_t b = 0; b < B; b++) {
+            // setInitialPositionBeam writes a rotation; rounding in its file I/O is removed here (Gram-Schmidt on the
+            // columns) because the sweeps use refLambdaf.T() & refLambdaf = I exactly
+            double R[9];
+            for (int k = 0; k < 9; k++) R[k] = pr->refLambdaf[9 * b + k];
+            double c0[3] = {R[0], R[3], R[6]}, c1[3] = {R[1], R[4], R[7]};
+            const double n0 = sqrt(c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2]);
+            if (!(n0 > 0)) CREATE_FAIL(BF_ERR_INVALID, "bf_create: refLambdaf of beam %lld is singular", (long long)b);
+            for (int k = 0; k < 3; k++) c0[k] /= n0;
+            const double d01 = c0[0] * c1[0] + c0[1] * c1[1] + c0[2] * c1[2];
+            for (int k = 0; k < 3; k++) c1[k] -= d01 * c0[k];
+            const double n1 = sqrt(c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2]);
+            if (!(n1 > 0)) CREATE_FAIL(BF_ERR_INVALID, "bf_create: refLambdaf of beam %lld is singular", (long long)b);
+            for (int k = 0; k < 3; k++) c1[k] /= n1;
+            const double c2[3] = {c0[1] * c1[2] - c0[2] * c1[1], c0[2] * c1[0] - c0[0] * c1[2], c0[0] * c1[1] - c0[1] * c1[0]};
+            const double Rn[9] = {c0[0], c1[0], c2[0], c0[1], c1[1], c2[1], c0[2], c1[2], c2[2]};
+            for (int k = 0; k < 9; k++) h[k * bp + b] = Rn[k];
+        }
         CREATE_CUDA(up(c->d_refL, 9 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
         // boundary-condition classes and spring data
         std::vector<double> sk(2 * bp, 0.0), sd(6 * bp, 0.0);

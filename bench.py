@@ -307,7 +307,7 @@ def run_ours(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "beam_newton<true>", "kernel_ms": kern_ms,
+                "traffic": traffic, "kernel": "beam_newton<BFK_NEWMARK>", "kernel_ms": kern_ms,
                 "bytes_per_update": BYTES_PER_UPDATE_NEWMARK, "updates_per_launch": nCellsLocal,
                 "peak_source": peak_src, "kernel_share_of_step": (fwd.value + bwd.value) / ms.value,
                 "fwd_ms": fwd.value / max(nit.value, 1), "bwd_ms": bwd.value / max(nit.value, 1)}

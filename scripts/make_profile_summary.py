@@ -34,7 +34,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 summary = []
 with open(os.path.join(out, f"{tag}_beam_newton_ncu.md"), "w") as f:
-    f.write(f"# {tag}: ncu --set full --clock-control none, kernel beam_newton<true>\n\n")
+    f.write(f"# {tag}: ncu --set full --clock-control none, kernel beam_newton<BFK_NEWMARK> (shown by ncu as beam_newton<1>)\n\n")
     for r in rows[2:]:
         f.write(f"## launch: {r[col['Kernel Name']]}  grid {r[col.get('Grid Size', 0)]} block {r[col.get('Block Size', 0)]}\n\n| metric | value | unit |\n|---|---|---|\n")
         rec = {}
