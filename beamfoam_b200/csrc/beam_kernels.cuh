@@ -118,6 +118,16 @@ DEV void st9(double* __restrict__ p, size_t i, size_t s, const M3& A)
     for (int k = 0; k < 9; k++) p[i + k * s] = A.a[k];
 }
 DEV Q4 ldq(const double* __restrict__ p, size_t i, size_t s) { return q4(p[i], p[i + s], p[i + 2 * s], p[i + 3 * s]); }
+// Loads the compiler may not sink towards their first use: issued where written, so that the latency of rows that
+// are consumed late in a cell is covered by the work in between.
+DEV double ldEarly(const double* p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+DEV V3 ld3Early(const double* p, size_t i, size_t s) { return v3(ldEarly(p + i), ldEarly(p + i + s), ldEarly(p + i + 2 * s)); }
+DEV Q4 ldqEarly(const double* p, size_t i, size_t s) { return q4(ldEarly(p + i), ldEarly(p + i + s), ldEarly(p + i + 2 * s), ldEarly(p + i + 3 * s)); }
 DEV void stq(double* __restrict__ p, size_t i, size_t s, Q4 q) { stS(p + i, q.w); stS(p + i + s, q.x); stS(p + i + 2 * s, q.y); stS(p + i + 3 * s, q.z); }
 // Gamma = refLambdaf.T() & ((Lambdaf.T() & dRdS) - dR0Ds)   Evolve.C:881-887, from the STORED W and
 // Lm = Lambdaf & refLambdaf:  Gamma = Lm.T() & dRdS - e0,  e0 = refLambdaf.T() & dR0Ds
@@ -559,9 +569,28 @@ DEV void pointForceSource(const BeamParams& p, const int b, const int i, double*
 
 // Loads (Evolve.C:193-279) and inertia (Evolve.C:320-536, with the Newmark predictor :167-186 on the first iteration
 // of a time step) of cell i, added to its diagonal block and source.
+// The Newmark rows of a cell; the forward sweep issues these loads at the top of the cell (ldEarly) and consumes
+// them after the face part.
+struct CellIn {
+    Q4 ql;
+    V3 Ac, Om, dOm;
+};
+template <int SCHEME, bool EARLY>
+DEV CellIn loadCellIn(const BeamParams& p, const int b, const int i)
+{
+    CellIn c;
+    c.ql = q4(1, 0, 0, 0);
+    c.Ac = c.Om = c.dOm = v3(0, 0, 0);
+    if (SCHEME == BFK_NEWMARK) {
+        const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31), c4 = tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31);
+        if (EARLY) { c.ql = ldqEarly(p.Lam, c4, TS); c.Ac = ld3Early(p.Ac, c3, TS); c.Om = ld3Early(p.Om, c3, TS); c.dOm = ld3Early(p.dOm, c3, TS); }
+        else { c.ql = ldq(p.Lam, c4, TS); c.Ac = ld3(p.Ac, c3, TS); c.Om = ld3(p.Om, c3, TS); c.dOm = ld3(p.dOm, c3, TS); }
+    }
+    return c;
+}
 template <int SCHEME>
 DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const double dZ, const double ARho,
-                            double (&Dc)[6][6], double (&src)[6])
+                            const CellIn& cell, double (&Dc)[6][6], double (&src)[6])
 {
     const double dt = p.dt, gamma = p.gamma;
     // ---- loads: Evolve.C:193-209,274-279
@@ -576,9 +605,9 @@ DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const
         for (int r = 0; r < 6; r++) src[r] -= p.pfSrc[c6 + (size_t)r * TS];
     }
     if (SCHEME == BFK_NEWMARK) { // inertia: Evolve.C:320-536 (+ predictor :167-186 on the first iteration)
-        const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
-        V3 Ac = ld3(p.Ac, c3, TS), dOm = ld3(p.dOm, c3, TS), Om;
-        const V3 OmS = ld3(p.Om, c3, TS); // Omega*
+        const M3 Lm = quatToMat(cell.ql);
+        V3 Ac = cell.Ac, dOm = cell.dOm, Om;
+        const V3 OmS = cell.Om; // Omega*
         if (p.first) {
             const V3 Ao = Ac, dOo = dOm;
             const V3 Uo = ld3(p.U, c3, TS) + p.gdtPrev * Ao, Oo = OmS + p.gdtPrev * dOo; // end of the previous step
@@ -650,6 +679,11 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
 {
     // Dc is an OUTPUT: each 3x3 block of the carry is fetched from the stash (R_DC) where its first
     // contribution is added
+#ifdef BEAM_NO_EARLY_LOADS
+    const CellIn cell = loadCellIn<SCHEME, false>(p, b, i);
+#else
+    const CellIn cell = loadCellIn<SCHEME, true>(p, b, i);
+#endif
 #pragma unroll
     for (int r = 0; r < 6; r++) src[r] = smLd(sm, R_SC + r);
     if (!LAST) {
@@ -725,7 +759,7 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
             for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
         }
     }
-    addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, Dc, src);
+    addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, cell, Dc, src);
 #pragma unroll
     for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
 }
