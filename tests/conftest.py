@@ -31,3 +31,9 @@ def gpu_lib():
     lib = load_library()
     assert lib.bf_backend() == b"cuda-sm100a"
     return lib
+
+
+@pytest.fixture(scope="session")
+def oracle_lib_path():
+    """Path of the oracle library, for hosts that dlopen() an implementation of the ABI themselves."""
+    return build_oracle()
