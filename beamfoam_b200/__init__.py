@@ -8,7 +8,7 @@ beamModel / fvPatchField interface for this path.
 from . import _lib  # noqa: F401
 from ._lib import BeamGpuError, load_library  # noqa: F401
 from .beamModel import BeamCase, axisAngleRotation, coupledTotalLagNewtonRaphsonBeam, shard_range  # noqa: F401
-from . import cases, crossSections, fvPatchFields  # noqa: F401
+from . import beamMomentumContribution, cases, crossSections, fvPatchFields  # noqa: F401
 
-__all__ = ["BeamCase", "BeamGpuError", "axisAngleRotation", "cases", "coupledTotalLagNewtonRaphsonBeam",
+__all__ = ["BeamCase", "BeamGpuError", "axisAngleRotation", "beamMomentumContribution", "cases", "coupledTotalLagNewtonRaphsonBeam",
            "crossSections", "fvPatchFields", "load_library", "shard_range"]

@@ -62,6 +62,12 @@ class bf_step_out(C.Structure):
                 ("currentResidualNorm", C.c_double), ("deltaXNorm", C.c_double), ("xNorm", C.c_double)]
 
 
+class bf_momentum_contribution(C.Structure):
+    _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("coeffs", C.c_double * 6)]
+
+
+BF_CONTRIB_MORISON_DRAG, BF_CONTRIB_GROUND_CONTACT, BF_MAX_CONTRIBUTIONS = 0, 1, 8
+
 bf_reduce_fn = C.CFUNCTYPE(C.c_int, _dp, C.c_int32, C.c_void_p)
 
 # every symbol include/beamgpu.h declares: name -> (restype, argtypes)
@@ -81,6 +87,8 @@ EXPORTS = {
     "bf_mirror_wait": (C.c_int, [C.c_void_p]),
     "bf_set_distributed_loads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bf_set_point_forces": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bf_set_momentum_contributions": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(bf_momentum_contribution), C.c_void_p,
+                                                C.c_void_p]),
     "bf_set_bc_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "bf_beam_energy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bf_begin_step": (C.c_int, [C.c_void_p, C.c_double]),

@@ -82,6 +82,12 @@ class BeamCase:
     pointForces: Optional[Sequence[tuple]] = None
     # setInitialPositionBeam -rotateAngle '(axis angle)': 3x3 T (all beams) or (nBeams,3,3); None = I
     initialRotation: Optional[np.ndarray] = None
+    # setInitialPositionBeam -translate '(x y z)': (3,) or (nBeams,3); only the momentum contributions read it
+    initialTranslation: Optional[np.ndarray] = None
+    # constant/beamMomentumContributionProperties: list of morisonDragContribution / groundContactContribution
+    momentumContributions: Optional[Sequence] = None
+    # crossSection.R() per beam (circle: radius, rectangle: h/2): read by the momentum contributions only
+    R: Union[float, Sequence[float]] = 0.0
     # system/controlDict
     deltaT: float = 1.0
     endTime: float = 1.0
@@ -207,6 +213,21 @@ class coupledTotalLagNewtonRaphsonBeam:
                 self.set_field(var, None, left, right)
         if case.q is not None or case.m is not None:
             self._set_loads(case.q, case.m, lo, hi)
+
+        if case.momentumContributions:
+            lst = (L.bf_momentum_contribution * len(case.momentumContributions))()
+            for k, mc in enumerate(case.momentumContributions):
+                lst[k].type = mc.type
+                for j, v in enumerate(mc.coeffs()):
+                    lst[k].coeffs[j] = float(v)
+            radius = np.ascontiguousarray(case.per_beam(case.R)[sl])
+            tr = None
+            if case.initialTranslation is not None:
+                tr = np.asarray(case.initialTranslation, dtype=np.float64)
+                tr = np.ascontiguousarray(np.broadcast_to(tr, (case.nBeams, 3))[sl] if tr.ndim == 1 else tr[sl])
+            self._keep += (lst, radius, tr)
+            self._check(self.lib.bf_set_momentum_contributions(
+                ctx, len(case.momentumContributions), lst, radius.ctypes.data, tr.ctypes.data if tr is not None else None))
 
         self.tol = L.bf_tolerances(case.nCorrectors, case.rtol(), case.solutionTol, case.absoluteTol,
                                    case.divergenceTol)

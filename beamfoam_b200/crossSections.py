@@ -17,6 +17,9 @@ class circle:
     scalingArea: float = 1.0
     scalingSecondMomentArea: float = 1.0
 
+    def R(self):
+        return self.radius
+
     def A(self):
         return self.scalingArea * math.pi * self.radius ** 2
 
@@ -36,6 +39,9 @@ class rectangle:
     h: float
     scalingArea: float = 1.0
     scalingSecondMomentArea: float = 1.0
+
+    def R(self):  # rectangle.H:133-136
+        return self.h / 2
 
     def A(self):
         return self.scalingArea * self.b * self.h

@@ -70,7 +70,8 @@ struct BeamParams {
     const double *q, *m, *Lc; // optional (may be null)
     // optional point forces (Evolve.C:211-271), 9 per cell: sum F, sum zeta F over zeta > 0, sum zeta F over zeta < 0
     const double* pf;
-    double* pfSrc; // [cells][6] their contribution to the source, formed by beam_point_forces before each sweep
+    double* pfSrc; // [cells][6] source terms formed before each sweep by beam_point_forces and beam_momentum_contributions
+                   // (beam_contrib.cuh), subtracted from the source; null when the case has neither
     // Euler d2dt2Scheme only: old-time level of W, U, Omega (3 each) and Lambda (quaternion), written by the first
     // iteration of a time step.  With Euler, U / Om hold the plain fields (no step constants) and dOm is not used.
     double *Wold, *Uold, *Omold, *Lamold;
@@ -599,7 +600,7 @@ DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const
     if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, TS));
     subV(src, 0, Lcell * ld3(p.weight, b, p.Bpad));
     if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, TS));
-    if (p.pf) {
+    if (p.pfSrc) { // point forces and momentum contributions, formed by their pre-kernels
         const size_t c6 = tileRow((size_t)(b >> 5), p.nmax, i, 6, b & 31);
 #pragma unroll
         for (int r = 0; r < 6; r++) src[r] -= p.pfSrc[c6 + (size_t)r * TS];

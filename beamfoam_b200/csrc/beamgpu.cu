@@ -8,6 +8,7 @@
 #include "../../include/beamgpu.h"
 #include "beam_kernels.cuh"
 #include "beam_long.cuh"
+#include "beam_contrib.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -46,7 +47,7 @@ struct bf_ctx {
     std::vector<int64_t> cellStart, faceStart;
     bool uniformN;
     // device pools
-    void* pools[20];
+    void* pools[32];
     int nPools;
     int32_t *d_nSeg, *d_wType, *d_thType;
     int64_t *d_cellStart, *d_faceStart;
@@ -55,6 +56,7 @@ struct bf_ctx {
     double *d_Wold, *d_Uold, *d_Omold, *d_Lamold; // Euler d2dt2Scheme: old-time level
     double *d_pf, *d_pfSrc;                       // point forces, 9 per cell, and their source terms, 6 per cell (on first use)
     bool hasPf;
+    ContribParams contrib; // beamMomentumContribution list (bf_set_momentum_contributions); contrib.n == 0: none
     double *d_Lf, *d_K, *d_Q, *d_M; // d_Lf, d_Lam: unit quaternions (4 components); Gamma is derived, not stored
     double *d_Wb, *d_Thb, *d_Lamb, *d_DWb, *d_DThb, *d_force, *d_wPresc, *d_thPresc, *d_follower, *d_offset,
         *d_moment, *d_springK, *d_springDir;
@@ -895,6 +897,45 @@ extern "C" int bf_set_point_forces(bf_ctx* c, int64_t n, const int64_t* cell, co
     return BF_OK;
 }
 
+// constant/beamMomentumContributionProperties (CTL.C:1137-1182; Evolve.C:539-571): see beam_contrib.cuh
+extern "C" int bf_set_momentum_contributions(bf_ctx* c, int32_t n, const bf_momentum_contribution* list, const double* radius,
+                                             const double* translation)
+{
+    if (n < 0 || n > BF_MAX_CONTRIBUTIONS || (n > 0 && (!list || !radius))) return fail(c, BF_ERR_INVALID, "bf_set_momentum_contributions: bad argument");
+    for (int i = 0; i < n; i++) {
+        if (list[i].type != BF_CONTRIB_MORISON_DRAG && list[i].type != BF_CONTRIB_GROUND_CONTACT)
+            return fail(c, BF_ERR_INVALID, "unknown beamMomentumContributionType %d", list[i].type);
+        if (list[i].type == BF_CONTRIB_MORISON_DRAG && c->scheme == BF_SCHEME_STEADY) // morisonDragContribution.C:178-190
+            return fail(c, BF_ERR_UNSUPPORTED, "Momentum contribution due to Morison drag for time scheme steadyState is not defined!!");
+    }
+    c->contrib.n = 0;
+    if (!n) return BF_OK;
+    CUDA_OK(c, cudaSetDevice(c->device));
+    const size_t bp = (size_t)c->Bpad;
+    if (!c->contrib.radius) {
+        double *r = nullptr, *t = nullptr;
+        int rc = devAlloc(c, (void**)&r, sizeof(double) * bp);
+        if (!rc) rc = devAlloc(c, (void**)&t, sizeof(double) * 3 * bp);
+        if (!rc && !c->d_pfSrc) rc = devAlloc(c, (void**)&c->d_pfSrc, sizeof(double) * 6 * (size_t)c->nmax * bp);
+        if (rc) return rc;
+        c->contrib.radius = r; c->contrib.translation = t;
+    }
+    std::vector<double> h(4 * bp, 0.0);
+    for (int64_t b = 0; b < c->B; b++) {
+        h[b] = radius[b];
+        if (translation) for (int k = 0; k < 3; k++) h[(1 + k) * bp + b] = translation[3 * b + k];
+    }
+    CUDA_OK(c, cudaMemcpyAsync((void*)c->contrib.radius, h.data(), sizeof(double) * bp, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync((void*)c->contrib.translation, h.data() + bp, sizeof(double) * 3 * bp, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++) {
+        c->contrib.type[i] = list[i].type;
+        for (int k = 0; k < 6; k++) c->contrib.coeffs[i][k] = list[i].coeffs[k];
+    }
+    c->contrib.n = n;
+    return BF_OK;
+}
+
 extern "C" int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const double* v)
 {
     if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !v) return fail(c, BF_ERR_INVALID, "bf_set_bc_values: bad argument");
@@ -1003,7 +1044,7 @@ static BeamParams makeParams(bf_ctx* c)
     p.W = c->d_W; p.Th = c->d_Th; p.Lam = c->d_Lam; p.U = c->d_U; p.Ac = c->d_Ac; p.Om = c->d_Om; p.dOm = c->d_dOm;
     p.DW = c->d_DW; p.DTh = c->d_DTh;
     p.q = c->hasQ ? c->d_q : nullptr; p.m = c->hasM ? c->d_m : nullptr; p.Lc = c->d_Lc;
-    p.pf = c->hasPf ? c->d_pf : nullptr; p.pfSrc = c->d_pfSrc;
+    p.pf = c->hasPf ? c->d_pf : nullptr; p.pfSrc = (c->hasPf || c->contrib.n) ? c->d_pfSrc : nullptr;
     p.Wold = c->d_Wold; p.Uold = c->d_Uold; p.Omold = c->d_Omold; p.Lamold = c->d_Lamold;
     p.Lf = c->d_Lf; p.K = c->d_K; p.Q = c->d_Q; p.M = c->d_M;
     p.Wb = c->d_Wb; p.Thb = c->d_Thb; p.Lamb = c->d_Lamb; p.DWb = c->d_DWb; p.DThb = c->d_DThb; p.force = c->d_force;
@@ -1026,6 +1067,15 @@ static int launchIteration(bf_ctx* c)
     const BeamParams p = makeParams(c);
     if (p.pf) { // lever arms follow the current W: re-evaluated every iteration (Evolve.C:221)
         beam_point_forces<<<(unsigned)((c->B + 127) / 128), 128, 0, c->stream>>>(p);
+        c->launches++;
+    }
+    if (c->contrib.n) { // beamMomentumContribution sources follow the current W and U: every iteration (Evolve.C:539-571)
+        ContribParams cp = c->contrib;
+        cp.keepPointForces = p.pf != nullptr;
+        const unsigned cgrid = (unsigned)(((size_t)((c->B + 31) / 32) * 32 * (size_t)c->nmax + 127) / 128);
+        if (c->scheme == BF_SCHEME_NEWMARK) beam_momentum_contributions<BFK_NEWMARK><<<cgrid, 128, 0, c->stream>>>(p, cp);
+        else if (c->scheme == BF_SCHEME_EULER) beam_momentum_contributions<BFK_EULER><<<cgrid, 128, 0, c->stream>>>(p, cp);
+        else beam_momentum_contributions<BFK_STEADY><<<cgrid, 128, 0, c->stream>>>(p, cp);
         c->launches++;
     }
     if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[0], c->stream));

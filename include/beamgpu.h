@@ -239,6 +239,31 @@ int bf_set_distributed_loads(bf_ctx* ctx, const double* q, const double* m);
 int bf_set_point_forces(bf_ctx* ctx, int64_t n, const int64_t* cell, const double* zeta,
                         const double* force);
 
+/* constant/beamMomentumContributionProperties: the run-time selectable explicit momentum sources
+ * (src/wireBunchingModels/beamMomentumContribution; created in CTL.C:1137-1182, added to the source in
+ * Evolve.C:539-571 for every d2dt2Scheme; their diagCoeff() is zero).  Both evaluate, per cell, the
+ * mid-point derivative of the Hermite spline through the current face points and tangents
+ * (numerics/HermiteSpline/HermiteSpline.C:83-108,300-385,468-513; CTL.C:1263-1427,1518-1645) and the
+ * cell velocity U:
+ *   BF_CONTRIB_MORISON_DRAG    morisonDragContribution.C:103-195   coeffs = { Cdn, Cdt, rhoFluid }
+ *   BF_CONTRIB_GROUND_CONTACT  groundContactContribution.C:111-236 coeffs = { kNormal, cNormal,
+ *                              kTangential, muFriction, groundZ }
+ * radius[nBeams] = crossSection.R() (circle.H:117, rectangle.H:133: h/2); translation[nBeams*3] = the
+ * -translate vector of setInitialPositionBeam (refW = T & C + translate - C; NULL => 0).
+ * The reference evaluates the spline of beam 0 only (currentBeamPoints() with the default bI = 0), so its
+ * result is defined for single-beam cases; here every beam gets its own spline.  morisonDrag with the
+ * steadyState scheme is a FatalError in the reference: BF_ERR_UNSUPPORTED.  n = 0 removes all. */
+#define BF_CONTRIB_MORISON_DRAG    0
+#define BF_CONTRIB_GROUND_CONTACT  1
+#define BF_MAX_CONTRIBUTIONS       8
+typedef struct bf_momentum_contribution {
+    int32_t type;
+    int32_t reserved;
+    double  coeffs[6];
+} bf_momentum_contribution;
+int bf_set_momentum_contributions(bf_ctx* ctx, int32_t n, const bf_momentum_contribution* list,
+                                  const double* radius, const double* translation);
+
 /* Per-step boundary values == what W_/Theta_.boundaryFieldRef().updateCoeffs()
  * (Evolve.C:156-157) evaluates from the BC time series at the new time.
  * values: [nBeams*3] for patch `end`; entries of beams whose BC class does not

@@ -137,6 +137,12 @@ struct bf_ctx {
     int64_t nPointForces;
     int64_t* pfCell;
     double *pfZeta, *pfForce;
+    /* beamMomentumContribution list (CTL.C:1137-1182) and the geometry it reads: mesh.C(), mesh.Cf(), refW_, refWf_ */
+    int32_t nContrib;
+    bf_momentum_contribution contrib[BF_MAX_CONTRIBUTIONS];
+    double *radius;                /* [B] R(bI) */
+    double *meshC, *meshCf;        /* [N*3], [NF*3] cell and face centres of createBeamMesh (beams along x from 0) */
+    double *refW, *refWf;          /* [N*3], [NF*3] written by setInitialPositionBeam; zero on a fresh mesh */
     /* boundary-condition objects */
     int32_t *wType, *thType;
     double *springK, *springDir;
@@ -203,7 +209,8 @@ int bf_destroy(bf_ctx* c)
                     c->Thetab, c->ThetabPrev, c->Lambda, c->Lambdab, c->DW, c->DWb, c->DTheta, c->DThetab, c->U,
                     c->Accl, c->Omega, c->dotOmega, c->q, c->m, c->wType, c->thType, c->springK, c->springDir,
                     c->wPresc, c->thPresc, c->force, c->followerForce, c->offsetForce, c->moment, c->d, c->l, c->u,
-                    c->source, c->solVec, c->Wold, c->Uold, c->Omegaold, c->Lambdaold, c->pfCell, c->pfZeta, c->pfForce};
+                    c->source, c->solVec, c->Wold, c->Uold, c->Omegaold, c->Lambdaold, c->pfCell, c->pfZeta, c->pfForce,
+                    c->radius, c->meshC, c->meshCf, c->refW, c->refWf};
     for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) free(ptrs[i]);
     free(c);
     return BF_OK;
@@ -240,6 +247,7 @@ int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf_bc* bc, co
     const int64_t N = c->N = c->cellStart[B], F = c->F = c->faceStart[B], NF = c->NF = F + 2 * B;
     ALLOC(c->own, F); ALLOC(c->nei, F); ALLOC(c->pcell, 2 * B); ALLOC(c->dc, NF); ALLOC(c->wf, F); ALLOC(c->L, N);
     ALLOC(c->cellBeam, N); ALLOC(c->faceBeam, NF);
+    ALLOC(c->radius, B); ALLOC(c->meshC, 3 * N); ALLOC(c->meshCf, 3 * NF); ALLOC(c->refW, 3 * N); ALLOC(c->refWf, 3 * NF);
     ALLOC(c->CQ, 3 * B); ALLOC(c->CM, 3 * B); ALLOC(c->ARho, B); ALLOC(c->CIRho, 3 * B); ALLOC(c->weight, 3 * B);
     for (int64_t b = 0; b < B; b++) {
         const int n = c->nSeg[b];
@@ -248,12 +256,15 @@ int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf_bc* bc, co
             const int64_t cell = c->cellStart[b] + i;
             c->cellBeam[cell] = (int32_t)b;
             c->L[cell] = lay->cellLength ? lay->cellLength[cell] : dZ;
+            c->meshC[3 * cell] = (i + 0.5) * dZ; /* createBeamMesh.C:224-237: every beam runs along x from 0, section centred on the axis */
         }
+        c->meshCf[3 * (F + B + b)] = n * dZ;
         for (int i = 1; i < n; i++) { /* createBeamMesh.C:357-370,398-408 */
             const int64_t f = c->faceStart[b] + i - 1;
             c->own[f] = (int32_t)(c->cellStart[b] + i - 1);
             c->nei[f] = (int32_t)(c->cellStart[b] + i);
             c->dc[f] = 1.0 / dZ;
+            c->meshCf[3 * f] = i * dZ;
             c->wf[f] = 0.5;
             c->faceBeam[f] = (int32_t)b;
         }
@@ -488,6 +499,42 @@ int bf_set_point_forces(bf_ctx* c, int64_t n, const int64_t* cell, const double*
 /* fvc:: helpers on the 1-D chain mesh (orthogonal snGrad, linear interpolate) */
 /* ------------------------------------------------------------------------- */
 /* snGrad of a vol vector field at face f (internal: (nei-own)*dc; boundary: (b-c)*dc) */
+/* constant/beamMomentumContributionProperties (CTL.C:1137-1182) */
+int bf_set_momentum_contributions(bf_ctx* c, int32_t n, const bf_momentum_contribution* list, const double* radius,
+                                  const double* translation)
+{
+    if (n < 0 || n > BF_MAX_CONTRIBUTIONS || (n > 0 && (!list || !radius))) { snprintf(c->err, 512, "bf_set_momentum_contributions: bad argument"); return BF_ERR_INVALID; }
+    for (int i = 0; i < n; i++) {
+        if (list[i].type != BF_CONTRIB_MORISON_DRAG && list[i].type != BF_CONTRIB_GROUND_CONTACT) { snprintf(c->err, 512, "unknown beamMomentumContributionType %d", list[i].type); return BF_ERR_INVALID; }
+        if (list[i].type == BF_CONTRIB_MORISON_DRAG && c->scheme == BF_SCHEME_STEADY) { /* morisonDragContribution.C:178-190 */
+            snprintf(c->err, 512, "Momentum contribution due to Morison drag for time scheme steadyState is not defined!!");
+            return BF_ERR_UNSUPPORTED;
+        }
+    }
+    c->nContrib = n;
+    if (!n) return BF_OK;
+    memcpy(c->contrib, list, sizeof(bf_momentum_contribution) * (size_t)n);
+    memcpy(c->radius, radius, sizeof(double) * (size_t)c->B);
+    /* refW = (T & C) + translate - C, refWf likewise (setInitialPositionBeam.C:236-290) */
+    for (int64_t b = 0; b < c->B; b++) {
+        const double* T = c->refLambdaf + 9 * (c->F + b); /* the rigid rotation of the beam (patch face value) */
+        const double tr[3] = {translation ? translation[3 * b] : 0, translation ? translation[3 * b + 1] : 0, translation ? translation[3 * b + 2] : 0};
+        for (int i = 0; i < c->nSeg[b]; i++) {
+            const int64_t cell = c->cellStart[b] + i;
+            double v[3];
+            t_mul_v(T, c->meshC + 3 * cell, v);
+            for (int k = 0; k < 3; k++) c->refW[3 * cell + k] = v[k] + tr[k] - c->meshC[3 * cell + k];
+        }
+        for (int j = 0; j <= c->nSeg[b]; j++) {
+            const int64_t f = j == 0 ? c->F + b : j == c->nSeg[b] ? c->F + c->B + b : c->faceStart[b] + j - 1;
+            double v[3];
+            t_mul_v(T, c->meshCf + 3 * f, v);
+            for (int k = 0; k < 3; k++) c->refWf[3 * f + k] = v[k] + tr[k] - c->meshCf[3 * f + k];
+        }
+    }
+    return BF_OK;
+}
+
 static void snGrad(const bf_ctx* c, const double* vI, const double* vB, int64_t f, double* o)
 {
     if (f < c->F) {
@@ -779,6 +826,183 @@ static void addPointForces(bf_ctx* c)
         double M0[3];
         cross(DR, F0, M0);
         for (int j = 0; j < 3; j++) src[6 * cell + 3 + j] -= M0[j];
+    }
+}
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * beamMomentumContribution (Evolve.C:539-571): explicit sources, per cell, from the mid-point derivative of the
+ * Hermite spline through the current beam points and tangents.  Restated function by function:
+ *   currentBeamPoints    CTL.C:1263-1427        currentBeamTangents  CTL.C:1518-1645
+ *   HermiteSpline ctor   HermiteSpline.C:190-217, calcParam :34-56, segLengths :985-998, arcLength :342-386,
+ *   localParameter :300-340, paramFirstDerivative :515-536, firstDerivative :468-513, static position :1096-1128,
+ *   calcMidPointDerivatives :83-108
+ * The reference builds the spline of beam 0 only (default bI = 0); here each beam has its own. */
+typedef struct { int n; const double *P, *T; double *cseg, *param; } HSpline;
+
+static void hs_paramFirstDerivative(const HSpline* h, int seg, double zeta, double* o)
+{
+    const double *t0 = h->T + 3 * seg, *t1 = h->T + 3 * (seg + 1), *p0 = h->P + 3 * seg, *p1 = h->P + 3 * (seg + 1);
+    const double dH0 = 3 * (zeta * zeta - 1) / 4, dH1 = -3 * (zeta * zeta - 1) / 4;
+    const double dHt0 = (3 * zeta * zeta - 2 * zeta - 1) / 4, dHt1 = (3 * zeta * zeta + 2 * zeta - 1) / 4;
+    for (int k = 0; k < 3; k++) o[k] = p0[k] * dH0 + p1[k] * dH1 + h->cseg[seg] * (t0[k] * dHt0 + t1[k] * dHt1) / 2;
+}
+static double hs_arcLength(const HSpline* h, int seg, double zeta)
+{
+    if (zeta < -1 + SMALL) return 0;
+    int n = (int)(12 * (zeta + 1) / 2); /* label n(12*(zeta+1)/2) */
+    if ((n % 2) > 0) n += 1;
+    if (n < 2) n = 2;
+    const double hh = (zeta + 1) / n;
+    double arcLen = 0, a[3], b[3], d[3];
+    for (int i = 1; i <= n / 2; i++) { /* composite Simpson 1/3 */
+        hs_paramFirstDerivative(h, seg, -1 + (2 * i - 2) * hh, a);
+        hs_paramFirstDerivative(h, seg, -1 + (2 * i - 1) * hh, b);
+        hs_paramFirstDerivative(h, seg, -1 + (2 * i) * hh, d);
+        arcLen += hh * (vmag(a) + 4 * vmag(b) + vmag(d)) / 3;
+    }
+    return arcLen;
+}
+static double hs_localParameter(const HSpline* h, int seg, double arcLen)
+{
+    const double totalArcLength = h->param[seg + 1] - h->param[seg];
+    if (arcLen > totalArcLength - SMALL) return 1;
+    if (arcLen < SMALL) return -1;
+    double residual, zeta0 = -1, zeta1 = 1, zeta2 = 0;
+    do { /* secant iteration on the arc length, :320-338 */
+        const double f0 = hs_arcLength(h, seg, zeta0) - arcLen, f1 = hs_arcLength(h, seg, zeta1) - arcLen;
+        zeta2 = zeta1 - f1 * (zeta1 - zeta0) / (f1 - f0);
+        residual = fabs(zeta2 - zeta1) / 2;
+        zeta0 = zeta1;
+        zeta1 = zeta2;
+    } while (residual > 1e-4);
+    return zeta2;
+}
+static void hs_firstDerivative(const HSpline* h, int seg, double zeta, double* o)
+{
+    if (zeta <= -1) { memcpy(o, h->T + 3 * seg, 24); return; }
+    if (zeta >= 1.0) { memcpy(o, h->T + 3 * (seg + 1), 24); return; }
+    hs_paramFirstDerivative(h, seg, zeta, o);
+    const double m = vmag(o);
+    for (int k = 0; k < 3; k++) o[k] /= m;
+}
+/* dRdScell = HermiteSpline(currentBeamPoints(), currentBeamTangents()).midPointDerivatives() of beam b: [n*3] */
+static void midPointDerivatives(const bf_ctx* c, int64_t b, double* dRdS)
+{
+    const int n = c->nSeg[b];
+    const int64_t c0 = c->cellStart[b], f0 = c->faceStart[b], pl = c->F + b, pr = c->F + c->B + b;
+    double* curCf = (double*)malloc(sizeof(double) * 3 * (n + 1)); /* faces of the beam, left patch .. right patch */
+    double* tang = (double*)malloc(sizeof(double) * 3 * n);
+    double* curC = (double*)malloc(sizeof(double) * 3 * n);
+    double* P = (double*)malloc(sizeof(double) * 3 * (n + 1));
+    double* T = (double*)malloc(sizeof(double) * 3 * (n + 1));
+    double* cseg = (double*)malloc(sizeof(double) * n);
+    double* param = (double*)malloc(sizeof(double) * (n + 1));
+    /* surfaceVectorField curCf(mesh.Cf() + refWf_ + fvc::interpolate(W_)) :1281-1282 */
+    for (int j = 0; j <= n; j++) {
+        const int64_t f = j == 0 ? pl : j == n ? pr : f0 + j - 1;
+        double Wf[3];
+        interpolate(c, c->W, c->Wb, f, Wf);
+        for (int k = 0; k < 3; k++) curCf[3 * j + k] = c->meshCf[3 * f + k] + c->refWf[3 * f + k] + Wf[k];
+    }
+    for (int i = 0; i < n; i++) { /* cell tangents :1284-1313: upper face - lower face, / (mag + SMALL) */
+        double v[3];
+        for (int k = 0; k < 3; k++) v[k] = curCf[3 * (i + 1) + k] - curCf[3 * i + k];
+        const double m = vmag(v) + SMALL;
+        for (int k = 0; k < 3; k++) {
+            tang[3 * i + k] = v[k] / m;
+            curC[3 * i + k] = c->meshC[3 * (c0 + i) + k] + c->refW[3 * (c0 + i) + k] + c->W[3 * (c0 + i) + k]; /* :1315-1316 */
+        }
+    }
+    memcpy(P, curCf, 24);
+    memcpy(P + 3 * n, curCf + 3 * n, 24);
+    for (int j = 1; j < n; j++) { /* HermiteSpline::position(curC[own], tangents[own], curC[nei], tangents[nei], 0) :1320-1331 */
+        const double *p0 = curC + 3 * (j - 1), *p1 = curC + 3 * j, *t0 = tang + 3 * (j - 1), *t1 = tang + 3 * j;
+        const double zeta = 0;
+        const double H0 = (2.0 + zeta) * (1.0 - zeta) * (1.0 - zeta) / 4, H1 = (2.0 - zeta) * (1.0 + zeta) * (1.0 + zeta) / 4;
+        const double Ht0 = (1.0 + zeta) * (1.0 - zeta) * (1.0 - zeta) / 4, Ht1 = -(1.0 - zeta) * (1.0 + zeta) * (1.0 + zeta) / 4;
+        double dv[3];
+        for (int k = 0; k < 3; k++) dv[k] = p1[k] - p0[k];
+        const double cc = vmag(dv);
+        for (int k = 0; k < 3; k++) P[3 * j + k] = p0[k] * H0 + p1[k] * H1 + cc * (Ht0 * t0[k] + Ht1 * t1[k]) / 2;
+    }
+    /* currentBeamTangents: R0 = C + refW + W; snGrad(R0) / mag; start patch *= -1   :1546-1556 */
+    for (int j = 0; j <= n; j++) {
+        double v[3];
+        if (j == 0 || j == n) {
+            const int64_t f = j == 0 ? pl : pr, cell = c0 + (j == 0 ? 0 : n - 1), pb = (j == 0 ? 0 : c->B) + b;
+            for (int k = 0; k < 3; k++) /* boundary of R0: Cf + refW_b (= refWf_b) + W_b */
+                v[k] = ((c->meshCf[3 * f + k] + c->refWf[3 * f + k] + c->Wb[3 * pb + k]) - curC[3 * (cell - c0) + k]) * c->dc[f];
+        } else {
+            const int64_t f = f0 + j - 1;
+            for (int k = 0; k < 3; k++) v[k] = (curC[3 * j + k] - curC[3 * (j - 1) + k]) * c->dc[f];
+        }
+        const double m = vmag(v);
+        for (int k = 0; k < 3; k++) T[3 * j + k] = (j == 0 ? -1 : 1) * (v[k] / m);
+    }
+    /* HermiteSpline(points, tangents): tangents /= mag(tangents); c_ = chord lengths; calcParam() */
+    for (int j = 0; j <= n; j++) {
+        const double m = vmag(T + 3 * j);
+        for (int k = 0; k < 3; k++) T[3 * j + k] /= m;
+    }
+    HSpline h = {n, P, T, cseg, param};
+    for (int i = 0; i < n; i++) {
+        double dv[3];
+        for (int k = 0; k < 3; k++) dv[k] = P[3 * (i + 1) + k] - P[3 * i + k];
+        cseg[i] = vmag(dv);
+    }
+    param[0] = 0.0;
+    for (int i = 1; i <= n; i++) param[i] = param[i - 1] + hs_arcLength(&h, i - 1, 1);
+    for (int i = 0; i < n; i++) { /* calcMidPointDerivatives :83-108 */
+        const double segLen = param[i + 1] - param[i];
+        const double zeta = hs_localParameter(&h, i, segLen / 2);
+        hs_firstDerivative(&h, i, zeta, dRdS + 3 * i);
+    }
+    free(curCf); free(tang); free(curC); free(P); free(T); free(cseg); free(param);
+}
+
+static void addMomentumContributions(bf_ctx* c)
+{
+    if (!c->nContrib) return;
+    double* src = c->source;
+    for (int64_t b = 0; b < c->B; b++) {
+        const int n = c->nSeg[b];
+        const int64_t c0 = c->cellStart[b];
+        const double R = c->radius[b];
+        double* dRdS = (double*)malloc(sizeof(double) * 3 * n);
+        midPointDerivatives(c, b, dRdS);
+        for (int ci = 0; ci < c->nContrib; ci++) {
+            const bf_momentum_contribution* mc = c->contrib + ci;
+            for (int i = 0; i < n; i++) {
+                const int64_t cell = c0 + i;
+                const double *U = c->U + 3 * cell, *d = dRdS + 3 * i;
+                double Ut[3], Un[3], UtHat[3], UnHat[3], res[3] = {0, 0, 0};
+                const double Ud = U[0] * d[0] + U[1] * d[1] + U[2] * d[2];
+                for (int k = 0; k < 3; k++) { Ut[k] = Ud * d[k]; Un[k] = U[k] - Ud * d[k]; }
+                const double mt = vmag(Ut) + SMALL, mn = vmag(Un) + SMALL;
+                for (int k = 0; k < 3; k++) { UtHat[k] = Ut[k] / mt; UnHat[k] = Un[k] / mn; }
+                if (mc->type == BF_CONTRIB_MORISON_DRAG) { /* morisonDragContribution.C:103-176 */
+                    const double Cdn = mc->coeffs[0], Cdt = mc->coeffs[1], rhoFluid = mc->coeffs[2], L = c->L[cell];
+                    const double Fdn = rhoFluid * Cdn * R * L * (Un[0] * Un[0] + Un[1] * Un[1] + Un[2] * Un[2]);
+                    const double Fdt = rhoFluid * Cdt * R * L * (Ut[0] * Ut[0] + Ut[1] * Ut[1] + Ut[2] * Ut[2]);
+                    for (int k = 0; k < 3; k++) res[k] = Fdn * UnHat[k] + Fdt * UtHat[k];
+                } else { /* groundContactContribution.C:111-217 */
+                    const double kN = mc->coeffs[0], cN = mc->coeffs[1], kT = mc->coeffs[2], mu = mc->coeffs[3], groundZ = mc->coeffs[4];
+                    const double z = c->refW[3 * cell + 2] + c->W[3 * cell + 2];
+                    if (z < groundZ) {
+                        const double fn = (2 * R * kN * (groundZ - z)) - (2 * R * cN * (U[2] > 0 ? U[2] : 0));
+                        double ft[3];
+                        if (kT * 2.0 * R * vmag(Ut) >= mu * fabs(fn))
+                            for (int k = 0; k < 3; k++) ft[k] = -mu * fabs(fn) * UtHat[k];
+                        else
+                            for (int k = 0; k < 3; k++) ft[k] = -2.0 * R * kT * Ut[k];
+                        res[0] += ft[0]; res[1] += ft[1]; res[2] += (fn + ft[2]);
+                    }
+                }
+                for (int k = 0; k < 3; k++) src[6 * cell + k] += res[k]; /* Evolve.C:553-556; angularMomentumSource = 0 */
+            }
+        }
+        free(dRdS);
     }
 }
 
@@ -1156,6 +1380,7 @@ int bf_newton_iteration(bf_ctx* c, double sumsq[3])
     assembleMatrixCoefficients(c); /* :190 */
     assembleBoundaryConditions(c); /* Matrix.C:474 */
     addLoadsAndInertia(c);         /* :192-536 */
+    addMomentumContributions(c);   /* :539-571 */
 
     double res = 0; /* EigenOF.C:253-282 with x0 = 0: ||b||^2 */
     for (int64_t i = 0; i < 6 * N; i++) res += c->source[i] * c->source[i];
