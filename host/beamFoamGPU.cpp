@@ -45,7 +45,7 @@ struct Abi {
 #define BF_FN(name) decltype(&::name) name = nullptr;
     BF_FN(bf_create) BF_FN(bf_destroy) BF_FN(bf_last_error) BF_FN(bf_version) BF_FN(bf_backend) BF_FN(bf_num_cells)
     BF_FN(bf_set_field) BF_FN(bf_get_field) BF_FN(bf_set_distributed_loads) BF_FN(bf_set_point_forces)
-    BF_FN(bf_set_bc_values) BF_FN(bf_begin_step) BF_FN(bf_evolve) BF_FN(bf_launch_count)
+    BF_FN(bf_set_bc_values) BF_FN(bf_set_momentum_contributions) BF_FN(bf_begin_step) BF_FN(bf_evolve) BF_FN(bf_launch_count)
 #undef BF_FN
     void load(const std::string& path)
     {
@@ -56,7 +56,7 @@ struct Abi {
     if (!name) fatal(std::string("symbol ") + #name + " is missing from " + path);
         BF_SYM(bf_create) BF_SYM(bf_destroy) BF_SYM(bf_last_error) BF_SYM(bf_version) BF_SYM(bf_backend) BF_SYM(bf_num_cells)
         BF_SYM(bf_set_field) BF_SYM(bf_get_field) BF_SYM(bf_set_distributed_loads) BF_SYM(bf_set_point_forces)
-        BF_SYM(bf_set_bc_values) BF_SYM(bf_begin_step) BF_SYM(bf_evolve) BF_SYM(bf_launch_count)
+        BF_SYM(bf_set_bc_values) BF_SYM(bf_set_momentum_contributions) BF_SYM(bf_begin_step) BF_SYM(bf_evolve) BF_SYM(bf_launch_count)
 #undef BF_SYM
     }
 };
@@ -161,7 +161,7 @@ struct BeamCase {
     std::string dir;
     int nBeams = 0;
     std::vector<int32_t> nSeg;
-    vec length, A, Iyy, Izz, J, E, G, rho;
+    vec length, A, Iyy, Izz, J, E, G, rho, R;
     std::vector<PatchField> W[2], Th[2]; // [end][beam]
     int scheme = BF_SCHEME_STEADY;
     double beta = 0.25, gamma = 0.5;
@@ -172,6 +172,8 @@ struct BeamCase {
     vec q = {0, 0, 0}, m = {0, 0, 0}; // uniform internalField of 0/q, 0/m
     std::vector<PointForce> pointForces;
     vec refL;                          // [nBeams*9], identity unless setInitialPositionBeam ran
+    vec translation;                   // [nBeams*3]
+    std::vector<bf_momentum_contribution> contributions; // constant/beamMomentumContributionProperties
     bool rotated = false;
     double deltaT = 1, endTime = 1;
     int device = 0;
@@ -195,15 +197,16 @@ void readBeamProperties(BeamCase& c)
         const std::string cs = d.word("crossSectionModel");
         const Dict& cd = d.subDict(cs + "CrossSectionModelDict");
         const double sA = cd.scalarOr("scalingArea", 1.0), sI = cd.scalarOr("scalingSecondMomentArea", 1.0);
-        double A, Ixx, Iyy;
+        double A, Ixx, Iyy, R;
         if (cs == "circle") { // circle.H:123-144
             const double r = cd.scalar("radius");
-            A = sA * M_PI * r * r; Ixx = Iyy = sI * M_PI * r * r * r * r / 4;
+            A = sA * M_PI * r * r; Ixx = Iyy = sI * M_PI * r * r * r * r / 4; R = r;
         } else if (cs == "rectangle") { // rectangle.H:145-166
             const double bb = cd.scalar("b"), h = cd.scalar("h");
-            A = sA * bb * h; Ixx = sI * bb * h * h * h / 12; Iyy = sI * h * bb * bb * bb / 12;
+            A = sA * bb * h; Ixx = sI * bb * h * h * h / 12; Iyy = sI * h * bb * bb * bb / 12; R = h / 2; // rectangle.H:133-136
         } else fatal("Unknown crossSectionModel " + cs + " (circle, rectangle are supported)");
         c.A.push_back(A);
+        c.R.push_back(R);
         c.Iyy.push_back(Ixx); // beamModel.H:449-489: Iyy(b) = crossSection.Ixx(), Izz(b) = crossSection.Iyy(), J = IT()
         c.Izz.push_back(Iyy);
         c.J.push_back(cs == "circle" ? 2 * Ixx : Ixx + Iyy);
@@ -304,17 +307,46 @@ void readCase(BeamCase& c)
     // what setInitialPositionBeam left behind
     c.refL.assign((size_t)c.nBeams * 9, 0.0);
     for (int b = 0; b < c.nBeams; b++) c.refL[9 * b] = c.refL[9 * b + 4] = c.refL[9 * b + 8] = 1.0;
+    c.translation.assign((size_t)c.nBeams * 3, 0.0);
     const std::string ip = c.dir + "/constant/initialPositionBeam";
     if (exists(ip)) {
-        const auto d = foam::readDictionary(ip);
+        const auto d_ = foam::readDictionary(ip);
         for (int b = 0; b < c.nBeams; b++) {
             const std::string z = "beam_" + std::to_string(b);
-            if (!d->found(z)) continue;
-            const vec T = d->subDict(z).vector("rotation");
+            if (!d_->found(z)) continue;
+            const vec T = d_->subDict(z).vector("rotation");
             if (T.size() != 9) fatal("rotation of " + z + " is not a tensor in " + ip);
             for (int k = 0; k < 9; k++) c.refL[9 * b + k] = T[k];
+            const vec d = d_->subDict(z).vector("translation");
+            for (int k = 0; k < 3; k++) c.translation[3 * b + k] = d[k];
             c.rotated = true;
         }
+    }
+}
+
+// constant/beamMomentumContributionProperties (CTL.C:1137-1182): beamMomentumContributions ( name { beamMomentumContributionType T; TCoeffs {..} } )
+void readMomentumContributions(BeamCase& c)
+{
+    const std::string f = c.dir + "/constant/beamMomentumContributionProperties";
+    if (!exists(f)) return;
+    const auto d = foam::readDictionary(f);
+    const foam::Entry& e = d->lookup("beamMomentumContributions");
+    if (e.values.empty() || e.values[0].kind != Value::LIST) fatal("keyword beamMomentumContributions is not a list in " + f);
+    for (const Value& v : e.values[0].list) {
+        if (v.kind != Value::NAMED_DICT) fatal("entries of beamMomentumContributions must be dictionaries in " + f);
+        const std::string type = v.dict->word("beamMomentumContributionType");
+        const Dict& k = v.dict->subDict(type + "Coeffs");
+        bf_momentum_contribution mc;
+        memset(&mc, 0, sizeof mc);
+        if (type == "morisonDrag") { // morisonDragContribution.C:48-75
+            mc.type = BF_CONTRIB_MORISON_DRAG;
+            mc.coeffs[0] = k.scalar("Cdn"); mc.coeffs[1] = k.scalar("Cdt"); mc.coeffs[2] = k.scalar("rhoFluid");
+        } else if (type == "groundContact") { // groundContactContribution.C:48-83
+            mc.type = BF_CONTRIB_GROUND_CONTACT;
+            mc.coeffs[0] = k.scalar("kNormal"); mc.coeffs[1] = k.scalar("cNormal"); mc.coeffs[2] = k.scalar("kTangential");
+            mc.coeffs[3] = k.scalar("muFriction"); mc.coeffs[4] = k.scalar("groundZ");
+        } else fatal("Unknown beamMomentumContribution type " + type + "\n\nValid beamMomentumContribution types are :\n(groundContact morisonDrag)");
+        c.contributions.push_back(mc);
     }
 }
 
@@ -395,6 +427,7 @@ int setInitialPositionBeam(BeamCase& c, const std::string& zone, const std::stri
 int beamFoam(BeamCase& c, const std::string& libPath, int maxSteps)
 {
     readCase(c);
+    readMomentumContributions(c);
     Abi abi;
     abi.load(libPath);
     const int B = c.nBeams;
@@ -441,6 +474,8 @@ int beamFoam(BeamCase& c, const std::string& libPath, int maxSteps)
             }
         if (any) CHECK(abi.bf_set_field(ctx, isW ? BF_FIELD_W : BF_FIELD_THETA, nullptr, lr[0].data(), lr[1].data()));
     }
+    if (!c.contributions.empty())
+        CHECK(abi.bf_set_momentum_contributions(ctx, (int32_t)c.contributions.size(), c.contributions.data(), c.R.data(), c.translation.data()));
     const int64_t nCells = abi.bf_num_cells(ctx);
     if (c.hasQ || c.hasM) {
         vec q, m;

@@ -233,6 +233,59 @@ coupledTotalLagNewtonRaphsonBeamGPU::coupledTotalLagNewtonRaphsonBeamGPU(Time& r
         reinterpret_cast<const double*>(q().primitiveField().cdata()),
         reinterpret_cast<const double*>(m().primitiveField().cdata())
     ), "bf_set_distributed_loads");
+
+    // constant/beamMomentumContributionProperties (CTL.C:1137-1182): the base class keeps its list private, so the
+    // dictionary is read again; only the coefficients cross the ABI, the per-cell arithmetic runs on the device
+    IOobject mcHeader("beamMomentumContributionProperties", runTime.constant(), runTime, IOobject::MUST_READ);
+    if (mcHeader.typeHeaderOk<dictionary>(true))
+    {
+        IOdictionary mcDict(mcHeader);
+        const PtrList<entry> entries(mcDict.lookup("beamMomentumContributions"));
+        List<bf_momentum_contribution> list(entries.size());
+        forAll(entries, i)
+        {
+            const dictionary& e = entries[i].dict();
+            const word type(e.lookup("beamMomentumContributionType"));
+            const dictionary& k = e.subDict(type + "Coeffs");
+            bf_momentum_contribution& mc = list[i];
+            std::memset(&mc, 0, sizeof(mc));
+            if (type == "morisonDrag")
+            {
+                mc.type = BF_CONTRIB_MORISON_DRAG;
+                mc.coeffs[0] = readScalar(k.lookup("Cdn"));
+                mc.coeffs[1] = readScalar(k.lookup("Cdt"));
+                mc.coeffs[2] = readScalar(k.lookup("rhoFluid"));
+            }
+            else if (type == "groundContact")
+            {
+                mc.type = BF_CONTRIB_GROUND_CONTACT;
+                mc.coeffs[0] = readScalar(k.lookup("kNormal"));
+                mc.coeffs[1] = readScalar(k.lookup("cNormal"));
+                mc.coeffs[2] = readScalar(k.lookup("kTangential"));
+                mc.coeffs[3] = readScalar(k.lookup("muFriction"));
+                mc.coeffs[4] = readScalar(k.lookup("groundZ"));
+            }
+            else
+            {
+                FatalErrorInFunction << "Unknown beamMomentumContribution type " << type << abort(FatalError);
+            }
+        }
+        // R(bI) and the rigid translation of each beam: refW = (T & C) + translate - C  =>  translate = refW_b + C_b - T & C_b
+        const volVectorField& refW = field<volVectorField>("refW");
+        const volTensorField& refLambda = field<volTensorField>("refLambda");
+        scalarField radius(nBeams());
+        vectorField translate(nBeams(), vector::zero);
+        forAll(radius, bI)
+        {
+            radius[bI] = R(bI);
+            const label c0 = startCells()[bI];
+            translate[bI] = refW[c0] + mesh().C()[c0] - (refLambda[c0] & mesh().C()[c0]);
+        }
+        check(bf_set_momentum_contributions
+        (
+            ctx_, list.size(), list.cdata(), radius.cdata(), reinterpret_cast<const double*>(translate.cdata())
+        ), "bf_set_momentum_contributions");
+    }
 }
 
 coupledTotalLagNewtonRaphsonBeamGPU::~coupledTotalLagNewtonRaphsonBeamGPU()

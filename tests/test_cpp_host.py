@@ -7,6 +7,7 @@ the C++ host runs its Allrun, and the histories it writes must equal what the Py
 through the same library.  CPU tests bind the oracle library (test infrastructure); the GPU test binds
 libbeamgpu.so.  When the reference checkout is present its shipped tutorial directories are run UNCHANGED.
 """
+import dataclasses
 import os
 import shutil
 import subprocess
@@ -128,12 +129,24 @@ def write_case(case, caseDir, rotateAngle=None):
         f.write(HEADER.format(cls="dictionary", obj="fvSchemes"))
         f.write(f"ddtSchemes\n{{\n    default {case.d2dt2Scheme};\n}}\nd2dt2Schemes\n{{\n    default      {case.d2dt2Scheme};\n}}\n"
                 "laplacianSchemes\n{\n    default         none;}\nsnGradSchemes\n{\n    default         orthogonal;\n}\n")
+    if case.momentumContributions:
+        with open(os.path.join(caseDir, "constant", "beamMomentumContributionProperties"), "w") as f:
+            f.write(HEADER.format(cls="dictionary", obj="beamMomentumContributionProperties"))
+            f.write("beamMomentumContributions\n(\n")
+            for k, mc in enumerate(case.momentumContributions):
+                t = type(mc).__name__.replace("Contribution", "")
+                f.write(f"    contribution{k}\n    {{\n        beamMomentumContributionType {t};\n        {t}Coeffs\n        {{\n")
+                for key, val in dataclasses.asdict(mc).items():
+                    f.write(f"            {key} {val!r};\n")
+                f.write("        }\n    }\n")
+            f.write(");\n")
     with open(os.path.join(caseDir, "Allrun"), "w") as f:
         f.write("#!/bin/bash\n. $WM_PROJECT_DIR/bin/tools/RunFunctions\napplication=`getApplication`\n\nrunApplication createBeamMesh\n")
         if rotateAngle is not None:
             axis, deg = rotateAngle
             for b in range(B):
-                f.write(f"runApplication -s beam_{b} setInitialPositionBeam -cellZone beam_{b} -translate '(0 {0.4 * b} 0)' "
+                tr = np.broadcast_to(np.zeros(3) if case.initialTranslation is None else case.initialTranslation, (B, 3))[b]
+                f.write(f"runApplication -s beam_{b} setInitialPositionBeam -cellZone beam_{b} -translate '({float(tr[0])!r} {float(tr[1])!r} {float(tr[2])!r})' "
                         f"-rotateAngle '(({axis[0]} {axis[1]} {axis[2]}) {deg})'\n")
         f.write("\n# run beamFoam\nrunApplication $application\n")
 
@@ -167,7 +180,14 @@ def _cases():
     c3.section = ("circle", dict(radius=0.65828153))
     c4 = cases.cantilever(nSegments=20, deltaT=0.02)
     c4.section = ("circle", dict(radius=0.2))
-    return [(c1, ((0, -1, 0), 90), 6), (c2, None, 1), (c3, None, 5), (c4, None, 5)]
+    from beamfoam_b200.beamMomentumContribution import groundContactContribution, morisonDragContribution
+    c5 = dataclasses.replace(cases.multiBeamDensity(2, 10), R=0.1, deltaT=2e-3,
+                             initialTranslation=np.array([[0.0, 0.0, 0.1], [0.0, 0.4, 0.1]]),
+                             momentumContributions=[morisonDragContribution(1.2, 0.05, 1000.0),
+                                                    groundContactContribution(2e3, 50.0, 4e2, 0.3, 1.2)])
+    c5.section = ("rectangle", dict(b=0.2, h=0.2, nx=1, ny=1))
+    c5.name = "withMomentumContributions"
+    return [(c1, ((0, -1, 0), 90), 6), (c2, None, 1), (c3, None, 5), (c4, None, 5), (c5, ((0, -1, 0), 90), 6)]
 
 
 def _compare(exe, libPath, lib, tmp_path, tol):
