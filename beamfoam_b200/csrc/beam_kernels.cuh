@@ -371,6 +371,9 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 #ifndef BEAM_PF_DIST
 #define BEAM_PF_DIST 1 // cells of look-ahead of the backward sweep's L2 prefetch
 #endif
+#ifndef BEAM_PFCELL_DIST
+#define BEAM_PFCELL_DIST 1 // the L2 prefetch of the Newmark cell rows runs this many cells ahead of their cp.async
+#endif
 #ifndef BEAM_MIN_BLOCKS
 #define BEAM_MIN_BLOCKS 2
 #endif
@@ -394,8 +397,14 @@ enum {
     B_LF = 3,    //   Lambdaf & refLambdaf of face i+1, quaternion (4)
     B_K = 7, B_Q = 10, B_M = 13, //   K, Q, M of face i+1
     B_ROWS = 16,
+    // second use of the same buffer inside a cell (Newmark): the rows of cell i that the inertia terms read, brought in
+    // by the TMA engine while the face part runs (completion on the warp's second mbarrier)
+    C_LAM = 0,   //   Lambda of cell i, quaternion (4)
+    C_AC = 4, C_OM = 7, C_DOM = 10, //   Accl, Omega*, dotOmega of cell i
+    C_U = 13,    //   U* of cell i (only read on the first iteration of a time step)
     R_DC = R_BUF + B_ROWS, // the carry: (nei part of d_i) - l_{i-1} & uPrime_{i-1}, row-major 6x6 (36)
-    R_TOTAL = R_DC + 36
+    R_CI = R_DC + 36,      // diag CIRho (3): a global load per cell was an exposed L2 round trip (L1 is carved out for this slab)
+    R_TOTAL = R_CI + 3     // 112 rows = 28 KB per warp: two 4-warp blocks per SM fill the 228 KB exactly
 };
 #define WARP_SMEM_DOUBLES (R_TOTAL * 32)
 #define SMEM_HEADER_BYTES 128 // one mbarrier (8 B) per warp
@@ -461,20 +470,44 @@ DEV void bulkLoad(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t
                      smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
 }
 
-// Prefetch of cell i for the whole warp: one elected lane arms the warp's mbarrier with the byte count and
-// issues one bulk copy per array (every address is warp-uniform).  Face arrays are read at face i+1, W at
-// cell i+1, the Newmark cell arrays at cell i.
+// Per-lane asynchronous copies global -> shared (LDGSTS): no register holds the value in flight, and a lane only ever
+// touches its own column of the slab, so no warp-level synchronisation is needed around them.
+DEV void cpAsync8(double* dstSmem, const double* srcGlobal)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal) : "memory");
+}
+DEV void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The warp's 16-row buffer is filled twice per cell:
+//   fwdPrefetchFace(i): face i+1 and W of cell i+1, by the TMA engine (one elected lane, one bulk copy per array,
+//                       completion on the warp's mbarrier) -- issued in the middle of cell i-1, waited for at the top
+//                       of cell i: from DRAM, with two thirds of a cell to cover it;
+//   fwdPrefetchCell(i): the Newmark rows of cell i, by per-lane cp.async from L2 (they are L2-prefetched half a cell
+//                       earlier) -- issued at the top of cell i as soon as the face rows are in registers, waited for
+//                       after the face part.  A bulk copy is too slow for this window (its completion was 0.9 us late
+//                       per cell), and plain loads "issued early" do not work either: at 255 registers ptxas sinks them
+//                       to their first use and the warp sits out an L2 round trip per cell (17 % of the sweep).
+DEV int laneId()
+{
+    int l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); // re-read where needed: a value kept across the cell gets spilled
+    return l;
+}
 template <int SCHEME>
-DEV void fwdPrefetch(const BeamParams& p, size_t T, double* warpSm, uint64_t* bar, int lane, int i)
+DEV void fwdPrefetchFace(const BeamParams& p, size_t T, double* warpSm, uint64_t* bar, int i)
 {
     const int Rc = p.nmax, Rf = p.nmax + 1;
-    if (SCHEME == BFK_NEWMARK) { // rows of cell i read by plain loads late in the assembly: pull them closer now
-        const size_t n3 = tileRow(T, Rc, i, 3, lane);
-        pfNm(p.Lam + tileRow(T, Rc, i, 4, 0) + 4 * lane); // 4 rows x 32 doubles: one double in four per lane
-        pfNm(p.Ac + n3); pfNm(p.Ac + n3 + 2 * TS);
-        pfNm(p.Om + n3); pfNm(p.Om + n3 + 2 * TS);
-        pfNm(p.dOm + n3); pfNm(p.dOm + n3 + 2 * TS);
-        if (p.first) { pfNm(p.U + n3); pfNm(p.U + n3 + 2 * TS); }
+    const int lane = laneId();
+    if (SCHEME == BFK_NEWMARK) { // the cell rows of the same cell: pull them into L2 now, the bulk copy follows a phase later
+        // one address per lane and array: nc rows x 32 doubles are contiguous, lane l touches double nc*l, so every
+        // 32-byte sector of the nc x 256 B run is requested once
+        const int ic = min(i + BEAM_PFCELL_DIST - 1, Rc - 1);
+        const size_t n3 = tileRow(T, Rc, ic, 3, 0) + 3 * lane;
+        pfNm(p.Lam + tileRow(T, Rc, ic, 4, 0) + 4 * lane);
+        pfNm(p.Ac + n3);
+        pfNm(p.Om + n3);
+        pfNm(p.dOm + n3);
+        if (p.first) pfNm(p.U + n3);
     }
     if (lane != 0) return;
     const bool hasW = i + 1 < p.nmax; // no cell i+1 in the slab for the last row
@@ -485,6 +518,24 @@ DEV void fwdPrefetch(const BeamParams& p, size_t T, double* warpSm, uint64_t* ba
     bulkLoad(buf + B_K * 32, p.K + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
     bulkLoad(buf + B_Q * 32, p.Q + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
     bulkLoad(buf + B_M * 32, p.M + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
+}
+DEV void fwdPrefetchCell(const BeamParams& p, size_t T, double* sm, int i)
+{
+    const int Rc = p.nmax, lane = laneId();
+    const size_t c3 = tileRow(T, Rc, i, 3, lane), c4 = tileRow(T, Rc, i, 4, lane);
+    double* buf = sm + (size_t)R_BUF * 32;
+#pragma unroll
+    for (int k = 0; k < 4; k++) cpAsync8(buf + (C_LAM + k) * 32, p.Lam + c4 + k * TS);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        cpAsync8(buf + (C_AC + k) * 32, p.Ac + c3 + k * TS);
+        cpAsync8(buf + (C_OM + k) * 32, p.Om + c3 + k * TS);
+        cpAsync8(buf + (C_DOM + k) * 32, p.dOm + c3 + k * TS);
+    }
+    if (p.first) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) cpAsync8(buf + (C_U + k) * 32, p.U + c3 + k * TS);
+    }
 }
 
 // Boundary closure is executed for 2 of the n cells of a beam; keeping it out of line keeps its
@@ -574,23 +625,34 @@ DEV void pointForceSource(const BeamParams& p, const int b, const int i, double*
 // them after the face part.
 struct CellIn {
     Q4 ql;
-    V3 Ac, Om, dOm;
+    V3 Ac, Om, dOm, U;
 };
+DEV CellIn loadCellInSm(const double* sm, bool first)
+{
+    CellIn c;
+    c.ql = smLdq(sm, R_BUF + C_LAM);
+    c.Ac = smLd3(sm, R_BUF + C_AC);
+    c.Om = smLd3(sm, R_BUF + C_OM);
+    c.dOm = smLd3(sm, R_BUF + C_DOM);
+    c.U = first ? smLd3(sm, R_BUF + C_U) : v3(0, 0, 0);
+    return c;
+}
 template <int SCHEME, bool EARLY>
 DEV CellIn loadCellIn(const BeamParams& p, const int b, const int i)
 {
     CellIn c;
     c.ql = q4(1, 0, 0, 0);
-    c.Ac = c.Om = c.dOm = v3(0, 0, 0);
+    c.Ac = c.Om = c.dOm = c.U = v3(0, 0, 0);
     if (SCHEME == BFK_NEWMARK) {
         const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31), c4 = tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31);
         if (EARLY) { c.ql = ldqEarly(p.Lam, c4, TS); c.Ac = ld3Early(p.Ac, c3, TS); c.Om = ld3Early(p.Om, c3, TS); c.dOm = ld3Early(p.dOm, c3, TS); }
         else { c.ql = ldq(p.Lam, c4, TS); c.Ac = ld3(p.Ac, c3, TS); c.Om = ld3(p.Om, c3, TS); c.dOm = ld3(p.dOm, c3, TS); }
+        if (p.first) c.U = ld3(p.U, c3, TS);
     }
     return c;
 }
 template <int SCHEME>
-DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const double dZ, const double ARho,
+DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const double dZ, const double ARho, const V3 CI,
                             const CellIn& cell, double (&Dc)[6][6], double (&src)[6])
 {
     const double dt = p.dt, gamma = p.gamma;
@@ -598,7 +660,7 @@ DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const
     const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31);
     const double Lcell = p.Lc ? p.Lc[tileRow((size_t)(b >> 5), p.nmax, i, 1, b & 31)] : dZ;
     if (p.q) subV(src, 0, Lcell * ld3(p.q, c3, TS));
-    subV(src, 0, Lcell * ld3(p.weight, b, p.Bpad));
+    if (p.weight) subV(src, 0, Lcell * ld3(p.weight, b, p.Bpad)); // null when no beam has a self-weight
     if (p.m) subV(src, 3, Lcell * ld3(p.m, c3, TS));
     if (p.pfSrc) { // point forces and momentum contributions, formed by their pre-kernels
         const size_t c6 = tileRow((size_t)(b >> 5), p.nmax, i, 6, b & 31);
@@ -611,7 +673,7 @@ DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const
         const V3 OmS = cell.Om; // Omega*
         if (p.first) {
             const V3 Ao = Ac, dOo = dOm;
-            const V3 Uo = ld3(p.U, c3, TS) + p.gdtPrev * Ao, Oo = OmS + p.gdtPrev * dOo; // end of the previous step
+            const V3 Uo = cell.U + p.gdtPrev * Ao, Oo = OmS + p.gdtPrev * dOo; // end of the previous step
             const double k1 = p.nk1, k2 = p.nk2;
             Ac = v3(-k1 * Uo.x - k2 * Ao.x, -k1 * Uo.y - k2 * Ao.y, -k1 * Uo.z - k2 * Ao.z);
             dOm = v3(-k1 * Oo.x - k2 * dOo.x, -k1 * Oo.y - k2 * dOo.y, -k1 * Oo.z - k2 * dOo.z);
@@ -621,7 +683,6 @@ DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const
         // QRho = ARho L Accl, MRho = L Lambda (CI dotOmega + Omega x CI Omega) :369-419;  QRhoCoeff, MRhoCoeff :459-535:
         //   MRhoCoeff/L = S(a) + g1 (S(Lambda CI Omega) - Lambda S(Omega) CI Lambda.T()) - g2 Lambda CI Lambda.T()
         //               = S(a + g1 Lambda CI Omega) + Lambda (-(g1 S(Omega) + g2 I) CI Lambda.T()),  g1 = gamma/(beta dt), g2 = 1/(beta dt^2)
-        const V3 CI = ld3(p.CI, b, p.Bpad);
         const V3 CIOm = cmul(CI, Om), CIdO = cmul(CI, dOm);
         const V3 w = v3(fma(-Om.z, CIOm.y, fma(Om.y, CIOm.z, CIdO.x)), fma(-Om.x, CIOm.z, fma(Om.z, CIOm.x, CIdO.y)),
                         fma(-Om.y, CIOm.x, fma(Om.x, CIOm.y, CIdO.z)));
@@ -648,7 +709,6 @@ DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const
         const V3 U = ld3(p.U, c3, TS), Om = ld3(p.Om, c3, TS);
         // on the first iteration of a step the old-time level IS the current one (the backward sweep stores it)
         const V3 Uold = p.first ? U : ld3(p.Uold, c3, TS), Omold = p.first ? Om : ld3(p.Omold, c3, TS);
-        const V3 CI = ld3(p.CI, b, p.Bpad);
         const V3 CIOm = cmul(CI, Om);
         const V3 gyro = cross(Om, CIOm);
         const V3 a = mul(Lm, cmul(CI, idt * (Om - Omold)) + gyro);
@@ -669,22 +729,16 @@ DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const
     }
 }
 
-// Assembly of cell i (first half of a forward step).  Reads the prefetch buffer (face i+1,
-// W_{i+1}, Newmark state of cell i), adds the own part of d_i and the loads/inertia to the
-// carry Dc, forms source_i, and parks the face tensors in the stash.  LAST = the cell whose right
-// face is the right patch: it closes the patch instead of an internal face.
-template <int SCHEME, bool LAST>
-DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, const int i, const double dZ,
-                     const double dcI, const double h, const double ARho, const FaceIn& in, double (&Dc)[6][6],
-                     double (&src)[6], V3& Wi, double& res)
+// Assembly of cell i, face part (first third of a forward step).  Takes the rows of face i+1 and W_{i+1} (from the
+// prefetch buffer, already in registers), adds the own part of d_i to the carry Dc, starts source_i, and parks the face
+// tensors in the stash.  LAST = the cell whose right face is the right patch: it closes the patch instead of an
+// internal face.  The loads and inertia of the cell follow in addLoadsAndInertia once its Newmark rows have arrived.
+template <bool LAST>
+DEV void fwdFacePart(const BeamParams& p, const int b, double* __restrict__ sm, const double dcI, const double h,
+                     const FaceIn& in, double (&Dc)[6][6], double (&src)[6], V3& Wi)
 {
     // Dc is an OUTPUT: each 3x3 block of the carry is fetched from the stash (R_DC) where its first
     // contribution is added
-#ifdef BEAM_NO_EARLY_LOADS
-    const CellIn cell = loadCellIn<SCHEME, false>(p, b, i);
-#else
-    const CellIn cell = loadCellIn<SCHEME, true>(p, b, i);
-#endif
 #pragma unroll
     for (int r = 0; r < 6; r++) src[r] = smLd(sm, R_SC + r);
     if (!LAST) {
@@ -760,9 +814,6 @@ DEV void fwdAssemble(const BeamParams& p, const int b, double* __restrict__ sm, 
             for (int c = 0; c < 6; c++) Dc[r][c] = D36[6 * r + c];
         }
     }
-    addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, cell, Dc, src);
-#pragma unroll
-    for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
 }
 
 // Elimination step of cell i (second half): D'_i = Dc is factored by 2x2 block elimination over
@@ -880,18 +931,63 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
 // its patch code and stack arrays stay out of the register allocation of the steady-state loop.
 template <int SCHEME>
 __device__ __noinline__ double fwdLastCell(const BeamParams& p, const int b, double* __restrict__ sm, const int i,
-                                           const double dZ, const double ARho, V3 Wi)
+                                           const double dZ, const double ARho, V3 Wi, const CellIn* cell)
 {
     double Dc[6][6], src[6], res = 0.0;
     FaceIn none;
     none.Wn = none.K = none.Q = none.M = v3(0, 0, 0); none.qf = q4(1, 0, 0, 0);
-    fwdAssemble<SCHEME, true>(p, b, sm, i, dZ, 1.0 / dZ, 0.5 * dZ, ARho, none, Dc, src, Wi, res);
+    fwdFacePart<true>(p, b, sm, 1.0 / dZ, 0.5 * dZ, none, Dc, src, Wi);
+    addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, smLd3(sm, R_CI), *cell, Dc, src);
+#pragma unroll
+    for (int r = 0; r < 6; r++) res += src[r] * src[r];
     fwdEliminate<true>(p, b, sm, i, Dc, src);
     return res;
 }
 
-// Forward sweep of the 32 beams of one warp.  sm = the warp's slab + lane; bar = the warp's mbarrier.
-// phase = number of buffer fills this warp's mbarrier has completed so far (its parity selects the wait).
+// One forward step for a cell that is not interior in every lane of the warp (see forwardSweep): same protocol on the
+// two barriers, per-lane branches around the per-lane parts.  Out of line: it runs once per beam in a uniform bundle.
+template <int SCHEME>
+__device__ __noinline__ void fwdCellGeneric(const BeamParams& p, const int b, double* __restrict__ warpSm, uint64_t* bar,
+                                            const int i, const int nW, uint32_t* phase, V3* WiIO, double* resIO)
+{
+    const size_t T = (size_t)(b >> 5);
+    double* sm = warpSm + (threadIdx.x & 31);
+    V3 Wi = *WiIO;
+    double res = 0.0;
+    mbarWait(bar, *phase & 1u);
+    const FaceIn in = loadFaceIn(sm);
+    __syncwarp();
+    if (SCHEME == BFK_NEWMARK) fwdPrefetchCell(p, T, sm, i);
+    else if (i + 1 < nW) fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
+    const int nb = (int)smLd(sm, R_N); // cells of this lane's beam
+    const bool interior = i < nb - 1;  // a cell with an internal face on its right
+    double src[6], Dc[6][6];
+    if (interior) {
+        const double dz = smLd(sm, R_DZ);
+        fwdFacePart<false>(p, b, sm, rcpFast(dz), 0.5 * dz, in, Dc, src, Wi);
+    }
+    CellIn cell;
+    if (SCHEME == BFK_NEWMARK) {
+        cpAsyncWaitAll();
+        cell = loadCellInSm(sm, p.first != 0);
+        __syncwarp();
+        if (i + 1 < nW) fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
+    } else
+        cell = loadCellIn<SCHEME, false>(p, b, i);
+    *phase += 1;
+    if (interior) {
+        addLoadsAndInertia<SCHEME>(p, b, i, smLd(sm, R_DZ), smLd(sm, R_ARHO), smLd3(sm, R_CI), cell, Dc, src);
+#pragma unroll
+        for (int r = 0; r < 6; r++) res += src[r] * src[r];
+        fwdEliminate<false>(p, b, sm, i, Dc, src);
+    } else if (i == nb - 1)
+        res += fwdLastCell<SCHEME>(p, b, sm, i, smLd(sm, R_DZ), smLd(sm, R_ARHO), Wi, &cell);
+    *WiIO = Wi;
+    *resIO += res;
+}
+
+// Forward sweep of the 32 beams of one warp.  sm = the warp's slab + lane; bar = the warp's mbarrier for the face rows.
+// phase = number of cells this warp has processed so far: the barrier completes once per cell, its parity selects the wait.
 template <int SCHEME>
 DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ warpSm, uint64_t* bar, uint32_t& phase)
 {
@@ -904,7 +1000,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
     const int n = live ? p.nSeg[b] : 0;
     const int nW = __reduce_max_sync(0xffffffffu, n); // cells of the longest beam of the warp
     __syncwarp(); // (persistent blocks) every lane has left the previous tile's buffer
-    if (nW > 0) fwdPrefetch<SCHEME>(p, T, warpSm, bar, lane, 0);
+    if (nW > 0) fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, 0);
 
     {
         const M3 refL = ld9(p.refL, b, s);
@@ -915,6 +1011,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
         smSt(sm, R_N, (double)n);
         smSt3(sm, R_CQ, ld3(p.CQ, b, s));
         smSt3(sm, R_CM, ld3(p.CM, b, s));
+        smSt3(sm, R_CI, SCHEME != BFK_STEADY ? ld3(p.CI, b, s) : v3(0, 0, 0));
 #pragma unroll
         for (int r = 0; r < 6; r++) smSt(sm, R_LB + r, 0.0);
     }
@@ -936,21 +1033,36 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
             for (int c = 0; c < 6; c++) smSt(sm, R_DC + 6 * r + c, D36[6 * r + c]);
         }
     }
-    for (int i = 0; i < nW; i++) {
+    // Cells 0 .. nFast-1 have an internal face on their right in EVERY lane of the warp: straight-line code, the
+    // warp-collective steps (barrier waits, buffer hand-over) sit between the per-lane parts without any divergence.
+    // The remaining cells (the last cell of each beam; all cells past the shortest beam of a ragged warp) take the
+    // generic out-of-line step.
+    const int nFast = __reduce_min_sync(0xffffffffu, n) - 1;
+    int i = 0;
+    for (; i < nFast; i++) {
         mbarWait(bar, phase & 1u);
-        phase++;
         const FaceIn in = loadFaceIn(sm);
-        __syncwarp(); // every lane holds its buffer rows in registers: refill the buffer for the next cell now
-        if (i + 1 < nW) fwdPrefetch<SCHEME>(p, T, warpSm, bar, lane, i + 1);
-        const int nb = (int)smLd(sm, R_N); // cells of this lane's beam
-        if (i < nb - 1) { // a cell with an internal face on its right
-            double src[6], Dc[6][6];
-            const double dz = smLd(sm, R_DZ);
-            fwdAssemble<SCHEME, false>(p, b, sm, i, dz, rcpFast(dz), 0.5 * dz, smLd(sm, R_ARHO), in, Dc, src, Wi, res);
-            fwdEliminate<false>(p, b, sm, i, Dc, src);
-        } else if (i == nb - 1)
-            res += fwdLastCell<SCHEME>(p, b, sm, i, smLd(sm, R_DZ), smLd(sm, R_ARHO), Wi);
+        __syncwarp(); // every lane holds its buffer rows in registers: the buffer is free for the next fill
+        if (SCHEME == BFK_NEWMARK) fwdPrefetchCell(p, T, sm, i);
+        else fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
+        double src[6], Dc[6][6];
+        const double dz = smLd(sm, R_DZ);
+        fwdFacePart<false>(p, b, sm, rcpFast(dz), 0.5 * dz, in, Dc, src, Wi);
+        CellIn cell;
+        if (SCHEME == BFK_NEWMARK) { // the Newmark rows of cell i have arrived; hand the buffer to face i+2 / cell i+1
+            cpAsyncWaitAll();
+            cell = loadCellInSm(sm, p.first != 0);
+            __syncwarp();
+            fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
+        } else
+            cell = loadCellIn<SCHEME, false>(p, b, i);
+        phase++;
+        addLoadsAndInertia<SCHEME>(p, b, i, dz, smLd(sm, R_ARHO), smLd3(sm, R_CI), cell, Dc, src);
+#pragma unroll
+        for (int r = 0; r < 6; r++) res += src[r] * src[r]; // ||source||^2 (EigenOF.C:253-282, x0 = 0)
+        fwdEliminate<false>(p, b, sm, i, Dc, src);
     }
+    for (; i < nW; i++) fwdCellGeneric<SCHEME>(p, b, warpSm, bar, i, nW, &phase, &Wi, &res);
     return res;
 }
 

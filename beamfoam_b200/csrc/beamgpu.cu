@@ -55,7 +55,7 @@ struct bf_ctx {
     double *d_W, *d_Th, *d_Lam, *d_U, *d_Ac, *d_Om, *d_dOm, *d_DW, *d_DTh, *d_q, *d_m, *d_Lc;
     double *d_Wold, *d_Uold, *d_Omold, *d_Lamold; // Euler d2dt2Scheme: old-time level
     double *d_pf, *d_pfSrc;                       // point forces, 9 per cell, and their source terms, 6 per cell (on first use)
-    bool hasPf;
+    bool hasPf, hasWeight;
     ContribParams contrib; // beamMomentumContribution list (bf_set_momentum_contributions); contrib.n == 0: none
     double *d_Lf, *d_K, *d_Q, *d_M; // d_Lf, d_Lam: unit quaternions (4 components); Gamma is derived, not stored
     double *d_Wb, *d_Thb, *d_Lamb, *d_DWb, *d_DThb, *d_force, *d_wPresc, *d_thPresc, *d_follower, *d_offset,
@@ -370,7 +370,13 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->stream = nullptr; c->nPools = 0; c->h_sums = nullptr; c->comm = nullptr;
     c->ev[0] = c->ev[1] = c->ev[2] = nullptr;
     c->reducer = nullptr; c->reducerUser = nullptr;
-    c->launches = 0; c->timing = 0; c->splitKernels = getenv("BEAMGPU_SPLIT_KERNELS") ? 1 : 0;
+    c->launches = 0; c->timing = 0; c->splitKernels = 1;
+    // Product path: the two sweeps as two launches per Newton iteration (beam_forward, beam_backward).  The single fused
+    // launch (beam_newton: every thread runs both sweeps) measures 5-6 % slower on B200: with all SMs in the same phase
+    // the latency-bound forward sweep is not disturbed by the HBM-saturating backward sweep of a neighbouring block.
+    // BEAMGPU_FUSED_KERNEL=1 (or BEAMGPU_SPLIT_KERNELS=0) selects the fused launch.
+    if (const char* e = getenv("BEAMGPU_FUSED_KERNEL")) c->splitKernels = atoi(e) ? 0 : 1;
+    if (const char* e = getenv("BEAMGPU_SPLIT_KERNELS")) c->splitKernels = atoi(e) ? 1 : 0;
     c->evRegion[0] = c->evRegion[1] = nullptr;
     c->copyStream = nullptr; c->evStaged = c->evCopied = nullptr; c->copyPending = false; c->fwdMs = c->bwdMs = 0; c->timedIters = 0;
     c->hasQ = c->hasM = false;
@@ -524,7 +530,10 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         fill3(pr->CQ, 1.0); CREATE_CUDA(up(c->d_CQ, 3 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
         fill3(pr->CM, 1.0); CREATE_CUDA(up(c->d_CM, 3 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
         fill3(pr->CIRho, 0.0); CREATE_CUDA(up(c->d_CI, 3 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
-        fill3(pr->weight, 0.0); CREATE_CUDA(up(c->d_weight, 3 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        fill3(pr->weight, 0.0);
+        c->hasWeight = false;
+        for (double w : h) c->hasWeight = c->hasWeight || w != 0.0;
+        CREATE_CUDA(up(c->d_weight, 3 * bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
         std::fill(h.begin(), h.end(), 0.0);
         if (pr->ARho) for (int64_t b = 0; b < B; b++) h[b] = pr->ARho[b];
         CREATE_CUDA(up(c->d_ARho, bp)); CREATE_CUDA(cudaStreamSynchronize(c->stream));
@@ -1040,7 +1049,7 @@ static BeamParams makeParams(bf_ctx* c)
     p.nAcc = 1.0 / (p.beta * p.dt * p.dt); p.nU = (1.0 / p.dt) * (p.gamma / p.beta);
     p.gdt = p.gamma * p.dt; p.gdtPrev = p.gamma * c->dtStar;
     p.nSeg = c->d_nSeg; p.dZ = c->d_dZ; p.CQ = c->d_CQ; p.CM = c->d_CM; p.ARho = c->d_ARho; p.CI = c->d_CI;
-    p.weight = c->d_weight; p.refL = c->d_refL; p.wType = c->d_wType; p.thType = c->d_thType;
+    p.weight = c->hasWeight ? c->d_weight : nullptr; p.refL = c->d_refL; p.wType = c->d_wType; p.thType = c->d_thType;
     p.W = c->d_W; p.Th = c->d_Th; p.Lam = c->d_Lam; p.U = c->d_U; p.Ac = c->d_Ac; p.Om = c->d_Om; p.dOm = c->d_dOm;
     p.DW = c->d_DW; p.DTh = c->d_DTh;
     p.q = c->hasQ ? c->d_q : nullptr; p.m = c->hasM ? c->d_m : nullptr; p.Lc = c->d_Lc;
@@ -1108,12 +1117,12 @@ static int launchIteration(bf_ctx* c)
         else if (c->scheme == BF_SCHEME_EULER) long_update_cells<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
         else long_update_cells<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
         c->launches += 2;
-    } else if (c->splitKernels) { // profiling aid: the same two sweeps as two launches
+    } else if (c->splitKernels && !c->pipelined) { // product path: one launch per sweep
         LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
         LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
         c->launches += 2;
-    } else if (c->pipelined) { // product path: persistent blocks, forward and backward sweeps of different tiles overlap
+    } else if (c->pipelined) { // experiment (BEAMGPU_PIPELINE=1): persistent blocks, sweeps of different tiles overlap
         if (++c->epoch == 0x7fffffff) { // flags compare equal to the epoch: start over before it wraps
             CUDA_OK(c, cudaMemsetAsync(c->d_fDone, 0, sizeof(int) * (size_t)c->grid, c->stream));
             c->epoch = 1;

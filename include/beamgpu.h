@@ -306,9 +306,10 @@ int bf_beam_energy(bf_ctx* ctx, double* out);
 /* ---- instrumentation --------------------------------------------------------
  * Kernel launches issued by this context since creation (bench gpu_launches),
  * and device time in ms of the Newton-iteration kernels since the last reset,
- * measured with CUDA events on the context's stream.  The product path is ONE fused kernel per
- * iteration: fwd_ms then holds its time and bwd_ms is 0; with BEAMGPU_SPLIT_KERNELS=1 in the
- * environment the two sweeps are launched separately (profiling aid) and both are filled. */
+ * measured with CUDA events on the context's stream.  The product path is two launches per
+ * iteration (beam_forward, beam_backward): fwd_ms and bwd_ms hold their times.  With
+ * BEAMGPU_FUSED_KERNEL=1 in the environment both sweeps run in one launch (beam_newton); fwd_ms
+ * then holds its time and bwd_ms is 0. */
 int64_t bf_launch_count(const bf_ctx* ctx);
 int bf_kernel_time_ms(bf_ctx* ctx, int32_t reset, double* fwd_ms, double* bwd_ms,
                       int64_t* iterations);

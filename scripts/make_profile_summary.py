@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Turns gpurun_out/{launches.csv,prof.ncu-rep} into tracked summaries under profiles/.
+"""Turns gpurun_out/{launches.csv,prof.ncu-rep} into tracked summaries under profiles/ (prof.ncu-rep holds one
+launch of beam_forward and one of beam_backward: the two launches of a Newton iteration).
     python scripts/make_profile_summary.py r01
 """
 import csv, json, os, subprocess, sys
@@ -33,8 +34,8 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "l1tex__t_sector_hit_rate.pct",
         "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 summary = []
-with open(os.path.join(out, f"{tag}_beam_newton_ncu.md"), "w") as f:
-    f.write(f"# {tag}: ncu --set full --clock-control none, kernel beam_newton<BFK_NEWMARK> (shown by ncu as beam_newton<1>)\n\n")
+with open(os.path.join(out, f"{tag}_newton_iteration_ncu.md"), "w") as f:
+    f.write(f"# {tag}: ncu --set full --clock-control none, the two launches of one Newton iteration: beam_forward<BFK_NEWMARK>, beam_backward<BFK_NEWMARK> (shown by ncu as <1>)\n\n")
     for r in rows[2:]:
         f.write(f"## launch: {r[col['Kernel Name']]}  grid {r[col.get('Grid Size', 0)]} block {r[col.get('Block Size', 0)]}\n\n| metric | value | unit |\n|---|---|---|\n")
         rec = {}
@@ -50,8 +51,13 @@ with open(os.path.join(out, f"{tag}_beam_newton_ncu.md"), "w") as f:
         summary.append(rec)
 def gb(x, unit):
     x = float(x); return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(unit, 1)
-r = summary[-1]
-traffic = gb(r["dram__bytes_read.sum"], rows[1][col["dram__bytes_read.sum"]]) + gb(r["dram__bytes_write.sum"], rows[1][col["dram__bytes_write.sum"]])
-json.dump({"beam_newton_dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_beam_newton_ncu.md",
-           "cells_per_launch": 13107200, "bytes_per_update": traffic / 13107200}, open(os.path.join(out, "traffic.json"), "w"), indent=1)
-print("traffic per launch %.3f GB = %.0f B/update" % (traffic / 1e9, traffic / 13107200))
+unit = lambda k: rows[1][col[k]]
+per = {}
+for r, row in zip(summary, rows[2:]):
+    name = "beam_forward" if "beam_forward" in row[col["Kernel Name"]] else "beam_backward" if "beam_backward" in row[col["Kernel Name"]] else row[col["Kernel Name"]]
+    per[name] = gb(r["dram__bytes_read.sum"], unit("dram__bytes_read.sum")) + gb(r["dram__bytes_write.sum"], unit("dram__bytes_write.sum"))
+traffic = per.get("beam_forward", 0) + per.get("beam_backward", 0)
+json.dump({"newton_iteration_dram_bytes": traffic, "beam_forward_dram_bytes": per.get("beam_forward"), "beam_backward_dram_bytes": per.get("beam_backward"),
+           "source": f"profiles/{tag}_newton_iteration_ncu.md", "cells_per_launch": 13107200, "bytes_per_update": traffic / 13107200},
+          open(os.path.join(out, "traffic.json"), "w"), indent=1)
+print("traffic per Newton iteration %.3f GB = %.0f B/update" % (traffic / 1e9, traffic / 13107200), per)
