@@ -90,6 +90,8 @@ struct BeamParams {
     double* partial;
     // pipelined launch (beam_newton_pipelined): tickets and per-tile "forward done" flags
     int nTiles;
+    int pipePolicy; // 0: first block of an SM takes forward tickets, second backward tickets; 1: every block takes forward tickets
+                    // while there are any, then backward tickets (the forward sweep's partial last wave is filled with backward work)
     int epoch;   // value a flag takes when the forward sweep of this launch has finished the tile
     int* ctl;    // [0] next forward ticket, [1] next backward ticket, [2 + smid] blocks seen on an SM; zeroed per launch
     int* fDone;  // [nTiles]
@@ -1361,7 +1363,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton_pip
     }
     __syncthreads();
     role = sTicket[0];
-    bool forwardLeft = role == 0;
+    bool forwardLeft = role == 0 || p.pipePolicy == 1;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {

@@ -62,7 +62,7 @@ struct bf_ctx {
         *d_moment, *d_springK, *d_springDir;
     double *d_uP, *d_bP, *d_partial, *d_sums;
     int *d_ctl, *d_fDone; // pipelined launch: tickets / per-SM role counters, per-tile forward-done flags
-    int epoch, pipeGrid, pipelined;
+    int epoch, pipeGrid, pipelined, pipePolicy;
     unsigned long long* d_trace; // BEAMGPU_TRACE=1: per-tile sweep time stamps of the last pipelined launch
     // few long beams: one thread per cell, assembled block rows, block parallel cyclic reduction (beam_long.cuh)
     int longMode, longBlocks;
@@ -496,6 +496,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         // steady state but a launch is only 3.5 tiles per SM deep, so the ramp (backward blocks idle until the first
         // forward tile is done) and the tail cost more than that (4.99 ms vs 4.35 ms).
         c->pipelined = getenv("BEAMGPU_PIPELINE") ? 1 : 0;
+        c->pipePolicy = getenv("BEAMGPU_PIPELINE_POLICY") ? atoi(getenv("BEAMGPU_PIPELINE_POLICY")) : 1;
         c->d_trace = nullptr;
         // BEAMGPU_LONG_BEAMS = 1 / 0 forces the cell-parallel path on / off; by default it serves bundles that cannot
         // occupy the GPU with one thread per beam but have enough cells per beam to do so with one thread per cell
@@ -1060,7 +1061,7 @@ static BeamParams makeParams(bf_ctx* c)
     p.wPresc = c->d_wPresc; p.thPresc = c->d_thPresc; p.follower = c->d_follower; p.offset = c->d_offset;
     p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir;
     p.uP = c->d_uP; p.bP = c->d_bP; p.partial = c->d_partial;
-    p.nTiles = c->grid; p.epoch = c->epoch; p.ctl = c->d_ctl; p.fDone = c->d_fDone; p.trace = c->d_trace;
+    p.nTiles = c->grid; p.pipePolicy = c->pipePolicy; p.epoch = c->epoch; p.ctl = c->d_ctl; p.fDone = c->d_fDone; p.trace = c->d_trace;
     return p;
 }
 
