@@ -479,6 +479,10 @@ DEV void cpAsync8(double* dstSmem, const double* srcGlobal)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal) : "memory");
 }
 DEV void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Orders this thread's generic-proxy accesses to shared memory (the LDS reads of the buffer, the cp.async writes into it)
+// before later async-proxy writes to the same rows (the next bulk copy).  Every lane executes it, then the warp
+// synchronises, then the elected lane issues the copy.
+DEV void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // The warp's 16-row buffer is filled twice per cell:
 //   fwdPrefetchFace(i): face i+1 and W of cell i+1, by the TMA engine (one elected lane, one bulk copy per array,
@@ -958,6 +962,7 @@ __device__ __noinline__ void fwdCellGeneric(const BeamParams& p, const int b, do
     double res = 0.0;
     mbarWait(bar, *phase & 1u);
     const FaceIn in = loadFaceIn(sm);
+    if (SCHEME != BFK_NEWMARK) fenceProxyAsync();
     __syncwarp();
     if (SCHEME == BFK_NEWMARK) fwdPrefetchCell(p, T, sm, i);
     else if (i + 1 < nW) fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
@@ -972,6 +977,7 @@ __device__ __noinline__ void fwdCellGeneric(const BeamParams& p, const int b, do
     if (SCHEME == BFK_NEWMARK) {
         cpAsyncWaitAll();
         cell = loadCellInSm(sm, p.first != 0);
+        fenceProxyAsync();
         __syncwarp();
         if (i + 1 < nW) fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
     } else
@@ -1044,6 +1050,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
     for (; i < nFast; i++) {
         mbarWait(bar, phase & 1u);
         const FaceIn in = loadFaceIn(sm);
+        if (SCHEME != BFK_NEWMARK) fenceProxyAsync();
         __syncwarp(); // every lane holds its buffer rows in registers: the buffer is free for the next fill
         if (SCHEME == BFK_NEWMARK) fwdPrefetchCell(p, T, sm, i);
         else fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
@@ -1054,6 +1061,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
         if (SCHEME == BFK_NEWMARK) { // the Newmark rows of cell i have arrived; hand the buffer to face i+2 / cell i+1
             cpAsyncWaitAll();
             cell = loadCellInSm(sm, p.first != 0);
+            fenceProxyAsync();
             __syncwarp();
             fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
         } else

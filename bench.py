@@ -16,9 +16,10 @@ value   = state resident in HBM; the K timed steps are bracketed by a barrier +
 e2e     = the same K steps through the host-facing call sequence with HOST buffers inside
           the timed region: BC values host->device every step, W and Theta mirrored
           device->host into pinned buffers every step.
-roofline= the fused Newton-iteration kernel: 760 B (Newmark) algorithmic bytes per
-          beam-cell update / measured kernel time, against the measured HBM
-          copy bandwidth of MEASURED_PEAKS.json.
+roofline= one Newton iteration = two launches (beam_forward, beam_backward): 760 B (Newmark)
+          algorithmic bytes per beam-cell update / measured time of the pair,
+          against the measured HBM copy bandwidth of MEASURED_PEAKS.json; `launches` lists each
+          kernel with its own time and measured DRAM bytes.
 """
 from __future__ import annotations
 

@@ -26,6 +26,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 namespace
 {
@@ -582,9 +583,17 @@ int main(int argc, char** argv)
         else if (a[0] != '-' && app.empty()) app = a;
         else fatal("unknown argument " + a);
     }
-    if (lib.empty()) { // next to the executable's repository: <repo>/beamfoam_b200/libbeamgpu.so, or $BEAMGPU_LIB
+    if (lib.empty()) { // $BEAMGPU_LIB, else <repo>/beamfoam_b200/libbeamgpu.so next to this executable's directory
         const char* e = getenv("BEAMGPU_LIB");
-        lib = e ? e : "libbeamgpu.so";
+        if (e) lib = e;
+        else {
+            char exe[4096];
+            const ssize_t n = readlink("/proc/self/exe", exe, sizeof exe - 1);
+            std::string dir = n > 0 ? std::string(exe, (size_t)n) : std::string(argv[0]);
+            const size_t slash = dir.rfind('/');
+            dir = slash == std::string::npos ? "." : dir.substr(0, slash);
+            lib = dir + "/../beamfoam_b200/libbeamgpu.so";
+        }
     }
     try {
         BeamCase c;

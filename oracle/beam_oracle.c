@@ -1458,6 +1458,8 @@ int oracle_get_system(bf_ctx* c, double* d, double* l, double* u, double* source
     return BF_OK;
 }
 /* helper functions exposed for unit tests against closed forms */
+/* test hook: dRdScell of one beam, [nSeg*3] (needs bf_set_momentum_contributions to have set refW, refWf) */
+void oracle_midpoint_derivatives(bf_ctx* c, int64_t beam, double* out) { midPointDerivatives(c, beam, out); }
 void oracle_rotationMatrix(const double* th, double* R) { rotationMatrix(th, R); }
 void oracle_spinTensor(const double* v, double* S) { spin(v, S); }
 void oracle_inv(const double* A, double* O) { t_inv(A, O); }

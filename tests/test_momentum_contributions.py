@@ -121,6 +121,33 @@ def test_ground_contact_friction_switches_between_stick_and_slip(oracle_lib):
         m.close()
 
 
+def test_spline_midpoint_derivative_on_a_rolled_up_beam(oracle_lib):
+    """tutorials/cantilever at t = 0.25: the prescribed end rotation rolls the beam into a quarter circle in the x-z plane,
+    so the unit tangent at arc length s is known; the Hermite-spline mid-point derivative (CTL.C:1263-1427, 1518-1645,
+    HermiteSpline.C:83-108) must reproduce it to the O(h^2) of the discretisation."""
+    import ctypes as C
+    n = 40
+    c = dataclasses.replace(cases.cantilever(nSegments=n, deltaT=0.0125), R=0.2,
+                            momentumContributions=[groundContactContribution(0.0, 0.0, 0.0, 0.0, -1e30)])  # inert: z never below
+    m = coupledTotalLagNewtonRaphsonBeam(c, library=oracle_lib)
+    m.run(nSteps=20)
+    out = np.zeros((n, 3))
+    oracle_lib.oracle_midpoint_derivatives.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    oracle_lib.oracle_midpoint_derivatives.restype = None
+    oracle_lib.oracle_midpoint_derivatives(m._ctx, 0, out.ctypes.data)
+    W = m.get_field("W")[0]
+    pos = W + np.stack([(np.arange(n) + 0.5) * c.length / n, np.zeros(n), np.zeros(n)], axis=1)
+    # tangent from the cell-centre positions themselves (central differences): independent of any sign convention
+    fd = np.gradient(pos, axis=0)
+    fd /= np.linalg.norm(fd, axis=1, keepdims=True)
+    assert np.allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-12)
+    assert np.max(np.abs(out[1:-1] - fd[1:-1])) < 2e-3
+    # and it is a quarter circle: the tangent turns by pi/2 over the length
+    turn = np.arccos(np.clip(out[0] @ out[-1], -1, 1))
+    assert abs(turn - (np.pi / 2) * (n - 1) / n) < 2e-2
+    m.close()
+
+
 def _bundle(nBeams=3, n=16, steps=25):
     """Transient cantilever bundle (Newmark) with both contributions, per-beam translation, ragged lengths."""
     c = cases.multiBeamDensity(nBeams, n, jitter=True)
