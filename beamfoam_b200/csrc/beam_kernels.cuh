@@ -482,7 +482,11 @@ DEV void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // Orders this thread's generic-proxy accesses to shared memory (the LDS reads of the buffer, the cp.async writes into it)
 // before later async-proxy writes to the same rows (the next bulk copy).  Every lane executes it, then the warp
 // synchronises, then the elected lane issues the copy.
+#ifdef BEAM_NO_PROXY_FENCE
+DEV void fenceProxyAsync() {}
+#else
 DEV void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 // The warp's 16-row buffer is filled twice per cell:
 //   fwdPrefetchFace(i): face i+1 and W of cell i+1, by the TMA engine (one elected lane, one bulk copy per array,
