@@ -164,6 +164,8 @@ class coupledTotalLagNewtonRaphsonBeam:
 
         self._bcs = {}
         self._bcCache = {}
+        self._bcUploaded = set()
+        self.h2dBytes = 0  # bytes handed to bf_set_bc_values so far
         wType = np.zeros(2 * B, np.int32)
         thType = np.zeros(2 * B, np.int32)
         springK = np.zeros(2 * B)
@@ -360,10 +362,14 @@ class coupledTotalLagNewtonRaphsonBeam:
     # ------------------------------------------------------------- hot path
     def updateCoeffs(self, t: float):
         """W_/Theta_.boundaryFieldRef().updateCoeffs() (Evolve.C:156-157): evaluate every
-        BC series at time t and hand the values to the device."""
+        BC series at time t and hand the values to the device.  Patch fields without a series are handed over once
+        (their updateCoeffs() does nothing in the reference either)."""
         for end in (0, 1):
             for var in ("W", "Theta"):
                 spec, objs = self._bcs[(end, var)]
+                dependent = spec.timeDependent if objs is None else any(o.timeDependent for o in objs)
+                if not dependent and (end, var) in self._bcUploaded:
+                    continue
                 vals = self._bc_values(end, var, t)
                 kinds = {spec.kind} if objs is None else {o.kind for o in objs}
                 for kind in kinds:
@@ -372,6 +378,8 @@ class coupledTotalLagNewtonRaphsonBeam:
                         v = np.where(np.array([o.kind == kind for o in objs])[:, None], vals, 0.0)
                     v = np.ascontiguousarray(v)
                     self._check(self.lib.bf_set_bc_values(self._ctx, end, kind, v.ctypes.data))
+                    self.h2dBytes += v.nbytes
+                self._bcUploaded.add((end, var))
 
     def updatePointForces(self, t: float):
         """pointForces()[pfI].second()(runTime().value()) (Evolve.C:219): evaluate the point-force series at

@@ -52,6 +52,14 @@ class _PatchField:
     def valueAt(self, t: float) -> np.ndarray:  # what updateCoeffs() would set
         raise NotImplementedError
 
+    @property
+    def timeDependent(self) -> bool:
+        """True if updateCoeffs() looks a value up in a time series; a plain ``value``/``force``/``moment`` entry is
+        set once (fixedValueFvPatchField::updateCoeffs does nothing)."""
+        return any(isinstance(getattr(self, k, None), interpolationTable)
+                   for k in ("displacementSeries", "thetaSeries", "forceSeries", "transitionSeries",
+                             "followerForceSeries", "offsetForceSeries", "momentSeries"))
+
     def values(self, t: float, nBeams: int) -> np.ndarray:
         v = np.broadcast_to(self.valueAt(t), (nBeams, 3)).copy()
         if self.scale is not None:
