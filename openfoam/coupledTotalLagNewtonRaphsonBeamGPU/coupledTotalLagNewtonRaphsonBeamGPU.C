@@ -106,6 +106,21 @@ void coupledTotalLagNewtonRaphsonBeamGPU::download(const label id, surfaceTensor
     UNPACK_PATCHES(f, 9, L, R)
 }
 
+// Patch values only (what the function objects read every step through historyPatch: beamDisplacements.C:56-63,
+// beamForcesMoments.C:56-68); the internal field stays as it was mirrored at the last write time.
+void coupledTotalLagNewtonRaphsonBeamGPU::downloadPatches(const label id, volVectorField& f)
+{
+    List<scalar> L(3*nBeams()), R(3*nBeams());
+    check(bf_get_field(ctx_, id, nullptr, L.data(), R.data()), "bf_get_field");
+    UNPACK_PATCHES(f, 3, L, R)
+}
+void coupledTotalLagNewtonRaphsonBeamGPU::downloadPatches(const label id, surfaceVectorField& f)
+{
+    List<scalar> L(3*nBeams()), R(3*nBeams());
+    check(bf_get_field(ctx_, id, nullptr, L.data(), R.data()), "bf_get_field");
+    UNPACK_PATCHES(f, 3, L, R)
+}
+
 // The host patch-field objects stay responsible for dictionary parsing and for the time series:
 // updateCoeffs() evaluates them at the new time exactly as Evolve.C:156-157 does; the values go
 // to the device, which re-implements the boundary-face arithmetic (BC.C, evaluate()).
@@ -364,23 +379,37 @@ scalar coupledTotalLagNewtonRaphsonBeamGPU::evolve()
     Info<< "    Newton iterations: " << out.nIter
         << ", residual " << out.currentResidualNorm << ", step " << out.deltaXNorm << endl;
 
-    // mirror back what boundary conditions, function objects and write() look up by name
-    download(BF_FIELD_W, solutionW(), true);
-    download(BF_FIELD_THETA, solutionTheta(), true);
-    download(BF_FIELD_DW, field<volVectorField>("DW"), true);
-    download(BF_FIELD_DTHETA, field<volVectorField>("DTheta"), true);
-    download(BF_FIELD_LAMBDA, field<volTensorField>("Lambda"));
-    download(BF_FIELD_LAMBDAF, solutionLambda());
-    download(BF_FIELD_GAMMA, field<surfaceVectorField>("Gamma"));
-    download(BF_FIELD_K, field<surfaceVectorField>("K"));
-    download(BF_FIELD_Q, field<surfaceVectorField>("Q"));
-    download(BF_FIELD_M, field<surfaceVectorField>("M"));
-    if (!steadyState())
+    // Mirror back what boundary conditions, function objects and write() look up by name.  Every step: the patch values
+    // (function objects with a historyPatch).  The internal fields only when something on the host reads them: at write
+    // times (runTime.write(), beamFoam.C:87), or every step with `mirrorFields everyStep;` in the Coeffs dictionary (needed
+    // if a function object such as beamEnergyData reads internal fields each step; bf_beam_energy replaces that one).
+    const bool everyStep = d.lookupOrDefault<word>("mirrorFields", "outputTime") == "everyStep";
+    if (everyStep || runTime().outputTime() || runTime().timeIndex() == runTime().startTimeIndex() + 1)
     {
-        download(BF_FIELD_U, field<volVectorField>("U"), false);
-        download(BF_FIELD_ACCL, field<volVectorField>("Accl"), false);
-        download(BF_FIELD_OMEGA, field<volVectorField>("Omega"), false);
-        download(BF_FIELD_DOTOMEGA, field<volVectorField>("dotOmega"), false);
+        download(BF_FIELD_W, solutionW(), true);
+        download(BF_FIELD_THETA, solutionTheta(), true);
+        download(BF_FIELD_DW, field<volVectorField>("DW"), true);
+        download(BF_FIELD_DTHETA, field<volVectorField>("DTheta"), true);
+        download(BF_FIELD_LAMBDA, field<volTensorField>("Lambda"));
+        download(BF_FIELD_LAMBDAF, solutionLambda());
+        download(BF_FIELD_GAMMA, field<surfaceVectorField>("Gamma"));
+        download(BF_FIELD_K, field<surfaceVectorField>("K"));
+        download(BF_FIELD_Q, field<surfaceVectorField>("Q"));
+        download(BF_FIELD_M, field<surfaceVectorField>("M"));
+        if (!steadyState())
+        {
+            download(BF_FIELD_U, field<volVectorField>("U"), false);
+            download(BF_FIELD_ACCL, field<volVectorField>("Accl"), false);
+            download(BF_FIELD_OMEGA, field<volVectorField>("Omega"), false);
+            download(BF_FIELD_DOTOMEGA, field<volVectorField>("dotOmega"), false);
+        }
+    }
+    else
+    {
+        downloadPatches(BF_FIELD_W, solutionW());
+        downloadPatches(BF_FIELD_THETA, solutionTheta());
+        downloadPatches(BF_FIELD_Q, field<surfaceVectorField>("Q"));
+        downloadPatches(BF_FIELD_M, field<surfaceVectorField>("M"));
     }
     solutionW().storePrevIter();
     solutionTheta().storePrevIter();
