@@ -75,3 +75,13 @@ def test_every_bc_class(gpu_lib, oracle_lib, long_path):
         for a, b in zip(g.get_field(f), o.get_field(f)):
             if a.size:
                 assert np.max(np.abs(a - b)) <= 1e-8 * max(np.max(np.abs(b)), 1.0), f
+
+
+def test_momentum_contributions(gpu_lib, oracle_lib, long_path):
+    """The per-cell source array of beam_momentum_contributions feeds long_assemble as it feeds the forward sweep."""
+    from beamfoam_b200.beamMomentumContribution import groundContactContribution, morisonDragContribution
+    case = dataclasses.replace(cases.multiBeamDensity(4, 18, jitter=True), R=0.1, deltaT=2e-3,
+                               initialTranslation=np.array([0.0, 0.0, 0.1]),
+                               momentumContributions=[morisonDragContribution(1.2, 0.05, 1000.0),
+                                                      groundContactContribution(2e3, 50.0, 4e2, 0.3, 1.2)])
+    run_pair(case, gpu_lib, oracle_lib, nSteps=20, tip_rtol=1e-9)
