@@ -153,3 +153,43 @@ def test_oracle_matches_committed_golden(oracle_lib):
         out = generate(name, oracle_lib)
         assert list(out["iters"]) == list(ref["iters"])
         np.testing.assert_allclose(out["tipW"], ref["tipW"], rtol=1e-12, atol=1e-15)
+
+
+def test_elastica_tip_force_large_deflection(oracle_lib):
+    """Cantilever under a dead transverse tip force P with P L^2/EI = 1, 2, 5, 10: the planar elastica
+    theta'' = -(P/EI) cos(theta), theta(0) = 0, theta'(L) = 0 (Bisshopp & Drucker 1945; tabulated by Mattiasson 1981:
+    w/L = 0.30172, 0.49346, 0.71379, 0.81061; u/L = 0.05643, 0.16064, 0.38763, 0.55500) is integrated here to 1e-9.
+    The finite-volume beam adds shear and axial compliance, 3 EI/(GA L^2) = 6e-4 of the deflection for this section
+    (L = 10, r = 0.2), and an O(h^2) discretisation error at 100 cells: agreement within 2e-3 of the deflection pins the
+    force-loaded branch (explicitQ, CQTheta, the dr x Q term, forceBeamDisplacementNR::evaluate) the way the roll-up test
+    pins the moment-loaded one."""
+    import dataclasses
+    from scipy.integrate import solve_bvp
+    from beamfoam_b200.fvPatchFields import forceBeamDisplacementNR, interpolationTable, momentBeamRotationNR
+    L, EI = 10.0, 100.0
+    table = {1.0: (0.30172, 0.05643), 2.0: (0.49346, 0.16064), 5.0: (0.71379, 0.38763), 10.0: (0.81061, 0.55500)}
+    for lam, (w_tab, u_tab) in table.items():
+        P = lam * EI / L ** 2
+        # elastica in s in [0, L]: y = (theta, theta', x, z), tip force P along +z
+        def rhs(s, y):
+            return np.vstack([y[1], -(P / EI) * np.cos(y[0]), np.cos(y[0]), np.sin(y[0])])
+        def bc(ya, yb):
+            return np.array([ya[0], yb[1], ya[2], ya[3]])
+        s = np.linspace(0, L, 400)
+        y0 = np.zeros((4, s.size))
+        y0[0] = 0.5 * lam * (s / L) * (1 - 0.5 * s / L) / (1 + 0.3 * lam)
+        y0[2] = s
+        sol = solve_bvp(rhs, bc, s, y0, tol=1e-10, max_nodes=200000)
+        assert sol.status == 0
+        w_el, u_el = sol.y[3, -1] / L, 1.0 - sol.y[2, -1] / L
+        assert abs(w_el - w_tab) < 2e-5 and abs(u_el - u_tab) < 2e-5, (lam, w_el, u_el)  # the tabulated values
+        case = dataclasses.replace(
+            cases.cantilever(nSegments=100, deltaT=0.05), divergenceTol=1e12,
+            W_right=forceBeamDisplacementNR(forceSeries=interpolationTable([(0, (0, 0, 0)), (1, (0, 0, P))])),
+            Theta_right=momentBeamRotationNR(moment=(0, 0, 0)))
+        m, its, _ = run(case, oracle_lib)
+        tip = m.tip(1)[0][0]
+        assert abs(tip[2] / L - w_el) < 2e-3 * w_el, (lam, tip, w_el)
+        assert abs(-tip[0] / L - u_el) < 4e-3 * u_el + 1e-5, (lam, tip, u_el)
+        assert abs(tip[1]) < 1e-9 and max(its) <= 8
+        m.close()
