@@ -193,3 +193,67 @@ def test_elastica_tip_force_large_deflection(oracle_lib):
         assert abs(-tip[0] / L - u_el) < 4e-3 * u_el + 1e-5, (lam, tip, u_el)
         assert abs(tip[1]) < 1e-9 and max(its) <= 8
         m.close()
+
+
+def test_cantilever_first_bending_period(oracle_lib):
+    """Newmark (1/4, 1/2) response of a slender cantilever to a small step tip force: the tip swings about the static
+    deflection with the first bending period T1 = 2 pi / (1.8751^2 sqrt(EI / (rho A L^4))) (Euler-Bernoulli; the
+    section's r/L = 0.01 makes shear and rotary inertia corrections ~1e-4, the trapezoidal rule stretches the period by
+    (omega dt)^2/12 = 8e-5).  Pins the translational inertia terms QRho, QRhoCoeff (Evolve.C:369-419, 459-466) and the
+    predictor/corrector of U, Accl (Evolve.C:167-186, 782-789) against a closed form: measured T/T1 = 1.0000 at 40 cells
+    (0.9992 at 20, 1.0002 at 80); asserted within 2e-3."""
+    import dataclasses
+    from beamfoam_b200.crossSections import circle
+    from beamfoam_b200.fvPatchFields import forceBeamDisplacementNR, momentBeamRotationNR
+    L, r, E, rho = 2.0, 0.02, 2.0e9, 1000.0
+    cs = circle(r)
+    EI, rhoA = E * cs.Ixx(), rho * cs.A()
+    T1 = 2 * np.pi / (1.8751 ** 2 * np.sqrt(EI / (rhoA * L ** 4)))
+    F = 1e-3 * 3 * EI / L ** 3  # static tip deflection 1e-3 L: linear regime
+    base = cases.dynamicCantilever(nBeams=1, nSegments=40, rho=rho, deltaT=T1 / 200)
+    case = dataclasses.replace(base, A=cs.A(), Iyy=cs.Ixx(), Izz=cs.Iyy(), J=cs.IT(), E=E, G=E / 2.6, length=L,
+                               initialRotation=None, W_right=forceBeamDisplacementNR(force=(0, 0, F)),
+                               Theta_right=momentBeamRotationNR(moment=(0, 0, 0)), endTime=10 * T1)
+    m, its, hist = run(case, oracle_lib, nSteps=1200, record=True)  # six periods
+    t, w = hist[:, 0], hist[:, 3]
+    ws = F * L ** 3 / (3 * EI)
+    assert abs(np.max(w) / (2 * ws) - 1) < 0.05  # undamped step response overshoots to twice the static deflection
+    # frequency of the dominant mode: least-squares fit of a cos(wt) + b sin(wt) to w - ws, scanned over +-5 % of omega_1
+    # (single zero crossings wander by +-0.5 % with the second mode's 3 % share of the tip response)
+    y = w - ws
+    om = np.linspace(0.95, 1.05, 2001) * 2 * np.pi / T1
+    res = [np.linalg.lstsq(np.stack([np.cos(o * t), np.sin(o * t)], 1), y, rcond=None)[1][0] for o in om]
+    T_fit = 2 * np.pi / om[int(np.argmin(res))]
+    assert abs(T_fit / T1 - 1) < 2e-3, (T_fit, T1)
+    assert max(its) <= 4
+    m.close()
+
+
+def test_torsional_wave_period(oracle_lib):
+    """Fixed-free rod under a small step torque about its axis: the twist obeys the wave equation with speed
+    c = sqrt(GJ / (rho J)) = sqrt(G / rho), so the tip twist is a triangular wave about the static value M L/(GJ) with period
+    4 L / c.  Pins the rotary inertia terms MRho, MRhoCoeff with CIRho = diag(rho J, rho I, rho I) (Evolve.C:375-382,
+    467-535; CTL.C:621-667) and the Omega / dotOmega update (Evolve.C:849-863): measured T/T0 = 1.000 +- 1e-3."""
+    import dataclasses
+    from beamfoam_b200.crossSections import circle
+    from beamfoam_b200.fvPatchFields import forceBeamDisplacementNR, momentBeamRotationNR
+    L, r, E, G, rho = 2.0, 0.02, 2.0e9, 0.8e9, 1000.0
+    cs = circle(r)
+    T0 = 4 * L / np.sqrt(G / rho)
+    Mx = 1e-3 * G * cs.IT() / L  # static tip twist 1e-3 rad
+    base = cases.dynamicCantilever(nBeams=1, nSegments=50, rho=rho, deltaT=T0 / 400)
+    case = dataclasses.replace(base, A=cs.A(), Iyy=cs.Ixx(), Izz=cs.Iyy(), J=cs.IT(), E=E, G=G, length=L, initialRotation=None,
+                               W_right=forceBeamDisplacementNR(force=(0, 0, 0)),
+                               Theta_right=momentBeamRotationNR(moment=(Mx, 0, 0)), endTime=10 * T0)
+    m = coupledTotalLagNewtonRaphsonBeam(case, library=oracle_lib)
+    hist = []
+    its = m.run(nSteps=2000, callback=lambda mm: hist.append((mm.time, mm.tip(1)[1][0][0])))
+    h = np.array(hist)
+    t, y = h[:, 0], h[:, 1] - 1e-3
+    assert abs(np.max(h[:, 1]) / 2e-3 - 1) < 0.05  # overshoot to twice the static twist
+    om = np.linspace(0.95, 1.05, 2001) * 2 * np.pi / T0
+    res = [np.linalg.lstsq(np.stack([np.cos(o * t), np.sin(o * t)], 1), y, rcond=None)[1][0] for o in om]
+    T_fit = 2 * np.pi / om[int(np.argmin(res))]
+    assert abs(T_fit / T0 - 1) < 3e-3, (T_fit, T0)
+    assert max(its) <= 4
+    m.close()
