@@ -1,7 +1,7 @@
-// beam_kernels.cuh — the fused Newton-iteration kernels (FP64, sm_100a).
+// beam_kernels.cuh — the Newton-iteration kernels (FP64, sm_100a).
 //
-// One Newton iteration of coupledTotalLagNewtonRaphsonBeam::evolve() is ONE kernel
-// (beam_newton) made of two sweeps that every thread runs back to back:
+// One Newton iteration of coupledTotalLagNewtonRaphsonBeam::evolve() is two sweeps over every beam, launched as two
+// kernels (beam_forward, beam_backward; beam_newton runs both in one launch and measures slower):
 //
 //   forwardSweep  : per beam, left -> right.  For every cell it recomputes the face
 //                   coefficients (updateEqnCoefficients, Evolve.C:673-753), assembles the
@@ -121,16 +121,6 @@ DEV void st9(double* __restrict__ p, size_t i, size_t s, const M3& A)
     for (int k = 0; k < 9; k++) p[i + k * s] = A.a[k];
 }
 DEV Q4 ldq(const double* __restrict__ p, size_t i, size_t s) { return q4(p[i], p[i + s], p[i + 2 * s], p[i + 3 * s]); }
-// Loads the compiler may not sink towards their first use: issued where written, so that the latency of rows that
-// are consumed late in a cell is covered by the work in between.
-DEV double ldEarly(const double* p)
-{
-    double v;
-    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-DEV V3 ld3Early(const double* p, size_t i, size_t s) { return v3(ldEarly(p + i), ldEarly(p + i + s), ldEarly(p + i + 2 * s)); }
-DEV Q4 ldqEarly(const double* p, size_t i, size_t s) { return q4(ldEarly(p + i), ldEarly(p + i + s), ldEarly(p + i + 2 * s), ldEarly(p + i + 3 * s)); }
 DEV void stq(double* __restrict__ p, size_t i, size_t s, Q4 q) { stS(p + i, q.w); stS(p + i + s, q.x); stS(p + i + 2 * s, q.y); stS(p + i + 3 * s, q.z); }
 // Gamma = refLambdaf.T() & ((Lambdaf.T() & dRdS) - dR0Ds)   Evolve.C:881-887, from the STORED W and
 // Lm = Lambdaf & refLambdaf:  Gamma = Lm.T() & dRdS - e0,  e0 = refLambdaf.T() & dR0Ds
@@ -631,8 +621,8 @@ DEV void pointForceSource(const BeamParams& p, const int b, const int i, double*
 
 // Loads (Evolve.C:193-279) and inertia (Evolve.C:320-536, with the Newmark predictor :167-186 on the first iteration
 // of a time step) of cell i, added to its diagonal block and source.
-// The Newmark rows of a cell; the forward sweep issues these loads at the top of the cell (ldEarly) and consumes
-// them after the face part.
+// The Newmark rows of a cell: the forward sweep brings them in by cp.async (fwdPrefetchCell / loadCellInSm); the other
+// callers (Euler and steadyState, the cell-parallel path) load them directly.
 struct CellIn {
     Q4 ql;
     V3 Ac, Om, dOm, U;
@@ -647,7 +637,7 @@ DEV CellIn loadCellInSm(const double* sm, bool first)
     c.U = first ? smLd3(sm, R_BUF + C_U) : v3(0, 0, 0);
     return c;
 }
-template <int SCHEME, bool EARLY>
+template <int SCHEME>
 DEV CellIn loadCellIn(const BeamParams& p, const int b, const int i)
 {
     CellIn c;
@@ -655,8 +645,7 @@ DEV CellIn loadCellIn(const BeamParams& p, const int b, const int i)
     c.Ac = c.Om = c.dOm = c.U = v3(0, 0, 0);
     if (SCHEME == BFK_NEWMARK) {
         const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31), c4 = tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31);
-        if (EARLY) { c.ql = ldqEarly(p.Lam, c4, TS); c.Ac = ld3Early(p.Ac, c3, TS); c.Om = ld3Early(p.Om, c3, TS); c.dOm = ld3Early(p.dOm, c3, TS); }
-        else { c.ql = ldq(p.Lam, c4, TS); c.Ac = ld3(p.Ac, c3, TS); c.Om = ld3(p.Om, c3, TS); c.dOm = ld3(p.dOm, c3, TS); }
+        c.ql = ldq(p.Lam, c4, TS); c.Ac = ld3(p.Ac, c3, TS); c.Om = ld3(p.Om, c3, TS); c.dOm = ld3(p.dOm, c3, TS);
         if (p.first) c.U = ld3(p.U, c3, TS);
     }
     return c;
@@ -985,7 +974,7 @@ __device__ __noinline__ void fwdCellGeneric(const BeamParams& p, const int b, do
         __syncwarp();
         if (i + 1 < nW) fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
     } else
-        cell = loadCellIn<SCHEME, false>(p, b, i);
+        cell = loadCellIn<SCHEME>(p, b, i);
     *phase += 1;
     if (interior) {
         addLoadsAndInertia<SCHEME>(p, b, i, smLd(sm, R_DZ), smLd(sm, R_ARHO), smLd3(sm, R_CI), cell, Dc, src);
@@ -1069,7 +1058,7 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
             __syncwarp();
             fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
         } else
-            cell = loadCellIn<SCHEME, false>(p, b, i);
+            cell = loadCellIn<SCHEME>(p, b, i);
         phase++;
         addLoadsAndInertia<SCHEME>(p, b, i, dz, smLd(sm, R_ARHO), smLd3(sm, R_CI), cell, Dc, src);
 #pragma unroll

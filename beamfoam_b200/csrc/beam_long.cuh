@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) long_assemble(const BeamParams p, const L
             }
         }
         const double ARho = SCHEME != BFK_STEADY ? p.ARho[b] : 0.0;
-        addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, SCHEME != BFK_STEADY ? ld3(p.CI, b, p.Bpad) : v3(0, 0, 0), loadCellIn<SCHEME, false>(p, b, i), D, src);
+        addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, SCHEME != BFK_STEADY ? ld3(p.CI, b, p.Bpad) : v3(0, 0, 0), loadCellIn<SCHEME>(p, b, i), D, src);
         for (int r = 0; r < 6; r++) v[0] += src[r] * src[r];
         double *oD = q.D0 + 36 * g, *oL = q.L0 + 36 * g, *oU = q.U0 + 36 * g, *oR = q.R0 + 6 * g;
         for (int r = 0; r < 6; r++) {
