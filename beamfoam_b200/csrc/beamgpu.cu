@@ -341,6 +341,7 @@ extern "C" int bf_destroy(bf_ctx* c)
 
 static int devAlloc(bf_ctx* c, void** p, size_t bytes)
 {
+    if (c->nPools >= (int)(sizeof c->pools / sizeof c->pools[0])) return fail(c, BF_ERR_NOMEM, "device pool table full");
     CUDA_OK(c, cudaMalloc(p, bytes));
     CUDA_OK(c, cudaMemsetAsync(*p, 0, bytes, c->stream));
     c->pools[c->nPools++] = *p;
@@ -898,7 +899,7 @@ extern "C" int bf_set_point_forces(bf_ctx* c, int64_t n, const int64_t* cell, co
     }
     if (!c->d_pf) {
         int rc = devAlloc(c, (void**)&c->d_pf, sizeof(double) * 9 * (size_t)c->nmax * c->Bpad);
-        if (!rc) rc = devAlloc(c, (void**)&c->d_pfSrc, sizeof(double) * 6 * (size_t)c->nmax * c->Bpad);
+        if (!rc && !c->d_pfSrc) rc = devAlloc(c, (void**)&c->d_pfSrc, sizeof(double) * 6 * (size_t)c->nmax * c->Bpad); // shared with the momentum contributions
         if (rc) return rc;
     }
     int rc = xferInternal(c, c->d_pf, h.data(), 9, 0, FK_PLAIN, true);
