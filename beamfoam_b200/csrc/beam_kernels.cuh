@@ -469,6 +469,9 @@ DEV void cpAsync8(double* dstSmem, const double* srcGlobal)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal) : "memory");
 }
 DEV void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+DEV void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+DEV void cpAsyncWaitGroup() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // Orders this thread's generic-proxy accesses to shared memory (the LDS reads of the buffer, the cp.async writes into it)
 // before later async-proxy writes to the same rows (the next bulk copy).  Every lane executes it, then the warp
 // synchronises, then the elected lane issues the copy.
@@ -1072,6 +1075,10 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
 // ---------------------------------------------------------------------------
 // backward: back-substitution + BC evaluate + updateSolutionVariables + norms
 // ---------------------------------------------------------------------------
+// Shared-memory stage of the backward sweep (bwdStageScratch): rows per stage, two stages per warp.  Staging the rows of
+// face i+1 as well (13 more rows per stage) was measured: 2.44 ms against 1.98 ms.
+#define BWD_STAGE_ROWS 42 // uPrime 36, bPrime 6
+#define BWD_SMEM_BYTES ((BEAM_THREADS / 32) * 2 * BWD_STAGE_ROWS * 32 * sizeof(double))
 struct FaceState {
     Q4 Lf;
     V3 K, Q, M;
@@ -1240,14 +1247,14 @@ DEV void updateFacesOfCell(const BeamParams& p, const int b, const int i, const 
         const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f4 = tileRow(T, Rf, i + 1, 4, lane);
         const Q4 qfOld = ldq(p.Lf, f4, s);
         const V3 Kold = ld3(p.K, f3, s);
+        const V3 Qold = ld3(p.Q, f3, s), Mold = ld3(p.M, f3, s);
         FaceState o;
         if (i == n - 1) { // right patch
-            o = patchUpdate(p, 1, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s), Wold, DW, DT, dcB, delta);
+            o = patchUpdate(p, 1, b, qfOld, CQ, CM, Kold, Qold, Mold, Wold, DW, DT, dcB, delta);
         } else {
             const M3 LmOld = quatToMat(qfOld);
             const V3 t = dR0 + dcI * (WoldN - Wold);
-            const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, t), Kold,
-                                                ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcI, false);
+            const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, t), Kold, Qold, Mold, t, dcI, false);
             o = updateFace(f, qfOld, LmOld, Kold, DW, xWn, DT, xTn, dcI, false);
         }
         stq(p.Lf, f4, s, o.Lf);
@@ -1264,8 +1271,22 @@ DEV void updateFacesOfCell(const BeamParams& p, const int b, const int i, const 
     }
 }
 
+// The block-Thomas scratch of a cell (uPrime 36 + bPrime 6) is the first thing the backward step needs and the largest
+// thing it reads.  With a shared-memory slab (sm != null: two stages of 42 rows per warp, [row][32 lanes], a lane only ever
+// touches its own column, so no warp-level synchronisation) every lane brings the scratch of cell i-1 in by cp.async while
+// it works on cell i, straight from DRAM; without a slab the rows are L2-prefetched one cell ahead and loaded at the top.
+DEV void bwdStageScratch(const BeamParams& p, const size_t T, const int lane, const int i, double* stage)
+{
+    const size_t u0 = tileRow(T, p.nmax, i, 36, lane), b0 = tileRow(T, p.nmax, i, 6, lane);
+#pragma unroll
+    for (int k = 0; k < 36; k++) cpAsync8(stage + k * 32, p.uP + u0 + (size_t)k * TS);
+#pragma unroll
+    for (int k = 0; k < 6; k++) cpAsync8(stage + (36 + k) * 32, p.bP + b0 + (size_t)k * TS);
+    cpAsyncCommit();
+}
+
 template <int SCHEME>
-DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2)
+DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2, double* sm = nullptr)
 {
     const size_t s = TS;
     const size_t T = (size_t)(b >> 5);
@@ -1286,14 +1307,18 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
 
         V3 xWn = v3(0, 0, 0), xTn = v3(0, 0, 0); // x_{i+1}
         V3 WoldN = v3(0, 0, 0);
+        if (sm && n > 0) bwdStageScratch(p, T, lane, n - 1, sm + ((n - 1) & 1) * BWD_STAGE_ROWS * 32);
         for (int i = n - 1; i >= 0; i--) {
             // ---- back substitution: x_i = bPrime_i - uPrime_i & x_{i+1}
             const size_t u0 = tileRow(T, Rc, i, 36, lane), b0 = tileRow(T, Rc, i, 6, lane);
+            if (sm && i >= 1) bwdStageScratch(p, T, lane, i - 1, sm + ((i - 1) & 1) * BWD_STAGE_ROWS * 32);
             if (i >= BEAM_PF_DIST) { // prefetch what iteration i-D reads: scratch and cell i-D, face i-D+1
                 const int ic = i - BEAM_PF_DIST;
                 const size_t m3 = tileRow(T, Rc, ic, 3, lane), g3 = tileRow(T, Rf, ic + 1, 3, lane);
-                pfRows<36>(p.uP, tileRow(T, Rc, ic, 36, lane), s);
-                pfRows<6>(p.bP, tileRow(T, Rc, ic, 6, lane), s);
+                if (!sm) {
+                    pfRows<36>(p.uP, tileRow(T, Rc, ic, 36, lane), s);
+                    pfRows<6>(p.bP, tileRow(T, Rc, ic, 6, lane), s);
+                }
                 pfRows<3>(p.W, m3, s); pfRows<3>(p.Th, m3, s);
                 pfRows<4>(p.Lam, tileRow(T, Rc, ic, 4, lane), s);
                 if (SCHEME == BFK_NEWMARK) {
@@ -1305,16 +1330,33 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 pfRows<3>(p.Q, g3, s); pfRows<3>(p.M, g3, s);
             }
             double x[6];
+            if (sm) {
+                if (i >= 1) cpAsyncWaitGroup<1>(); else cpAsyncWaitGroup<0>(); // all but the group just committed
+                const double* st = sm + (i & 1) * BWD_STAGE_ROWS * 32;
 #pragma unroll
-            for (int r = 0; r < 6; r++) x[r] = __ldcg(p.bP + b0 + (size_t)r * s); // written by another SM in this launch: L2
-            if (i < n - 1) {
-                const double xn[6] = {xWn.x, xWn.y, xWn.z, xTn.x, xTn.y, xTn.z};
+                for (int r = 0; r < 6; r++) x[r] = smLd(st, 36 + r);
+                if (i < n - 1) {
+                    const double xn[6] = {xWn.x, xWn.y, xWn.z, xTn.x, xTn.y, xTn.z};
 #pragma unroll
-                for (int r = 0; r < 6; r++) {
-                    double acc = 0.0;
+                    for (int r = 0; r < 6; r++) {
+                        double acc = 0.0;
 #pragma unroll
-                    for (int c = 0; c < 6; c++) acc += __ldcg(p.uP + u0 + (size_t)(6 * r + c) * s) * xn[c];
-                    x[r] -= acc;
+                        for (int c = 0; c < 6; c++) acc += smLd(st, 6 * r + c) * xn[c];
+                        x[r] -= acc;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 6; r++) x[r] = __ldcg(p.bP + b0 + (size_t)r * s); // written by another SM in this launch: L2
+                if (i < n - 1) {
+                    const double xn[6] = {xWn.x, xWn.y, xWn.z, xTn.x, xTn.y, xTn.z};
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 6; c++) acc += __ldcg(p.uP + u0 + (size_t)(6 * r + c) * s) * xn[c];
+                        x[r] -= acc;
+                    }
                 }
             }
             const V3 DW = v3(x[0], x[1], x[2]), DT = v3(x[3], x[4], x[5]);
@@ -1444,9 +1486,15 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(co
 template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_backward(const BeamParams p)
 {
+    extern __shared__ __align__(128) unsigned char beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
-    if (b < p.B) backwardSweep<SCHEME>(p, b, v[0], v[1]);
+#ifdef BEAM_BWD_NO_ASYNC_SCRATCH
+    double* slab = nullptr;
+#else
+    double* slab = (double*)beam_smem + (size_t)(threadIdx.x >> 5) * 2 * BWD_STAGE_ROWS * 32 + (threadIdx.x & 31);
+#endif
+    if (b < p.B) backwardSweep<SCHEME>(p, b, v[0], v[1], slab);
     blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
 }
 

@@ -401,6 +401,9 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     OPT_IN_SMEM(beam_newton_pipelined);
     OPT_IN_SMEM(beam_newton);
     OPT_IN_SMEM(beam_forward);
+    CREATE_CUDA(cudaFuncSetAttribute(beam_backward<BFK_STEADY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_backward<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_backward<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
@@ -1122,7 +1125,7 @@ static int launchIteration(bf_ctx* c)
     } else if (c->splitKernels && !c->pipelined) { // product path: one launch per sweep
         LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
-        LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
+        LAUNCH_SCHEME(beam_backward, c->grid, BWD_SMEM_BYTES, p);
         c->launches += 2;
     } else if (c->pipelined) { // experiment (BEAMGPU_PIPELINE=1): persistent blocks, sweeps of different tiles overlap
         if (++c->epoch == 0x7fffffff) { // flags compare equal to the epoch: start over before it wraps
