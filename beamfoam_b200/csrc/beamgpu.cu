@@ -484,7 +484,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     {
         char* cur;
         if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->grid + 3 * (size_t)((c->N + 127) / 128) + 8) + sizeof(int) * (CTL_INTS + (size_t)c->grid) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
-        c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
+        c->d_uP = carve<double>(cur, 42 * nc_ * bp); c->d_bP = nullptr; // uPrime and bPrime share one array (scratchBase)
         c->d_partial = carve<double>(cur, 3 * (size_t)c->grid + 3 * (size_t)((c->N + 127) / 128)); c->d_sums = carve<double>(cur, 8);
         c->d_ctl = carve<int>(cur, CTL_INTS); c->d_fDone = carve<int>(cur, (size_t)c->grid);
         c->epoch = 0;
