@@ -84,8 +84,8 @@ struct BeamParams {
     double *Wb, *Thb, *Lamb, *DWb, *DThb, *force;
     const double *wPresc, *thPresc, *follower, *offset, *moment, *springK, *springDir;
     // block-Thomas scratch
-    double* uP; // [tile][nmax][21 pairs][32][2]: uPrime (36) and bPrime (6) of a cell, see scratchBase
-    double* bP; // unused (the right-hand sides live in the last three pairs of uP)
+    double* uP; // [tile][nmax][36][32]
+    double* bP; // [tile][nmax][6][32]
     // per-tile partial sums: [3][nTiles], tile = 128 consecutive beams (one block's worth)
     double* partial;
     // pipelined launch (beam_newton_pipelined): tickets and per-tile "forward done" flags
@@ -130,20 +130,6 @@ DEV V3 gammaOf(const M3& Lm, V3 e0, V3 t) { return mulT(Lm, t) - e0; }
 // tileRow(T, R, r, nc, lane) = first component of row r (cell or face) of the lane's beam.
 #define TS ((size_t)32)
 DEV size_t tileRow(size_t T, int R, int r, int nc, int lane) { return ((T * (size_t)R + (size_t)r) * nc) * TS + lane; }
-
-// Block-Thomas scratch of a cell: 42 doubles (uPrime row-major 36, then bPrime 6) as 21 PAIRS, the pair q of lane l at
-// double index (((T*R + i)*21 + q)*32 + l)*2: a lane's pair is 16 contiguous bytes (one STG.128 / one 16-byte cp.async /
-// one LDS.128 instead of two 8-byte ones), a warp's pair row 512 contiguous bytes, a cell 21 x 512 B.
-#define SCR_PAIRS 21
-DEV size_t scratchBase(size_t T, int R, int i, int lane) { return (((T * (size_t)R + (size_t)i) * SCR_PAIRS) * 32 + lane) * 2; }
-DEV void stPair(double* p, double a, double b)
-{
-#ifdef BEAM_NO_STREAM_HINTS
-    *(double2*)p = make_double2(a, b);
-#else
-    __stcs((double2*)p, make_double2(a, b));
-#endif
-}
 
 // L2 prefetch of the rows the NEXT loop iteration will read.  The serial recurrence of a beam
 // leaves only ~2 resident warps per scheduler (register-bound), so the DRAM latency of the loads
@@ -483,9 +469,6 @@ DEV void cpAsync8(double* dstSmem, const double* srcGlobal)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal) : "memory");
 }
 DEV void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-DEV void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-DEV void cpAsyncWaitGroup() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // Orders this thread's generic-proxy accesses to shared memory (the LDS reads of the buffer, the cp.async writes into it)
 // before later async-proxy writes to the same rows (the next bulk copy).  Every lane executes it, then the warp
 // synchronises, then the elected lane issues the copy.
@@ -884,20 +867,22 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
         X1[0][c] = x1.x; X1[1][c] = x1.y; X1[2][c] = x1.z;
         X2[0][c] = x2.x; X2[1][c] = x2.y; X2[2][c] = x2.z;
     }
-    // ---- store uPrime (36) and bPrime (6) as 21 pairs (scratchBase)
-    double* sp = p.uP + scratchBase((size_t)(b >> 5), p.nmax, i, b & 31);
+    // ---- store uPrime (36) and bPrime (6)
+    const size_t u0 = tileRow((size_t)(b >> 5), p.nmax, i, 36, b & 31), b0 = tileRow((size_t)(b >> 5), p.nmax, i, 6, b & 31);
     if (!LAST) {
 #pragma unroll
         for (int r = 0; r < 3; r++)
 #pragma unroll
-            for (int c = 0; c < 6; c += 2) {
-                stPair(sp + (size_t)((6 * r + c) / 2) * 64, X1[r][c], X1[r][c + 1]);
-                stPair(sp + (size_t)((6 * (r + 3) + c) / 2) * 64, X2[r][c], X2[r][c + 1]);
+            for (int c = 0; c < 6; c++) {
+                stS(p.uP + u0 + (size_t)(6 * r + c) * TS, X1[r][c]);
+                stS(p.uP + u0 + (size_t)(6 * (r + 3) + c) * TS, X2[r][c]);
             }
     }
-    stPair(sp + (size_t)18 * 64, X1[0][6], X1[1][6]);
-    stPair(sp + (size_t)19 * 64, X1[2][6], X2[0][6]);
-    stPair(sp + (size_t)20 * 64, X2[1][6], X2[2][6]);
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        stS(p.bP + b0 + (size_t)r * TS, X1[r][6]);
+        stS(p.bP + b0 + (size_t)(r + 3) * TS, X2[r][6]);
+    }
     if (!LAST) {
         // ---- carry for cell i+1, one row of l at a time, each entry one fused chain that starts from d_nei:
         //      Dc[r][c] = d_nei[r][c] - sum_k l[r][k] X[k][c];   -lb[r] = 0 - sum_k l[r][k] X[k][6]
@@ -1087,10 +1072,6 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
 // ---------------------------------------------------------------------------
 // backward: back-substitution + BC evaluate + updateSolutionVariables + norms
 // ---------------------------------------------------------------------------
-// Shared-memory stage of the backward sweep (bwdStageScratch): rows per stage, two stages per warp.  Staging the rows of
-// face i+1 as well (13 more rows per stage) was measured: 2.44 ms against 1.98 ms.
-#define BWD_STAGE_DOUBLES (SCR_PAIRS * 64) // one cell's scratch of one warp: 21 pair rows x 32 lanes x 2
-#define BWD_SMEM_BYTES ((BEAM_THREADS / 32) * 2 * BWD_STAGE_DOUBLES * sizeof(double))
 struct FaceState {
     Q4 Lf;
     V3 K, Q, M;
@@ -1259,14 +1240,14 @@ DEV void updateFacesOfCell(const BeamParams& p, const int b, const int i, const 
         const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f4 = tileRow(T, Rf, i + 1, 4, lane);
         const Q4 qfOld = ldq(p.Lf, f4, s);
         const V3 Kold = ld3(p.K, f3, s);
-        const V3 Qold = ld3(p.Q, f3, s), Mold = ld3(p.M, f3, s);
         FaceState o;
         if (i == n - 1) { // right patch
-            o = patchUpdate(p, 1, b, qfOld, CQ, CM, Kold, Qold, Mold, Wold, DW, DT, dcB, delta);
+            o = patchUpdate(p, 1, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s), Wold, DW, DT, dcB, delta);
         } else {
             const M3 LmOld = quatToMat(qfOld);
             const V3 t = dR0 + dcI * (WoldN - Wold);
-            const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, t), Kold, Qold, Mold, t, dcI, false);
+            const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, t), Kold,
+                                                ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcI, false);
             o = updateFace(f, qfOld, LmOld, Kold, DW, xWn, DT, xTn, dcI, false);
         }
         stq(p.Lf, f4, s, o.Lf);
@@ -1283,33 +1264,8 @@ DEV void updateFacesOfCell(const BeamParams& p, const int b, const int i, const 
     }
 }
 
-// The block-Thomas scratch of a cell (uPrime 36 + bPrime 6) is the first thing the backward step needs and the largest
-// thing it reads.  With a shared-memory slab (sm != null: two stages of 42 rows per warp, [row][32 lanes], a lane only ever
-// touches its own column, so no warp-level synchronisation) every lane brings the scratch of cell i-1 in by cp.async while
-// it works on cell i, straight from DRAM; without a slab the rows are L2-prefetched one cell ahead and loaded at the top.
-DEV void cpAsync16(double* dstSmem, const double* srcGlobal)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal) : "memory");
-}
-// stage = this lane's first pair of the stage (warp slab + lane*2)
-DEV void bwdStageScratch(const BeamParams& p, const size_t T, const int lane, const int i, double* stage)
-{
-    const double* src = p.uP + scratchBase(T, p.nmax, i, lane);
-#pragma unroll
-    for (int q = 0; q < SCR_PAIRS; q++) cpAsync16(stage + q * 64, src + (size_t)q * 64);
-    cpAsyncCommit();
-}
-DEV double2 ldsPair(const double* p)
-{
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smemAddr(p)));
-    return v;
-}
-// entry k (0..35 uPrime row-major, 36..41 bPrime) of a cell's scratch
-DEV double scrGl(const double* src, int k) { return __ldcg(src + (size_t)(k >> 1) * 64 + (k & 1)); }
-
 template <int SCHEME>
-DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2, double* sm = nullptr)
+DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2)
 {
     const size_t s = TS;
     const size_t T = (size_t)(b >> 5);
@@ -1330,14 +1286,14 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
 
         V3 xWn = v3(0, 0, 0), xTn = v3(0, 0, 0); // x_{i+1}
         V3 WoldN = v3(0, 0, 0);
-        if (sm && n > 0) bwdStageScratch(p, T, lane, n - 1, sm + ((n - 1) & 1) * BWD_STAGE_DOUBLES);
         for (int i = n - 1; i >= 0; i--) {
             // ---- back substitution: x_i = bPrime_i - uPrime_i & x_{i+1}
-            if (sm && i >= 1) bwdStageScratch(p, T, lane, i - 1, sm + ((i - 1) & 1) * BWD_STAGE_DOUBLES);
+            const size_t u0 = tileRow(T, Rc, i, 36, lane), b0 = tileRow(T, Rc, i, 6, lane);
             if (i >= BEAM_PF_DIST) { // prefetch what iteration i-D reads: scratch and cell i-D, face i-D+1
                 const int ic = i - BEAM_PF_DIST;
                 const size_t m3 = tileRow(T, Rc, ic, 3, lane), g3 = tileRow(T, Rf, ic + 1, 3, lane);
-                if (!sm) pfRows<SCR_PAIRS>(p.uP, scratchBase(T, Rc, ic, lane), 64);
+                pfRows<36>(p.uP, tileRow(T, Rc, ic, 36, lane), s);
+                pfRows<6>(p.bP, tileRow(T, Rc, ic, 6, lane), s);
                 pfRows<3>(p.W, m3, s); pfRows<3>(p.Th, m3, s);
                 pfRows<4>(p.Lam, tileRow(T, Rc, ic, 4, lane), s);
                 if (SCHEME == BFK_NEWMARK) {
@@ -1349,38 +1305,16 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
                 pfRows<3>(p.Q, g3, s); pfRows<3>(p.M, g3, s);
             }
             double x[6];
-            if (sm) {
-                if (i >= 1) cpAsyncWaitGroup<1>(); else cpAsyncWaitGroup<0>(); // all but the group just committed
-                const double* st = sm + (i & 1) * BWD_STAGE_DOUBLES;
-                auto pairAt = [&](int q) { return ldsPair(st + q * 64); }; // LDS.128, conflict-free
-                {
-                    const double2 b0 = pairAt(18), b1 = pairAt(19), b2 = pairAt(20);
-                    x[0] = b0.x; x[1] = b0.y; x[2] = b1.x; x[3] = b1.y; x[4] = b2.x; x[5] = b2.y;
-                }
-                if (i < n - 1) {
-                    const double xn[6] = {xWn.x, xWn.y, xWn.z, xTn.x, xTn.y, xTn.z};
 #pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        const double2 u0 = pairAt(3 * r), u1 = pairAt(3 * r + 1), u2 = pairAt(3 * r + 2);
-                        double acc = 0.0;
-                        acc += u0.x * xn[0]; acc += u0.y * xn[1]; acc += u1.x * xn[2];
-                        acc += u1.y * xn[3]; acc += u2.x * xn[4]; acc += u2.y * xn[5];
-                        x[r] -= acc;
-                    }
-                }
-            } else {
-                const double* src = p.uP + scratchBase(T, Rc, i, lane);
+            for (int r = 0; r < 6; r++) x[r] = __ldcg(p.bP + b0 + (size_t)r * s); // written by another SM in this launch: L2
+            if (i < n - 1) {
+                const double xn[6] = {xWn.x, xWn.y, xWn.z, xTn.x, xTn.y, xTn.z};
 #pragma unroll
-                for (int r = 0; r < 6; r++) x[r] = scrGl(src, 36 + r); // written by another SM in this launch: L2
-                if (i < n - 1) {
-                    const double xn[6] = {xWn.x, xWn.y, xWn.z, xTn.x, xTn.y, xTn.z};
+                for (int r = 0; r < 6; r++) {
+                    double acc = 0.0;
 #pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int c = 0; c < 6; c++) acc += scrGl(src, 6 * r + c) * xn[c];
-                        x[r] -= acc;
-                    }
+                    for (int c = 0; c < 6; c++) acc += __ldcg(p.uP + u0 + (size_t)(6 * r + c) * s) * xn[c];
+                    x[r] -= acc;
                 }
             }
             const V3 DW = v3(x[0], x[1], x[2]), DT = v3(x[3], x[4], x[5]);
@@ -1510,15 +1444,9 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(co
 template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_backward(const BeamParams p)
 {
-    extern __shared__ __align__(128) unsigned char beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
-#ifdef BEAM_BWD_NO_ASYNC_SCRATCH
-    double* slab = nullptr;
-#else
-    double* slab = (double*)beam_smem + (size_t)(threadIdx.x >> 5) * 2 * BWD_STAGE_DOUBLES + (threadIdx.x & 31) * 2;
-#endif
-    if (b < p.B) backwardSweep<SCHEME>(p, b, v[0], v[1], slab);
+    if (b < p.B) backwardSweep<SCHEME>(p, b, v[0], v[1]);
     blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
 }
 

@@ -401,9 +401,6 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     OPT_IN_SMEM(beam_newton_pipelined);
     OPT_IN_SMEM(beam_newton);
     OPT_IN_SMEM(beam_forward);
-    CREATE_CUDA(cudaFuncSetAttribute(beam_backward<BFK_STEADY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_backward<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_backward<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
@@ -484,7 +481,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     {
         char* cur;
         if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->grid + 3 * (size_t)((c->N + 127) / 128) + 8) + sizeof(int) * (CTL_INTS + (size_t)c->grid) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
-        c->d_uP = carve<double>(cur, 42 * nc_ * bp); c->d_bP = nullptr; // uPrime and bPrime share one array (scratchBase)
+        c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
         c->d_partial = carve<double>(cur, 3 * (size_t)c->grid + 3 * (size_t)((c->N + 127) / 128)); c->d_sums = carve<double>(cur, 8);
         c->d_ctl = carve<int>(cur, CTL_INTS); c->d_fDone = carve<int>(cur, (size_t)c->grid);
         c->epoch = 0;
@@ -1125,7 +1122,7 @@ static int launchIteration(bf_ctx* c)
     } else if (c->splitKernels && !c->pipelined) { // product path: one launch per sweep
         LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
-        LAUNCH_SCHEME(beam_backward, c->grid, BWD_SMEM_BYTES, p);
+        LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
         c->launches += 2;
     } else if (c->pipelined) { // experiment (BEAMGPU_PIPELINE=1): persistent blocks, sweeps of different tiles overlap
         if (++c->epoch == 0x7fffffff) { // flags compare equal to the epoch: start over before it wraps
