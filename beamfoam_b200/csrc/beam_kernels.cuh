@@ -1441,8 +1441,11 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(co
     v[0] = forwardSweep<SCHEME>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
     blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
+#ifndef BEAM_BWD_MIN_BLOCKS
+#define BEAM_BWD_MIN_BLOCKS BEAM_MIN_BLOCKS
+#endif
 template <int SCHEME>
-__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_backward(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backward(const BeamParams p)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
