@@ -72,7 +72,8 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a background thread every 5 ms (so that a
+    timed region of a few steps still gets samples), nvidia-smi -lms 200 as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -81,8 +82,42 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []   # (sm_mhz, reason bitmask)
+        self.running = False
+        self.thread = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # the CUDA ordinal of this process and the NVML index agree unless CUDA_VISIBLE_DEVICES reorders: go by UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+
+    def _poll(self, nv, h):
+        while self.running:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            nv, h = self._nvml_handle()
+            self.nvml = (nv, h)
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
@@ -96,6 +131,20 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            nv, h = self.nvml
+            self.running = False
+            self.thread.join(timeout=1.0)
+            try:
+                mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            sm = [a for a, _ in self.samples]
+            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 5 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -118,7 +167,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
 def make_case(args, world):
