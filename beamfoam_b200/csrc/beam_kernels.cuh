@@ -498,7 +498,15 @@ DEV void fwdPrefetchFace(const BeamParams& p, size_t T, double* warpSm, uint64_t
 {
     const int Rc = p.nmax, Rf = p.nmax + 1;
     const int lane = laneId();
-    if (SCHEME == BFK_NEWMARK) { // the cell rows of the same cell: pull them into L2 now, the bulk copy follows a phase later
+    if (SCHEME == BFK_EULER) { // the cell rows the Euler inertia terms read (fwdPrefetchCell)
+        const int ic = min(i + BEAM_PFCELL_DIST - 1, Rc - 1);
+        const size_t n3 = tileRow(T, Rc, ic, 3, 0) + 3 * lane;
+        pfNm(p.Lam + tileRow(T, Rc, ic, 4, 0) + 4 * lane);
+        pfNm(p.U + n3);
+        pfNm(p.Om + n3);
+        if (!p.first) { pfNm(p.Uold + n3); pfNm(p.Omold + n3); }
+    }
+    if (SCHEME == BFK_NEWMARK) { // the cell rows of the same cell: pull them into L2 now, the cp.async follows a phase later
         // one address per lane and array: nc rows x 32 doubles are contiguous, lane l touches double nc*l, so every
         // 32-byte sector of the nc x 256 B run is requested once
         const int ic = min(i + BEAM_PFCELL_DIST - 1, Rc - 1);
@@ -519,6 +527,7 @@ DEV void fwdPrefetchFace(const BeamParams& p, size_t T, double* warpSm, uint64_t
     bulkLoad(buf + B_Q * 32, p.Q + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
     bulkLoad(buf + B_M * 32, p.M + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
 }
+template <int SCHEME>
 DEV void fwdPrefetchCell(const BeamParams& p, size_t T, double* sm, int i)
 {
     const int Rc = p.nmax, lane = laneId();
@@ -526,15 +535,30 @@ DEV void fwdPrefetchCell(const BeamParams& p, size_t T, double* sm, int i)
     double* buf = sm + (size_t)R_BUF * 32;
 #pragma unroll
     for (int k = 0; k < 4; k++) cpAsync8(buf + (C_LAM + k) * 32, p.Lam + c4 + k * TS);
+    if (SCHEME == BFK_NEWMARK) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        cpAsync8(buf + (C_AC + k) * 32, p.Ac + c3 + k * TS);
-        cpAsync8(buf + (C_OM + k) * 32, p.Om + c3 + k * TS);
-        cpAsync8(buf + (C_DOM + k) * 32, p.dOm + c3 + k * TS);
-    }
-    if (p.first) {
+        for (int k = 0; k < 3; k++) {
+            cpAsync8(buf + (C_AC + k) * 32, p.Ac + c3 + k * TS);
+            cpAsync8(buf + (C_OM + k) * 32, p.Om + c3 + k * TS);
+            cpAsync8(buf + (C_DOM + k) * 32, p.dOm + c3 + k * TS);
+        }
+        if (p.first) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) cpAsync8(buf + (C_U + k) * 32, p.U + c3 + k * TS);
+            for (int k = 0; k < 3; k++) cpAsync8(buf + (C_U + k) * 32, p.U + c3 + k * TS);
+        }
+    } else { // Euler: U, Omega and their old-time level (in the rows Newmark uses for Accl and dotOmega)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            cpAsync8(buf + (C_U + k) * 32, p.U + c3 + k * TS);
+            cpAsync8(buf + (C_OM + k) * 32, p.Om + c3 + k * TS);
+        }
+        if (!p.first) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                cpAsync8(buf + (C_AC + k) * 32, p.Uold + c3 + k * TS);
+                cpAsync8(buf + (C_DOM + k) * 32, p.Omold + c3 + k * TS);
+            }
+        }
     }
 }
 
@@ -621,20 +645,28 @@ DEV void pointForceSource(const BeamParams& p, const int b, const int i, double*
 
 // Loads (Evolve.C:193-279) and inertia (Evolve.C:320-536, with the Newmark predictor :167-186 on the first iteration
 // of a time step) of cell i, added to its diagonal block and source.
-// The Newmark rows of a cell: the forward sweep brings them in by cp.async (fwdPrefetchCell / loadCellInSm); the other
-// callers (Euler and steadyState, the cell-parallel path) load them directly.
+// The rows of a cell that the inertia terms read: the forward sweep brings them in by cp.async (fwdPrefetchCell /
+// loadCellInSm); the cell-parallel path loads them directly (loadCellIn).
 struct CellIn {
-    Q4 ql;
-    V3 Ac, Om, dOm, U;
+    Q4 ql;             // Lambda of the cell
+    V3 Ac, Om, dOm, U; // Newmark: Accl, Omega*, dotOmega, U* (U* on the first iteration only)
+                       // Euler:   U.oldTime, Omega, Omega.oldTime, U
 };
+template <int SCHEME>
 DEV CellIn loadCellInSm(const double* sm, bool first)
 {
     CellIn c;
     c.ql = smLdq(sm, R_BUF + C_LAM);
-    c.Ac = smLd3(sm, R_BUF + C_AC);
     c.Om = smLd3(sm, R_BUF + C_OM);
-    c.dOm = smLd3(sm, R_BUF + C_DOM);
-    c.U = first ? smLd3(sm, R_BUF + C_U) : v3(0, 0, 0);
+    if (SCHEME == BFK_NEWMARK) {
+        c.Ac = smLd3(sm, R_BUF + C_AC);
+        c.dOm = smLd3(sm, R_BUF + C_DOM);
+        c.U = first ? smLd3(sm, R_BUF + C_U) : v3(0, 0, 0);
+    } else { // on the first iteration of a step the old-time level IS the current one (the backward sweep stores it)
+        c.U = smLd3(sm, R_BUF + C_U);
+        c.Ac = first ? c.U : smLd3(sm, R_BUF + C_AC);
+        c.dOm = first ? c.Om : smLd3(sm, R_BUF + C_DOM);
+    }
     return c;
 }
 template <int SCHEME>
@@ -643,10 +675,15 @@ DEV CellIn loadCellIn(const BeamParams& p, const int b, const int i)
     CellIn c;
     c.ql = q4(1, 0, 0, 0);
     c.Ac = c.Om = c.dOm = c.U = v3(0, 0, 0);
+    const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31), c4 = tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31);
     if (SCHEME == BFK_NEWMARK) {
-        const size_t c3 = tileRow((size_t)(b >> 5), p.nmax, i, 3, b & 31), c4 = tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31);
         c.ql = ldq(p.Lam, c4, TS); c.Ac = ld3(p.Ac, c3, TS); c.Om = ld3(p.Om, c3, TS); c.dOm = ld3(p.dOm, c3, TS);
         if (p.first) c.U = ld3(p.U, c3, TS);
+    }
+    if (SCHEME == BFK_EULER) {
+        c.ql = ldq(p.Lam, c4, TS); c.U = ld3(p.U, c3, TS); c.Om = ld3(p.Om, c3, TS);
+        c.Ac = p.first ? c.U : ld3(p.Uold, c3, TS);
+        c.dOm = p.first ? c.Om : ld3(p.Omold, c3, TS);
     }
     return c;
 }
@@ -704,10 +741,8 @@ DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const
     }
     if (SCHEME == BFK_EULER) { // Evolve.C:385-400, 490-513 with fvc::ddt(X) = (X - X.oldTime())/deltaT
         const double idt = 1.0 / dt;
-        const M3 Lm = quatToMat(ldq(p.Lam, tileRow((size_t)(b >> 5), p.nmax, i, 4, b & 31), TS));
-        const V3 U = ld3(p.U, c3, TS), Om = ld3(p.Om, c3, TS);
-        // on the first iteration of a step the old-time level IS the current one (the backward sweep stores it)
-        const V3 Uold = p.first ? U : ld3(p.Uold, c3, TS), Omold = p.first ? Om : ld3(p.Omold, c3, TS);
+        const M3 Lm = quatToMat(cell.ql);
+        const V3 U = cell.U, Om = cell.Om, Uold = cell.Ac, Omold = cell.dOm; // see CellIn
         const V3 CIOm = cmul(CI, Om);
         const V3 gyro = cross(Om, CIOm);
         const V3 a = mul(Lm, cmul(CI, idt * (Om - Omold)) + gyro);
@@ -955,9 +990,9 @@ __device__ __noinline__ void fwdCellGeneric(const BeamParams& p, const int b, do
     double res = 0.0;
     mbarWait(bar, *phase & 1u);
     const FaceIn in = loadFaceIn(sm);
-    if (SCHEME != BFK_NEWMARK) fenceProxyAsync();
+    if (SCHEME == BFK_STEADY) fenceProxyAsync();
     __syncwarp();
-    if (SCHEME == BFK_NEWMARK) fwdPrefetchCell(p, T, sm, i);
+    if (SCHEME != BFK_STEADY) fwdPrefetchCell<SCHEME>(p, T, sm, i);
     else if (i + 1 < nW) fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
     const int nb = (int)smLd(sm, R_N); // cells of this lane's beam
     const bool interior = i < nb - 1;  // a cell with an internal face on its right
@@ -967,9 +1002,9 @@ __device__ __noinline__ void fwdCellGeneric(const BeamParams& p, const int b, do
         fwdFacePart<false>(p, b, sm, rcpFast(dz), 0.5 * dz, in, Dc, src, Wi);
     }
     CellIn cell;
-    if (SCHEME == BFK_NEWMARK) {
+    if (SCHEME != BFK_STEADY) {
         cpAsyncWaitAll();
-        cell = loadCellInSm(sm, p.first != 0);
+        cell = loadCellInSm<SCHEME>(sm, p.first != 0);
         fenceProxyAsync();
         __syncwarp();
         if (i + 1 < nW) fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
@@ -1043,17 +1078,17 @@ DEV double forwardSweep(const BeamParams& p, const int b, double* __restrict__ w
     for (; i < nFast; i++) {
         mbarWait(bar, phase & 1u);
         const FaceIn in = loadFaceIn(sm);
-        if (SCHEME != BFK_NEWMARK) fenceProxyAsync();
+        if (SCHEME == BFK_STEADY) fenceProxyAsync();
         __syncwarp(); // every lane holds its buffer rows in registers: the buffer is free for the next fill
-        if (SCHEME == BFK_NEWMARK) fwdPrefetchCell(p, T, sm, i);
+        if (SCHEME != BFK_STEADY) fwdPrefetchCell<SCHEME>(p, T, sm, i);
         else fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
         double src[6], Dc[6][6];
         const double dz = smLd(sm, R_DZ);
         fwdFacePart<false>(p, b, sm, rcpFast(dz), 0.5 * dz, in, Dc, src, Wi);
         CellIn cell;
-        if (SCHEME == BFK_NEWMARK) { // the Newmark rows of cell i have arrived; hand the buffer to face i+2 / cell i+1
+        if (SCHEME != BFK_STEADY) { // the cell rows of cell i have arrived; hand the buffer to face i+2 / cell i+1
             cpAsyncWaitAll();
-            cell = loadCellInSm(sm, p.first != 0);
+            cell = loadCellInSm<SCHEME>(sm, p.first != 0);
             fenceProxyAsync();
             __syncwarp();
             fwdPrefetchFace<SCHEME>(p, T, warpSm, bar, i + 1);
