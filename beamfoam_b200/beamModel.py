@@ -165,6 +165,8 @@ class coupledTotalLagNewtonRaphsonBeam:
         self._bcs = {}
         self._bcCache = {}
         self._bcUploaded = set()
+        self._pinnedBC = {}
+        self._pinnedPtrs = []
         self.h2dBytes = 0  # bytes handed to bf_set_bc_values so far
         wType = np.zeros(2 * B, np.int32)
         thType = np.zeros(2 * B, np.int32)
@@ -260,6 +262,10 @@ class coupledTotalLagNewtonRaphsonBeam:
         if getattr(self, "_ctx", None):
             self.lib.bf_destroy(self._ctx)
             self._ctx = None
+            self._pinnedBC = {}
+            for ptr in self._pinnedPtrs:
+                self.lib.bf_host_free(ptr)
+            self._pinnedPtrs = []
 
     def __del__(self):
         try:
@@ -376,10 +382,24 @@ class coupledTotalLagNewtonRaphsonBeam:
                     v = vals
                     if objs is not None and len(kinds) > 1:
                         v = np.where(np.array([o.kind == kind for o in objs])[:, None], vals, 0.0)
-                    v = np.ascontiguousarray(v)
-                    self._check(self.lib.bf_set_bc_values(self._ctx, end, kind, v.ctypes.data))
-                    self.h2dBytes += v.nbytes
+                    buf = self._pinned_bc(end, var, kind)  # page-locked staging: the H2D copy is a plain DMA
+                    np.copyto(buf, v)
+                    self._check(self.lib.bf_set_bc_values(self._ctx, end, kind, buf.ctypes.data))
+                    self.h2dBytes += buf.nbytes
                 self._bcUploaded.add((end, var))
+
+    def _pinned_bc(self, end: int, var: str, kind: int) -> np.ndarray:
+        """[nBeams, 3] page-locked host array (bf_host_alloc: cudaHostAlloc in libbeamgpu, malloc in the oracle) that the
+        boundary values of one patch side are staged in before they cross the ABI."""
+        key = (end, var, kind)
+        buf = self._pinnedBC.get(key)
+        if buf is None:
+            ptr = C.c_void_p()
+            self._check(self.lib.bf_host_alloc(C.byref(ptr), self._B * 3 * 8))
+            self._pinnedPtrs.append(ptr)
+            buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(self._B, 3))
+            self._pinnedBC[key] = buf
+        return buf
 
     def updatePointForces(self, t: float):
         """pointForces()[pfI].second()(runTime().value()) (Evolve.C:219): evaluate the point-force series at
