@@ -17,7 +17,8 @@
 //
 // Output (instead of the function objects of system/controlDict): <case>/history/beamConvergenceData.dat
 // (time, iOuterCorr, initial residual: functionObjects/beamConvergenceData) and history/beamDisplacements_right.dat
-// (time, then W_b and Theta_b of the right patch of every beam: functionObjects/beamDisplacements).
+// (time, then W_b and Theta_b of the right patch of every beam: functionObjects/beamDisplacements); every writeInterval
+// steps the time directory <case>/<time>/{W,Theta} in OpenFOAM ASCII format (runTime.write()).
 #include "foamDictionary.hpp"
 #include "../include/beamgpu.h"
 
@@ -177,6 +178,8 @@ struct BeamCase {
     std::vector<bf_momentum_contribution> contributions; // constant/beamMomentumContributionProperties
     bool rotated = false;
     double deltaT = 1, endTime = 1;
+    int writeInterval = 0;             // system/controlDict writeControl timeStep; writeInterval n; (0: no field output)
+    int writePrecision = 6;
     int device = 0;
 };
 bool exists(const std::string& p) { struct stat s; return stat(p.c_str(), &s) == 0; }
@@ -263,6 +266,8 @@ void readCase(BeamCase& c)
     {
         const auto cd = foam::readDictionary(c.dir + "/system/controlDict");
         c.deltaT = cd->scalar("deltaT");
+        if (cd->wordOr("writeControl", "timeStep") == "timeStep") c.writeInterval = (int)cd->scalarOr("writeInterval", 0);
+        c.writePrecision = (int)cd->scalarOr("writePrecision", 6);
         c.endTime = cd->scalar("endTime");
     }
     if (exists(c.dir + "/constant/g")) c.g = foam::readDictionary(c.dir + "/constant/g")->vector("value");
@@ -425,6 +430,35 @@ int setInitialPositionBeam(BeamCase& c, const std::string& zone, const std::stri
         if (rc_ != BF_OK) fatal(std::string(#call) + " failed (" + std::to_string(rc_) + "): " + abi.bf_last_error(ctx)); \
     } while (0)
 
+// runTime.write() (beamFoam.C:87) for the two solution fields: <case>/<time>/W and Theta as OpenFOAM ASCII volVectorFields
+// (nonuniform internalField in createBeamMesh cell order, one value per end patch), readable by the reference's tools.
+std::string timeName(double t)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.6g", t); // timeFormat general, timePrecision 6
+    return buf;
+}
+void writeVolVectorField(const BeamCase& c, const std::string& dir, const char* name, const char* dims, const vec& I,
+                         const vec& L, const vec& R, const std::vector<PatchField> bc[2])
+{
+    FILE* f = fopen((dir + "/" + name).c_str(), "w");
+    if (!f) fatal("cannot write " + dir + "/" + name);
+    const int P = c.writePrecision;
+    fprintf(f, "FoamFile\n{\n    version     2.0;\n    format      ascii;\n    class       volVectorField;\n    object      %s;\n}\n\n", name);
+    fprintf(f, "dimensions      %s;\n\ninternalField   nonuniform List<vector>\n%zu\n(\n", dims, I.size() / 3);
+    for (size_t i = 0; i < I.size(); i += 3) fprintf(f, "(%.*g %.*g %.*g)\n", P, I[i], P, I[i + 1], P, I[i + 2]);
+    fprintf(f, ")\n;\n\nboundaryField\n{\n");
+    for (int b = 0; b < c.nBeams; b++)
+        for (int end = 0; end < 2; end++) {
+            const std::string pn = c.nBeams == 1 ? (end ? "right" : "left") : (end ? "right_" : "left_") + std::to_string(b);
+            const vec& v = end ? R : L;
+            fprintf(f, "    %s\n    {\n        type            %s;\n        value           uniform (%.*g %.*g %.*g);\n    }\n", pn.c_str(),
+                    bc[end][b].type.c_str(), P, v[3 * b], P, v[3 * b + 1], P, v[3 * b + 2]);
+        }
+    fprintf(f, "    beam\n    {\n        type            empty;\n    }\n}\n");
+    fclose(f);
+}
+
 int beamFoam(BeamCase& c, const std::string& libPath, int maxSteps)
 {
     readCase(c);
@@ -533,6 +567,15 @@ int beamFoam(BeamCase& c, const std::string& libPath, int maxSteps)
         totalIter += out.nIter;
         CHECK(abi.bf_get_field(ctx, BF_FIELD_W, nullptr, nullptr, Wr.data()));
         CHECK(abi.bf_get_field(ctx, BF_FIELD_THETA, nullptr, nullptr, Tr.data()));
+        if (c.writeInterval > 0 && step % c.writeInterval == 0) { // runTime.write()
+            vec WI(3 * nCells), TI(3 * nCells), WL(3 * B), TL(3 * B);
+            CHECK(abi.bf_get_field(ctx, BF_FIELD_W, WI.data(), WL.data(), Wr.data()));
+            CHECK(abi.bf_get_field(ctx, BF_FIELD_THETA, TI.data(), TL.data(), Tr.data()));
+            const std::string td = c.dir + "/" + timeName(t);
+            mkdir(td.c_str(), 0755);
+            writeVolVectorField(c, td, "W", "[0 1 0 0 0 0 0]", WI, WL, Wr, c.W);
+            writeVolVectorField(c, td, "Theta", "[0 0 0 0 0 0 0]", TI, TL, Tr, c.Th);
+        }
         fprintf(fc, "%.12g %d %.17g\n", t, out.nIter, out.initialResidualNorm);
         fprintf(fd, "%.12g", t);
         for (int b = 0; b < B; b++)

@@ -124,6 +124,7 @@ def write_case(case, caseDir, rotateAngle=None):
     with open(os.path.join(caseDir, "system", "controlDict"), "w") as f:
         f.write(HEADER.format(cls="dictionary", obj="controlDict"))
         f.write(f"application     beamFoam;\nstartTime       0;\nendTime         {case.endTime!r};\ndeltaT          {case.deltaT!r};//comment\n"
+                "writeControl    timeStep;\nwriteInterval   3;\nwritePrecision  10;\n"
                 "functions\n{\n   beamDisplacements1\n   {\n       type    beamDisplacements;\n       historyPatch    right;\n   }\n}\n")
     with open(os.path.join(caseDir, "system", "fvSchemes"), "w") as f:
         f.write(HEADER.format(cls="dictionary", obj="fvSchemes"))
@@ -157,6 +158,26 @@ def run_host(exe, caseDir, lib, steps):
     conv = np.loadtxt(os.path.join(caseDir, "history", "beamConvergenceData.dat"), ndmin=2)
     disp = np.loadtxt(os.path.join(caseDir, "history", "beamDisplacements_right.dat"), ndmin=2)
     return conv, disp
+
+
+def read_written_field(caseDir, steps, deltaT, name):
+    """internalField of <case>/<time>/<name> at the last write time (writeInterval 3), or None if none was due."""
+    k = (steps // 3) * 3
+    if k == 0:
+        return None
+    path = os.path.join(caseDir, f"{k * deltaT:.6g}", name)
+    assert os.path.exists(path), path
+    vals, inside = [], False
+    for ln in open(path):
+        ln = ln.strip()
+        if ln.startswith("internalField"):
+            inside = True
+            continue
+        if inside and ln.startswith("(") and ln.endswith(")") and len(ln) > 2:
+            vals.append([float(x) for x in ln[1:-1].split()])
+        elif inside and ln == ";":
+            break
+    return k, np.array(vals)
 
 
 def run_python(case, lib, steps):
@@ -200,6 +221,14 @@ def _compare(exe, libPath, lib, tmp_path, tol):
         scale = np.max(np.abs(rows))
         assert np.max(np.abs(disp[:, 1:] - rows)) <= tol * scale, case.name
         np.testing.assert_allclose(conv[:, 2], its[:, 1], rtol=1e-9)
+        written = read_written_field(d, steps, case.deltaT, "W")  # runTime.write(): <time>/W in OpenFOAM format
+        if written is not None:
+            k, Wf = written
+            m = coupledTotalLagNewtonRaphsonBeam(case, library=lib)
+            m.run(nSteps=k)
+            Wp = m.get_field("W")[0]
+            m.close()
+            assert Wf.shape == Wp.shape and np.max(np.abs(Wf - Wp)) <= 1e-8 * max(np.max(np.abs(Wp)), 1e-300), case.name
 
 
 def test_cpp_host_matches_python_host_on_written_cases(host_exe, oracle_lib_path, tmp_path):
