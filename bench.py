@@ -354,7 +354,7 @@ def run_ours(args):
     kern_ms = (fwd.value + bwd.value) / max(nit.value, 1)
     peak, peak_src = hbm_peak()
     achieved = BYTES_PER_UPDATE_NEWMARK * nCellsLocal / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-    traffic, per_kernel = None, None
+    traffic, per_kernel, fp64_per_update = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
@@ -363,9 +363,12 @@ def run_ours(args):
         fms, bms = fwd.value / max(nit.value, 1), bwd.value / max(nit.value, 1)
         per_kernel = [
             {"kernel": "beam_forward<BFK_NEWMARK>", "ms": fms, "dram_bytes": tj.get("beam_forward_dram_bytes"),
-             "dram_GBs": tj.get("beam_forward_dram_bytes", 0) * scale / (fms * 1e-3) / 1e9 if fms > 0 else None},
+             "dram_GBs": tj.get("beam_forward_dram_bytes", 0) * scale / (fms * 1e-3) / 1e9 if fms > 0 else None,
+             "fp64_TFLOPs": tj.get("beam_forward_fp64_flop", 0) * scale / (fms * 1e-3) / 1e12 if fms > 0 else None},
             {"kernel": "beam_backward<BFK_NEWMARK>", "ms": bms, "dram_bytes": tj.get("beam_backward_dram_bytes"),
-             "dram_GBs": tj.get("beam_backward_dram_bytes", 0) * scale / (bms * 1e-3) / 1e9 if bms > 0 else None}]
+             "dram_GBs": tj.get("beam_backward_dram_bytes", 0) * scale / (bms * 1e-3) / 1e9 if bms > 0 else None,
+             "fp64_TFLOPs": tj.get("beam_backward_fp64_flop", 0) * scale / (bms * 1e-3) / 1e12 if bms > 0 else None}]
+        fp64_per_update = tj.get("fp64_flop_per_update")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -373,7 +376,10 @@ def run_ours(args):
                 "kernel_ms": kern_ms, "bytes_per_update": BYTES_PER_UPDATE_NEWMARK, "updates_per_launch": nCellsLocal,
                 "peak_source": peak_src, "kernel_share_of_step": (fwd.value + bwd.value) / ms.value,
                 "fwd_ms": fwd.value / max(nit.value, 1), "bwd_ms": bwd.value / max(nit.value, 1),
-                "launches": per_kernel}
+                "launches": per_kernel,
+                "fp64": {"flop_per_update": fp64_per_update,
+                         "achieved_TFLOPs": fp64_per_update * nCellsLocal / (kern_ms * 1e-3) / 1e12 if fp64_per_update and kern_ms > 0 else None,
+                         "note": "thread-level DFMA x2 + DMUL + DADD of one ncu capture (profiles/traffic.json); B200 FP64 peak ~37 TFLOP/s"}}
 
     # ---- timed region 2: end to end with host buffers
     e2e = None

@@ -57,7 +57,30 @@ for r, row in zip(summary, rows[2:]):
     name = "beam_forward" if "beam_forward" in row[col["Kernel Name"]] else "beam_backward" if "beam_backward" in row[col["Kernel Name"]] else row[col["Kernel Name"]]
     per[name] = gb(r["dram__bytes_read.sum"], unit("dram__bytes_read.sum")) + gb(r["dram__bytes_write.sum"], unit("dram__bytes_write.sum"))
 traffic = per.get("beam_forward", 0) + per.get("beam_backward", 0)
+# ---- FP64 work per launch from the source page: thread-level DFMA (2 flop), DMUL, DADD (1 flop)
+def fp64_flop(kernel):
+    raw = subprocess.run(["ncu", "-i", os.path.join(ROOT, "gpurun_out", "prof.ncu-rep"), "--page", "source", "--csv",
+                          "--kernel-name", f"regex:{kernel}"], capture_output=True, text=True).stdout
+    lines = raw.splitlines()
+    idx = [i for i, l in enumerate(lines) if l.startswith('"Kernel Name"')]
+    if not idx:
+        return None
+    block = list(csv.reader(lines[idx[0] + 1: idx[1] if len(idx) > 1 else None]))
+    c = {h: i for i, h in enumerate(block[0])}
+    flop = 0
+    for r in block[1:]:
+        src = r[c["Source"]].split()
+        if not src:
+            continue
+        op = (src[1] if src[0].startswith("@") else src[0]).split(".")[0]
+        w = {"DFMA": 2, "DMUL": 1, "DADD": 1}.get(op)
+        if w:
+            flop += w * int(r[c["Thread Instructions Executed"]])
+    return flop
+flops = {k: fp64_flop(k) for k in ("beam_forward", "beam_backward")}
 json.dump({"newton_iteration_dram_bytes": traffic, "beam_forward_dram_bytes": per.get("beam_forward"), "beam_backward_dram_bytes": per.get("beam_backward"),
-           "source": f"profiles/{tag}_newton_iteration_ncu.md", "cells_per_launch": 13107200, "bytes_per_update": traffic / 13107200},
+           "beam_forward_fp64_flop": flops["beam_forward"], "beam_backward_fp64_flop": flops["beam_backward"],
+           "source": f"profiles/{tag}_newton_iteration_ncu.md", "cells_per_launch": 13107200, "bytes_per_update": traffic / 13107200,
+           "fp64_flop_per_update": (flops["beam_forward"] + flops["beam_backward"]) / 13107200 if all(flops.values()) else None},
           open(os.path.join(out, "traffic.json"), "w"), indent=1)
-print("traffic per Newton iteration %.3f GB = %.0f B/update" % (traffic / 1e9, traffic / 13107200), per)
+print("traffic per Newton iteration %.3f GB = %.0f B/update" % (traffic / 1e9, traffic / 13107200), per, "fp64 flop", flops)
