@@ -168,6 +168,7 @@ class coupledTotalLagNewtonRaphsonBeam:
         self._pinnedBC = {}
         self._pinnedPtrs = []
         self.h2dBytes = 0  # bytes handed to bf_set_bc_values so far
+        self._beganStepAt = None  # time index of the last bf_begin_step
         wType = np.zeros(2 * B, np.int32)
         thType = np.zeros(2 * B, np.int32)
         springK = np.zeros(2 * B)
@@ -426,7 +427,11 @@ class coupledTotalLagNewtonRaphsonBeam:
         diverged / non-converged step raises (FatalError in the reference)."""
         self.updateCoeffs(self.time)
         self.updatePointForces(self.time)
-        self._check(self.lib.bf_begin_step(self._ctx, float(self.case.deltaT)))
+        if self._beganStepAt != self.timeIndex:
+            # runTime++ happened since the last evolve(): new old-time level, Newmark predictor on the first iteration.
+            # A second evolve() at the same time index (FSI outer iterations) continues from the current state.
+            self._check(self.lib.bf_begin_step(self._ctx, float(self.case.deltaT)))
+            self._beganStepAt = self.timeIndex
         out = L.bf_step_out()
         rc = self.lib.bf_evolve(self._ctx, C.byref(self.tol), C.byref(out))
         self.lastStep = out

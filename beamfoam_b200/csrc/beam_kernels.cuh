@@ -86,16 +86,9 @@ struct BeamParams {
     // block-Thomas scratch
     double* uP; // [tile][nmax][36][32]
     double* bP; // [tile][nmax][6][32]
-    // per-tile partial sums: [3][nTiles], tile = 128 consecutive beams (one block's worth)
+    // per-block partial sums: partial[slot * nTiles + block], nTiles = the stride of the array (>= blocks of any launch)
     double* partial;
-    // pipelined launch (beam_newton_pipelined): tickets and per-tile "forward done" flags
     int nTiles;
-    int pipePolicy; // 0: first block of an SM takes forward tickets, second backward tickets; 1: every block takes forward tickets
-                    // while there are any, then backward tickets (the forward sweep's partial last wave is filled with backward work)
-    int epoch;   // value a flag takes when the forward sweep of this launch has finished the tile
-    int* ctl;    // [0] next forward ticket, [1] next backward ticket, [2 + smid] blocks seen on an SM; zeroed per launch
-    int* fDone;  // [nTiles]
-    unsigned long long* trace; // optional [nTiles][4]: forward start/end, backward start/end (globaltimer ns), else null
 };
 
 // Everything the sweeps write is next read a whole sweep later (3.7 GB of state + 4.4 GB of scratch against 126 MB of
@@ -850,6 +843,48 @@ DEV void fwdFacePart(const BeamParams& p, const int b, double* __restrict__ sm, 
     }
 }
 
+// Fallback of the elimination step when a 3x3 pivot block of D'_i is ill-conditioned (smallDet, beam_math.cuh): the whole
+// 6x6 block by LU with partial pivoting, the way the reference's SparseLU treats it (EigenOF.C:292-297).  The right-hand
+// sides are rebuilt from the stash exactly as in fwdEliminate.  X42 = D'^{-1} [u | source - lb], row-major [6][7].
+__device__ __noinline__ void fwdSolvePivoted(const double* __restrict__ sm, const double* __restrict__ D36,
+                                             const double* __restrict__ src6, const int last, double* __restrict__ X42)
+{
+    double A[6][6], Bq[6][7];
+    const int pi[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) A[r][c] = D36[6 * r + c];
+    const V3 hM = smLd3(sm, R_MF);
+#pragma unroll
+    for (int c = 0; c < 7; c++) {
+        V3 r1 = v3(0, 0, 0), r2 = v3(0, 0, 0);
+        if (c < 3) {
+            if (!last) {
+                r1 = v3(smLd(sm, R_P + pi[c][0]), smLd(sm, R_P + pi[c][1]), smLd(sm, R_P + pi[c][2]));
+                r2 = -smLd3(sm, R_QT + 3 * c);
+            }
+        } else if (c < 6) {
+            if (!last) {
+                const int k = c - 3;
+                const V3 s2k = k == 0 ? v3(0.0, -hM.z, hM.y) : k == 1 ? v3(hM.z, 0.0, -hM.x) : v3(-hM.y, hM.x, 0.0);
+                r1 = v3(smLd(sm, R_QT + k), smLd(sm, R_QT + 3 + k), smLd(sm, R_QT + 6 + k));
+                r2 = v3(smLd(sm, R_S1 + pi[k][0]) + smLd(sm, R_S3 + k) + s2k.x, smLd(sm, R_S1 + pi[k][1]) + smLd(sm, R_S3 + 3 + k) + s2k.y,
+                        smLd(sm, R_S1 + pi[k][2]) + smLd(sm, R_S3 + 6 + k) + s2k.z);
+            }
+        } else {
+            r1 = v3(src6[0] + smLd(sm, R_LB), src6[1] + smLd(sm, R_LB + 1), src6[2] + smLd(sm, R_LB + 2));
+            r2 = v3(src6[3] + smLd(sm, R_LB + 3), src6[4] + smLd(sm, R_LB + 4), src6[5] + smLd(sm, R_LB + 5));
+        }
+        Bq[0][c] = r1.x; Bq[1][c] = r1.y; Bq[2][c] = r1.z; Bq[3][c] = r2.x; Bq[4][c] = r2.y; Bq[5][c] = r2.z;
+    }
+    solve6<7>(A, Bq);
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 7; c++) X42[7 * r + c] = Bq[r][c];
+}
+
 // Elimination step of cell i (second half): D'_i = Dc is factored by 2x2 block elimination over
 // 3x3 blocks, X = D'^{-1} [u_i | source_i - l_{i-1} bPrime_{i-1}] is formed column by column,
 // stored (uPrime, bPrime), and folded straight into the carry of cell i+1:
@@ -860,6 +895,7 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
                       const double (&src)[6])
 {
     M3 Ai, AiB, Si, Cm;
+    bool illConditioned;
     {
         M3 A, Bm, E;
 #pragma unroll
@@ -871,13 +907,29 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
                 Cm.a[3 * r + c] = Dc[3 + r][c];
                 E.a[3 * r + c] = Dc[3 + r][3 + c];
             }
-        Ai = inv(A);
+        double detA, detS, mA, mS;
+        Ai = invDet(A, detA, mA);
         AiB = mul(Ai, Bm);
-        Si = inv(subMulM(E, Cm, AiB));
+        Si = invDet(subMulM(E, Cm, AiB), detS, mS);
+        illConditioned = smallDet(detA, mA) || smallDet(detS, mS);
     }
     // ---- X = D'^{-1} [u | source - lb], column by column; u comes back from the stash.  R_LB holds -lb.
     double X1[3][7], X2[3][7];
     const int pi[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}}; // symmetric storage: xx xy xz yy yz zz
+    if (illConditioned) { // a 3x3 pivot block is (near-)singular: pivoted LU of the whole 6x6 block, out of line
+        double D36[36], s6[6], X42[42];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            s6[r] = src[r];
+#pragma unroll
+            for (int c = 0; c < 6; c++) D36[6 * r + c] = Dc[r][c];
+        }
+        fwdSolvePivoted(sm, D36, s6, LAST, X42);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 7; c++) { X1[r][c] = X42[7 * r + c]; X2[r][c] = X42[7 * (r + 3) + c]; }
+    } else {
 #pragma unroll
     for (int c = 0; c < 7; c++) {
         if (c < 6 && LAST) continue;
@@ -901,6 +953,7 @@ DEV void fwdEliminate(const BeamParams& p, const int b, double* __restrict__ sm,
         const V3 x1 = subMul(y1, AiB, x2);
         X1[0][c] = x1.x; X1[1][c] = x1.y; X1[2][c] = x1.z;
         X2[0][c] = x2.x; X2[1][c] = x2.y; X2[2][c] = x2.z;
+    }
     }
     // ---- store uPrime (36) and bPrime (6)
     const size_t u0 = tileRow((size_t)(b >> 5), p.nmax, i, 36, b & 31), b0 = tileRow((size_t)(b >> 5), p.nmax, i, 6, b & 31);
@@ -1364,17 +1417,11 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
 }
 
 // ---------------------------------------------------------------------------
-// Kernels.
-//   beam_newton_pipelined : the product path, ONE launch per Newton iteration.  The forward sweep is
-//       FP64-pipe bound and leaves HBM idle, the backward sweep is HBM bound and leaves the FP64 pipe
-//       idle, and a sweep is a 200-step serial recurrence, so the two only overlap if different tiles
-//       (128 beams) are in different phases on the same SM at the same time.  Persistent blocks, two per
-//       SM: the first block to arrive on an SM takes forward tickets, the second takes backward tickets
-//       (and waits on the per-tile "forward done" flag); when the forward tickets run out the forward
-//       blocks drain backward tickets too.  Every wait is on a forward sweep that is already running,
-//       and forward sweeps never wait, so the scheme cannot deadlock.
-//   beam_newton           : each thread runs forward then backward on its own beam (all tiles in phase).
-//   beam_forward / beam_backward : the two sweeps as two launches, for profiling.
+// Kernels (one thread per beam).
+//   beam_forward / beam_backward : the product path for bundles of at least one wave of beams: the two sweeps as two
+//       launches per Newton iteration.
+//   beam_newton                  : both sweeps in one launch (BEAMGPU_FUSED_KERNEL=1); measures 5-6 % slower.
+// Bundles below one wave run the group-cooperative kernels of beam_coop.cuh (several lanes per beam).
 // ---------------------------------------------------------------------------
 DEV uint32_t warpBarrierSetup(unsigned char* smem)
 {
@@ -1384,76 +1431,6 @@ DEV uint32_t warpBarrierSetup(unsigned char* smem)
 }
 #define WARP_SLAB(smem, w) ((double*)((smem) + SMEM_HEADER_BYTES) + (size_t)(w) * WARP_SMEM_DOUBLES)
 
-template <int SCHEME>
-__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton_pipelined(const BeamParams p)
-{
-    extern __shared__ __align__(128) unsigned char beam_smem[];
-    __shared__ int sTicket[2]; // tile, kind (1 forward, 2 backward)
-    const int w = threadIdx.x >> 5;
-    uint32_t phase = warpBarrierSetup(beam_smem);
-    int role = 0;
-    if (threadIdx.x == 0) {
-        unsigned smid;
-        asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        sTicket[0] = atomicAdd(&p.ctl[2 + smid], 1) & 1; // first block on this SM: forward role, second: backward role
-    }
-    __syncthreads();
-    role = sTicket[0];
-    bool forwardLeft = role == 0 || p.pipePolicy == 1;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tile = -1, kind = 0;
-            if (forwardLeft) {
-                tile = atomicAdd(&p.ctl[0], 1);
-                if (tile < p.nTiles) kind = 1;
-            }
-            if (!kind) {
-                tile = atomicAdd(&p.ctl[1], 1);
-                if (tile < p.nTiles) {
-                    kind = 2;
-                    // acquire: the forward sweep of this launch has finished the tile (its scratch is visible)
-                    int seen;
-                    for (;;) {
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.fDone + tile) : "memory");
-                        if (seen == p.epoch) break;
-                        __nanosleep(200);
-                    }
-                }
-            }
-            sTicket[0] = tile; sTicket[1] = kind;
-        }
-        __syncthreads();
-        const int tile = sTicket[0], kind = sTicket[1];
-        if (!kind) break;
-        const int b = tile * BEAM_THREADS + threadIdx.x;
-        if (p.trace && threadIdx.x == 0) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            p.trace[4 * tile + (kind == 1 ? 0 : 2)] = t;
-        }
-        if (kind == 1) {
-            double v[1];
-            v[0] = forwardSweep<SCHEME>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
-            blockReduceStore<1>(v, p.partial, 0, p.nTiles, tile);
-            __threadfence(); // scratch + partial sums of every thread are visible device-wide ...
-            __syncthreads();
-            if (threadIdx.x == 0) // ... before the flag is
-                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.fDone + tile), "r"(p.epoch) : "memory");
-        } else {
-            forwardLeft = false;
-            __threadfence();
-            double v[2] = {0.0, 0.0};
-            if (b < p.B) backwardSweep<SCHEME>(p, b, v[0], v[1]);
-            blockReduceStore<2>(v, p.partial, 1, p.nTiles, tile);
-        }
-        if (p.trace && threadIdx.x == 0) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            p.trace[4 * tile + (kind == 1 ? 1 : 3)] = t;
-        }
-    }
-}
 template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton(const BeamParams p)
 {
@@ -1548,14 +1525,17 @@ __global__ void beam_energy(const BeamParams p, double* __restrict__ out)
     out[3 * (size_t)b] = intE; out[3 * (size_t)b + 1] = kinL; out[3 * (size_t)b + 2] = kinA;
 }
 
-// Deterministic final reduction of the per-block partial sums (fixed order).
-__global__ void beam_reduce_partials(const double* __restrict__ partial, int nBlocks, double* __restrict__ out,
+// Deterministic final reduction of the per-block partial sums (fixed order).  partial[k * stride + block]: slot 0 is
+// written by the nF blocks of the forward launch, slots 1 and 2 by the nB blocks of the backward launch (the two
+// launches of an iteration may come from different kernel families, see bf_ctx::coopFwd / coopBwd).
+__global__ void beam_reduce_partials(const double* __restrict__ partial, int stride, int nF, int nB, double* __restrict__ out,
                                      double* __restrict__ outHost)
 {
     __shared__ double sm[3][256];
     for (int k = 0; k < 3; k++) {
         double acc = 0.0;
-        for (int i = threadIdx.x; i < nBlocks; i += blockDim.x) acc += partial[(size_t)k * nBlocks + i];
+        const int nBlocks = k == 0 ? nF : nB;
+        for (int i = threadIdx.x; i < nBlocks; i += blockDim.x) acc += partial[(size_t)k * stride + i];
         sm[k][threadIdx.x] = acc;
     }
     __syncthreads();

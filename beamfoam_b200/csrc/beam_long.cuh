@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128) long_assemble(const BeamParams p, const L
             for (int c = 0; c < 6; c++) { oD[6 * r + c] = D[r][c]; oL[6 * r + c] = Lb[r][c]; oU[6 * r + c] = Ub[r][c]; }
         }
     }
-    blockReduceStore<1>(v, p.partial, 0, gridDim.x, blockIdx.x);
+    blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
 
 // Rows into working copy 0; right-hand side = source (first pass) or source - A x (refinement pass).
@@ -255,5 +255,5 @@ __global__ void __launch_bounds__(128) long_update_cells(const BeamParams p, con
         V3 Wold;
         updateCell<SCHEME>(p, (size_t)(b >> 5), b & 31, i, v3(x[0], x[1], x[2]), v3(x[3], x[4], x[5]), Wold, v[1]);
     }
-    blockReduceStore<2>(v, p.partial, 1, gridDim.x, blockIdx.x);
+    blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
 }

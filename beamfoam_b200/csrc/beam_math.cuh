@@ -272,6 +272,29 @@ DEV M3 inv(const M3& A)
     return r;
 }
 
+// inv(tensor) that also returns the determinant and the largest |entry|, for the pivot guard of the block eliminations
+DEV M3 invDet(const M3& A, double& det, double& amax)
+{
+    const double xx = A.a[0], xy = A.a[1], xz = A.a[2], yx = A.a[3], yy = A.a[4], yz = A.a[5], zx = A.a[6],
+                 zy = A.a[7], zz = A.a[8];
+    det = xx * yy * zz + xy * yz * zx + xz * yx * zy - xx * yz * zy - xy * yx * zz - xz * yy * zx;
+    double m = fabs(xx);
+#pragma unroll
+    for (int k = 1; k < 9; k++) m = fmax(m, fabs(A.a[k]));
+    amax = m;
+    const double id = rcpFast(det);
+    M3 r;
+    r.a[0] = (yy * zz - zy * yz) * id; r.a[1] = (xz * zy - xy * zz) * id; r.a[2] = (xy * yz - xz * yy) * id;
+    r.a[3] = (zx * yz - yx * zz) * id; r.a[4] = (xx * zz - xz * zx) * id; r.a[5] = (yx * xz - xx * yz) * id;
+    r.a[6] = (yx * zy - yy * zx) * id; r.a[7] = (xy * zx - xx * zy) * id; r.a[8] = (xx * yy - yx * xy) * id;
+    return r;
+}
+// A 3x3 diagonal sub-block whose determinant is small against the cube of its largest entry is ill-conditioned
+// (cond ~ amax^3 / |det|): the adjugate inverse then loses digits (or divides by zero) where a pivoted LU of the whole
+// 6x6 block -- what the reference's SparseLU does (EigenOF.C:292-297) -- still solves.  NaN counts as "small".
+#define BEAM_PIVOT_GUARD 1e-3
+DEV bool smallDet(double det, double amax) { return !(fabs(det) > BEAM_PIVOT_GUARD * amax * amax * amax); }
+
 // Rodrigues, exactly the reference's plain formula (phi = |theta| + SMALL, no series branch):
 // R = I + (sin phi / phi) S + ((1 - cos phi)/phi^2) S&S      pseudoVector.C:250-264
 DEV M3 rotationMatrix(V3 th)

@@ -8,6 +8,7 @@
 #include "../../include/beamgpu.h"
 #include "beam_kernels.cuh"
 #include "beam_long.cuh"
+#include "beam_coop.cuh"
 #include "beam_contrib.cuh"
 
 #include <cuda_runtime.h>
@@ -21,7 +22,6 @@
 #include <vector>
 
 #define BF_GREAT 1e15
-#define CTL_INTS (2 + 1024) // forward ticket, backward ticket, blocks seen per SM (smid < 1024)
 #define THREADS BEAM_THREADS
 
 static char g_create_err[512] = "";
@@ -43,6 +43,9 @@ struct bf_ctx {
     cudaStream_t stream;
     int64_t B, N, F;
     int Bpad, nmax, grid;
+    // bundles below one wave of beams: group-cooperative kernels (beam_coop.cuh), selectable per sweep
+    int coopFwd, coopBwd, coopGrid;
+    int partialStride; // leading dimension of d_partial: the largest block count of any kernel family
     std::vector<int32_t> nSeg, hostWType; // hostWType: [2][B]
     std::vector<int64_t> cellStart, faceStart;
     bool uniformN;
@@ -61,9 +64,6 @@ struct bf_ctx {
     double *d_Wb, *d_Thb, *d_Lamb, *d_DWb, *d_DThb, *d_force, *d_wPresc, *d_thPresc, *d_follower, *d_offset,
         *d_moment, *d_springK, *d_springDir;
     double *d_uP, *d_bP, *d_partial, *d_sums;
-    int *d_ctl, *d_fDone; // pipelined launch: tickets / per-SM role counters, per-tile forward-done flags
-    int epoch, pipeGrid, pipelined, pipePolicy;
-    unsigned long long* d_trace; // BEAMGPU_TRACE=1: per-tile sweep time stamps of the last pipelined launch
     // few long beams: one thread per cell, assembled block rows, block parallel cyclic reduction (beam_long.cuh)
     int longMode, longBlocks;
     int32_t* d_cellBeam;
@@ -82,6 +82,8 @@ struct bf_ctx {
     double betaN, gammaN, deltaT;
     double dtStar; // the time step the stored Newmark constants U*, Omega* belong to (beam_kernels.cuh, BeamParams)
     int iOuterCorr;
+    bool timeAdvanced; // set by bf_begin_step, cleared by the first Newton iteration after it: the Newmark predictor and the
+                       // Euler old-time capture belong to the time index, not to a call of evolve() (Evolve.C:167-186 reads oldTime())
     bool hasQ, hasM;
     bf_reduce_fn reducer;
     void* reducerUser;
@@ -398,9 +400,11 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     CREATE_CUDA(cudaFuncSetAttribute(KERNEL<BFK_STEADY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));  \
     CREATE_CUDA(cudaFuncSetAttribute(KERNEL<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)); \
     CREATE_CUDA(cudaFuncSetAttribute(KERNEL<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES))
-    OPT_IN_SMEM(beam_newton_pipelined);
     OPT_IN_SMEM(beam_newton);
     OPT_IN_SMEM(beam_forward);
+    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_coop<BFK_STEADY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_coop<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_coop<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM_BYTES));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
@@ -434,6 +438,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->deltaT = 1.0;
     c->dtStar = 1.0;
     c->iOuterCorr = 0;
+    c->timeAdvanced = true;
     const bool newmark = c->scheme != BF_SCHEME_STEADY; // U, Accl, Omega, dotOmega exist for both transient schemes
     const bool euler = c->scheme == BF_SCHEME_EULER;
     const size_t bp = (size_t)Bpad, nc_ = (size_t)nmax, nf_ = (size_t)nmax + 1;
@@ -480,25 +485,28 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     // ---- block-Thomas scratch + partial sums
     {
         char* cur;
-        if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->grid + 3 * (size_t)((c->N + 127) / 128) + 8) + sizeof(int) * (CTL_INTS + (size_t)c->grid) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        c->coopGrid = (Bpad + COOP_BEAMS_PER_BLOCK - 1) / COOP_BEAMS_PER_BLOCK;
+        c->partialStride = c->grid;
+        if ((int)((c->N + 127) / 128) > c->partialStride) c->partialStride = (int)((c->N + 127) / 128);
+        if (c->coopGrid > c->partialStride) c->partialStride = c->coopGrid;
+        if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->partialStride + 8) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
-        c->d_partial = carve<double>(cur, 3 * (size_t)c->grid + 3 * (size_t)((c->N + 127) / 128)); c->d_sums = carve<double>(cur, 8);
-        c->d_ctl = carve<int>(cur, CTL_INTS); c->d_fDone = carve<int>(cur, (size_t)c->grid);
-        c->epoch = 0;
-        // persistent pipelined launch: as many blocks as are co-resident (2 per SM with these kernels), never more
-        // than the 2 tickets (forward + backward) per tile
-        int perSm = 0, nSm = 0;
-        CREATE_CUDA(cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, c->device));
-        CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, beam_newton_pipelined<BFK_NEWMARK>, THREADS, SMEM_BYTES));
-        if (perSm < 1) perSm = 1;
-        if (perSm > 2) perSm = 2;
-        c->pipeGrid = perSm * nSm < 2 * c->grid ? perSm * nSm : 2 * c->grid;
-        // Off by default: measured on B200 at 65,536 x 200 the tile-level forward/backward overlap gains 12 % in the
-        // steady state but a launch is only 3.5 tiles per SM deep, so the ramp (backward blocks idle until the first
-        // forward tile is done) and the tail cost more than that (4.99 ms vs 4.35 ms).
-        c->pipelined = getenv("BEAMGPU_PIPELINE") ? 1 : 0;
-        c->pipePolicy = getenv("BEAMGPU_PIPELINE_POLICY") ? atoi(getenv("BEAMGPU_PIPELINE_POLICY")) : 1;
-        c->d_trace = nullptr;
+        c->d_partial = carve<double>(cur, 3 * (size_t)c->partialStride); c->d_sums = carve<double>(cur, 8);
+        // One thread per beam fills the GPU from one wave of beams (SMs x 8 warps x 32 lanes = 37,888 on a B200); below
+        // BEAMGPU_COOP_BELOW beams (default: measured crossover) a beam gets a group of 4 lanes.
+        // BEAMGPU_COOP = 1 / 0 / fwd / bwd forces the cooperative kernels on / off / for one sweep only (tests).
+        {
+            int nSm = 148;
+            cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, c->device);
+            long below = (long)nSm * 8 * 32 * 5 / 8;
+            if (const char* e = getenv("BEAMGPU_COOP_BELOW")) below = atol(e);
+            c->coopFwd = c->coopBwd = B < below ? 1 : 0;
+            if (const char* e = getenv("BEAMGPU_COOP")) {
+                if (!strcmp(e, "fwd")) { c->coopFwd = 1; c->coopBwd = 0; }
+                else if (!strcmp(e, "bwd")) { c->coopFwd = 0; c->coopBwd = 1; }
+                else c->coopFwd = c->coopBwd = atoi(e) ? 1 : 0;
+            }
+        }
         // BEAMGPU_LONG_BEAMS = 1 / 0 forces the cell-parallel path on / off; by default it serves bundles that cannot
         // occupy the GPU with one thread per beam but have enough cells per beam to do so with one thread per cell
         const char* lm = getenv("BEAMGPU_LONG_BEAMS");
@@ -506,7 +514,6 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         c->longBlocks = (int)((c->N + 127) / 128);
         c->d_cellBeam = nullptr; c->d_longX = nullptr;
         for (int k = 0; k < 12; k++) c->d_longRows[k] = nullptr;
-        if (getenv("BEAMGPU_TRACE") && devAlloc(c, (void**)&c->d_trace, sizeof(unsigned long long) * 4 * (size_t)c->grid)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
     }
     // ---- staging buffer (largest field in host ordering: a tensor vol field)
     c->stageDoubles = (size_t)c->N * 9;
@@ -981,6 +988,7 @@ extern "C" int bf_begin_step(bf_ctx* c, double deltaT)
     if (!(deltaT > 0)) return fail(c, BF_ERR_INVALID, "bf_begin_step: deltaT must be > 0");
     c->deltaT = deltaT;
     c->iOuterCorr = 0;
+    c->timeAdvanced = true;
     return BF_OK;
 }
 
@@ -1022,15 +1030,6 @@ extern "C" int bf_beam_energy(bf_ctx* c, double* out)
     return BF_OK;
 }
 
-// Debug aid (not in beamgpu.h): copies the [nTiles][4] time stamps of the last pipelined launch (BEAMGPU_TRACE=1).
-extern "C" int bf_debug_trace(bf_ctx* c, unsigned long long* out, int64_t maxTiles)
-{
-    if (!c->d_trace) return BF_ERR_INVALID;
-    const int64_t n = maxTiles < c->grid ? maxTiles : c->grid;
-    CUDA_OK(c, cudaStreamSynchronize(c->stream));
-    CUDA_OK(c, cudaMemcpy(out, c->d_trace, sizeof(unsigned long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
-    return (int)n;
-}
 extern "C" int bf_kernel_time_ms(bf_ctx* c, int32_t reset, double* fwd, double* bwd, int64_t* it)
 {
     if (fwd) *fwd = c->fwdMs;
@@ -1045,7 +1044,7 @@ static BeamParams makeParams(bf_ctx* c)
     BeamParams p;
     memset(&p, 0, sizeof p);
     p.B = (int)c->B; p.Bpad = c->Bpad; p.nmax = c->nmax;
-    p.newmark = c->scheme; p.first = c->iOuterCorr == 0; p.storeInc = c->storeInc;
+    p.newmark = c->scheme; p.first = c->timeAdvanced ? 1 : 0; p.storeInc = c->storeInc;
     p.dt = c->deltaT; p.beta = c->betaN; p.gamma = c->gammaN;
     p.nk1 = 1.0 / (p.dt * p.beta); p.nk2 = 0.5 / p.beta - 1.0; p.nVel = p.gamma / (p.beta * p.dt);
     p.nAcc = 1.0 / (p.beta * p.dt * p.dt); p.nU = (1.0 / p.dt) * (p.gamma / p.beta);
@@ -1062,10 +1061,16 @@ static BeamParams makeParams(bf_ctx* c)
     p.wPresc = c->d_wPresc; p.thPresc = c->d_thPresc; p.follower = c->d_follower; p.offset = c->d_offset;
     p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir;
     p.uP = c->d_uP; p.bP = c->d_bP; p.partial = c->d_partial;
-    p.nTiles = c->grid; p.pipePolicy = c->pipePolicy; p.epoch = c->epoch; p.ctl = c->d_ctl; p.fDone = c->d_fDone; p.trace = c->d_trace;
+    p.nTiles = c->partialStride;
     return p;
 }
 
+#define LAUNCH_SCHEME_T(KERNEL, GRID, THR, SMEM, P)                                                   \
+    do {                                                                                              \
+        if (c->scheme == BF_SCHEME_NEWMARK) KERNEL<BFK_NEWMARK><<<(GRID), (THR), (SMEM), c->stream>>>(P); \
+        else if (c->scheme == BF_SCHEME_EULER) KERNEL<BFK_EULER><<<(GRID), (THR), (SMEM), c->stream>>>(P); \
+        else KERNEL<BFK_STEADY><<<(GRID), (THR), (SMEM), c->stream>>>(P);                             \
+    } while (0)
 #define LAUNCH_SCHEME(KERNEL, GRID, SMEM, P)                                                          \
     do {                                                                                              \
         if (c->scheme == BF_SCHEME_NEWMARK) KERNEL<BFK_NEWMARK><<<(GRID), THREADS, (SMEM), c->stream>>>(P); \
@@ -1090,7 +1095,9 @@ static int launchIteration(bf_ctx* c)
         c->launches++;
     }
     if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[0], c->stream));
-    if (c->longMode) { // one thread per cell: assemble, block cyclic reduction, update
+    int nF = c->grid, nB = c->grid; // blocks that wrote the partial sums of the forward / backward part
+    if (c->longMode) {
+        nF = nB = c->longBlocks; // one thread per cell: assemble, block cyclic reduction, update
         LongParams q;
         q.N = c->N; q.cellBeam = c->d_cellBeam; q.cellStart = c->d_cellStart; q.X = c->d_longX;
         for (int k = 0; k < 2; k++) { q.L[k] = c->d_longRows[4 * k]; q.D[k] = c->d_longRows[4 * k + 1]; q.U[k] = c->d_longRows[4 * k + 2]; q.R[k] = c->d_longRows[4 * k + 3]; }
@@ -1119,33 +1126,26 @@ static int launchIteration(bf_ctx* c)
         else if (c->scheme == BF_SCHEME_EULER) long_update_cells<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
         else long_update_cells<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
         c->launches += 2;
-    } else if (c->splitKernels && !c->pipelined) { // product path: one launch per sweep
-        LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
+    } else if (c->splitKernels || c->coopFwd || c->coopBwd) { // product path: one launch per sweep
+        if (c->coopFwd) LAUNCH_SCHEME_T(beam_forward_coop, c->coopGrid, COOP_THREADS, COOP_SMEM_BYTES, p);
+        else LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
-        LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
+        if (c->coopBwd) LAUNCH_SCHEME_T(beam_backward_coop, c->coopGrid, COOP_THREADS, 0, p);
+        else LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
         c->launches += 2;
-    } else if (c->pipelined) { // experiment (BEAMGPU_PIPELINE=1): persistent blocks, sweeps of different tiles overlap
-        if (++c->epoch == 0x7fffffff) { // flags compare equal to the epoch: start over before it wraps
-            CUDA_OK(c, cudaMemsetAsync(c->d_fDone, 0, sizeof(int) * (size_t)c->grid, c->stream));
-            c->epoch = 1;
-        }
-        BeamParams q = p;
-        q.epoch = c->epoch;
-        CUDA_OK(c, cudaMemsetAsync(c->d_ctl, 0, sizeof(int) * CTL_INTS, c->stream));
-        LAUNCH_SCHEME(beam_newton_pipelined, c->pipeGrid, SMEM_BYTES, q);
-        if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
-        c->launches += 1;
+        nF = c->coopFwd ? c->coopGrid : c->grid;
+        nB = c->coopBwd ? c->coopGrid : c->grid;
     } else {
         LAUNCH_SCHEME(beam_newton, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
         c->launches += 1;
     }
     if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[2], c->stream));
-    beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->longMode ? c->longBlocks : c->grid, c->d_sums,
-                                                   c->comm ? nullptr : c->d_hsums);
+    beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, c->d_sums, c->comm ? nullptr : c->d_hsums);
     c->launches += 1;
     CUDA_OK(c, cudaGetLastError());
     if (p.first) c->dtStar = c->deltaT; // the backward sweep of a first iteration re-bases U*, Omega* on this step
+    c->timeAdvanced = false;
     c->iOuterCorr++;
     return BF_OK;
 }

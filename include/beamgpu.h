@@ -272,9 +272,15 @@ int bf_set_bc_values(bf_ctx* ctx, int32_t end, int32_t kind, const double* value
 
 /* ---- the hot path ---------------------------------------------------------- */
 
-/* Start of a time/load step (beamFoam.C:73-79): sets deltaT and resets
- * iOuterCorr.  With Newmark the predictor of Evolve.C:167-186 is applied inside
- * the first bf_newton_iteration of the step. */
+/* The time index advanced (runTime++ of beamFoam.C:73-79): sets deltaT, resets
+ * iOuterCorr and opens a new old-time level.  The Newmark predictor of
+ * Evolve.C:167-186 (Euler: the capture of W/U/Omega/Lambda.oldTime()) is applied
+ * by the FIRST Newton iteration after this call and by no other: bf_evolve /
+ * bf_newton_iteration called again without a new bf_begin_step (outer FSI
+ * iterations, a retry with other tolerances) continue from the current state of
+ * the same time level.  Call it once per time step, before bf_evolve.  A step
+ * that ended BF_DIVERGED leaves the state unusable (no roll-back): reset the
+ * fields with bf_set_field before going on. */
 int bf_begin_step(bf_ctx* ctx, double deltaT);
 
 /* One pass of the do{}-body of evolve() (Evolve.C:119-632): coefficients,

@@ -157,6 +157,7 @@ struct bf_ctx {
     int scheme;
     double betaN, gammaN, deltaT;
     int iOuterCorr;
+    int timeAdvanced; /* set by bf_begin_step (runTime++), cleared by the first Newton iteration after it */
     bf_reduce_fn reducer;
     void* reducerUser;
     int64_t launches;
@@ -337,6 +338,7 @@ int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf_bc* bc, co
     c->betaN = opt->newmarkBeta > 0 ? opt->newmarkBeta : 0.25;
     c->gammaN = opt->newmarkGamma > 0 ? opt->newmarkGamma : 0.5;
     c->deltaT = 1.0;
+    c->timeAdvanced = 1;
     *out = c;
     return BF_OK;
 fail_invalid:
@@ -469,6 +471,7 @@ int bf_begin_step(bf_ctx* c, double deltaT)
     if (!(deltaT > 0)) { snprintf(c->err, sizeof c->err, "bf_begin_step: deltaT must be > 0"); return BF_ERR_INVALID; }
     c->deltaT = deltaT;
     c->iOuterCorr = 0;
+    c->timeAdvanced = 1;
     /* runTime++ stores the old-time level of every field that has one (CTL.C:767-779) */
     memcpy(c->Wold, c->W, sizeof(double) * 3 * c->N);
     memcpy(c->Uold, c->U, sizeof(double) * 3 * c->N);
@@ -1367,7 +1370,10 @@ int bf_newton_iteration(bf_ctx* c, double sumsq[3])
             t_mul_v(c->Lambdaf + 9 * (F + p), c->followerForce + 3 * p, c->force + 3 * p);
     }
     updateEqnCoefficients(c); /* :163 */
-    if (c->scheme == BF_SCHEME_NEWMARK && c->iOuterCorr == 0) { /* :167-186 (old == current at step start) */
+    /* :167-186.  The reference tests iOuterCorr() == 0 and reads the oldTime() fields; here "old == current" holds on the
+     * first iteration after the time index advanced, so the predictor is tied to that (a second evolve() inside one
+     * time step continues from the current state instead of re-applying the predictor: DESIGN.md section 8, C12). */
+    if (c->scheme == BF_SCHEME_NEWMARK && c->timeAdvanced) {
         const double dt = c->deltaT, beta = c->betaN, gamma = c->gammaN;
         for (int64_t i = 0; i < 3 * N; i++) {
             const double Uo = c->U[i], Ao = c->Accl[i], Oo = c->Omega[i], dOo = c->dotOmega[i];
@@ -1397,6 +1403,7 @@ int bf_newton_iteration(bf_ctx* c, double sumsq[3])
     for (int64_t i = 0; i < 3 * N; i++) xn += c->W[i] * c->W[i];
     for (int64_t i = 0; i < 3 * N; i++) xn += c->Theta[i] * c->Theta[i]; /* :621-626 */
     sumsq[0] = res; sumsq[1] = dx; sumsq[2] = xn;
+    c->timeAdvanced = 0;
     c->iOuterCorr++;
     return BF_OK;
 }

@@ -1,0 +1,8 @@
+#!/bin/bash
+# first GPU call of round 2: cooperative kernels — parity in all four family combinations, then timings by bundle size
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+nvidia-smi -L
+make -C oracle > gpurun_out/make.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_coop.py -m gpu -q -x 2>&1 | tee gpurun_out/pytest_coop.log | tail -25
+timeout 600 python scripts/gpu_sizes.py 4096 8192 16384 32768 65536 2>&1 | tee gpurun_out/sizes.log

@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Runs on the GPU box: per-iteration forward / backward kernel times at several bundle sizes, for the one-thread-per-beam
+kernels (BEAMGPU_COOP=0) and the group-cooperative kernels (BEAMGPU_COOP=1).  usage: gpu_sizes.py beams [beams ...]"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from beamfoam_b200 import _lib as L, cases, coupledTotalLagNewtonRaphsonBeam, load_library  # noqa: E402
+
+lib = load_library()
+cells = int(os.environ.get("CELLS", "200"))
+for nb in map(int, sys.argv[1:]):
+    case = cases.multiBeamDensity(nb, cells, jitter=True)
+    for mode in os.environ.get("MODES", "0,1").split(","):
+        os.environ["BEAMGPU_COOP"] = mode
+        m = coupledTotalLagNewtonRaphsonBeam(case, library=lib, storeIncrements=False)
+        m.updateCoeffs(case.deltaT)
+        its = []
+        for k in range(6):
+            if k == 2:
+                lib.bf_set_timing(m._ctx, 1)
+                lib.bf_kernel_time_ms(m._ctx, 1, None, None, None)
+            m.loop()
+            m._check(lib.bf_begin_step(m._ctx, float(case.deltaT)))
+            out = L.bf_step_out()
+            m._check(lib.bf_evolve(m._ctx, C.byref(m.tol), C.byref(out)))
+            its.append(out.nIter)
+        f, b, n = C.c_double(), C.c_double(), C.c_int64()
+        lib.bf_kernel_time_ms(m._ctx, 1, C.byref(f), C.byref(b), C.byref(n))
+        fm, bm = f.value / n.value, b.value / n.value
+        print(f"beams {nb:6d} coop={mode:>3}: fwd {fm:.3f} ms  bwd {bm:.3f} ms  iter {fm + bm:.3f} ms  "
+              f"{nb * cells / (fm + bm) / 1e6:.3f} G updates/s  iters {its} tipW {m.tip(1)[0][-1]}", flush=True)
+        m.close()

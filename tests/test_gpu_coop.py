@@ -1,0 +1,128 @@
+"""The two kernel families of the Newton iteration against the oracle, in every combination.
+
+Bundles below one wave of beams run the group-cooperative kernels of beam_coop.cuh (4 lanes per beam), larger ones
+the one-thread-per-beam sweeps of beam_kernels.cuh; `bf_create` picks by beam count.  Every other GPU test uses small
+bundles and therefore exercises the cooperative pair; here BEAMGPU_COOP forces each family and each mixed pair
+(cooperative forward + per-beam backward and vice versa share the uPrime/bPrime scratch) on the same cases, with the
+north-star bar: identical Newton iteration counts per step, tips within 1e-10 relative.
+"""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+
+from beamfoam_b200 import cases, coupledTotalLagNewtonRaphsonBeam
+from test_gpu_parity import run_pair
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["0", "1", "fwd", "bwd"]
+
+
+@pytest.fixture(params=MODES)
+def coop_mode(request):
+    old = os.environ.get("BEAMGPU_COOP")
+    os.environ["BEAMGPU_COOP"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["BEAMGPU_COOP"]
+    else:
+        os.environ["BEAMGPU_COOP"] = old
+
+
+def test_newmark_bundle(gpu_lib, oracle_lib, coop_mode):
+    """3DdynamicCantileverMultiBeamDensity: 70 beams (not a multiple of a warp's 8 nor of a block's 16) x 37 cells
+    (not a multiple of the 4-cell batch)."""
+    run_pair(cases.multiBeamDensity(70, 37, jitter=True), gpu_lib, oracle_lib, nSteps=25)
+
+
+def test_steady_cantilever(gpu_lib, oracle_lib, coop_mode):
+    run_pair(cases.cantilever(), gpu_lib, oracle_lib, nSteps=30)
+
+
+def test_follower_force(gpu_lib, oracle_lib, coop_mode):
+    run_pair(cases.cantileverFollowerForce(), gpu_lib, oracle_lib, nSteps=40)
+
+
+def test_spring_and_free_ends(gpu_lib, oracle_lib, coop_mode):
+    run_pair(cases.beamAndSpringInSeries(), gpu_lib, oracle_lib, nSteps=10)
+    run_pair(cases.freeFlexibleBeam(), gpu_lib, oracle_lib, nSteps=40, tip_rtol=1e-9)
+
+
+def test_euler_scheme(gpu_lib, oracle_lib, coop_mode):
+    case = dataclasses.replace(cases.multiBeamDensity(9, 21, jitter=True), d2dt2Scheme="Euler")
+    run_pair(case, gpu_lib, oracle_lib, nSteps=20, tip_rtol=1e-9, check_fields=False)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9])
+def test_short_beams(gpu_lib, oracle_lib, coop_mode, n):
+    """Beams shorter than, equal to and just longer than one 4-cell batch; n = 1 closes both patches on one cell."""
+    case = dataclasses.replace(cases.multiBeamDensity(5, n), nSegments=n)
+    g = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
+    o = coupledTotalLagNewtonRaphsonBeam(case, library=oracle_lib)
+    assert g.run(nSteps=10) == o.run(nSteps=10)
+    for a, b in zip(g.tip(1), o.tip(1)):
+        assert np.max(np.abs(a - b)) <= 1e-10 * max(np.max(np.abs(b)), 1e-300)
+    g.close()
+    o.close()
+
+
+def test_ragged_bundle(gpu_lib, oracle_lib, coop_mode):
+    """Beams of different cell counts inside one warp: groups run out of cells at different batches."""
+    B = 19
+    nSeg = np.array([3 + (7 * b) % 23 for b in range(B)], dtype=np.int32)
+    case = dataclasses.replace(cases.multiBeamDensity(B, 10, jitter=True), nSegments=nSeg)
+    g = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
+    o = coupledTotalLagNewtonRaphsonBeam(case, library=oracle_lib)
+    assert g.run(nSteps=12) == o.run(nSteps=12)
+    for f in ("W", "Theta"):
+        a, b = g.get_field(f)[0], o.get_field(f)[0]
+        assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b)) + 1e-13
+    for a, b in zip(g.tip(1), o.tip(1)):
+        assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+    g.close()
+    o.close()
+
+
+def test_families_agree_at_4096_beams(gpu_lib):
+    """BASELINE configs[2] (4096 beams x 200 cells, Newmark): the cooperative and the per-beam kernels give the same
+    per-step iteration counts and tips equal to 1e-12 (they differ only in the order of a few additions)."""
+    case = cases.multiBeamDensity(4096, 200, jitter=True)
+    out = {}
+    for mode in ("0", "1"):
+        os.environ["BEAMGPU_COOP"] = mode
+        m = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib, storeIncrements=False)
+        out[mode] = (m.run(nSteps=4), m.tip(1))
+        m.close()
+    del os.environ["BEAMGPU_COOP"]
+    assert out["0"][0] == out["1"][0]
+    for a, b in zip(out["0"][1], out["1"][1]):
+        assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(b))
+
+
+def test_second_evolve_in_one_time_step(gpu_lib, oracle_lib):
+    """evolve() called twice at the same time index (FSI outer iterations, a retry with relaxed tolerances): the Newmark
+    predictor / the Euler old-time capture belong to bf_begin_step, so the second call continues from the converged
+    state of the same time level instead of advancing it a second time."""
+    for scheme in ("Newmark", "Euler"):
+        case = dataclasses.replace(cases.multiBeamDensity(6, 14, jitter=True), d2dt2Scheme=scheme)
+        g = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
+        o = coupledTotalLagNewtonRaphsonBeam(case, library=oracle_lib)
+        for m in (g, o):
+            m.run(nSteps=3)
+            assert m.loop()
+            m.evolve()
+        w1 = g.tip(1)[0].copy()
+        for m in (g, o):
+            m.evolve()  # same time index: no bf_begin_step
+        assert g.iOuterCorr() == o.iOuterCorr() <= 2
+        for a, b in zip(g.tip(1), o.tip(1)):
+            assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+        assert np.max(np.abs(g.tip(1)[0] - w1)) <= 1e-8 * np.max(np.abs(w1))  # the converged step stays where it was
+        for m in (g, o):
+            m.run(nSteps=2)
+        for a, b in zip(g.tip(1), o.tip(1)):
+            assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
+        g.close()
+        o.close()
