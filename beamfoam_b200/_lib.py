@@ -90,6 +90,7 @@ EXPORTS = {
     "bf_set_momentum_contributions": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(bf_momentum_contribution), C.c_void_p,
                                                 C.c_void_p]),
     "bf_set_bc_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "bf_get_patch_pair": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "bf_beam_energy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bf_begin_step": (C.c_int, [C.c_void_p, C.c_double]),
     "bf_newton_iteration": (C.c_int, [C.c_void_p, _dp]),
@@ -98,6 +99,7 @@ EXPORTS = {
     "bf_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "bf_comm_init_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "bf_launch_count": (C.c_int64, [C.c_void_p]),
+    "bf_kernel_family": (C.c_int32, [C.c_void_p]),
     "bf_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp, C.POINTER(C.c_int64)]),
     "bf_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "bf_region_mark": (C.c_int, [C.c_void_p, C.c_int32]),

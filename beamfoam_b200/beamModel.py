@@ -362,9 +362,9 @@ class coupledTotalLagNewtonRaphsonBeam:
 
     def tip(self, end: int = 1):
         """Patch values (W_b, Theta_b) of every beam at one end — the parity observable."""
-        _, wl, wr = self.get_field("W", internal=False)
-        _, tl, tr = self.get_field("Theta", internal=False)
-        return (wr, tr) if end == 1 else (wl, tl)
+        w, t = np.empty((self._B, 3)), np.empty((self._B, 3))
+        self._check(self.lib.bf_get_patch_pair(self._ctx, end, w.ctypes.data, t.ctypes.data))
+        return w, t
 
     # ------------------------------------------------------------- hot path
     def updateCoeffs(self, t: float):
@@ -388,6 +388,14 @@ class coupledTotalLagNewtonRaphsonBeam:
                     self._check(self.lib.bf_set_bc_values(self._ctx, end, kind, buf.ctypes.data))
                     self.h2dBytes += buf.nbytes
                 self._bcUploaded.add((end, var))
+
+    def pinned(self, shape) -> np.ndarray:
+        """A page-locked float64 host array owned by this object (bf_host_alloc), e.g. for bf_get_patch_pair."""
+        n = int(np.prod(shape))
+        ptr = C.c_void_p()
+        self._check(self.lib.bf_host_alloc(C.byref(ptr), n * 8))
+        self._pinnedPtrs.append(ptr)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=tuple(shape))
 
     def _pinned_bc(self, end: int, var: str, kind: int) -> np.ndarray:
         """[nBeams, 3] page-locked host array (bf_host_alloc: cudaHostAlloc in libbeamgpu, malloc in the oracle) that the

@@ -25,7 +25,8 @@
 #pragma once
 #include "beam_kernels.cuh"
 
-#define COOP_THREADS 64 // 2 warps = 16 beams per block: small blocks spread a small bundle over all SMs
+#define COOP_THREADS 32 // one warp = 8 beams per block: small blocks spread a small bundle over all SMs, and the
+                        // shared memory of an SM divides into 7 warps (one more than with 2-warp blocks)
 #define COOP_GROUP 4
 #define COOP_BEAMS_PER_WARP 8
 #define COOP_BEAMS_PER_BLOCK (COOP_THREADS / 32 * COOP_BEAMS_PER_WARP)
@@ -44,7 +45,11 @@ enum {
 // neighbour source part of the last cell of the previous batch [6][8]
 #define COOP_CARRY_OFF (K_ROWS * 32)
 #define COOP_SNPREV_OFF (COOP_CARRY_OFF + 42 * 8)
-#define COOP_WARP_DOUBLES (COOP_SNPREV_OFF + 6 * 8)
+// ... and the staging rows [ST_ROWS][32 lanes]: the face rows and W that the assembly of the NEXT batch reads, brought in by
+// per-lane cp.async (LDGSTS, no register in flight) while the current batch is being eliminated
+enum { ST_W = 0, ST_WN = 3, ST_LF = 6, ST_K = 10, ST_Q = 13, ST_M = 16, ST_ROWS = 19 };
+#define COOP_STAGE_OFF (COOP_SNPREV_OFF + 6 * 8)
+#define COOP_WARP_DOUBLES (COOP_STAGE_OFF + ST_ROWS * 32)
 #define COOP_SMEM_BYTES ((COOP_THREADS / 32) * COOP_WARP_DOUBLES * sizeof(double))
 
 // Pivoted fallback: D (row-major 36) x = cols, two right-hand sides per lane.
@@ -67,10 +72,10 @@ __device__ __noinline__ void coopSolvePivoted(const double* __restrict__ D36, do
 // Returns nothing; the complete source of the cell is SO (this record) + SN (record of cell i-1).
 template <int SCHEME>
 DEV void coopAssembleCell(const BeamParams& p, const int b, const int i, const int n, double* __restrict__ rec,
-                          const double dZ, const double dcI, const V3 dR0, const V3 CQ, const V3 CM, const double ARho, const V3 CI)
+                          const double* __restrict__ st, const double dZ, const double dcI, const V3 dR0, const V3 CQ, const V3 CM,
+                          const double ARho, const V3 CI)
 {
-    const size_t T = (size_t)(b >> 5);
-    const int lb = b & 31, Rc = p.nmax, Rf = p.nmax + 1;
+    const CellIn cell = loadCellIn<SCHEME>(p, b, i); // issued first: consumed after the face part
     double D[6][6], src[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
@@ -78,7 +83,7 @@ DEV void coopAssembleCell(const BeamParams& p, const int b, const int i, const i
 #pragma unroll
         for (int c = 0; c < 6; c++) D[r][c] = 0.0;
     }
-    const V3 Wi = ld3(p.W, tileRow(T, Rc, i, 3, lb), TS);
+    const V3 Wi = v3(st[(ST_W + 0) * 32], st[(ST_W + 1) * 32], st[(ST_W + 2) * 32]);
     if (i == 0 || i == n - 1) { // end patches: assembleBoundaryConditions (BC.C:64-1190), additive in D and source
         double D36[36], s6[6];
 #pragma unroll
@@ -95,10 +100,11 @@ DEV void coopAssembleCell(const BeamParams& p, const int b, const int i, const i
         }
     }
     if (i < n - 1) { // internal face i+1: the same folded form as fwdFacePart (beam_kernels.cuh)
-        const size_t f3 = tileRow(T, Rf, i + 1, 3, lb);
-        const V3 Wn = ld3(p.W, tileRow(T, Rc, i + 1, 3, lb), TS);
-        const Q4 qf = ldq(p.Lf, tileRow(T, Rf, i + 1, 4, lb), TS);
-        const V3 Kf = ld3(p.K, f3, TS), Qf = ld3(p.Q, f3, TS), Mf = ld3(p.M, f3, TS);
+        const V3 Wn = v3(st[(ST_WN + 0) * 32], st[(ST_WN + 1) * 32], st[(ST_WN + 2) * 32]);
+        const Q4 qf = q4(st[(ST_LF + 0) * 32], st[(ST_LF + 1) * 32], st[(ST_LF + 2) * 32], st[(ST_LF + 3) * 32]);
+        const V3 Kf = v3(st[(ST_K + 0) * 32], st[(ST_K + 1) * 32], st[(ST_K + 2) * 32]);
+        const V3 Qf = v3(st[(ST_Q + 0) * 32], st[(ST_Q + 1) * 32], st[(ST_Q + 2) * 32]);
+        const V3 Mf = v3(st[(ST_M + 0) * 32], st[(ST_M + 1) * 32], st[(ST_M + 2) * 32]);
         const double h = 0.5 * dZ;
         const V3 t = v3(dR0.x + dcI * (Wn.x - Wi.x), dR0.y + dcI * (Wn.y - Wi.y), dR0.z + dcI * (Wn.z - Wi.z));
         const V3 th = h * t;
@@ -151,7 +157,7 @@ DEV void coopAssembleCell(const BeamParams& p, const int b, const int i, const i
 #pragma unroll
         for (int k = K_SN; k < K_ROWS; k++) rec[k * 32] = 0.0;
     }
-    addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, CI, loadCellIn<SCHEME>(p, b, i), D, src);
+    addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, CI, cell, D, src);
 #pragma unroll
     for (int r = 0; r < 6; r++) {
         rec[(K_SO + r) * 32] = src[r];
@@ -160,18 +166,28 @@ DEV void coopAssembleCell(const BeamParams& p, const int b, const int i, const i
     }
 }
 
-// L2 prefetch of what the assembly of cell i of beam (T, lb) reads
+// What the assembly of cell i of beam (T, lb) reads: W of the cell and of its right neighbour and the rows of face i+1 by
+// cp.async into the lane's own staging column (nobody else touches it: no barrier needed, only cp.async.wait_all before
+// the reads); the rows the inertia terms read are pulled into L2 and loaded directly at the top of the assembly.
 template <int SCHEME>
-DEV void coopPrefetchCell(const BeamParams& p, const size_t T, const int lb, const int i, const int n)
+DEV void coopStageCell(const BeamParams& p, const size_t T, const int lb, const int i, const int n, double* __restrict__ st)
 {
     if (i >= n) return;
     const int Rc = p.nmax, Rf = p.nmax + 1;
     const size_t c3 = tileRow(T, Rc, i, 3, lb), c4 = tileRow(T, Rc, i, 4, lb);
-    pfRows<3>(p.W, c3, TS);
+#pragma unroll
+    for (int k = 0; k < 3; k++) cpAsync8(st + (ST_W + k) * 32, p.W + c3 + k * TS);
     if (i + 1 < n) {
-        const size_t f3 = tileRow(T, Rf, i + 1, 3, lb);
-        pfRows<4>(p.Lf, tileRow(T, Rf, i + 1, 4, lb), TS);
-        pfRows<3>(p.K, f3, TS); pfRows<3>(p.Q, f3, TS); pfRows<3>(p.M, f3, TS);
+        const size_t w3 = tileRow(T, Rc, i + 1, 3, lb), f3 = tileRow(T, Rf, i + 1, 3, lb), f4 = tileRow(T, Rf, i + 1, 4, lb);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            cpAsync8(st + (ST_WN + k) * 32, p.W + w3 + k * TS);
+            cpAsync8(st + (ST_K + k) * 32, p.K + f3 + k * TS);
+            cpAsync8(st + (ST_Q + k) * 32, p.Q + f3 + k * TS);
+            cpAsync8(st + (ST_M + k) * 32, p.M + f3 + k * TS);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) cpAsync8(st + (ST_LF + k) * 32, p.Lf + f4 + k * TS);
     }
     if (SCHEME != BFK_STEADY) {
         pfRows<4>(p.Lam, c4, TS);
@@ -322,6 +338,7 @@ __global__ void __launch_bounds__(COOP_THREADS) beam_forward_coop(const BeamPara
     double* rec = warpSm + lane;
     double* cy = warpSm + COOP_CARRY_OFF + g;
     double* sp = warpSm + COOP_SNPREV_OFF + g;
+    double* st = warpSm + COOP_STAGE_OFF + lane;
     const CoopBeam kb = coopLoadBeam<SCHEME>(p, b, live);
     const int n = kb.n;
     const int nW = __reduce_max_sync(0xffffffffu, n);
@@ -334,14 +351,15 @@ __global__ void __launch_bounds__(COOP_THREADS) beam_forward_coop(const BeamPara
 #pragma unroll
         for (int r = 0; r < 6; r++) sp[r * 8] = 0.0;
     }
-    coopPrefetchCell<SCHEME>(p, T, lb, j, n);
+    coopStageCell<SCHEME>(p, T, lb, j, n, st);
     __syncwarp();
     for (int i0 = 0; i0 < nW; i0 += COOP_GROUP) {
         // ---- (a) one lane per cell
         const int i = i0 + j;
         const bool mine = i < n;
-        if (mine) coopAssembleCell<SCHEME>(p, b, i, n, rec, kb.dZ, kb.dcI, kb.dR0, kb.CQ, kb.CM, kb.ARho, kb.CI);
-        coopPrefetchCell<SCHEME>(p, T, lb, i + COOP_GROUP, n); // the next batch's rows on their way to L2 during the elimination
+        cpAsyncWaitAll();
+        if (mine) coopAssembleCell<SCHEME>(p, b, i, n, rec, st, kb.dZ, kb.dcI, kb.dR0, kb.CQ, kb.CM, kb.ARho, kb.CI);
+        coopStageCell<SCHEME>(p, T, lb, i + COOP_GROUP, n, st); // the next batch's rows arrive during the elimination
         __syncwarp();
         if (mine) { // ||source||^2 (EigenOF.C:253-282, x0 = 0): own part + neighbour part from face i
 #pragma unroll
@@ -386,22 +404,37 @@ __global__ void __launch_bounds__(COOP_THREADS) beam_forward_coop(const BeamPara
 // ---------------------------------------------------------------------------------------------------------------------
 // backward: back-substitution redundantly in the group, update one lane per cell
 // ---------------------------------------------------------------------------------------------------------------------
+// The backward kernel takes no shared memory, so the whole L1 is a cache and a batch's rows (4 cells x 8 beams x ~77
+// doubles = 20 KB per warp) fit it many times over: the rows of the NEXT batch are prefetched into L1 while this one is
+// being updated, and the serial chain x_i = bPrime_i - uPrime_i x_{i+1} then reads L1 hits instead of exposing an L2
+// round trip per cell (the kernel is launched after the forward sweep wrote the scratch, so L1 holds nothing stale).
+DEV void pfL1(const double* __restrict__ p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <int NR>
+DEV void pfRowsL1(const double* __restrict__ p, size_t i0)
+{
+#pragma unroll
+    for (int k = 0; k < NR; k++) pfL1(p + i0 + (size_t)k * TS);
+}
 template <int SCHEME>
 DEV void coopPrefetchBack(const BeamParams& p, const size_t T, const int lb, const int i, const int n)
 {
     if (i < 0 || i >= n) return;
     const int Rc = p.nmax, Rf = p.nmax + 1;
     const size_t m3 = tileRow(T, Rc, i, 3, lb), g3 = tileRow(T, Rf, i + 1, 3, lb);
-    pfRows<36>(p.uP, tileRow(T, Rc, i, 36, lb), TS);
-    pfRows<6>(p.bP, tileRow(T, Rc, i, 6, lb), TS);
-    pfRows<3>(p.W, m3, TS); pfRows<3>(p.Th, m3, TS);
-    pfRows<4>(p.Lam, tileRow(T, Rc, i, 4, lb), TS);
+    pfRowsL1<36>(p.uP, tileRow(T, Rc, i, 36, lb));
+    pfRowsL1<6>(p.bP, tileRow(T, Rc, i, 6, lb));
+    pfRowsL1<3>(p.W, m3); pfRowsL1<3>(p.Th, m3);
+    pfRowsL1<4>(p.Lam, tileRow(T, Rc, i, 4, lb));
     if (SCHEME == BFK_NEWMARK) {
-        pfRows<3>(p.Ac, m3, TS); pfRows<3>(p.dOm, m3, TS);
-        if (p.first) { pfRows<3>(p.U, m3, TS); pfRows<3>(p.Om, m3, TS); }
+        pfRowsL1<3>(p.Ac, m3); pfRowsL1<3>(p.dOm, m3);
+        if (p.first) { pfRowsL1<3>(p.U, m3); pfRowsL1<3>(p.Om, m3); }
     }
-    pfRows<4>(p.Lf, tileRow(T, Rf, i + 1, 4, lb), TS);
-    pfRows<3>(p.K, g3, TS); pfRows<3>(p.Q, g3, TS); pfRows<3>(p.M, g3, TS);
+    if (SCHEME == BFK_EULER) {
+        pfRowsL1<3>(p.U, m3); pfRowsL1<3>(p.Om, m3);
+        if (!p.first) { pfRowsL1<3>(p.Wold, m3); pfRowsL1<3>(p.Uold, m3); pfRowsL1<4>(p.Lamold, tileRow(T, Rc, i, 4, lb)); }
+    }
+    pfRowsL1<4>(p.Lf, tileRow(T, Rf, i + 1, 4, lb));
+    pfRowsL1<3>(p.K, g3); pfRowsL1<3>(p.Q, g3); pfRowsL1<3>(p.M, g3);
 }
 
 template <int SCHEME>
@@ -442,13 +475,13 @@ __global__ void __launch_bounds__(COOP_THREADS) beam_backward_coop(const BeamPar
                 const size_t u0 = tileRow(T, Rc, ic, 36, lb), b0 = tileRow(T, Rc, ic, 6, lb);
                 double x[6];
 #pragma unroll
-                for (int r = 0; r < 6; r++) x[r] = __ldcg(p.bP + b0 + (size_t)r * TS);
+                for (int r = 0; r < 6; r++) x[r] = p.bP[b0 + (size_t)r * TS];
                 if (ic < n - 1) {
 #pragma unroll
                     for (int r = 0; r < 6; r++) {
                         double acc = 0.0;
 #pragma unroll
-                        for (int c = 0; c < 6; c++) acc += __ldcg(p.uP + u0 + (size_t)(6 * r + c) * TS) * xn[c];
+                        for (int c = 0; c < 6; c++) acc += p.uP[u0 + (size_t)(6 * r + c) * TS] * xn[c];
                         x[r] -= acc;
                     }
                 }

@@ -272,16 +272,16 @@ DEV M3 inv(const M3& A)
     return r;
 }
 
-// inv(tensor) that also returns the determinant and the largest |entry|, for the pivot guard of the block eliminations
-DEV M3 invDet(const M3& A, double& det, double& amax)
+// inv(tensor) that also returns the determinant and the squared Frobenius norm, for the pivot guard of the block eliminations
+DEV M3 invDet(const M3& A, double& det, double& frob2)
 {
     const double xx = A.a[0], xy = A.a[1], xz = A.a[2], yx = A.a[3], yy = A.a[4], yz = A.a[5], zx = A.a[6],
                  zy = A.a[7], zz = A.a[8];
     det = xx * yy * zz + xy * yz * zx + xz * yx * zy - xx * yz * zy - xy * yx * zz - xz * yy * zx;
-    double m = fabs(xx);
+    double f = xx * xx;
 #pragma unroll
-    for (int k = 1; k < 9; k++) m = fmax(m, fabs(A.a[k]));
-    amax = m;
+    for (int k = 1; k < 9; k++) f = fma(A.a[k], A.a[k], f);
+    frob2 = f;
     const double id = rcpFast(det);
     M3 r;
     r.a[0] = (yy * zz - zy * yz) * id; r.a[1] = (xz * zy - xy * zz) * id; r.a[2] = (xy * yz - xz * yy) * id;
@@ -289,11 +289,17 @@ DEV M3 invDet(const M3& A, double& det, double& amax)
     r.a[6] = (yx * zy - yy * zx) * id; r.a[7] = (xy * zx - xx * zy) * id; r.a[8] = (xx * yy - yx * xy) * id;
     return r;
 }
-// A 3x3 diagonal sub-block whose determinant is small against the cube of its largest entry is ill-conditioned
-// (cond ~ amax^3 / |det|): the adjugate inverse then loses digits (or divides by zero) where a pivoted LU of the whole
-// 6x6 block -- what the reference's SparseLU does (EigenOF.C:292-297) -- still solves.  NaN counts as "small".
+// A 3x3 diagonal sub-block whose determinant is small against the cube of its size is ill-conditioned
+// (cond ~ |A|^3 / |det|): the adjugate inverse then loses digits (or divides by zero) where a pivoted LU of the whole
+// 6x6 block -- what the reference's SparseLU does (EigenOF.C:292-297) -- still solves.  Size = the Frobenius norm
+// (9 FMAs; an FP64 max costs a compare and two selects per entry): det^2 <= guard^2 (|A|_F^2 / 3)^3, which for a
+// diagonal block diag(a, a, a eps) is eps <= guard.  NaN counts as "small".
 #define BEAM_PIVOT_GUARD 1e-3
-DEV bool smallDet(double det, double amax) { return !(fabs(det) > BEAM_PIVOT_GUARD * amax * amax * amax); }
+DEV bool smallDet(double det, double frob2)
+{
+    const double s = frob2 * (1.0 / 3.0);
+    return !(det * det > (BEAM_PIVOT_GUARD * BEAM_PIVOT_GUARD) * (s * s * s));
+}
 
 // Rodrigues, exactly the reference's plain formula (phi = |theta| + SMALL, no series branch):
 // R = I + (sin phi / phi) S + ((1 - cos phi)/phi^2) S&S      pseudoVector.C:250-264

@@ -126,6 +126,7 @@ extern "C" int64_t bf_num_cells(const bf_ctx* c) { return c->N; }
 extern "C" int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
 extern "C" int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
 extern "C" int64_t bf_launch_count(const bf_ctx* c) { return c->launches; }
+extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return c->longMode ? BF_FAMILY_CELL : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
 
 extern "C" int bf_host_alloc(void** p, int64_t bytes)
 {
@@ -954,33 +955,74 @@ extern "C" int bf_set_momentum_contributions(bf_ctx* c, int32_t n, const bf_mome
     return BF_OK;
 }
 
+// One host->device copy of a [B][3] patch array into the staging buffer, then any number of scatters into end arrays.
+static int stagePatchUpload(bf_ctx* c, const double* host)
+{
+    CUDA_OK(c, cudaMemcpyAsync(c->d_stagePatch, host, sizeof(double) * c->B * 3, cudaMemcpyHostToDevice, c->stream));
+    return BF_OK;
+}
+static void scatterPatch(bf_ctx* c, double* endArr, int end)
+{
+    transposePatch<true><<<(unsigned)((c->B + 255) / 256), 256, 0, c->stream>>>(endArr, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad,
+                                                                                c->nmax + 1, 3, end, 0);
+    c->launches++;
+}
 extern "C" int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const double* v)
 {
     if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !v) return fail(c, BF_ERR_INVALID, "bf_set_bc_values: bad argument");
     CUDA_OK(c, cudaSetDevice(c->device));
-    // entries of beams whose BC class does not use `kind` are never read by the kernels
+    // entries of beams whose BC class does not use `kind` are never read by the kernels.  One copy of the host array, one
+    // wait at the end (the caller may reuse its buffer on return); the scatters stay asynchronous on the stream.
+    double* dst = nullptr;
     switch (kind) {
-    case BF_BCV_W: return xferPatch(c, c->d_wPresc, (double*)v, 3, end, 0, true);
-    case BF_BCV_THETA: return xferPatch(c, c->d_thPresc, (double*)v, 3, end, 0, true);
-    case BF_BCV_MOMENT: return xferPatch(c, c->d_moment, (double*)v, 3, end, 0, true);
-    case BF_BCV_FORCE: {
+    case BF_BCV_W: dst = c->d_wPresc; break;
+    case BF_BCV_THETA: dst = c->d_thPresc; break;
+    case BF_BCV_MOMENT: dst = c->d_moment; break;
+    case BF_BCV_FORCE: break;
+    default: return fail(c, BF_ERR_INVALID, "bf_set_bc_values: unknown kind %d", kind);
+    }
+    if (dst) {
+        if (int rc = stagePatchUpload(c, v)) return rc;
+        scatterPatch(c, dst, end);
+    } else {
         // forceSeries -> force(), followerForceSeries -> followerForce_, offsetForceSeries -> offsetForce_.
         // force() of a spring patch is its own state (set in evaluate) and must not be overwritten.
-        int rc = xferPatch(c, c->d_follower, (double*)v, 3, end, 0, true);
-        if (!rc) rc = xferPatch(c, c->d_offset, (double*)v, 3, end, 0, true);
-        if (rc) return rc;
         const int32_t* wt = c->hostWType.data() + (size_t)end * c->B;
         bool anySpring = false;
         for (int64_t b = 0; b < c->B; b++) if (wt[b] == BF_W_SPRING) { anySpring = true; break; }
-        if (!anySpring) return xferPatch(c, c->d_force, (double*)v, 3, end, 0, true);
-        std::vector<double> cur((size_t)c->B * 3), in(v, v + (size_t)c->B * 3);
-        if ((rc = xferPatch(c, c->d_force, cur.data(), 3, end, 0, false))) return rc;
-        for (int64_t b = 0; b < c->B; b++)
-            if (wt[b] == BF_W_SPRING) for (int k = 0; k < 3; k++) in[3 * b + k] = cur[3 * b + k];
-        return xferPatch(c, c->d_force, in.data(), 3, end, 0, true);
+        if (int rc = stagePatchUpload(c, v)) return rc;
+        scatterPatch(c, c->d_follower, end);
+        scatterPatch(c, c->d_offset, end);
+        if (!anySpring) scatterPatch(c, c->d_force, end);
+        else {
+            std::vector<double> cur((size_t)c->B * 3), in(v, v + (size_t)c->B * 3);
+            if (int rc = xferPatch(c, c->d_force, cur.data(), 3, end, 0, false)) return rc;
+            for (int64_t b = 0; b < c->B; b++)
+                if (wt[b] == BF_W_SPRING) for (int k = 0; k < 3; k++) in[3 * b + k] = cur[3 * b + k];
+            return xferPatch(c, c->d_force, in.data(), 3, end, 0, true);
+        }
     }
-    default: return fail(c, BF_ERR_INVALID, "bf_set_bc_values: unknown kind %d", kind);
-    }
+    CUDA_OK(c, cudaGetLastError());
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+// Patch values of W and Theta of one end of every beam in ONE call (what functionObjects/beamDisplacements reads every
+// step): two gathers, two copies, one wait.
+extern "C" int bf_get_patch_pair(bf_ctx* c, int32_t end, double* W, double* Theta)
+{
+    if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !W || !Theta) return fail(c, BF_ERR_INVALID, "bf_get_patch_pair: bad argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    const unsigned grid = (unsigned)((c->B + 255) / 256);
+    const size_t n = (size_t)c->B * 3;
+    transposePatch<false><<<grid, 256, 0, c->stream>>>(c->d_Wb, c->d_stagePatch, c->d_nSeg, (int)c->B, c->Bpad, c->nmax + 1, 3, end, 0);
+    transposePatch<false><<<grid, 256, 0, c->stream>>>(c->d_Thb, c->d_stagePatch + n, c->d_nSeg, (int)c->B, c->Bpad, c->nmax + 1, 3, end, 0);
+    c->launches += 2;
+    CUDA_OK(c, cudaGetLastError());
+    CUDA_OK(c, cudaMemcpyAsync(W, c->d_stagePatch, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(Theta, c->d_stagePatch + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BF_OK;
 }
 
 extern "C" int bf_begin_step(bf_ctx* c, double deltaT)

@@ -269,6 +269,11 @@ int bf_set_momentum_contributions(bf_ctx* ctx, int32_t n, const bf_momentum_cont
  * values: [nBeams*3] for patch `end`; entries of beams whose BC class does not
  * use `kind` are ignored. */
 int bf_set_bc_values(bf_ctx* ctx, int32_t end, int32_t kind, const double* values);
+/* Patch values of W and Theta at one end of every beam ([nBeams][3] each) in one
+ * call -- the per-step read of functionObjects/beamDisplacements
+ * (functionObjects/beamDisplacements/beamDisplacements.C) -- equal to
+ * bf_get_field(W, ...) + bf_get_field(THETA, ...) for that side. */
+int bf_get_patch_pair(bf_ctx* ctx, int32_t end, double* W, double* Theta);
 
 /* ---- the hot path ---------------------------------------------------------- */
 
@@ -317,6 +322,17 @@ int bf_beam_energy(bf_ctx* ctx, double* out);
  * BEAMGPU_FUSED_KERNEL=1 in the environment both sweeps run in one launch (beam_newton); fwd_ms
  * then holds its time and bwd_ms is 0. */
 int64_t bf_launch_count(const bf_ctx* ctx);
+/* Which kernel family bf_create selected for this bundle (diagnostic; the results do
+ * not depend on it beyond rounding): BF_FAMILY_PER_BEAM one thread per beam (bundles of
+ * at least about one wave of beams), BF_FAMILY_GROUP 4 lanes per beam (smaller bundles),
+ * BF_FAMILY_CELL one thread per cell with block cyclic reduction (few long beams),
+ * BF_FAMILY_CPU for an implementation without kernels (the test oracle).  Mixed pairs
+ * forced through BEAMGPU_COOP=fwd|bwd report the family of the forward sweep. */
+#define BF_FAMILY_CPU (-1)
+#define BF_FAMILY_PER_BEAM 0
+#define BF_FAMILY_GROUP 1
+#define BF_FAMILY_CELL 2
+int32_t bf_kernel_family(const bf_ctx* ctx);
 int bf_kernel_time_ms(bf_ctx* ctx, int32_t reset, double* fwd_ms, double* bwd_ms,
                       int64_t* iterations);
 int bf_set_timing(bf_ctx* ctx, int32_t enabled);

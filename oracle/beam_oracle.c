@@ -178,6 +178,7 @@ int64_t bf_num_cells(const bf_ctx* c) { return c->N; }
 int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
 int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
 int64_t bf_launch_count(const bf_ctx* c) { (void)c; return 0; }
+int32_t bf_kernel_family(const bf_ctx* c) { (void)c; return BF_FAMILY_CPU; }
 int bf_kernel_time_ms(bf_ctx* c, int32_t r, double* a, double* b, int64_t* it)
 {
     (void)c; (void)r;
@@ -463,6 +464,14 @@ int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const double* v)
         default: snprintf(c->err, sizeof c->err, "bf_set_bc_values: unknown kind %d", kind); return BF_ERR_INVALID;
         }
     }
+    return BF_OK;
+}
+
+int bf_get_patch_pair(bf_ctx* c, int32_t end, double* W, double* Theta)
+{
+    if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !W || !Theta) { snprintf(c->err, sizeof c->err, "bf_get_patch_pair: bad argument"); return BF_ERR_INVALID; }
+    memcpy(W, c->Wb + 3 * end * c->B, sizeof(double) * 3 * c->B);
+    memcpy(Theta, c->Thetab + 3 * end * c->B, sizeof(double) * 3 * c->B);
     return BF_OK;
 }
 
