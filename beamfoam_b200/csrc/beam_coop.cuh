@@ -1,307 +1,78 @@
-// beam_coop.cuh — the Newton iteration for bundles BELOW ONE WAVE of beams: several lanes per beam.
+// beam_coop.cuh — the Newton iteration for bundles BELOW ONE WAVE of beams.
 //
 // One thread per beam (beam_kernels.cuh) needs >= 37,888 beams to fill a B200 (148 SMs x 8 warps x 32 lanes); with fewer
-// beams an iteration costs the latency of ONE thread walking its 200-cell recurrence (1.15 ms for 4096 as for 16,384
-// beams).  Here a beam is owned by a GROUP of 4 lanes, a warp holds 8 beams, and the sweeps alternate between two lane
-// mappings over batches of 4 consecutive cells:
+// beams an iteration costs the latency of ONE thread walking its 200-cell recurrence through assembly AND elimination
+// (~5000 cycles per cell: 1.15 ms for 4096 as for 16,384 beams).  Only the block-Thomas elimination is serial along a
+// beam; everything else of the iteration is independent per cell.  These kernels split the two:
 //
-//   forward   (a) assembly, one lane per CELL: lane (j, g) assembles cell i0+j of beam g -- face coefficients
-//                 (updateEqnCoefficients, Evolve.C:673-753), own blocks and source (Matrix.C:55-475), end-patch closure
-//                 (BC.C:64-1190), loads and inertia (Evolve.C:192-536) -- into a shared-memory record of the cell:
-//                 the 6x6 own part of d_i, the source parts, and the five 3x3 tensors that define u_i, l_{i+1} and the
-//                 neighbour part of d_{i+1}.  This part has no serial dependence and runs at full lane efficiency.
-//             (b) elimination, one lane per COLUMN: the block-Thomas recurrence of the 4 cells, cell by cell; the 4 lanes
-//                 of a group factor D'_i redundantly (2x2 block elimination over 3x3 adjugate inverses, pivoted 6x6 LU
-//                 when a 3x3 determinant is small against its block) and lanes 0..2 each solve for two columns of
-//                 uPrime_i, lane 3 for bPrime_i; every lane then forms its columns of the carry
-//                 d_nei - l uPrime | srcNei - l bPrime.  The carry travels through shared memory (42 doubles per beam).
-//   backward  back-substitution of 4 cells redundantly in the 4 lanes of the group (a 6x6 mat-vec per cell on the serial
-//             chain), then one lane per cell: updateSolutionVariables (Evolve.C:757-923) and the patch evaluate()s.
+//   beam_forward_ws  WARP-SPECIALISED, one block = 16 beams = two warps that run concurrently on two SM sub-partitions:
+//       assembler warp    one lane per CELL (2 consecutive cells x 16 beams per pass): face coefficients
+//                         (updateEqnCoefficients, Evolve.C:673-753), own blocks and source (Matrix.C:55-475), end-patch
+//                         closure (BC.C:64-1190), loads and inertia (Evolve.C:192-536) -> a shared-memory RECORD per cell:
+//                         the 3x3 tensors that define u_i, l_{i+1} and the face parts of d_i, d_{i+1}, the inertia
+//                         block and the source parts.  No serial dependence: full lane efficiency, runs ahead of ...
+//       eliminator warp   two lanes per beam, one lane per group of COLUMNS: the block-Thomas recurrence, cell by cell.
+//                         Both lanes factor D'_i (2x2 block elimination over 3x3 adjugate inverses; pivoted 6x6 LU when
+//                         a 3x3 determinant is small against its block), lane 0 solves for columns 0..2 of uPrime_i and
+//                         for bPrime_i, lane 1 for columns 3..5; each lane then forms its columns of the carry
+//                         d_nei - l uPrime | srcNei - l bPrime, which travels through shared memory.
+//       The records are double-buffered; the warps hand the buffers over with named barriers (bar.sync / bar.arrive:
+//       full[2], empty[2]).  The serial chain of a beam shrinks to factorisation + column solves (~1200 cycles per cell).
+//   beam_backsub     the serial part of the backward sweep only: x_i = bPrime_i - uPrime_i x_{i+1}, one thread per beam,
+//                    uPrime/bPrime streamed through a 4-cell cp.async ring in shared memory (the loads do not depend on x,
+//                    so the chain never waits for memory), x written to a tiled [cell][6][32] array.
+//   beam_update_faces / beam_update_cells   updateSolutionVariables (Evolve.C:757-923) and the patch evaluate()s with one
+//                    thread per CELL over the whole bundle: no serial dependence once x is known, so the latency of this
+//                    (HBM-bound) part is hidden by occupancy, not by the length of a beam.  Faces first (they read the
+//                    neighbour cell's pre-update W), then cells and the norms.
 //
-// The per-cell critical path shrinks from a whole assembly + elimination (~5000 cycles) to the factorisation and one
-// column solve (~700 cycles), and a bundle of B beams exposes 4B lanes.  State, scratch layout (uPrime/bPrime) and
-// every per-cell / per-face formula are shared with the one-thread-per-beam kernels, so the two forward and the two
-// backward kernels are interchangeable (tests/test_gpu_coop.py runs all four combinations).
+// State, scratch layout (uPrime/bPrime) and every per-cell / per-face formula are shared with the one-thread-per-beam
+// kernels, so the two forward and the two backward implementations are interchangeable (tests/test_gpu_coop.py runs all
+// four combinations against the oracle).
 #pragma once
 #include "beam_kernels.cuh"
 
-#define COOP_THREADS 32 // one warp = 8 beams per block: small blocks spread a small bundle over all SMs, and the
-                        // shared memory of an SM divides into 7 warps (one more than with 2-warp blocks)
-#define COOP_GROUP 4
-#define COOP_BEAMS_PER_WARP 8
-#define COOP_BEAMS_PER_BLOCK (COOP_THREADS / 32 * COOP_BEAMS_PER_WARP)
+#define WS_THREADS 64
+#define WS_BEAMS 16           // beams per block
+#define WS_BATCH 2            // cells per beam per assembler pass
+// record rows (per cell; row k of column col at rec[k * WS_COLS + col], col = buffer * 32 + slot * 16 + beam)
 enum {
-    K_DA = 0,   // 36: own contributions to d_i, row-major (face i+1 own part, inertia, end-patch closures)
-    K_SO = 36,  // 6: own part of source_i (face i+1, loads, inertia, end patches)
-    K_SN = 42,  // 6: neighbour part of source_{i+1} from face i+1: (eQ ; eM - eMQ)
-    K_P = 48,   // 9: P = a CQW (full)
-    K_QT = 57,  // 9: Qt = 0.5 CQTheta
-    K_SU = 66,  // 9: S1 + S3 + S2, lower-right block of u_i     (S1 = a CMTheta, S3 = 0.5 CMQTheta, S2 = 0.5 CMTheta2)
-    K_SL = 75,  // 9: S1 + S3 - S2, lower-right block of l_{i+1}
-    K_SD = 84,  // 9: S3 - S2 - S1, lower-right block of the neighbour part of d_{i+1}
-    K_ROWS = 93
+    K_DI = 0,   // 10: inertia part of d_i: QRhoCoeff, then the 3x3 MRhoCoeff block (Evolve.C:459-535)
+    K_SO = 10,  // 6: own part of source_i (face i+1, loads, inertia, end patches)
+    K_SN = 16,  // 6: neighbour part of source_{i+1} from face i+1: (eQ ; eM - eMQ)
+    K_P = 22,   // 9: P = a CQW
+    K_QT = 31,  // 9: Qt = 0.5 CQTheta
+    K_S1 = 40,  // 9: S1 = a CMTheta
+    K_S3 = 49,  // 9: S3 = 0.5 CMQTheta
+    K_HM = 58,  // 3: hM = 0.5 M of the face (0.5 CMTheta2 = -spin(hM))
+    K_ROWS = 61,
+    K_PD = K_SN // the LAST cell of a beam has no face i+1: rows K_SN .. K_SN+35 hold the right-patch closure (6x6, row-major)
 };
-// per warp: the records of one batch [K_ROWS][32 = cell slot j * 8 + beam g], the carry [7 columns][6][8 beams] and the
-// neighbour source part of the last cell of the previous batch [6][8]
-#define COOP_CARRY_OFF (K_ROWS * 32)
-#define COOP_SNPREV_OFF (COOP_CARRY_OFF + 42 * 8)
-// ... and the staging rows [ST_ROWS][32 lanes]: the face rows and W that the assembly of the NEXT batch reads, brought in by
-// per-lane cp.async (LDGSTS, no register in flight) while the current batch is being eliminated
-enum { ST_W = 0, ST_WN = 3, ST_LF = 6, ST_K = 10, ST_Q = 13, ST_M = 16, ST_ROWS = 19 };
-#define COOP_STAGE_OFF (COOP_SNPREV_OFF + 6 * 8)
-#define COOP_WARP_DOUBLES (COOP_STAGE_OFF + ST_ROWS * 32)
-#define COOP_SMEM_BYTES ((COOP_THREADS / 32) * COOP_WARP_DOUBLES * sizeof(double))
+#define WS_COLS 64
+#define WS_CARRY_OFF (K_ROWS * WS_COLS)        // carry [7 columns][6 rows][16 beams]
+#define WS_SMEM_DOUBLES (WS_CARRY_OFF + 42 * WS_BEAMS)
+#define WS_SMEM_BYTES (WS_SMEM_DOUBLES * sizeof(double))
+enum { BAR_FULL = 1, BAR_EMPTY = 3 }; // named barriers 1,2 / 3,4 (0 is __syncthreads)
 
-// Pivoted fallback: D (row-major 36) x = cols, two right-hand sides per lane.
-__device__ __noinline__ void coopSolvePivoted(const double* __restrict__ D36, double* __restrict__ cols12)
+DEV void namedSync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(WS_THREADS) : "memory"); }
+DEV void namedArrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(WS_THREADS) : "memory"); }
+
+// Pivoted fallback of the elimination: D (row-major 36) x = cols, four right-hand sides per lane.
+__device__ __noinline__ void wsSolvePivoted(const double* __restrict__ D36, double* __restrict__ cols24)
 {
-    double A[6][6], Bq[6][2];
+    double A[6][6], Bq[6][4];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
 #pragma unroll
         for (int c = 0; c < 6; c++) A[r][c] = D36[6 * r + c];
-        Bq[r][0] = cols12[r];
-        Bq[r][1] = cols12[6 + r];
+#pragma unroll
+        for (int s = 0; s < 4; s++) Bq[r][s] = cols24[6 * s + r];
     }
-    solve6<2>(A, Bq);
+    solve6<4>(A, Bq);
 #pragma unroll
-    for (int r = 0; r < 6; r++) { cols12[r] = Bq[r][0]; cols12[6 + r] = Bq[r][1]; }
-}
-
-// ---- (a) assembly of one cell into its record (rec = warp slab + lane; row k at rec[k * 32]) -------------------------
-// Returns nothing; the complete source of the cell is SO (this record) + SN (record of cell i-1).
-template <int SCHEME>
-DEV void coopAssembleCell(const BeamParams& p, const int b, const int i, const int n, double* __restrict__ rec,
-                          const double* __restrict__ st, const double dZ, const double dcI, const V3 dR0, const V3 CQ, const V3 CM,
-                          const double ARho, const V3 CI)
-{
-    const CellIn cell = loadCellIn<SCHEME>(p, b, i); // issued first: consumed after the face part
-    double D[6][6], src[6];
+    for (int r = 0; r < 6; r++)
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-        src[r] = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; c++) D[r][c] = 0.0;
-    }
-    const V3 Wi = v3(st[(ST_W + 0) * 32], st[(ST_W + 1) * 32], st[(ST_W + 2) * 32]);
-    if (i == 0 || i == n - 1) { // end patches: assembleBoundaryConditions (BC.C:64-1190), additive in D and source
-        double D36[36], s6[6];
-#pragma unroll
-        for (int k = 0; k < 36; k++) D36[k] = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; k++) s6[k] = 0.0;
-        if (i == 0) patchClosure(p, 0, b, Wi, D36, s6);
-        if (i == n - 1) patchClosure(p, 1, b, Wi, D36, s6);
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-            src[r] = s6[r];
-#pragma unroll
-            for (int c = 0; c < 6; c++) D[r][c] = D36[6 * r + c];
-        }
-    }
-    if (i < n - 1) { // internal face i+1: the same folded form as fwdFacePart (beam_kernels.cuh)
-        const V3 Wn = v3(st[(ST_WN + 0) * 32], st[(ST_WN + 1) * 32], st[(ST_WN + 2) * 32]);
-        const Q4 qf = q4(st[(ST_LF + 0) * 32], st[(ST_LF + 1) * 32], st[(ST_LF + 2) * 32], st[(ST_LF + 3) * 32]);
-        const V3 Kf = v3(st[(ST_K + 0) * 32], st[(ST_K + 1) * 32], st[(ST_K + 2) * 32]);
-        const V3 Qf = v3(st[(ST_Q + 0) * 32], st[(ST_Q + 1) * 32], st[(ST_Q + 2) * 32]);
-        const V3 Mf = v3(st[(ST_M + 0) * 32], st[(ST_M + 1) * 32], st[(ST_M + 2) * 32]);
-        const double h = 0.5 * dZ;
-        const V3 t = v3(dR0.x + dcI * (Wn.x - Wi.x), dR0.y + dcI * (Wn.y - Wi.y), dR0.z + dcI * (Wn.z - Wi.z));
-        const V3 th = h * t;
-        const M3 Lm = quatToMat(qf);
-        const V3 hQ = 0.5 * Qf;
-        const Sym3 Pm = conjDiagSym(Lm, dcI * CQ);                              // a*CQW :680
-        const V3 eQ = mul(Lm, cmul(CQ, mulTSub(Lm, t, v3(1.0, 0.0, 0.0))));     // :682 with Gamma of :881-887
-        const M3 Gh = mulSpinR(Pm, th);
-        M3 Qt = Gh;                                                             // 0.5*CQTheta :686-693
-        Qt.a[1] += hQ.z; Qt.a[2] -= hQ.y; Qt.a[3] -= hQ.z; Qt.a[5] += hQ.x; Qt.a[6] += hQ.y; Qt.a[7] -= hQ.x;
-        const V3 eMQ = cross(th, eQ);                                           // :737-741
-        const Sym3 S1 = conjDiagSym(Lm, dcI * CM);                              // a*CMTheta :699
-        const V3 eM = mul(Lm, cmul(CM, Kf));                                    // :684
-        M3 S3;                                                                  // 0.5*CMQTheta :718-735
-        {
-            const double d = dot(th, hQ);
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                const V3 y = cross(th, v3(Gh.a[r], Gh.a[3 + r], Gh.a[6 + r]));
-                const double q = r == 0 ? hQ.x : r == 1 ? hQ.y : hQ.z;
-                S3.a[3 * r] = fma(-q, th.x, y.x); S3.a[3 * r + 1] = fma(-q, th.y, y.y); S3.a[3 * r + 2] = fma(-q, th.z, y.z);
-                S3.a[4 * r] += d;
-            }
-        }
-        const V3 hM = 0.5 * Mf;                                                 // 0.5*CMTheta2 = -S(hM) :703
-        const M3 Pf = full(Pm), S1f = full(S1);
-        M3 S2 = m3zero();                                                       // -spin(hM)
-        S2.a[1] = hM.z; S2.a[2] = -hM.y; S2.a[3] = -hM.z; S2.a[5] = hM.x; S2.a[6] = hM.y; S2.a[7] = -hM.x;
-        const M3 Sm = S3 - S2;
-        const M3 Eo = (S3 - S1f) + S2;                                          // -a*CMTheta + 0.5*CMQTheta + 0.5*CMTheta2
-        addBlk(D, 0, 0, -1.0, Pf);
-        addBlk(D, 0, 3, 1.0, Qt);
-        addBlkT(D, 3, 0, 1.0, Qt);                                              // -a*CMQW = (0.5 CQTheta).T() :706-715
-        addBlk(D, 3, 3, 1.0, Eo);
-        subV(src, 0, eQ);
-        subV(src, 3, eM + eMQ);
-        const V3 sn2 = eM - eMQ;
-        rec[(K_SN + 0) * 32] = eQ.x; rec[(K_SN + 1) * 32] = eQ.y; rec[(K_SN + 2) * 32] = eQ.z;
-        rec[(K_SN + 3) * 32] = sn2.x; rec[(K_SN + 4) * 32] = sn2.y; rec[(K_SN + 5) * 32] = sn2.z;
-        const M3 Su = (S1f + S3) + S2, Sl = S1f + Sm, Sd = Sm - S1f;
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            rec[(K_P + k) * 32] = Pf.a[k];
-            rec[(K_QT + k) * 32] = Qt.a[k];
-            rec[(K_SU + k) * 32] = Su.a[k];
-            rec[(K_SL + k) * 32] = Sl.a[k];
-            rec[(K_SD + k) * 32] = Sd.a[k];
-        }
-    } else { // the last cell has no u, no l: zero tensors keep the column solve of the elimination finite
-#pragma unroll
-        for (int k = K_SN; k < K_ROWS; k++) rec[k * 32] = 0.0;
-    }
-    addLoadsAndInertia<SCHEME>(p, b, i, dZ, ARho, CI, cell, D, src);
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-        rec[(K_SO + r) * 32] = src[r];
-#pragma unroll
-        for (int c = 0; c < 6; c++) rec[(K_DA + 6 * r + c) * 32] = D[r][c];
-    }
-}
-
-// What the assembly of cell i of beam (T, lb) reads: W of the cell and of its right neighbour and the rows of face i+1 by
-// cp.async into the lane's own staging column (nobody else touches it: no barrier needed, only cp.async.wait_all before
-// the reads); the rows the inertia terms read are pulled into L2 and loaded directly at the top of the assembly.
-template <int SCHEME>
-DEV void coopStageCell(const BeamParams& p, const size_t T, const int lb, const int i, const int n, double* __restrict__ st)
-{
-    if (i >= n) return;
-    const int Rc = p.nmax, Rf = p.nmax + 1;
-    const size_t c3 = tileRow(T, Rc, i, 3, lb), c4 = tileRow(T, Rc, i, 4, lb);
-#pragma unroll
-    for (int k = 0; k < 3; k++) cpAsync8(st + (ST_W + k) * 32, p.W + c3 + k * TS);
-    if (i + 1 < n) {
-        const size_t w3 = tileRow(T, Rc, i + 1, 3, lb), f3 = tileRow(T, Rf, i + 1, 3, lb), f4 = tileRow(T, Rf, i + 1, 4, lb);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            cpAsync8(st + (ST_WN + k) * 32, p.W + w3 + k * TS);
-            cpAsync8(st + (ST_K + k) * 32, p.K + f3 + k * TS);
-            cpAsync8(st + (ST_Q + k) * 32, p.Q + f3 + k * TS);
-            cpAsync8(st + (ST_M + k) * 32, p.M + f3 + k * TS);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) cpAsync8(st + (ST_LF + k) * 32, p.Lf + f4 + k * TS);
-    }
-    if (SCHEME != BFK_STEADY) {
-        pfRows<4>(p.Lam, c4, TS);
-        pfRows<3>(p.Om, c3, TS);
-        if (SCHEME == BFK_NEWMARK) {
-            pfRows<3>(p.Ac, c3, TS); pfRows<3>(p.dOm, c3, TS);
-            if (p.first) pfRows<3>(p.U, c3, TS);
-        } else {
-            pfRows<3>(p.U, c3, TS);
-            if (!p.first) { pfRows<3>(p.Uold, c3, TS); pfRows<3>(p.Omold, c3, TS); }
-        }
-    }
-}
-
-// ---- (b) elimination of one cell by the 4 lanes of its group ---------------------------------------------------------
-// rc = record column of the cell (warp slab + slot * 8 + g), cy = carry column of the beam (warp slab + COOP_CARRY_OFF + g).
-// role 0..2: columns role and role+3 of [u_i]; role 3: the right-hand side.  Returns the lane's two columns of the new
-// carry in nA, nB (the caller stores them between two warp barriers).
-DEV void coopEliminateCell(const BeamParams& p, const size_t T, const int lb, const int i, const bool last, const int role,
-                           const double* __restrict__ rc, const double* __restrict__ cy, double (&nA)[6], double (&nB)[6])
-{
-    M3 A, Bm, Cm, E;
-#pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) { // D'_i = carry (column-major) + own part (row-major)
-            A.a[3 * r + c] = cy[(6 * c + r) * 8] + rc[(K_DA + 6 * r + c) * 32];
-            Bm.a[3 * r + c] = cy[(6 * (c + 3) + r) * 8] + rc[(K_DA + 6 * r + c + 3) * 32];
-            Cm.a[3 * r + c] = cy[(6 * c + r + 3) * 8] + rc[(K_DA + 6 * (r + 3) + c) * 32];
-            E.a[3 * r + c] = cy[(6 * (c + 3) + r + 3) * 8] + rc[(K_DA + 6 * (r + 3) + c + 3) * 32];
-        }
-    const bool isRhs = role == 3;
-    const int rr = isRhs ? 2 : role;
-    // the lane's two right-hand-side columns: (a) u[:, role] = (P[:, role] ; -Qt[role, :]) or the source, (b) u[:, role+3]
-    V3 a1, a2, b1, b2;
-    {
-        const V3 pc = v3(rc[(K_P + rr) * 32], rc[(K_P + 3 + rr) * 32], rc[(K_P + 6 + rr) * 32]);
-        const V3 qr = v3(rc[(K_QT + 3 * rr) * 32], rc[(K_QT + 3 * rr + 1) * 32], rc[(K_QT + 3 * rr + 2) * 32]);
-        const V3 s1 = v3(rc[(K_SO + 0) * 32] + cy[36 * 8], rc[(K_SO + 1) * 32] + cy[37 * 8], rc[(K_SO + 2) * 32] + cy[38 * 8]);
-        const V3 s2 = v3(rc[(K_SO + 3) * 32] + cy[39 * 8], rc[(K_SO + 4) * 32] + cy[40 * 8], rc[(K_SO + 5) * 32] + cy[41 * 8]);
-        a1 = isRhs ? s1 : pc;
-        a2 = isRhs ? s2 : -qr;
-        b1 = v3(rc[(K_QT + rr) * 32], rc[(K_QT + 3 + rr) * 32], rc[(K_QT + 6 + rr) * 32]);
-        b2 = v3(rc[(K_SU + rr) * 32], rc[(K_SU + 3 + rr) * 32], rc[(K_SU + 6 + rr) * 32]);
-    }
-    double detA, detS, mA, mS;
-    const M3 Ai = invDet(A, detA, mA);
-    const M3 AiB = mul(Ai, Bm);
-    const M3 S = subMulM(E, Cm, AiB);
-    const M3 Si = invDet(S, detS, mS);
-    V3 xa1, xa2, xb1, xb2;
-    if (smallDet(detA, mA) || smallDet(detS, mS)) { // identical in the 4 lanes of the group (same D')
-        double D36[36], cols[12];
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                D36[6 * r + c] = A.a[3 * r + c]; D36[6 * r + c + 3] = Bm.a[3 * r + c];
-                D36[6 * (r + 3) + c] = Cm.a[3 * r + c]; D36[6 * (r + 3) + c + 3] = E.a[3 * r + c];
-            }
-        cols[0] = a1.x; cols[1] = a1.y; cols[2] = a1.z; cols[3] = a2.x; cols[4] = a2.y; cols[5] = a2.z;
-        cols[6] = b1.x; cols[7] = b1.y; cols[8] = b1.z; cols[9] = b2.x; cols[10] = b2.y; cols[11] = b2.z;
-        coopSolvePivoted(D36, cols);
-        xa1 = v3(cols[0], cols[1], cols[2]); xa2 = v3(cols[3], cols[4], cols[5]);
-        xb1 = v3(cols[6], cols[7], cols[8]); xb2 = v3(cols[9], cols[10], cols[11]);
-    } else {
-        const V3 ya = mul(Ai, a1);
-        xa2 = mul(Si, subMul(a2, Cm, ya));
-        xa1 = subMul(ya, AiB, xa2);
-        const V3 yb = mul(Ai, b1);
-        xb2 = mul(Si, subMul(b2, Cm, yb));
-        xb1 = subMul(yb, AiB, xb2);
-    }
-    // ---- uPrime columns / bPrime to the scratch (same layout as the one-thread-per-beam sweeps)
-    if (isRhs) {
-        const size_t b0 = tileRow(T, p.nmax, i, 6, lb);
-        stS(p.bP + b0, xa1.x); stS(p.bP + b0 + TS, xa1.y); stS(p.bP + b0 + 2 * TS, xa1.z);
-        stS(p.bP + b0 + 3 * TS, xa2.x); stS(p.bP + b0 + 4 * TS, xa2.y); stS(p.bP + b0 + 5 * TS, xa2.z);
-    } else if (!last) {
-        double* u = p.uP + tileRow(T, p.nmax, i, 36, lb);
-        stS(u + (size_t)(role) * TS, xa1.x); stS(u + (size_t)(6 + role) * TS, xa1.y); stS(u + (size_t)(12 + role) * TS, xa1.z);
-        stS(u + (size_t)(18 + role) * TS, xa2.x); stS(u + (size_t)(24 + role) * TS, xa2.y); stS(u + (size_t)(30 + role) * TS, xa2.z);
-        stS(u + (size_t)(3 + role) * TS, xb1.x); stS(u + (size_t)(9 + role) * TS, xb1.y); stS(u + (size_t)(15 + role) * TS, xb1.z);
-        stS(u + (size_t)(21 + role) * TS, xb2.x); stS(u + (size_t)(27 + role) * TS, xb2.y); stS(u + (size_t)(33 + role) * TS, xb2.z);
-    }
-    // ---- the lane's columns of the carry of cell i+1:  N - l X,
-    //      l = [[P, -Qt], [Qt.T(), Sl]],  N = neighbour part of d_{i+1} = [[-P, -Qt], [-Qt.T(), Sd]] | srcNei
-    {
-        M3 Pf, Qt, Sl;
-#pragma unroll
-        for (int k = 0; k < 9; k++) { Pf.a[k] = rc[(K_P + k) * 32]; Qt.a[k] = rc[(K_QT + k) * 32]; Sl.a[k] = rc[(K_SL + k) * 32]; }
-        const V3 sn1 = v3(rc[(K_SN + 0) * 32], rc[(K_SN + 1) * 32], rc[(K_SN + 2) * 32]);
-        const V3 sn2 = v3(rc[(K_SN + 3) * 32], rc[(K_SN + 4) * 32], rc[(K_SN + 5) * 32]);
-        const V3 sd = v3(rc[(K_SD + rr) * 32], rc[(K_SD + 3 + rr) * 32], rc[(K_SD + 6 + rr) * 32]);
-        const V3 na1 = isRhs ? sn1 : -a1, na2 = isRhs ? sn2 : a2; // column role < 3 of N: (-P[:, c] ; -Qt[c, :])
-        const V3 nb1 = -b1, nb2 = sd;                             // column role + 3 of N: (-Qt[:, k] ; Sd[:, k])
-        const double xA1[3] = {xa1.x, xa1.y, xa1.z}, xA2[3] = {xa2.x, xa2.y, xa2.z};
-        const double xB1[3] = {xb1.x, xb1.y, xb1.z}, xB2[3] = {xb2.x, xb2.y, xb2.z};
-        const double nA1[3] = {na1.x, na1.y, na1.z}, nA2[3] = {na2.x, na2.y, na2.z};
-        const double nB1[3] = {nb1.x, nb1.y, nb1.z}, nB2[3] = {nb2.x, nb2.y, nb2.z};
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            double ta = nA1[r], tb = nB1[r], ba = nA2[r], bb = nB2[r];
-#pragma unroll
-            for (int k = 0; k < 3; k++) { ta = fma(-Pf.a[3 * r + k], xA1[k], ta); tb = fma(-Pf.a[3 * r + k], xB1[k], tb); }
-#pragma unroll
-            for (int k = 0; k < 3; k++) { ta = fma(Qt.a[3 * r + k], xA2[k], ta); tb = fma(Qt.a[3 * r + k], xB2[k], tb); }
-#pragma unroll
-            for (int k = 0; k < 3; k++) { ba = fma(-Sl.a[3 * r + k], xA2[k], ba); bb = fma(-Sl.a[3 * r + k], xB2[k], bb); }
-#pragma unroll
-            for (int k = 0; k < 3; k++) { ba = fma(-Qt.a[3 * k + r], xA1[k], ba); bb = fma(-Qt.a[3 * k + r], xB1[k], bb); }
-            nA[r] = ta; nA[3 + r] = ba; nB[r] = tb; nB[3 + r] = bb;
-        }
-    }
+        for (int s = 0; s < 4; s++) cols24[6 * s + r] = Bq[r][s];
 }
 
 // Per-beam constants of the lane's beam, loaded once.
@@ -326,197 +97,457 @@ DEV CoopBeam coopLoadBeam(const BeamParams& p, const int b, const bool live)
     return k;
 }
 
+// L2 prefetch of what the assembly of cell i of beam (T, lb) reads
 template <int SCHEME>
-__global__ void __launch_bounds__(COOP_THREADS) beam_forward_coop(const BeamParams p)
+DEV void wsPrefetchCell(const BeamParams& p, const size_t T, const int lb, const int i, const int n)
 {
-    extern __shared__ __align__(16) unsigned char coop_smem[];
+    if (i >= n) return;
+    const int Rc = p.nmax, Rf = p.nmax + 1;
+    const size_t c3 = tileRow(T, Rc, i, 3, lb), c4 = tileRow(T, Rc, i, 4, lb);
+    pfRows<3>(p.W, c3, TS);
+    if (i + 1 < n) {
+        const size_t f3 = tileRow(T, Rf, i + 1, 3, lb);
+        pfRows<4>(p.Lf, tileRow(T, Rf, i + 1, 4, lb), TS);
+        pfRows<3>(p.K, f3, TS); pfRows<3>(p.Q, f3, TS); pfRows<3>(p.M, f3, TS);
+    }
+    if (SCHEME != BFK_STEADY) {
+        pfRows<4>(p.Lam, c4, TS);
+        pfRows<3>(p.Om, c3, TS);
+        if (SCHEME == BFK_NEWMARK) {
+            pfRows<3>(p.Ac, c3, TS); pfRows<3>(p.dOm, c3, TS);
+            if (p.first) pfRows<3>(p.U, c3, TS);
+        } else {
+            pfRows<3>(p.U, c3, TS);
+            if (!p.first) { pfRows<3>(p.Uold, c3, TS); pfRows<3>(p.Omold, c3, TS); }
+        }
+    }
+}
+
+// ---- assembler: one cell into its record (rec = record base + column; row k at rec[k * WS_COLS]) -------------------------
+// cyInit (cell 0 only): the carry of the beam, initialised with the left-patch closure.  Returns the own part of the
+// source (K_SO) in so[]; the complete source of the cell is so + SN of cell i-1.
+template <int SCHEME>
+DEV void wsAssembleCell(const BeamParams& p, const int b, const int i, const int n, double* __restrict__ rec,
+                        double* __restrict__ cyInit, const CoopBeam& kb, double (&so)[6])
+{
+    const size_t T = (size_t)(b >> 5);
+    const int lb = b & 31, Rc = p.nmax, Rf = p.nmax + 1;
+    const CellIn cell = loadCellIn<SCHEME>(p, b, i); // issued first: consumed after the face part
+    double src[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) src[r] = 0.0;
+    const V3 Wi = ld3(p.W, tileRow(T, Rc, i, 3, lb), TS);
+    if (i == 0) { // left patch (BC.C:64-1190): its 6x6 part starts the carry, its source part joins the own source
+        double D36[36], s6[6];
+#pragma unroll
+        for (int k = 0; k < 36; k++) D36[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s6[k] = 0.0;
+        patchClosure(p, 0, b, Wi, D36, s6);
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            src[r] = s6[r];
+            cyInit[(36 + r) * WS_BEAMS] = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) cyInit[(6 * c + r) * WS_BEAMS] = D36[6 * r + c]; // the carry is column-major
+        }
+    }
+    if (i < n - 1) { // internal face i+1: the same folded form as fwdFacePart (beam_kernels.cuh)
+        const size_t f3 = tileRow(T, Rf, i + 1, 3, lb);
+        const V3 Wn = ld3(p.W, tileRow(T, Rc, i + 1, 3, lb), TS);
+        const Q4 qf = ldq(p.Lf, tileRow(T, Rf, i + 1, 4, lb), TS);
+        const V3 Kf = ld3(p.K, f3, TS), Qf = ld3(p.Q, f3, TS), Mf = ld3(p.M, f3, TS);
+        const double h = 0.5 * kb.dZ, dcI = kb.dcI;
+        const V3 t = v3(kb.dR0.x + dcI * (Wn.x - Wi.x), kb.dR0.y + dcI * (Wn.y - Wi.y), kb.dR0.z + dcI * (Wn.z - Wi.z));
+        const V3 th = h * t;
+        const M3 Lm = quatToMat(qf);
+        const V3 hQ = 0.5 * Qf;
+        const Sym3 Pm = conjDiagSym(Lm, dcI * kb.CQ);                           // a*CQW :680
+        const V3 eQ = mul(Lm, cmul(kb.CQ, mulTSub(Lm, t, v3(1.0, 0.0, 0.0))));  // :682 with Gamma of :881-887
+        const M3 Gh = mulSpinR(Pm, th);
+        M3 Qt = Gh;                                                             // 0.5*CQTheta :686-693
+        Qt.a[1] += hQ.z; Qt.a[2] -= hQ.y; Qt.a[3] -= hQ.z; Qt.a[5] += hQ.x; Qt.a[6] += hQ.y; Qt.a[7] -= hQ.x;
+        const V3 eMQ = cross(th, eQ);                                           // :737-741
+        const Sym3 S1 = conjDiagSym(Lm, dcI * kb.CM);                           // a*CMTheta :699
+        const V3 eM = mul(Lm, cmul(kb.CM, Kf));                                 // :684
+        M3 S3;                                                                  // 0.5*CMQTheta :718-735
+        {
+            const double d = dot(th, hQ);
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const V3 y = cross(th, v3(Gh.a[r], Gh.a[3 + r], Gh.a[6 + r]));
+                const double q = r == 0 ? hQ.x : r == 1 ? hQ.y : hQ.z;
+                S3.a[3 * r] = fma(-q, th.x, y.x); S3.a[3 * r + 1] = fma(-q, th.y, y.y); S3.a[3 * r + 2] = fma(-q, th.z, y.z);
+                S3.a[4 * r] += d;
+            }
+        }
+        const V3 hM = 0.5 * Mf;                                                 // 0.5*CMTheta2 = -S(hM) :703
+        const M3 Pf = full(Pm), S1f = full(S1);
+        subV(src, 0, eQ);
+        subV(src, 3, eM + eMQ);
+        const V3 sn2 = eM - eMQ;
+        rec[(K_SN + 0) * WS_COLS] = eQ.x; rec[(K_SN + 1) * WS_COLS] = eQ.y; rec[(K_SN + 2) * WS_COLS] = eQ.z;
+        rec[(K_SN + 3) * WS_COLS] = sn2.x; rec[(K_SN + 4) * WS_COLS] = sn2.y; rec[(K_SN + 5) * WS_COLS] = sn2.z;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            rec[(K_P + k) * WS_COLS] = Pf.a[k];
+            rec[(K_QT + k) * WS_COLS] = Qt.a[k];
+            rec[(K_S1 + k) * WS_COLS] = S1f.a[k];
+            rec[(K_S3 + k) * WS_COLS] = S3.a[k];
+        }
+        rec[(K_HM + 0) * WS_COLS] = hM.x; rec[(K_HM + 1) * WS_COLS] = hM.y; rec[(K_HM + 2) * WS_COLS] = hM.z;
+    } else { // the last cell: right patch instead of a face; its 6x6 part takes the tensor rows of the record
+        double D36[36], s6[6];
+#pragma unroll
+        for (int k = 0; k < 36; k++) D36[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s6[k] = 0.0;
+        patchClosure(p, 1, b, Wi, D36, s6);
+#pragma unroll
+        for (int r = 0; r < 6; r++) src[r] += s6[r];
+#pragma unroll
+        for (int k = 0; k < 36; k++) rec[(K_PD + k) * WS_COLS] = D36[k];
+    }
+    double D[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) D[r][c] = 0.0;
+    addLoadsAndInertia<SCHEME>(p, b, i, kb.dZ, kb.ARho, kb.CI, cell, D, src); // touches D[0..2][0..2] (diagonal) and D[3..5][3..5]
+    rec[K_DI * WS_COLS] = D[0][0];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) rec[(K_DI + 1 + 3 * r + c) * WS_COLS] = D[3 + r][3 + c];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        rec[(K_SO + r) * WS_COLS] = src[r];
+        so[r] = src[r];
+    }
+}
+
+// ---- eliminator: one cell by the 2 lanes of its beam ---------------------------------------------------------------------
+// rc = record column of the cell, cy = carry column of the beam (+ g).  role 0: columns 0..2 of u_i and the right-hand
+// side; role 1: columns 3..5 (and an idle fourth slot).  Returns the lane's columns of the new carry in nc[slot][row].
+DEV void wsEliminateCell(const BeamParams& p, const size_t T, const int lb, const int i, const bool last, const int role,
+                         const double* __restrict__ rc, const double* __restrict__ cy, double (&nc)[4][6])
+{
+#define RC(k) rc[(k) * WS_COLS]
+#define CY(c, r) cy[(6 * (c) + (r)) * WS_BEAMS]
+    M3 Pf, Qt, S1, S3, S2;
+    M3 A, Bm, Cm, E;
+    const double qd = RC(K_DI);
+    if (!last) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) { Pf.a[k] = RC(K_P + k); Qt.a[k] = RC(K_QT + k); S1.a[k] = RC(K_S1 + k); S3.a[k] = RC(K_S3 + k); }
+        const V3 hM = v3(RC(K_HM), RC(K_HM + 1), RC(K_HM + 2));
+        S2 = m3zero(); // -spin(hM)
+        S2.a[1] = hM.z; S2.a[2] = -hM.y; S2.a[3] = -hM.z; S2.a[5] = hM.x; S2.a[6] = hM.y; S2.a[7] = -hM.x;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { // D'_i = carry (column-major) + own part: [[-P + q I, Qt], [Qt.T(), S3 - S1 + S2 + inertia]]
+                A.a[3 * r + c] = CY(c, r) - Pf.a[3 * r + c] + (r == c ? qd : 0.0);
+                Bm.a[3 * r + c] = CY(c + 3, r) + Qt.a[3 * r + c];
+                Cm.a[3 * r + c] = CY(c, r + 3) + Qt.a[3 * c + r];
+                E.a[3 * r + c] = CY(c + 3, r + 3) + (((S3.a[3 * r + c] - S1.a[3 * r + c]) + S2.a[3 * r + c]) + RC(K_DI + 1 + 3 * r + c));
+            }
+    } else {
+        Pf = Qt = S1 = S3 = S2 = m3zero();
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { // carry + right-patch closure + inertia
+                A.a[3 * r + c] = CY(c, r) + RC(K_PD + 6 * r + c) + (r == c ? qd : 0.0);
+                Bm.a[3 * r + c] = CY(c + 3, r) + RC(K_PD + 6 * r + c + 3);
+                Cm.a[3 * r + c] = CY(c, r + 3) + RC(K_PD + 6 * (r + 3) + c);
+                E.a[3 * r + c] = CY(c + 3, r + 3) + (RC(K_PD + 6 * (r + 3) + c + 3) + RC(K_DI + 1 + 3 * r + c));
+            }
+    }
+    // ---- the lane's right-hand sides: slots 0..2 = u[:, 3 role + s], slot 3 = source - l bPrime (role 0 only)
+    //      u = [[P, Qt], [-Qt.T(), S1 + S3 + S2]]
+    double t1[4][3], t2[4][3];
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            t1[s][k] = role ? Qt.a[3 * k + s] : Pf.a[3 * k + s];
+            t2[s][k] = role ? (S1.a[3 * k + s] + S3.a[3 * k + s]) + S2.a[3 * k + s] : -Qt.a[3 * s + k];
+        }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        t1[3][k] = role ? 0.0 : RC(K_SO + k) + CY(6, k);
+        t2[3][k] = role ? 0.0 : RC(K_SO + 3 + k) + CY(6, 3 + k);
+    }
+    double detA, detS, fA, fS;
+    const M3 Ai = invDet(A, detA, fA);
+    const M3 AiB = mul(Ai, Bm);
+    const M3 S = subMulM(E, Cm, AiB);
+    const M3 Si = invDet(S, detS, fS);
+    double x1[4][3], x2[4][3];
+    if (smallDet(detA, fA) || smallDet(detS, fS)) { // identical in both lanes of the beam (same D')
+        double D36[36], cols[24];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                D36[6 * r + c] = A.a[3 * r + c]; D36[6 * r + c + 3] = Bm.a[3 * r + c];
+                D36[6 * (r + 3) + c] = Cm.a[3 * r + c]; D36[6 * (r + 3) + c + 3] = E.a[3 * r + c];
+            }
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) { cols[6 * s + k] = t1[s][k]; cols[6 * s + 3 + k] = t2[s][k]; }
+        wsSolvePivoted(D36, cols);
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) { x1[s][k] = cols[6 * s + k]; x2[s][k] = cols[6 * s + 3 + k]; }
+    } else {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const V3 y = mul(Ai, v3(t1[s][0], t1[s][1], t1[s][2]));
+            const V3 b2 = mul(Si, subMul(v3(t2[s][0], t2[s][1], t2[s][2]), Cm, y));
+            const V3 b1 = subMul(y, AiB, b2);
+            x1[s][0] = b1.x; x1[s][1] = b1.y; x1[s][2] = b1.z;
+            x2[s][0] = b2.x; x2[s][1] = b2.y; x2[s][2] = b2.z;
+        }
+    }
+    // ---- uPrime columns / bPrime to the scratch (same layout as the one-thread-per-beam sweeps)
+    if (role == 0) {
+        const size_t b0 = tileRow(T, p.nmax, i, 6, lb);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { stS(p.bP + b0 + (size_t)k * TS, x1[3][k]); stS(p.bP + b0 + (size_t)(3 + k) * TS, x2[3][k]); }
+    }
+    if (last) return;
+    {
+        double* u = p.uP + tileRow(T, p.nmax, i, 36, lb) + (size_t)(3 * role) * TS;
+#pragma unroll
+        for (int s = 0; s < 3; s++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                stS(u + (size_t)(6 * k + s) * TS, x1[s][k]);
+                stS(u + (size_t)(6 * (k + 3) + s) * TS, x2[s][k]);
+            }
+    }
+    // ---- the lane's columns of the carry of cell i+1:  N - l X,
+    //      l = [[P, -Qt], [Qt.T(), Sl]], Sl = S1 + S3 - S2;  N = [[-P, -Qt], [-Qt.T(), S3 - S2 - S1]] | srcNei
+    M3 Sl;
+#pragma unroll
+    for (int k = 0; k < 9; k++) Sl.a[k] = S1.a[k] + (S3.a[k] - S2.a[k]);
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        double n1[3], n2[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (s < 3) {
+                n1[k] = -t1[s][k];                                                                   // -P[:, s] or -Qt[:, s]
+                n2[k] = role ? (S3.a[3 * k + s] - S2.a[3 * k + s]) - S1.a[3 * k + s] : t2[s][k];     // Sd[:, s] or -Qt[s, :]
+            } else {
+                n1[k] = RC(K_SN + k);
+                n2[k] = RC(K_SN + 3 + k);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            double ta = n1[r], ba = n2[r];
+#pragma unroll
+            for (int k = 0; k < 3; k++) ta = fma(-Pf.a[3 * r + k], x1[s][k], ta);
+#pragma unroll
+            for (int k = 0; k < 3; k++) ta = fma(Qt.a[3 * r + k], x2[s][k], ta);
+#pragma unroll
+            for (int k = 0; k < 3; k++) ba = fma(-Sl.a[3 * r + k], x2[s][k], ba);
+#pragma unroll
+            for (int k = 0; k < 3; k++) ba = fma(-Qt.a[3 * k + r], x1[s][k], ba);
+            nc[s][r] = ta; nc[s][3 + r] = ba;
+        }
+    }
+#undef RC
+#undef CY
+}
+
+template <int SCHEME>
+__global__ void __launch_bounds__(WS_THREADS) beam_forward_ws(const BeamParams p)
+{
+    extern __shared__ __align__(16) unsigned char ws_smem[];
+    double* sm = (double*)ws_smem;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int g = lane & 7, j = lane >> 3; // beam of the warp; cell slot (assembly) / column role (elimination)
-    const int b = blockIdx.x * COOP_BEAMS_PER_BLOCK + w * COOP_BEAMS_PER_WARP + g;
+    const int g = lane & 15, j = lane >> 4; // beam of the block; cell slot (assembler) / column role (eliminator)
+    const int b = blockIdx.x * WS_BEAMS + g;
     const bool live = b < p.B;
-    double* warpSm = (double*)coop_smem + (size_t)w * COOP_WARP_DOUBLES;
-    double* rec = warpSm + lane;
-    double* cy = warpSm + COOP_CARRY_OFF + g;
-    double* sp = warpSm + COOP_SNPREV_OFF + g;
-    double* st = warpSm + COOP_STAGE_OFF + lane;
-    const CoopBeam kb = coopLoadBeam<SCHEME>(p, b, live);
-    const int n = kb.n;
-    const int nW = __reduce_max_sync(0xffffffffu, n);
     const size_t T = (size_t)(b >> 5);
     const int lb = b & 31;
+    double* cy = sm + WS_CARRY_OFF + g;
+    const int n = live ? p.nSeg[b] : 0;
+    const int nW = __reduce_max_sync(0xffffffffu, n);
+    const int nBatches = (nW + WS_BATCH - 1) / WS_BATCH;
     double res = 0.0;
-    // carry = 0, previous neighbour source = 0
-    for (int k = j; k < 42; k += 4) cy[k * 8] = 0.0;
-    if (j == 0) {
+    if (w == 1) {
+        // ================= assembler warp: lane (j, g) assembles cell 2k + j of beam g into buffer k & 1
+        const CoopBeam kb = coopLoadBeam<SCHEME>(p, b, live);
+        wsPrefetchCell<SCHEME>(p, T, lb, WS_BATCH + j, n);
+        for (int k = 0; k < nBatches; k++) {
+            const int buf = k & 1, i = WS_BATCH * k + j;
+            if (k >= 2) namedSync(BAR_EMPTY + buf); // the eliminator has finished with batch k - 2
+            double* rec = sm + buf * 32 + lane;
+            double so[6];
+            const bool mine = i < n;
+            if (mine) wsAssembleCell<SCHEME>(p, b, i, n, rec, cy, kb, so);
+            wsPrefetchCell<SCHEME>(p, T, lb, i + 2 * WS_BATCH, n);
+            __syncwarp();
+            if (mine) { // ||source||^2 (EigenOF.C:253-282, x0 = 0): own part + neighbour part from face i (cell i-1's record)
+                const double* prev = j ? rec - 16 : sm + (1 - buf) * 32 + 16 + g;
 #pragma unroll
-        for (int r = 0; r < 6; r++) sp[r * 8] = 0.0;
-    }
-    coopStageCell<SCHEME>(p, T, lb, j, n, st);
-    __syncwarp();
-    for (int i0 = 0; i0 < nW; i0 += COOP_GROUP) {
-        // ---- (a) one lane per cell
-        const int i = i0 + j;
-        const bool mine = i < n;
-        cpAsyncWaitAll();
-        if (mine) coopAssembleCell<SCHEME>(p, b, i, n, rec, st, kb.dZ, kb.dcI, kb.dR0, kb.CQ, kb.CM, kb.ARho, kb.CI);
-        coopStageCell<SCHEME>(p, T, lb, i + COOP_GROUP, n, st); // the next batch's rows arrive during the elimination
-        __syncwarp();
-        if (mine) { // ||source||^2 (EigenOF.C:253-282, x0 = 0): own part + neighbour part from face i
-#pragma unroll
-            for (int r = 0; r < 6; r++) {
-                const double sPrev = j == 0 ? sp[r * 8] : warpSm[(K_SN + r) * 32 + lane - 8];
-                const double s = rec[(K_SO + r) * 32] + sPrev;
-                res = fma(s, s, res);
-            }
-        }
-        __syncwarp();
-        // ---- (b) one lane per column, cell by cell
-#pragma unroll 1
-        for (int jj = 0; jj < COOP_GROUP; jj++) {
-            const int ic = i0 + jj;
-            const bool active = ic < n;
-            const bool last = ic == n - 1;
-            double nA[6], nB[6];
-            if (active) coopEliminateCell(p, T, lb, ic, last, j, warpSm + jj * 8 + g, cy, nA, nB);
-            __syncwarp(); // every lane has read the old carry
-            if (active && !last) {
-                const int cA = j == 3 ? 6 : j;
-#pragma unroll
-                for (int r = 0; r < 6; r++) cy[(6 * cA + r) * 8] = nA[r];
-                if (j < 3) {
-#pragma unroll
-                    for (int r = 0; r < 6; r++) cy[(6 * (j + 3) + r) * 8] = nB[r];
+                for (int r = 0; r < 6; r++) {
+                    const double s = so[r] + (i > 0 ? prev[(K_SN + r) * WS_COLS] : 0.0);
+                    res = fma(s, s, res);
                 }
             }
-            __syncwarp();
+            __threadfence_block();
+            namedArrive(BAR_FULL + buf);
         }
-        // the neighbour source part of the batch's last cell outlives its record
-        if (j == 3 && mine) {
+    } else {
+        // ================= eliminator warp: lanes (role j, g) walk the recurrence of beam g
+        for (int k = 0; k < nBatches; k++) {
+            const int buf = k & 1;
+            namedSync(BAR_FULL + buf);
+#pragma unroll 1
+            for (int jj = 0; jj < WS_BATCH; jj++) {
+                const int ic = WS_BATCH * k + jj;
+                const bool active = ic < n, last = ic == n - 1;
+                double nc[4][6];
+                if (active) wsEliminateCell(p, T, lb, ic, last, j, sm + buf * 32 + jj * 16 + g, cy, nc);
+                __syncwarp(); // both lanes of every beam have read the old carry
+                if (active && !last) {
 #pragma unroll
-            for (int r = 0; r < 6; r++) sp[r * 8] = rec[(K_SN + r) * 32];
+                    for (int s = 0; s < 3; s++)
+#pragma unroll
+                        for (int r = 0; r < 6; r++) cy[(6 * (3 * j + s) + r) * WS_BEAMS] = nc[s][r];
+                    if (j == 0) {
+#pragma unroll
+                        for (int r = 0; r < 6; r++) cy[(36 + r) * WS_BEAMS] = nc[3][r];
+                    }
+                }
+                __syncwarp();
+            }
+            if (k + 2 < nBatches) namedArrive(BAR_EMPTY + buf);
         }
-        __syncwarp();
     }
     double v[1] = {res};
     blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward: back-substitution redundantly in the group, update one lane per cell
+// backward, serial part: x_i = bPrime_i - uPrime_i & x_{i+1}.  One thread per beam; the 42 scratch rows of a cell are one
+// contiguous 42 x 256 B run per warp tile, streamed through a ring of BS_RING cells by per-lane cp.async.
+// X: tiled like a 6-component cell array, [tile][nmax][6][32].
 // ---------------------------------------------------------------------------------------------------------------------
-// The backward kernel takes no shared memory, so the whole L1 is a cache and a batch's rows (4 cells x 8 beams x ~77
-// doubles = 20 KB per warp) fit it many times over: the rows of the NEXT batch are prefetched into L1 while this one is
-// being updated, and the serial chain x_i = bPrime_i - uPrime_i x_{i+1} then reads L1 hits instead of exposing an L2
-// round trip per cell (the kernel is launched after the forward sweep wrote the scratch, so L1 holds nothing stale).
-DEV void pfL1(const double* __restrict__ p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-template <int NR>
-DEV void pfRowsL1(const double* __restrict__ p, size_t i0)
-{
-#pragma unroll
-    for (int k = 0; k < NR; k++) pfL1(p + i0 + (size_t)k * TS);
-}
-template <int SCHEME>
-DEV void coopPrefetchBack(const BeamParams& p, const size_t T, const int lb, const int i, const int n)
-{
-    if (i < 0 || i >= n) return;
-    const int Rc = p.nmax, Rf = p.nmax + 1;
-    const size_t m3 = tileRow(T, Rc, i, 3, lb), g3 = tileRow(T, Rf, i + 1, 3, lb);
-    pfRowsL1<36>(p.uP, tileRow(T, Rc, i, 36, lb));
-    pfRowsL1<6>(p.bP, tileRow(T, Rc, i, 6, lb));
-    pfRowsL1<3>(p.W, m3); pfRowsL1<3>(p.Th, m3);
-    pfRowsL1<4>(p.Lam, tileRow(T, Rc, i, 4, lb));
-    if (SCHEME == BFK_NEWMARK) {
-        pfRowsL1<3>(p.Ac, m3); pfRowsL1<3>(p.dOm, m3);
-        if (p.first) { pfRowsL1<3>(p.U, m3); pfRowsL1<3>(p.Om, m3); }
-    }
-    if (SCHEME == BFK_EULER) {
-        pfRowsL1<3>(p.U, m3); pfRowsL1<3>(p.Om, m3);
-        if (!p.first) { pfRowsL1<3>(p.Wold, m3); pfRowsL1<3>(p.Uold, m3); pfRowsL1<4>(p.Lamold, tileRow(T, Rc, i, 4, lb)); }
-    }
-    pfRowsL1<4>(p.Lf, tileRow(T, Rf, i + 1, 4, lb));
-    pfRowsL1<3>(p.K, g3); pfRowsL1<3>(p.Q, g3); pfRowsL1<3>(p.M, g3);
-}
+#define BS_THREADS 32
+#define BS_RING 4
+#define BS_SMEM_BYTES ((BS_THREADS / 32) * BS_RING * 42 * 32 * sizeof(double))
+DEV void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+DEV void cpAsyncWaitGroup() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int SCHEME>
-__global__ void __launch_bounds__(COOP_THREADS) beam_backward_coop(const BeamParams p)
+__global__ void __launch_bounds__(BS_THREADS) beam_backsub(const BeamParams p, double* __restrict__ X)
 {
+    extern __shared__ __align__(16) unsigned char bs_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int g = lane & 7, j = lane >> 3;
-    const int b = blockIdx.x * COOP_BEAMS_PER_BLOCK + w * COOP_BEAMS_PER_WARP + g;
-    const bool live = b < p.B;
+    const int b = blockIdx.x * BS_THREADS + threadIdx.x;
     const size_t T = (size_t)(b >> 5);
-    const int lb = b & 31, Rc = p.nmax;
-    const int n = live ? p.nSeg[b] : 0;
+    const int Rc = p.nmax;
+    const int n = b < p.B ? p.nSeg[b] : 0;
     const int nW = __reduce_max_sync(0xffffffffu, n);
-    const double dZ = p.dZ[b];
-    const double dcI = 1.0 / dZ, dcB = 2.0 / dZ, delta = 1.0 / dcB;
-    const V3 CQ = ld3(p.CQ, b, p.Bpad), CM = ld3(p.CM, b, p.Bpad);
-    V3 dR0, e0;
-    {
-        const M3 refL = ld9(p.refL, b, p.Bpad);
-        dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
-        e0 = mulT(refL, dR0);
-    }
-    double dx2 = 0.0, x2 = 0.0;
-    double xn[6] = {0, 0, 0, 0, 0, 0};   // x of the cell right of the one being substituted
-    V3 WoldCarry = v3(0, 0, 0);          // pre-update W of the first cell of the batch to the right
-    const int iTop = nW > 0 ? ((nW - 1) / COOP_GROUP) * COOP_GROUP : -COOP_GROUP;
-    coopPrefetchBack<SCHEME>(p, T, lb, iTop + j, n);
-    for (int i0 = iTop; i0 >= 0; i0 -= COOP_GROUP) {
-        coopPrefetchBack<SCHEME>(p, T, lb, i0 - COOP_GROUP + j, n);
-        // ---- back substitution x_i = bPrime_i - uPrime_i & x_{i+1} of the batch, in every lane of the group
-        double xm[6], xr[6]; // the lane's own cell (i0 + j) and its right neighbour
+    double* ring = (double*)bs_smem + (size_t)w * BS_RING * 42 * 32 + lane;
+    auto issue = [&](int i) { // rows of cell i -> ring slot i % BS_RING (own column only: no barrier needed)
+        if (i >= 0 && i < n) {
+            double* dst = ring + (size_t)(i % BS_RING) * 42 * 32;
+            const double* u = p.uP + tileRow(T, Rc, i, 36, lane);
+            const double* bb = p.bP + tileRow(T, Rc, i, 6, lane);
+            if (i < n - 1) {
 #pragma unroll
-        for (int r = 0; r < 6; r++) { xm[r] = 0.0; xr[r] = xn[r]; }
+                for (int k = 0; k < 36; k++) cpAsync8(dst + k * 32, u + (size_t)k * TS);
+            }
 #pragma unroll
-        for (int jj = COOP_GROUP - 1; jj >= 0; jj--) {
-            const int ic = i0 + jj;
-            if (ic < n) {
-                const size_t u0 = tileRow(T, Rc, ic, 36, lb), b0 = tileRow(T, Rc, ic, 6, lb);
-                double x[6];
+            for (int k = 0; k < 6; k++) cpAsync8(dst + (36 + k) * 32, bb + (size_t)k * TS);
+        }
+        cpAsyncCommit(); // one group per cell index, also when this lane has nothing to copy
+    };
+    for (int d = 0; d < BS_RING - 1; d++) issue(nW - 1 - d);
+    double xn[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = nW - 1; i >= 0; i--) {
+        issue(i - (BS_RING - 1));
+        cpAsyncWaitGroup<BS_RING - 1>(); // the group of cell i has landed
+        if (i < n) {
+            const double* src = ring + (size_t)(i % BS_RING) * 42 * 32;
+            double x[6];
 #pragma unroll
-                for (int r = 0; r < 6; r++) x[r] = p.bP[b0 + (size_t)r * TS];
-                if (ic < n - 1) {
-#pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int c = 0; c < 6; c++) acc += p.uP[u0 + (size_t)(6 * r + c) * TS] * xn[c];
-                        x[r] -= acc;
-                    }
-                }
+            for (int r = 0; r < 6; r++) x[r] = src[(36 + r) * 32];
+            if (i < n - 1) {
 #pragma unroll
                 for (int r = 0; r < 6; r++) {
-                    xn[r] = x[r];
-                    if (jj == j) xm[r] = x[r];
-                    if (jj == j + 1) xr[r] = x[r];
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; c++) acc += src[(6 * r + c) * 32] * xn[c];
+                    x[r] -= acc;
                 }
             }
-        }
-        // ---- one lane per cell: updateSolutionVariables (Evolve.C:757-923) and the patch evaluate()s
-        const int i = i0 + j;
-        const bool mine = i < n;
-        const V3 DW = v3(xm[0], xm[1], xm[2]), DT = v3(xm[3], xm[4], xm[5]);
-        V3 Wold = v3(0, 0, 0);
-        if (mine) {
+            double* o = X + tileRow(T, Rc, i, 6, lane);
 #pragma unroll
-            for (int r = 0; r < 6; r++) dx2 += xm[r] * xm[r];
-            updateCell<SCHEME>(p, T, lb, i, DW, DT, Wold, x2);
+            for (int r = 0; r < 6; r++) { xn[r] = x[r]; o[(size_t)r * TS] = x[r]; }
         }
-        // the pre-update W of cell i+1 lives in the lane of the next slot (same beam: lane + 8), or came from the
-        // previous batch for the last slot
-        V3 WoldN;
-        WoldN.x = __shfl_down_sync(0xffffffffu, Wold.x, 8);
-        WoldN.y = __shfl_down_sync(0xffffffffu, Wold.y, 8);
-        WoldN.z = __shfl_down_sync(0xffffffffu, Wold.z, 8);
-        if (j == COOP_GROUP - 1) WoldN = WoldCarry;
-        if (mine)
-            updateFacesOfCell(p, b, i, n, CQ, CM, dR0, e0, dcI, dcB, delta, Wold, WoldN, DW, DT, v3(xr[0], xr[1], xr[2]),
-                              v3(xr[3], xr[4], xr[5]));
-        WoldCarry.x = __shfl_sync(0xffffffffu, Wold.x, g);
-        WoldCarry.y = __shfl_sync(0xffffffffu, Wold.y, g);
-        WoldCarry.z = __shfl_sync(0xffffffffu, Wold.z, g);
     }
-    double v[2] = {dx2, x2};
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward, parallel part: one thread per (tile, cell, lane) = per cell of the bundle, beams fastest (coalesced rows).
+// ---------------------------------------------------------------------------------------------------------------------
+DEV bool cellOfThread(const BeamParams& p, int& b, int& i)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = (int)(t & 31);
+    const size_t row = t >> 5; // T * nmax + i
+    const size_t T = row / (size_t)p.nmax;
+    i = (int)(row - T * (size_t)p.nmax);
+    b = (int)(T * 32) + lane;
+    return b < p.B && i < p.nSeg[b];
+}
+DEV void ldX(const double* __restrict__ X, size_t T, int Rc, int i, int lane, V3& a, V3& c)
+{
+    const size_t x0 = tileRow(T, Rc, i, 6, lane);
+    a = v3(X[x0], X[x0 + TS], X[x0 + 2 * TS]);
+    c = v3(X[x0 + 3 * TS], X[x0 + 4 * TS], X[x0 + 5 * TS]);
+}
+// Faces first: they read the neighbour cell's pre-update W ...
+__global__ void __launch_bounds__(128) beam_update_faces(const BeamParams p, const double* __restrict__ X)
+{
+    int b, i;
+    if (!cellOfThread(p, b, i)) return;
+    const size_t T = (size_t)(b >> 5), sb = p.Bpad;
+    const int lane = b & 31, Rc = p.nmax, n = p.nSeg[b];
+    const double dZ = p.dZ[b], dcI = 1.0 / dZ, dcB = 2.0 / dZ, delta = 1.0 / dcB;
+    const V3 CQ = ld3(p.CQ, b, sb), CM = ld3(p.CM, b, sb);
+    const M3 refL = ld9(p.refL, b, sb);
+    const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]), e0 = mulT(refL, dR0);
+    V3 DW, DT, xWn = v3(0, 0, 0), xTn = v3(0, 0, 0), WoldN = v3(0, 0, 0);
+    ldX(X, T, Rc, i, lane, DW, DT);
+    if (i < n - 1) {
+        ldX(X, T, Rc, i + 1, lane, xWn, xTn);
+        WoldN = ld3(p.W, tileRow(T, Rc, i + 1, 3, lane), TS);
+    }
+    updateFacesOfCell(p, b, i, n, CQ, CM, dR0, e0, dcI, dcB, delta, ld3(p.W, tileRow(T, Rc, i, 3, lane), TS), WoldN, DW, DT, xWn, xTn);
+}
+// ... then the cells, and the two solution norms.
+template <int SCHEME>
+__global__ void __launch_bounds__(128) beam_update_cells(const BeamParams p, const double* __restrict__ X)
+{
+    int b, i;
+    double v[2] = {0.0, 0.0};
+    if (cellOfThread(p, b, i)) {
+        V3 DW, DT, Wold;
+        ldX(X, (size_t)(b >> 5), p.nmax, i, b & 31, DW, DT);
+        v[0] = DW.x * DW.x + DW.y * DW.y + DW.z * DW.z + DT.x * DT.x + DT.y * DT.y + DT.z * DT.z;
+        updateCell<SCHEME>(p, (size_t)(b >> 5), b & 31, i, DW, DT, Wold, v[1]);
+    }
     blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
 }

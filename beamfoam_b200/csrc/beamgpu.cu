@@ -45,6 +45,7 @@ struct bf_ctx {
     int Bpad, nmax, grid;
     // bundles below one wave of beams: group-cooperative kernels (beam_coop.cuh), selectable per sweep
     int coopFwd, coopBwd, coopGrid;
+    double* d_X; // coopBwd: the solution increments, tiled [tile][nmax][6][32] (beam_backsub -> beam_update_*)
     int partialStride; // leading dimension of d_partial: the largest block count of any kernel family
     std::vector<int32_t> nSeg, hostWType; // hostWType: [2][B]
     std::vector<int64_t> cellStart, faceStart;
@@ -403,9 +404,10 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     CREATE_CUDA(cudaFuncSetAttribute(KERNEL<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES))
     OPT_IN_SMEM(beam_newton);
     OPT_IN_SMEM(beam_forward);
-    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_coop<BFK_STEADY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_coop<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_coop<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_STEADY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
@@ -486,10 +488,12 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     // ---- block-Thomas scratch + partial sums
     {
         char* cur;
-        c->coopGrid = (Bpad + COOP_BEAMS_PER_BLOCK - 1) / COOP_BEAMS_PER_BLOCK;
+        c->coopGrid = (Bpad + WS_BEAMS - 1) / WS_BEAMS;
         c->partialStride = c->grid;
         if ((int)((c->N + 127) / 128) > c->partialStride) c->partialStride = (int)((c->N + 127) / 128);
         if (c->coopGrid > c->partialStride) c->partialStride = c->coopGrid;
+        const int cellGrid = (int)(((size_t)Bpad * (size_t)nmax + 127) / 128); // beam_update_*: one thread per (padded) cell
+        if (cellGrid > c->partialStride) c->partialStride = cellGrid;
         if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->partialStride + 8) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
         c->d_partial = carve<double>(cur, 3 * (size_t)c->partialStride); c->d_sums = carve<double>(cur, 8);
@@ -508,6 +512,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
                 else c->coopFwd = c->coopBwd = atoi(e) ? 1 : 0;
             }
         }
+        c->d_X = nullptr;
+        if (c->coopBwd && devAlloc(c, (void**)&c->d_X, sizeof(double) * 6 * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         // BEAMGPU_LONG_BEAMS = 1 / 0 forces the cell-parallel path on / off; by default it serves bundles that cannot
         // occupy the GPU with one thread per beam but have enough cells per beam to do so with one thread per cell
         const char* lm = getenv("BEAMGPU_LONG_BEAMS");
@@ -1169,14 +1175,21 @@ static int launchIteration(bf_ctx* c)
         else long_update_cells<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
         c->launches += 2;
     } else if (c->splitKernels || c->coopFwd || c->coopBwd) { // product path: one launch per sweep
-        if (c->coopFwd) LAUNCH_SCHEME_T(beam_forward_coop, c->coopGrid, COOP_THREADS, COOP_SMEM_BYTES, p);
+        if (c->coopFwd) LAUNCH_SCHEME_T(beam_forward_ws, c->coopGrid, WS_THREADS, WS_SMEM_BYTES, p);
         else LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
-        if (c->coopBwd) LAUNCH_SCHEME_T(beam_backward_coop, c->coopGrid, COOP_THREADS, 0, p);
-        else LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
+        const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
+        if (c->coopBwd) { // serial back-substitution, then the update with one thread per cell
+            beam_backsub<<<(unsigned)((c->Bpad + BS_THREADS - 1) / BS_THREADS), BS_THREADS, BS_SMEM_BYTES, c->stream>>>(p, c->d_X);
+            beam_update_faces<<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            if (c->scheme == BF_SCHEME_NEWMARK) beam_update_cells<BFK_NEWMARK><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            else if (c->scheme == BF_SCHEME_EULER) beam_update_cells<BFK_EULER><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            else beam_update_cells<BFK_STEADY><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            c->launches += 2;
+        } else LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
         c->launches += 2;
         nF = c->coopFwd ? c->coopGrid : c->grid;
-        nB = c->coopBwd ? c->coopGrid : c->grid;
+        nB = c->coopBwd ? cellGrid : c->grid;
     } else {
         LAUNCH_SCHEME(beam_newton, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));

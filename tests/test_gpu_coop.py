@@ -1,10 +1,11 @@
 """The two kernel families of the Newton iteration against the oracle, in every combination.
 
-Bundles below one wave of beams run the group-cooperative kernels of beam_coop.cuh (4 lanes per beam), larger ones
-the one-thread-per-beam sweeps of beam_kernels.cuh; `bf_create` picks by beam count.  Every other GPU test uses small
-bundles and therefore exercises the cooperative pair; here BEAMGPU_COOP forces each family and each mixed pair
-(cooperative forward + per-beam backward and vice versa share the uPrime/bPrime scratch) on the same cases, with the
-north-star bar: identical Newton iteration counts per step, tips within 1e-10 relative.
+Bundles below one wave of beams run the kernels of beam_coop.cuh (warp-specialised forward sweep with two lanes per
+beam in the elimination; serial back-substitution + one-thread-per-cell update), larger ones the one-thread-per-beam
+sweeps of beam_kernels.cuh; `bf_create` picks by beam count.  Every other GPU test uses small bundles and therefore
+exercises the first family; here BEAMGPU_COOP forces each family and each mixed pair (the forward sweep of one with the
+backward sweep of the other: they share the uPrime/bPrime scratch) on the same cases, with the north-star bar:
+identical Newton iteration counts per step, tips within 1e-10 relative.
 """
 import dataclasses
 import os
@@ -32,8 +33,8 @@ def coop_mode(request):
 
 
 def test_newmark_bundle(gpu_lib, oracle_lib, coop_mode):
-    """3DdynamicCantileverMultiBeamDensity: 70 beams (not a multiple of a warp's 8 nor of a block's 16) x 37 cells
-    (not a multiple of the 4-cell batch)."""
+    """3DdynamicCantileverMultiBeamDensity: 70 beams (not a multiple of a block's 16 nor of a tile's 32) x 37 cells
+    (not a multiple of the 2-cell batch)."""
     run_pair(cases.multiBeamDensity(70, 37, jitter=True), gpu_lib, oracle_lib, nSteps=25)
 
 
@@ -57,7 +58,7 @@ def test_euler_scheme(gpu_lib, oracle_lib, coop_mode):
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9])
 def test_short_beams(gpu_lib, oracle_lib, coop_mode, n):
-    """Beams shorter than, equal to and just longer than one 4-cell batch; n = 1 closes both patches on one cell."""
+    """Beams shorter than, equal to and just longer than one or two 2-cell batches; n = 1 closes both patches on one cell."""
     case = dataclasses.replace(cases.multiBeamDensity(5, n), nSegments=n)
     g = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
     o = coupledTotalLagNewtonRaphsonBeam(case, library=oracle_lib)
@@ -69,7 +70,7 @@ def test_short_beams(gpu_lib, oracle_lib, coop_mode, n):
 
 
 def test_ragged_bundle(gpu_lib, oracle_lib, coop_mode):
-    """Beams of different cell counts inside one warp: groups run out of cells at different batches."""
+    """Beams of different cell counts inside one block: beams run out of cells at different batches."""
     B = 19
     nSeg = np.array([3 + (7 * b) % 23 for b in range(B)], dtype=np.int32)
     case = dataclasses.replace(cases.multiBeamDensity(B, 10, jitter=True), nSegments=nSeg)
