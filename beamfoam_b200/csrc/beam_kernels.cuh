@@ -82,6 +82,7 @@ struct BeamParams {
     double *Lf, *K, *Q, *M;
     // ends [2][nc][Bpad]
     double *Wb, *Thb, *Lamb, *DWb, *DThb, *force;
+    double* ifW; // [3][Bpad] split sweeps: pre-update W of the cell left of the interface
     const double *wPresc, *thPresc, *follower, *offset, *moment, *springK, *springDir;
     // block-Thomas scratch
     double* uP; // [tile][nmax][36][32]
@@ -362,6 +363,9 @@ DEV void blockReduceStore(double (&v)[NV], double* __restrict__ partial, int slo
 #ifndef BEAM_MIN_BLOCKS
 #define BEAM_MIN_BLOCKS 2
 #endif
+#ifndef BEAM_BWD_MIN_BLOCKS
+#define BEAM_BWD_MIN_BLOCKS BEAM_MIN_BLOCKS
+#endif
 enum {
     R_DR0 = 0,   // dR0Ds = refLambdaf & e_x (3)
     R_DZ = 3,    // dZ of the beam (1)
@@ -486,13 +490,16 @@ DEV int laneId()
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); // re-read where needed: a value kept across the cell gets spilled
     return l;
 }
+// cellRow: the cell whose Newmark / Euler rows are pulled into L2 (its cp.async follows a phase later); wRow, faceRow: the
+// rows of W and of the face arrays that the bulk copies fetch (the neighbour cell and the face towards it).  A
+// left-to-right sweep passes (i, i + 1, i + 1); the mirrored half of a split beam walks the rows downwards.
 template <int SCHEME>
-DEV void fwdPrefetchFace(const BeamParams& p, size_t T, double* warpSm, uint64_t* bar, int i)
+DEV void fwdPrefetchFaceRows(const BeamParams& p, size_t T, double* warpSm, uint64_t* bar, int cellRow, int wRow, int faceRow)
 {
     const int Rc = p.nmax, Rf = p.nmax + 1;
     const int lane = laneId();
     if (SCHEME == BFK_EULER) { // the cell rows the Euler inertia terms read (fwdPrefetchCell)
-        const int ic = min(i + BEAM_PFCELL_DIST - 1, Rc - 1);
+        const int ic = max(min(cellRow, Rc - 1), 0);
         const size_t n3 = tileRow(T, Rc, ic, 3, 0) + 3 * lane;
         pfNm(p.Lam + tileRow(T, Rc, ic, 4, 0) + 4 * lane);
         pfNm(p.U + n3);
@@ -502,7 +509,7 @@ DEV void fwdPrefetchFace(const BeamParams& p, size_t T, double* warpSm, uint64_t
     if (SCHEME == BFK_NEWMARK) { // the cell rows of the same cell: pull them into L2 now, the cp.async follows a phase later
         // one address per lane and array: nc rows x 32 doubles are contiguous, lane l touches double nc*l, so every
         // 32-byte sector of the nc x 256 B run is requested once
-        const int ic = min(i + BEAM_PFCELL_DIST - 1, Rc - 1);
+        const int ic = max(min(cellRow, Rc - 1), 0);
         const size_t n3 = tileRow(T, Rc, ic, 3, 0) + 3 * lane;
         pfNm(p.Lam + tileRow(T, Rc, ic, 4, 0) + 4 * lane);
         pfNm(p.Ac + n3);
@@ -511,14 +518,19 @@ DEV void fwdPrefetchFace(const BeamParams& p, size_t T, double* warpSm, uint64_t
         if (p.first) pfNm(p.U + n3);
     }
     if (lane != 0) return;
-    const bool hasW = i + 1 < p.nmax; // no cell i+1 in the slab for the last row
+    const bool hasW = wRow >= 0 && wRow < p.nmax; // no neighbour cell in the slab past either end
     mbarExpectTx(bar, ((hasW ? 3 : 0) + 4 + 9) * 256u);
     double* buf = warpSm + (size_t)R_BUF * 32;
-    if (hasW) bulkLoad(buf + B_W * 32, p.W + tileRow(T, Rc, i + 1, 3, 0), 3 * 256, bar);
-    bulkLoad(buf + B_LF * 32, p.Lf + tileRow(T, Rf, i + 1, 4, 0), 4 * 256, bar);
-    bulkLoad(buf + B_K * 32, p.K + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
-    bulkLoad(buf + B_Q * 32, p.Q + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
-    bulkLoad(buf + B_M * 32, p.M + tileRow(T, Rf, i + 1, 3, 0), 3 * 256, bar);
+    if (hasW) bulkLoad(buf + B_W * 32, p.W + tileRow(T, Rc, wRow, 3, 0), 3 * 256, bar);
+    bulkLoad(buf + B_LF * 32, p.Lf + tileRow(T, Rf, faceRow, 4, 0), 4 * 256, bar);
+    bulkLoad(buf + B_K * 32, p.K + tileRow(T, Rf, faceRow, 3, 0), 3 * 256, bar);
+    bulkLoad(buf + B_Q * 32, p.Q + tileRow(T, Rf, faceRow, 3, 0), 3 * 256, bar);
+    bulkLoad(buf + B_M * 32, p.M + tileRow(T, Rf, faceRow, 3, 0), 3 * 256, bar);
+}
+template <int SCHEME>
+DEV void fwdPrefetchFace(const BeamParams& p, size_t T, double* warpSm, uint64_t* bar, int i)
+{
+    fwdPrefetchFaceRows<SCHEME>(p, T, warpSm, bar, i + BEAM_PFCELL_DIST - 1, i + 1, i + 1);
 }
 template <int SCHEME>
 DEV void fwdPrefetchCell(const BeamParams& p, size_t T, double* sm, int i)
@@ -760,7 +772,11 @@ DEV void addLoadsAndInertia(const BeamParams& p, const int b, const int i, const
 // prefetch buffer, already in registers), adds the own part of d_i to the carry Dc, starts source_i, and parks the face
 // tensors in the stash.  LAST = the cell whose right face is the right patch: it closes the patch instead of an
 // internal face.  The loads and inertia of the cell follow in addLoadsAndInertia once its Newmark rows have arrived.
-template <bool LAST>
+// MIR: the cell belongs to the mirrored half of a split beam (forwardSweepSplit): the sweep walks right to left, "the
+// next cell" is cell i-1 and the face between them is seen from its neighbour side.  The neighbour-side blocks are the
+// owner-side blocks with Qt and M negated (d_nei = [[-P, -Qt], [-Qt.T(), S3 - S2 - S1]], l = [[P, -Qt], [Qt.T(), S1 + S3 - S2]],
+// source parts (+eQ ; eM - eMQ)), i.e. the same code with th, hQ, hM, eQ, eM negated; t keeps the face's own orientation.
+template <bool LAST, bool MIR = false>
 DEV void fwdFacePart(const BeamParams& p, const int b, double* __restrict__ sm, const double dcI, const double h,
                      const FaceIn& in, double (&Dc)[6][6], double (&src)[6], V3& Wi)
 {
@@ -776,11 +792,12 @@ DEV void fwdFacePart(const BeamParams& p, const int b, double* __restrict__ sm, 
         //   0.5 CMQTheta = -(Gh.T() S(th) + S(th) S(hQ)),  Gh = P S(th),  S(a) S(b) = b a.T() - (a.b) I
         const V3 Wn = in.Wn;
         const V3 dR0 = smLd3(sm, R_DR0);
-        const V3 t = v3(dR0.x + dcI * (Wn.x - Wi.x), dR0.y + dcI * (Wn.y - Wi.y), dR0.z + dcI * (Wn.z - Wi.z)); // dR0Ds + snGrad(W)
+        const double sdc = MIR ? -dcI : dcI;
+        const V3 t = v3(dR0.x + sdc * (Wn.x - Wi.x), dR0.y + sdc * (Wn.y - Wi.y), dR0.z + sdc * (Wn.z - Wi.z)); // dR0Ds + snGrad(W)
         Wi = Wn;
-        const V3 th = h * t;
+        const V3 th = (MIR ? -h : h) * t;
         const M3 Lm = quatToMat(in.qf);                                               // Lambdaf & refLambdaf :678
-        const V3 hQ = 0.5 * in.Q;
+        const V3 hQ = (MIR ? -0.5 : 0.5) * in.Q;
         V3 eQ;
         M3 Gh;
         {
@@ -788,6 +805,7 @@ DEV void fwdFacePart(const BeamParams& p, const int b, double* __restrict__ sm, 
             const Sym3 Pm = conjDiagSym(Lm, dcI * CQ);                                // a*CQW :680
             // refLambdaf.T() & dR0Ds = e_x: bf_create orthonormalises refLambdaf and dR0Ds is its first column
             eQ = mul(Lm, cmul(CQ, mulTSub(Lm, t, v3(1.0, 0.0, 0.0))));                // :682 with Gamma of :881-887
+            if (MIR) eQ = -eQ;
             Gh = mulSpinR(Pm, th);
             M3 Qt = Gh;                                                               // 0.5*CQTheta :686-693
             Qt.a[1] += hQ.z; Qt.a[2] -= hQ.y; Qt.a[3] -= hQ.z; Qt.a[5] += hQ.x; Qt.a[6] += hQ.y; Qt.a[7] -= hQ.x;
@@ -801,7 +819,8 @@ DEV void fwdFacePart(const BeamParams& p, const int b, double* __restrict__ sm, 
         {
             const V3 CM = smLd3(sm, R_CM);
             const Sym3 S1 = conjDiagSym(Lm, dcI * CM);                                // a*CMTheta :699
-            const V3 eM = mul(Lm, cmul(CM, in.K));                                    // :684
+            V3 eM = mul(Lm, cmul(CM, in.K));                                          // :684
+            if (MIR) eM = -eM;
             M3 S3;                                                                    // 0.5*CMQTheta :718-735
             {
                 const double d = dot(th, hQ);
@@ -813,7 +832,7 @@ DEV void fwdFacePart(const BeamParams& p, const int b, double* __restrict__ sm, 
                     S3.a[4 * r] += d;
                 }
             }
-            const V3 hM = 0.5 * in.M;                                                 // 0.5*CMTheta2 = -S(hM) :703
+            const V3 hM = (MIR ? -0.5 : 0.5) * in.M;                                  // 0.5*CMTheta2 = -S(hM) :703
             smStS(sm, R_S1, S1);
             smSt9(sm, R_S3, S3);
             smSt3(sm, R_MF, hM);
@@ -1313,6 +1332,37 @@ DEV void updateCell(const BeamParams& p, const size_t T, const int lane, const i
     }
 }
 
+// Update of the internal face j (between cell j-1, its owner (A), and cell j, its neighbour (B)): Evolve.C:804-836, 881-913
+// with the coefficients recomputed from the pre-solve state.  WoldA / WoldB: pre-update W of the two cells.
+DEV void updateInternalFace(const BeamParams& p, const int b, const int j, const V3 CQ, const V3 CM, const V3 dR0, const V3 e0,
+                            const double dcI, const V3 WoldA, const V3 WoldB, const V3 DWa, const V3 DTa, const V3 DWb, const V3 DTb)
+{
+    const size_t T = (size_t)(b >> 5);
+    const int lane = b & 31, Rf = p.nmax + 1;
+    const size_t f3 = tileRow(T, Rf, j, 3, lane), f4 = tileRow(T, Rf, j, 4, lane);
+    const Q4 qfOld = ldq(p.Lf, f4, TS);
+    const V3 Kold = ld3(p.K, f3, TS);
+    const M3 LmOld = quatToMat(qfOld);
+    const V3 t = dR0 + dcI * (WoldB - WoldA);
+    const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, t), Kold, ld3(p.Q, f3, TS), ld3(p.M, f3, TS), t, dcI, false);
+    const FaceState o = updateFace(f, qfOld, LmOld, Kold, DWa, DWb, DTa, DTb, dcI, false);
+    stq(p.Lf, f4, TS, o.Lf);
+    st3(p.K, f3, TS, o.K); st3(p.Q, f3, TS, o.Q); st3(p.M, f3, TS, o.M);
+}
+// The evaluate() of the patch fields of one end and the update of its boundary face (face 0 or face n); Wold, DW, DT
+// belong to the cell next to the patch.
+DEV void updatePatchFace(const BeamParams& p, const int b, const int end, const int n, const V3 CQ, const V3 CM, const double dcB,
+                         const double delta, const V3 Wold, const V3 DW, const V3 DT)
+{
+    const size_t T = (size_t)(b >> 5);
+    const int lane = b & 31, Rf = p.nmax + 1, j = end ? n : 0;
+    const size_t f3 = tileRow(T, Rf, j, 3, lane), f4 = tileRow(T, Rf, j, 4, lane);
+    const Q4 qfOld = ldq(p.Lf, f4, TS);
+    const V3 Kold = ld3(p.K, f3, TS);
+    const FaceState o = patchUpdate(p, end, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, TS), ld3(p.M, f3, TS), Wold, DW, DT, dcB, delta);
+    stq(p.Lf, f4, TS, o.Lf);
+    st3(p.K, f3, TS, o.K); st3(p.Q, f3, TS, o.Q); st3(p.M, f3, TS, o.M);
+}
 // The faces a cell owns in the update: face i+1 (internal, or the right patch for the last cell) and, for cell 0, the
 // left patch (Evolve.C:804-836, 881-913 and the evaluate() of the patch fields, Theta before W).  (A) = this cell,
 // (N) = cell i+1: WoldN its pre-update W, xWn / xTn its increments.
@@ -1320,36 +1370,9 @@ DEV void updateFacesOfCell(const BeamParams& p, const int b, const int i, const 
                            const V3 e0, const double dcI, const double dcB, const double delta, const V3 Wold, const V3 WoldN,
                            const V3 DW, const V3 DT, const V3 xWn, const V3 xTn)
 {
-    const size_t s = TS;
-    const size_t T = (size_t)(b >> 5);
-    const int lane = b & 31, Rf = p.nmax + 1;
-    // ---- face j = i+1
-    {
-        const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f4 = tileRow(T, Rf, i + 1, 4, lane);
-        const Q4 qfOld = ldq(p.Lf, f4, s);
-        const V3 Kold = ld3(p.K, f3, s);
-        FaceState o;
-        if (i == n - 1) { // right patch
-            o = patchUpdate(p, 1, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s), Wold, DW, DT, dcB, delta);
-        } else {
-            const M3 LmOld = quatToMat(qfOld);
-            const V3 t = dR0 + dcI * (WoldN - Wold);
-            const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, t), Kold,
-                                                ld3(p.Q, f3, s), ld3(p.M, f3, s), t, dcI, false);
-            o = updateFace(f, qfOld, LmOld, Kold, DW, xWn, DT, xTn, dcI, false);
-        }
-        stq(p.Lf, f4, s, o.Lf);
-        st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
-    }
-    if (i == 0) { // left patch: face 0
-        const size_t f3 = tileRow(T, Rf, 0, 3, lane), f4 = tileRow(T, Rf, 0, 4, lane);
-        const Q4 qfOld = ldq(p.Lf, f4, s);
-        const V3 Kold = ld3(p.K, f3, s);
-        const FaceState o = patchUpdate(p, 0, b, qfOld, CQ, CM, Kold, ld3(p.Q, f3, s), ld3(p.M, f3, s),
-                                        Wold, DW, DT, dcB, delta);
-        stq(p.Lf, f4, s, o.Lf);
-        st3(p.K, f3, s, o.K); st3(p.Q, f3, s, o.Q); st3(p.M, f3, s, o.M);
-    }
+    if (i == n - 1) updatePatchFace(p, b, 1, n, CQ, CM, dcB, delta, Wold, DW, DT);
+    else updateInternalFace(p, b, i + 1, CQ, CM, dR0, e0, dcI, Wold, WoldN, DW, DT, xWn, xTn);
+    if (i == 0) updatePatchFace(p, b, 0, n, CQ, CM, dcB, delta, Wold, DW, DT);
 }
 
 template <int SCHEME>
@@ -1453,9 +1476,6 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(co
     v[0] = forwardSweep<SCHEME>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
     blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
-#ifndef BEAM_BWD_MIN_BLOCKS
-#define BEAM_BWD_MIN_BLOCKS BEAM_MIN_BLOCKS
-#endif
 template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backward(const BeamParams p)
 {
@@ -1463,6 +1483,239 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backwa
     double v[2] = {0.0, 0.0};
     if (b < p.B) backwardSweep<SCHEME>(p, b, v[0], v[1]);
     blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------
+// SPLIT sweeps ("burn at both ends", a twisted block factorisation): TWO threads per beam.
+//   A bundle below one wave of beams cannot fill the GPU with one thread per beam, and an iteration then costs the latency
+//   of one thread walking all n cells.  The block-Thomas elimination can start from both ends at once: the left half
+//   eliminates cells 0 .. h-1 left to right exactly as forwardSweep does, the mirrored half eliminates cells n-1 .. h right to
+//   left (the same code on the neighbour-side blocks, see fwdFacePart<.., MIR>), and the two meet at the face between
+//   cells h-1 and h with
+//       x_{h-1} = bPrime_{h-1} - uPrime_{h-1} x_h ,   x_h = bPrime_h - uPrime_h x_{h-1}
+//   a 6x6 system that both halves solve (identically) at the start of the backward sweep before substituting outwards.
+//   No redundant arithmetic, half the serial length, twice the threads.  Uniform bundles only (every beam nmax cells: the
+//   mirrored half walks the rows downwards from nmax-1, and the bulk copies fetch one row for all 32 lanes); padding lanes
+//   run as dummy beams so that a warp never leaves the straight-line path.
+//   Ownership in the backward sweep: the left half updates cells 0..h-1, faces 1..h-1 and the left patch; the mirrored half
+//   updates cells h..n-1, faces h..n-1 (face c together with cell c) and the right patch.  The interface face h needs the
+//   pre-update W of cell h-1, which the left half overwrites concurrently: the mirrored half's forward sweep saves it (ifW).
+// ---------------------------------------------------------------------------
+template <int SCHEME, bool MIR>
+DEV double forwardSweepSplit(const BeamParams& p, const int b, double* __restrict__ warpSm, uint64_t* bar, uint32_t& phase)
+{
+    const size_t s = p.Bpad;
+    const int lane = threadIdx.x & 31;
+    const size_t T = (size_t)(b >> 5);
+    double* sm = warpSm + lane;
+    double res = 0.0;
+    const int n = p.nmax, hL = (n + 1) / 2;
+    const int m = MIR ? n - hL : hL; // cells of this half; the host selects the split sweeps only for n >= 2
+#define SROW(i) (MIR ? n - 1 - (i) : (i))            // cell row of local cell i
+#define SFACE(i) (MIR ? n - 1 - (i) : (i) + 1)       // the face between local cells i and i+1
+    __syncwarp();
+    if (m > 0) fwdPrefetchFaceRows<SCHEME>(p, T, warpSm, bar, SROW(0), SROW(1), SFACE(0));
+    {
+        const M3 refL = ld9(p.refL, b, s);
+        const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
+        smSt3(sm, R_DR0, dR0);
+        smSt(sm, R_DZ, p.dZ[b]);
+        smSt(sm, R_ARHO, SCHEME != BFK_STEADY ? p.ARho[b] : 0.0);
+        smSt(sm, R_N, (double)m);
+        smSt3(sm, R_CQ, ld3(p.CQ, b, s));
+        smSt3(sm, R_CM, ld3(p.CM, b, s));
+        smSt3(sm, R_CI, SCHEME != BFK_STEADY ? ld3(p.CI, b, s) : v3(0, 0, 0));
+#pragma unroll
+        for (int r = 0; r < 6; r++) smSt(sm, R_LB + r, 0.0);
+    }
+    V3 Wi = ld3(p.W, tileRow(T, p.nmax, SROW(0), 3, lane), TS);
+    {
+        double D36[36], s6[6];
+#pragma unroll
+        for (int k = 0; k < 36; k++) D36[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s6[k] = 0.0;
+        patchClosure(p, MIR ? 1 : 0, b, Wi, D36, s6);
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            smSt(sm, R_SC + r, s6[r]);
+#pragma unroll
+            for (int c = 0; c < 6; c++) smSt(sm, R_DC + 6 * r + c, D36[6 * r + c]);
+        }
+    }
+    for (int i = 0; i < m; i++) { // every cell of a half has an internal face towards the next one (the last: the interface)
+        mbarWait(bar, phase & 1u);
+        const FaceIn in = loadFaceIn(sm);
+        if (SCHEME == BFK_STEADY) fenceProxyAsync();
+        __syncwarp();
+        if (SCHEME != BFK_STEADY) fwdPrefetchCell<SCHEME>(p, T, sm, SROW(i));
+        else if (i + 1 < m) fwdPrefetchFaceRows<SCHEME>(p, T, warpSm, bar, SROW(i + 1), SROW(i + 2), SFACE(i + 1));
+        if (MIR && i == m - 1) // pre-update W of cell h-1, for the interface face in the backward sweep
+            st3(p.ifW, b, s, in.Wn);
+        double src[6], Dc[6][6];
+        const double dz = smLd(sm, R_DZ);
+        fwdFacePart<false, MIR>(p, b, sm, rcpFast(dz), 0.5 * dz, in, Dc, src, Wi);
+        CellIn cell;
+        if (SCHEME != BFK_STEADY) {
+            cpAsyncWaitAll();
+            cell = loadCellInSm<SCHEME>(sm, p.first != 0);
+            fenceProxyAsync();
+            __syncwarp();
+            if (i + 1 < m) fwdPrefetchFaceRows<SCHEME>(p, T, warpSm, bar, SROW(i + 1), SROW(i + 2), SFACE(i + 1));
+        } else
+            cell = loadCellIn<SCHEME>(p, b, SROW(i));
+        phase++;
+        addLoadsAndInertia<SCHEME>(p, b, SROW(i), dz, smLd(sm, R_ARHO), smLd3(sm, R_CI), cell, Dc, src);
+#pragma unroll
+        for (int r = 0; r < 6; r++) res += src[r] * src[r];
+        fwdEliminate<false>(p, b, sm, SROW(i), Dc, src);
+    }
+#undef SROW
+#undef SFACE
+    return b < p.B ? res : 0.0;
+}
+
+// x_{h-1} and x_h of a split beam from the last rows of its two halves (see above).  Pivoted 6x6 solve.
+__device__ __noinline__ void splitInterface(const BeamParams& p, const size_t T, const int lane, const int h, double* __restrict__ xL,
+                                            double* __restrict__ xR)
+{
+    const int Rc = p.nmax;
+    const double* uL = p.uP + tileRow(T, Rc, h - 1, 36, lane);
+    const double* uR = p.uP + tileRow(T, Rc, h, 36, lane);
+    const double* bL = p.bP + tileRow(T, Rc, h - 1, 6, lane);
+    const double* bR = p.bP + tileRow(T, Rc, h, 6, lane);
+    double UL[6][6], UR[6][6], A[6][6], rhs[6][1], br[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        br[r] = __ldcg(bR + (size_t)r * TS);
+#pragma unroll
+        for (int c = 0; c < 6; c++) { UL[r][c] = __ldcg(uL + (size_t)(6 * r + c) * TS); UR[r][c] = __ldcg(uR + (size_t)(6 * r + c) * TS); }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double acc = __ldcg(bL + (size_t)r * TS);
+#pragma unroll
+        for (int c = 0; c < 6; c++) acc = fma(-UL[r][c], br[c], acc);
+        rhs[r][0] = acc; // bPrime_{h-1} - uPrime_{h-1} bPrime_h
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            double a = r == c ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) a = fma(-UL[r][k], UR[k][c], a);
+            A[r][c] = a; // I - uPrime_{h-1} uPrime_h
+        }
+    }
+    solve6<1>(A, rhs);
+#pragma unroll
+    for (int r = 0; r < 6; r++) xL[r] = rhs[r][0];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double acc = br[r];
+#pragma unroll
+        for (int c = 0; c < 6; c++) acc = fma(-UR[r][c], xL[c], acc);
+        xR[r] = acc;
+    }
+}
+
+template <int SCHEME, bool MIR>
+DEV void backwardSweepSplit(const BeamParams& p, const int b, double& dx2, double& x2)
+{
+    const size_t s = TS;
+    const size_t T = (size_t)(b >> 5);
+    const int lane = b & 31, Rc = p.nmax, Rf = p.nmax + 1;
+    const int n = p.nmax, hL = (n + 1) / 2;
+    const double dZ = p.dZ[b];
+    const double dcI = 1.0 / dZ, dcB = 2.0 / dZ;
+    const double delta = 1.0 / dcB;
+    const V3 CQ = ld3(p.CQ, b, p.Bpad), CM = ld3(p.CM, b, p.Bpad);
+    V3 dR0, e0;
+    {
+        const M3 refL = ld9(p.refL, b, p.Bpad);
+        dR0 = v3(refL.a[0], refL.a[3], refL.a[6]);
+        e0 = mulT(refL, dR0);
+    }
+    double xL[6], xR[6];
+    splitInterface(p, T, lane, hL, xL, xR);
+    // xo = x of the cell visited before this one (towards the interface), Wo = its pre-update W
+    V3 xWo = MIR ? v3(xL[0], xL[1], xL[2]) : v3(xR[0], xR[1], xR[2]);
+    V3 xTo = MIR ? v3(xL[3], xL[4], xL[5]) : v3(xR[3], xR[4], xR[5]);
+    V3 Wo = MIR ? ld3(p.ifW, b, p.Bpad) : v3(0, 0, 0);
+    const int m = MIR ? n - hL : hL;
+    for (int k = 0; k < m; k++) {
+        const int i = MIR ? hL + k : hL - 1 - k; // the mirrored half walks outwards to the right, the left half to the left
+        {   // prefetch what the next step reads
+            const int ic = MIR ? i + BEAM_PF_DIST : i - BEAM_PF_DIST;
+            if (ic >= 0 && ic < n) {
+                const int jf = MIR ? ic : ic + 1; // the face that cell updates
+                const size_t m3 = tileRow(T, Rc, ic, 3, lane), g3 = tileRow(T, Rf, jf, 3, lane);
+                pfRows<36>(p.uP, tileRow(T, Rc, ic, 36, lane), s);
+                pfRows<6>(p.bP, tileRow(T, Rc, ic, 6, lane), s);
+                pfRows<3>(p.W, m3, s); pfRows<3>(p.Th, m3, s);
+                pfRows<4>(p.Lam, tileRow(T, Rc, ic, 4, lane), s);
+                if (SCHEME == BFK_NEWMARK) {
+                    pfRows<3>(p.Ac, m3, s); pfRows<3>(p.dOm, m3, s);
+                    if (p.first) { pfRows<3>(p.U, m3, s); pfRows<3>(p.Om, m3, s); }
+                }
+                pfRows<4>(p.Lf, tileRow(T, Rf, jf, 4, lane), s);
+                pfRows<3>(p.K, g3, s);
+                pfRows<3>(p.Q, g3, s); pfRows<3>(p.M, g3, s);
+            }
+        }
+        double x[6];
+        if (k == 0) {
+#pragma unroll
+            for (int r = 0; r < 6; r++) x[r] = MIR ? xR[r] : xL[r];
+        } else { // x_i = bPrime_i - uPrime_i & x_(previous cell of the walk)
+            const size_t u0 = tileRow(T, Rc, i, 36, lane), b0 = tileRow(T, Rc, i, 6, lane);
+            const double xn[6] = {xWo.x, xWo.y, xWo.z, xTo.x, xTo.y, xTo.z};
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc += __ldcg(p.uP + u0 + (size_t)(6 * r + c) * s) * xn[c];
+                x[r] = __ldcg(p.bP + b0 + (size_t)r * s) - acc;
+            }
+        }
+        const V3 DW = v3(x[0], x[1], x[2]), DT = v3(x[3], x[4], x[5]);
+#pragma unroll
+        for (int r = 0; r < 6; r++) dx2 += x[r] * x[r];
+        V3 Wold;
+        updateCell<SCHEME>(p, T, lane, i, DW, DT, Wold, x2);
+        if (MIR) { // face i: owner = cell i-1 (the previous cell of the walk), neighbour = this cell
+            updateInternalFace(p, b, i, CQ, CM, dR0, e0, dcI, Wo, Wold, xWo, xTo, DW, DT);
+            if (i == n - 1) updatePatchFace(p, b, 1, n, CQ, CM, dcB, delta, Wold, DW, DT);
+        } else {   // face i+1: owner = this cell, neighbour = the previous cell of the walk; the interface face is the other half's
+            if (k > 0) updateInternalFace(p, b, i + 1, CQ, CM, dR0, e0, dcI, Wold, Wo, DW, DT, xWo, xTo);
+            if (i == 0) updatePatchFace(p, b, 0, n, CQ, CM, dcB, delta, Wold, DW, DT);
+        }
+        xWo = DW; xTo = DT; Wo = Wold;
+    }
+}
+
+// grid (ceil(B / BEAM_THREADS), 2): blockIdx.y = 0 the left halves, 1 the mirrored halves
+template <int SCHEME>
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward_split(const BeamParams p)
+{
+    extern __shared__ __align__(128) unsigned char beam_smem[];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5;
+    uint32_t phase = warpBarrierSetup(beam_smem);
+    double v[1] = {0.0};
+    if ((b & ~31) < p.Bpad) { // a warp wholly past the padded bundle has no tile in memory (lanes B..Bpad-1 run as dummy beams)
+        if (blockIdx.y) v[0] = forwardSweepSplit<SCHEME, true>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
+        else v[0] = forwardSweepSplit<SCHEME, false>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
+    }
+    blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.y * gridDim.x + blockIdx.x);
+}
+template <int SCHEME>
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backward_split(const BeamParams p)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[2] = {0.0, 0.0};
+    if (b < p.B) {
+        if (blockIdx.y) backwardSweepSplit<SCHEME, true>(p, b, v[0], v[1]);
+        else backwardSweepSplit<SCHEME, false>(p, b, v[0], v[1]);
+    }
+    blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.y * gridDim.x + blockIdx.x);
 }
 
 // Source contribution of the point forces for every cell of every beam (one thread per beam, its cells in turn).

@@ -45,6 +45,8 @@ struct bf_ctx {
     int Bpad, nmax, grid;
     // bundles below one wave of beams: group-cooperative kernels (beam_coop.cuh), selectable per sweep
     int coopFwd, coopBwd, coopGrid;
+    int split; // two threads per beam (beam_forward_split / beam_backward_split): uniform bundles between the two other families
+    double* d_ifW;
     double* d_X; // coopBwd: the solution increments, tiled [tile][nmax][6][32] (beam_backsub -> beam_update_*)
     int partialStride; // leading dimension of d_partial: the largest block count of any kernel family
     std::vector<int32_t> nSeg, hostWType; // hostWType: [2][B]
@@ -127,7 +129,7 @@ extern "C" int64_t bf_num_cells(const bf_ctx* c) { return c->N; }
 extern "C" int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
 extern "C" int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
 extern "C" int64_t bf_launch_count(const bf_ctx* c) { return c->launches; }
-extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return c->longMode ? BF_FAMILY_CELL : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
+extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return c->longMode ? BF_FAMILY_CELL : c->split ? BF_FAMILY_SPLIT : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
 
 extern "C" int bf_host_alloc(void** p, int64_t bytes)
 {
@@ -404,6 +406,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     CREATE_CUDA(cudaFuncSetAttribute(KERNEL<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES))
     OPT_IN_SMEM(beam_newton);
     OPT_IN_SMEM(beam_forward);
+    OPT_IN_SMEM(beam_forward_split);
     CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_STEADY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
@@ -448,7 +451,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
 
     // ---- per-beam + end arrays (one pool)
     {
-        const size_t bytes = 256 * 40 + sizeof(double) * bp * (1 + 3 + 3 + 1 + 3 + 3 + 9 + 2 * (3 + 3 + 9 + 3 + 3 + 3 + 3 + 3 + 3 + 3 + 3 + 1 + 3)) +
+        const size_t bytes = 256 * 44 + sizeof(double) * bp * (3 + 1 + 3 + 3 + 1 + 3 + 3 + 9 + 2 * (3 + 3 + 9 + 3 + 3 + 3 + 3 + 3 + 3 + 3 + 3 + 1 + 3)) +
                              sizeof(int32_t) * bp * 5 + sizeof(int64_t) * 2 * (size_t)(B + 1);
         char* cur;
         if (devAlloc(c, (void**)&cur, bytes)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
@@ -459,7 +462,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         c->d_DWb = carve<double>(cur, 6 * bp); c->d_DThb = carve<double>(cur, 6 * bp); c->d_force = carve<double>(cur, 6 * bp);
         c->d_wPresc = carve<double>(cur, 6 * bp); c->d_thPresc = carve<double>(cur, 6 * bp);
         c->d_follower = carve<double>(cur, 6 * bp); c->d_offset = carve<double>(cur, 6 * bp);
-        c->d_moment = carve<double>(cur, 6 * bp); c->d_springK = carve<double>(cur, 2 * bp);
+        c->d_moment = carve<double>(cur, 6 * bp); c->d_springK = carve<double>(cur, 2 * bp); c->d_ifW = carve<double>(cur, 3 * bp);
         c->d_springDir = carve<double>(cur, 6 * bp);
         c->d_nSeg = carve<int32_t>(cur, bp); c->d_wType = carve<int32_t>(cur, 2 * bp); c->d_thType = carve<int32_t>(cur, 2 * bp);
         c->d_cellStart = carve<int64_t>(cur, (size_t)B + 1); c->d_faceStart = carve<int64_t>(cur, (size_t)B + 1);
@@ -489,7 +492,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     {
         char* cur;
         c->coopGrid = (Bpad + WS_BEAMS - 1) / WS_BEAMS;
-        c->partialStride = c->grid;
+        c->partialStride = 2 * c->grid; // the split sweeps launch two blocks per 128 beams
         if ((int)((c->N + 127) / 128) > c->partialStride) c->partialStride = (int)((c->N + 127) / 128);
         if (c->coopGrid > c->partialStride) c->partialStride = c->coopGrid;
         const int cellGrid = (int)(((size_t)Bpad * (size_t)nmax + 127) / 128); // beam_update_*: one thread per (padded) cell
@@ -511,6 +514,17 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
                 else if (!strcmp(e, "bwd")) { c->coopFwd = 0; c->coopBwd = 1; }
                 else c->coopFwd = c->coopBwd = atoi(e) ? 1 : 0;
             }
+        }
+        // between the two: two threads per beam (uniform bundles).  BEAMGPU_SPLIT = 1 / 0 forces it on / off.
+        {
+            int nSm = 148;
+            cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, c->device);
+            long below = (long)nSm * 8 * 32 * 5 / 8;
+            if (const char* e = getenv("BEAMGPU_SPLIT_BELOW")) below = atol(e);
+            c->split = (!c->coopFwd && !c->coopBwd && B < below) ? 1 : 0;
+            if (const char* e = getenv("BEAMGPU_SPLIT")) c->split = atoi(e) ? 1 : 0;
+            if (!c->uniformN || nmax < 2) c->split = 0;
+            if (c->split) c->coopFwd = c->coopBwd = 0;
         }
         c->d_X = nullptr;
         if (c->coopBwd && devAlloc(c, (void**)&c->d_X, sizeof(double) * 6 * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
@@ -1107,7 +1121,7 @@ static BeamParams makeParams(bf_ctx* c)
     p.Lf = c->d_Lf; p.K = c->d_K; p.Q = c->d_Q; p.M = c->d_M;
     p.Wb = c->d_Wb; p.Thb = c->d_Thb; p.Lamb = c->d_Lamb; p.DWb = c->d_DWb; p.DThb = c->d_DThb; p.force = c->d_force;
     p.wPresc = c->d_wPresc; p.thPresc = c->d_thPresc; p.follower = c->d_follower; p.offset = c->d_offset;
-    p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir;
+    p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir; p.ifW = c->d_ifW;
     p.uP = c->d_uP; p.bP = c->d_bP; p.partial = c->d_partial;
     p.nTiles = c->partialStride;
     return p;
@@ -1174,6 +1188,13 @@ static int launchIteration(bf_ctx* c)
         else if (c->scheme == BF_SCHEME_EULER) long_update_cells<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
         else long_update_cells<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
         c->launches += 2;
+    } else if (c->split) { // two threads per beam, the halves meet in the middle
+        const dim3 g2((unsigned)c->grid, 2);
+        LAUNCH_SCHEME(beam_forward_split, g2, SMEM_BYTES, p);
+        if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
+        LAUNCH_SCHEME(beam_backward_split, g2, 0, p);
+        c->launches += 2;
+        nF = nB = 2 * c->grid;
     } else if (c->splitKernels || c->coopFwd || c->coopBwd) { // product path: one launch per sweep
         if (c->coopFwd) LAUNCH_SCHEME_T(beam_forward_ws, c->coopGrid, WS_THREADS, WS_SMEM_BYTES, p);
         else LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);

@@ -324,14 +324,16 @@ int bf_beam_energy(bf_ctx* ctx, double* out);
 int64_t bf_launch_count(const bf_ctx* ctx);
 /* Which kernel family bf_create selected for this bundle (diagnostic; the results do
  * not depend on it beyond rounding): BF_FAMILY_PER_BEAM one thread per beam (bundles of
- * at least about one wave of beams), BF_FAMILY_GROUP 4 lanes per beam (smaller bundles),
- * BF_FAMILY_CELL one thread per cell with block cyclic reduction (few long beams),
+ * at least about one wave of beams), BF_FAMILY_GROUP assembler + eliminator warps (small bundles),
+ * BF_FAMILY_SPLIT two threads per beam that eliminate from both ends and meet in the
+ * middle, BF_FAMILY_CELL one thread per cell with block cyclic reduction (few long beams),
  * BF_FAMILY_CPU for an implementation without kernels (the test oracle).  Mixed pairs
  * forced through BEAMGPU_COOP=fwd|bwd report the family of the forward sweep. */
 #define BF_FAMILY_CPU (-1)
 #define BF_FAMILY_PER_BEAM 0
 #define BF_FAMILY_GROUP 1
 #define BF_FAMILY_CELL 2
+#define BF_FAMILY_SPLIT 3
 int32_t bf_kernel_family(const bf_ctx* ctx);
 int bf_kernel_time_ms(bf_ctx* ctx, int32_t reset, double* fwd_ms, double* bwd_ms,
                       int64_t* iterations);
