@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(WS_THREADS) beam_forward_ws(const BeamParams p
 // X: tiled like a 6-component cell array, [tile][nmax][6][32].
 // ---------------------------------------------------------------------------------------------------------------------
 #define BS_THREADS 32
-#define BS_RING 4
+#define BS_RING 8
 #define BS_SMEM_BYTES ((BS_THREADS / 32) * BS_RING * 42 * 32 * sizeof(double))
 DEV void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

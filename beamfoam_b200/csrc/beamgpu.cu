@@ -500,31 +500,30 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->partialStride + 8) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
         c->d_partial = carve<double>(cur, 3 * (size_t)c->partialStride); c->d_sums = carve<double>(cur, 8);
-        // One thread per beam fills the GPU from one wave of beams (SMs x 8 warps x 32 lanes = 37,888 on a B200); below
-        // BEAMGPU_COOP_BELOW beams (default: measured crossover) a beam gets a group of 4 lanes.
-        // BEAMGPU_COOP = 1 / 0 / fwd / bwd forces the cooperative kernels on / off / for one sweep only (tests).
+        // Kernel family by bundle size (measured on B200, 200-cell Newmark beams, ms per Newton iteration):
+        //      beams      4096   8192   16384  32768  65536
+        //      per beam   1.17   1.18   1.20   1.84   3.69     one thread per beam: flat below one wave (37,888 beams)
+        //      split      0.61   0.62   1.01   1.93   3.51     two threads per beam, half the serial length
+        //      group      0.60   0.96   1.87   3.48   6.72     assembler + eliminator warps: lowest latency, half the throughput
+        // With w = B/32 warps and S = 8 warps x SMs resident, one thread per beam costs ceil(w/S) sweep rounds and the split
+        // sweeps ceil(2w/S)/2: split when that is fewer, or equal with more than one round (the shorter tasks fill the last
+        // round better).  The split sweeps need a uniform bundle; small ragged bundles take the group kernels.
+        // BEAMGPU_SPLIT = 1 / 0 and BEAMGPU_COOP = 1 / 0 / fwd / bwd force a family on / off (tests, scripts/gpu_sizes.py).
         {
             int nSm = 148;
             cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, c->device);
-            long below = (long)nSm * 8 * 32 * 5 / 8;
-            if (const char* e = getenv("BEAMGPU_COOP_BELOW")) below = atol(e);
-            c->coopFwd = c->coopBwd = B < below ? 1 : 0;
+            const long S = 8L * nSm, w = (B + 31) / 32;
+            const long r1 = 2 * ((w + S - 1) / S), r2 = (2 * w + S - 1) / S; // in half rounds
+            c->split = (r2 < r1 || (r2 == r1 && w > S)) ? 1 : 0;
+            if (const char* e = getenv("BEAMGPU_SPLIT")) c->split = atoi(e) ? 1 : 0;
+            if (!c->uniformN || nmax < 2) c->split = 0;
+            c->coopFwd = c->coopBwd = (!c->split && B < 6144) ? 1 : 0;
             if (const char* e = getenv("BEAMGPU_COOP")) {
                 if (!strcmp(e, "fwd")) { c->coopFwd = 1; c->coopBwd = 0; }
                 else if (!strcmp(e, "bwd")) { c->coopFwd = 0; c->coopBwd = 1; }
                 else c->coopFwd = c->coopBwd = atoi(e) ? 1 : 0;
+                if (c->coopFwd || c->coopBwd) c->split = 0;
             }
-        }
-        // between the two: two threads per beam (uniform bundles).  BEAMGPU_SPLIT = 1 / 0 forces it on / off.
-        {
-            int nSm = 148;
-            cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, c->device);
-            long below = (long)nSm * 8 * 32 * 5 / 8;
-            if (const char* e = getenv("BEAMGPU_SPLIT_BELOW")) below = atol(e);
-            c->split = (!c->coopFwd && !c->coopBwd && B < below) ? 1 : 0;
-            if (const char* e = getenv("BEAMGPU_SPLIT")) c->split = atoi(e) ? 1 : 0;
-            if (!c->uniformN || nmax < 2) c->split = 0;
-            if (c->split) c->coopFwd = c->coopBwd = 0;
         }
         c->d_X = nullptr;
         if (c->coopBwd && devAlloc(c, (void**)&c->d_X, sizeof(double) * 6 * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }

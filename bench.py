@@ -50,8 +50,11 @@ METRIC = "beam-cell Newton updates/s"
 UNIT = "updates/s"
 BYTES_PER_UPDATE = {"Newmark": 760.0, "steadyState": 552.0, "Euler": 760.0}  # 95 / 69 doubles
 HBM_FALLBACK_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
-FAMILY = {0: "one thread per beam (beam_forward / beam_backward)", 1: "4 lanes per beam (beam_forward_coop / beam_backward_coop)",
-          2: "one thread per cell, block cyclic reduction (long_*)", -1: "cpu"}
+FAMILY = {0: "one thread per beam (beam_forward / beam_backward)",
+          1: "assembler + eliminator warps (beam_forward_ws), serial back-substitution + one thread per cell (beam_backsub, beam_update_*)",
+          2: "one thread per cell, block cyclic reduction (long_*)",
+          3: "two threads per beam meeting in the middle (beam_forward_split / beam_backward_split)", -1: "cpu"}
+FAMILY_ENV = {0: ("0", "0"), 1: ("1", "0"), 3: ("0", "1")}  # BEAMGPU_COOP, BEAMGPU_SPLIT that force a family
 CONFIGS = {
     "bundle65536": dict(beams=65536, cells=200, baseline="configs[3]"),
     "bundle4096": dict(beams=4096, cells=200, baseline="configs[2]"),
@@ -448,14 +451,15 @@ def verify(args, D: Dist, lib, case, total, main: Bundle, iters, tips):
     out = {}
     # (1) a sample of this rank's beams as a stand-alone bundle, same kernel family, same per-step iteration counts
     S = min(256, hi - lo)
-    saved = os.environ.get("BEAMGPU_COOP")
-    if main.family in (0, 1):
-        os.environ["BEAMGPU_COOP"] = str(main.family)
+    saved = {k: os.environ.get(k) for k in ("BEAMGPU_COOP", "BEAMGPU_SPLIT")}
+    if main.family in FAMILY_ENV:
+        os.environ["BEAMGPU_COOP"], os.environ["BEAMGPU_SPLIT"] = FAMILY_ENV[main.family]
     sample = Bundle(args, D, lib, case, total, beamRange=(lo, lo + S), comm=False)
-    if saved is None:
-        os.environ.pop("BEAMGPU_COOP", None)
-    else:
-        os.environ["BEAMGPU_COOP"] = saved
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
     assert sample.family == main.family, (sample.family, main.family)
     for n in iters:
         sample.step_fixed(n)
@@ -543,9 +547,9 @@ def run_ours(args):
     kern_ms = fms + bms
     peak, peak_src = hbm_peak()
     achieved = bpu * nCellsLocal / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-    names = {0: ("beam_forward", "beam_backward"), 1: ("beam_forward_coop", "beam_backward_coop"),
-             2: ("long_assemble + long_pcr_*", "long_update_*")}[main.family]
-    tj = load_traffic({0: "per_beam", 1: "group", 2: "cell"}[main.family])
+    names = {0: ("beam_forward", "beam_backward"), 1: ("beam_forward_ws", "beam_backsub + beam_update_faces + beam_update_cells"),
+             2: ("long_assemble + long_pcr_*", "long_update_*"), 3: ("beam_forward_split", "beam_backward_split")}[main.family]
+    tj = load_traffic({0: "per_beam", 1: "group", 2: "cell", 3: "split"}[main.family])
     traffic, per_kernel, fp64 = None, None, None
     if tj:
         scale = nCellsLocal / float(tj["cells_per_launch"])
