@@ -370,6 +370,7 @@ template <int SCHEME>
 __global__ void __launch_bounds__(WS_THREADS) beam_forward_ws(const BeamParams p)
 {
     extern __shared__ __align__(16) unsigned char ws_smem[];
+    if (convLeave(p.cv, false)) return;
     double* sm = (double*)ws_smem;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = lane & 15, j = lane >> 4; // beam of the block; cell slot (assembler) / column role (eliminator)
@@ -452,6 +453,7 @@ DEV void cpAsyncWaitGroup() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : 
 __global__ void __launch_bounds__(BS_THREADS) beam_backsub(const BeamParams p, double* __restrict__ X)
 {
     extern __shared__ __align__(16) unsigned char bs_smem[];
+    if (convLeave(p.cv, true)) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x * BS_THREADS + threadIdx.x;
     const size_t T = (size_t)(b >> 5);
@@ -521,6 +523,7 @@ DEV void ldX(const double* __restrict__ X, size_t T, int Rc, int i, int lane, V3
 // Faces first: they read the neighbour cell's pre-update W ...
 __global__ void __launch_bounds__(128) beam_update_faces(const BeamParams p, const double* __restrict__ X)
 {
+    if (convLeave(p.cv, true)) return;
     int b, i;
     if (!cellOfThread(p, b, i)) return;
     const size_t T = (size_t)(b >> 5), sb = p.Bpad;
@@ -541,6 +544,7 @@ __global__ void __launch_bounds__(128) beam_update_faces(const BeamParams p, con
 template <int SCHEME>
 __global__ void __launch_bounds__(128) beam_update_cells(const BeamParams p, const double* __restrict__ X)
 {
+    if (convLeave(p.cv, true)) return;
     int b, i;
     double v[2] = {0.0, 0.0};
     if (cellOfThread(p, b, i)) {

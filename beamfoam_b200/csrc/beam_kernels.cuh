@@ -38,7 +38,26 @@
 #define BFK_NEWMARK 1
 #define BFK_EULER 2
 
+// The convergence test of the Newton loop (checkConvergence, Evolve.C:926-1026) evaluated ON THE DEVICE, so that
+// bf_evolve can enqueue iterations ahead of the test: the sweeps of iteration k+1 start with a look at the global norms of
+// iteration k and leave at once when the loop ended there.  Every rank owns an exchange buffer
+// [2 banks][CONV_MAXK iterations][nRanks][4 doubles: sum source^2, sum dx^2, sum x^2, tag]; the 1-block reduction
+// kernel of iteration k writes this rank's record into the buffer of EVERY rank (peer memory over NVLink, CUDA IPC) --
+// a one-sided 32-byte store per peer instead of a collective -- and whoever needs the global sums adds the nRanks
+// records in rank order (bit-identical on every rank).  tag = 2 * epoch of the evolve() call (+1: this rank had seen the
+// loop end before iteration k: the record carries no sums).
+#define CONV_MAXK 4096
+#define CONV_MAX_RANKS 16
+struct ConvCtl {
+    const double* xbuf; // this rank's bank of the exchange buffer; null: the host decides (bf_newton_iteration, reducer callback)
+    int nRanks, iter;   // iter: the Newton iteration the launch belongs to
+    double tag;
+    double absTol, resTol, solTol, divTol;
+    int nCorr;
+};
+
 struct BeamParams {
+    ConvCtl cv;
     int B;        // beams in this context
     int Bpad;     // padded beam count (leading dimension)
     int nmax;     // max cells per beam
@@ -306,6 +325,67 @@ DEV void bcClosure(double (&D)[6][6], double (&b)[6], const FaceCoef& f, const E
         }
     }
     subV(b, 3, f.eMQ); // :1178-1187
+}
+
+DEV double ldAcquireSys(const double* p)
+{
+    double v;
+    asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+DEV void stReleaseSys(double* p, double v) { asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+// Global sums of iteration k, added in rank order.  wait: spin until every rank's record is there.  Returns -1: a record
+// is missing (only without wait), 1: a rank had seen the loop end before iteration k, 0: s holds the sums.
+DEV int convSums(const ConvCtl& c, const int k, const bool wait, double (&s)[3])
+{
+    s[0] = s[1] = s[2] = 0.0;
+    int ended = 0;
+    for (int r = 0; r < c.nRanks; r++) {
+        const double* rec = c.xbuf + ((size_t)k * c.nRanks + r) * 4;
+        double tag;
+        for (;;) {
+            tag = ldAcquireSys(rec + 3);
+            if (tag == c.tag || tag == c.tag + 1.0) break;
+            if (!wait) return -1;
+            __nanosleep(100);
+        }
+        if (tag != c.tag) ended = 1;
+        s[0] += ldAcquireSys(rec); s[1] += ldAcquireSys(rec + 1); s[2] += ldAcquireSys(rec + 2);
+    }
+    return ended;
+}
+// The five exit rules of checkConvergence (Evolve.C:926-1026) on the squared global sums: does the loop end with iteration k?
+DEV bool convRules(const ConvCtl& c, const int k, const double (&s)[3], const double initSq)
+{
+    if (!(s[0] == s[0]) || !(s[1] == s[1]) || !(s[2] == s[2])) return true; // non-finite: a singular block
+    const double cur = sqrt(s[0]), dx = sqrt(s[1]), xn = sqrt(s[2]);
+    const double init = k == 0 ? cur : sqrt(initSq);
+    if (cur <= c.absTol) return true;
+    if (cur <= c.resTol * init) return true;
+    if (dx <= c.solTol * xn) return true;
+    if (cur >= c.divTol * init && k > 1) return true;
+    return k >= c.nCorr;
+}
+// 1: the loop ends with iteration k or had ended before, 0: it goes on, -1: not known yet (only without wait)
+DEV int convDecide(const ConvCtl& c, const int k, const bool wait)
+{
+    double s[3], s0[3] = {0, 0, 0};
+    const int m = convSums(c, k, wait, s);
+    if (m) return m;
+    if (k > 0) convSums(c, 0, true, s0); // the initial residual; its records arrived long ago
+    return convRules(c, k, s, s0[0]) ? 1 : 0;
+}
+// Prologue of every sweep kernel: true = leave, the loop ended with an earlier iteration.  The forward sweeps do not wait
+// (if the records of the previous iteration are not all there yet they run speculatively: they write scratch and partial
+// sums only, and the time they take is time this GPU would have waited for the slowest one); the backward sweeps, which
+// change the state, wait.
+DEV bool convLeave(const ConvCtl& c, const bool wait)
+{
+    if (!c.xbuf || c.iter == 0) return false;
+    __shared__ int sLeave;
+    if (threadIdx.x == 0) sLeave = convDecide(c, c.iter - 1, wait) == 1;
+    __syncthreads();
+    return sLeave != 0;
 }
 
 // Block reduction of up to 3 values; thread 0 writes partial[(slot0 + k)*nTiles + tile].
@@ -1470,6 +1550,7 @@ template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(const BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
+    if (convLeave(p.cv, false)) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5;
     uint32_t phase = warpBarrierSetup(beam_smem);
     double v[1] = {0.0};
@@ -1479,6 +1560,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(co
 template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backward(const BeamParams p)
 {
+    if (convLeave(p.cv, true)) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
     if (b < p.B) backwardSweep<SCHEME>(p, b, v[0], v[1]);
@@ -1697,6 +1779,7 @@ template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward_split(const BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
+    if (convLeave(p.cv, false)) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5;
     uint32_t phase = warpBarrierSetup(beam_smem);
     double v[1] = {0.0};
@@ -1709,6 +1792,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward_sp
 template <int SCHEME>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backward_split(const BeamParams p)
 {
+    if (convLeave(p.cv, true)) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
     if (b < p.B) {
@@ -1801,6 +1885,52 @@ __global__ void beam_reduce_partials(const double* __restrict__ partial, int str
         out[threadIdx.x] = sm[threadIdx.x][0];
         if (outHost) outHost[threadIdx.x] = sm[threadIdx.x][0]; // mapped pinned host memory
     }
+}
+struct PeerTable {
+    double* bank[CONV_MAX_RANKS]; // the current bank of every rank's exchange buffer (own included)
+};
+// The same reduction, then this rank's record of iteration cv.iter into every rank's buffer.
+__global__ void beam_reduce_exchange(const double* __restrict__ partial, int stride, int nF, int nB, const ConvCtl cv,
+                                     const PeerTable peers, const int rank)
+{
+    __shared__ double sm[3][256];
+    __shared__ int ended;
+    for (int k = 0; k < 3; k++) {
+        double acc = 0.0;
+        const int nBlocks = k == 0 ? nF : nB;
+        for (int i = threadIdx.x; i < nBlocks; i += blockDim.x) acc += partial[(size_t)k * stride + i];
+        sm[k][threadIdx.x] = acc;
+    }
+    if (threadIdx.x == 0) ended = cv.iter > 0 && convDecide(cv, cv.iter - 1, true) == 1; // the sweeps of this iteration did not run
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+            for (int k = 0; k < 3; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < cv.nRanks) {
+        double* rec = peers.bank[threadIdx.x] + ((size_t)cv.iter * cv.nRanks + rank) * 4;
+        rec[0] = sm[0][0]; rec[1] = sm[1][0]; rec[2] = sm[2][0];
+        __threadfence_system();
+        stReleaseSys(rec + 3, cv.tag + (ended ? 1.0 : 0.0));
+    }
+}
+// Global sums and verdict of iterations k0 .. k1-1 into mapped host memory, [k - k0][4]: sums, then 1 = the loop ends with
+// this iteration, 2 = it had ended before, 0 = it goes on.  Launched after the last enqueued iteration of a chunk.
+__global__ void beam_publish_chunk(const ConvCtl cv, const int k0, const int k1, double* __restrict__ outHost)
+{
+    if (threadIdx.x != 0) return;
+    double s0[3] = {0, 0, 0};
+    if (k0 > 0) convSums(cv, 0, true, s0);
+    for (int k = k0; k < k1; k++) {
+        double s[3];
+        const int ended = convSums(cv, k, true, s);
+        if (k == 0) { s0[0] = s[0]; }
+        double* o = outHost + 4 * (k - k0);
+        o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+        o[3] = ended ? 2.0 : convRules(cv, k, s, s0[0]) ? 1.0 : 0.0;
+    }
+    __threadfence_system();
 }
 __global__ void beam_publish_sums(const double* __restrict__ in, double* __restrict__ outHost)
 {

@@ -23,6 +23,7 @@
 
 #define BF_GREAT 1e15
 #define THREADS BEAM_THREADS
+#define PIPE_CHUNK_MAX 16
 
 static char g_create_err[512] = "";
 
@@ -93,6 +94,16 @@ struct bf_ctx {
     // NCCL
     NcclApi nccl;
     void* comm;
+    // pipelined Newton loop (device-side convergence test, one-sided exchange of the norm sums; beam_kernels.cuh ConvCtl)
+    double* d_xbuf;            // [2 banks][CONV_MAXK][xRanks][4], cudaMalloc (its IPC handle is exported to the peers)
+    double* peerXbuf[CONV_MAX_RANKS]; // every rank's buffer as mapped into this process (own: d_xbuf)
+    int xRanks, xRank;
+    long long epoch;
+    int lastIters;             // Newton iterations of the previous step: how far ahead the next one is enqueued
+    double* h_res;             // pinned + mapped: verdicts of a chunk of iterations, [PIPE_CHUNK_MAX][4]
+    double* d_hres;
+    ConvCtl cvNow;             // filled by bf_evolve for launchIteration; xbuf == nullptr: the host decides
+    cudaEvent_t evIter[16][3]; // per enqueued iteration of a chunk: start, between the sweeps, end (timing)
     // instrumentation
     int64_t launches;
     int timing, splitKernels;
@@ -335,6 +346,11 @@ extern "C" int bf_destroy(bf_ctx* c)
     if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
     for (int i = 0; i < c->nPools; i++) cudaFree(c->pools[i]);
     if (c->h_sums) cudaFreeHost(c->h_sums);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    for (int r = 0; r < c->xRanks; r++)
+        if (r != c->xRank && c->peerXbuf[r]) cudaIpcCloseMemHandle(c->peerXbuf[r]);
+    if (c->d_xbuf) cudaFree(c->d_xbuf);
+    for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) if (c->evIter[i][k]) cudaEventDestroy(c->evIter[i][k]);
     for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->evRegion[i]) cudaEventDestroy(c->evRegion[i]);
     if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
@@ -385,6 +401,10 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     if (const char* e = getenv("BEAMGPU_FUSED_KERNEL")) c->splitKernels = atoi(e) ? 0 : 1;
     if (const char* e = getenv("BEAMGPU_SPLIT_KERNELS")) c->splitKernels = atoi(e) ? 1 : 0;
     c->evRegion[0] = c->evRegion[1] = nullptr;
+    c->d_xbuf = nullptr; c->xRanks = 1; c->xRank = 0; c->epoch = 0; c->lastIters = 4; c->h_res = nullptr; c->d_hres = nullptr;
+    memset(&c->cvNow, 0, sizeof c->cvNow);
+    for (int i = 0; i < CONV_MAX_RANKS; i++) c->peerXbuf[i] = nullptr;
+    for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) c->evIter[i][k] = nullptr;
     c->copyStream = nullptr; c->evStaged = c->evCopied = nullptr; c->copyPending = false; c->fwdMs = c->bwdMs = 0; c->timedIters = 0;
     c->hasQ = c->hasM = false;
     c->d_q = c->d_m = c->d_Lc = c->d_DW = c->d_DTh = nullptr;
@@ -543,6 +563,13 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     if (devAlloc(c, (void**)&c->d_stagePatchQ, sizeof(double) * (size_t)B * 4)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
     CREATE_CUDA(cudaHostAlloc((void**)&c->h_sums, 8 * sizeof(double), cudaHostAllocMapped));
     CREATE_CUDA(cudaHostGetDevicePointer((void**)&c->d_hsums, c->h_sums, 0));
+    CREATE_CUDA(cudaHostAlloc((void**)&c->h_res, PIPE_CHUNK_MAX * 4 * sizeof(double), cudaHostAllocMapped));
+    CREATE_CUDA(cudaHostGetDevicePointer((void**)&c->d_hres, c->h_res, 0));
+    for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) CREATE_CUDA(cudaEventCreate(&c->evIter[i][k]));
+    // the exchange buffer is its own cudaMalloc: CUDA IPC exports whole allocations
+    CREATE_CUDA(cudaMalloc((void**)&c->d_xbuf, sizeof(double) * 2 * CONV_MAXK * CONV_MAX_RANKS * 4));
+    CREATE_CUDA(cudaMemsetAsync(c->d_xbuf, 0, sizeof(double) * 2 * CONV_MAXK * CONV_MAX_RANKS * 4, c->stream));
+    c->peerXbuf[0] = c->d_xbuf;
 
     // ---- upload constants
     {
@@ -1123,6 +1150,7 @@ static BeamParams makeParams(bf_ctx* c)
     p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir; p.ifW = c->d_ifW;
     p.uP = c->d_uP; p.bP = c->d_bP; p.partial = c->d_partial;
     p.nTiles = c->partialStride;
+    p.cv = c->cvNow;
     return p;
 }
 
@@ -1139,8 +1167,10 @@ static BeamParams makeParams(bf_ctx* c)
         else KERNEL<BFK_STEADY><<<(GRID), THREADS, (SMEM), c->stream>>>(P);                           \
     } while (0)
 // Launches one Newton iteration; the three LOCAL sums of squares end up in d_sums.
-static int launchIteration(bf_ctx* c)
+// evs: the three timing events of this iteration (bf_evolve's pipelined loop passes one set per enqueued iteration)
+static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
 {
+    if (!evs) evs = c->ev;
     const BeamParams p = makeParams(c);
     if (p.pf) { // lever arms follow the current W: re-evaluated every iteration (Evolve.C:221)
         beam_point_forces<<<(unsigned)((c->B + 127) / 128), 128, 0, c->stream>>>(p);
@@ -1155,7 +1185,7 @@ static int launchIteration(bf_ctx* c)
         else beam_momentum_contributions<BFK_STEADY><<<cgrid, 128, 0, c->stream>>>(p, cp);
         c->launches++;
     }
-    if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[0], c->stream));
+    if (c->timing) CUDA_OK(c, cudaEventRecord(evs[0], c->stream));
     int nF = c->grid, nB = c->grid; // blocks that wrote the partial sums of the forward / backward part
     if (c->longMode) {
         nF = nB = c->longBlocks; // one thread per cell: assemble, block cyclic reduction, update
@@ -1181,7 +1211,7 @@ static int launchIteration(bf_ctx* c)
             long_pcr_finish<<<gb, 128, 0, c->stream>>>(q);
             c->launches += 2;
         }
-        if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
+        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
         long_update_faces<<<gb, 128, 0, c->stream>>>(p, q);
         if (c->scheme == BF_SCHEME_NEWMARK) long_update_cells<BFK_NEWMARK><<<gb, 128, 0, c->stream>>>(p, q);
         else if (c->scheme == BF_SCHEME_EULER) long_update_cells<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
@@ -1190,14 +1220,14 @@ static int launchIteration(bf_ctx* c)
     } else if (c->split) { // two threads per beam, the halves meet in the middle
         const dim3 g2((unsigned)c->grid, 2);
         LAUNCH_SCHEME(beam_forward_split, g2, SMEM_BYTES, p);
-        if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
+        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
         LAUNCH_SCHEME(beam_backward_split, g2, 0, p);
         c->launches += 2;
         nF = nB = 2 * c->grid;
     } else if (c->splitKernels || c->coopFwd || c->coopBwd) { // product path: one launch per sweep
         if (c->coopFwd) LAUNCH_SCHEME_T(beam_forward_ws, c->coopGrid, WS_THREADS, WS_SMEM_BYTES, p);
         else LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
-        if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
+        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
         const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
         if (c->coopBwd) { // serial back-substitution, then the update with one thread per cell
             beam_backsub<<<(unsigned)((c->Bpad + BS_THREADS - 1) / BS_THREADS), BS_THREADS, BS_SMEM_BYTES, c->stream>>>(p, c->d_X);
@@ -1212,11 +1242,17 @@ static int launchIteration(bf_ctx* c)
         nB = c->coopBwd ? cellGrid : c->grid;
     } else {
         LAUNCH_SCHEME(beam_newton, c->grid, SMEM_BYTES, p);
-        if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[1], c->stream));
+        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
         c->launches += 1;
     }
-    if (c->timing) CUDA_OK(c, cudaEventRecord(c->ev[2], c->stream));
-    beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, c->d_sums, c->comm ? nullptr : c->d_hsums);
+    if (c->timing) CUDA_OK(c, cudaEventRecord(evs[2], c->stream));
+    if (p.cv.xbuf) { // pipelined loop: the sums go into every rank's exchange buffer (one-sided), nobody waits here
+        PeerTable pt;
+        const size_t bank = (size_t)(c->epoch & 1) * CONV_MAXK * c->xRanks * 4;
+        for (int r = 0; r < CONV_MAX_RANKS; r++) pt.bank[r] = r < c->xRanks ? c->peerXbuf[r] + bank : nullptr;
+        beam_reduce_exchange<<<1, 256, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, p.cv, pt, c->xRank);
+    } else
+        beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, c->d_sums, c->comm ? nullptr : c->d_hsums);
     c->launches += 1;
     CUDA_OK(c, cudaGetLastError());
     if (p.first) c->dtStar = c->deltaT; // the backward sweep of a first iteration re-bases U*, Omega* on this step
@@ -1252,6 +1288,92 @@ extern "C" int bf_newton_iteration(bf_ctx* c, double sumsq[3])
 
 enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
 
+// checkConvergence (Evolve.C:926-1026) on the squared global sums of iteration `iteration`.  Returns true when the
+// loop ends; *status = BF_OK / BF_DIVERGED / BF_MAXITER, and the error text of the two failures.
+static bool checkConvergence(bf_ctx* c, const bf_tolerances* tol, int iteration, const double s[3], double* initialResidualNorm,
+                             double* currentResidualNorm, double* deltaXNorm, double* XNorm, int* status)
+{
+    if (!(s[0] == s[0]) || !(s[1] == s[1]) || !(s[2] == s[2])) { // NaN: a singular block -- the reference would abort inside SparseLU
+        *status = BF_DIVERGED;
+        fail(c, BF_DIVERGED, "Iteration %d: non-finite residual/solution norm", iteration);
+        return true;
+    }
+    *currentResidualNorm = sqrt(s[0]);
+    *deltaXNorm = sqrt(s[1]);
+    *XNorm = sqrt(s[2]);
+    if (iteration == 0) *initialResidualNorm = *currentResidualNorm;
+    if (*currentResidualNorm <= tol->absoluteTol) return true;
+    if (*currentResidualNorm <= tol->residualTol * *initialResidualNorm) return true;
+    if (*deltaXNorm <= tol->solutionTol * *XNorm) return true;
+    if (*currentResidualNorm >= tol->divergenceTol * *initialResidualNorm && iteration > 1) {
+        fail(c, BF_DIVERGED, "Iteration %d: Diverged - Residual grew excessively.", iteration);
+        *status = BF_DIVERGED;
+        return true;
+    }
+    if (iteration >= tol->nCorrectors) {
+        fail(c, BF_MAXITER, "Iteration %d: Failed - Maximum iterations reached.", iteration);
+        *status = BF_MAXITER;
+        return true;
+    }
+    return false;
+}
+
+// The pipelined Newton loop: the iterations of a chunk are enqueued back to back without waiting for their norms; every
+// sweep kernel looks at the global norms of the previous iteration itself (convLeave) and the ones past the end of the loop
+// leave at once.  The host reads the verdicts of a whole chunk with ONE synchronisation.  The chunk is the iteration
+// count of the previous step (the same on every rank, so every rank enqueues the same launches).
+static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
+{
+    double initialResidualNorm = 1, currentResidualNorm = BF_GREAT, deltaXNorm = BF_GREAT, XNorm = BF_GREAT;
+    int status = BF_OK, nIter = 0;
+    c->epoch++;
+    ConvCtl cv;
+    cv.xbuf = c->d_xbuf + (size_t)(c->epoch & 1) * CONV_MAXK * c->xRanks * 4;
+    cv.nRanks = c->xRanks; cv.iter = 0; cv.tag = 2.0 * (double)c->epoch;
+    cv.absTol = tol->absoluteTol; cv.resTol = tol->residualTol; cv.solTol = tol->solutionTol; cv.divTol = tol->divergenceTol;
+    cv.nCorr = tol->nCorrectors;
+    int chunk = c->lastIters < 1 ? 1 : c->lastIters > PIPE_CHUNK_MAX ? PIPE_CHUNK_MAX : c->lastIters;
+    bool done = false;
+    for (int k0 = 0; !done;) {
+        int k1 = k0 + chunk;
+        if (k1 > tol->nCorrectors + 1) k1 = tol->nCorrectors + 1; // iteration nCorrectors always ends the loop
+        for (int k = k0; k < k1; k++) {
+            cv.iter = k;
+            c->cvNow = cv;
+            int rc = launchIteration(c, c->evIter[k - k0]);
+            if (rc) { c->cvNow.xbuf = nullptr; out->status = rc; return rc; }
+        }
+        c->cvNow.xbuf = nullptr;
+        beam_publish_chunk<<<1, 32, 0, c->stream>>>(cv, k0, k1, c->d_hres);
+        c->launches++;
+        CUDA_OK(c, cudaGetLastError());
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        for (int k = k0; k < k1 && !done; k++) {
+            const double* r = c->h_res + 4 * (k - k0);
+            done = checkConvergence(c, tol, k, r, &initialResidualNorm, &currentResidualNorm, &deltaXNorm, &XNorm, &status);
+            nIter = k + 1;
+            if (c->timing) {
+                float a = 0, b = 0;
+                CUDA_OK(c, cudaEventElapsedTime(&a, c->evIter[k - k0][0], c->evIter[k - k0][1]));
+                CUDA_OK(c, cudaEventElapsedTime(&b, c->evIter[k - k0][1], c->evIter[k - k0][2]));
+                c->fwdMs += a; c->bwdMs += b; c->timedIters++;
+            }
+            if (done != (r[3] == 1.0)) return fail(c, BF_ERR_CUDA, "iteration %d: host and device disagree on the convergence test", k);
+        }
+        k0 = k1;
+        chunk = 1; // the prediction was short: go on one iteration at a time
+    }
+    c->lastIters = nIter;
+    c->iOuterCorr = nIter;
+    out->nIter = nIter;
+    out->status = status;
+    out->initialResidualNorm = initialResidualNorm;
+    out->currentResidualNorm = currentResidualNorm;
+    out->deltaXNorm = deltaXNorm;
+    out->xNorm = XNorm;
+    return status;
+}
+
 // evolve(): Evolve.C:55-670, checkConvergence :926-1026
 extern "C" int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
 {
@@ -1260,6 +1382,12 @@ extern "C" int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
     double initialResidualNorm = 1, currentResidualNorm = BF_GREAT, deltaXNorm = BF_GREAT, XNorm = BF_GREAT;
     memset(out, 0, sizeof *out);
     c->iOuterCorr = 0;
+    // Pipelined loop whenever the sums can be exchanged on the device: a single context, or peers attached with
+    // bf_comm_ipc_attach.  A host reducer / NCCL communicator without peer memory, the cell-parallel path and the fused
+    // launch keep the host in the loop (one synchronisation per iteration).
+    const bool pipelined = !c->reducer && (!c->comm || c->xRanks > 1) && !c->longMode && (c->splitKernels || c->split || c->coopFwd || c->coopBwd) &&
+                           tol->nCorrectors < CONV_MAXK - 1 && !getenv("BEAMGPU_NO_PIPELINE");
+    if (pipelined) return evolvePipelined(c, tol, out);
     int status = BF_OK;
     for (;;) {
         const int iteration = c->iOuterCorr; // the value passed as iOuterCorr()++
@@ -1272,28 +1400,7 @@ extern "C" int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
         }
         if ((rc = fetchSums(c, s))) { out->status = rc; return rc; }
         if (c->reducer && c->reducer(s, 3, c->reducerUser)) { out->status = BF_ERR_COMM; return fail(c, BF_ERR_COMM, "norm reducer failed"); }
-        if (!(s[0] == s[0]) || !(s[1] == s[1])) { // NaN: a singular block — the reference would abort inside SparseLU
-            out->status = BF_DIVERGED;
-            out->nIter = c->iOuterCorr;
-            return fail(c, BF_DIVERGED, "Iteration %d: non-finite residual/solution norm", iteration);
-        }
-        currentResidualNorm = sqrt(s[0]);
-        deltaXNorm = sqrt(s[1]);
-        XNorm = sqrt(s[2]);
-        if (iteration == 0) initialResidualNorm = currentResidualNorm;
-        if (currentResidualNorm <= tol->absoluteTol) break;
-        if (currentResidualNorm <= tol->residualTol * initialResidualNorm) break;
-        if (deltaXNorm <= tol->solutionTol * XNorm) break;
-        if (currentResidualNorm >= tol->divergenceTol * initialResidualNorm && iteration > 1) {
-            fail(c, BF_DIVERGED, "Iteration %d: Diverged - Residual grew excessively.", iteration);
-            status = BF_DIVERGED;
-            break;
-        }
-        if (iteration >= tol->nCorrectors) {
-            fail(c, BF_MAXITER, "Iteration %d: Failed - Maximum iterations reached.", iteration);
-            status = BF_MAXITER;
-            break;
-        }
+        if (checkConvergence(c, tol, iteration, s, &initialResidualNorm, &currentResidualNorm, &deltaXNorm, &XNorm, &status)) break;
     }
     out->nIter = c->iOuterCorr;
     out->status = status;
@@ -1302,6 +1409,41 @@ extern "C" int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
     out->deltaXNorm = deltaXNorm;
     out->xNorm = XNorm;
     return status;
+}
+
+// ---- one-sided exchange over peer memory (CUDA IPC): see ConvCtl in beam_kernels.cuh -------------------------------
+extern "C" int bf_comm_ipc_export(bf_ctx* c, void* handle64)
+{
+    if (!handle64) return fail(c, BF_ERR_INVALID, "bf_comm_ipc_export: null argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof h == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CUDA_OK(c, cudaIpcGetMemHandle(&h, c->d_xbuf));
+    memcpy(handle64, &h, sizeof h);
+    return BF_OK;
+}
+extern "C" int bf_comm_ipc_attach(bf_ctx* c, int32_t nRanks, int32_t rank, const void* handles)
+{
+    if (!handles || nRanks < 1 || nRanks > CONV_MAX_RANKS || rank < 0 || rank >= nRanks)
+        return fail(c, BF_ERR_INVALID, "bf_comm_ipc_attach: bad argument (at most %d ranks)", CONV_MAX_RANKS);
+    CUDA_OK(c, cudaSetDevice(c->device));
+    for (int r = 0; r < nRanks; r++) {
+        if (r == rank) { c->peerXbuf[r] = c->d_xbuf; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * (size_t)r, sizeof h);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; q++) if (q != rank && c->peerXbuf[q]) { cudaIpcCloseMemHandle(c->peerXbuf[q]); c->peerXbuf[q] = nullptr; }
+            c->peerXbuf[rank] = c->d_xbuf;
+            return fail(c, BF_ERR_COMM, "cudaIpcOpenMemHandle of rank %d failed: %s", r, cudaGetErrorString(e));
+        }
+        c->peerXbuf[r] = (double*)ptr;
+    }
+    c->xRanks = nRanks;
+    c->xRank = rank;
+    c->peerXbuf[rank] = c->d_xbuf;
+    return BF_OK;
 }
 
 extern "C" int bf_set_reducer(bf_ctx* c, bf_reduce_fn fn, void* user)

@@ -230,7 +230,7 @@ def config_dict(args, world, total, scaling):
         "workload": wl, "config": args.config, "beams_total": total, "beams_per_gpu": per, "cells_per_beam": args.cells,
         "cells_total": total * args.cells, "tolerances": "the tutorial's (nCorrectors, residualTol, solutionTol unchanged)",
         "l2_policy": l2,
-        "parallelism": f"beams sharded over {world} GPU(s) ({scaling} scaling); one 3-double all-reduce per Newton iteration",
+        "parallelism": f"beams sharded over {world} GPU(s) ({scaling} scaling); the only exchange is the sum of 3 doubles per Newton iteration",
     }
 
 
@@ -370,8 +370,26 @@ class Bundle:
         self.model = coupledTotalLagNewtonRaphsonBeam(case, library=lib, device=D.local, beamRange=self.range,
                                                       storeIncrements=False)
         self.ctx = self.model._ctx
-        if comm and D.world > 1:  # built-in reducer: ncclAllReduce of the 3 squared norms on the library's stream
+        self.exchange = "none (one GPU)"
+        if comm and D.world > 1:
+            # fallback reducer: ncclAllReduce of the 3 squared norms on the library's stream, one host round trip per iteration
             self.model._check(lib.bf_comm_init_nccl(self.ctx, D.nccl_id(lib), D.world, D.rank))
+            self.exchange = "ncclAllReduce per iteration"
+            if not os.environ.get("BEAMGPU_NO_IPC"):
+                # one-sided exchange over NVLink peer memory + device-side convergence test (bf_comm_ipc_attach)
+                h = (C.c_char * 64)()
+                ok = lib.bf_comm_ipc_export(self.ctx, h) == 0
+                mine = D.torch.frombuffer(bytearray(h.raw), dtype=D.torch.uint8).clone().cuda()
+                allh = [D.torch.empty_like(mine) for _ in range(D.world)]
+                D.dist.all_gather(allh, mine)
+                blob = b"".join(t.cpu().numpy().tobytes() for t in allh)
+                ok = ok and lib.bf_comm_ipc_attach(self.ctx, D.world, D.rank, blob) == 0
+                if D.min(1.0 if ok else 0.0) == 1.0:
+                    self.exchange = "one-sided peer-memory stores (CUDA IPC over NVLink), convergence test on the device"
+                elif ok:
+                    raise SystemExit("bench.py: peer memory mapped on some ranks only")
+                else:
+                    sys.stderr.write("bench.py: peer memory not available: " + lib.bf_last_error(self.ctx).decode() + "\n")
         self.cells = self.model.nCells
         self.timeDependent = args.config == "long"  # the bundle's loads are constant in time: handed over once
         self.family = int(lib.bf_kernel_family(self.ctx))
@@ -521,6 +539,7 @@ def run_ours(args):
     case = make_case(args, total)
     main = Bundle(args, D, lib, case, total)
     model, ctx = main.model, main.ctx
+    exchange = main.exchange
     nCellsLocal = main.cells
     flush = None
     if args.config == "long":
@@ -663,6 +682,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": r["launches"], "roofline": roofline, "cpu_baseline": cpu,
             "newton_iterations_per_step": r["timed_iters"] / args.steps, "newton_iterations": r["iters"],
             "wall_ms_per_step": r["wall_ms"] / args.steps, "parity": parity, "weak": weak, "impl": "ours",
+            "norm_exchange": exchange,
         }
         print(json.dumps(line), flush=True)
     D.close()

@@ -307,6 +307,16 @@ int bf_set_reducer(bf_ctx* ctx, bf_reduce_fn fn, void* user);
  * host (MPI_Bcast in an OpenFOAM host).  libnccl is dlopen()ed on first use. */
 int bf_nccl_unique_id(void* uniqueId128);
 int bf_comm_init_nccl(bf_ctx* ctx, const void* uniqueId128, int32_t nRanks, int32_t rank);
+/* One-sided exchange over peer memory (NVLink / NVSwitch, one process per GPU on one node): every context owns a small
+ * exchange buffer; bf_comm_ipc_export returns its 64-byte CUDA IPC handle, the host gathers the handles of all ranks
+ * (MPI_Allgather in an OpenFOAM host) and hands the nRanks x 64 bytes, in rank order, to bf_comm_ipc_attach.  From then on
+ * the reduction kernel of a Newton iteration writes this rank's three sums straight into every rank's buffer, every sweep
+ * kernel evaluates checkConvergence (Evolve.C:926-1026) on the device, and bf_evolve enqueues whole Newton loops without a
+ * host round trip or a collective per iteration (the same device-side loop serves a single context).  Results are
+ * identical to the NCCL / reducer path: the records are added in rank order on every rank.  BF_ERR_COMM if the peers
+ * cannot be mapped (the context then keeps its previous reducer). */
+int bf_comm_ipc_export(bf_ctx* ctx, void* handle64);
+int bf_comm_ipc_attach(bf_ctx* ctx, int32_t nRanks, int32_t rank, const void* handles);
 
 /* ---- observables computed next to the state ----------------------------------
  * Replaces functionObjects/beamEnergyData/beamEnergyData.C:84-215 (a reduction over every cell and face
