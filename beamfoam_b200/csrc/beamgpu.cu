@@ -370,6 +370,24 @@ static int devAlloc(bf_ctx* c, void** p, size_t bytes)
     return BF_OK;
 }
 
+// Buffers of the cell-parallel path (beam_long.cuh): the assembled block rows, two working copies, the solution and the
+// beam of every cell.  Allocated by bf_create for few long beams, on first use by bf_newton_iteration_checked otherwise.
+static int ensureLongBuffers(bf_ctx* c)
+{
+    if (c->d_cellBeam) return BF_OK;
+    char* cur;
+    const size_t N = (size_t)c->N;
+    if (int rc = devAlloc(c, (void**)&cur, sizeof(double) * N * (3 * (36 * 3 + 6) + 6) + sizeof(int32_t) * N + 256 * 16)) return rc;
+    for (int k = 0; k < 12; k++) c->d_longRows[k] = carve<double>(cur, (k % 4 == 3 ? 6 : 36) * N);
+    c->d_longX = carve<double>(cur, 6 * N + 6); // one row of slack: the last cell reads "x of the next cell" unguarded
+    c->d_cellBeam = carve<int32_t>(cur, N);
+    std::vector<int32_t> cb(N);
+    for (int64_t b = 0; b < c->B; b++) for (int64_t g = c->cellStart[b]; g < c->cellStart[b + 1]; g++) cb[g] = (int32_t)b;
+    CUDA_OK(c, cudaMemcpyAsync(c->d_cellBeam, cb.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
 // Replaces the constructor state set-up of CTL.C:74-1182 for what the hot path touches.
 extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf_bc* bc, const bf_options* opt,
                          bf_ctx** out)
@@ -659,18 +677,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         c->launches += 3;
         CREATE_CUDA(cudaGetLastError());
     }
-    if (c->longMode) {
-        char* cur;
-        const size_t N = (size_t)c->N;
-        if (devAlloc(c, (void**)&cur, sizeof(double) * N * (3 * (36 * 3 + 6) + 6) + sizeof(int32_t) * N + 256 * 16)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
-        for (int k = 0; k < 12; k++) c->d_longRows[k] = carve<double>(cur, (k % 4 == 3 ? 6 : 36) * N);
-        c->d_longX = carve<double>(cur, 6 * N + 6); // one row of slack: the last cell reads "x of the next cell" unguarded
-        c->d_cellBeam = carve<int32_t>(cur, N);
-        std::vector<int32_t> cb(N);
-        for (int64_t b = 0; b < B; b++) for (int64_t g = c->cellStart[b]; g < c->cellStart[b + 1]; g++) cb[g] = (int32_t)b;
-        CREATE_CUDA(cudaMemcpyAsync(c->d_cellBeam, cb.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
-        CREATE_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    if (c->longMode && ensureLongBuffers(c)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
     if (lay->cellLength) { // L() per cell (HermiteSpline::segLengths), otherwise dZ
         char* cur;
         if (devAlloc(c, (void**)&cur, sizeof(double) * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
@@ -738,6 +745,7 @@ static int drainMirror(bf_ctx* c)
     return BF_OK;
 }
 static BeamParams makeParams(bf_ctx* c);
+static int ensureLongBuffers(bf_ctx* c);
 // Device state -> host-ordered (createBeamMesh) array `dst` in device memory, on the compute stream.
 static void stageInternal(bf_ctx* c, double* dev, int nc, int surface, int kind, double* dst)
 {
@@ -1284,6 +1292,84 @@ extern "C" int bf_newton_iteration(bf_ctx* c, double sumsq[3])
     int rc = launchIteration(c);
     if (rc) return rc;
     return fetchSums(c, sumsq);
+}
+
+// Diagnostic: one Newton iteration (as bf_newton_iteration) together with the normwise backward error of its linear solve,
+//     eta = ||b - A x||_2 / (||A||_F ||x||_2 + ||b||_2),
+// A, b = the block system assembled from the pre-solve state by the cell-parallel assembly (long_assemble: the blocks the
+// reference hands to BlockEigenSolverOF, EigenOF.C:60-175), x = the increments the sweeps produced.  Needs storeIncrements.
+__global__ void linearResidualKernel(const BeamParams p, const LongParams q, double* __restrict__ acc4)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v[4] = {0, 0, 0, 0}; // r^2, b^2, A^2, x^2
+    if (g < q.N) {
+        const int b = q.cellBeam[g];
+        const int i = (int)(g - q.cellStart[b]), n = p.nSeg[b];
+        const size_t T = (size_t)(b >> 5);
+        const int lane = b & 31;
+        double x[3][6];
+        for (int d = -1; d <= 1; d++) {
+            const int ii = i + d;
+            for (int k = 0; k < 6; k++) x[d + 1][k] = 0.0;
+            if (ii < 0 || ii >= n) continue;
+            const size_t c3 = tileRow(T, p.nmax, ii, 3, lane);
+            for (int k = 0; k < 3; k++) { x[d + 1][k] = p.DW[c3 + (size_t)k * TS]; x[d + 1][3 + k] = p.DTh[c3 + (size_t)k * TS]; }
+        }
+        for (int r = 0; r < 6; r++) {
+            double a = q.R0[6 * g + r];
+            v[1] += a * a;
+            for (int c = 0; c < 6; c++) {
+                const double l = q.L0[36 * g + 6 * r + c], d = q.D0[36 * g + 6 * r + c], u = q.U0[36 * g + 6 * r + c];
+                a -= l * x[0][c] + d * x[1][c] + u * x[2][c];
+                v[2] += l * l + d * d + u * u;
+            }
+            v[0] += a * a;
+            v[3] += x[1][r] * x[1][r];
+        }
+    }
+    for (int k = 0; k < 4; k++) {
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(acc4 + k, v[k]);
+    }
+}
+extern "C" int bf_newton_iteration_checked(bf_ctx* c, double sumsq[3], double* backwardError)
+{
+    if (!backwardError) return fail(c, BF_ERR_INVALID, "bf_newton_iteration_checked: null argument");
+    if (!c->storeInc) return fail(c, BF_ERR_INVALID, "bf_newton_iteration_checked needs storeIncrements (the solution of the linear solve)");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    if (int rc = ensureLongBuffers(c)) return rc;
+    {   // the assembled system of the state as it is now
+        const BeamParams p = makeParams(c);
+        if (p.pf) beam_point_forces<<<(unsigned)((c->B + 127) / 128), 128, 0, c->stream>>>(p);
+        if (c->contrib.n) return fail(c, BF_ERR_UNSUPPORTED, "bf_newton_iteration_checked: momentum contributions are not supported");
+        LongParams q;
+        memset(&q, 0, sizeof q);
+        q.N = c->N; q.cellBeam = c->d_cellBeam; q.cellStart = c->d_cellStart;
+        q.L0 = c->d_longRows[8]; q.D0 = c->d_longRows[9]; q.U0 = c->d_longRows[10]; q.R0 = c->d_longRows[11];
+        const int gb = (int)((c->N + 127) / 128);
+        if (c->scheme == BF_SCHEME_NEWMARK) long_assemble<BFK_NEWMARK><<<gb, 128, 0, c->stream>>>(p, q);
+        else if (c->scheme == BF_SCHEME_EULER) long_assemble<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
+        else long_assemble<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
+        c->launches++;
+        CUDA_OK(c, cudaGetLastError());
+    }
+    int rc = bf_newton_iteration(c, sumsq);
+    if (rc) return rc;
+    {
+        const BeamParams p = makeParams(c);
+        LongParams q;
+        memset(&q, 0, sizeof q);
+        q.N = c->N; q.cellBeam = c->d_cellBeam; q.cellStart = c->d_cellStart;
+        q.L0 = c->d_longRows[8]; q.D0 = c->d_longRows[9]; q.U0 = c->d_longRows[10]; q.R0 = c->d_longRows[11];
+        CUDA_OK(c, cudaMemsetAsync(c->d_sums + 4, 0, 4 * sizeof(double), c->stream));
+        linearResidualKernel<<<(unsigned)((c->N + 127) / 128), 128, 0, c->stream>>>(p, q, c->d_sums + 4);
+        c->launches++;
+        double h[4];
+        CUDA_OK(c, cudaMemcpyAsync(h, c->d_sums + 4, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        *backwardError = sqrt(h[0]) / (sqrt(h[2]) * sqrt(h[3]) + sqrt(h[1]));
+    }
+    return BF_OK;
 }
 
 enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };

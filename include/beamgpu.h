@@ -295,6 +295,13 @@ int bf_begin_step(bf_ctx* ctx, double deltaT);
  * context (EigenOF.C:279-281 "use sum instead of gSum"); no reducer applied. */
 int bf_newton_iteration(bf_ctx* ctx, double sumsq[3]);
 
+/* Diagnostic twin of bf_newton_iteration: the same iteration, plus the normwise backward error of its linear solve
+ *   eta = ||b - A x||_2 / (||A||_F ||x||_2 + ||b||_2)
+ * over the whole bundle, with A, b the block system of EigenOF.C:60-175 assembled from the pre-solve state by an independent
+ * kernel and x the increments the solve produced (the context must keep them: bf_options.storeIncrements).  A backward
+ * stable solve gives eta of the order of 1e-16; tests/test_gpu_robustness.py reports it for every kernel family. */
+int bf_newton_iteration_checked(bf_ctx* ctx, double sumsq[3], double* backwardError);
+
 /* The whole Newton loop of evolve() with checkConvergence (Evolve.C:926-1026)
  * evaluated on the (reduced) norms.  Always fills `out`. */
 int bf_evolve(bf_ctx* ctx, const bf_tolerances* tol, bf_step_out* out);

@@ -179,6 +179,7 @@ int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
 int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
 int64_t bf_launch_count(const bf_ctx* c) { (void)c; return 0; }
 int32_t bf_kernel_family(const bf_ctx* c) { (void)c; return BF_FAMILY_CPU; }
+int bf_newton_iteration_checked(bf_ctx* c, double sumsq[3], double* eta) { (void)sumsq; (void)eta; snprintf(c->err, sizeof c->err, "diagnostic of the CUDA library only"); return BF_ERR_UNSUPPORTED; }
 int bf_comm_ipc_export(bf_ctx* c, void* h) { (void)h; snprintf(c->err, sizeof c->err, "the CPU oracle has no peer memory"); return BF_ERR_UNSUPPORTED; }
 int bf_comm_ipc_attach(bf_ctx* c, int32_t n, int32_t r, const void* h) { (void)n; (void)r; (void)h; snprintf(c->err, sizeof c->err, "the CPU oracle has no peer memory"); return BF_ERR_UNSUPPORTED; }
 int bf_kernel_time_ms(bf_ctx* c, int32_t r, double* a, double* b, int64_t* it)
