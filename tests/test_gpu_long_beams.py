@@ -24,7 +24,8 @@ def test_config1_follower_beam_10000_cells(gpu_lib, oracle_lib):
     """BASELINE configs[1]: cantileverFollowerForce with nSegments 10000 (the path is chosen automatically).  20 load
     steps: without the refinement pass of the cyclic reduction the Newton loop needs 5-6 iterations from step 3 on
     where the reference-shaped pivoted LU of the oracle needs 4."""
-    run_pair(cases.cantileverFollowerForce(nSegments=10000), gpu_lib, oracle_lib, nSteps=20, tip_rtol=1e-7, field_rtol=1e-5)
+    # tips at 1e-10 (measured 3e-15); the field check is looser only because Gamma divides W differences of 1e-15 by dZ = 0.01
+    run_pair(cases.cantileverFollowerForce(nSegments=10000), gpu_lib, oracle_lib, nSteps=20, field_rtol=1e-7)
 
 
 def test_cantilever_roll_up(gpu_lib, oracle_lib, long_path):
@@ -38,13 +39,13 @@ def test_newmark_bundle_ragged(gpu_lib, oracle_lib, long_path):
 
 
 def test_free_flexible_beam(gpu_lib, oracle_lib, long_path):
-    run_pair(cases.freeFlexibleBeam(), gpu_lib, oracle_lib, nSteps=100, tip_rtol=1e-9)
+    run_pair(cases.freeFlexibleBeam(), gpu_lib, oracle_lib, nSteps=100)
 
 
 def test_euler_and_point_forces(gpu_lib, oracle_lib, long_path):
     base = dataclasses.replace(cases.multiBeamDensity(3, 10), d2dt2Scheme="Euler",
                                pointForces=[(4, 0.5, (20.0, 0, -10.0)), (10, -1.0, (0, 15.0, 0)), (29, 1.0, (5.0, 5.0, 5.0))])
-    run_pair(base, gpu_lib, oracle_lib, nSteps=30, tip_rtol=1e-9)
+    run_pair(base, gpu_lib, oracle_lib, nSteps=30)
 
 
 def test_every_bc_class(gpu_lib, oracle_lib, long_path):
@@ -84,4 +85,4 @@ def test_momentum_contributions(gpu_lib, oracle_lib, long_path):
                                initialTranslation=np.array([0.0, 0.0, 0.1]),
                                momentumContributions=[morisonDragContribution(1.2, 0.05, 1000.0),
                                                       groundContactContribution(2e3, 50.0, 4e2, 0.3, 1.2)])
-    run_pair(case, gpu_lib, oracle_lib, nSteps=20, tip_rtol=1e-9)
+    run_pair(case, gpu_lib, oracle_lib, nSteps=20)

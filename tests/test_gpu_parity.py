@@ -90,15 +90,14 @@ def test_follower_force(gpu_lib, oracle_lib):
 
 def test_follower_force_long_beam(gpu_lib, oracle_lib):
     """configs[1] physics at reduced length for the oracle's sake: 2000 segments, 5 steps."""
-    run_pair(cases.cantileverFollowerForce(nSegments=2000), gpu_lib, oracle_lib, nSteps=5, tip_rtol=1e-8,
-             field_rtol=1e-6)
+    run_pair(cases.cantileverFollowerForce(nSegments=2000), gpu_lib, oracle_lib, nSteps=5)
 
 
 @pytest.mark.parametrize("F", [0.0, 0.294, 0.588])
 def test_large_deflection(gpu_lib, oracle_lib, F):
-    # very slender strip (EA/EI ~ 7.5e7): the converged answer is conditioned ~1e6 worse than
-    # the others, so the two FP orderings agree to ~1e-8 rather than 1e-10.
-    run_pair(cases.largeDeflectionCantilever(F), gpu_lib, oracle_lib, nSteps=1, tip_rtol=1e-7, field_rtol=1e-5)
+    # very slender strip (EA/EI ~ 7.5e7, Iyy/Izz ~ 4e3): the rotational 3x3 pivot block is ill-conditioned and the 6x6 blocks
+    # go through the pivoted LU (smallDet); measured difference to the oracle 1e-15 (round 1, without the pivoting: 1e-8)
+    run_pair(cases.largeDeflectionCantilever(F), gpu_lib, oracle_lib, nSteps=1)
 
 
 def test_dynamic_cantilever(gpu_lib, oracle_lib):
@@ -111,7 +110,7 @@ def test_multibeam_density(gpu_lib, oracle_lib):
 
 
 def test_free_flexible_beam(gpu_lib, oracle_lib):
-    run_pair(cases.freeFlexibleBeam(), gpu_lib, oracle_lib, nSteps=300, tip_rtol=1e-9)
+    run_pair(cases.freeFlexibleBeam(), gpu_lib, oracle_lib, nSteps=300)
 
 
 def test_spring_in_series(gpu_lib, oracle_lib):
@@ -119,7 +118,7 @@ def test_spring_in_series(gpu_lib, oracle_lib):
 
 
 def test_cantilever_spring(gpu_lib, oracle_lib):
-    run_pair(cases.cantileverSpring(), gpu_lib, oracle_lib, nSteps=1, tip_rtol=1e-9)
+    run_pair(cases.cantileverSpring(), gpu_lib, oracle_lib, nSteps=1)
 
 
 def test_ragged_bundle_with_jitter(gpu_lib, oracle_lib):
@@ -174,8 +173,8 @@ def test_point_forces_steady_and_newmark(gpu_lib, oracle_lib):
 
 def test_euler_scheme(gpu_lib, oracle_lib):
     case = dataclasses.replace(cases.multiBeamDensity(7, 16, jitter=True), d2dt2Scheme="Euler")
-    worst = run_pair(case, gpu_lib, oracle_lib, nSteps=60, tip_rtol=1e-9)
-    assert worst <= 1e-9
+    worst = run_pair(case, gpu_lib, oracle_lib, nSteps=60)
+    assert worst <= 1e-10
     # a change of time step between steps (old-time levels are per step, not per dt)
     g = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
     o = coupledTotalLagNewtonRaphsonBeam(case, library=oracle_lib)
@@ -184,7 +183,7 @@ def test_euler_scheme(gpu_lib, oracle_lib):
         m.case = dataclasses.replace(m.case, deltaT=2.5e-3)
         m.run(nSteps=3)
     for a, b in zip(g.tip(1), o.tip(1)):
-        assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))
+        assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
     for f in ("U", "Accl", "Omega"):
         a, b = g.get_field(f)[0], o.get_field(f)[0]
         assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-3), f
