@@ -101,6 +101,9 @@ EXPORTS = {
     "bf_launch_count": (C.c_int64, [C.c_void_p]),
     "bf_kernel_family": (C.c_int32, [C.c_void_p]),
     "bf_newton_iteration_checked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bf_set_couplings": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bf_set_linear_solver": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double]),
+    "bf_linear_iterations": (C.c_int32, [C.c_void_p]),
     "bf_comm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bf_comm_ipc_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "bf_kernel_time_ms": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp, C.POINTER(C.c_int64)]),

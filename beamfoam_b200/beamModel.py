@@ -86,6 +86,10 @@ class BeamCase:
     initialTranslation: Optional[np.ndarray] = None
     # constant/beamMomentumContributionProperties: list of morisonDragContribution / groundContactContribution
     momentumContributions: Optional[Sequence] = None
+    # inter-beam couplings (synthetic, see include/beamgpu.h bf_set_couplings): (cellA, cellB, stiffness)
+    # with cell labels of the whole bundle; linearSolver = (maxIter, tolerance, relTol) of the coupled BiCGStab
+    couplings: Optional[Sequence[tuple]] = None
+    linearSolver: Optional[tuple] = None
     # crossSection.R() per beam (circle: radius, rectangle: h/2): read by the momentum contributions only
     R: Union[float, Sequence[float]] = 0.0
     # system/controlDict
@@ -218,6 +222,18 @@ class coupledTotalLagNewtonRaphsonBeam:
                 self.set_field(var, None, left, right)
         if case.q is not None or case.m is not None:
             self._set_loads(case.q, case.m, lo, hi)
+        if case.couplings:
+            allStart = np.concatenate([[0], np.cumsum(case.per_beam(case.nSegments, np.int64))])
+            c0, c1 = int(allStart[lo]), int(allStart[hi])
+            cp = np.asarray([(a, b, k) for a, b, k in case.couplings], dtype=np.float64)
+            a, b = cp[:, 0].astype(np.int64), cp[:, 1].astype(np.int64)
+            inside = (a >= c0) & (a < c1) & (b >= c0) & (b < c1)
+            if np.any(((a >= c0) & (a < c1)) != ((b >= c0) & (b < c1))):
+                raise ValueError("a coupling pair spans two shards: coupled beams must live in one context")
+            a, b, k = np.ascontiguousarray(a[inside] - c0), np.ascontiguousarray(b[inside] - c0), np.ascontiguousarray(cp[inside, 2])
+            self._check(self.lib.bf_set_couplings(ctx, len(a), a.ctypes.data, b.ctypes.data, k.ctypes.data))
+        if case.linearSolver:
+            self._check(self.lib.bf_set_linear_solver(ctx, int(case.linearSolver[0]), float(case.linearSolver[1]), float(case.linearSolver[2])))
 
         if case.momentumContributions:
             lst = (L.bf_momentum_contribution * len(case.momentumContributions))()

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = [os.path.join(HERE, "csrc", "beamgpu.cu")]
 HEADERS = [os.path.join(HERE, "csrc", "beam_kernels.cuh"), os.path.join(HERE, "csrc", "beam_long.cuh"),
-           os.path.join(HERE, "csrc", "beam_coop.cuh"),
+           os.path.join(HERE, "csrc", "beam_coop.cuh"), os.path.join(HERE, "csrc", "beam_bicgstab.cuh"),
            os.path.join(HERE, "csrc", "beam_contrib.cuh"),
            os.path.join(HERE, "csrc", "beam_math.cuh"),
            os.path.join(ROOT, "include", "beamgpu.h")]

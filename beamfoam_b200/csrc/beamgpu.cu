@@ -9,6 +9,7 @@
 #include "beam_kernels.cuh"
 #include "beam_long.cuh"
 #include "beam_coop.cuh"
+#include "beam_bicgstab.cuh"
 #include "beam_contrib.cuh"
 
 #include <cuda_runtime.h>
@@ -94,6 +95,13 @@ struct bf_ctx {
     // NCCL
     NcclApi nccl;
     void* comm;
+    // coupled bundles (beam_bicgstab.cuh): adjacency of the couplings, factors of the tridiagonal part, Krylov vectors
+    int64_t nPairs;
+    int64_t *d_adjPtr, *d_adjCol;
+    double *d_adjK, *d_cplDinv, *d_cplUP, *d_cplVec; // d_cplVec: r, rw, p, ph, v, s, sh, t (8 x 6N)
+    double *h_lin, *d_hlin;                         // pinned + mapped: dot products of the Krylov loop
+    int linMaxIter, linIterations;
+    double linTol, linRelTol;
     // pipelined Newton loop (device-side convergence test, one-sided exchange of the norm sums; beam_kernels.cuh ConvCtl)
     double* d_xbuf;            // [2 banks][CONV_MAXK][xRanks][4], cudaMalloc (its IPC handle is exported to the peers)
     double* peerXbuf[CONV_MAX_RANKS]; // every rank's buffer as mapped into this process (own: d_xbuf)
@@ -140,7 +148,7 @@ extern "C" int64_t bf_num_cells(const bf_ctx* c) { return c->N; }
 extern "C" int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
 extern "C" int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
 extern "C" int64_t bf_launch_count(const bf_ctx* c) { return c->launches; }
-extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return c->longMode ? BF_FAMILY_CELL : c->split ? BF_FAMILY_SPLIT : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
+extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return (c->longMode || c->nPairs) ? BF_FAMILY_CELL : c->split ? BF_FAMILY_SPLIT : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
 
 extern "C" int bf_host_alloc(void** p, int64_t bytes)
 {
@@ -347,6 +355,7 @@ extern "C" int bf_destroy(bf_ctx* c)
     for (int i = 0; i < c->nPools; i++) cudaFree(c->pools[i]);
     if (c->h_sums) cudaFreeHost(c->h_sums);
     if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->h_lin) cudaFreeHost(c->h_lin);
     for (int r = 0; r < c->xRanks; r++)
         if (r != c->xRank && c->peerXbuf[r]) cudaIpcCloseMemHandle(c->peerXbuf[r]);
     if (c->d_xbuf) cudaFree(c->d_xbuf);
@@ -419,6 +428,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     if (const char* e = getenv("BEAMGPU_FUSED_KERNEL")) c->splitKernels = atoi(e) ? 0 : 1;
     if (const char* e = getenv("BEAMGPU_SPLIT_KERNELS")) c->splitKernels = atoi(e) ? 1 : 0;
     c->evRegion[0] = c->evRegion[1] = nullptr;
+    c->nPairs = 0; c->d_adjPtr = c->d_adjCol = nullptr; c->d_adjK = c->d_cplDinv = c->d_cplUP = c->d_cplVec = nullptr;
+    c->h_lin = c->d_hlin = nullptr; c->linMaxIter = 1000; c->linIterations = 0; c->linTol = 1e-13; c->linRelTol = 0.0;
     c->d_xbuf = nullptr; c->xRanks = 1; c->xRank = 0; c->epoch = 0; c->lastIters = 4; c->h_res = nullptr; c->d_hres = nullptr;
     memset(&c->cvNow, 0, sizeof c->cvNow);
     for (int i = 0; i < CONV_MAX_RANKS; i++) c->peerXbuf[i] = nullptr;
@@ -746,6 +757,7 @@ static int drainMirror(bf_ctx* c)
 }
 static BeamParams makeParams(bf_ctx* c);
 static int ensureLongBuffers(bf_ctx* c);
+static int solveCoupled(bf_ctx* c, const CoupledParams& q);
 // Device state -> host-ordered (createBeamMesh) array `dst` in device memory, on the compute stream.
 static void stageInternal(bf_ctx* c, double* dev, int nc, int surface, int kind, double* dst)
 {
@@ -1195,7 +1207,33 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
     }
     if (c->timing) CUDA_OK(c, cudaEventRecord(evs[0], c->stream));
     int nF = c->grid, nB = c->grid; // blocks that wrote the partial sums of the forward / backward part
-    if (c->longMode) {
+    if (c->nPairs) { // coupled bundle: cell-parallel assembly, couplings, BiCGStab preconditioned by the per-beam solve, cell-parallel update
+        LongParams q;
+        memset(&q, 0, sizeof q);
+        q.N = c->N; q.cellBeam = c->d_cellBeam; q.cellStart = c->d_cellStart; q.X = c->d_longX;
+        q.L0 = c->d_longRows[8]; q.D0 = c->d_longRows[9]; q.U0 = c->d_longRows[10]; q.R0 = c->d_longRows[11];
+        CoupledParams cq;
+        cq.N = c->N; cq.B = (int)c->B; cq.cellStart = c->d_cellStart; cq.cellBeam = c->d_cellBeam;
+        cq.adjPtr = c->d_adjPtr; cq.adjCol = c->d_adjCol; cq.adjK = c->d_adjK;
+        cq.L = q.L0; cq.D = q.D0; cq.U = q.U0; cq.R = q.R0; cq.Dinv = c->d_cplDinv; cq.UP = c->d_cplUP;
+        const int gb = (int)((c->N + 127) / 128);
+        if (c->scheme == BF_SCHEME_NEWMARK) long_assemble<BFK_NEWMARK><<<gb, 128, 0, c->stream>>>(p, q);
+        else if (c->scheme == BF_SCHEME_EULER) long_assemble<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
+        else long_assemble<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
+        cpl_add_couplings<<<gb, 128, 0, c->stream>>>(p, cq);
+        c->launches += 2;
+        if (int rc = solveCoupled(c, cq)) return rc;
+        // ||source||^2 of the coupled system (the assembly's partial sums do not contain the spring forces)
+        cpl_dots<<<1, 256, 0, c->stream>>>(6 * c->N, cq.R, cq.R, nullptr, nullptr, nullptr, nullptr, nullptr, c->d_hlin);
+        cpl_set_partial0<<<1, 256, 0, c->stream>>>(c->d_partial, gb, c->d_hlin);
+        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
+        long_update_faces<<<gb, 128, 0, c->stream>>>(p, q);
+        if (c->scheme == BF_SCHEME_NEWMARK) long_update_cells<BFK_NEWMARK><<<gb, 128, 0, c->stream>>>(p, q);
+        else if (c->scheme == BF_SCHEME_EULER) long_update_cells<BFK_EULER><<<gb, 128, 0, c->stream>>>(p, q);
+        else long_update_cells<BFK_STEADY><<<gb, 128, 0, c->stream>>>(p, q);
+        c->launches += 4;
+        nF = nB = gb;
+    } else if (c->longMode) {
         nF = nB = c->longBlocks; // one thread per cell: assemble, block cyclic reduction, update
         LongParams q;
         q.N = c->N; q.cellBeam = c->d_cellBeam; q.cellStart = c->d_cellStart; q.X = c->d_longX;
@@ -1292,6 +1330,117 @@ extern "C" int bf_newton_iteration(bf_ctx* c, double sumsq[3])
     int rc = launchIteration(c);
     if (rc) return rc;
     return fetchSums(c, sumsq);
+}
+
+// ---- coupled bundles: bf_set_couplings, the BiCGStab loop (myBlockBiCGStabSolver.C:79-189) ---------------------------------
+extern "C" int bf_set_couplings(bf_ctx* c, int64_t nPairs, const int64_t* cellA, const int64_t* cellB, const double* stiffness)
+{
+    if (nPairs < 0 || (nPairs > 0 && (!cellA || !cellB || !stiffness))) return fail(c, BF_ERR_INVALID, "bf_set_couplings: bad argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    c->nPairs = 0;
+    if (!nPairs) return BF_OK;
+    const size_t N = (size_t)c->N;
+    std::vector<int64_t> ptr(N + 1, 0), col(2 * (size_t)nPairs), fill(N, 0);
+    std::vector<double> kv(2 * (size_t)nPairs);
+    for (int64_t p = 0; p < nPairs; p++) {
+        if (cellA[p] < 0 || cellA[p] >= c->N || cellB[p] < 0 || cellB[p] >= c->N || cellA[p] == cellB[p])
+            return fail(c, BF_ERR_INVALID, "bf_set_couplings: pair %lld out of range", (long long)p);
+        ptr[cellA[p] + 1]++; ptr[cellB[p] + 1]++;
+    }
+    for (size_t g = 0; g < N; g++) ptr[g + 1] += ptr[g];
+    for (int64_t p = 0; p < nPairs; p++) { // in pair order: the gather of a cell adds its partners in the order the host gave them
+        const int64_t a = cellA[p], b = cellB[p];
+        col[ptr[a] + fill[a]] = b; kv[ptr[a] + fill[a]++] = stiffness[p];
+        col[ptr[b] + fill[b]] = a; kv[ptr[b] + fill[b]++] = stiffness[p];
+    }
+    if (int rc = ensureLongBuffers(c)) return rc;
+    if (!c->d_cplVec) {
+        int rc = devAlloc(c, (void**)&c->d_cplDinv, sizeof(double) * 36 * N);
+        if (!rc) rc = devAlloc(c, (void**)&c->d_cplUP, sizeof(double) * 36 * N);
+        if (!rc) rc = devAlloc(c, (void**)&c->d_cplVec, sizeof(double) * 8 * 6 * N);
+        if (!rc) rc = devAlloc(c, (void**)&c->d_adjPtr, sizeof(int64_t) * (N + 1));
+        if (rc) return rc;
+        CUDA_OK(c, cudaHostAlloc((void**)&c->h_lin, 16 * sizeof(double), cudaHostAllocMapped));
+        CUDA_OK(c, cudaHostGetDevicePointer((void**)&c->d_hlin, c->h_lin, 0));
+    }
+    // the adjacency arrays are re-allocated per call (the pair count may change); the pool frees them with the context
+    if (int rc = devAlloc(c, (void**)&c->d_adjCol, sizeof(int64_t) * col.size())) return rc;
+    if (int rc = devAlloc(c, (void**)&c->d_adjK, sizeof(double) * kv.size())) return rc;
+    CUDA_OK(c, cudaMemcpyAsync(c->d_adjPtr, ptr.data(), sizeof(int64_t) * (N + 1), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_adjCol, col.data(), sizeof(int64_t) * col.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_adjK, kv.data(), sizeof(double) * kv.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->nPairs = nPairs;
+    return BF_OK;
+}
+extern "C" int bf_set_linear_solver(bf_ctx* c, int32_t maxIter, double tolerance, double relTol)
+{
+    if (maxIter < 1 || !(tolerance >= 0) || !(relTol >= 0)) return fail(c, BF_ERR_INVALID, "bf_set_linear_solver: bad argument");
+    c->linMaxIter = maxIter; c->linTol = tolerance; c->linRelTol = relTol;
+    return BF_OK;
+}
+extern "C" int32_t bf_linear_iterations(const bf_ctx* c) { return c->linIterations; }
+
+// Solves (T + C) x = R for the rows assembled in q; x = d_longX.  The loop is the reference's, statement by statement;
+// the scalars live on the host (three synchronisations per iteration: this path is not the tuned one).
+static int solveCoupled(bf_ctx* c, const CoupledParams& q)
+{
+    const int64_t n = 6 * c->N;
+    double *r = c->d_cplVec, *rw = r + n, *pv = r + 2 * n, *ph = r + 3 * n, *v = r + 4 * n, *sv = r + 5 * n, *sh = r + 6 * n, *t = r + 7 * n;
+    double* x = c->d_longX;
+    const unsigned gv = (unsigned)((n + 255) / 256), gc = (unsigned)((c->N + 127) / 128), gb = (unsigned)((c->B + 63) / 64);
+    auto dots = [&](const double* a0, const double* b0, const double* a1, const double* b1, const double* a2, const double* b2, const double* l1) {
+        cpl_dots<<<1, 256, 0, c->stream>>>(n, a0, b0, a1, b1, a2, b2, l1, c->d_hlin);
+        c->launches++;
+        return cudaStreamSynchronize(c->stream);
+    };
+    cpl_factor<<<gb, 64, 0, c->stream>>>(q);
+    CUDA_OK(c, cudaMemsetAsync(x, 0, sizeof(double) * n, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(r, q.R, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream)); // r = b - A x0, x0 = 0
+    CUDA_OK(c, cudaMemcpyAsync(rw, q.R, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(c, cudaMemsetAsync(pv, 0, sizeof(double) * n, c->stream));
+    CUDA_OK(c, cudaMemsetAsync(v, 0, sizeof(double) * n, c->stream));
+    c->launches++;
+    CUDA_OK(c, dots(rw, r, nullptr, nullptr, nullptr, nullptr, r));
+    double norm[6], rho = 1e20, rhoNext = c->h_lin[0];
+    for (int k = 0; k < 6; k++) norm[k] = c->h_lin[3 + k] + 1e-20; // normFactor with x0 = 0: gSum(cmptMag(b)) + small
+    auto measure = [&]() { double m = 0; for (int k = 0; k < 6; k++) if (c->h_lin[3 + k] / norm[k] > m) m = c->h_lin[3 + k] / norm[k]; return m; };
+    const double initial = measure();
+    double final = initial;
+    c->linIterations = 0;
+    auto stop = [&]() { return c->linIterations >= c->linMaxIter || final < c->linTol || (c->linRelTol > 1e-20 && final <= c->linRelTol * initial); };
+    if (!stop()) {
+        double rhoOld, alpha = 0, omega = 1e20, beta;
+        do {
+            rhoOld = rho;
+            rho = rhoNext; // gSumProd(rw, r)
+            beta = rho / rhoOld * (alpha / omega);
+            if (rho == 0) { // restart if breakdown occurs
+                CUDA_OK(c, cudaMemcpyAsync(rw, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+                CUDA_OK(c, dots(rw, r, nullptr, nullptr, nullptr, nullptr, nullptr));
+                rho = c->h_lin[0];
+                alpha = 0; omega = 0; beta = 0;
+            }
+            cpl_update_p<<<gv, 256, 0, c->stream>>>(n, pv, r, v, beta, omega);
+            cpl_precond<<<gb, 64, 0, c->stream>>>(q, pv, ph);
+            cpl_amul<<<gc, 128, 0, c->stream>>>(q, ph, v);
+            CUDA_OK(c, dots(rw, v, nullptr, nullptr, nullptr, nullptr, nullptr));
+            alpha = rho / c->h_lin[0];
+            cpl_update_s<<<gv, 256, 0, c->stream>>>(n, sv, r, v, alpha);
+            cpl_precond<<<gb, 64, 0, c->stream>>>(q, sv, sh);
+            cpl_amul<<<gc, 128, 0, c->stream>>>(q, sh, t);
+            CUDA_OK(c, dots(t, sv, t, t, nullptr, nullptr, nullptr));
+            omega = c->h_lin[0] / c->h_lin[1];
+            cpl_update_xr<<<gv, 256, 0, c->stream>>>(n, x, r, ph, sh, sv, t, alpha, omega);
+            CUDA_OK(c, dots(rw, r, nullptr, nullptr, nullptr, nullptr, r));
+            rhoNext = c->h_lin[0];
+            final = measure();
+            c->linIterations++;
+            c->launches += 7;
+        } while (!stop());
+    }
+    CUDA_OK(c, cudaGetLastError());
+    return BF_OK;
 }
 
 // Diagnostic: one Newton iteration (as bf_newton_iteration) together with the normwise backward error of its linear solve,
@@ -1471,7 +1620,7 @@ extern "C" int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
     // Pipelined loop whenever the sums can be exchanged on the device: a single context, or peers attached with
     // bf_comm_ipc_attach.  A host reducer / NCCL communicator without peer memory, the cell-parallel path and the fused
     // launch keep the host in the loop (one synchronisation per iteration).
-    const bool pipelined = !c->reducer && (!c->comm || c->xRanks > 1) && !c->longMode && (c->splitKernels || c->split || c->coopFwd || c->coopBwd) &&
+    const bool pipelined = !c->reducer && (!c->comm || c->xRanks > 1) && !c->longMode && !c->nPairs && (c->splitKernels || c->split || c->coopFwd || c->coopBwd) &&
                            tol->nCorrectors < CONV_MAXK - 1 && !getenv("BEAMGPU_NO_PIPELINE");
     if (pipelined) return evolvePipelined(c, tol, out);
     int status = BF_OK;

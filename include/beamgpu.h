@@ -275,6 +275,20 @@ int bf_set_bc_values(bf_ctx* ctx, int32_t end, int32_t kind, const double* value
  * bf_get_field(W, ...) + bf_get_field(THETA, ...) for that side. */
 int bf_get_patch_pair(bf_ctx* ctx, int32_t end, double* W, double* Theta);
 
+/* Coupled bundles: inter-beam couplings turn the union of block-tridiagonal systems into ONE block-sparse
+ * system -- the shape of fvBlockMatrices/multibeamFvBlockMatrix/multibeamFvBlockMatrix.C:298-470 (per-beam tridiagonal blocks
+ * plus 6x6 blocks between cells of different beams) -- which is solved by the preconditioned BiCGStab of
+ * numerics/blockLduMatrix/BlockLduSolvers/BlockBiCGStab/myBlockBiCGStabSolver.C:79-189 with the per-beam block-Thomas solve
+ * as the preconditioner.  The reference compiles neither and its contact model is not in its repository, so the coupling is
+ * SYNTHETIC and parity is pinned to the CPU oracle only: pair p is a linear spring of stiffness[p] between the centres of cells
+ * cellA[p] and cellB[p] (indices of this context, createBeamMesh order), force on A = k (W_B - W_A).  nPairs = 0 restores
+ * the uncoupled path.  bf_set_linear_solver: maxIter / tolerance / relTol of the fvSolution solver dictionary
+ * (BlockLduSolver::stop of foam-extend 4.1: cmptMax of the componentwise L1 residual over gSum(cmptMag(b))); defaults
+ * 1000, 1e-13, 0.  bf_linear_iterations: BiCGStab iterations of the last Newton iteration. */
+int bf_set_couplings(bf_ctx* ctx, int64_t nPairs, const int64_t* cellA, const int64_t* cellB, const double* stiffness);
+int bf_set_linear_solver(bf_ctx* ctx, int32_t maxIter, double tolerance, double relTol);
+int32_t bf_linear_iterations(const bf_ctx* ctx);
+
 /* ---- the hot path ---------------------------------------------------------- */
 
 /* The time index advanced (runTime++ of beamFoam.C:73-79): sets deltaT, resets
