@@ -167,45 +167,73 @@ __global__ void __launch_bounds__(128) long_pcr_load(const BeamParams p, const L
 }
 
 // One step of block parallel cyclic reduction with stride q.step.  Row i:  L_i x_{i-s} + D_i x_i + U_i x_{i+s} = R_i.
-// Eliminating x_{i-s} with row i-s and x_{i+s} with row i+s leaves a row that couples x_i to x_{i-2s}, x_{i+2s}.
-__global__ void __launch_bounds__(128) long_pcr_step(const BeamParams p, const LongParams q)
+// Eliminating x_{i-s} with row i-s and x_{i+s} with row i+s leaves a row that couples x_i to x_{i-2s}, x_{i+2s}:
+//     D_i <- D_i - L_i Z^-_U - U_i Z^+_L,   L_i <- -L_i Z^-_L,   U_i <- -U_i Z^+_U,   R_i <- R_i - L_i z^-_R - U_i z^+_R
+// with Z^- = D_{i-s}^{-1} [L | U | R]_{i-s} and Z^+ the same of row i+s.
+// SEVEN threads per row, one per COLUMN: thread c < 6 owns column c of the new L_i, D_i, U_i, thread 6 the right-hand side.
+// Every thread factors the two neighbour diagonal blocks itself (pivoted 6x6, in registers) and solves only for its own
+// columns, so the step is 7 N light threads instead of N heavy ones with 300 doubles of local arrays each (round 1: 70 us
+// per step for 10^4 cells, latency-bound on local memory).
+// Elimination of the coupling of row g to row h (SIDE 0: h = g - s through L_g, 1: h = g + s through U_g) for the thread's column c.
+template <int SIDE>
+DEV void pcrEliminateSide(const double* __restrict__ Din, const double* __restrict__ Lin, const double* __restrict__ Uin,
+                          const double* __restrict__ Rin, const int64_t g, const int64_t h, const bool exists, const int c,
+                          double (&colD)[6], double (&colL)[6], double (&colU)[6])
 {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!exists) return;
+    double A[6][6], Z[6][2]; // Z = D_h^{-1} [column c of L_h | column c of U_h]   (thread 6: [R_h | 0])
+    const int cc = c < 6 ? c : 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) A[r][k] = Din[36 * h + 6 * r + k];
+        const double lv = Lin[36 * h + 6 * r + cc], uv = Uin[36 * h + 6 * r + cc], rv = Rin[6 * h + r];
+        Z[r][0] = c < 6 ? lv : rv;
+        Z[r][1] = c < 6 ? uv : 0.0;
+    }
+    solve6reg<2>(A, Z);
+    const double* C = (SIDE ? Uin : Lin) + 36 * g; // the coupling of row g to row h
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) { const double ck = C[6 * r + k]; a0 = fma(ck, Z[k][0], a0); a1 = fma(ck, Z[k][1], a1); }
+        if (SIDE) { colD[r] -= a0; colU[r] = c < 6 ? -a1 : 0.0; }   // row g+s couples back to x_g through its L (thread 6: R_g -= C z_R)
+        else { colD[r] -= c < 6 ? a1 : a0; colL[r] = c < 6 ? -a0 : 0.0; } // row g-s couples back to x_g through its U
+    }
+}
+
+#define PCR_COLS 7
+__global__ void __launch_bounds__(64, 8) long_pcr_step(const BeamParams p, const LongParams q)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t g = t / PCR_COLS;
+    const int c = (int)(t - g * PCR_COLS);
     if (g >= q.N) return;
     const int b = q.cellBeam[g];
     const int i = (int)(g - q.cellStart[b]), n = p.nSeg[b], s = q.step, in = q.src, out = 1 - q.src;
-    double D[36], L[36], U[36], R[6], nL[36], nU[36];
-    for (int k = 0; k < 36; k++) { D[k] = q.D[in][36 * g + k]; L[k] = q.L[in][36 * g + k]; U[k] = q.U[in][36 * g + k]; nL[k] = nU[k] = 0.0; }
-    for (int k = 0; k < 6; k++) R[k] = q.R[in][6 * g + k];
-    for (int side = 0; side < 2; side++) {
-        const int j = side ? i + s : i - s;
-        if (j < 0 || j >= n) continue;
-        const int64_t h = side ? g + s : g - s;
-        double A[36], Z[6 * 13]; // Z = D_j^{-1} [L_j | U_j | R_j]
-        for (int r = 0; r < 6; r++) {
-            for (int c = 0; c < 6; c++) {
-                A[6 * r + c] = q.D[in][36 * h + 6 * r + c];
-                Z[13 * r + c] = q.L[in][36 * h + 6 * r + c];
-                Z[13 * r + 6 + c] = q.U[in][36 * h + 6 * r + c];
-            }
-            Z[13 * r + 12] = q.R[in][6 * h + r];
-        }
-        luSolve6(A, Z, 13);
-        const double* C = side ? U : L; // the coupling of row i to row j
-        for (int r = 0; r < 6; r++) {
-            for (int c = 0; c < 6; c++) {
-                double aL = 0.0, aU = 0.0;
-                for (int k = 0; k < 6; k++) { aL += C[6 * r + k] * Z[13 * k + c]; aU += C[6 * r + k] * Z[13 * k + 6 + c]; }
-                if (side) { D[6 * r + c] -= aL; nU[6 * r + c] = -aU; } // row i+s couples back to x_i through its L
-                else { D[6 * r + c] -= aU; nL[6 * r + c] = -aL; }      // row i-s couples back to x_i through its U
-            }
-            double aR = 0.0;
-            for (int k = 0; k < 6; k++) aR += C[6 * r + k] * Z[13 * k + 12];
-            R[r] -= aR;
-        }
+    const double *Din = q.D[in], *Lin = q.L[in], *Uin = q.U[in], *Rin = q.R[in];
+    double colD[6], colL[6], colU[6];
+    if (c < 6) {
+#pragma unroll
+        for (int r = 0; r < 6; r++) { colD[r] = Din[36 * g + 6 * r + c]; colL[r] = 0.0; colU[r] = 0.0; }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 6; r++) { colD[r] = Rin[6 * g + r]; colL[r] = 0.0; colU[r] = 0.0; }
     }
-    for (int k = 0; k < 36; k++) { q.D[out][36 * g + k] = D[k]; q.L[out][36 * g + k] = nL[k]; q.U[out][36 * g + k] = nU[k]; }
-    for (int k = 0; k < 6; k++) q.R[out][6 * g + k] = R[k];
+    pcrEliminateSide<0>(Din, Lin, Uin, Rin, g, g - s, i - s >= 0, c, colD, colL, colU);
+    pcrEliminateSide<1>(Din, Lin, Uin, Rin, g, g + s, i + s < n, c, colD, colL, colU);
+    if (c < 6) {
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            q.D[out][36 * g + 6 * r + c] = colD[r];
+            q.L[out][36 * g + 6 * r + c] = colL[r];
+            q.U[out][36 * g + 6 * r + c] = colU[r];
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 6; r++) q.R[out][6 * g + r] = colD[r];
+    }
 }
 
 __global__ void __launch_bounds__(128) long_pcr_finish(const LongParams q)

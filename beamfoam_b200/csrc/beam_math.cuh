@@ -483,6 +483,68 @@ DEV void solve6(double (&A)[6][6], double (&B)[6][NR])
     }
 }
 
+// The same solve for code that must stay in registers: nvcc recognises "find the pivot row p, then exchange rows k and p"
+// and indexes the arrays with the run-time p, which sends them to local memory (fine in the out-of-line fallbacks that use
+// solve6, ruinous in a kernel whose whole work is this solve).  Here the largest pivot is bubbled up instead: row k is
+// compared with each row below it in turn and exchanged when that one has the larger entry, so every select depends on
+// values only.  The permutation differs from solve6's, the pivot (the largest entry of the column) does not.
+// (The pivot steps are template-recursive: with "#pragma unroll" alone nvcc re-rolls the outer loop of this size and
+// walks the rows through a pointer into local memory.)
+template <int NR, int K>
+DEV void solve6regStep(double (&A)[6][6], double (&B)[6][NR], double (&piv)[6])
+{
+    if constexpr (K < 6) {
+#pragma unroll
+        for (int r = K + 1; r < 6; r++) {
+            const bool sw = fabs(A[r][K]) > fabs(A[K][K]);
+#pragma unroll
+            for (int c = K; c < 6; c++) {
+                const double t0 = A[K][c], t1 = A[r][c];
+                A[K][c] = sw ? t1 : t0;
+                A[r][c] = sw ? t0 : t1;
+            }
+#pragma unroll
+            for (int c = 0; c < NR; c++) {
+                const double t0 = B[K][c], t1 = B[r][c];
+                B[K][c] = sw ? t1 : t0;
+                B[r][c] = sw ? t0 : t1;
+            }
+        }
+        const double ip = rcpFast(A[K][K]);
+        piv[K] = ip;
+#pragma unroll
+        for (int r = K + 1; r < 6; r++) {
+            const double m = A[r][K] * ip;
+#pragma unroll
+            for (int c = K + 1; c < 6; c++) A[r][c] -= m * A[K][c];
+#pragma unroll
+            for (int c = 0; c < NR; c++) B[r][c] -= m * B[K][c];
+        }
+        solve6regStep<NR, K + 1>(A, B, piv);
+    }
+}
+template <int NR, int K>
+DEV void solve6regBack(double (&A)[6][6], double (&B)[6][NR], const double (&piv)[6])
+{
+    if constexpr (K >= 0) {
+#pragma unroll
+        for (int c = 0; c < NR; c++) {
+            double s = B[K][c];
+#pragma unroll
+            for (int j = K + 1; j < 6; j++) s -= A[K][j] * B[j][c];
+            B[K][c] = s * piv[K];
+        }
+        solve6regBack<NR, K - 1>(A, B, piv);
+    }
+}
+template <int NR>
+DEV void solve6reg(double (&A)[6][6], double (&B)[6][NR])
+{
+    double piv[6];
+    solve6regStep<NR, 0>(A, B, piv);
+    solve6regBack<NR, 5>(A, B, piv);
+}
+
 // ---------------------------------------------------------------------------
 // 6x6 solve by 2x2 block elimination over 3x3 blocks, D = [[A, B], [C, E]]:
 //   X2 = S^{-1} (R2 - C A^{-1} R1),  X1 = A^{-1} R1 - A^{-1} B X2,  S = E - C A^{-1} B,

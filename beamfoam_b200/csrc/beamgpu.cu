@@ -1250,7 +1250,7 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
             long_pcr_load<<<gb, 128, 0, c->stream>>>(p, q);
             for (int s = 1; s < c->nmax; s *= 2) {
                 q.step = s;
-                long_pcr_step<<<gb, 128, 0, c->stream>>>(p, q);
+                long_pcr_step<<<(unsigned)((c->N * PCR_COLS + 63) / 64), 64, 0, c->stream>>>(p, q);
                 q.src = 1 - q.src;
                 c->launches++;
             }
