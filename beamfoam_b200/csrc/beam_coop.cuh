@@ -501,6 +501,63 @@ __global__ void __launch_bounds__(BS_THREADS) beam_backsub(const BeamParams p, d
     }
 }
 
+// The same after a SPLIT forward sweep (beam_forward_split: the left half eliminated left to right, the mirrored half right
+// to left): two threads per beam, grid (ceil(B / BS_THREADS), 2).  Both solve the 6x6 interface system (splitInterface), then
+// the left half substitutes outwards to cell 0, x_i = bPrime_i - uPrime_i x_{i+1}, and the mirrored half to cell n-1,
+// x_i = bPrime_i - uPrime_i x_{i-1}.  Uniform bundles (every beam nmax cells).
+__global__ void __launch_bounds__(BS_THREADS) beam_backsub_split(const BeamParams p, double* __restrict__ X)
+{
+    extern __shared__ __align__(16) unsigned char bs_smem[];
+    if (convLeave(p.cv, true)) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.x * BS_THREADS + threadIdx.x;
+    const bool mir = blockIdx.y != 0;
+    const size_t T = (size_t)(b >> 5);
+    const int Rc = p.nmax, n = p.nmax, hL = (n + 1) / 2;
+    const bool live = b < p.B;
+    const int m = mir ? n - hL : hL; // steps of this half; step k visits cell hL + k (mirrored) or hL - 1 - k
+    double* ring = (double*)bs_smem + (size_t)w * BS_RING * 42 * 32 + lane;
+    auto cellOf = [&](int k) { return mir ? hL + k : hL - 1 - k; };
+    auto issue = [&](int k) { // rows of step k -> ring slot k % BS_RING (own column only: no barrier needed)
+        if (live && k >= 1 && k < m) { // step 0 takes its x from the interface solve
+            const int i = cellOf(k);
+            double* dst = ring + (size_t)(k % BS_RING) * 42 * 32;
+            const double* u = p.uP + tileRow(T, Rc, i, 36, lane);
+            const double* bb = p.bP + tileRow(T, Rc, i, 6, lane);
+#pragma unroll
+            for (int r = 0; r < 36; r++) cpAsync8(dst + r * 32, u + (size_t)r * TS);
+#pragma unroll
+            for (int r = 0; r < 6; r++) cpAsync8(dst + (36 + r) * 32, bb + (size_t)r * TS);
+        }
+        cpAsyncCommit();
+    };
+    for (int d = 0; d < BS_RING - 1; d++) issue(d);
+    double xL[6], xR[6], xn[6];
+    if (live) splitInterface(p, T, lane, hL, xL, xR);
+    for (int k = 0; k < m; k++) {
+        issue(k + BS_RING - 1);
+        cpAsyncWaitGroup<BS_RING - 1>();
+        if (!live) continue;
+        double x[6];
+        if (k == 0) {
+#pragma unroll
+            for (int r = 0; r < 6; r++) x[r] = mir ? xR[r] : xL[r];
+        } else {
+            const double* src = ring + (size_t)(k % BS_RING) * 42 * 32;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc += src[(6 * r + c) * 32] * xn[c];
+                x[r] = src[(36 + r) * 32] - acc;
+            }
+        }
+        double* o = X + tileRow(T, Rc, cellOf(k), 6, lane);
+#pragma unroll
+        for (int r = 0; r < 6; r++) { xn[r] = x[r]; o[(size_t)r * TS] = x[r]; }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // backward, parallel part: one thread per (tile, cell, lane) = per cell of the bundle, beams fastest (coalesced rows).
 // ---------------------------------------------------------------------------------------------------------------------
@@ -521,7 +578,10 @@ DEV void ldX(const double* __restrict__ X, size_t T, int Rc, int i, int lane, V3
     c = v3(X[x0 + 3 * TS], X[x0 + 4 * TS], X[x0 + 5 * TS]);
 }
 // Faces first: they read the neighbour cell's pre-update W ...
-__global__ void __launch_bounds__(128) beam_update_faces(const BeamParams p, const double* __restrict__ X)
+#ifndef BEAM_FACES_MIN_BLOCKS
+#define BEAM_FACES_MIN_BLOCKS 3 // 168 registers: 12 warps per SM; measured 6 % faster than 2 (255 registers) or 4 (128, spills) at 4096 beams
+#endif
+__global__ void __launch_bounds__(128, BEAM_FACES_MIN_BLOCKS) beam_update_faces(const BeamParams p, const double* __restrict__ X)
 {
     if (convLeave(p.cv, true)) return;
     int b, i;

@@ -119,6 +119,12 @@ DEV void stS(double* p, double v) { *p = v; }
 #else
 DEV void stS(double* p, double v) { __stcs(p, v); }
 #endif
+// scratch written by the forward launch, read by the backward launch: through L2 (BEAM_SCRATCH_L1: through L1 as well)
+#ifdef BEAM_SCRATCH_L1
+DEV double ldScratch(const double* p) { return *p; }
+#else
+DEV double ldScratch(const double* p) { return __ldcg(p); }
+#endif
 DEV V3 ld3(const double* __restrict__ p, size_t i, size_t s) { return v3(p[i], p[i + s], p[i + 2 * s]); }
 DEV void st3(double* __restrict__ p, size_t i, size_t s, V3 v) { stS(p + i, v.x); stS(p + i + s, v.y); stS(p + i + 2 * s, v.z); }
 DEV M3 ld9(const double* __restrict__ p, size_t i, size_t s)
@@ -1497,14 +1503,14 @@ DEV void backwardSweep(const BeamParams& p, const int b, double& dx2, double& x2
             }
             double x[6];
 #pragma unroll
-            for (int r = 0; r < 6; r++) x[r] = __ldcg(p.bP + b0 + (size_t)r * s); // written by another SM in this launch: L2
+            for (int r = 0; r < 6; r++) x[r] = ldScratch(p.bP + b0 + (size_t)r * s); // written by another SM in this launch: L2
             if (i < n - 1) {
                 const double xn[6] = {xWn.x, xWn.y, xWn.z, xTn.x, xTn.y, xTn.z};
 #pragma unroll
                 for (int r = 0; r < 6; r++) {
                     double acc = 0.0;
 #pragma unroll
-                    for (int c = 0; c < 6; c++) acc += __ldcg(p.uP + u0 + (size_t)(6 * r + c) * s) * xn[c];
+                    for (int c = 0; c < 6; c++) acc += ldScratch(p.uP + u0 + (size_t)(6 * r + c) * s) * xn[c];
                     x[r] -= acc;
                 }
             }
@@ -1754,8 +1760,8 @@ DEV void backwardSweepSplit(const BeamParams& p, const int b, double& dx2, doubl
             for (int r = 0; r < 6; r++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int c = 0; c < 6; c++) acc += __ldcg(p.uP + u0 + (size_t)(6 * r + c) * s) * xn[c];
-                x[r] = __ldcg(p.bP + b0 + (size_t)r * s) - acc;
+                for (int c = 0; c < 6; c++) acc += ldScratch(p.uP + u0 + (size_t)(6 * r + c) * s) * xn[c];
+                x[r] = ldScratch(p.bP + b0 + (size_t)r * s) - acc;
             }
         }
         const V3 DW = v3(x[0], x[1], x[2]), DT = v3(x[3], x[4], x[5]);

@@ -148,7 +148,7 @@ extern "C" int64_t bf_num_cells(const bf_ctx* c) { return c->N; }
 extern "C" int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
 extern "C" int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
 extern "C" int64_t bf_launch_count(const bf_ctx* c) { return c->launches; }
-extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return (c->longMode || c->nPairs) ? BF_FAMILY_CELL : c->split ? BF_FAMILY_SPLIT : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
+extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return (c->longMode || c->nPairs) ? BF_FAMILY_CELL : (c->split && c->coopBwd) ? BF_FAMILY_SPLIT_CELL : c->split ? BF_FAMILY_SPLIT : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
 
 extern "C" int bf_host_alloc(void** p, int64_t bytes)
 {
@@ -460,6 +460,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_backsub_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
@@ -571,8 +572,10 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
                 if (!strcmp(e, "fwd")) { c->coopFwd = 1; c->coopBwd = 0; }
                 else if (!strcmp(e, "bwd")) { c->coopFwd = 0; c->coopBwd = 1; }
                 else c->coopFwd = c->coopBwd = atoi(e) ? 1 : 0;
-                if (c->coopFwd || c->coopBwd) c->split = 0;
+                if (c->coopFwd) c->split = 0;
             }
+            // small uniform bundles: the split forward sweep with the cell-parallel backward sweep (measured fastest below ~5k beams)
+            if (c->split && !getenv("BEAMGPU_COOP")) c->coopBwd = B < 5120 ? 1 : 0;
         }
         c->d_X = nullptr;
         if (c->coopBwd && devAlloc(c, (void**)&c->d_X, sizeof(double) * 6 * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
@@ -1267,9 +1270,20 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
         const dim3 g2((unsigned)c->grid, 2);
         LAUNCH_SCHEME(beam_forward_split, g2, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
-        LAUNCH_SCHEME(beam_backward_split, g2, 0, p);
-        c->launches += 2;
         nF = nB = 2 * c->grid;
+        if (c->coopBwd) { // small bundles: serial back-substitution of the two halves, then the update with one thread per cell
+            const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
+            const dim3 gs((unsigned)((c->Bpad + BS_THREADS - 1) / BS_THREADS), 2);
+            beam_backsub_split<<<gs, BS_THREADS, BS_SMEM_BYTES, c->stream>>>(p, c->d_X);
+            beam_update_faces<<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            if (c->scheme == BF_SCHEME_NEWMARK) beam_update_cells<BFK_NEWMARK><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            else if (c->scheme == BF_SCHEME_EULER) beam_update_cells<BFK_EULER><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            else beam_update_cells<BFK_STEADY><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            c->launches += 2;
+            nB = cellGrid;
+        } else
+            LAUNCH_SCHEME(beam_backward_split, g2, 0, p);
+        c->launches += 2;
     } else if (c->splitKernels || c->coopFwd || c->coopBwd) { // product path: one launch per sweep
         if (c->coopFwd) LAUNCH_SCHEME_T(beam_forward_ws, c->coopGrid, WS_THREADS, WS_SMEM_BYTES, p);
         else LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);

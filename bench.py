@@ -53,8 +53,10 @@ HBM_FALLBACK_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallbac
 FAMILY = {0: "one thread per beam (beam_forward / beam_backward)",
           1: "assembler + eliminator warps (beam_forward_ws), serial back-substitution + one thread per cell (beam_backsub, beam_update_*)",
           2: "one thread per cell, block cyclic reduction (long_*)",
-          3: "two threads per beam meeting in the middle (beam_forward_split / beam_backward_split)", -1: "cpu"}
-FAMILY_ENV = {0: ("0", "0"), 1: ("1", "0"), 3: ("0", "1")}  # BEAMGPU_COOP, BEAMGPU_SPLIT that force a family
+          3: "two threads per beam meeting in the middle (beam_forward_split / beam_backward_split)",
+          4: "two threads per beam in the forward sweep (beam_forward_split), serial back-substitution + one thread per cell "
+             "(beam_backsub_split, beam_update_*)", -1: "cpu"}
+FAMILY_ENV = {0: ("0", "0"), 1: ("1", "0"), 3: ("0", "1"), 4: ("bwd", "1")}  # BEAMGPU_COOP, BEAMGPU_SPLIT that force a family
 CONFIGS = {
     "bundle65536": dict(beams=65536, cells=200, baseline="configs[3]"),
     "bundle4096": dict(beams=4096, cells=200, baseline="configs[2]"),
@@ -567,8 +569,9 @@ def run_ours(args):
     peak, peak_src = hbm_peak()
     achieved = bpu * nCellsLocal / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     names = {0: ("beam_forward", "beam_backward"), 1: ("beam_forward_ws", "beam_backsub + beam_update_faces + beam_update_cells"),
-             2: ("long_assemble + long_pcr_*", "long_update_*"), 3: ("beam_forward_split", "beam_backward_split")}[main.family]
-    tj = load_traffic({0: "per_beam", 1: "group", 2: "cell", 3: "split"}[main.family])
+             2: ("long_assemble + long_pcr_*", "long_update_*"), 3: ("beam_forward_split", "beam_backward_split"),
+             4: ("beam_forward_split", "beam_backsub_split + beam_update_faces + beam_update_cells")}[main.family]
+    tj = load_traffic({0: "per_beam", 1: "group", 2: "cell", 3: "split", 4: "split_cell"}[main.family])
     traffic, per_kernel, fp64 = None, None, None
     if tj:
         scale = nCellsLocal / float(tj["cells_per_launch"])

@@ -13,9 +13,9 @@ lib = load_library()
 cells = int(os.environ.get("CELLS", "200"))
 for nb in map(int, sys.argv[1:]):
     case = cases.multiBeamDensity(nb, cells, jitter=True)
-    for mode in os.environ.get("MODES", "0,1,s").split(","):  # 0 per beam, 1 group (warp-specialised), s split
-        os.environ["BEAMGPU_COOP"] = "0" if mode == "s" else mode
-        os.environ["BEAMGPU_SPLIT"] = "1" if mode == "s" else "0"
+    for mode in os.environ.get("MODES", "0,1,s,sc").split(","):  # 0 per beam, 1 group (warp-specialised), s split, sc split + cell-parallel backward
+        os.environ["BEAMGPU_COOP"] = {"s": "0", "sc": "bwd"}.get(mode, mode)
+        os.environ["BEAMGPU_SPLIT"] = "1" if mode in ("s", "sc") else "0"
         m = coupledTotalLagNewtonRaphsonBeam(case, library=lib, storeIncrements=False)
         m.updateCoeffs(case.deltaT)
         its = []

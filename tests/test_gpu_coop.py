@@ -20,7 +20,8 @@ from test_gpu_parity import run_pair
 pytestmark = pytest.mark.gpu
 
 # family -> (BEAMGPU_COOP, BEAMGPU_SPLIT)
-MODES = {"per_beam": ("0", "0"), "group": ("1", "0"), "group_fwd": ("fwd", "0"), "group_bwd": ("bwd", "0"), "split": ("0", "1")}
+MODES = {"per_beam": ("0", "0"), "group": ("1", "0"), "group_fwd": ("fwd", "0"), "group_bwd": ("bwd", "0"), "split": ("0", "1"),
+         "split_cell": ("bwd", "1")}
 
 
 def set_family(name):
@@ -99,13 +100,13 @@ def test_families_agree_at_4096_beams(gpu_lib):
     order)."""
     case = cases.multiBeamDensity(4096, 200, jitter=True)
     out = {}
-    for mode in ("per_beam", "group", "split"):
+    for mode in ("per_beam", "group", "split", "split_cell"):
         set_family(mode)
         m = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib, storeIncrements=False)
         out[mode] = (m.run(nSteps=4), m.tip(1))
         m.close()
     clear_family()
-    for mode in ("group", "split"):
+    for mode in ("group", "split", "split_cell"):
         assert out["per_beam"][0] == out[mode][0], mode
         for a, b in zip(out["per_beam"][1], out[mode][1]):
             assert np.max(np.abs(a - b)) <= 1e-11 * np.max(np.abs(b)), mode

@@ -65,7 +65,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("family", ["per_beam", "group", "split"])
+@pytest.mark.parametrize("family", ["per_beam", "group", "split", "split_cell"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_adversarial_case(gpu_lib, oracle_lib, name, family):
     mk, steps, tol = CASES[name]
