@@ -24,6 +24,9 @@ OUTPUT = os.path.join(HERE, "libbeamgpu.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v",
+    # the shared CUDA runtime (libcudart.so.12 is in the loader path of this image, rpath as a second source): the static
+    # runtime would embed every runtime entry point's name in the shipped .so, used or not
+    "--cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64",
 ]
 
 
