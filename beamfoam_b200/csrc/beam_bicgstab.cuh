@@ -33,7 +33,7 @@ struct CoupledParams {
     double *Dinv, *UP;         // the factors of the block-tridiagonal part
 };
 
-__global__ void cpl_add_couplings(const BeamParams p, const CoupledParams q)
+__global__ void cpl_add_couplings(const __grid_constant__ BeamParams p, const CoupledParams q)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= q.N || q.adjPtr[g] == q.adjPtr[g + 1]) return;

@@ -141,7 +141,7 @@ DEV void cellSplineAndVelocity(const BeamParams& p, const ContribParams& cp, con
 }
 
 template <int SCHEME>
-__global__ void beam_momentum_contributions(const BeamParams p, const ContribParams cp)
+__global__ void beam_momentum_contributions(const __grid_constant__ BeamParams p, const ContribParams cp)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = (int)(g & 31);

@@ -50,6 +50,7 @@
 #define CONV_MAX_RANKS 16
 struct ConvCtl {
     const double* xbuf; // this rank's bank of the exchange buffer; null: the host decides (bf_newton_iteration, reducer callback)
+    double* vflag;      // [CONV_MAXK] verdict cache of this bank: tag + 0.5 = the loop ended with (or before) iteration k, tag + 0.25 = it goes on
     int nRanks, iter;   // iter: the Newton iteration the launch belongs to
     double tag;
     double absTol, resTol, solTol, divTol;
@@ -389,7 +390,21 @@ DEV bool convLeave(const ConvCtl& c, const bool wait)
 {
     if (!c.xbuf || c.iter == 0) return false;
     __shared__ int sLeave;
-    if (threadIdx.x == 0) sLeave = convDecide(c, c.iter - 1, wait) == 1;
+    if (threadIdx.x == 0) {
+        // The verdict on iteration k is the same for whoever computes it: the first block that has all the records caches it,
+        // the thousands of short-lived blocks of the cell-parallel kernels then pay one L2 load instead of 4 nRanks (+ 4 nRanks
+        // for the initial residual) system-scope loads each.
+        volatile double* vf = c.vflag + (c.iter - 1);
+        const double v = *vf;
+        int d;
+        if (v == c.tag + 0.5) d = 1;
+        else if (v == c.tag + 0.25) d = 0;
+        else {
+            d = convDecide(c, c.iter - 1, wait);
+            if (d >= 0) *vf = c.tag + (d == 1 ? 0.5 : 0.25);
+        }
+        sLeave = d == 1;
+    }
     __syncthreads();
     return sLeave != 0;
 }
@@ -1541,7 +1556,7 @@ DEV uint32_t warpBarrierSetup(unsigned char* smem)
 #define WARP_SLAB(smem, w) ((double*)((smem) + SMEM_HEADER_BYTES) + (size_t)(w) * WARP_SMEM_DOUBLES)
 
 template <int SCHEME>
-__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton(const __grid_constant__ BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
     const int b = blockIdx.x * blockDim.x + threadIdx.x, w = threadIdx.x >> 5;
@@ -1553,7 +1568,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_newton(con
     blockReduceStore<3>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
 template <int SCHEME>
-__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(const __grid_constant__ BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
     if (convLeave(p.cv, false)) return;
@@ -1564,7 +1579,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward(co
     blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.x);
 }
 template <int SCHEME>
-__global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backward(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backward(const __grid_constant__ BeamParams p)
 {
     if (convLeave(p.cv, true)) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1782,7 +1797,7 @@ DEV void backwardSweepSplit(const BeamParams& p, const int b, double& dx2, doubl
 
 // grid (ceil(B / BEAM_THREADS), 2): blockIdx.y = 0 the left halves, 1 the mirrored halves
 template <int SCHEME>
-__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward_split(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward_split(const __grid_constant__ BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
     if (convLeave(p.cv, false)) return;
@@ -1796,7 +1811,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward_sp
     blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.y * gridDim.x + blockIdx.x);
 }
 template <int SCHEME>
-__global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backward_split(const BeamParams p)
+__global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backward_split(const __grid_constant__ BeamParams p)
 {
     if (convLeave(p.cv, true)) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1809,7 +1824,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backwa
 }
 
 // Source contribution of the point forces for every cell of every beam (one thread per beam, its cells in turn).
-__global__ void beam_point_forces(const BeamParams p)
+__global__ void beam_point_forces(const __grid_constant__ BeamParams p)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.B) return;
@@ -1827,7 +1842,7 @@ __global__ void beam_point_forces(const BeamParams p)
 // strains Gamma, K (0.5 L[own] on internal faces, 0.25 L[cell] on the end faces) and the linear / angular kinetic
 // energy of the cells, straight from the device state.  One thread per beam; out[3 b + k].
 template <int SCHEME>
-__global__ void beam_energy(const BeamParams p, double* __restrict__ out)
+__global__ void beam_energy(const __grid_constant__ BeamParams p, double* __restrict__ out)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.B) return;

@@ -72,7 +72,7 @@ DEV void putBlk(double (&D)[6][6], int r0, int c0, double s, const M3& T)
 }
 
 template <int SCHEME>
-__global__ void __launch_bounds__(128) long_assemble(const BeamParams p, const LongParams q)
+__global__ void __launch_bounds__(128) long_assemble(const __grid_constant__ BeamParams p, const LongParams q)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double v[1] = {0.0};
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128) long_assemble(const BeamParams p, const L
 }
 
 // Rows into working copy 0; right-hand side = source (first pass) or source - A x (refinement pass).
-__global__ void __launch_bounds__(128) long_pcr_load(const BeamParams p, const LongParams q)
+__global__ void __launch_bounds__(128) long_pcr_load(const __grid_constant__ BeamParams p, const LongParams q)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= q.N) return;
@@ -204,7 +204,7 @@ DEV void pcrEliminateSide(const double* __restrict__ Din, const double* __restri
 }
 
 #define PCR_COLS 7
-__global__ void __launch_bounds__(64, 8) long_pcr_step(const BeamParams p, const LongParams q)
+__global__ void __launch_bounds__(64, 8) long_pcr_step(const __grid_constant__ BeamParams p, const LongParams q)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t g = t / PCR_COLS;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128) long_pcr_finish(const LongParams q)
 }
 
 // Faces first (they read the neighbour cell's pre-update W) ...
-__global__ void __launch_bounds__(128) long_update_faces(const BeamParams p, const LongParams q)
+__global__ void __launch_bounds__(128) long_update_faces(const __grid_constant__ BeamParams p, const LongParams q)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= q.N) return;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128) long_update_faces(const BeamParams p, con
 }
 // ... then the cells, and the two solution norms.
 template <int SCHEME>
-__global__ void __launch_bounds__(128) long_update_cells(const BeamParams p, const LongParams q)
+__global__ void __launch_bounds__(128) long_update_cells(const __grid_constant__ BeamParams p, const LongParams q)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};

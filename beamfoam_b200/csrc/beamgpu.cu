@@ -47,6 +47,8 @@ struct bf_ctx {
     int Bpad, nmax, grid;
     // bundles below one wave of beams: group-cooperative kernels (beam_coop.cuh), selectable per sweep
     int coopFwd, coopBwd, coopGrid;
+    int wsBpb; // beams (half beams with split) per block of beam_forward_ws: 16 (two eliminator lanes per beam) or 32 (one)
+    int wsEw;  // eliminator warps per block: 1, or 2 (wsBpb = 32: the two column groups of a beam in two warps)
     int split; // two threads per beam (beam_forward_split / beam_backward_split): uniform bundles between the two other families
     double* d_ifW;
     double* d_X; // coopBwd: the solution increments, tiled [tile][nmax][6][32] (beam_backsub -> beam_update_*)
@@ -104,6 +106,7 @@ struct bf_ctx {
     double linTol, linRelTol;
     // pipelined Newton loop (device-side convergence test, one-sided exchange of the norm sums; beam_kernels.cuh ConvCtl)
     double* d_xbuf;            // [2 banks][CONV_MAXK][xRanks][4], cudaMalloc (its IPC handle is exported to the peers)
+    double* d_vflag;           // [2 banks][CONV_MAXK] verdict cache (ConvCtl::vflag), local
     double* peerXbuf[CONV_MAX_RANKS]; // every rank's buffer as mapped into this process (own: d_xbuf)
     int xRanks, xRank;
     long long epoch;
@@ -148,7 +151,7 @@ extern "C" int64_t bf_num_cells(const bf_ctx* c) { return c->N; }
 extern "C" int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
 extern "C" int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
 extern "C" int64_t bf_launch_count(const bf_ctx* c) { return c->launches; }
-extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return (c->longMode || c->nPairs) ? BF_FAMILY_CELL : (c->split && c->coopBwd) ? BF_FAMILY_SPLIT_CELL : c->split ? BF_FAMILY_SPLIT : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
+extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return (c->longMode || c->nPairs) ? BF_FAMILY_CELL : (c->split && c->coopFwd) ? BF_FAMILY_SPLIT_GROUP : (c->split && c->coopBwd) ? BF_FAMILY_SPLIT_CELL : c->split ? BF_FAMILY_SPLIT : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
 
 extern "C" int bf_host_alloc(void** p, int64_t bytes)
 {
@@ -291,7 +294,7 @@ __global__ void convertRotation(double* __restrict__ tens, double* __restrict__ 
 // Gamma = refLambdaf.T() & ((Lambdaf.T() & (dR0Ds + snGrad(W))) - dR0Ds)  (Evolve.C:881-887), evaluated from the
 // stored W / Lambdaf when the host asks for the field.  One thread per beam; internal faces into host order,
 // patch faces into left[b*3..], right[b*3..].
-__global__ void gammaField(const BeamParams p, const int64_t* __restrict__ faceStart, double* __restrict__ internal,
+__global__ void gammaField(const __grid_constant__ BeamParams p, const int64_t* __restrict__ faceStart, double* __restrict__ internal,
                            double* __restrict__ left, double* __restrict__ right)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,6 +362,7 @@ extern "C" int bf_destroy(bf_ctx* c)
     for (int r = 0; r < c->xRanks; r++)
         if (r != c->xRank && c->peerXbuf[r]) cudaIpcCloseMemHandle(c->peerXbuf[r]);
     if (c->d_xbuf) cudaFree(c->d_xbuf);
+    if (c->d_vflag) cudaFree(c->d_vflag);
     for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) if (c->evIter[i][k]) cudaEventDestroy(c->evIter[i][k]);
     for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->evRegion[i]) cudaEventDestroy(c->evRegion[i]);
@@ -430,7 +434,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->evRegion[0] = c->evRegion[1] = nullptr;
     c->nPairs = 0; c->d_adjPtr = c->d_adjCol = nullptr; c->d_adjK = c->d_cplDinv = c->d_cplUP = c->d_cplVec = nullptr;
     c->h_lin = c->d_hlin = nullptr; c->linMaxIter = 1000; c->linIterations = 0; c->linTol = 1e-13; c->linRelTol = 0.0;
-    c->d_xbuf = nullptr; c->xRanks = 1; c->xRank = 0; c->epoch = 0; c->lastIters = 4; c->h_res = nullptr; c->d_hres = nullptr;
+    c->d_xbuf = nullptr; c->d_vflag = nullptr; c->xRanks = 1; c->xRank = 0; c->epoch = 0; c->lastIters = 4; c->h_res = nullptr; c->d_hres = nullptr;
     memset(&c->cvNow, 0, sizeof c->cvNow);
     for (int i = 0; i < CONV_MAX_RANKS; i++) c->peerXbuf[i] = nullptr;
     for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) c->evIter[i][k] = nullptr;
@@ -456,11 +460,13 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     OPT_IN_SMEM(beam_newton);
     OPT_IN_SMEM(beam_forward);
     OPT_IN_SMEM(beam_forward_split);
-    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_STEADY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_NEWMARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_forward_ws<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
+#define OPT_IN_WS(BPB, SPLIT, EW)                                                                                                                              \
+    CREATE_CUDA((cudaFuncSetAttribute(beam_forward_ws<BFK_STEADY, BPB, SPLIT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES(BPB, EW))));  \
+    CREATE_CUDA((cudaFuncSetAttribute(beam_forward_ws<BFK_NEWMARK, BPB, SPLIT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES(BPB, EW)))); \
+    CREATE_CUDA((cudaFuncSetAttribute(beam_forward_ws<BFK_EULER, BPB, SPLIT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES(BPB, EW))))
+    OPT_IN_WS(16, false, 1); OPT_IN_WS(16, true, 1); OPT_IN_WS(32, false, 1); OPT_IN_WS(32, true, 1); OPT_IN_WS(32, false, 2); OPT_IN_WS(32, true, 2);
     CREATE_CUDA(cudaFuncSetAttribute(beam_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES));
-    CREATE_CUDA(cudaFuncSetAttribute(beam_backsub_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES));
+    CREATE_CUDA(cudaFuncSetAttribute(beam_backsub_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSS_SMEM_BYTES));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
@@ -541,24 +547,28 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     // ---- block-Thomas scratch + partial sums
     {
         char* cur;
-        c->coopGrid = (Bpad + WS_BEAMS - 1) / WS_BEAMS;
+        c->wsBpb = 16; c->wsEw = 1;
+        c->coopGrid = (Bpad + 15) / 16;
         c->partialStride = 2 * c->grid; // the split sweeps launch two blocks per 128 beams
         if ((int)((c->N + 127) / 128) > c->partialStride) c->partialStride = (int)((c->N + 127) / 128);
-        if (c->coopGrid > c->partialStride) c->partialStride = c->coopGrid;
+        if (2 * c->coopGrid > c->partialStride) c->partialStride = 2 * c->coopGrid;
         const int cellGrid = (int)(((size_t)Bpad * (size_t)nmax + 127) / 128); // beam_update_*: one thread per (padded) cell
         if (cellGrid > c->partialStride) c->partialStride = cellGrid;
         if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->partialStride + 8) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
         c->d_partial = carve<double>(cur, 3 * (size_t)c->partialStride); c->d_sums = carve<double>(cur, 8);
         // Kernel family by bundle size (measured on B200, 200-cell Newmark beams, ms per Newton iteration):
-        //      beams      4096   8192   16384  32768  65536
-        //      per beam   1.17   1.18   1.20   1.84   3.69     one thread per beam: flat below one wave (37,888 beams)
-        //      split      0.61   0.62   1.01   1.93   3.51     two threads per beam, half the serial length
-        //      group      0.60   0.96   1.87   3.48   6.72     assembler + eliminator warps: lowest latency, half the throughput
+        //      beams        4096   8192   16384  32768  65536
+        //      per beam     1.17   1.18   1.20   1.84   3.69   one thread per beam: flat below one wave (37,888 beams)
+        //      split        0.61   0.63   1.01   1.93   3.51   two threads per beam, half the serial length
+        //      split cell   0.47   0.63   1.17                 split forward sweep, backward part with one thread per cell
+        //      split group  0.40   0.77   1.41                 assembler + eliminator warps per half beam (16 per block), cell-parallel backward
+        //      group        0.60   0.96   1.87   3.48   6.72   the same for whole beams (serves ragged bundles)
         // With w = B/32 warps and S = 8 warps x SMs resident, one thread per beam costs ceil(w/S) sweep rounds and the split
         // sweeps ceil(2w/S)/2: split when that is fewer, or equal with more than one round (the shorter tasks fill the last
-        // round better).  The split sweeps need a uniform bundle; small ragged bundles take the group kernels.
-        // BEAMGPU_SPLIT = 1 / 0 and BEAMGPU_COOP = 1 / 0 / fwd / bwd force a family on / off (tests, scripts/gpu_sizes.py).
+        // round better).  The split sweeps need a uniform bundle; small ragged bundles take the group kernels.  The split group
+        // kernels occupy 8 warps per 32 beams: they serve bundles whose B/4 warps are resident at once.
+        // BEAMGPU_SPLIT = 1 / 0, BEAMGPU_COOP = 1 / 0 / fwd / bwd and BEAMGPU_WS = 16 / 32 / 33 force a family (tests, scripts/gpu_sizes.py).
         {
             int nSm = 148;
             cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, c->device);
@@ -572,10 +582,19 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
                 if (!strcmp(e, "fwd")) { c->coopFwd = 1; c->coopBwd = 0; }
                 else if (!strcmp(e, "bwd")) { c->coopFwd = 0; c->coopBwd = 1; }
                 else c->coopFwd = c->coopBwd = atoi(e) ? 1 : 0;
-                if (c->coopFwd) c->split = 0;
+                if (c->coopFwd && !getenv("BEAMGPU_WS")) c->split = 0;
             }
-            // small uniform bundles: the split forward sweep with the cell-parallel backward sweep (measured fastest below ~5k beams)
-            if (c->split && !getenv("BEAMGPU_COOP")) c->coopBwd = B < 5120 ? 1 : 0;
+            // BEAMGPU_WS = 16 / 32: the warp-specialised forward kernel with that many beams per block (with BEAMGPU_SPLIT=1: per
+            // half beam); 33: 32 per block with two eliminator warps
+            if (const char* e = getenv("BEAMGPU_WS")) {
+                c->wsBpb = atoi(e) >= 32 ? 32 : 16;
+                c->wsEw = atoi(e) == 33 ? 2 : 1;
+                c->coopFwd = 1;
+            }
+            if (c->split && !getenv("BEAMGPU_COOP") && !getenv("BEAMGPU_WS")) {
+                c->coopBwd = B < 9216 ? 1 : 0;                  // cell-parallel backward part: ahead below ~5k beams, level with the split sweep up to 8192
+                c->coopFwd = 8L * w <= S ? 1 : 0;               // split group forward: all its warps resident at once
+            }
         }
         c->d_X = nullptr;
         if (c->coopBwd && devAlloc(c, (void**)&c->d_X, sizeof(double) * 6 * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
@@ -602,6 +621,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     CREATE_CUDA(cudaMalloc((void**)&c->d_xbuf, sizeof(double) * 2 * CONV_MAXK * CONV_MAX_RANKS * 4));
     CREATE_CUDA(cudaMemsetAsync(c->d_xbuf, 0, sizeof(double) * 2 * CONV_MAXK * CONV_MAX_RANKS * 4, c->stream));
     c->peerXbuf[0] = c->d_xbuf;
+    CREATE_CUDA(cudaMalloc((void**)&c->d_vflag, sizeof(double) * 2 * CONV_MAXK));
+    CREATE_CUDA(cudaMemsetAsync(c->d_vflag, 0, sizeof(double) * 2 * CONV_MAXK, c->stream));
 
     // ---- upload constants
     {
@@ -1189,6 +1210,22 @@ static BeamParams makeParams(bf_ctx* c)
         else if (c->scheme == BF_SCHEME_EULER) KERNEL<BFK_EULER><<<(GRID), THREADS, (SMEM), c->stream>>>(P); \
         else KERNEL<BFK_STEADY><<<(GRID), THREADS, (SMEM), c->stream>>>(P);                           \
     } while (0)
+// The warp-specialised forward kernel (beam_coop.cuh): 16 or 32 beams per block, whole beams or halves (grid.y = 2).
+template <int BPB, bool SPLIT, int EW>
+static void launchForwardWsT(bf_ctx* c, const BeamParams& p)
+{
+    const dim3 g((unsigned)((c->Bpad + BPB - 1) / BPB), SPLIT ? 2 : 1);
+    if (c->scheme == BF_SCHEME_NEWMARK) beam_forward_ws<BFK_NEWMARK, BPB, SPLIT, EW><<<g, WS_THREADS(EW), WS_SMEM_BYTES(BPB, EW), c->stream>>>(p);
+    else if (c->scheme == BF_SCHEME_EULER) beam_forward_ws<BFK_EULER, BPB, SPLIT, EW><<<g, WS_THREADS(EW), WS_SMEM_BYTES(BPB, EW), c->stream>>>(p);
+    else beam_forward_ws<BFK_STEADY, BPB, SPLIT, EW><<<g, WS_THREADS(EW), WS_SMEM_BYTES(BPB, EW), c->stream>>>(p);
+}
+static int launchForwardWs(bf_ctx* c, const BeamParams& p) // returns the number of blocks (partial sums of slot 0)
+{
+    if (c->wsBpb == 32 && c->wsEw == 2) { if (c->split) launchForwardWsT<32, true, 2>(c, p); else launchForwardWsT<32, false, 2>(c, p); }
+    else if (c->wsBpb == 32) { if (c->split) launchForwardWsT<32, true, 1>(c, p); else launchForwardWsT<32, false, 1>(c, p); }
+    else { if (c->split) launchForwardWsT<16, true, 1>(c, p); else launchForwardWsT<16, false, 1>(c, p); }
+    return ((c->Bpad + c->wsBpb - 1) / c->wsBpb) * (c->split ? 2 : 1);
+}
 // Launches one Newton iteration; the three LOCAL sums of squares end up in d_sums.
 // evs: the three timing events of this iteration (bf_evolve's pipelined loop passes one set per enqueued iteration)
 static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
@@ -1268,13 +1305,14 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
         c->launches += 2;
     } else if (c->split) { // two threads per beam, the halves meet in the middle
         const dim3 g2((unsigned)c->grid, 2);
-        LAUNCH_SCHEME(beam_forward_split, g2, SMEM_BYTES, p);
-        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
         nF = nB = 2 * c->grid;
+        if (c->coopFwd) nF = launchForwardWs(c, p); // assembler + eliminator warps per half beam
+        else LAUNCH_SCHEME(beam_forward_split, g2, SMEM_BYTES, p);
+        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
         if (c->coopBwd) { // small bundles: serial back-substitution of the two halves, then the update with one thread per cell
             const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
-            const dim3 gs((unsigned)((c->Bpad + BS_THREADS - 1) / BS_THREADS), 2);
-            beam_backsub_split<<<gs, BS_THREADS, BS_SMEM_BYTES, c->stream>>>(p, c->d_X);
+            const dim3 gs((unsigned)(c->Bpad / 32), 2);
+            beam_backsub_split<<<gs, 32, BSS_SMEM_BYTES, c->stream>>>(p, c->d_X);
             beam_update_faces<<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
             if (c->scheme == BF_SCHEME_NEWMARK) beam_update_cells<BFK_NEWMARK><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
             else if (c->scheme == BF_SCHEME_EULER) beam_update_cells<BFK_EULER><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
@@ -1285,7 +1323,8 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
             LAUNCH_SCHEME(beam_backward_split, g2, 0, p);
         c->launches += 2;
     } else if (c->splitKernels || c->coopFwd || c->coopBwd) { // product path: one launch per sweep
-        if (c->coopFwd) LAUNCH_SCHEME_T(beam_forward_ws, c->coopGrid, WS_THREADS, WS_SMEM_BYTES, p);
+        int nWs = 0;
+        if (c->coopFwd) nWs = launchForwardWs(c, p);
         else LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
         const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
@@ -1298,7 +1337,7 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
             c->launches += 2;
         } else LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
         c->launches += 2;
-        nF = c->coopFwd ? c->coopGrid : c->grid;
+        nF = c->coopFwd ? nWs : c->grid;
         nB = c->coopBwd ? cellGrid : c->grid;
     } else {
         LAUNCH_SCHEME(beam_newton, c->grid, SMEM_BYTES, p);
@@ -1461,7 +1500,7 @@ static int solveCoupled(bf_ctx* c, const CoupledParams& q)
 //     eta = ||b - A x||_2 / (||A||_F ||x||_2 + ||b||_2),
 // A, b = the block system assembled from the pre-solve state by the cell-parallel assembly (long_assemble: the blocks the
 // reference hands to BlockEigenSolverOF, EigenOF.C:60-175), x = the increments the sweeps produced.  Needs storeIncrements.
-__global__ void linearResidualKernel(const BeamParams p, const LongParams q, double* __restrict__ acc4)
+__global__ void linearResidualKernel(const __grid_constant__ BeamParams p, const LongParams q, double* __restrict__ acc4)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double v[4] = {0, 0, 0, 0}; // r^2, b^2, A^2, x^2
@@ -1578,6 +1617,7 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
     c->epoch++;
     ConvCtl cv;
     cv.xbuf = c->d_xbuf + (size_t)(c->epoch & 1) * CONV_MAXK * c->xRanks * 4;
+    cv.vflag = c->d_vflag + (size_t)(c->epoch & 1) * CONV_MAXK;
     cv.nRanks = c->xRanks; cv.iter = 0; cv.tag = 2.0 * (double)c->epoch;
     cv.absTol = tol->absoluteTol; cv.resTol = tol->residualTol; cv.solTol = tol->solutionTol; cv.divTol = tol->divergenceTol;
     cv.nCorr = tol->nCorrectors;

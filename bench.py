@@ -55,8 +55,11 @@ FAMILY = {0: "one thread per beam (beam_forward / beam_backward)",
           2: "one thread per cell, block cyclic reduction (long_*)",
           3: "two threads per beam meeting in the middle (beam_forward_split / beam_backward_split)",
           4: "two threads per beam in the forward sweep (beam_forward_split), serial back-substitution + one thread per cell "
+             "(beam_backsub_split, beam_update_*)",
+          5: "assembler + eliminator warps per half beam (beam_forward_ws, split), serial back-substitution + one thread per cell "
              "(beam_backsub_split, beam_update_*)", -1: "cpu"}
-FAMILY_ENV = {0: ("0", "0"), 1: ("1", "0"), 3: ("0", "1"), 4: ("bwd", "1")}  # BEAMGPU_COOP, BEAMGPU_SPLIT that force a family
+# BEAMGPU_COOP, BEAMGPU_SPLIT, BEAMGPU_WS that force a family
+FAMILY_ENV = {0: ("0", "0", None), 1: ("1", "0", None), 3: ("0", "1", None), 4: ("bwd", "1", None), 5: ("bwd", "1", "16")}
 CONFIGS = {
     "bundle65536": dict(beams=65536, cells=200, baseline="configs[3]"),
     "bundle4096": dict(beams=4096, cells=200, baseline="configs[2]"),
@@ -471,9 +474,11 @@ def verify(args, D: Dist, lib, case, total, main: Bundle, iters, tips):
     out = {}
     # (1) a sample of this rank's beams as a stand-alone bundle, same kernel family, same per-step iteration counts
     S = min(256, hi - lo)
-    saved = {k: os.environ.get(k) for k in ("BEAMGPU_COOP", "BEAMGPU_SPLIT")}
+    saved = {k: os.environ.get(k) for k in ("BEAMGPU_COOP", "BEAMGPU_SPLIT", "BEAMGPU_WS")}
     if main.family in FAMILY_ENV:
-        os.environ["BEAMGPU_COOP"], os.environ["BEAMGPU_SPLIT"] = FAMILY_ENV[main.family]
+        os.environ["BEAMGPU_COOP"], os.environ["BEAMGPU_SPLIT"], ws = FAMILY_ENV[main.family]
+        if ws:
+            os.environ["BEAMGPU_WS"] = ws
     sample = Bundle(args, D, lib, case, total, beamRange=(lo, lo + S), comm=False)
     for k, v in saved.items():
         if v is None:
@@ -570,8 +575,9 @@ def run_ours(args):
     achieved = bpu * nCellsLocal / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     names = {0: ("beam_forward", "beam_backward"), 1: ("beam_forward_ws", "beam_backsub + beam_update_faces + beam_update_cells"),
              2: ("long_assemble + long_pcr_*", "long_update_*"), 3: ("beam_forward_split", "beam_backward_split"),
-             4: ("beam_forward_split", "beam_backsub_split + beam_update_faces + beam_update_cells")}[main.family]
-    tj = load_traffic({0: "per_beam", 1: "group", 2: "cell", 3: "split", 4: "split_cell"}[main.family])
+             4: ("beam_forward_split", "beam_backsub_split + beam_update_faces + beam_update_cells"),
+             5: ("beam_forward_ws", "beam_backsub_split + beam_update_faces + beam_update_cells")}[main.family]
+    tj = load_traffic({0: "per_beam", 1: "group", 2: "cell", 3: "split", 4: "split_cell", 5: "split_group"}[main.family])
     traffic, per_kernel, fp64 = None, None, None
     if tj:
         scale = nCellsLocal / float(tj["cells_per_launch"])

@@ -366,6 +366,7 @@ int64_t bf_launch_count(const bf_ctx* ctx);
 #define BF_FAMILY_CELL 2
 #define BF_FAMILY_SPLIT 3
 #define BF_FAMILY_SPLIT_CELL 4 /* split forward sweep, backward sweep with one thread per cell (small uniform bundles) */
+#define BF_FAMILY_SPLIT_GROUP 5 /* assembler + eliminator warps per HALF beam, backward sweep with one thread per cell (bundles below half a wave) */
 int32_t bf_kernel_family(const bf_ctx* ctx);
 int bf_kernel_time_ms(bf_ctx* ctx, int32_t reset, double* fwd_ms, double* bwd_ms,
                       int64_t* iterations);

@@ -14,8 +14,13 @@ cells = int(os.environ.get("CELLS", "200"))
 for nb in map(int, sys.argv[1:]):
     case = cases.multiBeamDensity(nb, cells, jitter=True)
     for mode in os.environ.get("MODES", "0,1,s,sc").split(","):  # 0 per beam, 1 group (warp-specialised), s split, sc split + cell-parallel backward
-        os.environ["BEAMGPU_COOP"] = {"s": "0", "sc": "bwd"}.get(mode, mode)
-        os.environ["BEAMGPU_SPLIT"] = "1" if mode in ("s", "sc") else "0"
+        # w16 / w32: split + warp-specialised forward (16 / 32 half beams per block) + cell-parallel backward; w16b / w32b: with
+        # the split backward sweep; g32: unsplit, 32 beams per block
+        os.environ["BEAMGPU_COOP"] = {"s": "0", "sc": "bwd", "w16": "bwd", "w32": "bwd", "w33": "bwd", "w16b": "0", "w32b": "0", "w33b": "0", "g32": "1", "g33": "1"}.get(mode, mode)
+        os.environ["BEAMGPU_SPLIT"] = "1" if mode in ("s", "sc", "w16", "w32", "w33", "w16b", "w32b", "w33b") else "0"
+        os.environ.pop("BEAMGPU_WS", None)
+        if mode[0] in "wg":
+            os.environ["BEAMGPU_WS"] = mode[1:3]
         m = coupledTotalLagNewtonRaphsonBeam(case, library=lib, storeIncrements=False)
         m.updateCoeffs(case.deltaT)
         its = []

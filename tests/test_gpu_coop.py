@@ -19,18 +19,23 @@ from test_gpu_parity import run_pair
 
 pytestmark = pytest.mark.gpu
 
-# family -> (BEAMGPU_COOP, BEAMGPU_SPLIT)
+# family -> (BEAMGPU_COOP, BEAMGPU_SPLIT[, BEAMGPU_WS]); BEAMGPU_WS = beams per block of the warp-specialised forward kernel
 MODES = {"per_beam": ("0", "0"), "group": ("1", "0"), "group_fwd": ("fwd", "0"), "group_bwd": ("bwd", "0"), "split": ("0", "1"),
-         "split_cell": ("bwd", "1")}
+         "split_cell": ("bwd", "1"), "group32": ("1", "0", "32"), "split_group16": ("bwd", "1", "16"),
+         "split_group32": ("bwd", "1", "32"), "split_group16_sweep": ("0", "1", "16"), "group33": ("1", "0", "33"),
+         "split_group33": ("bwd", "1", "33")}  # 33 = 32 beams per block, two eliminator warps
 
 
 def set_family(name):
-    os.environ["BEAMGPU_COOP"], os.environ["BEAMGPU_SPLIT"] = MODES[name]
+    os.environ["BEAMGPU_COOP"], os.environ["BEAMGPU_SPLIT"] = MODES[name][:2]
+    os.environ.pop("BEAMGPU_WS", None)
+    if len(MODES[name]) > 2:
+        os.environ["BEAMGPU_WS"] = MODES[name][2]
 
 
 def clear_family():
-    os.environ.pop("BEAMGPU_COOP", None)
-    os.environ.pop("BEAMGPU_SPLIT", None)
+    for k in ("BEAMGPU_COOP", "BEAMGPU_SPLIT", "BEAMGPU_WS"):
+        os.environ.pop(k, None)
 
 
 @pytest.fixture(params=sorted(MODES))
@@ -100,13 +105,14 @@ def test_families_agree_at_4096_beams(gpu_lib):
     order)."""
     case = cases.multiBeamDensity(4096, 200, jitter=True)
     out = {}
-    for mode in ("per_beam", "group", "split", "split_cell"):
+    families = ("per_beam", "group", "split", "split_cell", "group32", "split_group16", "split_group32", "split_group33")
+    for mode in families:
         set_family(mode)
         m = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib, storeIncrements=False)
         out[mode] = (m.run(nSteps=4), m.tip(1))
         m.close()
     clear_family()
-    for mode in ("group", "split", "split_cell"):
+    for mode in families[1:]:
         assert out["per_beam"][0] == out[mode][0], mode
         for a, b in zip(out["per_beam"][1], out[mode][1]):
             assert np.max(np.abs(a - b)) <= 1e-11 * np.max(np.abs(b)), mode
