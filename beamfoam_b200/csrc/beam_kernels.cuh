@@ -341,46 +341,67 @@ DEV double ldAcquireSys(const double* p)
     return v;
 }
 DEV void stReleaseSys(double* p, double v) { asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
-// Global sums of iteration k, added in rank order.  wait: spin until every rank's record is there.  Returns -1: a record
-// is missing (only without wait), 1: a rank had seen the loop end before iteration k, 0: s holds the sums.
-DEV int convSums(const ConvCtl& c, const int k, const bool wait, double (&s)[3])
+// Global sums of iteration k, added in rank order, by ONE WARP: lane r reads the record of rank r (a system-scope load is a
+// round trip of the order of a microsecond; one thread reading 4 nRanks of them in turn cost 45 us per block on 8 GPUs), the
+// sums are then added in rank order through shuffles (bit-identical on every rank).  wait: spin until every rank's record is
+// there.  s[3] = the sums of iteration 0 (the initial residual; its records arrived long ago).  Returns -1: a record is missing
+// (only without wait), 1: a rank had seen the loop end before iteration k, 0: s holds the sums.  Call with all 32 lanes.
+DEV int convSums(const ConvCtl& c, const int k, const bool wait, double (&s)[4])
 {
-    s[0] = s[1] = s[2] = 0.0;
-    int ended = 0;
-    for (int r = 0; r < c.nRanks; r++) {
-        const double* rec = c.xbuf + ((size_t)k * c.nRanks + r) * 4;
+    const int lane = threadIdx.x & 31;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, i0 = 0.0;
+    int state = 0;
+    if (lane < c.nRanks) {
+        const double* rec = c.xbuf + ((size_t)k * c.nRanks + lane) * 4;
         double tag;
         for (;;) {
             tag = ldAcquireSys(rec + 3);
             if (tag == c.tag || tag == c.tag + 1.0) break;
-            if (!wait) return -1;
+            if (!wait) { state = -1; break; }
             __nanosleep(100);
         }
-        if (tag != c.tag) ended = 1;
-        s[0] += ldAcquireSys(rec); s[1] += ldAcquireSys(rec + 1); s[2] += ldAcquireSys(rec + 2);
+        if (state == 0) {
+            if (tag != c.tag) state = 1;
+            v0 = ldAcquireSys(rec); v1 = ldAcquireSys(rec + 1); v2 = ldAcquireSys(rec + 2);
+            i0 = k > 0 ? ldAcquireSys(c.xbuf + (size_t)lane * 4) : v0;
+        }
     }
-    return ended;
+    __syncwarp();
+    const bool missing = __any_sync(0xffffffffu, state == -1), ended = __any_sync(0xffffffffu, state == 1);
+    s[0] = s[1] = s[2] = s[3] = 0.0;
+    for (int r = 0; r < c.nRanks; r++) {
+        s[0] += __shfl_sync(0xffffffffu, v0, r); s[1] += __shfl_sync(0xffffffffu, v1, r);
+        s[2] += __shfl_sync(0xffffffffu, v2, r); s[3] += __shfl_sync(0xffffffffu, i0, r);
+    }
+    return missing ? -1 : ended ? 1 : 0;
 }
 // The five exit rules of checkConvergence (Evolve.C:926-1026) on the squared global sums: does the loop end with iteration k?
-DEV bool convRules(const ConvCtl& c, const int k, const double (&s)[3], const double initSq)
+DEV bool convRules(const ConvCtl& c, const int k, const double (&s)[4])
 {
     if (!(s[0] == s[0]) || !(s[1] == s[1]) || !(s[2] == s[2])) return true; // non-finite: a singular block
     const double cur = sqrt(s[0]), dx = sqrt(s[1]), xn = sqrt(s[2]);
-    const double init = k == 0 ? cur : sqrt(initSq);
+    const double init = k == 0 ? cur : sqrt(s[3]);
     if (cur <= c.absTol) return true;
     if (cur <= c.resTol * init) return true;
     if (dx <= c.solTol * xn) return true;
     if (cur >= c.divTol * init && k > 1) return true;
     return k >= c.nCorr;
 }
-// 1: the loop ends with iteration k or had ended before, 0: it goes on, -1: not known yet (only without wait)
+// 1: the loop ends with iteration k or had ended before, 0: it goes on, -1: not known yet (only without wait).  The verdict is
+// the same for whoever computes it: the first warp that has all the records caches it (ConvCtl::vflag), and the thousands of
+// short-lived blocks of the cell-parallel kernels then pay one L2 load.  Call with all 32 lanes of a warp.
 DEV int convDecide(const ConvCtl& c, const int k, const bool wait)
 {
-    double s[3], s0[3] = {0, 0, 0};
+    volatile double* vf = c.vflag + k;
+    const double v = *vf;
+    if (v == c.tag + 0.5) return 1;
+    if (v == c.tag + 0.25) return 0;
+    double s[4];
     const int m = convSums(c, k, wait, s);
-    if (m) return m;
-    if (k > 0) convSums(c, 0, true, s0); // the initial residual; its records arrived long ago
-    return convRules(c, k, s, s0[0]) ? 1 : 0;
+    if (m < 0) return -1;
+    const int d = m ? 1 : convRules(c, k, s) ? 1 : 0;
+    if ((threadIdx.x & 31) == 0) *vf = c.tag + (d == 1 ? 0.5 : 0.25);
+    return d;
 }
 // Prologue of every sweep kernel: true = leave, the loop ended with an earlier iteration.  The forward sweeps do not wait
 // (if the records of the previous iteration are not all there yet they run speculatively: they write scratch and partial
@@ -390,20 +411,9 @@ DEV bool convLeave(const ConvCtl& c, const bool wait)
 {
     if (!c.xbuf || c.iter == 0) return false;
     __shared__ int sLeave;
-    if (threadIdx.x == 0) {
-        // The verdict on iteration k is the same for whoever computes it: the first block that has all the records caches it,
-        // the thousands of short-lived blocks of the cell-parallel kernels then pay one L2 load instead of 4 nRanks (+ 4 nRanks
-        // for the initial residual) system-scope loads each.
-        volatile double* vf = c.vflag + (c.iter - 1);
-        const double v = *vf;
-        int d;
-        if (v == c.tag + 0.5) d = 1;
-        else if (v == c.tag + 0.25) d = 0;
-        else {
-            d = convDecide(c, c.iter - 1, wait);
-            if (d >= 0) *vf = c.tag + (d == 1 ? 0.5 : 0.25);
-        }
-        sLeave = d == 1;
+    if (threadIdx.x < 32) {
+        const int d = convDecide(c, c.iter - 1, wait);
+        if (threadIdx.x == 0) sLeave = d == 1;
     }
     __syncthreads();
     return sLeave != 0;
@@ -1886,22 +1896,34 @@ __global__ void beam_energy(const __grid_constant__ BeamParams p, double* __rest
 // Deterministic final reduction of the per-block partial sums (fixed order).  partial[k * stride + block]: slot 0 is
 // written by the nF blocks of the forward launch, slots 1 and 2 by the nB blocks of the backward launch (the two
 // launches of an iteration may come from different kernel families, see bf_ctx::coopFwd / coopBwd).
-__global__ void beam_reduce_partials(const double* __restrict__ partial, int stride, int nF, int nB, double* __restrict__ out,
-                                     double* __restrict__ outHost)
+// One block of RED_THREADS threads; every thread adds its strided share of each slot with four independent accumulators (the
+// cell-parallel backward part leaves one partial per 128 cells -- 12,800 of them for 8192 beams: 256 threads adding 50 values
+// one dependent L2 round trip after the other made this kernel 40 us of a 630 us iteration).
+#define RED_THREADS 1024
+DEV void reducePartialsBlock(const double* __restrict__ partial, int stride, int nF, int nB, double (&sm)[3][RED_THREADS])
 {
-    __shared__ double sm[3][256];
+    const int t = threadIdx.x, nt = blockDim.x;
     for (int k = 0; k < 3; k++) {
-        double acc = 0.0;
-        const int nBlocks = k == 0 ? nF : nB;
-        for (int i = threadIdx.x; i < nBlocks; i += blockDim.x) acc += partial[(size_t)k * stride + i];
-        sm[k][threadIdx.x] = acc;
+        const double* src = partial + (size_t)k * stride;
+        const int n = k == 0 ? nF : nB;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = t;
+        for (; i + 3 * nt < n; i += 4 * nt) { a0 += src[i]; a1 += src[i + nt]; a2 += src[i + 2 * nt]; a3 += src[i + 3 * nt]; }
+        for (; i < n; i += nt) a0 += src[i];
+        sm[k][t] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o)
-            for (int k = 0; k < 3; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + o];
+    for (int o = nt / 2; o > 0; o >>= 1) {
+        if (t < o)
+            for (int k = 0; k < 3; k++) sm[k][t] += sm[k][t + o];
         __syncthreads();
     }
+}
+__global__ void __launch_bounds__(RED_THREADS) beam_reduce_partials(const double* __restrict__ partial, int stride, int nF, int nB,
+                                                                    double* __restrict__ out, double* __restrict__ outHost)
+{
+    __shared__ double sm[3][RED_THREADS];
+    reducePartialsBlock(partial, stride, nF, nB, sm);
     if (threadIdx.x < 3) {
         out[threadIdx.x] = sm[threadIdx.x][0];
         if (outHost) outHost[threadIdx.x] = sm[threadIdx.x][0]; // mapped pinned host memory
@@ -1911,24 +1933,16 @@ struct PeerTable {
     double* bank[CONV_MAX_RANKS]; // the current bank of every rank's exchange buffer (own included)
 };
 // The same reduction, then this rank's record of iteration cv.iter into every rank's buffer.
-__global__ void beam_reduce_exchange(const double* __restrict__ partial, int stride, int nF, int nB, const ConvCtl cv,
-                                     const PeerTable peers, const int rank)
+__global__ void __launch_bounds__(RED_THREADS) beam_reduce_exchange(const double* __restrict__ partial, int stride, int nF, int nB,
+                                                                    const ConvCtl cv, const PeerTable peers, const int rank)
 {
-    __shared__ double sm[3][256];
+    __shared__ double sm[3][RED_THREADS];
     __shared__ int ended;
-    for (int k = 0; k < 3; k++) {
-        double acc = 0.0;
-        const int nBlocks = k == 0 ? nF : nB;
-        for (int i = threadIdx.x; i < nBlocks; i += blockDim.x) acc += partial[(size_t)k * stride + i];
-        sm[k][threadIdx.x] = acc;
+    if (threadIdx.x >= RED_THREADS - 32) { // the last warp (the first ones carry the tail of the tree): did the sweeps of this iteration run?
+        const int d = cv.iter > 0 ? convDecide(cv, cv.iter - 1, true) : 0;
+        if (threadIdx.x == RED_THREADS - 32) ended = d == 1;
     }
-    if (threadIdx.x == 0) ended = cv.iter > 0 && convDecide(cv, cv.iter - 1, true) == 1; // the sweeps of this iteration did not run
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o)
-            for (int k = 0; k < 3; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + o];
-        __syncthreads();
-    }
+    reducePartialsBlock(partial, stride, nF, nB, sm);
     if ((int)threadIdx.x < cv.nRanks) {
         double* rec = peers.bank[threadIdx.x] + ((size_t)cv.iter * cv.nRanks + rank) * 4;
         rec[0] = sm[0][0]; rec[1] = sm[1][0]; rec[2] = sm[2][0];
@@ -1940,18 +1954,16 @@ __global__ void beam_reduce_exchange(const double* __restrict__ partial, int str
 // this iteration, 2 = it had ended before, 0 = it goes on.  Launched after the last enqueued iteration of a chunk.
 __global__ void beam_publish_chunk(const ConvCtl cv, const int k0, const int k1, double* __restrict__ outHost)
 {
-    if (threadIdx.x != 0) return;
-    double s0[3] = {0, 0, 0};
-    if (k0 > 0) convSums(cv, 0, true, s0);
-    for (int k = k0; k < k1; k++) {
-        double s[3];
-        const int ended = convSums(cv, k, true, s);
-        if (k == 0) { s0[0] = s[0]; }
+    const int k = k0 + (int)(threadIdx.x >> 5); // one warp per iteration of the chunk
+    if (k >= k1) return;
+    double s[4];
+    const int ended = convSums(cv, k, true, s);
+    if ((threadIdx.x & 31) == 0) {
         double* o = outHost + 4 * (k - k0);
         o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
-        o[3] = ended ? 2.0 : convRules(cv, k, s, s0[0]) ? 1.0 : 0.0;
+        o[3] = ended ? 2.0 : convRules(cv, k, s) ? 1.0 : 0.0;
+        __threadfence_system();
     }
-    __threadfence_system();
 }
 __global__ void beam_publish_sums(const double* __restrict__ in, double* __restrict__ outHost)
 {

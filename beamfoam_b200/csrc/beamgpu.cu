@@ -126,6 +126,8 @@ struct bf_ctx {
     cudaEvent_t ev[3];
     double fwdMs, bwdMs;
     int64_t timedIters;
+    double fwdMsK[8], bwdMsK[8], gapMsK[8]; // BEAMGPU_TIMING_DUMP: the same by iteration index of the step (gap: end of iteration k-1 to start of k)
+    int64_t itersK[8];
 };
 
 static int fail(bf_ctx* c, int code, const char* fmt, ...)
@@ -355,6 +357,10 @@ extern "C" int bf_destroy(bf_ctx* c)
     if (!c) return BF_OK;
     cudaSetDevice(c->device);
     if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+    if (getenv("BEAMGPU_TIMING_DUMP"))
+        for (int k = 0; k < 8; k++)
+            if (c->itersK[k]) fprintf(stderr, "beamgpu rank %d iteration %d of a step: fwd %.4f ms  bwd %.4f ms  gap before %.4f ms  (%lld samples)\n", c->xRank, k,
+                                      c->fwdMsK[k] / c->itersK[k], c->bwdMsK[k] / c->itersK[k], c->gapMsK[k] / c->itersK[k], (long long)c->itersK[k]);
     for (int i = 0; i < c->nPools; i++) cudaFree(c->pools[i]);
     if (c->h_sums) cudaFreeHost(c->h_sums);
     if (c->h_res) cudaFreeHost(c->h_res);
@@ -439,6 +445,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     for (int i = 0; i < CONV_MAX_RANKS; i++) c->peerXbuf[i] = nullptr;
     for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) c->evIter[i][k] = nullptr;
     c->copyStream = nullptr; c->evStaged = c->evCopied = nullptr; c->copyPending = false; c->fwdMs = c->bwdMs = 0; c->timedIters = 0;
+    memset(c->fwdMsK, 0, sizeof c->fwdMsK); memset(c->bwdMsK, 0, sizeof c->bwdMsK); memset(c->gapMsK, 0, sizeof c->gapMsK); memset(c->itersK, 0, sizeof c->itersK);
     c->hasQ = c->hasM = false;
     c->d_q = c->d_m = c->d_Lc = c->d_DW = c->d_DTh = nullptr;
     c->d_Wold = c->d_Uold = c->d_Omold = c->d_Lamold = c->d_pf = c->d_pfSrc = nullptr;
@@ -1349,9 +1356,9 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
         PeerTable pt;
         const size_t bank = (size_t)(c->epoch & 1) * CONV_MAXK * c->xRanks * 4;
         for (int r = 0; r < CONV_MAX_RANKS; r++) pt.bank[r] = r < c->xRanks ? c->peerXbuf[r] + bank : nullptr;
-        beam_reduce_exchange<<<1, 256, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, p.cv, pt, c->xRank);
+        beam_reduce_exchange<<<1, RED_THREADS, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, p.cv, pt, c->xRank);
     } else
-        beam_reduce_partials<<<1, 256, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, c->d_sums, c->comm ? nullptr : c->d_hsums);
+        beam_reduce_partials<<<1, RED_THREADS, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, c->d_sums, c->comm ? nullptr : c->d_hsums);
     c->launches += 1;
     CUDA_OK(c, cudaGetLastError());
     if (p.first) c->dtStar = c->deltaT; // the backward sweep of a first iteration re-bases U*, Omega* on this step
@@ -1633,7 +1640,7 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
             if (rc) { c->cvNow.xbuf = nullptr; out->status = rc; return rc; }
         }
         c->cvNow.xbuf = nullptr;
-        beam_publish_chunk<<<1, 32, 0, c->stream>>>(cv, k0, k1, c->d_hres);
+        beam_publish_chunk<<<1, 32 * (k1 - k0), 0, c->stream>>>(cv, k0, k1, c->d_hres);
         c->launches++;
         CUDA_OK(c, cudaGetLastError());
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -1646,6 +1653,11 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
                 CUDA_OK(c, cudaEventElapsedTime(&a, c->evIter[k - k0][0], c->evIter[k - k0][1]));
                 CUDA_OK(c, cudaEventElapsedTime(&b, c->evIter[k - k0][1], c->evIter[k - k0][2]));
                 c->fwdMs += a; c->bwdMs += b; c->timedIters++;
+                if (k < 8) {
+                    float g = 0;
+                    if (k > k0) cudaEventElapsedTime(&g, c->evIter[k - k0 - 1][2], c->evIter[k - k0][0]);
+                    c->fwdMsK[k] += a; c->bwdMsK[k] += b; c->gapMsK[k] += g; c->itersK[k]++;
+                }
             }
             if (done != (r[3] == 1.0)) return fail(c, BF_ERR_CUDA, "iteration %d: host and device disagree on the convergence test", k);
         }

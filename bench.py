@@ -113,19 +113,20 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML in a background thread every 5 ms (so that a
-    timed region of a few steps still gets samples), nvidia-smi -lms 200 as the fallback."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through NVML, on request: the timed loop calls kick()
+    before a step, a waiting thread wakes, lets the step's launches go out (0.3 ms) and reads the clock and the event
+    reasons of this rank's GPU ONCE, while the GPU is busy with that step and the main thread sits in its stream
+    synchronisation.  Free-running pollers are not neutral when 8 ranks advance in lockstep: a 5 ms polling thread per rank
+    (interpreter lock + the driver's locks of the process that is launching kernels) delayed some rank in nearly every
+    3 ms step, which every other rank then waits for in the next convergence test (+0.18 ms per step, 6 %); polling child
+    processes stalled steps for milliseconds.  Every rank samples its own GPU; gather() combines the ranks."""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
-        self.nvml = None
-        self.samples = []   # (sm_mhz, reason bitmask)
+        self.samples = []  # (sm_mhz, reason bitmask)
+        self.req = threading.Event()
         self.running = False
+        self.nvml = None
         self.thread = None
 
     def _nvml_handle(self):
@@ -140,75 +141,69 @@ class ClockSampler:
         except Exception:
             return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
 
-    def _poll(self, nv, h):
-        while self.running:
+    def _serve(self, nv, h):
+        while True:
+            self.req.wait()
+            self.req.clear()
+            if not self.running:
+                return
+            time.sleep(0.0003)
             try:
                 self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
                                      int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
             except Exception:
                 pass
-            time.sleep(0.005)
 
     def start(self):
         try:
             nv, h = self._nvml_handle()
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)  # the first call is the slow one: outside the timed region
             self.nvml = (nv, h)
             self.running = True
-            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread = threading.Thread(target=self._serve, args=(nv, h), daemon=True)
             self.thread.start()
-            return
         except Exception:
             self.nvml = None
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def kick(self):
+        if self.nvml is not None:
+            self.req.set()
 
     def stop(self):
-        if self.nvml is not None:
-            nv, h = self.nvml
-            self.running = False
-            self.thread.join(timeout=1.0)
-            try:
-                mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            except Exception:
-                mx = None
-            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
-                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
-            sm = [a for a, _ in self.samples]
-            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples))
-            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": reasons,
-                    "samples": len(sm), "source": "nvml, 5 ms period"}
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        """This rank's samples: {"sm": [...], "reasons": bitmask-or, "max": MHz} (None without NVML)."""
+        if self.nvml is None:
+            return None
+        nv, h = self.nvml
+        self.running = False
+        self.req.set()
+        self.thread.join(timeout=1.0)
         try:
-            self.proc.wait(timeout=5)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9 or f[0] != str(self.gpu):
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 200"}
+            mx = None
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        return {"sm": [a for a, _ in self.samples], "max": mx,
+                "reasons": sorted(k for k, bit in bits.items() if any(r & bit for _, r in self.samples))}
+
+    @staticmethod
+    def gather(D, mine):
+        """The JSON line's `clocks` from every rank's samples (rank 0 reports; the collective runs outside the timed region)."""
+        allr = [mine]
+        if D.world > 1:
+            import torch.distributed as dist
+            allr = [None] * D.world
+            dist.all_gather_object(allr, mine)
+        allr = [r for r in allr if r]
+        if not allr:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        sm = [x for r in allr for x in r["sm"]]
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r["max"] or 0.0) for r in allr) or None,
+               "reasons": sorted({x for r in allr for x in r["reasons"]}), "samples": len(sm),
+               "source": "nvml, one reading per rank and sampled step, taken while the step runs on the GPU"}
+        if D.world > 1:
+            out["sm_mhz_slowest_gpu"] = min(statistics.median(r["sm"]) for r in allr if r["sm"]) if sm else None
+        return out
 
 
 def make_case(args, total):
@@ -431,20 +426,25 @@ class Bundle:
         lib.bf_kernel_time_ms(ctx, 1, None, None, None)
         launches0 = lib.bf_launch_count(ctx)
         ms = C.c_double()
-        D.barrier()
         sampler.start()
+        stride = max(1, steps // 10)  # about ten clock readings per rank over the region
+        D.barrier()
         t0 = time.perf_counter()
         region = 0.0
         if flush is None:
             lib.bf_region_mark(ctx, 0)
-            for _ in range(steps):
+            for i in range(steps):
+                if i % stride == 0:
+                    sampler.kick()
                 iters.append(self.step_resident())
             lib.bf_region_mark(ctx, 1)
             self.model._check(lib.bf_region_elapsed_ms(ctx, C.byref(ms)))
             region = ms.value
         else:
-            for _ in range(steps):
+            for i in range(steps):
                 flush()
+                if i % stride == 0:
+                    sampler.kick()
                 lib.bf_region_mark(ctx, 0)
                 iters.append(self.step_resident())
                 lib.bf_region_mark(ctx, 1)
@@ -452,7 +452,7 @@ class Bundle:
                 region += ms.value
         D.barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
-        clocks = sampler.stop()
+        clocks = ClockSampler.gather(D, sampler.stop())
         fwd, bwd, nit = C.c_double(), C.c_double(), C.c_int64()
         lib.bf_kernel_time_ms(ctx, 1, C.byref(fwd), C.byref(bwd), C.byref(nit))
         lib.bf_set_timing(ctx, 0)
