@@ -91,6 +91,8 @@ EXPORTS = {
                                                 C.c_void_p]),
     "bf_set_bc_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "bf_get_patch_pair": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bf_set_step_outputs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bf_set_bc_values_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "bf_beam_energy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bf_begin_step": (C.c_int, [C.c_void_p, C.c_double]),
     "bf_newton_iteration": (C.c_int, [C.c_void_p, _dp]),

@@ -401,9 +401,20 @@ class coupledTotalLagNewtonRaphsonBeam:
                         v = np.where(np.array([o.kind == kind for o in objs])[:, None], vals, 0.0)
                     buf = self._pinned_bc(end, var, kind)  # page-locked staging: the H2D copy is a plain DMA
                     np.copyto(buf, v)
-                    self._check(self.lib.bf_set_bc_values(self._ctx, end, kind, buf.ctypes.data))
+                    # the staging array is page-locked and refilled once per step: the upload need not be waited for
+                    self._check(self.lib.bf_set_bc_values_async(self._ctx, end, kind, buf.ctypes.data))
                     self.h2dBytes += buf.nbytes
                 self._bcUploaded.add((end, var))
+
+    def stepOutputs(self, end: int = 1):
+        """Registers (once) and returns two page-locked [nBeams, 3] arrays that every evolve() fills with the patch values of W
+        and Theta of `end` before it returns (bf_set_step_outputs): the per-step read of functionObjects/beamDisplacements
+        without a second synchronisation."""
+        if getattr(self, "_stepOut", None) is None or self._stepOut[0] != end:
+            W, T = self.pinned((self._B, 3)), self.pinned((self._B, 3))
+            self._check(self.lib.bf_set_step_outputs(self._ctx, end, W.ctypes.data, T.ctypes.data))
+            self._stepOut = (end, W, T)
+        return self._stepOut[1], self._stepOut[2]
 
     def pinned(self, shape) -> np.ndarray:
         """A page-locked float64 host array owned by this object (bf_host_alloc), e.g. for bf_get_patch_pair."""

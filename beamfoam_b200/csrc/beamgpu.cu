@@ -78,6 +78,9 @@ struct bf_ctx {
     double* d_longX;
     double* d_stage; // staging buffer in host (AoS) ordering
     double* d_stagePatch; // separate small staging for patch values (never shared with a pending mirror)
+    double* d_stageOut;   // staging of the step outputs (bf_set_step_outputs): [2][B][3]
+    int outEnd;
+    double *outW, *outTheta;
     double* d_stageQ;     // host-ordered quaternions (4 per cell/face) between the transposition and the tensor conversion
     double* d_stagePatchQ;
     size_t stageDoubles;
@@ -440,6 +443,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->evRegion[0] = c->evRegion[1] = nullptr;
     c->nPairs = 0; c->d_adjPtr = c->d_adjCol = nullptr; c->d_adjK = c->d_cplDinv = c->d_cplUP = c->d_cplVec = nullptr;
     c->h_lin = c->d_hlin = nullptr; c->linMaxIter = 1000; c->linIterations = 0; c->linTol = 1e-13; c->linRelTol = 0.0;
+    c->d_stageOut = nullptr; c->outEnd = 0; c->outW = c->outTheta = nullptr;
     c->d_xbuf = nullptr; c->d_vflag = nullptr; c->xRanks = 1; c->xRank = 0; c->epoch = 0; c->lastIters = 4; c->h_res = nullptr; c->d_hres = nullptr;
     memset(&c->cvNow, 0, sizeof c->cvNow);
     for (int i = 0; i < CONV_MAX_RANKS; i++) c->peerXbuf[i] = nullptr;
@@ -1064,7 +1068,10 @@ static void scatterPatch(bf_ctx* c, double* endArr, int end)
                                                                                 c->nmax + 1, 3, end, 0);
     c->launches++;
 }
-extern "C" int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const double* v)
+static int setBcValues(bf_ctx* c, int32_t end, int32_t kind, const double* v, bool wait);
+extern "C" int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const double* v) { return setBcValues(c, end, kind, v, true); }
+extern "C" int bf_set_bc_values_async(bf_ctx* c, int32_t end, int32_t kind, const double* v) { return setBcValues(c, end, kind, v, false); }
+static int setBcValues(bf_ctx* c, int32_t end, int32_t kind, const double* v, bool wait)
 {
     if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !v) return fail(c, BF_ERR_INVALID, "bf_set_bc_values: bad argument");
     CUDA_OK(c, cudaSetDevice(c->device));
@@ -1100,7 +1107,7 @@ extern "C" int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const doub
         }
     }
     CUDA_OK(c, cudaGetLastError());
-    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (wait) CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return BF_OK;
 }
 
@@ -1119,6 +1126,28 @@ extern "C" int bf_get_patch_pair(bf_ctx* c, int32_t end, double* W, double* Thet
     CUDA_OK(c, cudaMemcpyAsync(W, c->d_stagePatch, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaMemcpyAsync(Theta, c->d_stagePatch + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BF_OK;
+}
+
+static int stagePatchPair(bf_ctx* c, int end, double* W, double* Theta)
+{
+    const unsigned grid = (unsigned)((c->B + 255) / 256);
+    const size_t n = (size_t)c->B * 3;
+    transposePatch<false><<<grid, 256, 0, c->stream>>>(c->d_Wb, c->d_stageOut, c->d_nSeg, (int)c->B, c->Bpad, c->nmax + 1, 3, end, 0);
+    transposePatch<false><<<grid, 256, 0, c->stream>>>(c->d_Thb, c->d_stageOut + n, c->d_nSeg, (int)c->B, c->Bpad, c->nmax + 1, 3, end, 0);
+    c->launches += 2;
+    CUDA_OK(c, cudaGetLastError());
+    CUDA_OK(c, cudaMemcpyAsync(W, c->d_stageOut, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(Theta, c->d_stageOut + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    return BF_OK;
+}
+// Step outputs: patch W and Theta of one end of every beam, delivered by bf_evolve itself (see beamgpu.h)
+extern "C" int bf_set_step_outputs(bf_ctx* c, int32_t end, double* W, double* Theta)
+{
+    if ((end != BF_END_LEFT && end != BF_END_RIGHT) || (!W) != (!Theta)) return fail(c, BF_ERR_INVALID, "bf_set_step_outputs: bad argument");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    if (W && !c->d_stageOut && devAlloc(c, (void**)&c->d_stageOut, sizeof(double) * (size_t)c->B * 6)) return fail(c, BF_ERR_NOMEM, "%s", c->err);
+    c->outEnd = end; c->outW = W; c->outTheta = Theta;
     return BF_OK;
 }
 
@@ -1643,6 +1672,8 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
         beam_publish_chunk<<<1, 32 * (k1 - k0), 0, c->stream>>>(cv, k0, k1, c->d_hres);
         c->launches++;
         CUDA_OK(c, cudaGetLastError());
+        // step outputs ride behind every chunk (a chunk that turns out not to be the last is simply overwritten by the next)
+        if (c->outW) { if (int rc = stagePatchPair(c, c->outEnd, c->outW, c->outTheta)) return rc; }
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
         for (int k = k0; k < k1 && !done; k++) {
             const double* r = c->h_res + 4 * (k - k0);
@@ -1702,6 +1733,10 @@ extern "C" int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
         if ((rc = fetchSums(c, s))) { out->status = rc; return rc; }
         if (c->reducer && c->reducer(s, 3, c->reducerUser)) { out->status = BF_ERR_COMM; return fail(c, BF_ERR_COMM, "norm reducer failed"); }
         if (checkConvergence(c, tol, iteration, s, &initialResidualNorm, &currentResidualNorm, &deltaXNorm, &XNorm, &status)) break;
+    }
+    if (c->outW) {
+        if (int rc = stagePatchPair(c, c->outEnd, c->outW, c->outTheta)) return rc;
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
     }
     out->nIter = c->iOuterCorr;
     out->status = status;

@@ -611,7 +611,7 @@ def run_ours(args):
         wf, tf = L.FIELDS["W"], L.FIELDS["Theta"]
         fields = (C.c_int32 * 2)(wf, tf)
         hosts = (C.c_void_p * 2)(Wh.data_ptr(), Th.data_ptr())
-        tipW, tipT = model.pinned((B, 3)), model.pinned((B, 3))
+        tipW, tipT = model.stepOutputs(1)  # filled by every evolve() before it returns (bf_set_step_outputs)
 
         def step_e2e(k, interval):
             """One step as the reference's beamFoam.C:73-89 runs it: BC series -> device, evolve(), the function objects'
@@ -621,8 +621,7 @@ def run_ours(args):
             model.updateCoeffs(model.time)  # host -> device
             model._check(lib.bf_begin_step(ctx, float(case.deltaT)))
             out = L.bf_step_out()
-            model._check(lib.bf_evolve(ctx, C.byref(model.tol), C.byref(out)))
-            model._check(lib.bf_get_patch_pair(ctx, 1, tipW.ctypes.data, tipT.ctypes.data))
+            model._check(lib.bf_evolve(ctx, C.byref(model.tol), C.byref(out)))  # patch W, Theta of every beam are in tipW, tipT now
             if (k + 1) % interval == 0:
                 # queued on the copy stream: overlaps the next step's Newton loop
                 model._check(lib.bf_mirror_begin(ctx, 2, fields, hosts))

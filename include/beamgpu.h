@@ -269,11 +269,22 @@ int bf_set_momentum_contributions(bf_ctx* ctx, int32_t n, const bf_momentum_cont
  * values: [nBeams*3] for patch `end`; entries of beams whose BC class does not
  * use `kind` are ignored. */
 int bf_set_bc_values(bf_ctx* ctx, int32_t end, int32_t kind, const double* values);
+/* The same without the wait for the upload: `values` must be page-locked (bf_host_alloc)
+ * and must stay unchanged until the next bf_evolve / bf_newton_iteration has returned
+ * (a host that refills the same buffer once per time step satisfies this by construction). */
+int bf_set_bc_values_async(bf_ctx* ctx, int32_t end, int32_t kind, const double* values);
 /* Patch values of W and Theta at one end of every beam ([nBeams][3] each) in one
  * call -- the per-step read of functionObjects/beamDisplacements
  * (functionObjects/beamDisplacements/beamDisplacements.C) -- equal to
  * bf_get_field(W, ...) + bf_get_field(THETA, ...) for that side. */
 int bf_get_patch_pair(bf_ctx* ctx, int32_t end, double* W, double* Theta);
+/* Step outputs: registers two page-locked host arrays ([nBeams][3] each, bf_host_alloc) that
+ * every following bf_evolve fills with the patch values of W and Theta of `end` BEFORE it
+ * returns -- the same values bf_get_patch_pair would deliver, riding behind the Newton loop
+ * on the context's stream, so that a host that reads them after every step
+ * (functionObjects/beamDisplacements) pays no second synchronisation.  W = Theta = NULL
+ * unregisters. */
+int bf_set_step_outputs(bf_ctx* ctx, int32_t end, double* W, double* Theta);
 
 /* Coupled bundles: inter-beam couplings turn the union of block-tridiagonal systems into ONE block-sparse
  * system -- the shape of fvBlockMatrices/multibeamFvBlockMatrix/multibeamFvBlockMatrix.C:298-470 (per-beam tridiagonal blocks

@@ -166,6 +166,7 @@ struct bf_ctx {
     int timeAdvanced; /* set by bf_begin_step (runTime++), cleared by the first Newton iteration after it */
     bf_reduce_fn reducer;
     void* reducerUser;
+    int outEnd; double *outW, *outTheta; /* bf_set_step_outputs */
     int64_t launches;
 };
 
@@ -499,6 +500,14 @@ int bf_set_bc_values(bf_ctx* c, int32_t end, int32_t kind, const double* v)
         default: snprintf(c->err, sizeof c->err, "bf_set_bc_values: unknown kind %d", kind); return BF_ERR_INVALID;
         }
     }
+    return BF_OK;
+}
+
+int bf_set_bc_values_async(bf_ctx* c, int32_t end, int32_t kind, const double* v) { return bf_set_bc_values(c, end, kind, v); }
+int bf_set_step_outputs(bf_ctx* c, int32_t end, double* W, double* Theta)
+{
+    if ((end != BF_END_LEFT && end != BF_END_RIGHT) || (!W) != (!Theta)) { snprintf(c->err, sizeof c->err, "bf_set_step_outputs: bad argument"); return BF_ERR_INVALID; }
+    c->outEnd = end; c->outW = W; c->outTheta = Theta;
     return BF_OK;
 }
 
@@ -1608,6 +1617,7 @@ int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
             break;
         }
     }
+    if (c->outW) bf_get_patch_pair(c, c->outEnd, c->outW, c->outTheta);
     out->nIter = c->iOuterCorr;
     out->status = status;
     out->initialResidualNorm = initialResidualNorm;
