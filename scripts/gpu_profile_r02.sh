@@ -4,7 +4,7 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export BEAMGPU_NO_PIPELINE=1   # one host round trip per iteration: no speculative (early-exit) launches among the captured ones
-WHAT=${@:-launches split65536 perbeam32768 split8192 group4096}   # gpurun copies back at most 64 MiB: two captures per call
+WHAT=${@:-launches split65536 perbeam32768 splitcell8192 splitgroup4096 group4096}   # gpurun copies back at most 64 MiB: two captures per call
 want() { [[ " $WHAT " == *" $1 "* ]]; }
 CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-verify"
 if want launches; then
@@ -20,5 +20,6 @@ cap() { # name modes beams kernel-regex count.  Skips 5 iterations: the captured
 }
 cap split65536 s 65536 '^beam_(forward|backward)_split$' 2
 cap perbeam32768 0 32768 '^beam_(forward|backward)$' 2
-cap split8192 s 8192 '^beam_(forward|backward)_split$' 2
+cap splitcell8192 sc 8192 '^beam_(forward_split|backsub_split|update_faces|update_cells)$' 4
+cap splitgroup4096 w16 4096 '^beam_(forward_ws|backsub_split|update_faces|update_cells)$' 4
 cap group4096 1 4096 '^beam_(forward_ws|backsub|update_faces|update_cells)$' 4
