@@ -21,10 +21,10 @@
 //   beam_backsub     the serial part of the backward sweep only: x_i = bPrime_i - uPrime_i x_{i+1}, one thread per beam,
 //                    uPrime/bPrime streamed through a 4-cell cp.async ring in shared memory (the loads do not depend on x,
 //                    so the chain never waits for memory), x written to a tiled [cell][6][32] array.
-//   beam_update_faces / beam_update_cells   updateSolutionVariables (Evolve.C:757-923) and the patch evaluate()s with one
-//                    thread per CELL over the whole bundle: no serial dependence once x is known, so the latency of this
-//                    (HBM-bound) part is hidden by occupancy, not by the length of a beam.  Faces first (they read the
-//                    neighbour cell's pre-update W), then cells and the norms.
+//   beam_update      updateSolutionVariables (Evolve.C:757-923) and the patch evaluate()s with one thread per CELL over the
+//                    whole bundle: no serial dependence once x is known, so the latency of this (HBM-bound) part is hidden by
+//                    occupancy, not by the length of a beam.  A thread updates its cell, the face towards the next cell (with
+//                    the neighbour's pre-update W, which the forward part saved) and the end patches of its beam; norms.
 //
 // State, scratch layout (uPrime/bPrime) and every per-cell / per-face formula are shared with the one-thread-per-beam
 // kernels, so the two forward and the two backward implementations are interchangeable (tests/test_gpu_coop.py runs all
@@ -151,6 +151,7 @@ DEV void wsAssembleCell(const BeamParams& p, const int b, const int row, const b
 #pragma unroll
     for (int r = 0; r < 6; r++) src[r] = 0.0;
     const V3 Wi = ld3(p.W, tileRow(T, Rc, row, 3, lb), TS);
+    if (p.wSave) st3(p.wSave, tileRow(T, Rc, row, 3, lb), TS, Wi); // this cell's pre-update W, for beam_update
     if (firstCell) { // end patch (BC.C:64-1190): its 6x6 part starts the carry, its source part joins the own source
         double D36[36], s6[6];
 #pragma unroll
@@ -636,28 +637,16 @@ __global__ void __launch_bounds__(32) beam_backsub_split(const __grid_constant__
 // ---------------------------------------------------------------------------------------------------------------------
 // backward, parallel part: one thread per (tile, cell, lane) = per cell of the bundle, beams fastest (coalesced rows).
 // ---------------------------------------------------------------------------------------------------------------------
-DEV bool cellOfThread(const BeamParams& p, int& b, int& i)
-{
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = (int)(t & 31);
-    const size_t row = t >> 5; // T * nmax + i
-    const size_t T = row / (size_t)p.nmax;
-    i = (int)(row - T * (size_t)p.nmax);
-    b = (int)(T * 32) + lane;
-    return b < p.B && i < p.nSeg[b];
-}
-DEV void ldX(const double* __restrict__ X, size_t T, int Rc, int i, int lane, V3& a, V3& c)
-{
-    const size_t x0 = tileRow(T, Rc, i, 6, lane);
-    a = v3(X[x0], X[x0 + TS], X[x0 + 2 * TS]);
-    c = v3(X[x0 + 3 * TS], X[x0 + 4 * TS], X[x0 + 5 * TS]);
-}
-// Faces first: they read the neighbour cell's pre-update W ...
-// Everything a face update reads is requested up front, before the first branch on a loaded value (cell count of the beam, end
+// updateSolutionVariables (Evolve.C:757-923) and the patch evaluate()s for ONE cell and the faces it owns, one thread per cell.
+// The face between cells i and i+1 needs the pre-update W of BOTH cells while the thread of cell i+1 is writing its new W: the
+// forward part of the iteration saved every cell's old W (BeamParams::wSave, three streaming stores per cell from a register it
+// holds anyway), so the two updates have no read-after-write hazard and run in one kernel -- one launch and 9 of 73 doubles per
+// cell less than a faces kernel followed by a cells kernel.
+// Everything the thread reads is requested up front, before the first branch on a loaded value (cell count of the beam, end
 // patches): one round trip to DRAM per thread instead of four or five dependent ones -- with one thread per cell there is no
 // loop to hide them behind, only other warps.  Rows are clamped, not predicated: the arrays are allocated for the padded bundle.
-#ifndef BEAM_FACES_MIN_BLOCKS
-#define BEAM_FACES_MIN_BLOCKS 3
+#ifndef BEAM_UPDATE_MIN_BLOCKS
+#define BEAM_UPDATE_MIN_BLOCKS 3
 #endif
 // A load the compiler must issue where it stands: left to itself it sinks every load below the early-exit branch and next to
 // its first use (to save registers), which turns one round trip into a chain of them.
@@ -668,55 +657,59 @@ DEV double ldNow(const double* p)
     return v;
 }
 DEV V3 ldNow3(const double* __restrict__ p, size_t i, size_t s) { return v3(ldNow(p + i), ldNow(p + i + s), ldNow(p + i + 2 * s)); }
-__global__ void __launch_bounds__(128, BEAM_FACES_MIN_BLOCKS) beam_update_faces(const __grid_constant__ BeamParams p, const double* __restrict__ X)
+template <int SCHEME>
+__global__ void __launch_bounds__(128, BEAM_UPDATE_MIN_BLOCKS) beam_update(const __grid_constant__ BeamParams p, const double* __restrict__ X)
 {
     if (convLeave(p.cv, true)) return;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = (int)(t & 31), Rc = p.nmax, Rf = p.nmax + 1;
     const size_t row = t >> 5, T = row / (size_t)Rc, sb = p.Bpad;
     const int i = (int)(row - T * (size_t)Rc), b = (int)(T * 32) + lane;
-    if (T * 32 >= (size_t)p.Bpad) return;
-    const int iN = min(i + 1, Rc - 1);
-    const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f4 = tileRow(T, Rf, i + 1, 4, lane);
-    const size_t x0 = tileRow(T, Rc, i, 6, lane), xN = tileRow(T, Rc, iN, 6, lane);
-    // from DRAM first ...
-    const Q4 qfOld = q4(ldNow(p.Lf + f4), ldNow(p.Lf + f4 + TS), ldNow(p.Lf + f4 + 2 * TS), ldNow(p.Lf + f4 + 3 * TS));
-    const V3 Kold = ldNow3(p.K, f3, TS), Qold = ldNow3(p.Q, f3, TS), Mold = ldNow3(p.M, f3, TS);
-    const V3 Wold = ldNow3(p.W, tileRow(T, Rc, i, 3, lane), TS), WoldN = ldNow3(p.W, tileRow(T, Rc, iN, 3, lane), TS);
-    const V3 DW = ldNow3(X, x0, TS), DT = ldNow3(X, x0 + 3 * TS, TS), xWn = ldNow3(X, xN, TS), xTn = ldNow3(X, xN + 3 * TS, TS);
-    // ... then the per-beam constants (cache hits)
-    const int n = p.nSeg[b];
-    const double dZ = ldNow(p.dZ + b);
-    const V3 CQ = ldNow3(p.CQ, b, sb), CM = ldNow3(p.CM, b, sb);
-    M3 refL;
-#pragma unroll
-    for (int k = 0; k < 9; k++) refL.a[k] = ldNow(p.refL + b + k * sb);
-    if (b >= p.B || i >= n) return;
-    const double dcI = 1.0 / dZ, dcB = 2.0 / dZ, delta = 1.0 / dcB;
-    if (i < n - 1) { // internal face i+1 (Evolve.C:804-836, 881-913), owner = this cell, neighbour = cell i+1
-        const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]), e0 = mulT(refL, dR0);
-        const M3 LmOld = quatToMat(qfOld);
-        const V3 tv = dR0 + dcI * (WoldN - Wold);
-        const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, tv), Kold, Qold, Mold, tv, dcI, false);
-        const FaceState o = updateFace(f, qfOld, LmOld, Kold, DW, xWn, DT, xTn, dcI, false);
-        stq(p.Lf, f4, TS, o.Lf);
-        st3(p.K, f3, TS, o.K); st3(p.Q, f3, TS, o.Q); st3(p.M, f3, TS, o.M);
-    } else
-        updatePatchFace(p, b, 1, n, CQ, CM, dcB, delta, Wold, DW, DT);
-    if (i == 0) updatePatchFace(p, b, 0, n, CQ, CM, dcB, delta, Wold, DW, DT);
-}
-// ... then the cells, and the two solution norms.
-template <int SCHEME>
-__global__ void __launch_bounds__(128) beam_update_cells(const __grid_constant__ BeamParams p, const double* __restrict__ X)
-{
-    if (convLeave(p.cv, true)) return;
-    int b, i;
     double v[2] = {0.0, 0.0};
-    if (cellOfThread(p, b, i)) {
-        V3 DW, DT, Wold;
-        ldX(X, (size_t)(b >> 5), p.nmax, i, b & 31, DW, DT);
-        v[0] = DW.x * DW.x + DW.y * DW.y + DW.z * DW.z + DT.x * DT.x + DT.y * DT.y + DT.z * DT.z;
-        updateCell<SCHEME>(p, (size_t)(b >> 5), b & 31, i, DW, DT, Wold, v[1]);
+    if (T * 32 < (size_t)p.Bpad) {
+        const int iN = min(i + 1, Rc - 1);
+        const size_t f3 = tileRow(T, Rf, i + 1, 3, lane), f4 = tileRow(T, Rf, i + 1, 4, lane);
+        const size_t x0 = tileRow(T, Rc, i, 6, lane), xN = tileRow(T, Rc, iN, 6, lane);
+        // from DRAM first ...
+        const Q4 qfOld = q4(ldNow(p.Lf + f4), ldNow(p.Lf + f4 + TS), ldNow(p.Lf + f4 + 2 * TS), ldNow(p.Lf + f4 + 3 * TS));
+        const V3 Kold = ldNow3(p.K, f3, TS), Qold = ldNow3(p.Q, f3, TS), Mold = ldNow3(p.M, f3, TS);
+        const V3 WoldN = ldNow3(p.wSave, tileRow(T, Rc, iN, 3, lane), TS);
+        CellOld old; // the cell's own rows (its W is still the old one: only this thread writes it)
+        {
+            const size_t c3 = tileRow(T, Rc, i, 3, lane), c4 = tileRow(T, Rc, i, 4, lane);
+            old.W = ldNow3(p.W, c3, TS);
+            old.q = q4(ldNow(p.Lam + c4), ldNow(p.Lam + c4 + TS), ldNow(p.Lam + c4 + 2 * TS), ldNow(p.Lam + c4 + 3 * TS));
+            old.Th = ldNow3(p.Th, c3, TS);
+            old.Ac = old.dOm = v3(0, 0, 0);
+            if (SCHEME == BFK_NEWMARK) { old.Ac = ldNow3(p.Ac, c3, TS); old.dOm = ldNow3(p.dOm, c3, TS); }
+        }
+        const V3 DW = ldNow3(X, x0, TS), DT = ldNow3(X, x0 + 3 * TS, TS), xWn = ldNow3(X, xN, TS), xTn = ldNow3(X, xN + 3 * TS, TS);
+        // ... then the per-beam constants (cache hits)
+        const int n = p.nSeg[b];
+        const double dZ = ldNow(p.dZ + b);
+        const V3 CQ = ldNow3(p.CQ, b, sb), CM = ldNow3(p.CM, b, sb);
+        M3 refL;
+#pragma unroll
+        for (int k = 0; k < 9; k++) refL.a[k] = ldNow(p.refL + b + k * sb);
+        if (b < p.B && i < n) {
+            // ---- the cell
+            const V3 Wold = old.W;
+            v[0] = DW.x * DW.x + DW.y * DW.y + DW.z * DW.z + DT.x * DT.x + DT.y * DT.y + DT.z * DT.z;
+            updateCellFrom<SCHEME>(p, T, lane, i, DW, DT, old, v[1]);
+            // ---- the faces it owns
+            const double dcI = 1.0 / dZ, dcB = 2.0 / dZ, delta = 1.0 / dcB;
+            if (i < n - 1) { // internal face i+1 (Evolve.C:804-836, 881-913), owner = this cell, neighbour = cell i+1
+                const V3 dR0 = v3(refL.a[0], refL.a[3], refL.a[6]), e0 = mulT(refL, dR0);
+                const M3 LmOld = quatToMat(qfOld);
+                const V3 tv = dR0 + dcI * (WoldN - Wold);
+                const FaceCoef f = faceCoefficients(LmOld, CQ, CM, gammaOf(LmOld, e0, tv), Kold, Qold, Mold, tv, dcI, false);
+                const FaceState o = updateFace(f, qfOld, LmOld, Kold, DW, xWn, DT, xTn, dcI, false);
+                stq(p.Lf, f4, TS, o.Lf);
+                st3(p.K, f3, TS, o.K); st3(p.Q, f3, TS, o.Q); st3(p.M, f3, TS, o.M);
+            } else
+                updatePatchFace(p, b, 1, n, CQ, CM, dcB, delta, Wold, DW, DT);
+            if (i == 0) updatePatchFace(p, b, 0, n, CQ, CM, dcB, delta, Wold, DW, DT);
+        }
     }
     blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
 }

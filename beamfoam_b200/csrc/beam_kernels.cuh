@@ -103,6 +103,8 @@ struct BeamParams {
     // ends [2][nc][Bpad]
     double *Wb, *Thb, *Lamb, *DWb, *DThb, *force;
     double* ifW; // [3][Bpad] split sweeps: pre-update W of the cell left of the interface
+    double* wSave; // cells [tile][nmax][3][32]: the pre-update W, saved by the forward part for beam_update (one thread per cell: a
+                   // cell's thread reads its neighbour's OLD W while the neighbour's thread writes the new one); null otherwise
     const double *wPresc, *thPresc, *follower, *offset, *moment, *springK, *springDir;
     // block-Thomas scratch
     double* uP; // [tile][nmax][36][32]
@@ -1383,24 +1385,38 @@ __device__ __noinline__ FaceState patchUpdate(const BeamParams& p, int end, int 
     return updateFace(f, qOld, LmOld, Kold, DWc, DWb, DTc, DTb, dcB, true);
 }
 
-// updateSolutionVariables for ONE cell (Evolve.C:759-802, 839-869): Theta, W, Lambda and the time-scheme fields.
-// DW, DT = the solved increments of the cell; returns the pre-update W (the faces need it) and adds |W|^2 + |Theta|^2.
+// The rows of a cell that its update reads on every iteration (Newmark: + Accl, dotOmega).
+struct CellOld {
+    V3 W, Th, Ac, dOm;
+    Q4 q;
+};
 template <int SCHEME>
-DEV void updateCell(const BeamParams& p, const size_t T, const int lane, const int i, const V3 DW, const V3 DT, V3& WoldOut,
-                    double& x2)
+DEV CellOld loadCellOld(const BeamParams& p, const size_t T, const int lane, const int i)
+{
+    CellOld o;
+    const size_t c3 = tileRow(T, p.nmax, i, 3, lane), c4 = tileRow(T, p.nmax, i, 4, lane);
+    o.W = ld3(p.W, c3, TS);
+    o.q = ldq(p.Lam, c4, TS);
+    o.Th = ld3(p.Th, c3, TS);
+    o.Ac = o.dOm = v3(0, 0, 0);
+    if (SCHEME == BFK_NEWMARK) { o.Ac = ld3(p.Ac, c3, TS); o.dOm = ld3(p.dOm, c3, TS); }
+    return o;
+}
+template <int SCHEME>
+DEV void updateCellFrom(const BeamParams& p, const size_t T, const int lane, const int i, const V3 DW, const V3 DT, const CellOld& old,
+                        double& x2)
 {
     const size_t s = TS;
     const int Rc = p.nmax;
     const double dt = p.dt, gamma = p.gamma;
     // ---- cell i: Evolve.C:759-802, 839-863
     const size_t c3 = tileRow(T, Rc, i, 3, lane), c4 = tileRow(T, Rc, i, 4, lane);
-    const V3 Wold = ld3(p.W, c3, s);
-    WoldOut = Wold;
-    const Q4 qOld = ldq(p.Lam, c4, s);
+    const V3 Wold = old.W;
+    const Q4 qOld = old.q;
     // Lambda.T() & DTheta.  R(DTheta) leaves its own axis unchanged, so this vector is the same for
     // the Lambda before the update (:759) and after it (:853-862): (R Lambda).T() & DT = Lambda.T() & DT
     const V3 LtDT = mulT(quatToMat(qOld), DT);
-    const V3 Thn = ld3(p.Th, c3, s) + LtDT;             // :759
+    const V3 Thn = old.Th + LtDT;                       // :759
     const V3 Wnew = Wold + DW;                          // :769
     st3(p.Th, c3, s, Thn);
     st3(p.W, c3, s, Wnew);
@@ -1409,7 +1425,7 @@ DEV void updateCell(const BeamParams& p, const size_t T, const int lane, const i
     x2 += dot(Wnew, Wnew) + dot(Thn, Thn);
     if (p.storeInc) { st3(p.DW, c3, s, DW); st3(p.DTh, c3, s, DT); }
     if (SCHEME == BFK_NEWMARK) {
-        V3 Ac = ld3(p.Ac, c3, s), dOm = ld3(p.dOm, c3, s);
+        V3 Ac = old.Ac, dOm = old.dOm;
         if (p.first) { // predictor :167-186, and the step constants U*, Omega* (see BeamParams)
             const double k1 = p.nk1, k2 = p.nk2;
             const V3 Ao = Ac, dOo = dOm;
@@ -1441,6 +1457,17 @@ DEV void updateCell(const BeamParams& p, const size_t T, const int lane, const i
         const M3 Pm = mulTM(Ln, idt * (Ln - Lo)); // Lambda.T() & ddt(Lambda)
         st3(p.Om, c3, s, v3(Pm.a[7], Pm.a[2], Pm.a[3])); // axialVector: (T.zy, T.xz, T.yx)
     }
+}
+
+// updateSolutionVariables for ONE cell (Evolve.C:759-802, 839-869): Theta, W, Lambda and the time-scheme fields.
+// DW, DT = the solved increments of the cell; returns the pre-update W (the faces need it) and adds |W|^2 + |Theta|^2.
+template <int SCHEME>
+DEV void updateCell(const BeamParams& p, const size_t T, const int lane, const int i, const V3 DW, const V3 DT, V3& WoldOut,
+                    double& x2)
+{
+    const CellOld old = loadCellOld<SCHEME>(p, T, lane, i);
+    WoldOut = old.W;
+    updateCellFrom<SCHEME>(p, T, lane, i, DW, DT, old, x2);
 }
 
 // Update of the internal face j (between cell j-1, its owner (A), and cell j, its neighbour (B)): Evolve.C:804-836, 881-913
@@ -1614,7 +1641,7 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_BWD_MIN_BLOCKS) beam_backwa
 //   updates cells h..n-1, faces h..n-1 (face c together with cell c) and the right patch.  The interface face h needs the
 //   pre-update W of cell h-1, which the left half overwrites concurrently: the mirrored half's forward sweep saves it (ifW).
 // ---------------------------------------------------------------------------
-template <int SCHEME, bool MIR>
+template <int SCHEME, bool MIR, bool SAVEW>
 DEV double forwardSweepSplit(const BeamParams& p, const int b, double* __restrict__ warpSm, uint64_t* bar, uint32_t& phase)
 {
     const size_t s = p.Bpad;
@@ -1665,6 +1692,7 @@ DEV double forwardSweepSplit(const BeamParams& p, const int b, double* __restric
         else if (i + 1 < m) fwdPrefetchFaceRows<SCHEME>(p, T, warpSm, bar, SROW(i + 1), SROW(i + 2), SFACE(i + 1));
         if (MIR && i == m - 1) // pre-update W of cell h-1, for the interface face in the backward sweep
             st3(p.ifW, b, s, in.Wn);
+        if (SAVEW) st3(p.wSave, tileRow(T, p.nmax, SROW(i), 3, lane), TS, Wi); // this cell's pre-update W, for beam_update
         double src[6], Dc[6][6];
         const double dz = smLd(sm, R_DZ);
         fwdFacePart<false, MIR>(p, b, sm, rcpFast(dz), 0.5 * dz, in, Dc, src, Wi);
@@ -1806,7 +1834,7 @@ DEV void backwardSweepSplit(const BeamParams& p, const int b, double& dx2, doubl
 }
 
 // grid (ceil(B / BEAM_THREADS), 2): blockIdx.y = 0 the left halves, 1 the mirrored halves
-template <int SCHEME>
+template <int SCHEME, bool SAVEW>
 __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward_split(const __grid_constant__ BeamParams p)
 {
     extern __shared__ __align__(128) unsigned char beam_smem[];
@@ -1815,8 +1843,8 @@ __global__ void __launch_bounds__(BEAM_THREADS, BEAM_MIN_BLOCKS) beam_forward_sp
     uint32_t phase = warpBarrierSetup(beam_smem);
     double v[1] = {0.0};
     if ((b & ~31) < p.Bpad) { // a warp wholly past the padded bundle has no tile in memory (lanes B..Bpad-1 run as dummy beams)
-        if (blockIdx.y) v[0] = forwardSweepSplit<SCHEME, true>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
-        else v[0] = forwardSweepSplit<SCHEME, false>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
+        if (blockIdx.y) v[0] = forwardSweepSplit<SCHEME, true, SAVEW>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
+        else v[0] = forwardSweepSplit<SCHEME, false, SAVEW>(p, b, WARP_SLAB(beam_smem, w), (uint64_t*)beam_smem + w, phase);
     }
     blockReduceStore<1>(v, p.partial, 0, p.nTiles, blockIdx.y * gridDim.x + blockIdx.x);
 }

@@ -51,7 +51,8 @@ struct bf_ctx {
     int wsEw;  // eliminator warps per block: 1, or 2 (wsBpb = 32: the two column groups of a beam in two warps)
     int split; // two threads per beam (beam_forward_split / beam_backward_split): uniform bundles between the two other families
     double* d_ifW;
-    double* d_X; // coopBwd: the solution increments, tiled [tile][nmax][6][32] (beam_backsub -> beam_update_*)
+    double* d_X; // coopBwd: the solution increments, tiled [tile][nmax][6][32] (beam_backsub -> beam_update)
+    double* d_Wsave; // coopBwd: the pre-update W of every cell, tiled like W (saved by the forward part, read by beam_update)
     int partialStride; // leading dimension of d_partial: the largest block count of any kernel family
     std::vector<int32_t> nSeg, hostWType; // hostWType: [2][B]
     std::vector<int64_t> cellStart, faceStart;
@@ -470,7 +471,11 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     CREATE_CUDA(cudaFuncSetAttribute(KERNEL<BFK_EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES))
     OPT_IN_SMEM(beam_newton);
     OPT_IN_SMEM(beam_forward);
-    OPT_IN_SMEM(beam_forward_split);
+#define OPT_IN_SMEM2(KERNEL, FLAG)                                                                                                \
+    CREATE_CUDA((cudaFuncSetAttribute(KERNEL<BFK_STEADY, FLAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)));  \
+    CREATE_CUDA((cudaFuncSetAttribute(KERNEL<BFK_NEWMARK, FLAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES))); \
+    CREATE_CUDA((cudaFuncSetAttribute(KERNEL<BFK_EULER, FLAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)))
+    OPT_IN_SMEM2(beam_forward_split, false); OPT_IN_SMEM2(beam_forward_split, true);
 #define OPT_IN_WS(BPB, SPLIT, EW)                                                                                                                              \
     CREATE_CUDA((cudaFuncSetAttribute(beam_forward_ws<BFK_STEADY, BPB, SPLIT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES(BPB, EW))));  \
     CREATE_CUDA((cudaFuncSetAttribute(beam_forward_ws<BFK_NEWMARK, BPB, SPLIT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES(BPB, EW)))); \
@@ -607,8 +612,9 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
                 c->coopFwd = 8L * w <= S ? 1 : 0;               // split group forward: all its warps resident at once
             }
         }
-        c->d_X = nullptr;
-        if (c->coopBwd && devAlloc(c, (void**)&c->d_X, sizeof(double) * 6 * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        c->d_X = c->d_Wsave = nullptr;
+        if (c->coopBwd && devAlloc(c, (void**)&c->d_X, sizeof(double) * 9 * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        if (c->coopBwd) c->d_Wsave = c->d_X + 6 * nc_ * bp;
         // BEAMGPU_LONG_BEAMS = 1 / 0 forces the cell-parallel path on / off; by default it serves bundles that cannot
         // occupy the GPU with one thread per beam but have enough cells per beam to do so with one thread per cell
         const char* lm = getenv("BEAMGPU_LONG_BEAMS");
@@ -1227,7 +1233,7 @@ static BeamParams makeParams(bf_ctx* c)
     p.Lf = c->d_Lf; p.K = c->d_K; p.Q = c->d_Q; p.M = c->d_M;
     p.Wb = c->d_Wb; p.Thb = c->d_Thb; p.Lamb = c->d_Lamb; p.DWb = c->d_DWb; p.DThb = c->d_DThb; p.force = c->d_force;
     p.wPresc = c->d_wPresc; p.thPresc = c->d_thPresc; p.follower = c->d_follower; p.offset = c->d_offset;
-    p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir; p.ifW = c->d_ifW;
+    p.moment = c->d_moment; p.springK = c->d_springK; p.springDir = c->d_springDir; p.ifW = c->d_ifW; p.wSave = c->d_Wsave;
     p.uP = c->d_uP; p.bP = c->d_bP; p.partial = c->d_partial;
     p.nTiles = c->partialStride;
     p.cv = c->cvNow;
@@ -1343,17 +1349,24 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
         const dim3 g2((unsigned)c->grid, 2);
         nF = nB = 2 * c->grid;
         if (c->coopFwd) nF = launchForwardWs(c, p); // assembler + eliminator warps per half beam
-        else LAUNCH_SCHEME(beam_forward_split, g2, SMEM_BYTES, p);
+        else if (c->coopBwd) { // the cell-parallel update reads the pre-update W the sweep saves
+            if (c->scheme == BF_SCHEME_NEWMARK) beam_forward_split<BFK_NEWMARK, true><<<g2, THREADS, SMEM_BYTES, c->stream>>>(p);
+            else if (c->scheme == BF_SCHEME_EULER) beam_forward_split<BFK_EULER, true><<<g2, THREADS, SMEM_BYTES, c->stream>>>(p);
+            else beam_forward_split<BFK_STEADY, true><<<g2, THREADS, SMEM_BYTES, c->stream>>>(p);
+        } else {
+            if (c->scheme == BF_SCHEME_NEWMARK) beam_forward_split<BFK_NEWMARK, false><<<g2, THREADS, SMEM_BYTES, c->stream>>>(p);
+            else if (c->scheme == BF_SCHEME_EULER) beam_forward_split<BFK_EULER, false><<<g2, THREADS, SMEM_BYTES, c->stream>>>(p);
+            else beam_forward_split<BFK_STEADY, false><<<g2, THREADS, SMEM_BYTES, c->stream>>>(p);
+        }
         if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
         if (c->coopBwd) { // small bundles: serial back-substitution of the two halves, then the update with one thread per cell
             const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
             const dim3 gs((unsigned)(c->Bpad / 32), 2);
             beam_backsub_split<<<gs, 32, BSS_SMEM_BYTES, c->stream>>>(p, c->d_X);
-            beam_update_faces<<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            if (c->scheme == BF_SCHEME_NEWMARK) beam_update_cells<BFK_NEWMARK><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            else if (c->scheme == BF_SCHEME_EULER) beam_update_cells<BFK_EULER><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            else beam_update_cells<BFK_STEADY><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            c->launches += 2;
+            if (c->scheme == BF_SCHEME_NEWMARK) beam_update<BFK_NEWMARK><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            else if (c->scheme == BF_SCHEME_EULER) beam_update<BFK_EULER><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            else beam_update<BFK_STEADY><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            c->launches += 1;
             nB = cellGrid;
         } else
             LAUNCH_SCHEME(beam_backward_split, g2, 0, p);
@@ -1365,12 +1378,13 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
         if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
         const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
         if (c->coopBwd) { // serial back-substitution, then the update with one thread per cell
+            if (!c->coopFwd) // beam_forward does not save the pre-update W (a combination only tests force): a device copy of the array
+                CUDA_OK(c, cudaMemcpyAsync(c->d_Wsave, c->d_W, sizeof(double) * 3 * (size_t)c->nmax * (size_t)c->Bpad, cudaMemcpyDeviceToDevice, c->stream));
             beam_backsub<<<(unsigned)((c->Bpad + BS_THREADS - 1) / BS_THREADS), BS_THREADS, BS_SMEM_BYTES, c->stream>>>(p, c->d_X);
-            beam_update_faces<<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            if (c->scheme == BF_SCHEME_NEWMARK) beam_update_cells<BFK_NEWMARK><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            else if (c->scheme == BF_SCHEME_EULER) beam_update_cells<BFK_EULER><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            else beam_update_cells<BFK_STEADY><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            c->launches += 2;
+            if (c->scheme == BF_SCHEME_NEWMARK) beam_update<BFK_NEWMARK><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            else if (c->scheme == BF_SCHEME_EULER) beam_update<BFK_EULER><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            else beam_update<BFK_STEADY><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            c->launches += 1;
         } else LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
         c->launches += 2;
         nF = c->coopFwd ? nWs : c->grid;

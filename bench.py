@@ -51,13 +51,13 @@ UNIT = "updates/s"
 BYTES_PER_UPDATE = {"Newmark": 760.0, "steadyState": 552.0, "Euler": 760.0}  # 95 / 69 doubles
 HBM_FALLBACK_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
 FAMILY = {0: "one thread per beam (beam_forward / beam_backward)",
-          1: "assembler + eliminator warps (beam_forward_ws), serial back-substitution + one thread per cell (beam_backsub, beam_update_*)",
+          1: "assembler + eliminator warps (beam_forward_ws), serial back-substitution + one thread per cell (beam_backsub, beam_update)",
           2: "one thread per cell, block cyclic reduction (long_*)",
           3: "two threads per beam meeting in the middle (beam_forward_split / beam_backward_split)",
           4: "two threads per beam in the forward sweep (beam_forward_split), serial back-substitution + one thread per cell "
-             "(beam_backsub_split, beam_update_*)",
+             "(beam_backsub_split, beam_update)",
           5: "assembler + eliminator warps per half beam (beam_forward_ws, split), serial back-substitution + one thread per cell "
-             "(beam_backsub_split, beam_update_*)", -1: "cpu"}
+             "(beam_backsub_split, beam_update)", -1: "cpu"}
 # BEAMGPU_COOP, BEAMGPU_SPLIT, BEAMGPU_WS that force a family
 FAMILY_ENV = {0: ("0", "0", None), 1: ("1", "0", None), 3: ("0", "1", None), 4: ("bwd", "1", None), 5: ("bwd", "1", "16")}
 CONFIGS = {
@@ -573,10 +573,10 @@ def run_ours(args):
     kern_ms = fms + bms
     peak, peak_src = hbm_peak()
     achieved = bpu * nCellsLocal / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-    names = {0: ("beam_forward", "beam_backward"), 1: ("beam_forward_ws", "beam_backsub + beam_update_faces + beam_update_cells"),
+    names = {0: ("beam_forward", "beam_backward"), 1: ("beam_forward_ws", "beam_backsub + beam_update"),
              2: ("long_assemble + long_pcr_*", "long_update_*"), 3: ("beam_forward_split", "beam_backward_split"),
-             4: ("beam_forward_split", "beam_backsub_split + beam_update_faces + beam_update_cells"),
-             5: ("beam_forward_ws", "beam_backsub_split + beam_update_faces + beam_update_cells")}[main.family]
+             4: ("beam_forward_split", "beam_backsub_split + beam_update"),
+             5: ("beam_forward_ws", "beam_backsub_split + beam_update")}[main.family]
     tj = load_traffic({0: "per_beam", 1: "group", 2: "cell", 3: "split", 4: "split_cell", 5: "split_group"}[main.family])
     traffic, per_kernel, fp64 = None, None, None
     if tj:

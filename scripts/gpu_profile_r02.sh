@@ -20,6 +20,6 @@ cap() { # name modes beams kernel-regex count.  Skips 5 iterations: the captured
 }
 cap split65536 s 65536 '^beam_(forward|backward)_split$' 2
 cap perbeam32768 0 32768 '^beam_(forward|backward)$' 2
-cap splitcell8192 sc 8192 '^beam_(forward_split|backsub_split|update_faces|update_cells)$' 4
-cap splitgroup4096 w16 4096 '^beam_(forward_ws|backsub_split|update_faces|update_cells)$' 4
-cap group4096 1 4096 '^beam_(forward_ws|backsub|update_faces|update_cells)$' 4
+cap splitcell8192 sc 8192 '^beam_(forward_split|backsub_split|update)$' 3
+cap splitgroup4096 w16 4096 '^beam_(forward_ws|backsub_split|update)$' 3
+cap group4096 1 4096 '^beam_(forward_ws|backsub|update)$' 3

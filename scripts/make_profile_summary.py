@@ -16,9 +16,9 @@ CELLS = 200
 CAPTURES = {  # report -> (family key of traffic.json, beams, forward kernels, backward kernels)
     "split65536": ("split", 65536, ["beam_forward_split"], ["beam_backward_split"]),
     "perbeam32768": ("per_beam", 32768, ["beam_forward"], ["beam_backward"]),
-    "splitcell8192": ("split_cell", 8192, ["beam_forward_split"], ["beam_backsub_split", "beam_update_faces", "beam_update_cells"]),
-    "splitgroup4096": ("split_group", 4096, ["beam_forward_ws"], ["beam_backsub_split", "beam_update_faces", "beam_update_cells"]),
-    "group4096": ("group", 4096, ["beam_forward_ws"], ["beam_backsub", "beam_update_faces", "beam_update_cells"]),
+    "splitcell8192": ("split_cell", 8192, ["beam_forward_split"], ["beam_backsub_split", "beam_update"]),
+    "splitgroup4096": ("split_group", 4096, ["beam_forward_ws"], ["beam_backsub_split", "beam_update"]),
+    "group4096": ("group", 4096, ["beam_forward_ws"], ["beam_backsub", "beam_update"]),
 }
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
