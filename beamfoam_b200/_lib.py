@@ -102,6 +102,7 @@ EXPORTS = {
     "bf_comm_init_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "bf_launch_count": (C.c_int64, [C.c_void_p]),
     "bf_kernel_family": (C.c_int32, [C.c_void_p]),
+    "bf_split_point": (C.c_int32, [C.c_void_p]),
     "bf_newton_iteration_checked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bf_set_couplings": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bf_set_linear_solver": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double]),

@@ -175,7 +175,7 @@ DEV void wsAssembleCell(const BeamParams& p, const int b, const int row, const b
         const V3 Kf = ld3(p.K, f3, TS), Qf = ld3(p.Q, f3, TS), Mf = ld3(p.M, f3, TS);
         const double h = 0.5 * kb.dZ, dcI = kb.dcI, sdc = MIR ? -dcI : dcI;
         const V3 t = v3(kb.dR0.x + sdc * (Wn.x - Wi.x), kb.dR0.y + sdc * (Wn.y - Wi.y), kb.dR0.z + sdc * (Wn.z - Wi.z));
-        if (MIR && p.ifW && row == (p.nmax + 1) / 2) st3(p.ifW, b, p.Bpad, Wn); // pre-update W of cell h-1 (beam_backward_split)
+        if (MIR && p.ifW && row == p.hL) st3(p.ifW, b, p.Bpad, Wn); // pre-update W of cell h-1 (beam_backward_split)
         const V3 th = (MIR ? -h : h) * t;
         const M3 Lm = quatToMat(qf);
         const V3 hQ = (MIR ? -0.5 : 0.5) * Qf;
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(WS_THREADS(EW), EW == 2 ? 4 : 1) beam_forward_
     double* cy = sm + WS_CARRY_OFF + g; // EW = 2: two buffers, cell ic reads buffer ic & 1 and writes the other
     const int n = live ? p.nSeg[b] : 0;
     // cells of this lane's walk: the whole beam, or its half (left: rows 0 .. hL-1 upwards, mirrored: rows nmax-1 .. hL downwards)
-    const int hL = (p.nmax + 1) / 2;
+    const int hL = p.hL;
     const int m = !SPLIT ? n : !live ? 0 : mir ? p.nmax - hL : hL;
     const int nW = __reduce_max_sync(0xffffffffu, m);
     const int nBatches = (nW + NB - 1) / NB;
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(32) beam_backsub_split(const __grid_constant__
     const int b = blockIdx.x * 32 + lane;
     const bool mir = blockIdx.y != 0;
     const size_t T = blockIdx.x;
-    const int Rc = p.nmax, n = p.nmax, hL = (n + 1) / 2;
+    const int Rc = p.nmax, n = p.nmax, hL = p.hL;
     const bool live = b < p.B;
     const int m = mir ? n - hL : hL; // steps of this half; step k visits cell hL + k (mirrored) or hL - 1 - k
     if (lane == 0) {

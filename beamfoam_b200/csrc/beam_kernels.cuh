@@ -62,6 +62,7 @@ struct BeamParams {
     int B;        // beams in this context
     int Bpad;     // padded beam count (leading dimension)
     int nmax;     // max cells per beam
+    int hL;       // split sweeps: the left part of a beam is cells 0 .. hL-1, the mirrored part cells hL .. nmax-1 (1 <= hL < nmax)
     int newmark;  // d2dt2Scheme: BFK_STEADY / BFK_NEWMARK / BFK_EULER (the kernels are instantiated per scheme)
     int first;    // 1 on the first Newton iteration of a time step (Newmark predictor)
     int storeInc; // keep DW/DTheta cell fields
@@ -1649,8 +1650,8 @@ DEV double forwardSweepSplit(const BeamParams& p, const int b, double* __restric
     const size_t T = (size_t)(b >> 5);
     double* sm = warpSm + lane;
     double res = 0.0;
-    const int n = p.nmax, hL = (n + 1) / 2;
-    const int m = MIR ? n - hL : hL; // cells of this half; the host selects the split sweeps only for n >= 2
+    const int n = p.nmax, hL = p.hL;
+    const int m = MIR ? n - hL : hL; // cells of this part; the host selects the split sweeps only for n >= 2
 #define SROW(i) (MIR ? n - 1 - (i) : (i))            // cell row of local cell i
 #define SFACE(i) (MIR ? n - 1 - (i) : (i) + 1)       // the face between local cells i and i+1
     __syncwarp();
@@ -1764,7 +1765,7 @@ DEV void backwardSweepSplit(const BeamParams& p, const int b, double& dx2, doubl
     const size_t s = TS;
     const size_t T = (size_t)(b >> 5);
     const int lane = b & 31, Rc = p.nmax, Rf = p.nmax + 1;
-    const int n = p.nmax, hL = (n + 1) / 2;
+    const int n = p.nmax, hL = p.hL;
     const double dZ = p.dZ[b];
     const double dcI = 1.0 / dZ, dcB = 2.0 / dZ;
     const double delta = 1.0 / dcB;

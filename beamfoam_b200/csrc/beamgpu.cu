@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #define BF_GREAT 1e15
@@ -49,6 +50,7 @@ struct bf_ctx {
     int coopFwd, coopBwd, coopGrid;
     int wsBpb; // beams (half beams with split) per block of beam_forward_ws: 16 (two eliminator lanes per beam) or 32 (one)
     int wsEw;  // eliminator warps per block: 1, or 2 (wsBpb = 32: the two column groups of a beam in two warps)
+    int hL;    // split sweeps: cells of the left part of every beam (BeamParams::hL)
     int split; // two threads per beam (beam_forward_split / beam_backward_split): uniform bundles between the two other families
     double* d_ifW;
     double* d_X; // coopBwd: the solution increments, tiled [tile][nmax][6][32] (beam_backsub -> beam_update)
@@ -157,6 +159,7 @@ extern "C" int64_t bf_num_cells(const bf_ctx* c) { return c->N; }
 extern "C" int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
 extern "C" int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
 extern "C" int64_t bf_launch_count(const bf_ctx* c) { return c->launches; }
+extern "C" int32_t bf_split_point(const bf_ctx* c) { return c->split ? c->hL : 0; }
 extern "C" int32_t bf_kernel_family(const bf_ctx* c) { return (c->longMode || c->nPairs) ? BF_FAMILY_CELL : (c->split && c->coopFwd) ? BF_FAMILY_SPLIT_GROUP : (c->split && c->coopBwd) ? BF_FAMILY_SPLIT_CELL : c->split ? BF_FAMILY_SPLIT : c->coopFwd ? BF_FAMILY_GROUP : BF_FAMILY_PER_BEAM; }
 
 extern "C" int bf_host_alloc(void** p, int64_t bytes)
@@ -612,6 +615,36 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
                 c->coopFwd = 8L * w <= S ? 1 : 0;               // split group forward: all its warps resident at once
             }
         }
+        // Where the two threads of a beam meet.  Equal halves for the single-wave families; the split SWEEPS of a bundle that
+        // takes several rounds of resident blocks (65,536 beams: 512 + 512 blocks of 100 cells on 296 slots = 3.46 rounds, the
+        // last one half empty) choose the parts so that the rounds come out even: blocks are dispatched in order (all left parts,
+        // then all mirrored parts), so list scheduling of `grid` tasks of hL cells followed by `grid` tasks of nmax - hL cells on
+        // the resident slots predicts the length of the launch in cell steps; e.g. 150 + 50 cells -> 350 steps instead of 400.
+        c->hL = (nmax + 1) / 2;
+        if (c->split && !c->coopFwd && !c->coopBwd && nmax >= 8) {
+            int nSm = 148;
+            cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, c->device);
+            const int slots = BEAM_MIN_BLOCKS * nSm, nb = c->grid;
+            auto makespan = [&](int a) {
+                std::vector<long> h(slots, 0); // min-heap of slot finish times
+                auto cmp = [](long x, long y) { return x > y; };
+                for (int pass = 0; pass < 2; pass++)
+                    for (int t = 0; t < nb; t++) {
+                        std::pop_heap(h.begin(), h.end(), cmp);
+                        h.back() += pass ? nmax - a : a;
+                        std::push_heap(h.begin(), h.end(), cmp);
+                    }
+                return *std::max_element(h.begin(), h.end());
+            };
+            const long equal = makespan(c->hL);
+            long best = equal;
+            for (int a = c->hL + 1; a <= nmax - 2; a++) {
+                const long m_ = makespan(a);
+                if (m_ < best) { best = m_; c->hL = a; }
+            }
+            if (best * 100 > equal * 97) c->hL = (nmax + 1) / 2; // not worth leaving the symmetric split
+        }
+        if (const char* e = getenv("BEAMGPU_SPLIT_AT")) { const int a = atoi(e); if (a >= 1 && a < nmax) c->hL = a; }
         c->d_X = c->d_Wsave = nullptr;
         if (c->coopBwd && devAlloc(c, (void**)&c->d_X, sizeof(double) * 9 * nc_ * bp)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         if (c->coopBwd) c->d_Wsave = c->d_X + 6 * nc_ * bp;
@@ -1217,7 +1250,7 @@ static BeamParams makeParams(bf_ctx* c)
 {
     BeamParams p;
     memset(&p, 0, sizeof p);
-    p.B = (int)c->B; p.Bpad = c->Bpad; p.nmax = c->nmax;
+    p.B = (int)c->B; p.Bpad = c->Bpad; p.nmax = c->nmax; p.hL = c->hL;
     p.newmark = c->scheme; p.first = c->timeAdvanced ? 1 : 0; p.storeInc = c->storeInc;
     p.dt = c->deltaT; p.beta = c->betaN; p.gamma = c->gammaN;
     p.nk1 = 1.0 / (p.dt * p.beta); p.nk2 = 0.5 / p.beta - 1.0; p.nVel = p.gamma / (p.beta * p.dt);

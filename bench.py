@@ -474,7 +474,9 @@ def verify(args, D: Dist, lib, case, total, main: Bundle, iters, tips):
     out = {}
     # (1) a sample of this rank's beams as a stand-alone bundle, same kernel family, same per-step iteration counts
     S = min(256, hi - lo)
-    saved = {k: os.environ.get(k) for k in ("BEAMGPU_COOP", "BEAMGPU_SPLIT", "BEAMGPU_WS")}
+    saved = {k: os.environ.get(k) for k in ("BEAMGPU_COOP", "BEAMGPU_SPLIT", "BEAMGPU_WS", "BEAMGPU_SPLIT_AT")}
+    if int(lib.bf_split_point(main.ctx)) > 0:  # the sample must meet in the middle where the bundle does (rounding)
+        os.environ["BEAMGPU_SPLIT_AT"] = str(int(lib.bf_split_point(main.ctx)))
     if main.family in FAMILY_ENV:
         os.environ["BEAMGPU_COOP"], os.environ["BEAMGPU_SPLIT"], ws = FAMILY_ENV[main.family]
         if ws:

@@ -379,6 +379,9 @@ int64_t bf_launch_count(const bf_ctx* ctx);
 #define BF_FAMILY_SPLIT_CELL 4 /* split forward sweep, backward sweep with one thread per cell (small uniform bundles) */
 #define BF_FAMILY_SPLIT_GROUP 5 /* assembler + eliminator warps per HALF beam, backward sweep with one thread per cell (bundles below half a wave) */
 int32_t bf_kernel_family(const bf_ctx* ctx);
+/* Split families: the number of cells of the left part of every beam (the two threads of a beam meet at the face after it);
+ * 0 otherwise.  BEAMGPU_SPLIT_AT in the environment of bf_create forces it (diagnostic: results depend on it at rounding level). */
+int32_t bf_split_point(const bf_ctx* ctx);
 int bf_kernel_time_ms(bf_ctx* ctx, int32_t reset, double* fwd_ms, double* bwd_ms,
                       int64_t* iterations);
 int bf_set_timing(bf_ctx* ctx, int32_t enabled);

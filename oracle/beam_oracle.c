@@ -186,6 +186,7 @@ int64_t bf_num_internal_faces(const bf_ctx* c) { return c->F; }
 int64_t bf_num_beams(const bf_ctx* c) { return c->B; }
 int64_t bf_launch_count(const bf_ctx* c) { (void)c; return 0; }
 int32_t bf_kernel_family(const bf_ctx* c) { (void)c; return BF_FAMILY_CPU; }
+int32_t bf_split_point(const bf_ctx* c) { (void)c; return 0; }
 int bf_set_couplings(bf_ctx* c, int64_t nPairs, const int64_t* cellA, const int64_t* cellB, const double* stiffness)
 {
     if (nPairs < 0 || (nPairs > 0 && (!cellA || !cellB || !stiffness))) { snprintf(c->err, sizeof c->err, "bf_set_couplings: bad argument"); return BF_ERR_INVALID; }

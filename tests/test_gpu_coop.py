@@ -143,3 +143,21 @@ def test_second_evolve_in_one_time_step(gpu_lib, oracle_lib):
             assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b))
         g.close()
         o.close()
+
+
+@pytest.mark.parametrize("family", ["split", "split_cell", "split_group16", "split_group16_sweep"])
+@pytest.mark.parametrize("at", [1, 9, 30, 36])
+def test_unequal_split(gpu_lib, oracle_lib, family, at):
+    """The two threads of a beam may meet anywhere (bf_create moves the meeting face of a multi-round bundle so that the rounds
+    of resident blocks come out even, e.g. 150 + 50 cells for 65,536 beams): parts of 1, 9, 30 and 36 of 37 cells."""
+    set_family(family)
+    os.environ["BEAMGPU_SPLIT_AT"] = str(at)
+    try:
+        case = cases.multiBeamDensity(70, 37, jitter=True)
+        m = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
+        assert gpu_lib.bf_split_point(m._ctx) == at
+        m.close()
+        run_pair(case, gpu_lib, oracle_lib, nSteps=12)
+    finally:
+        os.environ.pop("BEAMGPU_SPLIT_AT", None)
+        clear_family()
