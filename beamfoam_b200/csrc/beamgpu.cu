@@ -580,8 +580,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         //      beams        4096   8192   16384  32768  65536
         //      per beam     1.17   1.18   1.20   1.84   3.69   one thread per beam: flat below one wave (37,888 beams)
         //      split        0.61   0.63   1.01   1.93   3.51   two threads per beam, half the serial length
-        //      split cell   0.47   0.63   1.17                 split forward sweep, backward part with one thread per cell
-        //      split group  0.40   0.77   1.41                 assembler + eliminator warps per half beam (16 per block), cell-parallel backward
+        //      split cell   0.45   0.61   1.17                 split forward sweep, backward part with one thread per cell
+        //      split group  0.395  0.76   1.41                assembler + eliminator warps per half beam (16 per block), cell-parallel backward
         //      group        0.60   0.96   1.87   3.48   6.72   the same for whole beams (serves ragged bundles)
         // With w = B/32 warps and S = 8 warps x SMs resident, one thread per beam costs ceil(w/S) sweep rounds and the split
         // sweeps ceil(2w/S)/2: split when that is fewer, or equal with more than one round (the shorter tasks fill the last
