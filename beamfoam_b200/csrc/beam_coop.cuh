@@ -47,15 +47,19 @@
 #define WS_BATCH(BPB) (32 / (BPB)) // cells per beam per assembler pass
 // record rows (per cell; row k of column col at rec[k * WS_COLS + col], col = buffer * 32 + slot * BPB + beam)
 enum {
-    K_DI = 0,   // 10: inertia part of d_i: QRhoCoeff, then the 3x3 MRhoCoeff block (Evolve.C:459-535)
+    K_DI = 0,   // 1: QRhoCoeff (inertia part of the translational diagonal, Evolve.C:459-535)
+    K_EO = 1,   // 9: own part of the rotational diagonal block: ((S3 - S1) + S2) + MRhoCoeff; S2 = -spin(hM)
     K_SO = 10,  // 6: own part of source_i (face i+1, loads, inertia, end patches)
     K_SN = 16,  // 6: neighbour part of source_{i+1} from face i+1: (eQ ; eM - eMQ)
-    K_P = 22,   // 9: P = a CQW
-    K_QT = 31,  // 9: Qt = 0.5 CQTheta
-    K_S1 = 40,  // 9: S1 = a CMTheta
-    K_S3 = 49,  // 9: S3 = 0.5 CMQTheta
-    K_HM = 58,  // 3: hM = 0.5 M of the face (0.5 CMTheta2 = -spin(hM))
-    K_ROWS = 61,
+    // the blocks of u_i = [[P, Qt], [-Qt.T(), Su]] and of the neighbour part N = [[-P, -Qt], [-Qt.T(), Sd]] of d_{i+1}, laid out
+    // so that the column group of a lane (role 0: columns 0..2, role 1: columns 3..5) is an ADDRESS offset, not a select:
+    K_P = 22,   // 9: P = a CQW                                  u11          (+ 9 role -> u12)
+    K_QT = 31,  // 9: Qt = 0.5 CQTheta                           u12
+    K_NQT = 40, // 9: -Qt.T()                                    u21 = N21    (+ 9 role -> u22, + 18 role -> N22)
+    K_SU = 49,  // 9: Su = (S1 + S3) + S2                        u22          S1 = a CMTheta, S3 = 0.5 CMQTheta
+    K_SD = 58,  // 9: Sd = (S3 - S2) - S1                        N22
+    K_SL = 67,  // 9: Sl = S1 + (S3 - S2)                        l22
+    K_ROWS = 76,
     K_PD = K_SN // the LAST cell of a beam has no face i+1: rows K_SN .. K_SN+35 hold the right-patch closure (6x6, row-major)
 };
 #define WS_COLS 64
@@ -167,6 +171,7 @@ DEV void wsAssembleCell(const BeamParams& p, const int b, const int row, const b
             for (int c = 0; c < 6; c++) cyInit[(6 * c + r) * BPB] = D36[6 * r + c]; // the carry is column-major
         }
     }
+    double eo[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // own part of the rotational diagonal block from the face (none for a last cell)
     if (hasFace) { // internal face towards the next cell: the same folded form as fwdFacePart (beam_kernels.cuh)
         const int rowN = MIR ? row - 1 : row + 1, fr = MIR ? row : row + 1;
         const size_t f3 = tileRow(T, Rf, fr, 3, lb);
@@ -207,14 +212,18 @@ DEV void wsAssembleCell(const BeamParams& p, const int b, const int row, const b
         const V3 sn2 = eM - eMQ;
         rec[(K_SN + 0) * WS_COLS] = eQ.x; rec[(K_SN + 1) * WS_COLS] = eQ.y; rec[(K_SN + 2) * WS_COLS] = eQ.z;
         rec[(K_SN + 3) * WS_COLS] = sn2.x; rec[(K_SN + 4) * WS_COLS] = sn2.y; rec[(K_SN + 5) * WS_COLS] = sn2.z;
+        const double s2[9] = {0.0, hM.z, -hM.y, -hM.z, 0.0, hM.x, hM.y, -hM.x, 0.0}; // S2 = -spin(hM)
 #pragma unroll
         for (int k = 0; k < 9; k++) {
+            const double sm3 = S3.a[k] - s2[k]; // S3 - S2
             rec[(K_P + k) * WS_COLS] = Pf.a[k];
             rec[(K_QT + k) * WS_COLS] = Qt.a[k];
-            rec[(K_S1 + k) * WS_COLS] = S1f.a[k];
-            rec[(K_S3 + k) * WS_COLS] = S3.a[k];
+            rec[(K_NQT + k) * WS_COLS] = -Qt.a[3 * (k % 3) + k / 3];
+            rec[(K_SU + k) * WS_COLS] = (S1f.a[k] + S3.a[k]) + s2[k];
+            rec[(K_SD + k) * WS_COLS] = sm3 - S1f.a[k];
+            rec[(K_SL + k) * WS_COLS] = S1f.a[k] + sm3;
+            eo[k] = (S3.a[k] - S1f.a[k]) + s2[k];
         }
-        rec[(K_HM + 0) * WS_COLS] = hM.x; rec[(K_HM + 1) * WS_COLS] = hM.y; rec[(K_HM + 2) * WS_COLS] = hM.z;
     } else { // the last cell of an unsplit beam: right patch instead of a face; its 6x6 part takes the tensor rows of the record
         double D36[36], s6[6];
 #pragma unroll
@@ -237,7 +246,7 @@ DEV void wsAssembleCell(const BeamParams& p, const int b, const int row, const b
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
-        for (int c = 0; c < 3; c++) rec[(K_DI + 1 + 3 * r + c) * WS_COLS] = D[3 + r][3 + c];
+        for (int c = 0; c < 3; c++) rec[(K_EO + 3 * r + c) * WS_COLS] = hasFace ? eo[3 * r + c] + D[3 + r][3 + c] : D[3 + r][3 + c];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
         rec[(K_SO + r) * WS_COLS] = src[r];
@@ -257,16 +266,13 @@ DEV void wsEliminateCell(const BeamParams& p, const size_t T, const int lb, cons
     constexpr int NU = ROLES == 2 ? 3 : 6, NS = NU + 1; // u columns of the lane; slot NU = the right-hand side
 #define RC(k) rc[(k) * WS_COLS]
 #define CY(c, r) cy[(6 * (c) + (r)) * BPB]
-#define UPPER(s) (ROLES == 2 ? role != 0 : (s) >= 3) // the slot's column is one of columns 3..5
-    M3 Pf, Qt, S1, S3, S2;
+#define UPPER(s) (ROLES == 2 ? role : (s) >= 3) // the slot's column is one of columns 3..5 (ROLES = 2: an address offset, see the record)
+    M3 Pf, Qt;
     M3 A, Bm, Cm, E;
     const double qd = RC(K_DI);
     if (!last) {
 #pragma unroll
-        for (int k = 0; k < 9; k++) { Pf.a[k] = RC(K_P + k); Qt.a[k] = RC(K_QT + k); S1.a[k] = RC(K_S1 + k); S3.a[k] = RC(K_S3 + k); }
-        const V3 hM = v3(RC(K_HM), RC(K_HM + 1), RC(K_HM + 2));
-        S2 = m3zero(); // -spin(hM)
-        S2.a[1] = hM.z; S2.a[2] = -hM.y; S2.a[3] = -hM.z; S2.a[5] = hM.x; S2.a[6] = hM.y; S2.a[7] = -hM.x;
+        for (int k = 0; k < 9; k++) { Pf.a[k] = RC(K_P + k); Qt.a[k] = RC(K_QT + k); }
 #pragma unroll
         for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -274,10 +280,10 @@ DEV void wsEliminateCell(const BeamParams& p, const size_t T, const int lb, cons
                 A.a[3 * r + c] = CY(c, r) - Pf.a[3 * r + c] + (r == c ? qd : 0.0);
                 Bm.a[3 * r + c] = CY(c + 3, r) + Qt.a[3 * r + c];
                 Cm.a[3 * r + c] = CY(c, r + 3) + Qt.a[3 * c + r];
-                E.a[3 * r + c] = CY(c + 3, r + 3) + (((S3.a[3 * r + c] - S1.a[3 * r + c]) + S2.a[3 * r + c]) + RC(K_DI + 1 + 3 * r + c));
+                E.a[3 * r + c] = CY(c + 3, r + 3) + RC(K_EO + 3 * r + c);
             }
     } else {
-        Pf = Qt = S1 = S3 = S2 = m3zero();
+        Pf = Qt = m3zero();
 #pragma unroll
         for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -285,19 +291,19 @@ DEV void wsEliminateCell(const BeamParams& p, const size_t T, const int lb, cons
                 A.a[3 * r + c] = CY(c, r) + RC(K_PD + 6 * r + c) + (r == c ? qd : 0.0);
                 Bm.a[3 * r + c] = CY(c + 3, r) + RC(K_PD + 6 * r + c + 3);
                 Cm.a[3 * r + c] = CY(c, r + 3) + RC(K_PD + 6 * (r + 3) + c);
-                E.a[3 * r + c] = CY(c + 3, r + 3) + (RC(K_PD + 6 * (r + 3) + c + 3) + RC(K_DI + 1 + 3 * r + c));
+                E.a[3 * r + c] = CY(c + 3, r + 3) + (RC(K_PD + 6 * (r + 3) + c + 3) + RC(K_EO + 3 * r + c));
             }
     }
     // ---- the lane's right-hand sides: slots 0..NU-1 = its columns of u, slot NU = source - l bPrime (role 0 only)
-    //      u = [[P, Qt], [-Qt.T(), S1 + S3 + S2]]
+    //      u = [[P, Qt], [-Qt.T(), Su]]: column q of the lane's group sits 9 * (group) rows further down the record
     double t1[NS][3], t2[NS][3];
 #pragma unroll
     for (int s = 0; s < NU; s++)
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const int q = s % 3;
-            t1[s][k] = UPPER(s) ? Qt.a[3 * k + q] : Pf.a[3 * k + q];
-            t2[s][k] = UPPER(s) ? (S1.a[3 * k + q] + S3.a[3 * k + q]) + S2.a[3 * k + q] : -Qt.a[3 * q + k];
+            const int q = s % 3, up = UPPER(s) ? 9 : 0;
+            t1[s][k] = RC(K_P + up + 3 * k + q); // (a last cell reads rows of its patch closure here: its u columns are solved
+            t2[s][k] = RC(K_NQT + up + 3 * k + q); //  for but never stored)
         }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -359,16 +365,16 @@ DEV void wsEliminateCell(const BeamParams& p, const size_t T, const int lb, cons
     //      l = [[P, -Qt], [Qt.T(), Sl]], Sl = S1 + S3 - S2;  N = [[-P, -Qt], [-Qt.T(), S3 - S2 - S1]] | srcNei
     M3 Sl;
 #pragma unroll
-    for (int k = 0; k < 9; k++) Sl.a[k] = S1.a[k] + (S3.a[k] - S2.a[k]);
+    for (int k = 0; k < 9; k++) Sl.a[k] = RC(K_SL + k);
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         double n1[3], n2[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             if (s < NU) {
-                const int q = s % 3;
-                n1[k] = -t1[s][k];                                                                       // -P[:, q] or -Qt[:, q]
-                n2[k] = UPPER(s) ? (S3.a[3 * k + q] - S2.a[3 * k + q]) - S1.a[3 * k + q] : t2[s][k];     // Sd[:, q] or -Qt[q, :]
+                const int q = s % 3, up = UPPER(s) ? 18 : 0;
+                n1[k] = -t1[s][k];                      // -P[:, q] or -Qt[:, q]
+                n2[k] = RC(K_NQT + up + 3 * k + q);     // -Qt[q, :] or Sd[:, q]
             } else {
                 n1[k] = RC(K_SN + k);
                 n2[k] = RC(K_SN + 3 + k);

@@ -55,6 +55,7 @@ struct ConvCtl {
     double tag;
     double absTol, resTol, solTol, divTol;
     int nCorr;
+    unsigned long long waitNs; // how long a kernel waits for a peer's record before it gives the peer up (BF_ERR_COMM)
 };
 
 struct BeamParams {
@@ -348,7 +349,15 @@ DEV void stReleaseSys(double* p, double v) { asm volatile("st.release.sys.global
 // round trip of the order of a microsecond; one thread reading 4 nRanks of them in turn cost 45 us per block on 8 GPUs), the
 // sums are then added in rank order through shuffles (bit-identical on every rank).  wait: spin until every rank's record is
 // there.  s[3] = the sums of iteration 0 (the initial residual; its records arrived long ago).  Returns -1: a record is missing
-// (only without wait), 1: a rank had seen the loop end before iteration k, 0: s holds the sums.  Call with all 32 lanes.
+// (only without wait), 1: a rank had seen the loop end before iteration k, 2: a peer's record did not arrive within
+// ConvCtl::waitNs (the peer died or never launched: the kernels must not spin on the GPU for ever -- the loop is treated as ended
+// and the host reports BF_ERR_COMM), 0: s holds the sums.  Call with all 32 lanes.
+DEV unsigned long long globalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 DEV int convSums(const ConvCtl& c, const int k, const bool wait, double (&s)[4])
 {
     const int lane = threadIdx.x & 31;
@@ -357,11 +366,17 @@ DEV int convSums(const ConvCtl& c, const int k, const bool wait, double (&s)[4])
     if (lane < c.nRanks) {
         const double* rec = c.xbuf + ((size_t)k * c.nRanks + lane) * 4;
         double tag;
-        for (;;) {
+        unsigned long long t0 = 0;
+        for (unsigned spins = 0;; spins++) {
             tag = ldAcquireSys(rec + 3);
             if (tag == c.tag || tag == c.tag + 1.0) break;
             if (!wait) { state = -1; break; }
             __nanosleep(100);
+            if ((spins & 1023u) == 1023u) { // look at the clock every ~0.1 ms of waiting
+                const unsigned long long t = globalTimerNs();
+                if (!t0) t0 = t;
+                else if (t - t0 > c.waitNs) { state = 2; break; }
+            }
         }
         if (state == 0) {
             if (tag != c.tag) state = 1;
@@ -371,12 +386,13 @@ DEV int convSums(const ConvCtl& c, const int k, const bool wait, double (&s)[4])
     }
     __syncwarp();
     const bool missing = __any_sync(0xffffffffu, state == -1), ended = __any_sync(0xffffffffu, state == 1);
+    const bool lost = __any_sync(0xffffffffu, state == 2);
     s[0] = s[1] = s[2] = s[3] = 0.0;
     for (int r = 0; r < c.nRanks; r++) {
         s[0] += __shfl_sync(0xffffffffu, v0, r); s[1] += __shfl_sync(0xffffffffu, v1, r);
         s[2] += __shfl_sync(0xffffffffu, v2, r); s[3] += __shfl_sync(0xffffffffu, i0, r);
     }
-    return missing ? -1 : ended ? 1 : 0;
+    return lost ? 2 : missing ? -1 : ended ? 1 : 0;
 }
 // The five exit rules of checkConvergence (Evolve.C:926-1026) on the squared global sums: does the loop end with iteration k?
 DEV bool convRules(const ConvCtl& c, const int k, const double (&s)[4])
@@ -402,7 +418,7 @@ DEV int convDecide(const ConvCtl& c, const int k, const bool wait)
     double s[4];
     const int m = convSums(c, k, wait, s);
     if (m < 0) return -1;
-    const int d = m ? 1 : convRules(c, k, s) ? 1 : 0;
+    const int d = m ? 1 : convRules(c, k, s) ? 1 : 0; // a lost peer (m == 2) ends the loop on this rank as well
     if ((threadIdx.x & 31) == 0) *vf = c.tag + (d == 1 ? 0.5 : 0.25);
     return d;
 }
@@ -1990,7 +2006,7 @@ __global__ void beam_publish_chunk(const ConvCtl cv, const int k0, const int k1,
     if ((threadIdx.x & 31) == 0) {
         double* o = outHost + 4 * (k - k0);
         o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
-        o[3] = ended ? 2.0 : convRules(cv, k, s) ? 1.0 : 0.0;
+        o[3] = ended == 2 ? 3.0 : ended ? 2.0 : convRules(cv, k, s) ? 1.0 : 0.0; // 3: a peer's record never arrived
         __threadfence_system();
     }
 }

@@ -113,6 +113,7 @@ struct bf_ctx {
     // pipelined Newton loop (device-side convergence test, one-sided exchange of the norm sums; beam_kernels.cuh ConvCtl)
     double* d_xbuf;            // [2 banks][CONV_MAXK][xRanks][4], cudaMalloc (its IPC handle is exported to the peers)
     double* d_vflag;           // [2 banks][CONV_MAXK] verdict cache (ConvCtl::vflag), local
+    unsigned long long peerWaitNs; // ConvCtl::waitNs: 20 s, or BEAMGPU_PEER_TIMEOUT_S seconds
     double* peerXbuf[CONV_MAX_RANKS]; // every rank's buffer as mapped into this process (own: d_xbuf)
     int xRanks, xRank;
     long long epoch;
@@ -447,6 +448,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->evRegion[0] = c->evRegion[1] = nullptr;
     c->nPairs = 0; c->d_adjPtr = c->d_adjCol = nullptr; c->d_adjK = c->d_cplDinv = c->d_cplUP = c->d_cplVec = nullptr;
     c->h_lin = c->d_hlin = nullptr; c->linMaxIter = 1000; c->linIterations = 0; c->linTol = 1e-13; c->linRelTol = 0.0;
+    c->peerWaitNs = 20000000000ull;
+    if (const char* e = getenv("BEAMGPU_PEER_TIMEOUT_S")) { const double t = atof(e); if (t > 0) c->peerWaitNs = (unsigned long long)(t * 1e9); }
     c->d_stageOut = nullptr; c->outEnd = 0; c->outW = c->outTheta = nullptr;
     c->d_xbuf = nullptr; c->d_vflag = nullptr; c->xRanks = 1; c->xRank = 0; c->epoch = 0; c->lastIters = 4; c->h_res = nullptr; c->d_hres = nullptr;
     memset(&c->cvNow, 0, sizeof c->cvNow);
@@ -1704,6 +1707,7 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
     cv.nRanks = c->xRanks; cv.iter = 0; cv.tag = 2.0 * (double)c->epoch;
     cv.absTol = tol->absoluteTol; cv.resTol = tol->residualTol; cv.solTol = tol->solutionTol; cv.divTol = tol->divergenceTol;
     cv.nCorr = tol->nCorrectors;
+    cv.waitNs = c->peerWaitNs;
     int chunk = c->lastIters < 1 ? 1 : c->lastIters > PIPE_CHUNK_MAX ? PIPE_CHUNK_MAX : c->lastIters;
     bool done = false;
     for (int k0 = 0; !done;) {
@@ -1724,6 +1728,10 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
         for (int k = k0; k < k1 && !done; k++) {
             const double* r = c->h_res + 4 * (k - k0);
+            if (r[3] == 3.0) { // a peer died or never launched: its record of this iteration did not arrive (the kernels gave up waiting)
+                out->status = BF_ERR_COMM; out->nIter = k;
+                return fail(c, BF_ERR_COMM, "iteration %d: the norm sums of a peer rank did not arrive within %g s", k, c->peerWaitNs * 1e-9);
+            }
             done = checkConvergence(c, tol, k, r, &initialResidualNorm, &currentResidualNorm, &deltaXNorm, &XNorm, &status);
             nIter = k + 1;
             if (c->timing) {
