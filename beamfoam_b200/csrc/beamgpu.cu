@@ -122,6 +122,11 @@ struct bf_ctx {
     double* d_hres;
     ConvCtl cvNow;             // filled by bf_evolve for launchIteration; xbuf == nullptr: the host decides
     cudaEvent_t evIter[16][3]; // per enqueued iteration of a chunk: start, between the sweeps, end (timing)
+    // the 1-block reduction of iteration k runs on a side stream while the (speculative) forward part of iteration k+1 already
+    // occupies the GPU: only the backward part of k+1 needs the verdict.  The partial sums alternate between two banks.
+    cudaStream_t redStream;
+    cudaEvent_t evSwept, evReduced;
+    bool redPending;           // a reduction on redStream that the main stream has not waited for yet
     // instrumentation
     int64_t launches;
     int timing, splitKernels;
@@ -380,6 +385,9 @@ extern "C" int bf_destroy(bf_ctx* c)
     for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) if (c->evIter[i][k]) cudaEventDestroy(c->evIter[i][k]);
     for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->evRegion[i]) cudaEventDestroy(c->evRegion[i]);
+    if (c->redStream) { cudaStreamSynchronize(c->redStream); cudaStreamDestroy(c->redStream); }
+    if (c->evSwept) cudaEventDestroy(c->evSwept);
+    if (c->evReduced) cudaEventDestroy(c->evReduced);
     if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
     if (c->evStaged) cudaEventDestroy(c->evStaged);
     if (c->evCopied) cudaEventDestroy(c->evCopied);
@@ -439,6 +447,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->ev[0] = c->ev[1] = c->ev[2] = nullptr;
     c->reducer = nullptr; c->reducerUser = nullptr;
     c->launches = 0; c->timing = 0; c->splitKernels = 1;
+    c->redStream = nullptr; c->evSwept = c->evReduced = nullptr; c->redPending = false;
     // Product path: the two sweeps as two launches per Newton iteration (beam_forward, beam_backward).  The single fused
     // launch (beam_newton: every thread runs both sweeps) measures 5-6 % slower on B200: with all SMs in the same phase
     // the latency-bound forward sweep is not disturbed by the HBM-saturating backward sweep of a neighbouring block.
@@ -490,6 +499,9 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     CREATE_CUDA(cudaFuncSetAttribute(beam_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES));
     CREATE_CUDA(cudaFuncSetAttribute(beam_backsub_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSS_SMEM_BYTES));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&c->redStream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->evSwept, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->evReduced, cudaEventDisableTiming));
     for (int i = 0; i < 3; i++) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; i++) CREATE_CUDA(cudaEventCreate(&c->evRegion[i]));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
@@ -576,9 +588,9 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         if (2 * c->coopGrid > c->partialStride) c->partialStride = 2 * c->coopGrid;
         const int cellGrid = (int)(((size_t)Bpad * (size_t)nmax + 127) / 128); // beam_update_*: one thread per (padded) cell
         if (cellGrid > c->partialStride) c->partialStride = cellGrid;
-        if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 3 * (size_t)c->partialStride + 8) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
+        if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 6 * (size_t)c->partialStride + 8) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
-        c->d_partial = carve<double>(cur, 3 * (size_t)c->partialStride); c->d_sums = carve<double>(cur, 8);
+        c->d_partial = carve<double>(cur, 6 * (size_t)c->partialStride); c->d_sums = carve<double>(cur, 8); // partial sums: two banks (pipelined loop: by iteration parity)
         // Kernel family by bundle size (measured on B200, 200-cell Newmark beams, ms per Newton iteration):
         //      beams        4096   8192   16384  32768  65536
         //      per beam     1.17   1.18   1.20   1.84   3.69   one thread per beam: flat below one wave (37,888 beams)
@@ -1309,7 +1321,17 @@ static int launchForwardWs(bf_ctx* c, const BeamParams& p) // returns the number
 static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
 {
     if (!evs) evs = c->ev;
-    const BeamParams p = makeParams(c);
+    BeamParams p = makeParams(c);
+    // pipelined loop: the reduction of this iteration will run beside the forward part of the next one, which writes its
+    // partial sums into the other bank
+    const bool sideReduce = p.cv.xbuf && !getenv("BEAMGPU_NO_SIDE_REDUCE");
+    if (sideReduce) p.partial = c->d_partial + (size_t)(p.cv.iter & 1) * 3 * (size_t)c->partialStride;
+    // between the forward and the backward part: the backward part starts with the verdict of the previous iteration
+#define MID_ITERATION()                                                                                     \
+    do {                                                                                                    \
+        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));                                      \
+        if (c->redPending) { CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->evReduced, 0)); c->redPending = false; } \
+    } while (0)
     if (p.pf) { // lever arms follow the current W: re-evaluated every iteration (Evolve.C:221)
         beam_point_forces<<<(unsigned)((c->B + 127) / 128), 128, 0, c->stream>>>(p);
         c->launches++;
@@ -1394,7 +1416,7 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
             else if (c->scheme == BF_SCHEME_EULER) beam_forward_split<BFK_EULER, false><<<g2, THREADS, SMEM_BYTES, c->stream>>>(p);
             else beam_forward_split<BFK_STEADY, false><<<g2, THREADS, SMEM_BYTES, c->stream>>>(p);
         }
-        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
+        MID_ITERATION();
         if (c->coopBwd) { // small bundles: serial back-substitution of the two halves, then the update with one thread per cell
             const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
             const dim3 gs((unsigned)(c->Bpad / 32), 2);
@@ -1411,7 +1433,7 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
         int nWs = 0;
         if (c->coopFwd) nWs = launchForwardWs(c, p);
         else LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
-        if (c->timing) CUDA_OK(c, cudaEventRecord(evs[1], c->stream));
+        MID_ITERATION();
         const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
         if (c->coopBwd) { // serial back-substitution, then the update with one thread per cell
             if (!c->coopFwd) // beam_forward does not save the pre-update W (a combination only tests force): a device copy of the array
@@ -1435,7 +1457,14 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
         PeerTable pt;
         const size_t bank = (size_t)(c->epoch & 1) * CONV_MAXK * c->xRanks * 4;
         for (int r = 0; r < CONV_MAX_RANKS; r++) pt.bank[r] = r < c->xRanks ? c->peerXbuf[r] + bank : nullptr;
-        beam_reduce_exchange<<<1, RED_THREADS, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, p.cv, pt, c->xRank);
+        if (sideReduce) {
+            CUDA_OK(c, cudaEventRecord(c->evSwept, c->stream));
+            CUDA_OK(c, cudaStreamWaitEvent(c->redStream, c->evSwept, 0));
+            beam_reduce_exchange<<<1, RED_THREADS, 0, c->redStream>>>(p.partial, c->partialStride, nF, nB, p.cv, pt, c->xRank);
+            CUDA_OK(c, cudaEventRecord(c->evReduced, c->redStream));
+            c->redPending = true;
+        } else
+            beam_reduce_exchange<<<1, RED_THREADS, 0, c->stream>>>(p.partial, c->partialStride, nF, nB, p.cv, pt, c->xRank);
     } else
         beam_reduce_partials<<<1, RED_THREADS, 0, c->stream>>>(c->d_partial, c->partialStride, nF, nB, c->d_sums, c->comm ? nullptr : c->d_hsums);
     c->launches += 1;
@@ -1717,9 +1746,14 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
             cv.iter = k;
             c->cvNow = cv;
             int rc = launchIteration(c, c->evIter[k - k0]);
-            if (rc) { c->cvNow.xbuf = nullptr; out->status = rc; return rc; }
+            if (rc) { // leave nothing behind on the side stream
+                c->cvNow.xbuf = nullptr;
+                if (c->redPending) { cudaStreamWaitEvent(c->stream, c->evReduced, 0); c->redPending = false; }
+                out->status = rc; return rc;
+            }
         }
         c->cvNow.xbuf = nullptr;
+        if (c->redPending) { CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->evReduced, 0)); c->redPending = false; }
         beam_publish_chunk<<<1, 32 * (k1 - k0), 0, c->stream>>>(cv, k0, k1, c->d_hres);
         c->launches++;
         CUDA_OK(c, cudaGetLastError());
