@@ -654,6 +654,10 @@ __global__ void __launch_bounds__(32) beam_backsub_split(const __grid_constant__
 #ifndef BEAM_UPDATE_MIN_BLOCKS
 #define BEAM_UPDATE_MIN_BLOCKS 3
 #endif
+#ifndef BEAM_UPDATE_MIN_WARPS
+#define BEAM_UPDATE_MIN_WARPS 12 // resident one-warp blocks per SM the register budget is cut for: 168 registers.  Measured at
+                                 // 8192 beams (backward part, ms): 12 warps 0.301, 13 (152 registers) 0.315, 14 (144) 0.320, 16 (128) 0.320 -- spills
+#endif
 // A load the compiler must issue where it stands: left to itself it sinks every load below the early-exit branch and next to
 // its first use (to save registers), which turns one round trip into a chain of them.
 DEV double ldNow(const double* p)
@@ -663,10 +667,15 @@ DEV double ldNow(const double* p)
     return v;
 }
 DEV V3 ldNow3(const double* __restrict__ p, size_t i, size_t s) { return v3(ldNow(p + i), ldNow(p + i + s), ldNow(p + i + 2 * s)); }
-template <int SCHEME>
-__global__ void __launch_bounds__(128, BEAM_UPDATE_MIN_BLOCKS) beam_update(const __grid_constant__ BeamParams p, const double* __restrict__ X)
+// WARP_BLOCKS: one warp per block (a block = one cell row of one 32-beam tile).  The thousands of short-lived blocks then need
+// no block barrier (the verdict of the previous iteration and the two partial sums stay inside the warp), a warp's registers
+// are free again the moment IT is done rather than when the slowest of four is, and the look at the verdict comes after the
+// loads have been requested instead of a round trip to L2 before them.
+template <int SCHEME, bool WARP_BLOCKS>
+__global__ void __launch_bounds__(WARP_BLOCKS ? 32 : 128, WARP_BLOCKS ? BEAM_UPDATE_MIN_WARPS : BEAM_UPDATE_MIN_BLOCKS)
+beam_update(const __grid_constant__ BeamParams p, const double* __restrict__ X)
 {
-    if (convLeave(p.cv, true)) return;
+    if (!WARP_BLOCKS && convLeave(p.cv, true)) return;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = (int)(t & 31), Rc = p.nmax, Rf = p.nmax + 1;
     const size_t row = t >> 5, T = row / (size_t)Rc, sb = p.Bpad;
@@ -697,6 +706,7 @@ __global__ void __launch_bounds__(128, BEAM_UPDATE_MIN_BLOCKS) beam_update(const
         M3 refL;
 #pragma unroll
         for (int k = 0; k < 9; k++) refL.a[k] = ldNow(p.refL + b + k * sb);
+        if (WARP_BLOCKS && p.cv.xbuf && p.cv.iter > 0 && convDecide(p.cv, p.cv.iter - 1, true) == 1) return; // the loop ended earlier
         if (b < p.B && i < n) {
             // ---- the cell
             const V3 Wold = old.W;
@@ -717,5 +727,13 @@ __global__ void __launch_bounds__(128, BEAM_UPDATE_MIN_BLOCKS) beam_update(const
             if (i == 0) updatePatchFace(p, b, 0, n, CQ, CM, dcB, delta, Wold, DW, DT);
         }
     }
-    blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
+    if (WARP_BLOCKS) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+            if (lane == 0) p.partial[(size_t)(1 + k) * p.nTiles + blockIdx.x] = v[k];
+        }
+    } else
+        blockReduceStore<2>(v, p.partial, 1, p.nTiles, blockIdx.x);
 }

@@ -1948,14 +1948,25 @@ __global__ void beam_energy(const __grid_constant__ BeamParams p, double* __rest
 DEV void reducePartialsBlock(const double* __restrict__ partial, int stride, int nF, int nB, double (&sm)[3][RED_THREADS])
 {
     const int t = threadIdx.x, nt = blockDim.x;
-    for (int k = 0; k < 3; k++) {
-        const double* src = partial + (size_t)k * stride;
-        const int n = k == 0 ? nF : nB;
+    {
+        const double* src = partial;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int i = t;
-        for (; i + 3 * nt < n; i += 4 * nt) { a0 += src[i]; a1 += src[i + nt]; a2 += src[i + 2 * nt]; a3 += src[i + 3 * nt]; }
-        for (; i < n; i += nt) a0 += src[i];
-        sm[k][t] = (a0 + a1) + (a2 + a3);
+        for (; i + 3 * nt < nF; i += 4 * nt) { a0 += src[i]; a1 += src[i + nt]; a2 += src[i + 2 * nt]; a3 += src[i + 3 * nt]; }
+        for (; i < nF; i += nt) a0 += src[i];
+        sm[0][t] = (a0 + a1) + (a2 + a3);
+    }
+    { // the two slots of the backward part side by side (eight loads in flight per thread; each slot in the order above)
+        const double *s1 = partial + (size_t)stride, *s2 = partial + 2 * (size_t)stride;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        int i = t;
+        for (; i + 3 * nt < nB; i += 4 * nt) {
+            a0 += s1[i]; a1 += s1[i + nt]; a2 += s1[i + 2 * nt]; a3 += s1[i + 3 * nt];
+            b0 += s2[i]; b1 += s2[i + nt]; b2 += s2[i + 2 * nt]; b3 += s2[i + 3 * nt];
+        }
+        for (; i < nB; i += nt) { a0 += s1[i]; b0 += s2[i]; }
+        sm[1][t] = (a0 + a1) + (a2 + a3);
+        sm[2][t] = (b0 + b1) + (b2 + b3);
     }
     __syncthreads();
     for (int o = nt / 2; o > 0; o >>= 1) {

@@ -127,6 +127,7 @@ struct bf_ctx {
     cudaStream_t redStream;
     cudaEvent_t evSwept, evReduced;
     bool redPending;           // a reduction on redStream that the main stream has not waited for yet
+    int updateWarpBlocks;      // beam_update with one warp per block (BEAMGPU_UPDATE_WARP_BLOCKS = 0: four)
     // instrumentation
     int64_t launches;
     int timing, splitKernels;
@@ -448,6 +449,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->reducer = nullptr; c->reducerUser = nullptr;
     c->launches = 0; c->timing = 0; c->splitKernels = 1;
     c->redStream = nullptr; c->evSwept = c->evReduced = nullptr; c->redPending = false;
+    c->updateWarpBlocks = 1;
+    if (const char* e = getenv("BEAMGPU_UPDATE_WARP_BLOCKS")) c->updateWarpBlocks = atoi(e) ? 1 : 0;
     // Product path: the two sweeps as two launches per Newton iteration (beam_forward, beam_backward).  The single fused
     // launch (beam_newton: every thread runs both sweeps) measures 5-6 % slower on B200: with all SMs in the same phase
     // the latency-bound forward sweep is not disturbed by the HBM-saturating backward sweep of a neighbouring block.
@@ -586,7 +589,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
         c->partialStride = 2 * c->grid; // the split sweeps launch two blocks per 128 beams
         if ((int)((c->N + 127) / 128) > c->partialStride) c->partialStride = (int)((c->N + 127) / 128);
         if (2 * c->coopGrid > c->partialStride) c->partialStride = 2 * c->coopGrid;
-        const int cellGrid = (int)(((size_t)Bpad * (size_t)nmax + 127) / 128); // beam_update_*: one thread per (padded) cell
+        const int cellGrid = (int)(((size_t)Bpad * (size_t)nmax + 31) / 32); // beam_update: one thread per (padded) cell, one warp per block
         if (cellGrid > c->partialStride) c->partialStride = cellGrid;
         if (devAlloc(c, (void**)&cur, sizeof(double) * (42 * nc_ * bp + 6 * (size_t)c->partialStride + 8) + 256 * 6)) { int rc_ = fail(nullptr, BF_ERR_NOMEM, "%s", c->err); bf_destroy(c); return rc_; }
         c->d_uP = carve<double>(cur, 36 * nc_ * bp); c->d_bP = carve<double>(cur, 6 * nc_ * bp);
@@ -1316,6 +1319,25 @@ static int launchForwardWs(bf_ctx* c, const BeamParams& p) // returns the number
     else { if (c->split) launchForwardWsT<16, true, 1>(c, p); else launchForwardWsT<16, false, 1>(c, p); }
     return ((c->Bpad + c->wsBpb - 1) / c->wsBpb) * (c->split ? 2 : 1);
 }
+// beam_update: one thread per cell; one warp per block (updateWarpBlocks) or four
+static int updateGrid(const bf_ctx* c)
+{
+    const size_t cellsPadded = (size_t)c->Bpad * (size_t)c->nmax;
+    return c->updateWarpBlocks ? (int)((cellsPadded + 31) / 32) : (int)((cellsPadded + 127) / 128);
+}
+static void launchUpdate(bf_ctx* c, const BeamParams& p, int cellGrid)
+{
+    if (c->updateWarpBlocks) {
+        if (c->scheme == BF_SCHEME_NEWMARK) beam_update<BFK_NEWMARK, true><<<cellGrid, 32, 0, c->stream>>>(p, c->d_X);
+        else if (c->scheme == BF_SCHEME_EULER) beam_update<BFK_EULER, true><<<cellGrid, 32, 0, c->stream>>>(p, c->d_X);
+        else beam_update<BFK_STEADY, true><<<cellGrid, 32, 0, c->stream>>>(p, c->d_X);
+    } else {
+        if (c->scheme == BF_SCHEME_NEWMARK) beam_update<BFK_NEWMARK, false><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+        else if (c->scheme == BF_SCHEME_EULER) beam_update<BFK_EULER, false><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+        else beam_update<BFK_STEADY, false><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+    }
+}
+
 // Launches one Newton iteration; the three LOCAL sums of squares end up in d_sums.
 // evs: the three timing events of this iteration (bf_evolve's pipelined loop passes one set per enqueued iteration)
 static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
@@ -1418,12 +1440,10 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
         }
         MID_ITERATION();
         if (c->coopBwd) { // small bundles: serial back-substitution of the two halves, then the update with one thread per cell
-            const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
+            const int cellGrid = updateGrid(c);
             const dim3 gs((unsigned)(c->Bpad / 32), 2);
             beam_backsub_split<<<gs, 32, BSS_SMEM_BYTES, c->stream>>>(p, c->d_X);
-            if (c->scheme == BF_SCHEME_NEWMARK) beam_update<BFK_NEWMARK><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            else if (c->scheme == BF_SCHEME_EULER) beam_update<BFK_EULER><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            else beam_update<BFK_STEADY><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            launchUpdate(c, p, cellGrid);
             c->launches += 1;
             nB = cellGrid;
         } else
@@ -1434,14 +1454,12 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
         if (c->coopFwd) nWs = launchForwardWs(c, p);
         else LAUNCH_SCHEME(beam_forward, c->grid, SMEM_BYTES, p);
         MID_ITERATION();
-        const int cellGrid = (int)(((size_t)c->Bpad * (size_t)c->nmax + 127) / 128);
+        const int cellGrid = updateGrid(c);
         if (c->coopBwd) { // serial back-substitution, then the update with one thread per cell
             if (!c->coopFwd) // beam_forward does not save the pre-update W (a combination only tests force): a device copy of the array
                 CUDA_OK(c, cudaMemcpyAsync(c->d_Wsave, c->d_W, sizeof(double) * 3 * (size_t)c->nmax * (size_t)c->Bpad, cudaMemcpyDeviceToDevice, c->stream));
             beam_backsub<<<(unsigned)((c->Bpad + BS_THREADS - 1) / BS_THREADS), BS_THREADS, BS_SMEM_BYTES, c->stream>>>(p, c->d_X);
-            if (c->scheme == BF_SCHEME_NEWMARK) beam_update<BFK_NEWMARK><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            else if (c->scheme == BF_SCHEME_EULER) beam_update<BFK_EULER><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
-            else beam_update<BFK_STEADY><<<cellGrid, 128, 0, c->stream>>>(p, c->d_X);
+            launchUpdate(c, p, cellGrid);
             c->launches += 1;
         } else LAUNCH_SCHEME(beam_backward, c->grid, 0, p);
         c->launches += 2;

@@ -530,7 +530,7 @@ def load_traffic(kind):
         return None
     if tj.get("kernel_sources_sha") != kernel_sources_sha():
         sys.stderr.write("bench.py: profiles/traffic.json is older than the kernel sources: roofline.traffic omitted "
-                         "(re-run scripts/gpu_profile_bundle.sh and scripts/make_traffic_json.py)\n")
+                         "(re-run scripts/gpu_profile_r02.sh on the GPU box and scripts/make_profile_summary.py r02)\n")
         return None
     return tj.get(kind)
 
