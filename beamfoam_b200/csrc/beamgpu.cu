@@ -121,7 +121,12 @@ struct bf_ctx {
     double* h_res;             // pinned + mapped: verdicts of a chunk of iterations, [PIPE_CHUNK_MAX][4]
     double* d_hres;
     ConvCtl cvNow;             // filled by bf_evolve for launchIteration; xbuf == nullptr: the host decides
-    cudaEvent_t evIter[16][3]; // per enqueued iteration of a chunk: start, between the sweeps, end (timing)
+    // per enqueued iteration of a chunk: start, between the sweeps, end (timing).  Two sets: the elapsed times of a chunk are
+    // read AFTER the next chunk (normally the next time step) has been enqueued, while the GPU works -- a dozen
+    // cudaEventElapsedTime calls between two steps are 1 % of a 1.6 ms step of a small bundle
+    cudaEvent_t evIter[2][16][3];
+    int evSet;                 // the set the next chunk records into
+    int evPendingSet, evPendingK0, evPendingN; // a finished chunk whose times have not been read yet (evPendingN iterations ran)
     // the 1-block reduction of iteration k runs on a side stream while the (speculative) forward part of iteration k+1 already
     // occupies the GPU: only the backward part of k+1 needs the verdict.  The partial sums alternate between two banks.
     cudaStream_t redStream;
@@ -366,11 +371,13 @@ static void launchTranspose(bf_ctx* c, double* dev, double* hostOrder, int nc, i
         dev, hostOrder, surface ? c->d_faceStart : c->d_cellStart, (int)c->B, surface ? c->nmax + 1 : c->nmax, nc, surface);
 }
 
+static void readChunkTimes(bf_ctx* c);
 extern "C" int bf_destroy(bf_ctx* c)
 {
     if (!c) return BF_OK;
     cudaSetDevice(c->device);
     if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+    readChunkTimes(c);
     if (getenv("BEAMGPU_TIMING_DUMP"))
         for (int k = 0; k < 8; k++)
             if (c->itersK[k]) fprintf(stderr, "beamgpu rank %d iteration %d of a step: fwd %.4f ms  bwd %.4f ms  gap before %.4f ms  (%lld samples)\n", c->xRank, k,
@@ -383,7 +390,7 @@ extern "C" int bf_destroy(bf_ctx* c)
         if (r != c->xRank && c->peerXbuf[r]) cudaIpcCloseMemHandle(c->peerXbuf[r]);
     if (c->d_xbuf) cudaFree(c->d_xbuf);
     if (c->d_vflag) cudaFree(c->d_vflag);
-    for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) if (c->evIter[i][k]) cudaEventDestroy(c->evIter[i][k]);
+    for (int s = 0; s < 2; s++) for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) if (c->evIter[s][i][k]) cudaEventDestroy(c->evIter[s][i][k]);
     for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->evRegion[i]) cudaEventDestroy(c->evRegion[i]);
     if (c->redStream) { cudaStreamSynchronize(c->redStream); cudaStreamDestroy(c->redStream); }
@@ -466,7 +473,8 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->d_xbuf = nullptr; c->d_vflag = nullptr; c->xRanks = 1; c->xRank = 0; c->epoch = 0; c->lastIters = 4; c->h_res = nullptr; c->d_hres = nullptr;
     memset(&c->cvNow, 0, sizeof c->cvNow);
     for (int i = 0; i < CONV_MAX_RANKS; i++) c->peerXbuf[i] = nullptr;
-    for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) c->evIter[i][k] = nullptr;
+    for (int s = 0; s < 2; s++) for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) c->evIter[s][i][k] = nullptr;
+    c->evSet = 0; c->evPendingN = 0; c->evPendingSet = 0; c->evPendingK0 = 0;
     c->copyStream = nullptr; c->evStaged = c->evCopied = nullptr; c->copyPending = false; c->fwdMs = c->bwdMs = 0; c->timedIters = 0;
     memset(c->fwdMsK, 0, sizeof c->fwdMsK); memset(c->bwdMsK, 0, sizeof c->bwdMsK); memset(c->gapMsK, 0, sizeof c->gapMsK); memset(c->itersK, 0, sizeof c->itersK);
     c->hasQ = c->hasM = false;
@@ -684,7 +692,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     CREATE_CUDA(cudaHostGetDevicePointer((void**)&c->d_hsums, c->h_sums, 0));
     CREATE_CUDA(cudaHostAlloc((void**)&c->h_res, PIPE_CHUNK_MAX * 4 * sizeof(double), cudaHostAllocMapped));
     CREATE_CUDA(cudaHostGetDevicePointer((void**)&c->d_hres, c->h_res, 0));
-    for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) CREATE_CUDA(cudaEventCreate(&c->evIter[i][k]));
+    for (int s = 0; s < 2; s++) for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) CREATE_CUDA(cudaEventCreate(&c->evIter[s][i][k]));
     // the exchange buffer is its own cudaMalloc: CUDA IPC exports whole allocations
     CREATE_CUDA(cudaMalloc((void**)&c->d_xbuf, sizeof(double) * 2 * CONV_MAXK * CONV_MAX_RANKS * 4));
     CREATE_CUDA(cudaMemsetAsync(c->d_xbuf, 0, sizeof(double) * 2 * CONV_MAXK * CONV_MAX_RANKS * 4, c->stream));
@@ -1255,8 +1263,10 @@ extern "C" int bf_beam_energy(bf_ctx* c, double* out)
     return BF_OK;
 }
 
+static void readChunkTimes(bf_ctx* c);
 extern "C" int bf_kernel_time_ms(bf_ctx* c, int32_t reset, double* fwd, double* bwd, int64_t* it)
 {
+    readChunkTimes(c);
     if (fwd) *fwd = c->fwdMs;
     if (bwd) *bwd = c->bwdMs;
     if (it) *it = c->timedIters;
@@ -1739,6 +1749,25 @@ static bool checkConvergence(bf_ctx* c, const bf_tolerances* tol, int iteration,
     return false;
 }
 
+// Elapsed times of the last finished chunk of the pipelined loop (its events have all completed: the chunk was synchronised).
+static void readChunkTimes(bf_ctx* c)
+{
+    const int n = c->evPendingN, k0 = c->evPendingK0;
+    c->evPendingN = 0;
+    cudaEvent_t (*ev)[3] = c->evIter[c->evPendingSet];
+    for (int j = 0; j < n; j++) {
+        const int k = k0 + j;
+        float a = 0, b = 0;
+        if (cudaEventElapsedTime(&a, ev[j][0], ev[j][1]) != cudaSuccess || cudaEventElapsedTime(&b, ev[j][1], ev[j][2]) != cudaSuccess) { cudaGetLastError(); return; }
+        c->fwdMs += a; c->bwdMs += b; c->timedIters++;
+        if (k < 8) {
+            float g = 0;
+            if (j > 0) cudaEventElapsedTime(&g, ev[j - 1][2], ev[j][0]);
+            c->fwdMsK[k] += a; c->bwdMsK[k] += b; c->gapMsK[k] += g; c->itersK[k]++;
+        }
+    }
+}
+
 // The pipelined Newton loop: the iterations of a chunk are enqueued back to back without waiting for their norms; every
 // sweep kernel looks at the global norms of the previous iteration itself (convLeave) and the ones past the end of the loop
 // leave at once.  The host reads the verdicts of a whole chunk with ONE synchronisation.  The chunk is the iteration
@@ -1758,12 +1787,14 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
     int chunk = c->lastIters < 1 ? 1 : c->lastIters > PIPE_CHUNK_MAX ? PIPE_CHUNK_MAX : c->lastIters;
     bool done = false;
     for (int k0 = 0; !done;) {
+        const int evSet = c->evSet;
+        c->evSet ^= 1;
         int k1 = k0 + chunk;
         if (k1 > tol->nCorrectors + 1) k1 = tol->nCorrectors + 1; // iteration nCorrectors always ends the loop
         for (int k = k0; k < k1; k++) {
             cv.iter = k;
             c->cvNow = cv;
-            int rc = launchIteration(c, c->evIter[k - k0]);
+            int rc = launchIteration(c, c->evIter[evSet][k - k0]);
             if (rc) { // leave nothing behind on the side stream
                 c->cvNow.xbuf = nullptr;
                 if (c->redPending) { cudaStreamWaitEvent(c->stream, c->evReduced, 0); c->redPending = false; }
@@ -1777,6 +1808,7 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
         CUDA_OK(c, cudaGetLastError());
         // step outputs ride behind every chunk (a chunk that turns out not to be the last is simply overwritten by the next)
         if (c->outW) { if (int rc = stagePatchPair(c, c->outEnd, c->outW, c->outTheta)) return rc; }
+        readChunkTimes(c); // of the previous chunk, while the GPU works on this one
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
         for (int k = k0; k < k1 && !done; k++) {
             const double* r = c->h_res + 4 * (k - k0);
@@ -1786,19 +1818,9 @@ static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out
             }
             done = checkConvergence(c, tol, k, r, &initialResidualNorm, &currentResidualNorm, &deltaXNorm, &XNorm, &status);
             nIter = k + 1;
-            if (c->timing) {
-                float a = 0, b = 0;
-                CUDA_OK(c, cudaEventElapsedTime(&a, c->evIter[k - k0][0], c->evIter[k - k0][1]));
-                CUDA_OK(c, cudaEventElapsedTime(&b, c->evIter[k - k0][1], c->evIter[k - k0][2]));
-                c->fwdMs += a; c->bwdMs += b; c->timedIters++;
-                if (k < 8) {
-                    float g = 0;
-                    if (k > k0) cudaEventElapsedTime(&g, c->evIter[k - k0 - 1][2], c->evIter[k - k0][0]);
-                    c->fwdMsK[k] += a; c->bwdMsK[k] += b; c->gapMsK[k] += g; c->itersK[k]++;
-                }
-            }
             if (done != (r[3] == 1.0)) return fail(c, BF_ERR_CUDA, "iteration %d: host and device disagree on the convergence test", k);
         }
+        if (c->timing) { c->evPendingSet = evSet; c->evPendingK0 = k0; c->evPendingN = nIter - k0; }
         k0 = k1;
         chunk = 1; // the prediction was short: go on one iteration at a time
     }
