@@ -133,6 +133,7 @@ struct bf_ctx {
     cudaEvent_t evSwept, evReduced;
     bool redPending;           // a reduction on redStream that the main stream has not waited for yet
     int updateWarpBlocks;      // beam_update with one warp per block (BEAMGPU_UPDATE_WARP_BLOCKS = 0: four)
+    int sideReduce;            // BEAMGPU_NO_SIDE_REDUCE = 1: the reduction stays in line on the main stream
     // instrumentation
     int64_t launches;
     int timing, splitKernels;
@@ -457,6 +458,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->launches = 0; c->timing = 0; c->splitKernels = 1;
     c->redStream = nullptr; c->evSwept = c->evReduced = nullptr; c->redPending = false;
     c->updateWarpBlocks = 1;
+    c->sideReduce = getenv("BEAMGPU_NO_SIDE_REDUCE") ? 0 : 1;
     if (const char* e = getenv("BEAMGPU_UPDATE_WARP_BLOCKS")) c->updateWarpBlocks = atoi(e) ? 1 : 0;
     // Product path: the two sweeps as two launches per Newton iteration (beam_forward, beam_backward).  The single fused
     // launch (beam_newton: every thread runs both sweeps) measures 5-6 % slower on B200: with all SMs in the same phase
@@ -1356,7 +1358,7 @@ static int launchIteration(bf_ctx* c, cudaEvent_t* evs = nullptr)
     BeamParams p = makeParams(c);
     // pipelined loop: the reduction of this iteration will run beside the forward part of the next one, which writes its
     // partial sums into the other bank
-    const bool sideReduce = p.cv.xbuf && !getenv("BEAMGPU_NO_SIDE_REDUCE");
+    const bool sideReduce = p.cv.xbuf && c->sideReduce;
     if (sideReduce) p.partial = c->d_partial + (size_t)(p.cv.iter & 1) * 3 * (size_t)c->partialStride;
     // between the forward and the backward part: the backward part starts with the verdict of the previous iteration
 #define MID_ITERATION()                                                                                     \

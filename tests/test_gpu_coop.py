@@ -161,3 +161,29 @@ def test_unequal_split(gpu_lib, oracle_lib, family, at):
     finally:
         os.environ.pop("BEAMGPU_SPLIT_AT", None)
         clear_family()
+
+
+@pytest.mark.parametrize("family", ["split_cell", "split_group16", "group", "split", "per_beam"])
+@pytest.mark.parametrize("switch", ["BEAMGPU_NO_SIDE_REDUCE=1", "BEAMGPU_UPDATE_WARP_BLOCKS=0", "BEAMGPU_NO_PIPELINE=1"])
+def test_loop_variants_are_bit_identical(gpu_lib, family, switch):
+    """How the Newton loop is driven does not touch a beam's arithmetic: the reduction in line instead of on the side stream,
+    beam_update with four warps per block instead of one, the host instead of the device deciding on convergence -- every
+    variant takes the same iterations and leaves bit-identical tips."""
+    case = cases.multiBeamDensity(70, 37, jitter=True)
+    k, v = switch.split("=")
+    results = []
+    for on in (False, True):
+        set_family(family)
+        if on:
+            os.environ[k] = v
+        try:
+            g = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
+            its = g.run(nSteps=12)
+            results.append((its, [t.copy() for t in g.tip(1)]))
+            g.close()
+        finally:
+            os.environ.pop(k, None)
+            clear_family()
+    assert results[0][0] == results[1][0]
+    for a, b in zip(results[0][1], results[1][1]):
+        assert np.array_equal(a, b)
