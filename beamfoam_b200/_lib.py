@@ -97,6 +97,8 @@ EXPORTS = {
     "bf_begin_step": (C.c_int, [C.c_void_p, C.c_double]),
     "bf_newton_iteration": (C.c_int, [C.c_void_p, _dp]),
     "bf_evolve": (C.c_int, [C.c_void_p, C.POINTER(bf_tolerances), C.POINTER(bf_step_out)]),
+    "bf_evolve_begin": (C.c_int, [C.c_void_p, C.POINTER(bf_tolerances)]),
+    "bf_evolve_end": (C.c_int, [C.c_void_p, C.POINTER(bf_step_out)]),
     "bf_set_reducer": (C.c_int, [C.c_void_p, bf_reduce_fn, C.c_void_p]),
     "bf_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "bf_comm_init_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

@@ -170,6 +170,8 @@ class coupledTotalLagNewtonRaphsonBeam:
         self._bcCache = {}
         self._bcUploaded = set()
         self._pinnedBC = {}
+        self._bcSet = 0        # which of the two sets of staging arrays updateCoeffs() fills
+        self._bcPrepared = []  # (end, kind, staging array) evaluated ahead by updateCoeffs(t, prepareOnly=True)
         self._pinnedPtrs = []
         self.h2dBytes = 0  # bytes handed to bf_set_bc_values so far
         self._beganStepAt = None  # time index of the last bf_begin_step
@@ -383,10 +385,14 @@ class coupledTotalLagNewtonRaphsonBeam:
         return w, t
 
     # ------------------------------------------------------------- hot path
-    def updateCoeffs(self, t: float):
+    def updateCoeffs(self, t: float, prepareOnly: bool = False):
         """W_/Theta_.boundaryFieldRef().updateCoeffs() (Evolve.C:156-157): evaluate every
         BC series at time t and hand the values to the device.  Patch fields without a series are handed over once
-        (their updateCoeffs() does nothing in the reference either)."""
+        (their updateCoeffs() does nothing in the reference either).
+        prepareOnly: evaluate into the OTHER set of page-locked staging arrays and keep the hand-over for uploadPrepared() --
+        what a host does between evolveBegin() and evolveEnd(), while the GPU runs the Newton loop of the open step."""
+        if prepareOnly:
+            self._bcSet ^= 1
         for end in (0, 1):
             for var in ("W", "Theta"):
                 spec, objs = self._bcs[(end, var)]
@@ -401,10 +407,20 @@ class coupledTotalLagNewtonRaphsonBeam:
                         v = np.where(np.array([o.kind == kind for o in objs])[:, None], vals, 0.0)
                     buf = self._pinned_bc(end, var, kind)  # page-locked staging: the H2D copy is a plain DMA
                     np.copyto(buf, v)
+                    if prepareOnly:
+                        self._bcPrepared.append((end, kind, buf))
+                        continue
                     # the staging array is page-locked and refilled once per step: the upload need not be waited for
                     self._check(self.lib.bf_set_bc_values_async(self._ctx, end, kind, buf.ctypes.data))
                     self.h2dBytes += buf.nbytes
                 self._bcUploaded.add((end, var))
+
+    def uploadPrepared(self):
+        """Hands the values of updateCoeffs(t, prepareOnly=True) to the device (after evolveEnd())."""
+        for end, kind, buf in self._bcPrepared:
+            self._check(self.lib.bf_set_bc_values_async(self._ctx, end, kind, buf.ctypes.data))
+            self.h2dBytes += buf.nbytes
+        self._bcPrepared = []
 
     def stepOutputs(self, end: int = 1):
         """Registers (once) and returns two page-locked [nBeams, 3] arrays that every evolve() fills with the patch values of W
@@ -427,7 +443,7 @@ class coupledTotalLagNewtonRaphsonBeam:
     def _pinned_bc(self, end: int, var: str, kind: int) -> np.ndarray:
         """[nBeams, 3] page-locked host array (bf_host_alloc: cudaHostAlloc in libbeamgpu, malloc in the oracle) that the
         boundary values of one patch side are staged in before they cross the ABI."""
-        key = (end, var, kind)
+        key = (end, var, kind, self._bcSet)
         buf = self._pinnedBC.get(key)
         if buf is None:
             ptr = C.c_void_p()
@@ -469,6 +485,25 @@ class coupledTotalLagNewtonRaphsonBeam:
             self._beganStepAt = self.timeIndex
         out = L.bf_step_out()
         rc = self.lib.bf_evolve(self._ctx, C.byref(self.tol), C.byref(out))
+        self.lastStep = out
+        self._iOuterCorr = out.nIter
+        self.totalIter_ += out.nIter
+        self._check(rc)
+        return out.initialResidualNorm
+
+    def evolveBegin(self):
+        """First half of evolve() for a host that prepares the next time level while the GPU works (bf_evolve_begin): the
+        boundary values of THIS time level must have been handed over (updateCoeffs / uploadPrepared)."""
+        self.updatePointForces(self.time)
+        if self._beganStepAt != self.timeIndex:
+            self._check(self.lib.bf_begin_step(self._ctx, float(self.case.deltaT)))
+            self._beganStepAt = self.timeIndex
+        self._check(self.lib.bf_evolve_begin(self._ctx, C.byref(self.tol)))
+
+    def evolveEnd(self) -> float:
+        """Second half (bf_evolve_end): waits, checks convergence as evolve() does, returns the initial residual norm."""
+        out = L.bf_step_out()
+        rc = self.lib.bf_evolve_end(self._ctx, C.byref(out))
         self.lastStep = out
         self._iOuterCorr = out.nIter
         self.totalIter_ += out.nIter

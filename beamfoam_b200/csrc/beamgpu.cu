@@ -40,8 +40,18 @@ struct NcclApi {
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
+struct PipeState { // the pipelined Newton loop of one evolve() (evolvePipelined; bf_evolve_begin / bf_evolve_end)
+    bool active;   // between bf_evolve_begin and bf_evolve_end
+    bool deferred; // bf_evolve_begin could not enqueue ahead (host-driven loop): bf_evolve_end runs bf_evolve
+    bool done;
+    bf_tolerances tol;
+    ConvCtl cv;
+    int k0, k1, chunk, evSet, nIter, status;
+    double initialResidualNorm, currentResidualNorm, deltaXNorm, XNorm;
+};
 struct bf_ctx {
     char err[512];
+    PipeState pipe;
     int device;
     cudaStream_t stream;
     int64_t B, N, F;
@@ -457,6 +467,7 @@ extern "C" int bf_create(const bf_layout* lay, const bf_beam_props* pr, const bf
     c->reducer = nullptr; c->reducerUser = nullptr;
     c->launches = 0; c->timing = 0; c->splitKernels = 1;
     c->redStream = nullptr; c->evSwept = c->evReduced = nullptr; c->redPending = false;
+    memset(&c->pipe, 0, sizeof c->pipe);
     c->updateWarpBlocks = 1;
     c->sideReduce = getenv("BEAMGPU_NO_SIDE_REDUCE") ? 0 : 1;
     if (const char* e = getenv("BEAMGPU_UPDATE_WARP_BLOCKS")) c->updateWarpBlocks = atoi(e) ? 1 : 0;
@@ -1141,6 +1152,7 @@ extern "C" int bf_set_bc_values_async(bf_ctx* c, int32_t end, int32_t kind, cons
 static int setBcValues(bf_ctx* c, int32_t end, int32_t kind, const double* v, bool wait)
 {
     if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !v) return fail(c, BF_ERR_INVALID, "bf_set_bc_values: bad argument");
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_set_bc_values between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     CUDA_OK(c, cudaSetDevice(c->device));
     // entries of beams whose BC class does not use `kind` are never read by the kernels.  One copy of the host array, one
     // wait at the end (the caller may reuse its buffer on return); the scatters stay asynchronous on the stream.
@@ -1221,6 +1233,7 @@ extern "C" int bf_set_step_outputs(bf_ctx* c, int32_t end, double* W, double* Th
 extern "C" int bf_begin_step(bf_ctx* c, double deltaT)
 {
     if (!(deltaT > 0)) return fail(c, BF_ERR_INVALID, "bf_begin_step: deltaT must be > 0");
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_begin_step between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     c->deltaT = deltaT;
     c->iOuterCorr = 0;
     c->timeAdvanced = true;
@@ -1524,6 +1537,7 @@ static int fetchSums(bf_ctx* c, double sumsq[3])
 
 extern "C" int bf_newton_iteration(bf_ctx* c, double sumsq[3])
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_newton_iteration between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     CUDA_OK(c, cudaSetDevice(c->device));
     int rc = launchIteration(c);
     if (rc) return rc;
@@ -1774,67 +1788,137 @@ static void readChunkTimes(bf_ctx* c)
 // sweep kernel looks at the global norms of the previous iteration itself (convLeave) and the ones past the end of the loop
 // leave at once.  The host reads the verdicts of a whole chunk with ONE synchronisation.  The chunk is the iteration
 // count of the previous step (the same on every rank, so every rank enqueues the same launches).
-static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
+extern "C" int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out);
+// One chunk is enqueued by pipeEnqueue and read back by pipeCollect; bf_evolve runs the two in a loop, bf_evolve_begin /
+// bf_evolve_end put the host between them (PipeState in the context).
+static void pipeInit(bf_ctx* c, const bf_tolerances* tol)
 {
-    double initialResidualNorm = 1, currentResidualNorm = BF_GREAT, deltaXNorm = BF_GREAT, XNorm = BF_GREAT;
-    int status = BF_OK, nIter = 0;
+    PipeState& st = c->pipe;
+    st.tol = *tol;
+    st.initialResidualNorm = 1; st.currentResidualNorm = st.deltaXNorm = st.XNorm = BF_GREAT;
+    st.status = BF_OK; st.nIter = 0; st.k0 = st.k1 = 0; st.done = false;
     c->epoch++;
-    ConvCtl cv;
+    ConvCtl& cv = st.cv;
     cv.xbuf = c->d_xbuf + (size_t)(c->epoch & 1) * CONV_MAXK * c->xRanks * 4;
     cv.vflag = c->d_vflag + (size_t)(c->epoch & 1) * CONV_MAXK;
     cv.nRanks = c->xRanks; cv.iter = 0; cv.tag = 2.0 * (double)c->epoch;
     cv.absTol = tol->absoluteTol; cv.resTol = tol->residualTol; cv.solTol = tol->solutionTol; cv.divTol = tol->divergenceTol;
     cv.nCorr = tol->nCorrectors;
     cv.waitNs = c->peerWaitNs;
-    int chunk = c->lastIters < 1 ? 1 : c->lastIters > PIPE_CHUNK_MAX ? PIPE_CHUNK_MAX : c->lastIters;
-    bool done = false;
-    for (int k0 = 0; !done;) {
-        const int evSet = c->evSet;
-        c->evSet ^= 1;
-        int k1 = k0 + chunk;
-        if (k1 > tol->nCorrectors + 1) k1 = tol->nCorrectors + 1; // iteration nCorrectors always ends the loop
-        for (int k = k0; k < k1; k++) {
-            cv.iter = k;
-            c->cvNow = cv;
-            int rc = launchIteration(c, c->evIter[evSet][k - k0]);
-            if (rc) { // leave nothing behind on the side stream
-                c->cvNow.xbuf = nullptr;
-                if (c->redPending) { cudaStreamWaitEvent(c->stream, c->evReduced, 0); c->redPending = false; }
-                out->status = rc; return rc;
-            }
+    st.chunk = c->lastIters < 1 ? 1 : c->lastIters > PIPE_CHUNK_MAX ? PIPE_CHUNK_MAX : c->lastIters;
+}
+static int pipeEnqueue(bf_ctx* c)
+{
+    PipeState& st = c->pipe;
+    st.evSet = c->evSet;
+    c->evSet ^= 1;
+    st.k1 = st.k0 + st.chunk;
+    if (st.k1 > st.tol.nCorrectors + 1) st.k1 = st.tol.nCorrectors + 1; // iteration nCorrectors always ends the loop
+    for (int k = st.k0; k < st.k1; k++) {
+        st.cv.iter = k;
+        c->cvNow = st.cv;
+        int rc = launchIteration(c, c->evIter[st.evSet][k - st.k0]);
+        if (rc) { // leave nothing behind on the side stream
+            c->cvNow.xbuf = nullptr;
+            if (c->redPending) { cudaStreamWaitEvent(c->stream, c->evReduced, 0); c->redPending = false; }
+            return rc;
         }
-        c->cvNow.xbuf = nullptr;
-        if (c->redPending) { CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->evReduced, 0)); c->redPending = false; }
-        beam_publish_chunk<<<1, 32 * (k1 - k0), 0, c->stream>>>(cv, k0, k1, c->d_hres);
-        c->launches++;
-        CUDA_OK(c, cudaGetLastError());
-        // step outputs ride behind every chunk (a chunk that turns out not to be the last is simply overwritten by the next)
-        if (c->outW) { if (int rc = stagePatchPair(c, c->outEnd, c->outW, c->outTheta)) return rc; }
-        readChunkTimes(c); // of the previous chunk, while the GPU works on this one
-        CUDA_OK(c, cudaStreamSynchronize(c->stream));
-        for (int k = k0; k < k1 && !done; k++) {
-            const double* r = c->h_res + 4 * (k - k0);
-            if (r[3] == 3.0) { // a peer died or never launched: its record of this iteration did not arrive (the kernels gave up waiting)
-                out->status = BF_ERR_COMM; out->nIter = k;
-                return fail(c, BF_ERR_COMM, "iteration %d: the norm sums of a peer rank did not arrive within %g s", k, c->peerWaitNs * 1e-9);
-            }
-            done = checkConvergence(c, tol, k, r, &initialResidualNorm, &currentResidualNorm, &deltaXNorm, &XNorm, &status);
-            nIter = k + 1;
-            if (done != (r[3] == 1.0)) return fail(c, BF_ERR_CUDA, "iteration %d: host and device disagree on the convergence test", k);
-        }
-        if (c->timing) { c->evPendingSet = evSet; c->evPendingK0 = k0; c->evPendingN = nIter - k0; }
-        k0 = k1;
-        chunk = 1; // the prediction was short: go on one iteration at a time
     }
-    c->lastIters = nIter;
-    c->iOuterCorr = nIter;
-    out->nIter = nIter;
-    out->status = status;
-    out->initialResidualNorm = initialResidualNorm;
-    out->currentResidualNorm = currentResidualNorm;
-    out->deltaXNorm = deltaXNorm;
-    out->xNorm = XNorm;
-    return status;
+    c->cvNow.xbuf = nullptr;
+    if (c->redPending) { CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->evReduced, 0)); c->redPending = false; }
+    beam_publish_chunk<<<1, 32 * (st.k1 - st.k0), 0, c->stream>>>(st.cv, st.k0, st.k1, c->d_hres);
+    c->launches++;
+    CUDA_OK(c, cudaGetLastError());
+    // step outputs ride behind every chunk (a chunk that turns out not to be the last is simply overwritten by the next)
+    if (c->outW) { if (int rc = stagePatchPair(c, c->outEnd, c->outW, c->outTheta)) return rc; }
+    readChunkTimes(c); // of the previous chunk, while the GPU works on this one
+    return BF_OK;
+}
+static int pipeCollect(bf_ctx* c, bf_step_out* out)
+{
+    PipeState& st = c->pipe;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    for (int k = st.k0; k < st.k1 && !st.done; k++) {
+        const double* r = c->h_res + 4 * (k - st.k0);
+        if (r[3] == 3.0) { // a peer died or never launched: its record of this iteration did not arrive (the kernels gave up waiting)
+            out->status = BF_ERR_COMM; out->nIter = k;
+            return fail(c, BF_ERR_COMM, "iteration %d: the norm sums of a peer rank did not arrive within %g s", k, c->peerWaitNs * 1e-9);
+        }
+        st.done = checkConvergence(c, &st.tol, k, r, &st.initialResidualNorm, &st.currentResidualNorm, &st.deltaXNorm, &st.XNorm, &st.status);
+        st.nIter = k + 1;
+        if (st.done != (r[3] == 1.0)) return fail(c, BF_ERR_CUDA, "iteration %d: host and device disagree on the convergence test", k);
+    }
+    if (c->timing) { c->evPendingSet = st.evSet; c->evPendingK0 = st.k0; c->evPendingN = st.nIter - st.k0; }
+    st.k0 = st.k1;
+    st.chunk = 1; // the prediction was short: go on one iteration at a time
+    return BF_OK;
+}
+static int pipeFinish(bf_ctx* c, bf_step_out* out)
+{
+    const PipeState& st = c->pipe;
+    c->lastIters = st.nIter;
+    c->iOuterCorr = st.nIter;
+    out->nIter = st.nIter;
+    out->status = st.status;
+    out->initialResidualNorm = st.initialResidualNorm;
+    out->currentResidualNorm = st.currentResidualNorm;
+    out->deltaXNorm = st.deltaXNorm;
+    out->xNorm = st.XNorm;
+    return st.status;
+}
+static int evolvePipelined(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
+{
+    pipeInit(c, tol);
+    while (!c->pipe.done) {
+        if (int rc = pipeEnqueue(c)) { out->status = rc; return rc; }
+        if (int rc = pipeCollect(c, out)) return rc;
+    }
+    return pipeFinish(c, out);
+}
+static bool canPipeline(const bf_ctx* c, const bf_tolerances* tol)
+{
+    // Pipelined loop whenever the sums can be exchanged on the device: a single context, or peers attached with
+    // bf_comm_ipc_attach.  A host reducer / NCCL communicator without peer memory, the cell-parallel path and the fused
+    // launch keep the host in the loop (one synchronisation per iteration).
+    return !c->reducer && (!c->comm || c->xRanks > 1) && !c->longMode && !c->nPairs && (c->splitKernels || c->split || c->coopFwd || c->coopBwd) &&
+           tol->nCorrectors < CONV_MAXK - 1 && !getenv("BEAMGPU_NO_PIPELINE");
+}
+
+// evolve() in two halves (include/beamgpu.h): bf_evolve_begin enqueues the Newton loop and returns, the host prepares the next
+// time level (evaluates its BC series into page-locked staging, writes the previous one) while the GPU works, bf_evolve_end
+// waits, checks and -- if the prediction of the iteration count was short -- runs the remaining iterations.
+extern "C" int bf_evolve_begin(bf_ctx* c, const bf_tolerances* tol)
+{
+    if (!tol) return fail(c, BF_ERR_INVALID, "bf_evolve_begin: null argument");
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_evolve_begin: the previous bf_evolve_begin has no bf_evolve_end yet");
+    CUDA_OK(c, cudaSetDevice(c->device));
+    c->pipe.tol = *tol;
+    c->pipe.deferred = !canPipeline(c, tol); // a host-driven loop cannot run ahead: bf_evolve_end does all of it
+    if (!c->pipe.deferred) {
+        c->iOuterCorr = 0;
+        pipeInit(c, tol);
+        if (int rc = pipeEnqueue(c)) return rc;
+    }
+    c->pipe.active = true;
+    return BF_OK;
+}
+extern "C" int bf_evolve_end(bf_ctx* c, bf_step_out* out)
+{
+    if (!out) return fail(c, BF_ERR_INVALID, "bf_evolve_end: null argument");
+    if (!c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_evolve_end without bf_evolve_begin");
+    c->pipe.active = false;
+    if (c->pipe.deferred) {
+        const bf_tolerances tol = c->pipe.tol;
+        return bf_evolve(c, &tol, out);
+    }
+    CUDA_OK(c, cudaSetDevice(c->device));
+    memset(out, 0, sizeof *out);
+    if (int rc = pipeCollect(c, out)) return rc;
+    while (!c->pipe.done) {
+        if (int rc = pipeEnqueue(c)) { out->status = rc; return rc; }
+        if (int rc = pipeCollect(c, out)) return rc;
+    }
+    return pipeFinish(c, out);
 }
 
 // evolve(): Evolve.C:55-670, checkConvergence :926-1026
@@ -1845,12 +1929,8 @@ extern "C" int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
     double initialResidualNorm = 1, currentResidualNorm = BF_GREAT, deltaXNorm = BF_GREAT, XNorm = BF_GREAT;
     memset(out, 0, sizeof *out);
     c->iOuterCorr = 0;
-    // Pipelined loop whenever the sums can be exchanged on the device: a single context, or peers attached with
-    // bf_comm_ipc_attach.  A host reducer / NCCL communicator without peer memory, the cell-parallel path and the fused
-    // launch keep the host in the loop (one synchronisation per iteration).
-    const bool pipelined = !c->reducer && (!c->comm || c->xRanks > 1) && !c->longMode && !c->nPairs && (c->splitKernels || c->split || c->coopFwd || c->coopBwd) &&
-                           tol->nCorrectors < CONV_MAXK - 1 && !getenv("BEAMGPU_NO_PIPELINE");
-    if (pipelined) return evolvePipelined(c, tol, out);
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_evolve between bf_evolve_begin and bf_evolve_end");
+    if (canPipeline(c, tol)) return evolvePipelined(c, tol, out);
     int status = BF_OK;
     for (;;) {
         const int iteration = c->iOuterCorr; // the value passed as iOuterCorr()++

@@ -331,6 +331,18 @@ int bf_newton_iteration_checked(bf_ctx* ctx, double sumsq[3], double* backwardEr
  * evaluated on the (reduced) norms.  Always fills `out`. */
 int bf_evolve(bf_ctx* ctx, const bf_tolerances* tol, bf_step_out* out);
 
+/* bf_evolve in two halves.  beamFoam.C:73-89 runs one time step after the other: updateCoeffs() of the boundary conditions
+ * (Evolve.C:156-157), the Newton loop, the function objects, runTime.write().  The BC series of the NEXT time level depend on
+ * nothing the solve produces, so a host can evaluate them (into page-locked staging) and do its writing while the GPU is
+ * busy: bf_evolve_begin enqueues the Newton loop of the open time step and returns at once, bf_evolve_end waits for it,
+ * evaluates checkConvergence on its norms exactly as bf_evolve does (running further iterations if the loop was not over)
+ * and fills `out`; the pair is bf_evolve, result for result.  Between the two calls the context accepts no call that would
+ * queue work behind the loop (bf_begin_step, bf_set_bc_values*, bf_newton_iteration, bf_evolve return BF_ERR_INVALID): hand
+ * the prepared values over after bf_evolve_end.  Where the loop needs the host in every iteration (a reducer callback,
+ * NCCL without peer memory, the cell-parallel path) bf_evolve_begin only records the request and bf_evolve_end does the work. */
+int bf_evolve_begin(bf_ctx* ctx, const bf_tolerances* tol);
+int bf_evolve_end(bf_ctx* ctx, bf_step_out* out);
+
 /* Multi-GPU: beams are sharded across contexts; the only exchange is the sum of
  * the three squared norms per Newton iteration. */
 int bf_set_reducer(bf_ctx* ctx, bf_reduce_fn fn, void* user);

@@ -167,6 +167,7 @@ struct bf_ctx {
     bf_reduce_fn reducer;
     void* reducerUser;
     int outEnd; double *outW, *outTheta; /* bf_set_step_outputs */
+    int evolveOpen; bf_tolerances openTol; /* bf_evolve_begin / bf_evolve_end */
     int64_t launches;
 };
 
@@ -1626,6 +1627,21 @@ int bf_evolve(bf_ctx* c, const bf_tolerances* tol, bf_step_out* out)
     out->deltaXNorm = deltaXNorm;
     out->xNorm = XNorm;
     return status;
+}
+
+/* The two halves of bf_evolve (include/beamgpu.h): on the CPU nothing runs ahead, the second half does the work. */
+int bf_evolve_begin(bf_ctx* c, const bf_tolerances* tol)
+{
+    if (!tol || c->evolveOpen) { snprintf(c->err, sizeof c->err, "bf_evolve_begin: null argument or no bf_evolve_end yet"); return BF_ERR_INVALID; }
+    c->openTol = *tol;
+    c->evolveOpen = 1;
+    return BF_OK;
+}
+int bf_evolve_end(bf_ctx* c, bf_step_out* out)
+{
+    if (!out || !c->evolveOpen) { snprintf(c->err, sizeof c->err, "bf_evolve_end without bf_evolve_begin"); return BF_ERR_INVALID; }
+    c->evolveOpen = 0;
+    return bf_evolve(c, &c->openTol, out);
 }
 
 /* ---- test-only accessors (not part of beamgpu.h) -------------------------- */

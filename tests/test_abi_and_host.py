@@ -129,3 +129,37 @@ def test_field_roundtrip_and_ordering(oracle_lib):
         np.testing.assert_array_equal(I, I2)
         np.testing.assert_array_equal(lft, l2)
         np.testing.assert_array_equal(rgt, r2)
+
+
+def run_two_halves(model, nSteps):
+    """The time loop of a host that evaluates the next time level's BC series while the solve of the open one runs:
+    uploadPrepared / evolveBegin / updateCoeffs(t + dt, prepareOnly) / evolveEnd."""
+    iters = []
+    while len(iters) < nSteps and model.loop():
+        if model._bcPrepared:
+            model.uploadPrepared()
+        else:
+            model.updateCoeffs(model.time)
+        model.evolveBegin()
+        model.updateCoeffs((model.timeIndex + 1) * model.case.deltaT, prepareOnly=True)  # the time loop() will set
+        model.evolveEnd()
+        iters.append(model.iOuterCorr())
+    return iters
+
+
+def test_evolve_in_two_halves_is_evolve(oracle_lib):
+    """bf_evolve_begin + bf_evolve_end = bf_evolve, result for result (time-dependent follower load, Evolve.C:156-157)."""
+    case = cases.cantileverFollowerForce()
+    a = coupledTotalLagNewtonRaphsonBeam(case, library=oracle_lib)
+    b = coupledTotalLagNewtonRaphsonBeam(case, library=oracle_lib)
+    assert a.run(nSteps=12) == run_two_halves(b, 12)
+    for x, y in zip(a.tip(1), b.tip(1)):
+        assert np.array_equal(x, y)
+    # the halves come in pairs
+    out = L.bf_step_out()
+    assert oracle_lib.bf_evolve_end(b._ctx, C.byref(out)) == L.BF_ERR_INVALID
+    assert oracle_lib.bf_evolve_begin(b._ctx, C.byref(b.tol)) == L.BF_OK
+    assert oracle_lib.bf_evolve_begin(b._ctx, C.byref(b.tol)) == L.BF_ERR_INVALID
+    assert oracle_lib.bf_evolve_end(b._ctx, C.byref(out)) in (L.BF_OK, L.BF_MAXITER, L.BF_DIVERGED)
+    a.close()
+    b.close()

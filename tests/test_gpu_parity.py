@@ -187,3 +187,28 @@ def test_euler_scheme(gpu_lib, oracle_lib):
     for f in ("U", "Accl", "Omega"):
         a, b = g.get_field(f)[0], o.get_field(f)[0]
         assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-3), f
+
+
+@pytest.mark.parametrize("name", ["cantileverFollowerForce", "multiBeamDensity"])
+def test_evolve_in_two_halves_is_evolve_on_the_gpu(gpu_lib, name):
+    """bf_evolve_begin / bf_evolve_end with the next level's BC values prepared in between: same iteration counts and
+    bit-identical tips as bf_evolve; calls that would queue work behind the open loop are refused."""
+    import ctypes as C
+    from beamfoam_b200 import _lib as L
+    from test_abi_and_host import run_two_halves
+    case = cases.cantileverFollowerForce() if name == "cantileverFollowerForce" else cases.multiBeamDensity(70, 37, jitter=True)
+    a = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
+    b = coupledTotalLagNewtonRaphsonBeam(case, library=gpu_lib)
+    assert a.run(nSteps=15) == run_two_halves(b, 15)
+    for x, y in zip(a.tip(1), b.tip(1)):
+        assert np.array_equal(x, y)
+    assert gpu_lib.bf_evolve_begin(b._ctx, C.byref(b.tol)) == L.BF_OK
+    s = (C.c_double * 3)()
+    assert gpu_lib.bf_newton_iteration(b._ctx, s) == L.BF_ERR_INVALID
+    assert gpu_lib.bf_begin_step(b._ctx, 1.0) == L.BF_ERR_INVALID
+    assert gpu_lib.bf_evolve_begin(b._ctx, C.byref(b.tol)) == L.BF_ERR_INVALID
+    out = L.bf_step_out()
+    gpu_lib.bf_evolve_end(b._ctx, C.byref(out))
+    assert gpu_lib.bf_evolve_end(b._ctx, C.byref(out)) == L.BF_ERR_INVALID
+    a.close()
+    b.close()
