@@ -962,6 +962,7 @@ static int xferPatch(bf_ctx* c, double* dev, double* host, int nc, int end, int 
 
 extern "C" int bf_set_field(bf_ctx* c, int32_t field, const double* internal, const double* left, const double* right)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_set_field between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     CUDA_OK(c, cudaSetDevice(c->device));
     double *dev, *endArr; int nc, surf, kind;
     int rc = fieldInfo(c, field, &dev, &endArr, &nc, &surf, &kind);
@@ -986,6 +987,7 @@ extern "C" int bf_set_field(bf_ctx* c, int32_t field, const double* internal, co
 
 extern "C" int bf_get_field(bf_ctx* c, int32_t field, double* internal, double* left, double* right)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_get_field between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     CUDA_OK(c, cudaSetDevice(c->device));
     double *dev, *endArr; int nc, surf, kind;
     int rc = fieldInfo(c, field, &dev, &endArr, &nc, &surf, &kind);
@@ -1010,6 +1012,7 @@ extern "C" int bf_get_field(bf_ctx* c, int32_t field, double* internal, double* 
 // step k+1.  bf_mirror_wait() (or the next bf_mirror_begin) waits for the copies.
 extern "C" int bf_mirror_begin(bf_ctx* c, int32_t nFields, const int32_t* fields, double* const* hostInternal)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_mirror_begin between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     if (nFields < 1 || !fields || !hostInternal) return fail(c, BF_ERR_INVALID, "bf_mirror_begin: bad argument");
     CUDA_OK(c, cudaSetDevice(c->device));
     if (c->copyPending) { // the staging regions are about to be overwritten
@@ -1050,6 +1053,7 @@ extern "C" int bf_mirror_wait(bf_ctx* c)
 
 extern "C" int bf_set_distributed_loads(bf_ctx* c, const double* q, const double* m)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_set_distributed_loads between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     CUDA_OK(c, cudaSetDevice(c->device));
     const double* src[2] = {q, m};
     double** dst[2] = {&c->d_q, &c->d_m};
@@ -1071,6 +1075,7 @@ extern "C" int bf_set_distributed_loads(bf_ctx* c, const double* q, const double
 // sum F0 and sum zeta*F0 for each side of the cell (the lever arm is zeta times a per-side vector): 9 doubles.
 extern "C" int bf_set_point_forces(bf_ctx* c, int64_t n, const int64_t* cell, const double* zeta, const double* force)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_set_point_forces between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     if (n < 0 || (n > 0 && (!cell || !zeta || !force))) return fail(c, BF_ERR_INVALID, "bf_set_point_forces: bad argument");
     CUDA_OK(c, cudaSetDevice(c->device));
     if (n == 0) { c->hasPf = false; return BF_OK; }
@@ -1099,6 +1104,7 @@ extern "C" int bf_set_point_forces(bf_ctx* c, int64_t n, const int64_t* cell, co
 extern "C" int bf_set_momentum_contributions(bf_ctx* c, int32_t n, const bf_momentum_contribution* list, const double* radius,
                                              const double* translation)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_set_momentum_contributions between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     if (n < 0 || n > BF_MAX_CONTRIBUTIONS || (n > 0 && (!list || !radius))) return fail(c, BF_ERR_INVALID, "bf_set_momentum_contributions: bad argument");
     for (int i = 0; i < n; i++) {
         if (list[i].type != BF_CONTRIB_MORISON_DRAG && list[i].type != BF_CONTRIB_GROUND_CONTACT)
@@ -1194,6 +1200,7 @@ static int setBcValues(bf_ctx* c, int32_t end, int32_t kind, const double* v, bo
 // step): two gathers, two copies, one wait.
 extern "C" int bf_get_patch_pair(bf_ctx* c, int32_t end, double* W, double* Theta)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_get_patch_pair between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     if ((end != BF_END_LEFT && end != BF_END_RIGHT) || !W || !Theta) return fail(c, BF_ERR_INVALID, "bf_get_patch_pair: bad argument");
     CUDA_OK(c, cudaSetDevice(c->device));
     const unsigned grid = (unsigned)((c->B + 255) / 256);
@@ -1262,6 +1269,7 @@ extern "C" int bf_region_elapsed_ms(bf_ctx* c, double* ms)
 // functionObjects/beamEnergyData: per-beam energies from the device state (no field leaves the device)
 extern "C" int bf_beam_energy(bf_ctx* c, double* out)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_beam_energy between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     if (!out) return fail(c, BF_ERR_INVALID, "bf_beam_energy: null argument");
     CUDA_OK(c, cudaSetDevice(c->device));
     if (int rc = drainMirror(c)) return rc;
@@ -1547,6 +1555,7 @@ extern "C" int bf_newton_iteration(bf_ctx* c, double sumsq[3])
 // ---- coupled bundles: bf_set_couplings, the BiCGStab loop (myBlockBiCGStabSolver.C:79-189) ---------------------------------
 extern "C" int bf_set_couplings(bf_ctx* c, int64_t nPairs, const int64_t* cellA, const int64_t* cellB, const double* stiffness)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_set_couplings between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     if (nPairs < 0 || (nPairs > 0 && (!cellA || !cellB || !stiffness))) return fail(c, BF_ERR_INVALID, "bf_set_couplings: bad argument");
     CUDA_OK(c, cudaSetDevice(c->device));
     c->nPairs = 0;
@@ -1695,6 +1704,7 @@ __global__ void linearResidualKernel(const __grid_constant__ BeamParams p, const
 }
 extern "C" int bf_newton_iteration_checked(bf_ctx* c, double sumsq[3], double* backwardError)
 {
+    if (c->pipe.active) return fail(c, BF_ERR_INVALID, "bf_newton_iteration_checked between bf_evolve_begin and bf_evolve_end: the Newton loop of the open step is still running");
     if (!backwardError) return fail(c, BF_ERR_INVALID, "bf_newton_iteration_checked: null argument");
     if (!c->storeInc) return fail(c, BF_ERR_INVALID, "bf_newton_iteration_checked needs storeIncrements (the solution of the linear solve)");
     CUDA_OK(c, cudaSetDevice(c->device));

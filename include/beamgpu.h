@@ -337,7 +337,8 @@ int bf_evolve(bf_ctx* ctx, const bf_tolerances* tol, bf_step_out* out);
  * busy: bf_evolve_begin enqueues the Newton loop of the open time step and returns at once, bf_evolve_end waits for it,
  * evaluates checkConvergence on its norms exactly as bf_evolve does (running further iterations if the loop was not over)
  * and fills `out`; the pair is bf_evolve, result for result.  Between the two calls the context accepts no call that would
- * queue work behind the loop (bf_begin_step, bf_set_bc_values*, bf_newton_iteration, bf_evolve return BF_ERR_INVALID): hand
+ * queue work behind the loop (bf_begin_step, bf_set_bc_values*, bf_set_field / bf_get_field, bf_mirror_begin, bf_get_patch_pair,
+ * the load setters, bf_newton_iteration, bf_evolve ... return BF_ERR_INVALID): hand
  * the prepared values over after bf_evolve_end.  Where the loop needs the host in every iteration (a reducer callback,
  * NCCL without peer memory, the cell-parallel path) bf_evolve_begin only records the request and bf_evolve_end does the work. */
 int bf_evolve_begin(bf_ctx* ctx, const bf_tolerances* tol);

@@ -206,6 +206,8 @@ def test_evolve_in_two_halves_is_evolve_on_the_gpu(gpu_lib, name):
     s = (C.c_double * 3)()
     assert gpu_lib.bf_newton_iteration(b._ctx, s) == L.BF_ERR_INVALID
     assert gpu_lib.bf_begin_step(b._ctx, 1.0) == L.BF_ERR_INVALID
+    buf = np.zeros((b._B, 3))
+    assert gpu_lib.bf_get_patch_pair(b._ctx, 1, buf.ctypes.data, buf.ctypes.data) == L.BF_ERR_INVALID
     assert gpu_lib.bf_evolve_begin(b._ctx, C.byref(b.tol)) == L.BF_ERR_INVALID
     out = L.bf_step_out()
     gpu_lib.bf_evolve_end(b._ctx, C.byref(out))
