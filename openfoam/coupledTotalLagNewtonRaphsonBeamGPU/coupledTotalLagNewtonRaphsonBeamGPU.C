@@ -133,7 +133,7 @@ void coupledTotalLagNewtonRaphsonBeamGPU::pushBoundaryValues()
 
     for (label end = 0; end < 2; end++)
     {
-        List<scalar> w(3*nBeams(), 0.0), th(3*nBeams(), 0.0), F(3*nBeams(), 0.0), M(3*nBeams(), 0.0);
+        double *w = bcStage_[end][0], *th = bcStage_[end][1], *F = bcStage_[end][2], *M = bcStage_[end][3];
         for (label b = 0; b < nBeams(); b++)
         {
             const label patchI = end ? endPatchIndex(b) : startPatchIndex(b);
@@ -167,10 +167,11 @@ void coupledTotalLagNewtonRaphsonBeamGPU::pushBoundaryValues()
                 w[3*b + k] = pW[fI][k]; th[3*b + k] = pT[fI][k]; F[3*b + k] = f[k]; M[3*b + k] = m[k];
             }
         }
-        check(bf_set_bc_values(ctx_, end, BF_BCV_W, w.cdata()), "bf_set_bc_values");
-        check(bf_set_bc_values(ctx_, end, BF_BCV_THETA, th.cdata()), "bf_set_bc_values");
-        check(bf_set_bc_values(ctx_, end, BF_BCV_FORCE, F.cdata()), "bf_set_bc_values");
-        check(bf_set_bc_values(ctx_, end, BF_BCV_MOMENT, M.cdata()), "bf_set_bc_values");
+        // the staging arrays are page-locked and refilled only at the next time step, after evolve() has returned
+        check(bf_set_bc_values_async(ctx_, end, BF_BCV_W, w), "bf_set_bc_values_async");
+        check(bf_set_bc_values_async(ctx_, end, BF_BCV_THETA, th), "bf_set_bc_values_async");
+        check(bf_set_bc_values_async(ctx_, end, BF_BCV_FORCE, F), "bf_set_bc_values_async");
+        check(bf_set_bc_values_async(ctx_, end, BF_BCV_MOMENT, M), "bf_set_bc_values_async");
     }
 }
 
@@ -183,6 +184,7 @@ coupledTotalLagNewtonRaphsonBeamGPU::coupledTotalLagNewtonRaphsonBeamGPU(Time& r
     nSeg_(nBeams(), 0),
     uploaded_(false)
 {
+    for (label end = 0; end < 2; end++) for (label k = 0; k < 4; k++) bcStage_[end][k] = nullptr;
     const label B = nBeams();
     List<int32_t> nSeg(B), wType(2*B), thType(2*B);
     List<scalar> length(B), CQ(3*B), CM(3*B), ARho(B), CIRho(3*B), weight(3*B), refL(9*B), sk(2*B, 0.0), sd(6*B, 0.0);
@@ -242,6 +244,15 @@ coupledTotalLagNewtonRaphsonBeamGPU::coupledTotalLagNewtonRaphsonBeamGPU(Time& r
         FatalErrorInFunction << "bf_create: " << bf_last_error(nullptr) << abort(FatalError);
     }
     if (Pstream::parRun()) { check(bf_set_reducer(ctx_, &reduceNorms, nullptr), "bf_set_reducer"); }
+    for (label end = 0; end < 2; end++)
+    {
+        for (label k = 0; k < 4; k++)
+        {
+            void* ptr = nullptr;
+            check(bf_host_alloc(&ptr, sizeof(double)*3*nBeams()), "bf_host_alloc");
+            bcStage_[end][k] = static_cast<double*>(ptr);
+        }
+    }
     check(bf_set_distributed_loads
     (
         ctx_,
@@ -306,6 +317,13 @@ coupledTotalLagNewtonRaphsonBeamGPU::coupledTotalLagNewtonRaphsonBeamGPU(Time& r
 coupledTotalLagNewtonRaphsonBeamGPU::~coupledTotalLagNewtonRaphsonBeamGPU()
 {
     bf_destroy(ctx_);
+    for (label end = 0; end < 2; end++)
+    {
+        for (label k = 0; k < 4; k++)
+        {
+            if (bcStage_[end][k]) bf_host_free(bcStage_[end][k]);
+        }
+    }
 }
 
 // * * * * * * * * * * * * * * * Member Functions  * * * * * * * * * * * * * //
